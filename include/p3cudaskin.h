@@ -1,0 +1,299 @@
+/*
+ * p3cudaskin.h -- C-ABI of libp3cudaskin.so, the B200 (sm_100a) backend for
+ * Panda3D's CPU vertex-animation hot path.
+ *
+ * This is the drop-in boundary.  Everything here is
+ * extern "C", plain-old-data, pointers and sizes; no C++/torch types cross it.
+ * Every entry point cites the reference interface it replaces (paths are
+ * relative to the Panda3D source tree, v1.11.0).
+ *
+ * The reference has no plugin API at this point of the engine; the de-facto
+ * boundary is
+ *     CPT(GeomVertexData) GeomVertexData::animate_vertices(bool force, Thread *)
+ *         panda/src/gobj/geomVertexData.h:160, geomVertexData.cxx:912-975
+ *     void GeomVertexData::update_animated_vertices(CData *, Thread *)
+ *         panda/src/gobj/geomVertexData.cxx:1433-1752
+ * A Panda-side shim flattens GeomVertexData /
+ * TransformBlendTable / SliderTable into the descriptors below and calls
+ * these functions in place of the CPU loops.  The library is loaded the way
+ * Panda loads its other plugins (load_dso + a well-known C symbol, cf.
+ * panda/src/audio/audioManager.cxx:63-104): the well-known symbol is
+ * p3cs_get_api().
+ *
+ * Conventions (identical to the reference):
+ *   - matrices are LMatrix4f: row-major 16 x float32, row vectors, v' = v * M,
+ *     translation in row 3 (panda/src/linmath/lmatrix4_src.I:743-745);
+ *   - numeric_type / contents use the integer values of GeomEnums::NumericType
+ *     and GeomEnums::Contents (panda/src/gobj/geomEnums.h:177-212);
+ *   - row ranges are SparseArray subranges [begin, end)
+ *     (panda/src/putil/sparseArray.h:43-163);
+ *   - all functions return 0 (P3CS_OK) or a p3cs_status error code; the text
+ *     of the last error of the calling thread is p3cs_last_error().  There is
+ *     NO CPU fallback: without a usable CUDA device every compute entry point
+ *     fails with P3CS_ERR_NO_DEVICE / P3CS_ERR_CUDA.
+ */
+#ifndef P3CUDASKIN_H
+#define P3CUDASKIN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define P3CS_EXPORT __declspec(dllexport)
+#else
+#define P3CS_EXPORT __attribute__((visibility("default")))
+#endif
+
+#define P3CS_API_VERSION 1
+
+typedef enum p3cs_status {
+  P3CS_OK = 0,
+  P3CS_ERR_INVALID = 1,      /* bad argument / inconsistent descriptor          */
+  P3CS_ERR_UNSUPPORTED = 2,  /* legal in Panda but not handled by this backend   */
+  P3CS_ERR_CUDA = 3,         /* a CUDA runtime call failed                       */
+  P3CS_ERR_NOMEM = 4,        /* host or device allocation failed                 */
+  P3CS_ERR_NO_DEVICE = 5     /* no CUDA device (there is no CPU fallback)        */
+} p3cs_status;
+
+/* GeomEnums::NumericType, panda/src/gobj/geomEnums.h:177-190 */
+enum {
+  P3CS_NT_UINT8 = 0, P3CS_NT_UINT16 = 1, P3CS_NT_UINT32 = 2,
+  P3CS_NT_PACKED_DCBA = 3, P3CS_NT_PACKED_DABC = 4,
+  P3CS_NT_FLOAT32 = 5, P3CS_NT_FLOAT64 = 6, P3CS_NT_STDFLOAT = 7,
+  P3CS_NT_INT8 = 8, P3CS_NT_INT16 = 9, P3CS_NT_INT32 = 10, P3CS_NT_PACKED_UFLOAT = 11
+};
+
+/* GeomEnums::Contents, panda/src/gobj/geomEnums.h:195-212 */
+enum {
+  P3CS_C_OTHER = 0, P3CS_C_POINT = 1, P3CS_C_CLIP_POINT = 2, P3CS_C_VECTOR = 3,
+  P3CS_C_TEXCOORD = 4, P3CS_C_COLOR = 5, P3CS_C_INDEX = 6, P3CS_C_MORPH_DELTA = 7,
+  P3CS_C_MATRIX = 8, P3CS_C_NORMAL = 9
+};
+
+/* CoordinateSystem, panda/src/linmath/coordinateSystem.h (PRC `coordinate-system`);
+ * selects the hpr convention of decompose_matrix/compose_matrix used for
+ * normals under a uniform scale (geomVertexData.cxx:1825-1827). */
+enum {
+  P3CS_CS_ZUP_RIGHT = 1, P3CS_CS_YUP_RIGHT = 2, P3CS_CS_ZUP_LEFT = 3, P3CS_CS_YUP_LEFT = 4
+};
+
+typedef struct p3cs_context_s *p3cs_context;  /* one CUDA device + stream            */
+typedef struct p3cs_mesh_s *p3cs_mesh;        /* static, shared data of a vertex data */
+typedef struct p3cs_group_s *p3cs_group;      /* n animated instances of one mesh     */
+
+/* One GeomVertexArrayData of the SOURCE GeomVertexData
+ * (panda/src/gobj/geomVertexArrayData.h; bytes = get_read_pointer(true)). */
+typedef struct p3cs_array_desc {
+  const void *data;    /* host pointer, num_rows * stride bytes; not retained     */
+  int32_t stride;      /* GeomVertexArrayFormat::get_stride()                     */
+  int32_t is_output;   /* 1 if the array survives get_post_animated_format()
+                          (geomVertexFormat.cxx:106-135): such arrays are copied
+                          row for row (copy_from, geomVertexData.cxx:1460) and
+                          then modified in place; 0 for arrays that hold only the
+                          transform_blend / morph-delta columns                   */
+} p3cs_array_desc;
+
+/* One GeomVertexColumn (panda/src/gobj/geomVertexColumn.h). */
+typedef struct p3cs_column_desc {
+  int32_t array;         /* index into p3cs_mesh_desc::arrays                     */
+  int32_t start;         /* GeomVertexColumn::get_start(), bytes into the row     */
+  int32_t num_values;    /* get_num_values()                                      */
+  int32_t numeric_type;  /* get_numeric_type(), P3CS_NT_*                          */
+  int32_t contents;      /* get_contents(), P3CS_C_*                               */
+} p3cs_column_desc;
+
+/* One application of a morph: a (C_morph_delta column, slider) pair with the
+ * slider's affected rows, in the iteration order of the reference loop
+ * geomVertexData.cxx:1467-1543 (morph column outer, slider index inner). */
+typedef struct p3cs_morph_desc {
+  int32_t slider;               /* index into the SliderTable (sliderTable.I:52)  */
+  p3cs_column_desc base;        /* column that is modified (array must be output) */
+  p3cs_column_desc delta;       /* C_morph_delta column read from the source      */
+  int32_t num_row_ranges;       /* SliderTable::get_slider_rows(slider)           */
+  const int32_t *row_ranges;    /* 2*num_row_ranges ints: begin,end pairs         */
+} p3cs_morph_desc;
+
+/* Flattened static description of one animated GeomVertexData. */
+typedef struct p3cs_mesh_desc {
+  uint32_t struct_size;         /* sizeof(p3cs_mesh_desc), for versioning         */
+  int32_t num_rows;             /* GeomVertexData::get_num_rows()                 */
+  int32_t coordinate_system;    /* P3CS_CS_*; 0 = P3CS_CS_ZUP_RIGHT               */
+
+  int32_t num_arrays;
+  const p3cs_array_desc *arrays;
+
+  /* Columns transformed by the blend matrices: GeomVertexFormat::get_point(i)
+   * then get_vector(i) of the post-animated format (geomVertexData.cxx:1582,
+   * 1622).  contents is C_POINT, C_VECTOR or C_NORMAL; float32 x 3 or x 4. */
+  int32_t num_skin_columns;
+  const p3cs_column_desc *skin_columns;
+
+  /* The `transform_blend` index column (InternalName::get_transform_blend());
+   * any of uint8/uint16/uint32, any stride (geomVertexData.cxx:1574-1750).
+   * array < 0 when the vertex data has no TransformBlendTable. */
+  p3cs_column_desc blend_column;
+
+  /* TransformBlendTable (transformBlendTable.h:45-157) as CSR.  Entries of a
+   * blend are listed in stored order (TransformBlend::get_transform(i),
+   * i = 0..n-1), which is the accumulation order of
+   * TransformBlend::recompute_result (transformBlend.cxx:228-231). */
+  int32_t num_transforms;           /* palette size T (rebuild_index order)       */
+  int32_t num_blends;
+  const int32_t *blend_offsets;     /* num_blends + 1                             */
+  const int32_t *blend_transform;   /* palette index per entry                    */
+  const float *blend_weight;        /* TransformBlend::get_weight(i)              */
+
+  /* TransformBlendTable::get_rows() (transformBlendTable.I:82-104). */
+  int32_t num_row_ranges;
+  const int32_t *row_ranges;        /* 2*num_row_ranges ints                      */
+
+  /* SliderTable (sliderTable.h) + GeomVertexFormat morph records. */
+  int32_t num_sliders;              /* S = SliderTable::get_num_sliders()         */
+  int32_t num_morphs;
+  const p3cs_morph_desc *morphs;
+} p3cs_mesh_desc;
+
+/* Optional caller-owned device buffers for a group (all may be NULL => the
+ * library allocates).  Lets the host keep palettes/outputs in buffers it
+ * shares with a renderer or registers with NCCL. */
+typedef struct p3cs_group_buffers {
+  void *palettes;          /* device, n * T * 64 bytes                            */
+  void *sliders;           /* device, n * S * 4 bytes                             */
+  void *const *outputs;    /* num output arrays device pointers, each
+                              n * p3cs_group_output_pitch() bytes                 */
+} p3cs_group_buffers;
+
+/* Timings of the last p3cs_group_animate (CUDA events on the context stream). */
+typedef struct p3cs_timings {
+  float blend_ms;    /* K1: blend-matrix + normal-matrix build                    */
+  float skin_ms;     /* K2: morph + skin + row write                              */
+  float total_ms;
+  int32_t launches;  /* kernels launched by the call                              */
+} p3cs_timings;
+
+/* ---- library ---------------------------------------------------------- */
+
+/* Version of this header the library was built against. */
+P3CS_EXPORT int p3cs_api_version(void);
+/* Number of CUDA devices visible (0 if none / no driver). */
+P3CS_EXPORT int p3cs_device_count(void);
+/* Text of the calling thread's last error ("" if none).  Mirrors the
+ * reference's convention of logging through a NotifyCategory and returning
+ * early (geomVertexData.cxx:1565-1570); the shim forwards this text to
+ * gobj_cat.error(). */
+P3CS_EXPORT const char *p3cs_last_error(void);
+
+/* ---- context ---------------------------------------------------------- */
+
+/* Binds a CUDA device and creates (or adopts) the stream all work of the
+ * context is ordered on.  One context per calling (cull) thread keeps the
+ * path re-entrant across meshes (SURVEY.md 8b "Threading"). `stream` may be
+ * NULL (the library creates a non-blocking stream) or a cudaStream_t. */
+P3CS_EXPORT int p3cs_context_create(int device, void *stream, p3cs_context *out);
+P3CS_EXPORT int p3cs_context_destroy(p3cs_context ctx);
+/* Blocks until all work queued on the context stream is done. */
+P3CS_EXPORT int p3cs_context_sync(p3cs_context ctx);
+/* The cudaStream_t of the context (for CUDA-event timing by the caller). */
+P3CS_EXPORT void *p3cs_context_stream(p3cs_context ctx);
+
+/* ---- mesh: the static half of a GeomVertexData -------------------------- */
+
+/* Uploads arrays, the transform_blend index column, the blend CSR, the rows
+ * mask and the sparse morph deltas to HBM.  Replaces the per-frame
+ * new_data->copy_from(this, true) of geomVertexData.cxx:1460 by a one-time
+ * upload; call again (destroy + create) when GeomVertexArrayData /
+ * TransformBlendTable get_modified() changes. Host pointers are not retained. */
+P3CS_EXPORT int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *desc, p3cs_mesh *out);
+P3CS_EXPORT int p3cs_mesh_destroy(p3cs_mesh mesh);
+/* Number of output arrays (arrays with is_output) and their geometry. */
+P3CS_EXPORT int p3cs_mesh_num_outputs(p3cs_mesh mesh);
+P3CS_EXPORT int p3cs_mesh_output_stride(p3cs_mesh mesh, int output);
+P3CS_EXPORT int p3cs_mesh_num_rows(p3cs_mesh mesh);
+
+/* ---- group: n animated instances of a mesh ----------------------------- */
+
+/* A group is n independent instances (a crowd of Characters sharing one
+ * GeomVertexData); n = 1 is the plain Actor case.  Each instance has its own
+ * palette (T joint matrices = JointVertexTransform::get_matrix in palette
+ * order, char/jointVertexTransform.cxx:56-60), its own slider values and its
+ * own output arrays (the `_animated_vertices` of geomVertexData.h:313). */
+P3CS_EXPORT int p3cs_group_create(p3cs_mesh mesh, int num_instances,
+                                  const p3cs_group_buffers *buffers, p3cs_group *out);
+P3CS_EXPORT int p3cs_group_destroy(p3cs_group group);
+
+/* Bytes between consecutive instances in output array `output`
+ * (num_rows * stride rounded up to 256). */
+P3CS_EXPORT size_t p3cs_group_output_pitch(p3cs_group group, int output);
+/* Device pointers (valid until the group is destroyed). */
+P3CS_EXPORT void *p3cs_group_palettes_device(p3cs_group group);
+P3CS_EXPORT void *p3cs_group_sliders_device(p3cs_group group);
+P3CS_EXPORT void *p3cs_group_output_device(p3cs_group group, int output);
+
+/* Host -> device: `count` palettes starting at instance `first`;
+ * host_matrices = count * T * 16 floats (UserVertexTransform::set_matrix /
+ * CharacterJoint::_skinning_matrix values).  Asynchronous on the context
+ * stream when the host memory is pinned. */
+P3CS_EXPORT int p3cs_group_set_palettes(p3cs_group group, int first, int count,
+                                        const float *host_matrices);
+/* Host -> device slider values, count * S floats (VertexSlider::get_slider). */
+P3CS_EXPORT int p3cs_group_set_sliders(p3cs_group group, int first, int count,
+                                       const float *host_values);
+
+/* The hot path: recomputes every blend (update_blend, geomVertexData.cxx:
+ * 1550-1556), applies morphs (1462-1543) and skins every point / vector /
+ * normal column (1558-1751) of all instances.  Asynchronous. */
+P3CS_EXPORT int p3cs_group_animate(p3cs_group group);
+
+/* Device -> host copy of `count` instances of one output array into
+ * host_dst (count * num_rows * stride bytes, tightly packed = the byte image
+ * of the animated GeomVertexArrayData).  Asynchronous when pinned;
+ * follow with p3cs_context_sync. */
+P3CS_EXPORT int p3cs_group_read_output(p3cs_group group, int output, int first, int count,
+                                       void *host_dst);
+/* Per-vertex selected blend index as the kernel saw it (int32 per row, -1 for
+ * rows outside TransformBlendTable::get_rows()); parity hook for the
+ * bit-exact blend-index / row-selection requirement. */
+P3CS_EXPORT int p3cs_group_read_selection(p3cs_group group, int32_t *host_dst);
+/* Blended matrices of one instance as computed by K1: num_blends * 16 floats
+ * (TransformBlend::get_blend results); parity hook. */
+P3CS_EXPORT int p3cs_group_read_blends(p3cs_group group, int instance, float *host_dst);
+
+P3CS_EXPORT int p3cs_group_last_timings(p3cs_group group, p3cs_timings *out);
+
+/* One-call equivalent of GeomVertexData::animate_vertices(force=true) for a
+ * single instance with HOST buffers: palette in, sliders in, animated arrays
+ * out (host_outputs[i] receives output array i), synchronous. */
+P3CS_EXPORT int p3cs_animate_vertices(p3cs_group group, int instance,
+                                      const float *host_palette, const float *host_sliders,
+                                      void *const *host_outputs);
+
+/* ---- plugin table (load_dso + dlsym("p3cs_get_api")) -------------------- */
+
+typedef struct p3cs_api {
+  int version;
+  int (*device_count)(void);
+  const char *(*last_error)(void);
+  int (*context_create)(int, void *, p3cs_context *);
+  int (*context_destroy)(p3cs_context);
+  int (*context_sync)(p3cs_context);
+  int (*mesh_create)(p3cs_context, const p3cs_mesh_desc *, p3cs_mesh *);
+  int (*mesh_destroy)(p3cs_mesh);
+  int (*group_create)(p3cs_mesh, int, const p3cs_group_buffers *, p3cs_group *);
+  int (*group_destroy)(p3cs_group);
+  int (*group_set_palettes)(p3cs_group, int, int, const float *);
+  int (*group_set_sliders)(p3cs_group, int, int, const float *);
+  int (*group_animate)(p3cs_group);
+  int (*group_read_output)(p3cs_group, int, int, int, void *);
+  int (*animate_vertices)(p3cs_group, int, const float *, const float *, void *const *);
+} p3cs_api;
+
+P3CS_EXPORT const p3cs_api *p3cs_get_api(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P3CUDASKIN_H */

@@ -1,0 +1,185 @@
+"""TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes wrapper of oracle/libskin_oracle.so (oracle/skin_oracle.c), the plain-C
+restatement of the reference's CPU vertex animation.  Imported only by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libskin_oracle.so")
+_lib = None
+
+
+class _Column(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("array", "start", "num_values", "numeric_type", "contents")]
+
+
+class _Morph(C.Structure):
+    _fields_ = [("slider", C.c_int32), ("base", _Column), ("delta", _Column),
+                ("num_row_ranges", C.c_int32), ("row_ranges", C.POINTER(C.c_int32))]
+
+
+class _Mesh(C.Structure):
+    _fields_ = [
+        ("num_rows", C.c_int32), ("coordinate_system", C.c_int32), ("num_arrays", C.c_int32),
+        ("array_data", C.POINTER(C.c_void_p)), ("array_stride", C.POINTER(C.c_int32)),
+        ("array_is_output", C.POINTER(C.c_int32)),
+        ("num_skin_columns", C.c_int32), ("skin_columns", C.POINTER(_Column)),
+        ("blend_column", _Column),
+        ("num_transforms", C.c_int32), ("num_blends", C.c_int32),
+        ("blend_offsets", C.POINTER(C.c_int32)), ("blend_transform", C.POINTER(C.c_int32)),
+        ("blend_weight", C.POINTER(C.c_float)),
+        ("num_row_ranges", C.c_int32), ("row_ranges", C.POINTER(C.c_int32)),
+        ("num_sliders", C.c_int32), ("num_morphs", C.c_int32), ("morphs", C.POINTER(_Morph)),
+    ]
+
+
+def build(force: bool = False) -> str:
+    """Compiles the oracle (gcc, oracle/Makefile).  Building the checker is not using it."""
+    src = os.path.join(_HERE, "skin_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "libskin_oracle.so"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.p3o_animate.restype = C.c_int
+        _lib.p3o_normal_xform.restype = C.c_int
+        _lib.p3o_invert4.restype = C.c_int
+        _lib.p3o_invert3.restype = C.c_int
+        _lib.p3o_decompose3.restype = C.c_int
+    return _lib
+
+
+def _col(c) -> _Column:
+    return _Column(*c.as_tuple()) if c is not None else _Column(-1, 0, 0, 0, 0)
+
+
+def _ip(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class OracleMesh:
+    """Keeps the ctypes view of a FlatMesh alive."""
+
+    def __init__(self, mesh):
+        self.mesh = mesh
+        self._keep = []
+        m = _Mesh()
+        m.num_rows = mesh.num_rows
+        m.coordinate_system = mesh.coordinate_system
+        na = len(mesh.arrays)
+        m.num_arrays = na
+        self._arrays = [np.ascontiguousarray(a) for a in mesh.arrays]
+        ptrs = (C.c_void_p * na)(*[a.ctypes.data for a in self._arrays])
+        strides = np.asarray(mesh.strides, np.int32)
+        is_out = np.asarray([1 if o else 0 for o in mesh.is_output], np.int32)
+        cols = (_Column * max(1, len(mesh.skin_columns)))(*[_col(c) for c in mesh.skin_columns])
+        self._keep += [ptrs, strides, is_out, cols]
+        m.array_data = C.cast(ptrs, C.POINTER(C.c_void_p))
+        m.array_stride = _ip(strides)
+        m.array_is_output = _ip(is_out)
+        m.num_skin_columns = len(mesh.skin_columns)
+        m.skin_columns = C.cast(cols, C.POINTER(_Column))
+        m.blend_column = _col(mesh.blend_column)
+        m.num_transforms = mesh.num_transforms
+        m.num_blends = mesh.num_blends
+        bo = np.ascontiguousarray(mesh.blend_offsets, np.int32)
+        bx = np.ascontiguousarray(mesh.blend_transform, np.int32)
+        bw = np.ascontiguousarray(mesh.blend_weight, np.float32)
+        rr = np.ascontiguousarray(mesh.row_ranges, np.int32).reshape(-1)
+        self._keep += [bo, bx, bw, rr]
+        m.blend_offsets, m.blend_transform = _ip(bo), _ip(bx)
+        m.blend_weight = bw.ctypes.data_as(C.POINTER(C.c_float))
+        m.num_row_ranges = rr.size // 2
+        m.row_ranges = _ip(rr)
+        m.num_sliders = mesh.num_sliders
+        morphs = (_Morph * max(1, len(mesh.morphs)))()
+        for i, mo in enumerate(mesh.morphs):
+            r = np.ascontiguousarray(mo.row_ranges, np.int32).reshape(-1)
+            self._keep.append(r)
+            morphs[i] = _Morph(mo.slider, _col(mo.base), _col(mo.delta), r.size // 2, _ip(r))
+        self._keep.append(morphs)
+        m.num_morphs = len(mesh.morphs)
+        m.morphs = C.cast(morphs, C.POINTER(_Morph))
+        self.c = m
+
+    def animate(self, palette: np.ndarray, sliders: Optional[np.ndarray] = None,
+                want_blends: bool = False, want_selection: bool = False):
+        """Returns (outputs, blends, selection): the animated output arrays
+        (uint8 [num_rows, stride] each), the blended matrices and the per-row selected blend."""
+        mesh = self.mesh
+        pal = np.ascontiguousarray(palette, np.float32).reshape(-1)
+        sl = np.ascontiguousarray(sliders if sliders is not None else np.zeros(max(1, mesh.num_sliders)), np.float32)
+        outs = [np.empty((mesh.num_rows, mesh.strides[a]), np.uint8) for a in mesh.output_arrays]
+        optrs = (C.c_void_p * max(1, len(outs)))(*[o.ctypes.data for o in outs])
+        blends = np.empty((mesh.num_blends, 16), np.float32) if want_blends else None
+        sel = np.empty(mesh.num_rows, np.int32) if want_selection else None
+        rc = lib().p3o_animate(
+            C.byref(self.c), pal.ctypes.data_as(C.c_void_p), sl.ctypes.data_as(C.c_void_p), optrs,
+            blends.ctypes.data_as(C.c_void_p) if blends is not None else None,
+            sel.ctypes.data_as(C.c_void_p) if sel is not None else None)
+        if rc != 0:
+            raise RuntimeError(f"oracle: unsupported input (rc={rc})")
+        return outs, blends, sel
+
+
+def animate(mesh, palette, sliders=None, want_blends=False, want_selection=False):
+    return OracleMesh(mesh).animate(palette, sliders, want_blends, want_selection)
+
+
+def normal_xform(mat16: np.ndarray, cs: int = 1) -> Tuple[int, np.ndarray, bool]:
+    m = np.ascontiguousarray(mat16, np.float32).reshape(16)
+    out = np.empty(16, np.float32)
+    norm = C.c_int(0)
+    branch = lib().p3o_normal_xform(m.ctypes.data_as(C.c_void_p), C.c_int(cs), out.ctypes.data_as(C.c_void_p), C.byref(norm))
+    return branch, out.reshape(4, 4), bool(norm.value)
+
+
+def invert4(mat16: np.ndarray) -> Tuple[bool, np.ndarray]:
+    m = np.ascontiguousarray(mat16, np.float32).reshape(16)
+    out = np.empty(16, np.float32)
+    ok = lib().p3o_invert4(m.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return bool(ok), out.reshape(4, 4)
+
+
+def decompose3(mat9: np.ndarray, cs: int = 1):
+    m = np.ascontiguousarray(mat9, np.float32).reshape(9)
+    scale, shear, hpr = (np.empty(3, np.float32) for _ in range(3))
+    ok = lib().p3o_decompose3(m.ctypes.data_as(C.c_void_p), C.c_int(cs), scale.ctypes.data_as(C.c_void_p),
+                              shear.ctypes.data_as(C.c_void_p), hpr.ctypes.data_as(C.c_void_p))
+    return bool(ok), scale, shear, hpr
+
+
+def compose3(scale, shear, hpr, cs: int = 1) -> np.ndarray:
+    out = np.empty(9, np.float32)
+    a = [np.ascontiguousarray(x, np.float32) for x in (scale, shear, hpr)]
+    lib().p3o_compose3(out.ctypes.data_as(C.c_void_p), a[0].ctypes.data_as(C.c_void_p),
+                       a[1].ctypes.data_as(C.c_void_p), a[2].ctypes.data_as(C.c_void_p), C.c_int(cs))
+    return out.reshape(3, 3)
+
+
+# ---- the real reference, when oracle/_ref was built here (oracle/build_ref.sh) ----
+
+REF_HARNESS = os.path.join(_HERE, "_ref", "bin", "ref_harness")
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_HARNESS)
+
+
+def ref_run(recipe_path: str, golden_path: str) -> None:
+    """Runs the UNMODIFIED reference's animate_vertices on a recipe (oracle/ref_harness.cxx)."""
+    subprocess.run([REF_HARNESS, "run", recipe_path, golden_path], check=True, capture_output=True)

@@ -1,0 +1,732 @@
+/*
+ * skin_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE (see skin_oracle.h).
+ *
+ * Plain-C restatement of Panda3D 1.11.0's CPU vertex animation.  Every
+ * function cites the reference lines it follows; arithmetic is written in the
+ * reference's exact operation order (scalar, non-Eigen branches) and this file
+ * must be compiled without FMA contraction or reassociation
+ * (-O2 -ffp-contract=off, no -ffast-math) so that results are bit-identical
+ * to the reference built with its default flags on x86-64
+ * (-O3 -ffast-math -fno-unsafe-math-optimizations, no FMA in the baseline ISA;
+ * dtool/CompilerFlags.cmake:17-18,143).
+ *
+ * Paths are relative to /root/reference (panda3d/panda3d v1.11.0).
+ */
+#include "skin_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* dtool/src/dtoolbase/nearly_zero.h:27-76 */
+#define NEARLY_ZERO_F 1.0e-6f
+#define IS_THRESHOLD_ZERO(v, t) ((v) < (t) && (v) > -(t))
+#define IS_THRESHOLD_EQUAL(a, b, t) (IS_THRESHOLD_ZERO((a) - (b), t))
+#define IS_NEARLY_ZERO(v) IS_THRESHOLD_ZERO(v, NEARLY_ZERO_F)
+#define IS_NEARLY_EQUAL(a, b) IS_THRESHOLD_EQUAL(a, b, NEARLY_ZERO_F)
+
+/* panda/src/linmath/mathNumbers.cxx:24-25 (double expression rounded to float) */
+static const float RAD_2_DEG_F = (float)(180.0 / 3.14159265358979323846);
+static const float DEG_2_RAD_F = (float)(3.14159265358979323846 / 180.0);
+
+#define M4(m, r, c) ((m)[(r) * 4 + (c)])
+#define M3(m, r, c) ((m)[(r) * 3 + (c)])
+
+/* TransformBlend::recompute_result, panda/src/gobj/transformBlend.cxx:226-231:
+ * result = zeros_mat; for each entry in stored order: accumulate(M_i, w_i).
+ * LMatrix4f::accumulate, panda/src/linmath/lmatrix4_src.I:1311-1336. */
+void p3o_blend(const float *palette, const int32_t *xf, const float *w, int n, float *out16) {
+  int i, k;
+  if (n == 0) {
+    /* An empty TransformBlend is never "modified" (seq stays UpdateSeq::initial,
+     * transformBlend.cxx:217-222), so its result keeps the CData constructor's
+     * value, the identity (transformBlend.I:362-366). */
+    for (k = 0; k < 16; ++k) out16[k] = (k % 5 == 0) ? 1.0f : 0.0f;
+    return;
+  }
+  for (k = 0; k < 16; ++k) out16[k] = 0.0f;
+  for (i = 0; i < n; ++i) {
+    const float *m = palette + (size_t)xf[i] * 16;
+    float weight = w[i];
+    for (k = 0; k < 16; ++k) {
+      out16[k] += m[k] * weight;
+    }
+  }
+}
+
+/* LMatrix3f::invert_from, panda/src/linmath/lmatrix3_src.I:917-965
+ * (DET2 :885, MATRIX3_DETERMINANT :886-889). */
+#define DET2(e00, e01, e10, e11) ((e00) * (e11) - (e10) * (e01))
+int p3o_invert3(const float *o, float *r) {
+  float det = (M3(o, 0, 0) * DET2(M3(o, 1, 1), M3(o, 1, 2), M3(o, 2, 1), M3(o, 2, 2))
+             - M3(o, 0, 1) * DET2(M3(o, 1, 0), M3(o, 1, 2), M3(o, 2, 0), M3(o, 2, 2))
+             + M3(o, 0, 2) * DET2(M3(o, 1, 0), M3(o, 1, 1), M3(o, 2, 0), M3(o, 2, 1)));
+  if (IS_THRESHOLD_ZERO(det, (NEARLY_ZERO_F * NEARLY_ZERO_F))) {
+    static const float ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    memcpy(r, ident, sizeof(ident));
+    return 0;
+  }
+  det = 1.0f / det;
+  M3(r, 0, 0) = det * DET2(M3(o, 1, 1), M3(o, 1, 2), M3(o, 2, 1), M3(o, 2, 2));
+  M3(r, 1, 0) = -det * DET2(M3(o, 1, 0), M3(o, 1, 2), M3(o, 2, 0), M3(o, 2, 2));
+  M3(r, 2, 0) = det * DET2(M3(o, 1, 0), M3(o, 1, 1), M3(o, 2, 0), M3(o, 2, 1));
+
+  M3(r, 0, 1) = -det * DET2(M3(o, 0, 1), M3(o, 0, 2), M3(o, 2, 1), M3(o, 2, 2));
+  M3(r, 1, 1) = det * DET2(M3(o, 0, 0), M3(o, 0, 2), M3(o, 2, 0), M3(o, 2, 2));
+  M3(r, 2, 1) = -det * DET2(M3(o, 0, 0), M3(o, 0, 1), M3(o, 2, 0), M3(o, 2, 1));
+
+  M3(r, 0, 2) = det * DET2(M3(o, 0, 1), M3(o, 0, 2), M3(o, 1, 1), M3(o, 1, 2));
+  M3(r, 1, 2) = -det * DET2(M3(o, 0, 0), M3(o, 0, 2), M3(o, 1, 0), M3(o, 1, 2));
+  M3(r, 2, 2) = det * DET2(M3(o, 0, 0), M3(o, 0, 1), M3(o, 1, 0), M3(o, 1, 1));
+  return 1;
+}
+
+/* LMatrix4f::decompose_mat, panda/src/linmath/lmatrix4_src.cxx:380-450 */
+static int lu_decompose4(float *a, int index[4]) {
+  int i, j, k;
+  float vv[4];
+  for (i = 0; i < 4; i++) {
+    float big = 0.0f;
+    for (j = 0; j < 4; j++) {
+      float temp = fabsf(M4(a, i, j));
+      if (temp > big) big = temp;
+    }
+    if (IS_THRESHOLD_ZERO(big, (NEARLY_ZERO_F * NEARLY_ZERO_F))) return 0;
+    vv[i] = 1.0f / big;
+  }
+  for (j = 0; j < 4; j++) {
+    float big;
+    int imax = -1;
+    for (i = 0; i < j; i++) {
+      float sum = M4(a, i, j);
+      for (k = 0; k < i; k++) sum -= M4(a, i, k) * M4(a, k, j);
+      M4(a, i, j) = sum;
+    }
+    big = 0.0f;
+    for (i = j; i < 4; i++) {
+      float sum = M4(a, i, j), dum;
+      for (k = 0; k < j; k++) sum -= M4(a, i, k) * M4(a, k, j);
+      M4(a, i, j) = sum;
+      dum = vv[i] * fabsf(sum);
+      if (dum >= big) {
+        big = dum;
+        imax = i;
+      }
+    }
+    if (imax < 0) return 0;
+    if (j != imax) {
+      for (k = 0; k < 4; k++) {
+        float dum = M4(a, imax, k);
+        M4(a, imax, k) = M4(a, j, k);
+        M4(a, j, k) = dum;
+      }
+      vv[imax] = vv[j];
+    }
+    index[j] = imax;
+    if (M4(a, j, j) == 0.0f) M4(a, j, j) = NEARLY_ZERO_F;
+    if (j != 4 - 1) {
+      float dum = 1.0f / M4(a, j, j);
+      for (i = j + 1; i < 4; i++) M4(a, i, j) *= dum;
+    }
+  }
+  return 1;
+}
+
+/* LMatrix4f::back_sub_mat, panda/src/linmath/lmatrix4_src.cxx:455-483 */
+static void lu_back_sub4(const float *a, const int index[4], float *inv, int row) {
+  int ii = -1, i, j;
+  for (i = 0; i < 4; i++) {
+    int ip = index[i];
+    float sum = M4(inv, row, ip);
+    M4(inv, row, ip) = M4(inv, row, i);
+    if (ii >= 0) {
+      for (j = ii; j <= i - 1; j++) sum -= M4(a, i, j) * M4(inv, row, j);
+    } else if (sum) {
+      ii = i;
+    }
+    M4(inv, row, i) = sum;
+  }
+  for (i = 4 - 1; i >= 0; i--) {
+    float sum = M4(inv, row, i);
+    for (j = i + 1; j < 4; j++) sum -= M4(a, i, j) * M4(inv, row, j);
+    M4(inv, row, i) = sum / M4(a, i, i);
+  }
+}
+
+static void ident4(float *m) {
+  memset(m, 0, 16 * sizeof(float));
+  M4(m, 0, 0) = M4(m, 1, 1) = M4(m, 2, 2) = M4(m, 3, 3) = 1.0f;
+}
+
+/* LMatrix4f::invert_from (non-Eigen), panda/src/linmath/lmatrix4_src.I:1194-1247;
+ * invert_affine_from :1263-1295.  Note: on a singular affine matrix the
+ * reference returns false and leaves `this` untouched (uninitialised `xform`
+ * at geomVertexData.cxx:1811); the oracle writes identity there and flags it. */
+int p3o_invert4(const float *o, float *r) {
+  if (IS_NEARLY_EQUAL(M4(o, 0, 3), 0.0f) && IS_NEARLY_EQUAL(M4(o, 1, 3), 0.0f) &&
+      IS_NEARLY_EQUAL(M4(o, 2, 3), 0.0f) && IS_NEARLY_EQUAL(M4(o, 3, 3), 1.0f)) {
+    float up[9], rot[9];
+    int i, j;
+    for (i = 0; i < 3; ++i)
+      for (j = 0; j < 3; ++j) M3(up, i, j) = M4(o, i, j);
+    if (!p3o_invert3(up, rot)) {
+      ident4(r);
+      return 0;
+    }
+    for (i = 0; i < 3; ++i)
+      for (j = 0; j < 3; ++j) M4(r, i, j) = M3(rot, i, j);
+    M4(r, 0, 3) = 0.0f;
+    M4(r, 1, 3) = 0.0f;
+    M4(r, 2, 3) = 0.0f;
+    M4(r, 3, 3) = 1.0f;
+    M4(r, 3, 0) = -(M4(o, 3, 0) * M4(r, 0, 0) + M4(o, 3, 1) * M4(r, 1, 0) + M4(o, 3, 2) * M4(r, 2, 0));
+    M4(r, 3, 1) = -(M4(o, 3, 0) * M4(r, 0, 1) + M4(o, 3, 1) * M4(r, 1, 1) + M4(o, 3, 2) * M4(r, 2, 1));
+    M4(r, 3, 2) = -(M4(o, 3, 0) * M4(r, 0, 2) + M4(o, 3, 1) * M4(r, 1, 2) + M4(o, 3, 2) * M4(r, 2, 2));
+    return 1;
+  } else {
+    float a[16], inv[16];
+    int index[4], row, i, j;
+    memcpy(a, o, sizeof(a));
+    if (!lu_decompose4(a, index)) {
+      ident4(r);
+      return 0;
+    }
+    ident4(inv);
+    for (row = 0; row < 4; row++) lu_back_sub4(a, index, inv, row);
+    /* transpose_from(inv) */
+    for (i = 0; i < 4; ++i)
+      for (j = 0; j < 4; ++j) M4(r, i, j) = M4(inv, j, i);
+    return 1;
+  }
+}
+
+/* LVecBase2f::normalize, panda/src/linmath/lvecBase2_src.I:274-286;
+ * operator /= multiplies by the reciprocal (:557-566). */
+static int normalize2(float *v) {
+  float l2 = v[0] * v[0] + v[1] * v[1];
+  if (l2 == 0.0f) {
+    v[0] = v[1] = 0.0f;
+    return 0;
+  } else if (!IS_THRESHOLD_EQUAL(l2, 1.0f, NEARLY_ZERO_F * NEARLY_ZERO_F)) {
+    float recip = 1.0f / sqrtf(l2);
+    v[0] *= recip;
+    v[1] *= recip;
+  }
+  return 1;
+}
+
+/* LVecBase3f::normalize, panda/src/linmath/lvecBase3_src.I:347-361 (+ /= :708-718) */
+static int normalize3(float *v) {
+  float l2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  if (l2 == 0.0f) {
+    v[0] = v[1] = v[2] = 0.0f;
+    return 0;
+  } else if (!IS_THRESHOLD_EQUAL(l2, 1.0f, (NEARLY_ZERO_F * NEARLY_ZERO_F))) {
+    float recip = 1.0f / sqrtf(l2);
+    v[0] *= recip;
+    v[1] *= recip;
+    v[2] *= recip;
+  }
+  return 1;
+}
+
+/* LMatrix3f::xform, VECTOR3_MATRIX3_PRODUCT, panda/src/linmath/lmatrix3_src.I:496-515 */
+static void xform3(const float *m, float *v) {
+  float r0 = v[0] * M3(m, 0, 0) + v[1] * M3(m, 1, 0) + v[2] * M3(m, 2, 0);
+  float r1 = v[0] * M3(m, 0, 1) + v[1] * M3(m, 1, 1) + v[2] * M3(m, 2, 1);
+  float r2 = v[0] * M3(m, 0, 2) + v[1] * M3(m, 1, 2) + v[2] * M3(m, 2, 2);
+  v[0] = r0;
+  v[1] = r1;
+  v[2] = r2;
+}
+
+/* MATRIX3_PRODUCT, panda/src/linmath/lmatrix3_src.I:662-671; res = a * b */
+static void mul3(float *res, const float *a, const float *b) {
+  int i, j;
+  for (i = 0; i < 3; ++i)
+    for (j = 0; j < 3; ++j)
+      M3(res, i, j) = M3(a, i, 0) * M3(b, 0, j) + M3(a, i, 1) * M3(b, 1, j) + M3(a, i, 2) * M3(b, 2, j);
+}
+
+/* unwind_zup_rotation, panda/src/linmath/compose_matrix_src.cxx:422-504 */
+static void unwind_zup_rotation(float *mat, float *hpr) {
+  float x[3], y[3], z[3], heading = 0, pitch = 0, roll = 0, p[2], rot[9];
+  memcpy(x, mat + 0, sizeof(x));
+  memcpy(y, mat + 3, sizeof(y));
+  memcpy(z, mat + 6, sizeof(z));
+
+  p[0] = y[0];
+  p[1] = y[1];
+  if (normalize2(p)) {
+    heading = -atan2f(p[0], p[1]);
+    M3(rot, 0, 0) = p[1];  M3(rot, 0, 1) = p[0];  M3(rot, 0, 2) = 0;
+    M3(rot, 1, 0) = -p[0]; M3(rot, 1, 1) = p[1];  M3(rot, 1, 2) = 0;
+    M3(rot, 2, 0) = 0;     M3(rot, 2, 1) = 0;     M3(rot, 2, 2) = 1;
+    xform3(rot, x);
+    xform3(rot, y);
+    xform3(rot, z);
+  }
+  p[0] = y[1];
+  p[1] = y[2];
+  if (normalize2(p)) {
+    pitch = atan2f(p[1], p[0]);
+    M3(rot, 0, 0) = 1; M3(rot, 0, 1) = 0;     M3(rot, 0, 2) = 0;
+    M3(rot, 1, 0) = 0; M3(rot, 1, 1) = p[0];  M3(rot, 1, 2) = -p[1];
+    M3(rot, 2, 0) = 0; M3(rot, 2, 1) = p[1];  M3(rot, 2, 2) = p[0];
+    xform3(rot, x);
+    xform3(rot, y);
+    xform3(rot, z);
+  }
+  p[0] = x[0];
+  p[1] = x[2];
+  if (normalize2(p)) {
+    roll = -atan2f(p[1], p[0]);
+    M3(rot, 0, 0) = p[0];  M3(rot, 0, 1) = 0; M3(rot, 0, 2) = -p[1];
+    M3(rot, 1, 0) = 0;     M3(rot, 1, 1) = 1; M3(rot, 1, 2) = 0;
+    M3(rot, 2, 0) = p[1];  M3(rot, 2, 1) = 0; M3(rot, 2, 2) = p[0];
+    xform3(rot, x);
+    xform3(rot, y);
+    xform3(rot, z);
+  }
+  memcpy(mat + 0, x, sizeof(x));
+  memcpy(mat + 3, y, sizeof(y));
+  memcpy(mat + 6, z, sizeof(z));
+  hpr[0] = heading * RAD_2_DEG_F;
+  hpr[1] = pitch * RAD_2_DEG_F;
+  hpr[2] = roll * RAD_2_DEG_F;
+}
+
+/* unwind_yup_rotation, panda/src/linmath/compose_matrix_src.cxx:315-412 */
+static void unwind_yup_rotation(float *mat, float *hpr) {
+  float x[3], y[3], z[3], heading = 0, pitch = 0, roll = 0, p[2], rot[9];
+  memcpy(x, mat + 0, sizeof(x));
+  memcpy(y, mat + 3, sizeof(y));
+  memcpy(z, mat + 6, sizeof(z));
+
+  p[0] = z[0];
+  p[1] = z[2];
+  if (normalize2(p)) {
+    heading = atan2f(p[0], p[1]);
+    M3(rot, 0, 0) = p[1];  M3(rot, 0, 1) = 0; M3(rot, 0, 2) = p[0];
+    M3(rot, 1, 0) = 0;     M3(rot, 1, 1) = 1; M3(rot, 1, 2) = 0;
+    M3(rot, 2, 0) = -p[0]; M3(rot, 2, 1) = 0; M3(rot, 2, 2) = p[1];
+    xform3(rot, x);
+    xform3(rot, y);
+    xform3(rot, z);
+  }
+  p[0] = z[1];
+  p[1] = z[2];
+  if (normalize2(p)) {
+    pitch = -atan2f(p[0], p[1]);
+    M3(rot, 0, 0) = 1; M3(rot, 0, 1) = 0;     M3(rot, 0, 2) = 0;
+    M3(rot, 1, 0) = 0; M3(rot, 1, 1) = p[1];  M3(rot, 1, 2) = p[0];
+    M3(rot, 2, 0) = 0; M3(rot, 2, 1) = -p[0]; M3(rot, 2, 2) = p[1];
+    xform3(rot, x);
+    xform3(rot, y);
+    xform3(rot, z);
+  }
+  p[0] = x[0];
+  p[1] = x[1];
+  if (normalize2(p)) {
+    roll = -atan2f(p[1], p[0]);
+    M3(rot, 0, 0) = p[0];  M3(rot, 0, 1) = -p[1]; M3(rot, 0, 2) = 0;
+    M3(rot, 1, 0) = p[1];  M3(rot, 1, 1) = p[0];  M3(rot, 1, 2) = 0;
+    M3(rot, 2, 0) = 0;     M3(rot, 2, 1) = 0;     M3(rot, 2, 2) = 1;
+    xform3(rot, x);
+    xform3(rot, y);
+    xform3(rot, z);
+  }
+  memcpy(mat + 0, x, sizeof(x));
+  memcpy(mat + 3, y, sizeof(y));
+  memcpy(mat + 6, z, sizeof(z));
+  hpr[0] = heading * RAD_2_DEG_F;
+  hpr[1] = pitch * RAD_2_DEG_F;
+  hpr[2] = roll * RAD_2_DEG_F;
+}
+
+/* decompose_matrix(LMatrix3f, scale, shear, hpr, cs),
+ * panda/src/linmath/compose_matrix_src.cxx:525-627 */
+int p3o_decompose3(const float *in9, int cs, float *scale, float *shear, float *hpr) {
+  float m[9];
+  memcpy(m, in9, sizeof(m));
+  switch (cs) {
+  case P3O_CS_ZUP_RIGHT:
+    unwind_zup_rotation(m, hpr);
+    break;
+  case P3O_CS_YUP_RIGHT:
+    unwind_yup_rotation(m, hpr);
+    break;
+  case P3O_CS_ZUP_LEFT:
+    M3(m, 0, 2) = -M3(m, 0, 2);
+    M3(m, 1, 2) = -M3(m, 1, 2);
+    M3(m, 2, 0) = -M3(m, 2, 0);
+    M3(m, 2, 1) = -M3(m, 2, 1);
+    unwind_zup_rotation(m, hpr);
+    hpr[0] = -hpr[0];
+    hpr[2] = -hpr[2];
+    break;
+  case P3O_CS_YUP_LEFT:
+    M3(m, 0, 2) = -M3(m, 0, 2);
+    M3(m, 1, 2) = -M3(m, 1, 2);
+    M3(m, 2, 0) = -M3(m, 2, 0);
+    M3(m, 2, 1) = -M3(m, 2, 1);
+    unwind_yup_rotation(m, hpr);
+    break;
+  default:
+    return 0;
+  }
+  scale[0] = M3(m, 0, 0);
+  scale[1] = M3(m, 1, 1);
+  scale[2] = M3(m, 2, 2);
+  if (scale[0] != 0.0f) {
+    M3(m, 0, 1) /= scale[0];
+    M3(m, 0, 2) /= scale[0];
+  }
+  if (scale[1] != 0.0f) {
+    M3(m, 1, 0) /= scale[1];
+    M3(m, 1, 2) /= scale[1];
+  }
+  if (scale[2] != 0.0f) {
+    M3(m, 2, 0) /= scale[2];
+    M3(m, 2, 1) /= scale[2];
+  }
+  shear[0] = M3(m, 0, 1) + M3(m, 1, 0);
+  shear[1] = M3(m, 2, 0) + M3(m, 0, 2);
+  shear[2] = M3(m, 2, 1) + M3(m, 1, 2);
+  return 1;
+}
+
+/* LMatrix3f::set_rotate_mat_normaxis, panda/src/linmath/lmatrix3_src.cxx:258-298 */
+static void rotate_mat_normaxis3(float *m, float angle, const float *axis, int cs) {
+  float a0 = axis[0], a1 = axis[1], a2 = axis[2];
+  float angle_rad, s, c, t, t0, t1, t2, s0, s1, s2;
+  if (cs == P3O_CS_ZUP_LEFT || cs == P3O_CS_YUP_LEFT) angle = -angle;
+  angle_rad = angle * DEG_2_RAD_F;
+  s = sinf(angle_rad);   /* csincos -> sincosf, dtool/src/dtoolbase/cmath.I:55-75 */
+  c = cosf(angle_rad);
+  t = 1.0f - c;
+  t0 = t * a0;
+  t1 = t * a1;
+  t2 = t * a2;
+  s0 = s * a0;
+  s1 = s * a1;
+  s2 = s * a2;
+  M3(m, 0, 0) = t0 * a0 + c;
+  M3(m, 0, 1) = t0 * a1 + s2;
+  M3(m, 0, 2) = t0 * a2 - s1;
+  M3(m, 1, 0) = t1 * a0 - s2;
+  M3(m, 1, 1) = t1 * a1 + c;
+  M3(m, 1, 2) = t1 * a2 + s0;
+  M3(m, 2, 0) = t2 * a0 + s1;
+  M3(m, 2, 1) = t2 * a1 - s0;
+  M3(m, 2, 2) = t2 * a2 + c;
+}
+
+/* compose_matrix(LMatrix3f &, scale, shear, hpr, cs),
+ * panda/src/linmath/compose_matrix_src.cxx:283-306;
+ * LMatrix3f::set_scale_shear_mat, lmatrix3_src.cxx:50-96;
+ * LVector3f::forward/right/up, lvector3_src.I:267-322. */
+void p3o_compose3(float *mat, const float *scale, const float *shear, const float *hpr, int cs) {
+  float fwd[3] = {0, 0, 0}, right[3] = {1, 0, 0}, up[3] = {0, 0, 0}, r[9], tmp[9];
+  switch (cs) {
+  case P3O_CS_ZUP_RIGHT:
+    M3(mat, 0, 0) = scale[0]; M3(mat, 0, 1) = shear[0] * scale[0]; M3(mat, 0, 2) = 0.0f;
+    M3(mat, 1, 0) = 0.0f; M3(mat, 1, 1) = scale[1]; M3(mat, 1, 2) = 0.0f;
+    M3(mat, 2, 0) = shear[1] * scale[2]; M3(mat, 2, 1) = shear[2] * scale[2]; M3(mat, 2, 2) = scale[2];
+    fwd[1] = 1; up[2] = 1;
+    break;
+  case P3O_CS_ZUP_LEFT:
+    M3(mat, 0, 0) = scale[0]; M3(mat, 0, 1) = shear[0] * scale[0]; M3(mat, 0, 2) = 0.0f;
+    M3(mat, 1, 0) = 0.0f; M3(mat, 1, 1) = scale[1]; M3(mat, 1, 2) = 0.0f;
+    M3(mat, 2, 0) = -shear[1] * scale[2]; M3(mat, 2, 1) = -shear[2] * scale[2]; M3(mat, 2, 2) = scale[2];
+    fwd[1] = -1; up[2] = 1;
+    break;
+  case P3O_CS_YUP_RIGHT:
+    M3(mat, 0, 0) = scale[0]; M3(mat, 0, 1) = 0.0f; M3(mat, 0, 2) = shear[1] * scale[0];
+    M3(mat, 1, 0) = shear[0] * scale[1]; M3(mat, 1, 1) = scale[1]; M3(mat, 1, 2) = shear[2] * scale[1];
+    M3(mat, 2, 0) = 0.0f; M3(mat, 2, 1) = 0.0f; M3(mat, 2, 2) = scale[2];
+    fwd[2] = -1; up[1] = 1;
+    break;
+  case P3O_CS_YUP_LEFT:
+  default:
+    M3(mat, 0, 0) = scale[0]; M3(mat, 0, 1) = 0.0f; M3(mat, 0, 2) = -shear[1] * scale[0];
+    M3(mat, 1, 0) = shear[0] * scale[1]; M3(mat, 1, 1) = scale[1]; M3(mat, 1, 2) = -shear[2] * scale[1];
+    M3(mat, 2, 0) = 0.0f; M3(mat, 2, 1) = 0.0f; M3(mat, 2, 2) = scale[2];
+    fwd[2] = 1; up[1] = 1;
+    break;
+  }
+  if (!IS_NEARLY_ZERO(hpr[2])) {
+    rotate_mat_normaxis3(r, hpr[2], fwd, cs);
+    memcpy(tmp, mat, sizeof(tmp));
+    mul3(mat, tmp, r);   /* mat *= r, lmatrix3_src.I:775-783 */
+  }
+  if (!IS_NEARLY_ZERO(hpr[1])) {
+    rotate_mat_normaxis3(r, hpr[1], right, cs);
+    memcpy(tmp, mat, sizeof(tmp));
+    mul3(mat, tmp, r);
+  }
+  if (!IS_NEARLY_ZERO(hpr[0])) {
+    rotate_mat_normaxis3(r, hpr[0], up, cs);
+    memcpy(tmp, mat, sizeof(tmp));
+    mul3(mat, tmp, r);
+  }
+}
+
+/* The C_normal prelude of GeomVertexData::do_transform_vector_column,
+ * panda/src/gobj/geomVertexData.cxx:1811-1840. */
+int p3o_normal_xform(const float *mat, int cs, float *xform, int *normalize) {
+  float sq0 = M4(mat, 0, 0) * M4(mat, 0, 0) + M4(mat, 0, 1) * M4(mat, 0, 1) + M4(mat, 0, 2) * M4(mat, 0, 2);
+  float sq1 = M4(mat, 1, 0) * M4(mat, 1, 0) + M4(mat, 1, 1) * M4(mat, 1, 1) + M4(mat, 1, 2) * M4(mat, 1, 2);
+  float sq2 = M4(mat, 2, 0) * M4(mat, 2, 0) + M4(mat, 2, 1) * M4(mat, 2, 1) + M4(mat, 2, 2) * M4(mat, 2, 2);
+  *normalize = 0;
+  if (IS_THRESHOLD_EQUAL(sq0, sq1, 2.0e-3f) && IS_THRESHOLD_EQUAL(sq0, sq2, 2.0e-3f)) {
+    float up3[9], scale[3], shear[3], hpr[3], ones[3] = {1, 1, 1}, c3[9];
+    int i, j;
+    if (IS_THRESHOLD_EQUAL(sq0, 1, 2.0e-3f)) {
+      memcpy(xform, mat, 16 * sizeof(float));
+      return 0;
+    }
+    for (i = 0; i < 3; ++i)
+      for (j = 0; j < 3; ++j) M3(up3, i, j) = M4(mat, i, j);
+    if (p3o_decompose3(up3, cs, scale, shear, hpr)) {
+      /* compose_matrix(LMatrix4f&, ...) = LMatrix4f(upper3, translate=0),
+       * panda/src/linmath/compose_matrix_src.I:18-28 */
+      p3o_compose3(c3, ones, shear, hpr, cs);
+      ident4(xform);
+      for (i = 0; i < 3; ++i)
+        for (j = 0; j < 3; ++j) M4(xform, i, j) = M3(c3, i, j);
+      return 1;
+    }
+    memcpy(xform, mat, 16 * sizeof(float)); /* unreachable for a valid cs */
+    *normalize = 1;
+    return 2;
+  } else {
+    float inv[16];
+    int i, j;
+    p3o_invert4(mat, inv);
+    for (i = 0; i < 4; ++i)
+      for (j = 0; j < 4; ++j) M4(xform, i, j) = M4(inv, j, i); /* transpose_in_place */
+    *normalize = 1;
+    return 3;
+  }
+}
+
+/* ---- column transforms: geomVertexData.cxx:1886-1956 + lmatrix4_src.I:704-784 ---- */
+
+static void xform_point3(float *v, const float *m) { /* table_xform_point3f / xform_point */
+  float r0 = v[0] * M4(m, 0, 0) + v[1] * M4(m, 1, 0) + v[2] * M4(m, 2, 0) + M4(m, 3, 0);
+  float r1 = v[0] * M4(m, 0, 1) + v[1] * M4(m, 1, 1) + v[2] * M4(m, 2, 1) + M4(m, 3, 1);
+  float r2 = v[0] * M4(m, 0, 2) + v[1] * M4(m, 1, 2) + v[2] * M4(m, 2, 2) + M4(m, 3, 2);
+  v[0] = r0;
+  v[1] = r1;
+  v[2] = r2;
+}
+
+static void xform_vec3(float *v, const float *m) { /* table_xform_vector3f / xform_vec */
+  float r0 = v[0] * M4(m, 0, 0) + v[1] * M4(m, 1, 0) + v[2] * M4(m, 2, 0);
+  float r1 = v[0] * M4(m, 0, 1) + v[1] * M4(m, 1, 1) + v[2] * M4(m, 2, 1);
+  float r2 = v[0] * M4(m, 0, 2) + v[1] * M4(m, 1, 2) + v[2] * M4(m, 2, 2);
+  v[0] = r0;
+  v[1] = r1;
+  v[2] = r2;
+}
+
+static void xform_vec4(float *v, const float *m) { /* table_xform_vecbase4f / xform */
+  float r[4];
+  int j;
+  for (j = 0; j < 4; ++j)
+    r[j] = v[0] * M4(m, 0, j) + v[1] * M4(m, 1, j) + v[2] * M4(m, 2, j) + v[3] * M4(m, 3, j);
+  memcpy(v, r, sizeof(r));
+}
+
+/* GeomVertexReader::get_data1i on an integer column */
+static int read_index(const uint8_t *p, int numeric_type) {
+  switch (numeric_type) {
+  case P3O_NT_UINT8: return *p;
+  case P3O_NT_UINT16: { uint16_t v; memcpy(&v, p, 2); return v; }
+  case P3O_NT_UINT32: { uint32_t v; memcpy(&v, p, 4); return (int)v; }
+  default: return -1;
+  }
+}
+
+/* do_transform_point_column / do_transform_vector_column for one run
+ * [begin,end) sharing one blend matrix (geomVertexData.cxx:1758-1880). */
+static void transform_run(const p3o_mesh *mesh, const p3o_column *col, uint8_t *out, int stride,
+                          const float *mat, int begin, int end) {
+  int nv = col->num_values, i;
+  uint8_t *datat = out + col->start + (size_t)begin * stride;
+  if (col->contents == P3O_C_POINT) {
+    for (i = 0; i < end - begin; ++i) {
+      float *v = (float *)(datat + (size_t)i * stride);
+      if (nv == 3) xform_point3(v, mat); else xform_vec4(v, mat);
+    }
+  } else {
+    float xform[16];
+    int normalize = 0;
+    if (col->contents == P3O_C_NORMAL) {
+      p3o_normal_xform(mat, mesh->coordinate_system, xform, &normalize);
+    } else {
+      memcpy(xform, mat, sizeof(xform));
+    }
+    for (i = 0; i < end - begin; ++i) {
+      float *v = (float *)(datat + (size_t)i * stride);
+      if (normalize) {          /* table_xform_normal3f, also for 4-component columns */
+        xform_vec3(v, xform);
+        normalize3(v);
+      } else if (nv == 3) {
+        xform_vec3(v, xform);
+      } else {
+        xform_vec4(v, xform);
+      }
+    }
+  }
+}
+
+/* float32 column read in the manner of GeomVertexReader::get_data3 / get_data4
+ * for plain float columns: missing components read as 0 (w as 1 for get_data4). */
+static void get3(const uint8_t *p, int nv, float *v) {
+  const float *f = (const float *)p;
+  v[0] = nv > 0 ? f[0] : 0.0f;
+  v[1] = nv > 1 ? f[1] : 0.0f;
+  v[2] = nv > 2 ? f[2] : 0.0f;
+}
+
+static int output_index(const p3o_mesh *mesh, int array) {
+  int i, o = 0;
+  for (i = 0; i < array; ++i) o += mesh->array_is_output[i] ? 1 : 0;
+  return mesh->array_is_output[array] ? o : -1;
+}
+
+int p3o_animate(const p3o_mesh *mesh, const float *palette, const float *sliders,
+                uint8_t *const *out_arrays, float *blends_out, int32_t *selection_out) {
+  int n = mesh->num_rows, a, o, ci, mi, i, j;
+  float *blends = NULL;
+
+  /* validate: only the float32 fast paths are restated */
+  for (ci = 0; ci < mesh->num_skin_columns; ++ci) {
+    const p3o_column *c = &mesh->skin_columns[ci];
+    if (c->numeric_type != P3O_NT_FLOAT32 || (c->num_values != 3 && c->num_values != 4)) return -1;
+    if (output_index(mesh, c->array) < 0) return -1;
+  }
+
+  /* (i) new_data->copy_from(this, true), geomVertexData.cxx:1460: whole-array
+   * memcpy because the post-animated array formats are data subsets with the
+   * same stride (geomVertexArrayFormat.cxx:414-419, remove_column :278-304). */
+  for (a = 0, o = 0; a < mesh->num_arrays; ++a) {
+    if (mesh->array_is_output[a]) {
+      memcpy(out_arrays[o], mesh->array_data[a], (size_t)n * mesh->array_stride[a]);
+      ++o;
+    }
+  }
+
+  /* (ii) morphs, geomVertexData.cxx:1462-1543 */
+  for (mi = 0; mi < mesh->num_morphs; ++mi) {
+    const p3o_morph *m = &mesh->morphs[mi];
+    float slider_value = sliders[m->slider];
+    int bo = output_index(mesh, m->base.array);
+    int bstride, dstride;
+    uint8_t *bdata;
+    const uint8_t *ddata;
+    if (bo < 0 || m->base.numeric_type != P3O_NT_FLOAT32 || m->delta.numeric_type != P3O_NT_FLOAT32) return -1;
+    if (slider_value == 0.0f) continue;
+    bstride = mesh->array_stride[m->base.array];
+    dstride = mesh->array_stride[m->delta.array];
+    bdata = out_arrays[bo] + m->base.start;
+    ddata = mesh->array_data[m->delta.array] + m->delta.start;
+    for (i = 0; i < m->num_row_ranges; ++i) {
+      int begin = m->row_ranges[2 * i], end = m->row_ranges[2 * i + 1];
+      for (j = begin; j < end; ++j) {
+        float *vertex = (float *)(bdata + (size_t)j * bstride);
+        const uint8_t *dp = ddata + (size_t)j * dstride;
+        float d[4];
+        if (m->base.num_values == 4) {
+          int homogeneous = (m->base.contents == P3O_C_POINT || m->base.contents == P3O_C_TEXCOORD);
+          if (homogeneous) {
+            /* :1499-1507  d *= slider_value * vertex[3] */
+            float s = slider_value * vertex[3];
+            get3(dp, m->delta.num_values, d);
+            d[0] *= s; d[1] *= s; d[2] *= s;
+            vertex[0] = vertex[0] + d[0];
+            vertex[1] = vertex[1] + d[1];
+            vertex[2] = vertex[2] + d[2];
+          } else {
+            /* :1516-1520  vertex + d * slider_value (4 components) */
+            const float *f = (const float *)dp;
+            int k;
+            /* default Packer::get_data4f pads missing components with 0
+             * (geomVertexColumn.cxx:718-737) */
+            for (k = 0; k < 4; ++k) d[k] = k < m->delta.num_values ? f[k] : 0.0f;
+            for (k = 0; k < 4; ++k) vertex[k] = vertex[k] + d[k] * slider_value;
+          }
+        } else {
+          /* :1531-1535  vertex + d * slider_value (<= 3 components) */
+          int k, nv = m->base.num_values;
+          get3(dp, m->delta.num_values, d);
+          for (k = 0; k < nv && k < 3; ++k) vertex[k] = vertex[k] + d[k] * slider_value;
+        }
+      }
+    }
+  }
+
+  if (selection_out) {
+    for (i = 0; i < n; ++i) selection_out[i] = -1;
+  }
+  if (mesh->blend_column.array < 0) return 0;
+
+  /* (iii) update_blend for every blend, geomVertexData.cxx:1550-1556 */
+  blends = (float *)malloc((size_t)(mesh->num_blends > 0 ? mesh->num_blends : 1) * 16 * sizeof(float));
+  if (!blends) return -2;
+  for (i = 0; i < mesh->num_blends; ++i) {
+    int b = mesh->blend_offsets[i], e = mesh->blend_offsets[i + 1];
+    p3o_blend(palette, mesh->blend_transform + b, mesh->blend_weight + b, e - b, blends + (size_t)i * 16);
+  }
+  if (blends_out) memcpy(blends_out, blends, (size_t)mesh->num_blends * 16 * sizeof(float));
+
+  /* (iv) run-length scan over the rows subranges, per column: points first,
+   * then vectors (geomVertexData.cxx:1574-1750; both the ushort fast path and
+   * the generic reader path visit the same runs). */
+  {
+    const p3o_column *bc = &mesh->blend_column;
+    const uint8_t *bt = mesh->array_data[bc->array] + bc->start;
+    int bstride = mesh->array_stride[bc->array];
+    for (ci = 0; ci < mesh->num_skin_columns; ++ci) {
+      const p3o_column *col = &mesh->skin_columns[ci];
+      int oa = output_index(mesh, col->array);
+      int stride = mesh->array_stride[col->array];
+      for (i = 0; i < mesh->num_row_ranges; ++i) {
+        int begin = mesh->row_ranges[2 * i], end = mesh->row_ranges[2 * i + 1];
+        int first_vertex = begin;
+        int first_bi;
+        if (begin >= end) continue;
+        first_bi = read_index(bt + (size_t)first_vertex * bstride, bc->numeric_type);
+        while (first_vertex < end) {
+          int next_vertex = first_vertex, next_bi = first_bi;
+          ++next_vertex;
+          while (next_vertex < end) {
+            next_bi = read_index(bt + (size_t)next_vertex * bstride, bc->numeric_type);
+            if (next_bi != first_bi) break;
+            ++next_vertex;
+          }
+          if (first_bi < 0 || first_bi >= mesh->num_blends) {
+            free(blends);
+            return -3;
+          }
+          transform_run(mesh, col, out_arrays[oa], stride, blends + (size_t)first_bi * 16,
+                        first_vertex, next_vertex);
+          if (selection_out) {
+            for (j = first_vertex; j < next_vertex; ++j) selection_out[j] = first_bi;
+          }
+          first_vertex = next_vertex;
+          first_bi = next_bi;
+        }
+      }
+    }
+    if (selection_out && mesh->num_skin_columns == 0) {
+      for (i = 0; i < mesh->num_row_ranges; ++i)
+        for (j = mesh->row_ranges[2 * i]; j < mesh->row_ranges[2 * i + 1]; ++j)
+          selection_out[j] = read_index(bt + (size_t)j * bstride, bc->numeric_type);
+    }
+  }
+  free(blends);
+  return 0;
+}

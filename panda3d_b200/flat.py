@@ -1,0 +1,142 @@
+"""Flattened description of one animated GeomVertexData -- what crosses the C-ABI.
+
+Field for field this is `p3cs_mesh_desc` of include/p3cudaskin.h: the source arrays,
+the columns the blend matrices transform, the `transform_blend` index column, the
+TransformBlendTable as CSR in stored entry order, the rows mask and the morph
+applications in the reference's iteration order (panda/src/gobj/geomVertexData.cxx:
+1462-1751).  Integer codes are GeomEnums values (panda/src/gobj/geomEnums.h:177-212).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+# GeomEnums::NumericType
+NT_uint8, NT_uint16, NT_uint32, NT_packed_dcba, NT_packed_dabc, NT_float32, NT_float64, \
+    NT_stdfloat, NT_int8, NT_int16, NT_int32, NT_packed_ufloat = range(12)
+# GeomEnums::Contents
+C_other, C_point, C_clip_point, C_vector, C_texcoord, C_color, C_index, C_morph_delta, \
+    C_matrix, C_normal = range(10)
+# CoordinateSystem (panda/src/linmath/coordinateSystem.h)
+CS_default, CS_zup_right, CS_yup_right, CS_zup_left, CS_yup_left, CS_invalid = range(6)
+
+NUMERIC_BYTES = {NT_uint8: 1, NT_uint16: 2, NT_uint32: 4, NT_packed_dcba: 4, NT_packed_dabc: 4,
+                 NT_float32: 4, NT_float64: 8, NT_stdfloat: 4, NT_int8: 1, NT_int16: 2, NT_int32: 4,
+                 NT_packed_ufloat: 4}
+
+
+@dataclass
+class Column:
+    """One GeomVertexColumn: (array, start, num_values, numeric_type, contents)."""
+    array: int
+    start: int
+    num_values: int
+    numeric_type: int
+    contents: int
+
+    def as_tuple(self) -> Tuple[int, int, int, int, int]:
+        return (self.array, self.start, self.num_values, self.numeric_type, self.contents)
+
+
+@dataclass
+class Morph:
+    """One (C_morph_delta column, slider) application with the slider's rows."""
+    slider: int
+    base: Column
+    delta: Column
+    row_ranges: np.ndarray  # int32 [k, 2]
+
+
+@dataclass
+class FlatMesh:
+    num_rows: int
+    arrays: List[np.ndarray]            # uint8 [num_rows, stride] per SOURCE array
+    is_output: List[bool]
+    skin_columns: List[Column]          # points first, then vectors
+    blend_column: Optional[Column]
+    num_transforms: int
+    blend_offsets: np.ndarray           # int32 [B+1]
+    blend_transform: np.ndarray         # int32 [nnz]
+    blend_weight: np.ndarray            # float32 [nnz]
+    row_ranges: np.ndarray              # int32 [k, 2]
+    num_sliders: int = 0
+    morphs: List[Morph] = field(default_factory=list)
+    coordinate_system: int = CS_zup_right
+
+    @property
+    def num_blends(self) -> int:
+        return int(len(self.blend_offsets) - 1)
+
+    @property
+    def strides(self) -> List[int]:
+        return [int(a.shape[1]) for a in self.arrays]
+
+    @property
+    def output_arrays(self) -> List[int]:
+        return [i for i, o in enumerate(self.is_output) if o]
+
+    def skinned_rows(self) -> int:
+        """Rows inside TransformBlendTable::get_rows() (what `vertices/s` counts)."""
+        if self.blend_column is None:
+            return 0
+        r = np.asarray(self.row_ranges).reshape(-1, 2)
+        return int((r[:, 1] - r[:, 0]).sum())
+
+    def blend_indices(self) -> np.ndarray:
+        """The per-row transform_blend value, as GeomVertexReader::get_data1i reads it."""
+        c = self.blend_column
+        if c is None:
+            return np.zeros(0, np.int64)
+        dt = {NT_uint8: np.uint8, NT_uint16: np.uint16, NT_uint32: np.uint32}[c.numeric_type]
+        nb = np.dtype(dt).itemsize
+        raw = np.ascontiguousarray(self.arrays[c.array][:, c.start:c.start + nb])
+        return raw.view(dt).reshape(-1).astype(np.int64)
+
+    def validate(self) -> None:
+        n = self.num_rows
+        for a in self.arrays:
+            if a.dtype != np.uint8 or a.ndim != 2 or a.shape[0] != n:
+                raise ValueError("arrays must be uint8 [num_rows, stride]")
+        for c in self.skin_columns:
+            if not self.is_output[c.array]:
+                raise ValueError("skin column in a non-output array")
+            if c.start + c.num_values * NUMERIC_BYTES[c.numeric_type] > self.arrays[c.array].shape[1]:
+                raise ValueError("skin column exceeds the stride")
+        if self.blend_column is not None:
+            bi = self.blend_indices()
+            r = np.asarray(self.row_ranges).reshape(-1, 2)
+            for b, e in r:
+                if not (0 <= b < e <= n):
+                    raise ValueError("bad row range")
+                if bi[b:e].size and int(bi[b:e].max()) >= self.num_blends:
+                    raise ValueError("transform_blend index out of range")
+            if len(self.blend_transform) and int(self.blend_transform.max()) >= self.num_transforms:
+                raise ValueError("blend refers to a transform outside the palette")
+
+
+def mesh_from_case(case: Dict[str, np.ndarray]) -> FlatMesh:
+    """Builds a FlatMesh from a golden case written by oracle/ref_harness.cxx."""
+    meta = case["meta"]
+    num_rows, na = int(meta[0]), int(meta[1])
+    arrays = [np.ascontiguousarray(case[f"src_array{a}"]).reshape(num_rows, -1).astype(np.uint8) for a in range(na)]
+    is_output = [bool(x) for x in case["src_is_output"]]
+    skin = [Column(*map(int, r)) for r in case["skin_columns"].reshape(-1, 5)]
+    bc = case["blend_column"]
+    blend_column = Column(*map(int, bc)) if int(bc[0]) >= 0 else None
+    morphs = []
+    mtab = case["morphs"].reshape(-1, 11)
+    mro = case["morph_row_offsets"]
+    mrows = case["morph_rows"].reshape(-1, 2)
+    for i, r in enumerate(mtab):
+        morphs.append(Morph(int(r[0]), Column(*map(int, r[1:6])), Column(*map(int, r[6:11])),
+                            mrows[int(mro[i]):int(mro[i + 1])].astype(np.int32)))
+    return FlatMesh(
+        num_rows=num_rows, arrays=arrays, is_output=is_output, skin_columns=skin,
+        blend_column=blend_column, num_transforms=int(meta[3]),
+        blend_offsets=case["blend_offsets"].astype(np.int32),
+        blend_transform=case["blend_transform"].astype(np.int32),
+        blend_weight=case["blend_weight"].astype(np.float32),
+        row_ranges=case["rows"].reshape(-1, 2).astype(np.int32),
+        num_sliders=int(meta[5]), morphs=morphs, coordinate_system=int(meta[6]) or CS_zup_right)

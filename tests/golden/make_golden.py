@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/*.p3cs by running the UNMODIFIED reference.
+
+Needs oracle/_ref (bash oracle/build_ref.sh, which needs /root/reference): every
+golden file holds the flattened inputs as the reference's own objects report them and
+the byte image of what GeomVertexData::animate_vertices(true, thread) returned
+(panda/src/gobj/geomVertexData.cxx:912), per frame.  Run from the repo root:
+    python tests/golden/make_golden.py
+The fixtures are small on purpose (a few hundred rows); they pin oracle/skin_oracle.c
+bit for bit (tests/test_oracle_golden.py) and are the first parity target of the CUDA path.
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+
+from panda3d_b200 import synth  # noqa: E402
+from panda3d_b200.casefile import save_case  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "bin", "ref_harness")
+REF = os.environ.get("P3D_REFERENCE", "/root/reference")
+
+
+def cases():
+    P, S = synth.make_palettes, synth.make_sliders
+    mk = synth.make_mesh
+    yield "basic", mk(600, 16, 120, seed=1), P(16, 2, 7), None
+    yield "sorted", mk(600, 16, 120, seed=21, index_order="sorted"), P(16, 2, 27), None
+    yield "tbn_uv", mk(500, 16, 100, seed=2, tbn=True, texcoord=True, index_order="runs"), P(16, 2, 8), None
+    yield "rigid", mk(400, 16, 16, seed=3, weights_per_blend=1, index_order="sorted"), P(16, 2, 9), None
+    yield "rigid_uniform_scale", mk(400, 16, 16, seed=3, weights_per_blend=1), P(16, 2, 10, scale=0.687), None
+    yield "rigid_nonuniform_scale", mk(400, 16, 16, seed=3, weights_per_blend=1), P(16, 2, 11, scale=(1, 1.2, 0.8)), None
+    yield "two_weights_near_uniform", mk(400, 8, 60, seed=31, weights_per_blend=2), P(8, 2, 32, scale=1.0, jitter=0.002), None
+    yield "align16", mk(400, 12, 80, seed=4, align16=True, texcoord=True), P(12, 2, 12), None
+    yield "align16_uniform_scale", mk(300, 12, 12, seed=4, align16=True, weights_per_blend=1), P(12, 2, 12, scale=1.3), None
+    yield "align16_tbn", mk(300, 12, 60, seed=41, align16=True, tbn=True), P(12, 1, 42), None
+    yield "morph", mk(800, 12, 100, seed=5, num_sliders=8, morph_columns=("vertex", "normal"), slider_band=0.2,
+                      index_order="runs"), P(12, 3, 13), S(8, 3, 14)
+    yield "rows_u32", mk(900, 12, 100, seed=6, rows=[(10, 300), (450, 451), (600, 899)], index_type="u32"), P(12, 2, 15), None
+    yield "u8_align16_morph", mk(300, 12, 100, seed=7, index_type="u8", align16=True, num_sliders=3, slider_band=0.5), \
+        P(12, 2, 16), S(3, 2, 17)
+    for cs, csname in ((2, "yup_right"), (3, "zup_left"), (4, "yup_left")):
+        yield "cs_" + csname, mk(300, 8, 8, seed=8, weights_per_blend=1, coordinate_system=cs), P(8, 1, 18, scale=0.5), None
+
+
+def main():
+    if not os.path.exists(HARNESS):
+        sys.exit("oracle/_ref/bin/ref_harness missing: run `bash oracle/build_ref.sh` first")
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, sm, pal, sl in cases():
+            recipe = os.path.join(tmp, name + ".recipe")
+            save_case(recipe, sm.recipe(pal, sl))
+            out = os.path.join(HERE, name + ".p3cs")
+            subprocess.run([HARNESS, "run", recipe, out], check=True, timeout=120)
+            print("wrote", out, os.path.getsize(out))
+    # config C1: the panda Actor (models/panda-model.egg + panda-walk4.egg), frames 0/10/37
+    model = os.path.join(REF, "models", "panda-model.egg")
+    anim = os.path.join(REF, "models", "panda-walk4.egg")
+    out = os.path.join(HERE, "panda_walk4.p3cs")
+    subprocess.run([HARNESS, "egg", model, anim, out, "0", "10", "37"], check=True, timeout=120,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    print("wrote", out, os.path.getsize(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,66 @@
+"""Pins oracle/skin_oracle.c (the CPU restatement) against the UNMODIFIED reference.
+
+tests/golden/*.p3cs were produced by oracle/ref_harness.cxx linked against Panda3D 1.11.0
+built from /root/reference (tests/golden/make_golden.py): inputs as the reference's objects
+report them, outputs = the bytes GeomVertexData::animate_vertices returned.  The bar is
+bit-exactness of every output byte and of every blended matrix.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_ids, golden_paths
+from oracle import oracle
+from panda3d_b200.casefile import load_case
+from panda3d_b200.flat import mesh_from_case
+
+
+def test_golden_fixtures_present():
+    ids = golden_ids()
+    assert "panda_walk4" in ids and "morph" in ids and len(ids) >= 15
+
+
+@pytest.mark.parametrize("path", golden_paths(), ids=golden_ids())
+def test_oracle_matches_reference_bit_exact(path):
+    case = load_case(path)
+    mesh = mesh_from_case(case)
+    mesh.validate()
+    om = oracle.OracleMesh(mesh)
+    frames = int(case["meta"][7])
+    assert frames >= 1
+    for fr in range(frames):
+        sliders = case["sliders"][fr] if mesh.num_sliders else None
+        outs, blends, sel = om.animate(case["palette"][fr], sliders, want_blends=True, want_selection=True)
+        assert len(outs) == int(case["meta"][2])
+        for o, out in enumerate(outs):
+            expect = case[f"expect{o}"][fr].reshape(mesh.num_rows, -1)
+            assert np.array_equal(out, expect), f"frame {fr} output {o}: {(out != expect).sum()} bytes differ"
+        assert np.array_equal(blends.view(np.uint32), case["expect_blends"][fr].view(np.uint32))
+        # selection: rows inside TransformBlendTable::get_rows() pick blendt[row], others none
+        bi = mesh.blend_indices()
+        mask = np.zeros(mesh.num_rows, bool)
+        for b, e in mesh.row_ranges:
+            mask[b:e] = True
+        assert np.array_equal(sel[mask], bi[mask]) and np.all(sel[~mask] == -1)
+
+
+def test_panda_walk4_shape_matches_survey():
+    """C1 = 1338 rows, 197 blends, 26 transforms, stride 32."""
+    case = load_case([p for p in golden_paths() if p.endswith("panda_walk4.p3cs")][0])
+    mesh = mesh_from_case(case)
+    assert (mesh.num_rows, mesh.num_blends, mesh.num_transforms) == (1338, 197, 26)
+    assert mesh.strides == [32, 2] and mesh.is_output == [True, False]
+    # real data exercises the identity-scale and the inverse-transpose normal branches
+    # (blended rotations are not orthonormal)
+    branches = {oracle.normal_xform(b)[0] for fr in range(3) for b in case["expect_blends"][fr]}
+    assert {0, 3} <= branches
+
+
+def test_golden_branch_coverage():
+    """The synthetic fixtures isolate each normal-matrix branch of geomVertexData.cxx:1811-1840."""
+    want = {"rigid": {0}, "rigid_uniform_scale": {1}, "rigid_nonuniform_scale": {3}}
+    for p in golden_paths():
+        name = p.rsplit("/", 1)[1][:-5]
+        if name in want:
+            case = load_case(p)
+            got = {oracle.normal_xform(b)[0] for b in case["expect_blends"][0]}
+            assert got == want[name], (name, got)
