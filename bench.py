@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- skinned vertices/s of the vertex-animation hot path on B200, beside the CPU path.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
+line on rank 0.  A *step* is one animate pass over the whole crowd (every joint matrix changed, so
+every blend is recomputed and every vertex re-skinned).
+
+Workload (BASELINE.json configs[2], the configuration the metric "... at 1/2/4/8 B200" is quoted on):
+a crowd of 10 000 instances of a 20 000-vertex, 128-joint character (4096 4-weight blends),
+position + normal animated (stride 24).  The crowd is sharded by instance over the N ranks with no
+data-path collective ("scaling": "strong": the total is fixed at 10 000 instances).
+
+  value     whole-job vertices/s, palettes already resident in HBM, CUDA events, max over ranks
+  e2e       the same through the C-ABI with HOST buffers: palettes H2D from pinned memory and the
+            animated vertex arrays D2H every step (what GeomVertexData::animate_vertices hands back)
+  roofline  the dominant kernel (skin): algorithmic bytes / summed per-launch CUDA-event time
+  cpu_baseline / --impl reference: the reference's own CPU animate_vertices (oracle/_ref, built from
+            /root/reference) on the box's host cores, one worker process per core.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TOTAL_INSTANCES = 10_000
+METRIC = "skinned vertices/sec"
+UNIT = "vertices/s"
+
+
+def workload_mesh():
+    from panda3d_b200 import synth
+    return synth.config_c3_mesh()
+
+
+def config_dict(args, n_gpus):
+    return {
+        "workload": "C3 crowd: 10000 instances x (20000 vertices, 128 joints, 4096 4-weight blends), "
+                    "pos+normal float32 stride 24, u16 transform_blend, rows=all",
+        "instances_total": args.instances, "vertices_per_step": args.instances * 20_000,
+        "sharding": f"instance i -> rank i % {n_gpus}, no data-path collective",
+        "l2": "per-rank output (>= 600 MB) exceeds the 126 MB L2; no flush needed",
+    }
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self.stop_flag.is_set():
+            try:
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((mhz, util))
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.02)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        loaded = [m for m, u in self.samples if u > 0] or [m for m, _ in self.samples]
+        return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------ CPU arms
+def cpu_reference_run(mesh_synth, steps: int, warmup: int, characters_per_worker: int, workers: int):
+    """Times the reference's own animate_vertices (oracle/_ref/bin/ref_harness bench) with one worker
+    process per core -- in-process threads scale negatively in the reference.  Falls
+    back to the oracle port (oracle/skin_oracle.c) when oracle/_ref is absent."""
+    from oracle import oracle
+    from panda3d_b200 import synth
+    from panda3d_b200.casefile import save_case
+    flat = mesh_synth.flat
+    frames = 4
+    pal = synth.make_palettes(flat.num_transforms, frames, 4242)
+    rows = flat.num_rows
+    if oracle.have_ref():
+        with tempfile.TemporaryDirectory() as tmp:
+            recipe = os.path.join(tmp, "bench.recipe")
+            save_case(recipe, mesh_synth.recipe(pal))
+            env = dict(os.environ)
+            t0 = time.time()
+            procs = [subprocess.Popen([oracle.REF_HARNESS, "bench", recipe, str(steps), str(warmup), str(characters_per_worker)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=env, text=True) for _ in range(workers)]
+            outs = [p.communicate()[0] for p in procs]
+            wall = time.time() - t0
+        rates, mean_s = [], []
+        for o in outs:
+            line = [ln for ln in o.splitlines() if ln.startswith("{")][-1]
+            j = json.loads(line)
+            rates.append(j["verts_per_s_mean"])
+            mean_s.append(j["mean_s"])
+        return {"value": float(sum(rates)), "kind": "reference", "cores": workers, "ms_per_step": 1e3 * max(mean_s),
+                "wall_s": wall, "vertices_per_step": rows * characters_per_worker * workers}
+    # the oracle port, one process per core
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+
+    def worker():
+        om = oracle.OracleMesh(flat)
+        ts = []
+        for it in range(warmup + steps):
+            t = time.perf_counter()
+            for c in range(characters_per_worker):
+                om.animate(pal[(it + c) % frames])
+            if it >= warmup:
+                ts.append(time.perf_counter() - t)
+        q.put(sum(ts) / len(ts))
+
+    t0 = time.time()
+    ps = [ctx.Process(target=worker) for _ in range(workers)]
+    [p.start() for p in ps]
+    means = [q.get() for _ in ps]
+    [p.join() for p in ps]
+    wall = time.time() - t0
+    return {"value": float(sum(rows * characters_per_worker / m for m in means)), "kind": "port", "cores": workers,
+            "ms_per_step": 1e3 * max(means), "wall_s": wall, "vertices_per_step": rows * characters_per_worker * workers}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sm = workload_mesh()
+    workers = os.cpu_count() or 1
+    chars = max(1, args.cpu_characters)
+    r = cpu_reference_run(sm, args.steps, args.warmup, chars, workers)
+    sample = f"{chars} character(s) per worker x {workers} worker processes per step (of {args.instances} instances)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, args.gpus),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import torch
+    from panda3d_b200 import _capi, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    sm = workload_mesh()
+    flat = sm.flat
+    rows, T = flat.num_rows, flat.num_transforms
+    n_local = len(range(rank, args.instances, world))
+    stream = torch.cuda.Stream()
+    sampler = ClockSampler(local_rank)
+    with torch.cuda.stream(stream):
+        ctx = _capi.Context(local_rank, stream.cuda_stream)
+        dmesh = _capi.Mesh(ctx, flat)
+        stride = dmesh.out_strides[0]
+        pitch = (rows * stride + 255) // 256 * 256
+        # device memory is torch's (plumbing): palettes, outputs
+        pal_host = torch.from_numpy(synth.make_palettes(T, n_local, 1000 + rank).reshape(n_local, T * 16)).pin_memory()
+        pal_dev = torch.empty((n_local, T * 16), dtype=torch.float32, device="cuda")
+        out_dev = torch.empty((n_local, pitch), dtype=torch.uint8, device="cuda")
+        grp = _capi.Group(dmesh, n_local, palettes_dev=pal_dev.data_ptr(), outputs_dev=[out_dev.data_ptr()])
+        assert grp.output_pitch(0) == pitch
+        pal_dev.copy_(pal_host, non_blocking=True)
+        stream.synchronize()
+
+        sampler.start()
+        # ---------------- kernel-only: palettes resident in HBM
+        for _ in range(args.warmup):
+            grp.animate()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            grp.animate()
+        e1.record(stream)
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        launches_per_step = grp.timings().launches
+
+        # ---------------- per-launch timing of the kernels (roofline), same workload, same stream
+        grp.set_profiling(True)
+        blend_ms, skin_ms, skin_launches = [], [], 0
+        for _ in range(min(args.steps, 10)):
+            grp.animate()
+            t = grp.timings()
+            blend_ms.append(t.blend_ms)
+            skin_ms.append(t.skin_ms)
+            skin_launches = t.skin_launches
+        grp.set_profiling(False)
+
+        # ---------------- end to end through the C-ABI with host buffers
+        e2e_steps = max(2, min(args.steps, args.e2e_steps))
+        out_host = torch.empty((n_local, rows * stride), dtype=torch.uint8).pin_memory()
+        h2d = n_local * T * 64
+        d2h = n_local * rows * stride
+
+        def e2e_step():
+            grp.set_palettes_ptr(pal_host.data_ptr(), 0, n_local)
+            grp.animate()
+            grp.read_output_ptr(0, 0, n_local, out_host.data_ptr())
+            ctx.sync()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record(stream)
+        barrier()
+        e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / e2e_steps)
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+
+        # a cheap sanity check that the timed work was real: one instance against the oracle
+        check = None
+        if rank == 0 and not args.no_check:
+            from oracle import oracle
+            inst = n_local // 2
+            expect, _, _ = oracle.OracleMesh(flat).animate(pal_host[inst].numpy())
+            got = out_host[inst].numpy().reshape(rows, stride)
+            g, e = got.view(np.float32).astype(np.float64), expect[0].view(np.float32).astype(np.float64)
+            check = {"instance": inst, "max_abs_err": float(np.abs(g - e).max()), "differing_bytes": int((got != expect[0]).sum())}
+
+    total_verts = float(sum_over_ranks(float(n_local * flat.skinned_rows())))
+    value = total_verts / (ms * 1e-3)
+    e2e_value = total_verts / (e2e_ms * 1e-3)
+    h2d_total, d2h_total = int(sum_over_ranks(float(h2d))), int(sum_over_ranks(float(d2h)))
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+        else:
+            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        # dominant kernel = skin (K2).  Algorithmic bytes per vertex of an instanced crowd: the source
+        # mesh is shared (L2), so the compulsory HBM traffic is the output row (stride bytes); K2 also
+        # gathers blend records from the L2-resident scratch, which is not counted.
+        skin_s = statistics.mean(skin_ms) * 1e-3
+        alg_bytes_per_step = n_local * rows * stride
+        logical_bytes_per_step = n_local * rows * (2 * stride + 2)
+        achieved = alg_bytes_per_step / skin_s / 1e9
+        roofline = {"bound": "hbm", "kernel": "skin_kernel (K2)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "launches_per_step": skin_launches, "avg_launch_ms": 1e3 * skin_s / max(1, skin_launches),
+                    "algorithmic_bytes_per_vertex": stride, "logical_gbs": logical_bytes_per_step / skin_s / 1e9,
+                    "blend_kernel_ms_per_step": statistics.mean(blend_ms), "skin_kernel_ms_per_step": statistics.mean(skin_ms)}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            workers = os.cpu_count() or 1
+            r = cpu_reference_run(sm, 5, 2, max(1, args.cpu_characters), workers)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                   "sample": f"{args.cpu_characters} character(s) x {workers} worker processes x 5 iterations of the same mesh"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(args, world),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
+                    "ms_per_step": e2e_ms, "steps": e2e_steps},
+            "gpu_launches": launches_per_step * args.steps, "clocks": sampler.summary(), "check": check,
+        }
+        print(json.dumps(line), flush=True)
+    grp.close()
+    dmesh.close()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--instances", type=int, default=TOTAL_INSTANCES)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-characters", type=int, default=4, help="characters per CPU worker process per step")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -169,10 +169,12 @@ typedef struct p3cs_group_buffers {
 
 /* Timings of the last p3cs_group_animate (CUDA events on the context stream). */
 typedef struct p3cs_timings {
-  float blend_ms;    /* K1: blend-matrix + normal-matrix build                    */
-  float skin_ms;     /* K2: morph + skin + row write                              */
-  float total_ms;
-  int32_t launches;  /* kernels launched by the call                              */
+  float blend_ms;          /* K1 (blend + normal matrices): sum over its launches; -1 if unknown */
+  float skin_ms;           /* K2 (morph + skin + row write): sum over its launches; -1 if unknown */
+  float total_ms;          /* first launch start -> last launch end                     */
+  int32_t launches;        /* kernels launched by the call                              */
+  int32_t blend_launches;
+  int32_t skin_launches;
 } p3cs_timings;
 
 /* ---- library ---------------------------------------------------------- */
@@ -262,6 +264,11 @@ P3CS_EXPORT int p3cs_group_read_selection(p3cs_group group, int32_t *host_dst);
  * (TransformBlend::get_blend results); parity hook. */
 P3CS_EXPORT int p3cs_group_read_blends(p3cs_group group, int instance, float *host_dst);
 
+/* With profiling on, every kernel launch of p3cs_group_animate is bracketed by
+ * its own CUDA event pair on the context stream, so blend_ms / skin_ms are the
+ * summed per-launch durations (the figures bench.py's roofline uses).  Off by
+ * default: then only total_ms is measured (one event pair per call). */
+P3CS_EXPORT int p3cs_group_set_profiling(p3cs_group group, int enable);
 P3CS_EXPORT int p3cs_group_last_timings(p3cs_group group, p3cs_timings *out);
 
 /* One-call equivalent of GeomVertexData::animate_vertices(force=true) for a

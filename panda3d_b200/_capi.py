@@ -1,0 +1,311 @@
+"""ctypes binding of libp3cudaskin.so (include/p3cudaskin.h).
+
+This is the only way the package computes anything: there is no Python / numpy / torch
+implementation of the path behind it.  A missing library raises at import of the library
+handle (`lib()`), a missing GPU raises P3csError(P3CS_ERR_NO_DEVICE) at Context creation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .flat import Column, FlatMesh
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libp3cudaskin.so")
+
+P3CS_OK, P3CS_ERR_INVALID, P3CS_ERR_UNSUPPORTED, P3CS_ERR_CUDA, P3CS_ERR_NOMEM, P3CS_ERR_NO_DEVICE = range(6)
+
+# every symbol include/p3cudaskin.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "p3cs_api_version", "p3cs_device_count", "p3cs_last_error",
+    "p3cs_context_create", "p3cs_context_destroy", "p3cs_context_sync", "p3cs_context_stream",
+    "p3cs_mesh_create", "p3cs_mesh_destroy", "p3cs_mesh_num_outputs", "p3cs_mesh_output_stride", "p3cs_mesh_num_rows",
+    "p3cs_group_create", "p3cs_group_destroy", "p3cs_group_output_pitch", "p3cs_group_palettes_device",
+    "p3cs_group_sliders_device", "p3cs_group_output_device", "p3cs_group_set_palettes", "p3cs_group_set_sliders",
+    "p3cs_group_animate", "p3cs_group_read_output", "p3cs_group_read_selection", "p3cs_group_read_blends",
+    "p3cs_group_set_profiling", "p3cs_group_last_timings", "p3cs_animate_vertices", "p3cs_get_api",
+]
+
+
+class P3csError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"p3cudaskin error {code}: {message}")
+        self.code = code
+
+
+class _ArrayDesc(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("stride", C.c_int32), ("is_output", C.c_int32)]
+
+
+class _ColumnDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("array", "start", "num_values", "numeric_type", "contents")]
+
+
+class _MorphDesc(C.Structure):
+    _fields_ = [("slider", C.c_int32), ("base", _ColumnDesc), ("delta", _ColumnDesc),
+                ("num_row_ranges", C.c_int32), ("row_ranges", C.POINTER(C.c_int32))]
+
+
+class _MeshDesc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("num_rows", C.c_int32), ("coordinate_system", C.c_int32),
+        ("num_arrays", C.c_int32), ("arrays", C.POINTER(_ArrayDesc)),
+        ("num_skin_columns", C.c_int32), ("skin_columns", C.POINTER(_ColumnDesc)),
+        ("blend_column", _ColumnDesc),
+        ("num_transforms", C.c_int32), ("num_blends", C.c_int32),
+        ("blend_offsets", C.POINTER(C.c_int32)), ("blend_transform", C.POINTER(C.c_int32)),
+        ("blend_weight", C.POINTER(C.c_float)),
+        ("num_row_ranges", C.c_int32), ("row_ranges", C.POINTER(C.c_int32)),
+        ("num_sliders", C.c_int32), ("num_morphs", C.c_int32), ("morphs", C.POINTER(_MorphDesc)),
+    ]
+
+
+class _GroupBuffers(C.Structure):
+    _fields_ = [("palettes", C.c_void_p), ("sliders", C.c_void_p), ("outputs", C.POINTER(C.c_void_p))]
+
+
+class Timings(C.Structure):
+    _fields_ = [("blend_ms", C.c_float), ("skin_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_int32),
+                ("blend_launches", C.c_int32), ("skin_launches", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libp3cudaskin.so; raises if it has not been built (python -m panda3d_b200.build_ext)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -m panda3d_b200.build_ext` "
+                              "(nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.p3cs_last_error.restype = C.c_char_p
+        L.p3cs_context_stream.restype = C.c_void_p
+        L.p3cs_group_output_pitch.restype = C.c_size_t
+        for n in ("p3cs_group_palettes_device", "p3cs_group_sliders_device", "p3cs_group_output_device"):
+            getattr(L, n).restype = C.c_void_p
+        L.p3cs_get_api.restype = C.c_void_p
+        L.p3cs_context_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.p3cs_context_destroy.argtypes = [C.c_void_p]
+        L.p3cs_context_sync.argtypes = [C.c_void_p]
+        L.p3cs_context_stream.argtypes = [C.c_void_p]
+        L.p3cs_mesh_create.argtypes = [C.c_void_p, C.POINTER(_MeshDesc), C.POINTER(C.c_void_p)]
+        L.p3cs_mesh_destroy.argtypes = [C.c_void_p]
+        L.p3cs_mesh_num_outputs.argtypes = [C.c_void_p]
+        L.p3cs_mesh_output_stride.argtypes = [C.c_void_p, C.c_int]
+        L.p3cs_mesh_num_rows.argtypes = [C.c_void_p]
+        L.p3cs_group_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(_GroupBuffers), C.POINTER(C.c_void_p)]
+        L.p3cs_group_destroy.argtypes = [C.c_void_p]
+        L.p3cs_group_output_pitch.argtypes = [C.c_void_p, C.c_int]
+        L.p3cs_group_palettes_device.argtypes = [C.c_void_p]
+        L.p3cs_group_sliders_device.argtypes = [C.c_void_p]
+        L.p3cs_group_output_device.argtypes = [C.c_void_p, C.c_int]
+        L.p3cs_group_set_palettes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.p3cs_group_set_sliders.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.p3cs_group_animate.argtypes = [C.c_void_p]
+        L.p3cs_group_read_output.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.p3cs_group_read_selection.argtypes = [C.c_void_p, C.c_void_p]
+        L.p3cs_group_read_blends.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.p3cs_group_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.p3cs_group_last_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
+        L.p3cs_animate_vertices.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != P3CS_OK:
+        raise P3csError(rc, lib().p3cs_last_error().decode())
+
+
+def device_count() -> int:
+    return int(lib().p3cs_device_count())
+
+
+def _col(c: Optional[Column]) -> _ColumnDesc:
+    return _ColumnDesc(*c.as_tuple()) if c is not None else _ColumnDesc(-1, 0, 0, 0, 0)
+
+
+def _ip(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class Context:
+    """p3cs_context: one CUDA device + the stream all work is ordered on."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self.handle = C.c_void_p()
+        _check(lib().p3cs_context_create(device, C.c_void_p(stream) if stream else None, C.byref(self.handle)))
+        self.device = device
+
+    @property
+    def stream(self) -> int:
+        return int(lib().p3cs_context_stream(self.handle) or 0)
+
+    def sync(self) -> None:
+        _check(lib().p3cs_context_sync(self.handle))
+
+    def close(self) -> None:
+        if self.handle:
+            lib().p3cs_context_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+def mesh_desc(mesh: FlatMesh, keep: list) -> _MeshDesc:
+    """Fills a p3cs_mesh_desc from a FlatMesh; `keep` receives the buffers that must outlive the call."""
+    d = _MeshDesc()
+    d.struct_size = C.sizeof(_MeshDesc)
+    d.num_rows = mesh.num_rows
+    d.coordinate_system = mesh.coordinate_system
+    arrays = [np.ascontiguousarray(a) for a in mesh.arrays]
+    ad = (_ArrayDesc * max(1, len(arrays)))(*[
+        _ArrayDesc(a.ctypes.data, int(a.shape[1]), 1 if o else 0) for a, o in zip(arrays, mesh.is_output)])
+    cols = (_ColumnDesc * max(1, len(mesh.skin_columns)))(*[_col(c) for c in mesh.skin_columns])
+    bo = np.ascontiguousarray(mesh.blend_offsets, np.int32)
+    bx = np.ascontiguousarray(mesh.blend_transform, np.int32)
+    bw = np.ascontiguousarray(mesh.blend_weight, np.float32)
+    rr = np.ascontiguousarray(mesh.row_ranges, np.int32).reshape(-1)
+    morphs = (_MorphDesc * max(1, len(mesh.morphs)))()
+    for i, mo in enumerate(mesh.morphs):
+        r = np.ascontiguousarray(mo.row_ranges, np.int32).reshape(-1)
+        keep.append(r)
+        morphs[i] = _MorphDesc(mo.slider, _col(mo.base), _col(mo.delta), r.size // 2, _ip(r))
+    keep += [arrays, ad, cols, bo, bx, bw, rr, morphs]
+    d.num_arrays = len(arrays)
+    d.arrays = C.cast(ad, C.POINTER(_ArrayDesc))
+    d.num_skin_columns = len(mesh.skin_columns)
+    d.skin_columns = C.cast(cols, C.POINTER(_ColumnDesc))
+    d.blend_column = _col(mesh.blend_column)
+    d.num_transforms = mesh.num_transforms
+    d.num_blends = mesh.num_blends
+    d.blend_offsets, d.blend_transform = _ip(bo), _ip(bx)
+    d.blend_weight = bw.ctypes.data_as(C.POINTER(C.c_float))
+    d.num_row_ranges = rr.size // 2
+    d.row_ranges = _ip(rr)
+    d.num_sliders = mesh.num_sliders
+    d.num_morphs = len(mesh.morphs)
+    d.morphs = C.cast(morphs, C.POINTER(_MorphDesc))
+    return d
+
+
+class Mesh:
+    """p3cs_mesh: the static half of a GeomVertexData, resident in HBM."""
+
+    def __init__(self, ctx: Context, mesh: FlatMesh):
+        self.ctx = ctx
+        self.flat = mesh
+        keep: list = []
+        d = mesh_desc(mesh, keep)
+        self.handle = C.c_void_p()
+        _check(lib().p3cs_mesh_create(ctx.handle, C.byref(d), C.byref(self.handle)))
+        self.num_outputs = int(lib().p3cs_mesh_num_outputs(self.handle))
+        self.out_strides = [int(lib().p3cs_mesh_output_stride(self.handle, o)) for o in range(self.num_outputs)]
+        self.num_rows = int(lib().p3cs_mesh_num_rows(self.handle))
+
+    def close(self) -> None:
+        if self.handle:
+            lib().p3cs_mesh_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+class Group:
+    """p3cs_group: n animated instances (a crowd of Characters) of one mesh."""
+
+    def __init__(self, mesh: Mesh, num_instances: int = 1, palettes_dev: int = 0, sliders_dev: int = 0,
+                 outputs_dev: Optional[Sequence[int]] = None):
+        self.mesh = mesh
+        self.n = num_instances
+        self.handle = C.c_void_p()
+        bufs = None
+        if palettes_dev or sliders_dev or outputs_dev:
+            outs = (C.c_void_p * max(1, mesh.num_outputs))(*[(outputs_dev[o] if outputs_dev else 0) or None
+                                                             for o in range(mesh.num_outputs)])
+            self._outs = outs
+            bufs = _GroupBuffers(palettes_dev or None, sliders_dev or None, C.cast(outs, C.POINTER(C.c_void_p)))
+        _check(lib().p3cs_group_create(mesh.handle, num_instances, C.byref(bufs) if bufs else None, C.byref(self.handle)))
+
+    # ---- device pointers / geometry
+    def output_pitch(self, o: int = 0) -> int:
+        return int(lib().p3cs_group_output_pitch(self.handle, o))
+
+    @property
+    def palettes_device(self) -> int:
+        return int(lib().p3cs_group_palettes_device(self.handle))
+
+    @property
+    def sliders_device(self) -> int:
+        return int(lib().p3cs_group_sliders_device(self.handle))
+
+    def output_device(self, o: int = 0) -> int:
+        return int(lib().p3cs_group_output_device(self.handle, o))
+
+    # ---- per-frame inputs
+    def set_palettes(self, matrices: np.ndarray, first: int = 0) -> None:
+        m = np.ascontiguousarray(matrices, np.float32)
+        t16 = self.mesh.flat.num_transforms * 16
+        count = m.size // t16 if t16 else 0
+        _check(lib().p3cs_group_set_palettes(self.handle, first, count, m.ctypes.data))
+
+    def set_palettes_ptr(self, host_ptr: int, first: int, count: int) -> None:
+        _check(lib().p3cs_group_set_palettes(self.handle, first, count, host_ptr))
+
+    def set_sliders(self, values: np.ndarray, first: int = 0) -> None:
+        v = np.ascontiguousarray(values, np.float32)
+        s = self.mesh.flat.num_sliders
+        count = v.size // s if s else 0
+        _check(lib().p3cs_group_set_sliders(self.handle, first, count, v.ctypes.data))
+
+    # ---- the hot path
+    def animate(self) -> None:
+        _check(lib().p3cs_group_animate(self.handle))
+
+    def set_profiling(self, enable: bool) -> None:
+        _check(lib().p3cs_group_set_profiling(self.handle, 1 if enable else 0))
+
+    def timings(self) -> Timings:
+        t = Timings()
+        _check(lib().p3cs_group_last_timings(self.handle, C.byref(t)))
+        return t
+
+    # ---- results
+    def read_output(self, o: int = 0, first: int = 0, count: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        count = self.n - first if count is None else count
+        stride = self.mesh.out_strides[o]
+        if out is None:
+            out = np.empty((count, self.mesh.num_rows, stride), np.uint8)
+        _check(lib().p3cs_group_read_output(self.handle, o, first, count, out.ctypes.data))
+        self.mesh.ctx.sync()
+        return out
+
+    def read_output_ptr(self, o: int, first: int, count: int, host_ptr: int) -> None:
+        _check(lib().p3cs_group_read_output(self.handle, o, first, count, host_ptr))
+
+    def read_selection(self) -> np.ndarray:
+        sel = np.empty(self.mesh.num_rows, np.int32)
+        _check(lib().p3cs_group_read_selection(self.handle, sel.ctypes.data))
+        return sel
+
+    def read_blends(self, instance: int = 0) -> np.ndarray:
+        b = np.empty((self.mesh.flat.num_blends, 16), np.float32)
+        _check(lib().p3cs_group_read_blends(self.handle, instance, b.ctypes.data))
+        return b
+
+    def animate_vertices(self, palette: np.ndarray, sliders: Optional[np.ndarray] = None, instance: int = 0) -> List[np.ndarray]:
+        """GeomVertexData::animate_vertices(force=True) with host buffers, one instance, synchronous."""
+        pal = np.ascontiguousarray(palette, np.float32)
+        sl = np.ascontiguousarray(sliders, np.float32) if sliders is not None else None
+        outs = [np.empty((self.mesh.num_rows, s), np.uint8) for s in self.mesh.out_strides]
+        ptrs = (C.c_void_p * max(1, len(outs)))(*[o.ctypes.data for o in outs])
+        _check(lib().p3cs_animate_vertices(self.handle, instance, pal.ctypes.data,
+                                           sl.ctypes.data if sl is not None else None, ptrs))
+        return outs
+
+    def close(self) -> None:
+        if self.handle:
+            lib().p3cs_group_destroy(self.handle)
+            self.handle = C.c_void_p()

@@ -1,0 +1,661 @@
+// p3cs_api.cu -- the C-ABI of libp3cudaskin.so (include/p3cudaskin.h): contexts, the
+// one-time flattening/upload of a GeomVertexData's static half, instance groups and the
+// per-frame animate call.  Host C++; the kernels are in p3cs_kernels.cu.
+#include "../../include/p3cudaskin.h"
+#include "p3cs_kernels.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace p3cs;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t err__ = (expr);                                                                 \
+    if (err__ != cudaSuccess)                                                                   \
+      return fail(err__ == cudaErrorMemoryAllocation ? P3CS_ERR_NOMEM : P3CS_ERR_CUDA,          \
+                  "%s failed: %s", #expr, cudaGetErrorString(err__));                           \
+  } while (0)
+
+// ------------------------------------------------------------------ objects
+struct p3cs_context_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+};
+
+struct p3cs_mesh_s {
+  p3cs_context ctx = nullptr;
+  MeshDev dev{};
+  std::vector<void *> allocations;
+  int index_array = -1;
+};
+
+struct p3cs_group_s {
+  p3cs_mesh mesh = nullptr;
+  int n = 0;
+  int chunk = 1;  // instances per blend/skin launch pair (records scratch stays L2-sized)
+  GroupDev dev{};
+  std::vector<void *> allocations;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> prof;  // event pairs per launch when profiling
+  std::vector<int> prof_kind;     // 0 blend, 1 skin, per pair
+  bool profiling = false;
+  p3cs_timings last{};
+  bool timed = false;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <class T>
+int upload(p3cs_mesh mesh, const T *host, size_t count, const T **out) {
+  *out = nullptr;
+  if (count == 0) count = 1;  // keep pointers non-null
+  void *d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, count * sizeof(T)));
+  mesh->allocations.push_back(d);
+  if (host != nullptr) CUDA_TRY(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, mesh->ctx->stream));
+  *out = static_cast<const T *>(d);
+  return P3CS_OK;
+}
+
+int numeric_bytes(int nt) {
+  switch (nt) {
+  case P3CS_NT_UINT8: case P3CS_NT_INT8: return 1;
+  case P3CS_NT_UINT16: case P3CS_NT_INT16: return 2;
+  case P3CS_NT_FLOAT64: return 8;
+  default: return 4;
+  }
+}
+
+size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// ------------------------------------------------------------------ library
+extern "C" int p3cs_api_version(void) { return P3CS_API_VERSION; }
+
+extern "C" int p3cs_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" const char *p3cs_last_error(void) { return g_last_error.c_str(); }
+
+// ------------------------------------------------------------------ context
+extern "C" int p3cs_context_create(int device, void *stream, p3cs_context *out) {
+  if (out == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_context_create: out is NULL");
+  *out = nullptr;
+  int n = p3cs_device_count();
+  if (n <= 0) return fail(P3CS_ERR_NO_DEVICE, "no CUDA device available (this backend has no CPU fallback)");
+  if (device < 0 || device >= n) return fail(P3CS_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+  CUDA_TRY(cudaSetDevice(device));
+  p3cs_context ctx = new (std::nothrow) p3cs_context_s;
+  if (ctx == nullptr) return fail(P3CS_ERR_NOMEM, "out of host memory");
+  ctx->device = device;
+  if (stream != nullptr) {
+    ctx->stream = static_cast<cudaStream_t>(stream);
+  } else {
+    cudaError_t err = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) {
+      delete ctx;
+      return fail(P3CS_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(err));
+    }
+    ctx->owns_stream = true;
+  }
+  *out = ctx;
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_context_destroy(p3cs_context ctx) {
+  if (ctx == nullptr) return P3CS_OK;
+  DeviceGuard g(ctx->device);
+  if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_context_sync(p3cs_context ctx) {
+  if (ctx == nullptr) return fail(P3CS_ERR_INVALID, "context is NULL");
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return P3CS_OK;
+}
+
+extern "C" void *p3cs_context_stream(p3cs_context ctx) { return ctx ? ctx->stream : nullptr; }
+
+// ------------------------------------------------------------------ mesh
+static int check_column(const p3cs_mesh_desc *d, const p3cs_column_desc &c, const char *what) {
+  if (c.array < 0 || c.array >= d->num_arrays) return fail(P3CS_ERR_INVALID, "%s: array %d out of range", what, c.array);
+  const int stride = d->arrays[c.array].stride;
+  if (c.start < 0 || c.num_values < 1 || c.start + c.num_values * numeric_bytes(c.numeric_type) > stride)
+    return fail(P3CS_ERR_INVALID, "%s: column [%d,+%d x %d) exceeds stride %d", what, c.start, c.num_values,
+                numeric_bytes(c.numeric_type), stride);
+  return P3CS_OK;
+}
+
+static int check_ranges(const int32_t *ranges, int count, int num_rows, const char *what) {
+  int prev_end = 0;
+  for (int i = 0; i < count; ++i) {
+    const int b = ranges[2 * i], e = ranges[2 * i + 1];
+    if (b < prev_end || e <= b || e > num_rows)
+      return fail(P3CS_ERR_INVALID, "%s: subrange %d = [%d,%d) is not a sorted, disjoint, non-empty range within %d rows", what, i, b, e, num_rows);
+    prev_end = e;
+  }
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_mesh *out) {
+  if (out == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_mesh_create: out is NULL");
+  *out = nullptr;
+  if (ctx == nullptr || d == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_mesh_create: NULL argument");
+  if (d->struct_size != sizeof(p3cs_mesh_desc))
+    return fail(P3CS_ERR_INVALID, "p3cs_mesh_desc::struct_size %u != %zu (header mismatch)", d->struct_size, sizeof(p3cs_mesh_desc));
+  if (d->num_rows < 0 || d->num_arrays < 0 || (d->num_arrays > 0 && d->arrays == nullptr))
+    return fail(P3CS_ERR_INVALID, "bad num_rows / arrays");
+  int cs = d->coordinate_system == 0 ? P3CS_CS_ZUP_RIGHT : d->coordinate_system;
+  if (cs < P3CS_CS_ZUP_RIGHT || cs > P3CS_CS_YUP_LEFT) return fail(P3CS_ERR_INVALID, "bad coordinate_system %d", cs);
+  const int N = d->num_rows;
+  DeviceGuard g(ctx->device);
+
+  p3cs_mesh mesh = new (std::nothrow) p3cs_mesh_s;
+  if (mesh == nullptr) return fail(P3CS_ERR_NOMEM, "out of host memory");
+  mesh->ctx = ctx;
+  MeshDev &m = mesh->dev;
+  m.num_rows = N;
+  m.coordinate_system = cs;
+  m.num_transforms = d->num_transforms;
+  m.num_blends = d->num_blends;
+  m.num_sliders = d->num_sliders;
+  int rc = P3CS_OK;
+  auto bail = [&](int code) {
+    p3cs_mesh_destroy(mesh);
+    return code;
+  };
+
+  // ---- output arrays: static image uploaded once (replaces the per-frame copy_from)
+  std::vector<int> out_of_array(d->num_arrays, -1);
+  for (int a = 0; a < d->num_arrays; ++a) {
+    const p3cs_array_desc &ad = d->arrays[a];
+    if (ad.stride <= 0 || (N > 0 && ad.data == nullptr)) return bail(fail(P3CS_ERR_INVALID, "array %d: bad stride/data", a));
+    if (!ad.is_output) continue;
+    if (m.num_outputs >= kMaxOutputs) return bail(fail(P3CS_ERR_UNSUPPORTED, "more than %d output arrays", kMaxOutputs));
+    if (ad.stride % 4 != 0) return bail(fail(P3CS_ERR_UNSUPPORTED, "output array %d: stride %d is not a multiple of 4", a, ad.stride));
+    out_of_array[a] = m.num_outputs;
+    m.stride[m.num_outputs] = ad.stride;
+    if ((rc = upload<uint8_t>(mesh, static_cast<const uint8_t *>(ad.data), (size_t)N * ad.stride, &m.src[m.num_outputs])) != P3CS_OK) return bail(rc);
+    ++m.num_outputs;
+  }
+
+  // ---- dynamic columns: skinned columns, then morph bases
+  auto find_dyn = [&](int output, int start) {
+    for (int c = 0; c < m.num_dyn; ++c)
+      if (m.dyn[c].output == output && m.dyn[c].start == start) return c;
+    return -1;
+  };
+  const bool has_blend = d->blend_column.array >= 0 && d->num_skin_columns > 0;
+  for (int i = 0; i < d->num_skin_columns; ++i) {
+    const p3cs_column_desc &c = d->skin_columns[i];
+    if ((rc = check_column(d, c, "skin column")) != P3CS_OK) return bail(rc);
+    if (out_of_array[c.array] < 0) return bail(fail(P3CS_ERR_INVALID, "skin column %d lives in a non-output array", i));
+    if (c.numeric_type != P3CS_NT_FLOAT32 || (c.num_values != 3 && c.num_values != 4))
+      return bail(fail(P3CS_ERR_UNSUPPORTED, "skin column %d: only float32 x 3 / x 4 columns are supported (got type %d x %d)", i, c.numeric_type, c.num_values));
+    if (c.start % 4 != 0) return bail(fail(P3CS_ERR_UNSUPPORTED, "skin column %d: start %d not 4-byte aligned", i, c.start));
+    int skin = c.contents == P3CS_C_POINT ? 1 : c.contents == P3CS_C_VECTOR ? 2 : c.contents == P3CS_C_NORMAL ? 3 : 0;
+    if (skin == 0) return bail(fail(P3CS_ERR_INVALID, "skin column %d: contents %d is not point/vector/normal", i, c.contents));
+    if (m.num_dyn >= kMaxDynColumns) return bail(fail(P3CS_ERR_UNSUPPORTED, "more than %d animated columns", kMaxDynColumns));
+    DynColumn &dc = m.dyn[m.num_dyn++];
+    dc.output = (int16_t)out_of_array[c.array];
+    dc.start = (int16_t)c.start;
+    dc.num_values = (int8_t)c.num_values;
+    dc.skin = (int8_t)skin;
+    dc.homogeneous = 0;
+    if (c.num_values == 4) m.full_records = 1;
+  }
+
+  // ---- transform_blend index column -> dense u16/u32
+  if (d->blend_column.array >= 0) {
+    const p3cs_column_desc &bc = d->blend_column;
+    if ((rc = check_column(d, bc, "transform_blend column")) != P3CS_OK) return bail(rc);
+    if (bc.numeric_type != P3CS_NT_UINT8 && bc.numeric_type != P3CS_NT_UINT16 && bc.numeric_type != P3CS_NT_UINT32)
+      return bail(fail(P3CS_ERR_UNSUPPORTED, "transform_blend column of numeric type %d", bc.numeric_type));
+    if (d->num_blends < 0 || d->num_transforms < 0 || d->blend_offsets == nullptr)
+      return bail(fail(P3CS_ERR_INVALID, "blend table missing"));
+    if ((rc = check_ranges(d->row_ranges, d->num_row_ranges, N, "TransformBlendTable rows")) != P3CS_OK) return bail(rc);
+    const int nnz = d->blend_offsets[d->num_blends];
+    if (d->blend_offsets[0] != 0) return bail(fail(P3CS_ERR_INVALID, "blend_offsets[0] != 0"));
+    for (int b = 0; b < d->num_blends; ++b)
+      if (d->blend_offsets[b + 1] < d->blend_offsets[b]) return bail(fail(P3CS_ERR_INVALID, "blend_offsets not monotonic at %d", b));
+    for (int e = 0; e < nnz; ++e)
+      if (d->blend_transform[e] < 0 || d->blend_transform[e] >= d->num_transforms)
+        return bail(fail(P3CS_ERR_INVALID, "blend entry %d refers to transform %d outside the palette (%d)", e, d->blend_transform[e], d->num_transforms));
+
+    const uint8_t *base = static_cast<const uint8_t *>(d->arrays[bc.array].data) + bc.start;
+    const int istride = d->arrays[bc.array].stride;
+    const bool wide = bc.numeric_type == P3CS_NT_UINT32;
+    std::vector<uint16_t> idx16;
+    std::vector<uint32_t> idx32;
+    if (wide) idx32.resize(std::max(N, 1)); else idx16.resize(std::max(N, 1));
+    for (int r = 0; r < N; ++r) {
+      const uint8_t *p = base + (size_t)r * istride;
+      uint32_t v;
+      if (bc.numeric_type == P3CS_NT_UINT8) v = *p;
+      else if (bc.numeric_type == P3CS_NT_UINT16) { uint16_t t; memcpy(&t, p, 2); v = t; }
+      else memcpy(&v, p, 4);
+      if (wide) idx32[r] = v; else idx16[r] = (uint16_t)v;
+    }
+    // every row the reference would transform must select an existing blend
+    bool full = d->num_row_ranges == 1 && d->row_ranges[0] == 0 && d->row_ranges[1] == N;
+    std::vector<uint32_t> mask;
+    if (!full) mask.assign(((size_t)N + 31) / 32 + 1, 0u);
+    for (int i = 0; i < d->num_row_ranges; ++i)
+      for (int r = d->row_ranges[2 * i]; r < d->row_ranges[2 * i + 1]; ++r) {
+        uint32_t v = wide ? idx32[r] : idx16[r];
+        if (v >= (uint32_t)d->num_blends)
+          return bail(fail(P3CS_ERR_INVALID, "row %d selects blend %u but the table has %d blends", r, v, d->num_blends));
+        if (!full) mask[r >> 5] |= 1u << (r & 31);
+      }
+    m.index_bytes = wide ? 4 : 2;
+    const void *dev_index = nullptr;
+    if (wide) { const uint32_t *p; rc = upload<uint32_t>(mesh, idx32.data(), idx32.size(), &p); dev_index = p; }
+    else { const uint16_t *p; rc = upload<uint16_t>(mesh, idx16.data(), idx16.size(), &p); dev_index = p; }
+    if (rc != P3CS_OK) return bail(rc);
+    m.index = dev_index;
+    if (!full && (rc = upload<uint32_t>(mesh, mask.data(), mask.size(), &m.rows_mask)) != P3CS_OK) return bail(rc);
+    if ((rc = upload<int>(mesh, d->blend_offsets, (size_t)d->num_blends + 1, &m.blend_offsets)) != P3CS_OK) return bail(rc);
+    if ((rc = upload<int>(mesh, d->blend_transform, (size_t)nnz, &m.blend_transform)) != P3CS_OK) return bail(rc);
+    if ((rc = upload<float>(mesh, d->blend_weight, (size_t)nnz, &m.blend_weight)) != P3CS_OK) return bail(rc);
+    (void)has_blend;
+  } else {
+    m.num_blends = 0;
+  }
+
+  // ---- morphs: dense delta columns + slider rows -> per-row CSR, in the reference's
+  // iteration order so rows hit by several morphs add up in the same order
+  if (d->num_morphs > 0) {
+    if (d->morphs == nullptr || d->num_sliders <= 0) return bail(fail(P3CS_ERR_INVALID, "morphs without sliders"));
+    if (d->num_sliders > 65536) return bail(fail(P3CS_ERR_UNSUPPORTED, "more than 65536 sliders"));
+    std::vector<int> counts((size_t)N + 1, 0);
+    std::vector<int> morph_dyn(d->num_morphs, -1);
+    for (int mi = 0; mi < d->num_morphs; ++mi) {
+      const p3cs_morph_desc &mo = d->morphs[mi];
+      if (mo.slider < 0 || mo.slider >= d->num_sliders) return bail(fail(P3CS_ERR_INVALID, "morph %d: slider %d out of range", mi, mo.slider));
+      if ((rc = check_column(d, mo.base, "morph base column")) != P3CS_OK) return bail(rc);
+      if ((rc = check_column(d, mo.delta, "morph delta column")) != P3CS_OK) return bail(rc);
+      if ((rc = check_ranges(mo.row_ranges, mo.num_row_ranges, N, "slider rows")) != P3CS_OK) return bail(rc);
+      if (out_of_array[mo.base.array] < 0) return bail(fail(P3CS_ERR_INVALID, "morph %d: base column in a non-output array", mi));
+      if (mo.base.numeric_type != P3CS_NT_FLOAT32 || mo.delta.numeric_type != P3CS_NT_FLOAT32 || mo.base.num_values > 4 ||
+          mo.base.start % 4 != 0 || mo.delta.start % 4 != 0)
+        return bail(fail(P3CS_ERR_UNSUPPORTED, "morph %d: only 4-byte aligned float32 base/delta columns are supported", mi));
+      int c = find_dyn(out_of_array[mo.base.array], mo.base.start);
+      if (c < 0) {
+        if (m.num_dyn >= kMaxDynColumns) return bail(fail(P3CS_ERR_UNSUPPORTED, "more than %d animated columns", kMaxDynColumns));
+        c = m.num_dyn++;
+        m.dyn[c].output = (int16_t)out_of_array[mo.base.array];
+        m.dyn[c].start = (int16_t)mo.base.start;
+        m.dyn[c].num_values = (int8_t)mo.base.num_values;
+        m.dyn[c].skin = 0;
+      }
+      m.dyn[c].homogeneous = (mo.base.num_values == 4 && (mo.base.contents == P3CS_C_POINT || mo.base.contents == P3CS_C_TEXCOORD)) ? 1 : 0;
+      morph_dyn[mi] = c;
+      for (int i = 0; i < mo.num_row_ranges; ++i)
+        for (int r = mo.row_ranges[2 * i]; r < mo.row_ranges[2 * i + 1]; ++r) counts[r + 1]++;
+    }
+    for (int r = 0; r < N; ++r) counts[r + 1] += counts[r];
+    const size_t total = counts[N];
+    std::vector<uint32_t> keys(std::max<size_t>(total, 1));
+    std::vector<float4> deltas(std::max<size_t>(total, 1));
+    std::vector<int> cursor(counts.begin(), counts.end() - 1);
+    for (int mi = 0; mi < d->num_morphs; ++mi) {
+      const p3cs_morph_desc &mo = d->morphs[mi];
+      const uint8_t *dbase = static_cast<const uint8_t *>(d->arrays[mo.delta.array].data) + mo.delta.start;
+      const int dstride = d->arrays[mo.delta.array].stride;
+      const int dn = std::min(mo.delta.num_values, mo.base.num_values == 4 && !m.dyn[morph_dyn[mi]].homogeneous ? 4 : 3);
+      for (int i = 0; i < mo.num_row_ranges; ++i)
+        for (int r = mo.row_ranges[2 * i]; r < mo.row_ranges[2 * i + 1]; ++r) {
+          float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // Packer::get_data3f/4f pad with 0 (geomVertexColumn.cxx:718-737)
+          memcpy(v, dbase + (size_t)r * dstride, (size_t)dn * 4);
+          const int e = cursor[r]++;
+          keys[e] = ((uint32_t)morph_dyn[mi] << 16) | (uint32_t)mo.slider;
+          deltas[e] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+    m.has_morphs = 1;
+    if ((rc = upload<int>(mesh, counts.data(), counts.size(), &m.morph_row_offsets)) != P3CS_OK) return bail(rc);
+    if ((rc = upload<uint32_t>(mesh, keys.data(), keys.size(), &m.morph_keys)) != P3CS_OK) return bail(rc);
+    if ((rc = upload<float4>(mesh, deltas.data(), deltas.size(), &m.morph_deltas)) != P3CS_OK) return bail(rc);
+  }
+  // uploads read from host vectors that die at scope exit: finish them now
+  cudaError_t err = cudaStreamSynchronize(ctx->stream);
+  if (err != cudaSuccess) return bail(fail(P3CS_ERR_CUDA, "mesh upload failed: %s", cudaGetErrorString(err)));
+  *out = mesh;
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_mesh_destroy(p3cs_mesh mesh) {
+  if (mesh == nullptr) return P3CS_OK;
+  DeviceGuard g(mesh->ctx->device);
+  for (void *p : mesh->allocations) cudaFree(p);
+  delete mesh;
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_mesh_num_outputs(p3cs_mesh mesh) { return mesh ? mesh->dev.num_outputs : 0; }
+extern "C" int p3cs_mesh_output_stride(p3cs_mesh mesh, int o) {
+  return (mesh && o >= 0 && o < mesh->dev.num_outputs) ? mesh->dev.stride[o] : 0;
+}
+extern "C" int p3cs_mesh_num_rows(p3cs_mesh mesh) { return mesh ? mesh->dev.num_rows : 0; }
+
+// ------------------------------------------------------------------ group
+static size_t record_floats(const MeshDev &m) { return m.full_records ? kRecFull : kRecCompact; }
+
+extern "C" int p3cs_group_create(p3cs_mesh mesh, int n, const p3cs_group_buffers *buffers, p3cs_group *out) {
+  if (out == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_create: out is NULL");
+  *out = nullptr;
+  if (mesh == nullptr || n <= 0) return fail(P3CS_ERR_INVALID, "p3cs_group_create: bad mesh / num_instances");
+  DeviceGuard g(mesh->ctx->device);
+  const MeshDev &m = mesh->dev;
+  p3cs_group grp = new (std::nothrow) p3cs_group_s;
+  if (grp == nullptr) return fail(P3CS_ERR_NOMEM, "out of host memory");
+  grp->mesh = mesh;
+  grp->n = n;
+  auto bail = [&](int code) {
+    p3cs_group_destroy(grp);
+    return code;
+  };
+  auto alloc = [&](size_t bytes, void **p) -> int {
+    CUDA_TRY(cudaMalloc(p, std::max<size_t>(bytes, 256)));
+    grp->allocations.push_back(*p);
+    return P3CS_OK;
+  };
+  int rc;
+  void *p = nullptr;
+  if (buffers != nullptr && buffers->palettes != nullptr) p = buffers->palettes;
+  else if ((rc = alloc((size_t)n * m.num_transforms * 64, &p)) != P3CS_OK) return bail(rc);
+  grp->dev.palettes = static_cast<const float *>(p);
+  if (buffers != nullptr && buffers->sliders != nullptr) p = buffers->sliders;
+  else {
+    if ((rc = alloc((size_t)n * m.num_sliders * 4, &p)) != P3CS_OK) return bail(rc);
+    cudaMemsetAsync(p, 0, std::max<size_t>((size_t)n * m.num_sliders * 4, 256), mesh->ctx->stream);
+  }
+  grp->dev.sliders = static_cast<const float *>(p);
+  for (int o = 0; o < m.num_outputs; ++o) {
+    grp->dev.pitch[o] = round_up((size_t)m.num_rows * m.stride[o], 256);
+    if (buffers != nullptr && buffers->outputs != nullptr && buffers->outputs[o] != nullptr) p = buffers->outputs[o];
+    else if ((rc = alloc(grp->dev.pitch[o] * n, &p)) != P3CS_OK) return bail(rc);
+    grp->dev.out[o] = static_cast<uint8_t *>(p);
+  }
+  // records scratch: sized so one chunk of instances stays L2-resident between K1 and K2
+  const size_t rec_bytes = std::max<size_t>((size_t)m.num_blends * record_floats(m) * 4, 4);
+  const size_t budget = 32u << 20;
+  grp->chunk = (int)std::max<size_t>(1, std::min<size_t>({(size_t)n, budget / rec_bytes, (size_t)65535}));
+  if ((rc = alloc(rec_bytes * grp->chunk, &p)) != P3CS_OK) return bail(rc);
+  grp->dev.records = static_cast<float *>(p);
+  for (auto &e : grp->ev) {
+    cudaError_t err = cudaEventCreate(&e);
+    if (err != cudaSuccess) return bail(fail(P3CS_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(err)));
+  }
+  *out = grp;
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_group_destroy(p3cs_group grp) {
+  if (grp == nullptr) return P3CS_OK;
+  DeviceGuard g(grp->mesh->ctx->device);
+  cudaStreamSynchronize(grp->mesh->ctx->stream);
+  for (void *p : grp->allocations) cudaFree(p);
+  for (auto e : grp->ev)
+    if (e) cudaEventDestroy(e);
+  for (auto e : grp->prof) cudaEventDestroy(e);
+  delete grp;
+  return P3CS_OK;
+}
+
+extern "C" size_t p3cs_group_output_pitch(p3cs_group grp, int o) {
+  return (grp && o >= 0 && o < grp->mesh->dev.num_outputs) ? grp->dev.pitch[o] : 0;
+}
+extern "C" void *p3cs_group_palettes_device(p3cs_group grp) { return grp ? const_cast<float *>(grp->dev.palettes) : nullptr; }
+extern "C" void *p3cs_group_sliders_device(p3cs_group grp) { return grp ? const_cast<float *>(grp->dev.sliders) : nullptr; }
+extern "C" void *p3cs_group_output_device(p3cs_group grp, int o) {
+  return (grp && o >= 0 && o < grp->mesh->dev.num_outputs) ? grp->dev.out[o] : nullptr;
+}
+
+static int check_span(p3cs_group grp, int first, int count, const char *what) {
+  if (grp == nullptr) return fail(P3CS_ERR_INVALID, "%s: group is NULL", what);
+  if (first < 0 || count < 0 || first + count > grp->n)
+    return fail(P3CS_ERR_INVALID, "%s: instances [%d,%d) outside the group of %d", what, first, first + count, grp->n);
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_group_set_palettes(p3cs_group grp, int first, int count, const float *host) {
+  int rc = check_span(grp, first, count, "p3cs_group_set_palettes");
+  if (rc != P3CS_OK) return rc;
+  if (host == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_set_palettes: host pointer is NULL");
+  DeviceGuard g(grp->mesh->ctx->device);
+  const size_t per = (size_t)grp->mesh->dev.num_transforms * 16;
+  if (per * count == 0) return P3CS_OK;
+  CUDA_TRY(cudaMemcpyAsync(const_cast<float *>(grp->dev.palettes) + per * first, host, per * count * 4, cudaMemcpyHostToDevice,
+                           grp->mesh->ctx->stream));
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_group_set_sliders(p3cs_group grp, int first, int count, const float *host) {
+  int rc = check_span(grp, first, count, "p3cs_group_set_sliders");
+  if (rc != P3CS_OK) return rc;
+  const size_t per = (size_t)grp->mesh->dev.num_sliders;
+  if (per * count == 0) return P3CS_OK;
+  if (host == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_set_sliders: host pointer is NULL");
+  DeviceGuard g(grp->mesh->ctx->device);
+  CUDA_TRY(cudaMemcpyAsync(const_cast<float *>(grp->dev.sliders) + per * first, host, per * count * 4, cudaMemcpyHostToDevice,
+                           grp->mesh->ctx->stream));
+  return P3CS_OK;
+}
+
+static int prof_event(p3cs_group grp, size_t i, cudaEvent_t *out) {
+  while (grp->prof.size() <= i) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    grp->prof.push_back(e);
+  }
+  *out = grp->prof[i];
+  return P3CS_OK;
+}
+
+static int animate_range(p3cs_group grp, int first, int count, bool timed) {
+  const MeshDev &m = grp->mesh->dev;
+  cudaStream_t s = grp->mesh->ctx->stream;
+  const bool prof = timed && grp->profiling;
+  int launches = 0, nblend = 0, nskin = 0, rc;
+  size_t pe = 0;
+  cudaEvent_t e0, e1;
+  grp->prof_kind.clear();
+  if (timed) CUDA_TRY(cudaEventRecord(grp->ev[0], s));
+  for (int c0 = first; c0 < first + count; c0 += grp->chunk) {
+    const int cn = std::min(grp->chunk, first + count - c0);
+    if (m.num_blends > 0) {
+      if (prof) {
+        if ((rc = prof_event(grp, pe++, &e0)) != P3CS_OK || (rc = prof_event(grp, pe++, &e1)) != P3CS_OK) return rc;
+        CUDA_TRY(cudaEventRecord(e0, s));
+      }
+      launch_blend(m, grp->dev, c0, cn, s);
+      if (prof) {
+        CUDA_TRY(cudaEventRecord(e1, s));
+        grp->prof_kind.push_back(0);
+      }
+      ++launches;
+      ++nblend;
+    }
+    if (prof) {
+      if ((rc = prof_event(grp, pe++, &e0)) != P3CS_OK || (rc = prof_event(grp, pe++, &e1)) != P3CS_OK) return rc;
+      CUDA_TRY(cudaEventRecord(e0, s));
+    }
+    launch_skin(m, grp->dev, c0, cn, s);
+    if (prof) {
+      CUDA_TRY(cudaEventRecord(e1, s));
+      grp->prof_kind.push_back(1);
+    }
+    ++launches;
+    ++nskin;
+  }
+  if (timed) CUDA_TRY(cudaEventRecord(grp->ev[1], s));
+  CUDA_TRY(cudaGetLastError());
+  grp->last.launches = launches;
+  grp->last.blend_launches = nblend;
+  grp->last.skin_launches = nskin;
+  grp->last.blend_ms = grp->last.skin_ms = -1.0f;
+  grp->timed = timed;
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_group_animate(p3cs_group grp) {
+  if (grp == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_animate: group is NULL");
+  DeviceGuard g(grp->mesh->ctx->device);
+  return animate_range(grp, 0, grp->n, true);
+}
+
+extern "C" int p3cs_group_set_profiling(p3cs_group grp, int enable) {
+  if (grp == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_set_profiling: group is NULL");
+  grp->profiling = enable != 0;
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_group_last_timings(p3cs_group grp, p3cs_timings *out) {
+  if (grp == nullptr || out == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_last_timings: NULL argument");
+  DeviceGuard g(grp->mesh->ctx->device);
+  if (grp->timed) {
+    CUDA_TRY(cudaEventSynchronize(grp->ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&grp->last.total_ms, grp->ev[0], grp->ev[1]));
+    if (!grp->prof_kind.empty()) {
+      float sum[2] = {0.0f, 0.0f};
+      for (size_t i = 0; i < grp->prof_kind.size(); ++i) {
+        float ms = 0.0f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, grp->prof[2 * i], grp->prof[2 * i + 1]));
+        sum[grp->prof_kind[i]] += ms;
+      }
+      grp->last.blend_ms = sum[0];
+      grp->last.skin_ms = sum[1];
+    }
+  }
+  *out = grp->last;
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_group_read_output(p3cs_group grp, int o, int first, int count, void *host_dst) {
+  int rc = check_span(grp, first, count, "p3cs_group_read_output");
+  if (rc != P3CS_OK) return rc;
+  const MeshDev &m = grp->mesh->dev;
+  if (o < 0 || o >= m.num_outputs || host_dst == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_read_output: bad output / destination");
+  DeviceGuard g(grp->mesh->ctx->device);
+  const size_t row_bytes = (size_t)m.num_rows * m.stride[o];
+  if (row_bytes == 0 || count == 0) return P3CS_OK;
+  CUDA_TRY(cudaMemcpy2DAsync(host_dst, row_bytes, grp->dev.out[o] + grp->dev.pitch[o] * first, grp->dev.pitch[o], row_bytes, count,
+                             cudaMemcpyDeviceToHost, grp->mesh->ctx->stream));
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_group_read_selection(p3cs_group grp, int32_t *host_dst) {
+  if (grp == nullptr || host_dst == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_read_selection: NULL argument");
+  const MeshDev &m = grp->mesh->dev;
+  DeviceGuard g(grp->mesh->ctx->device);
+  cudaStream_t s = grp->mesh->ctx->stream;
+  int32_t *sel = nullptr;
+  CUDA_TRY(cudaMalloc(&sel, std::max<size_t>((size_t)m.num_rows * 4, 4)));
+  GroupDev tmp = grp->dev;
+  tmp.selection = sel;
+  if (m.num_blends > 0) launch_blend(m, tmp, 0, 1, s);
+  launch_skin(m, tmp, 0, 1, s);
+  cudaError_t err = cudaMemcpyAsync(host_dst, sel, (size_t)m.num_rows * 4, cudaMemcpyDeviceToHost, s);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+  cudaFree(sel);
+  if (err != cudaSuccess) return fail(P3CS_ERR_CUDA, "p3cs_group_read_selection: %s", cudaGetErrorString(err));
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_group_read_blends(p3cs_group grp, int instance, float *host_dst) {
+  int rc = check_span(grp, instance, 1, "p3cs_group_read_blends");
+  if (rc != P3CS_OK) return rc;
+  if (host_dst == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_read_blends: destination is NULL");
+  const MeshDev &m = grp->mesh->dev;
+  if (m.num_blends == 0) return P3CS_OK;
+  DeviceGuard g(grp->mesh->ctx->device);
+  cudaStream_t s = grp->mesh->ctx->stream;
+  launch_blend(m, grp->dev, instance, 1, s);
+  const size_t rf = record_floats(m);
+  std::vector<float> rec((size_t)m.num_blends * rf);
+  CUDA_TRY(cudaMemcpyAsync(rec.data(), grp->dev.records, rec.size() * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (int b = 0; b < m.num_blends; ++b) {
+    const float *r = rec.data() + (size_t)b * rf;
+    float *o = host_dst + (size_t)b * 16;
+    if (m.full_records) {
+      memcpy(o, r, 64);
+    } else {
+      // compact records keep rows 0..3 x columns 0..2; column 3 is not stored
+      for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 3; ++j) o[i * 4 + j] = r[i * 3 + j];
+        o[i * 4 + 3] = NAN;
+      }
+    }
+  }
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_animate_vertices(p3cs_group grp, int instance, const float *host_palette, const float *host_sliders,
+                                     void *const *host_outputs) {
+  int rc = check_span(grp, instance, 1, "p3cs_animate_vertices");
+  if (rc != P3CS_OK) return rc;
+  const MeshDev &m = grp->mesh->dev;
+  if (m.num_transforms > 0 && (rc = p3cs_group_set_palettes(grp, instance, 1, host_palette)) != P3CS_OK) return rc;
+  if (m.num_sliders > 0 && (rc = p3cs_group_set_sliders(grp, instance, 1, host_sliders)) != P3CS_OK) return rc;
+  DeviceGuard g(grp->mesh->ctx->device);
+  if ((rc = animate_range(grp, instance, 1, false)) != P3CS_OK) return rc;
+  if (host_outputs != nullptr)
+    for (int o = 0; o < m.num_outputs; ++o)
+      if (host_outputs[o] != nullptr && (rc = p3cs_group_read_output(grp, o, instance, 1, host_outputs[o])) != P3CS_OK) return rc;
+  return p3cs_context_sync(grp->mesh->ctx);
+}
+
+// ------------------------------------------------------------------ plugin table
+extern "C" const p3cs_api *p3cs_get_api(void) {
+  static const p3cs_api api = {
+      P3CS_API_VERSION,        p3cs_device_count,  p3cs_last_error,        p3cs_context_create, p3cs_context_destroy,
+      p3cs_context_sync,       p3cs_mesh_create,   p3cs_mesh_destroy,      p3cs_group_create,   p3cs_group_destroy,
+      p3cs_group_set_palettes, p3cs_group_set_sliders, p3cs_group_animate, p3cs_group_read_output, p3cs_animate_vertices};
+  return &api;
+}

@@ -1,0 +1,65 @@
+// p3cs_kernels.cuh -- launch parameters shared by the kernels and the C-ABI host code.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace p3cs {
+
+constexpr int kMaxOutputs = 4;      // output arrays per mesh
+constexpr int kMaxDynColumns = 12;  // skinned and/or morphed columns per mesh
+
+// Per-blend record written by the blend kernel and gathered by the skin kernel.
+//   compact (no 4-component skin column): 12 floats M (rows 0..3 x cols 0..2), 9 floats N
+//   (normal matrix 3x3), 1 float flag (normalize) = 22 floats = 88 bytes;
+//   full: 16 floats M, 16 floats X, flag, padded to 36 floats = 144 bytes.
+constexpr int kRecCompact = 22;
+constexpr int kRecFull = 36;
+
+// A column that changes per frame: skinned (point/vector/normal) and/or a morph base.
+struct DynColumn {
+  int16_t output;      // output array index
+  int16_t start;       // byte offset in the row
+  int8_t num_values;   // 1..4
+  int8_t skin;         // 0 none, 1 point, 2 vector, 3 normal
+  int8_t homogeneous;  // morph: scale deltas by w (C_point / C_texcoord with 4 values)
+  int8_t pad;
+};
+
+struct MeshDev {
+  int num_rows;
+  int num_blends;
+  int num_transforms;
+  int num_sliders;
+  int coordinate_system;
+  int num_outputs;
+  int num_dyn;
+  int full_records;  // 1: kRecFull layout
+  int index_bytes;   // 2 or 4 (0: no blend table)
+  int has_morphs;
+  DynColumn dyn[kMaxDynColumns];
+  int stride[kMaxOutputs];
+  const uint8_t *src[kMaxOutputs];  // static image of each output array (num_rows*stride)
+  const void *index;                // dense transform_blend column, u16 or u32 per row
+  const uint32_t *rows_mask;        // bit per row; NULL = every row is in get_rows()
+  const int *blend_offsets;         // CSR of the TransformBlendTable
+  const int *blend_transform;
+  const float *blend_weight;
+  const int *morph_row_offsets;     // per-row CSR of morph entries (num_rows+1)
+  const uint32_t *morph_keys;       // (dyn column << 16) | slider
+  const float4 *morph_deltas;
+};
+
+struct GroupDev {
+  const float *palettes;  // [n][T][16]
+  const float *sliders;   // [n][S]
+  float *records;         // [chunk][B][rec]
+  uint8_t *out[kMaxOutputs];
+  size_t pitch[kMaxOutputs];
+  int32_t *selection;     // optional [num_rows] debug/parity output (instance 0 of the launch)
+};
+
+void launch_blend(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);
+void launch_skin(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);
+int skin_rows_per_tile(const MeshDev &mesh);
+
+}  // namespace p3cs

@@ -1,0 +1,208 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (libp3cudaskin.so), against
+  (1) the committed golden fixtures = bytes the UNMODIFIED reference produced, and
+  (2) the oracle (oracle/skin_oracle.c, itself pinned bit-exact to the reference) on seeded inputs.
+
+Bars (BASELINE.json north_star): blend-index / row selection bit-exact; float32 outputs within
+1e-5 relative (tolerance written below); static bytes identical.  The kernels are built without
+FMA contraction, so in practice every byte matches except through the sinf/cosf/atan2f of the
+uniform-scale normal branch; the tests assert the contract and report the max-abs error.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_ids, golden_paths
+from oracle import oracle
+from panda3d_b200 import _capi, flat as F, synth
+from panda3d_b200.casefile import load_case
+from panda3d_b200.flat import mesh_from_case
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5  # north_star: float32 positions/normals agree within 1e-5 relative
+
+
+def dynamic_float_mask(mesh):
+    """Byte mask per output array of the float columns the path may modify."""
+    masks = []
+    for a in mesh.output_arrays:
+        m = np.zeros(mesh.strides[a], bool)
+        cols = list(mesh.skin_columns) + [mo.base for mo in mesh.morphs]
+        for c in cols:
+            if c.array == a:
+                m[c.start:c.start + 4 * c.num_values] = True
+        masks.append(m)
+    return masks
+
+
+def compare_outputs(mesh, got, expect, what=""):
+    """Static bytes identical; dynamic floats within REL_TOL (relative to the vector magnitude
+    scale, floor 1e-30).  Returns (max_abs_error, number_of_differing_bytes)."""
+    max_abs, nbytes = 0.0, 0
+    for o, (g, e, mask) in enumerate(zip(got, expect, dynamic_float_mask(mesh))):
+        g = np.asarray(g).reshape(mesh.num_rows, -1)
+        e = np.asarray(e).reshape(mesh.num_rows, -1)
+        assert g.shape == e.shape
+        assert np.array_equal(g[:, ~mask], e[:, ~mask]), f"{what}: static bytes of output {o} differ"
+        nbytes += int((g != e).sum())
+        gf = np.ascontiguousarray(g[:, mask]).view(np.float32).astype(np.float64)
+        ef = np.ascontiguousarray(e[:, mask]).view(np.float32).astype(np.float64)
+        if gf.size:
+            err = np.abs(gf - ef)
+            max_abs = max(max_abs, float(err.max()))
+            scale = np.maximum(np.abs(ef), 1e-30)
+            # per component class: relative to the component, with the row's vector magnitude as floor
+            row_scale = np.maximum(scale, np.abs(ef).max(axis=1, keepdims=True))
+            rel = (err / row_scale).max()
+            assert rel <= REL_TOL, f"{what}: output {o} relative error {rel:.3e} > {REL_TOL}"
+    return max_abs, nbytes
+
+
+def expected_selection(mesh):
+    bi = mesh.blend_indices()
+    sel = np.full(mesh.num_rows, -1, np.int64)
+    if mesh.blend_column is not None:
+        for b, e in np.asarray(mesh.row_ranges).reshape(-1, 2):
+            sel[b:e] = bi[b:e]
+    return sel
+
+
+@pytest.mark.parametrize("path", golden_paths(), ids=golden_ids())
+def test_golden_fixture_parity(gpu_ctx, path):
+    """CUDA output vs the bytes the reference itself produced (tests/golden/, frames of each case)."""
+    case = load_case(path)
+    mesh = mesh_from_case(case)
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, 1)
+    try:
+        assert np.array_equal(grp.read_selection(), expected_selection(mesh)), "blend-index / row selection differs"
+        total_diff = 0
+        for fr in range(int(case["meta"][7])):
+            sliders = case["sliders"][fr] if mesh.num_sliders else None
+            got = grp.animate_vertices(case["palette"][fr], sliders)
+            expect = [case[f"expect{o}"][fr] for o in range(len(got))]
+            max_abs, nb = compare_outputs(mesh, got, expect, f"{path} frame {fr}")
+            total_diff += nb
+            blends = grp.read_blends(0)
+            eb = case["expect_blends"][fr]
+            cols = slice(None) if dmesh_full(mesh) else [0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14]
+            assert np.array_equal(blends[:, cols].view(np.uint32), eb.reshape(-1, 16)[:, cols].view(np.uint32)), \
+                "blended matrices are not bit-identical to TransformBlend::get_blend"
+        print(f"{path.rsplit('/', 1)[1]}: differing bytes vs reference = {total_diff}")
+    finally:
+        grp.close()
+        dmesh.close()
+
+
+def dmesh_full(mesh):
+    return any(c.num_values == 4 for c in mesh.skin_columns)
+
+
+SYNTH_CASES = {
+    "c2_small_random": dict(num_rows=20_000, num_transforms=64, num_blends=4096, index_order="random"),
+    "c2_small_sorted": dict(num_rows=20_000, num_transforms=64, num_blends=4096, index_order="sorted"),
+    "c5_layout": dict(num_rows=9_000, num_transforms=128, num_blends=2000, tbn=True, texcoord=True, index_order="runs"),
+    "c4_morphs": dict(num_rows=12_000, num_transforms=64, num_blends=2048, num_sliders=16, slider_band=0.1,
+                      morph_columns=("vertex", "normal"), index_order="runs"),
+    "ragged_rows": dict(num_rows=5_003, num_transforms=16, num_blends=300, rows=[(1, 2), (5, 1000), (1003, 5003)]),
+    "u32_index": dict(num_rows=70_001, num_transforms=32, num_blends=66_000, index_type="u32"),
+    "one_row": dict(num_rows=1, num_transforms=4, num_blends=1),
+    "align16": dict(num_rows=4_099, num_transforms=32, num_blends=700, align16=True, tbn=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SYNTH_CASES))
+def test_synthetic_parity_vs_oracle(gpu_ctx, name):
+    kw = dict(SYNTH_CASES[name])
+    sm = synth.make_mesh(seed=sum(map(ord, name)) % 1000, **kw)
+    mesh = sm.flat
+    frames = 2
+    pal = synth.make_palettes(mesh.num_transforms, frames, 99, jitter=0.3 if "align16" in name else 0.0)
+    sl = synth.make_sliders(mesh.num_sliders, frames, 98) if mesh.num_sliders else None
+    om = oracle.OracleMesh(mesh)
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, 1)
+    try:
+        assert np.array_equal(grp.read_selection(), expected_selection(mesh))
+        for fr in range(frames):
+            expect, _, sel = om.animate(pal[fr], sl[fr] if sl is not None else None, want_selection=True)
+            got = grp.animate_vertices(pal[fr], sl[fr] if sl is not None else None)
+            max_abs, nb = compare_outputs(mesh, got, expect, f"{name} frame {fr}")
+            print(f"{name} frame {fr}: max-abs error {max_abs:.3e}, differing bytes {nb}")
+    finally:
+        grp.close()
+        dmesh.close()
+
+
+def test_crowd_instances_are_independent(gpu_ctx):
+    """A group of n instances == n single-instance calls (crowd sharding unit)."""
+    sm = synth.make_mesh(3_000, 32, 500, seed=5, index_order="runs", num_sliders=4, slider_band=0.3)
+    mesh = sm.flat
+    n = 37
+    pal = synth.make_palettes(mesh.num_transforms, n, 7)
+    sl = synth.make_sliders(mesh.num_sliders, n, 8)
+    om = oracle.OracleMesh(mesh)
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, n)
+    try:
+        grp.set_palettes(pal)
+        grp.set_sliders(sl)
+        grp.animate()
+        out = grp.read_output(0)
+        for i in (0, 1, n // 2, n - 1):
+            expect, _, _ = om.animate(pal[i], sl[i])
+            compare_outputs(mesh, [out[i]], expect, f"instance {i}")
+        t = grp.timings()
+        assert t.launches >= 2 and t.total_ms > 0
+    finally:
+        grp.close()
+        dmesh.close()
+
+
+def test_full_size_c2_properties(gpu_ctx):
+    """BASELINE configs[1] at full size (100k vertices, 64 joints, 16 384 blends): size-independent
+    properties -- identity palette is a byte-exact copy; a rigid global translation moves every point
+    by it and leaves normals; linearity of blending in the palette (M -> 2M doubles positions)."""
+    sm = synth.config_c2("random")
+    mesh = sm.flat
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, 1)
+    try:
+        T = mesh.num_transforms
+        ident = np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (T, 1))
+        out = grp.animate_vertices(ident)[0]
+        src = mesh.arrays[0]
+        f_out, f_src = out.view(np.float32), src.view(np.float32)
+        # weights sum to 1 within an ulp, so identity blends reproduce positions to ~1e-7 relative
+        assert np.allclose(f_out, f_src, rtol=5e-7, atol=1e-7)
+        tr = ident.copy().reshape(T, 4, 4)
+        tr[:, 3, :3] = (1.0, -2.0, 0.5)
+        out_t = grp.animate_vertices(tr.reshape(T, 16))[0].view(np.float32)
+        assert np.allclose(out_t[:, :3] - f_out[:, :3], (1.0, -2.0, 0.5), atol=2e-6)
+        assert np.array_equal(out_t[:, 3:6], f_out[:, 3:6])
+        pal = synth.make_palettes(T, 1, 3)[0]
+        a = grp.animate_vertices(pal)[0].view(np.float32)
+        b = grp.animate_vertices(pal * 2.0)[0].view(np.float32)
+        assert np.array_equal(b[:, :3], a[:, :3] * 2.0)  # scaling by 2 is exact in floating point
+        # and the full-size result agrees with the oracle
+        expect, _, _ = oracle.OracleMesh(mesh).animate(pal)
+        compare_outputs(mesh, [grp.animate_vertices(pal)[0]], expect, "C2 full size")
+    finally:
+        grp.close()
+        dmesh.close()
+
+
+def test_unsupported_and_invalid_inputs_fail_loudly(gpu_ctx):
+    sm = synth.make_mesh(100, 4, 8, seed=1)
+    mesh = sm.flat
+    bad = F.FlatMesh(**{**mesh.__dict__})
+    bad.skin_columns = [F.Column(0, 0, 3, F.NT_float64, F.C_point)]
+    with pytest.raises(_capi.P3csError) as e:
+        _capi.Mesh(gpu_ctx, bad)
+    assert e.value.code in (_capi.P3CS_ERR_UNSUPPORTED, _capi.P3CS_ERR_INVALID)
+    bad2 = F.FlatMesh(**{**mesh.__dict__})
+    bad2.blend_offsets = mesh.blend_offsets[:3].copy()  # fewer blends than the indices select
+    bad2.blend_transform = mesh.blend_transform[:int(bad2.blend_offsets[-1])]
+    bad2.blend_weight = mesh.blend_weight[:int(bad2.blend_offsets[-1])]
+    with pytest.raises(_capi.P3csError) as e:
+        _capi.Mesh(gpu_ctx, bad2)
+    assert e.value.code == _capi.P3CS_ERR_INVALID
