@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libp3cudaskin.so")
-SOURCES = ["p3cs_api.cu", "p3cs_kernels.cu"]
-HEADERS = ["p3cs_kernels.cuh", "p3cs_math.cuh", os.path.join("..", "..", "include", "p3cudaskin.h")]
+SOURCES = ["p3cs_api.cu", "p3cs_kernels.cu", "p3cs_strip.cu"]
+HEADERS = ["p3cs_kernels.cuh", "p3cs_math.cuh", "p3cs_device.cuh", os.path.join("..", "..", "include", "p3cudaskin.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -40,6 +41,7 @@ static int fail(int code, const char *fmt, ...) {
 // ------------------------------------------------------------------ objects
 struct p3cs_context_s {
   int device = 0;
+  int sm_count = 148;
   cudaStream_t stream = nullptr;
   bool owns_stream = false;
 };
@@ -48,7 +50,7 @@ struct p3cs_mesh_s {
   p3cs_context ctx = nullptr;
   MeshDev dev{};
   std::vector<void *> allocations;
-  int index_array = -1;
+  bool use_strip = true;  // fused strip kernel (p3cs_strip.cu); false: blend + skin kernels
 };
 
 struct p3cs_group_s {
@@ -84,7 +86,8 @@ int upload(p3cs_mesh mesh, const T *host, size_t count, const T **out) {
   *out = nullptr;
   if (count == 0) count = 1;  // keep pointers non-null
   void *d = nullptr;
-  CUDA_TRY(cudaMalloc(&d, count * sizeof(T)));
+  // +16: the strip kernel's bulk copies round the last tile of an array up to 16 bytes
+  CUDA_TRY(cudaMalloc(&d, count * sizeof(T) + 16));
   mesh->allocations.push_back(d);
   if (host != nullptr) CUDA_TRY(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, mesh->ctx->stream));
   *out = static_cast<const T *>(d);
@@ -129,6 +132,7 @@ extern "C" int p3cs_context_create(int device, void *stream, p3cs_context *out) 
   p3cs_context ctx = new (std::nothrow) p3cs_context_s;
   if (ctx == nullptr) return fail(P3CS_ERR_NOMEM, "out of host memory");
   ctx->device = device;
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (stream != nullptr) {
     ctx->stream = static_cast<cudaStream_t>(stream);
   } else {
@@ -291,6 +295,43 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
           return bail(fail(P3CS_ERR_INVALID, "row %d selects blend %u but the table has %d blends", r, v, d->num_blends));
         if (!full) mask[r >> 5] |= 1u << (r & 31);
       }
+    // ---- strip-kernel tables: per tile the distinct blends, per row its slot in that list
+    {
+      const int nt = (N + kTileRows - 1) / kTileRows;
+      std::vector<uint16_t> local(std::max(N, 1), 0xFFFFu);
+      std::vector<int> rec_off(nt + 1, 0), rec_blend, ent_off(1, 0), ent_xf;
+      std::vector<float> ent_w;
+      std::vector<int> stamp(std::max(d->num_blends, 1), -1), slot(std::max(d->num_blends, 1), 0);
+      int max_rec = 0;
+      for (int t = 0; t < nt; ++t) {
+        const int r0 = t * kTileRows, r1 = std::min(N, r0 + kTileRows);
+        int count = 0;
+        for (int r = r0; r < r1; ++r) {
+          if (!full && !((mask[r >> 5] >> (r & 31)) & 1u)) continue;
+          const int b = (int)(wide ? idx32[r] : idx16[r]);
+          if (stamp[b] != t) {
+            stamp[b] = t;
+            slot[b] = count++;
+            rec_blend.push_back(b);
+            for (int e = d->blend_offsets[b]; e < d->blend_offsets[b + 1]; ++e) {
+              ent_xf.push_back(d->blend_transform[e]);
+              ent_w.push_back(d->blend_weight[e]);
+            }
+            ent_off.push_back((int)ent_xf.size());
+          }
+          local[r] = (uint16_t)slot[b];
+        }
+        rec_off[t + 1] = rec_off[t] + count;
+        max_rec = std::max(max_rec, count);
+      }
+      m.max_tile_records = max_rec;
+      if ((rc = upload<uint16_t>(mesh, local.data(), local.size(), &m.tile_local)) != P3CS_OK) return bail(rc);
+      if ((rc = upload<int>(mesh, rec_off.data(), rec_off.size(), &m.tile_rec_offsets)) != P3CS_OK) return bail(rc);
+      if ((rc = upload<int>(mesh, rec_blend.data(), rec_blend.size(), &m.tile_rec_blend)) != P3CS_OK) return bail(rc);
+      if ((rc = upload<int>(mesh, ent_off.data(), ent_off.size(), &m.trec_entry_offsets)) != P3CS_OK) return bail(rc);
+      if ((rc = upload<int>(mesh, ent_xf.data(), ent_xf.size(), &m.trec_transform)) != P3CS_OK) return bail(rc);
+      if ((rc = upload<float>(mesh, ent_w.data(), ent_w.size(), &m.trec_weight)) != P3CS_OK) return bail(rc);
+    }
     m.index_bytes = wide ? 4 : 2;
     const void *dev_index = nullptr;
     if (wide) { const uint32_t *p; rc = upload<uint32_t>(mesh, idx32.data(), idx32.size(), &p); dev_index = p; }
@@ -360,6 +401,21 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
     if ((rc = upload<int>(mesh, counts.data(), counts.size(), &m.morph_row_offsets)) != P3CS_OK) return bail(rc);
     if ((rc = upload<uint32_t>(mesh, keys.data(), keys.size(), &m.morph_keys)) != P3CS_OK) return bail(rc);
     if ((rc = upload<float4>(mesh, deltas.data(), deltas.size(), &m.morph_deltas)) != P3CS_OK) return bail(rc);
+  }
+  // ---- tile geometry of the strip kernel
+  m.num_tiles = (N + kTileRows - 1) / kTileRows;
+  m.tile_bytes = 0;
+  for (int o = 0; o < m.num_outputs; ++o) {
+    m.tile_out_offset[o] = m.tile_bytes;
+    m.tile_bytes += (int)round_up((size_t)kTileRows * m.stride[o], 128);
+  }
+  if (m.tile_rec_offsets == nullptr) {  // no blend table: every tile has zero records
+    std::vector<int> zeros((size_t)m.num_tiles + 1, 0);
+    if ((rc = upload<int>(mesh, zeros.data(), zeros.size(), &m.tile_rec_offsets)) != P3CS_OK) return bail(rc);
+  }
+  {
+    const char *path = getenv("P3CS_PATH");
+    mesh->use_strip = strip_smem_bytes(m) <= 200 * 1024 && !(path != nullptr && strcmp(path, "wide") == 0);
   }
   // uploads read from host vectors that die at scope exit: finish them now
   cudaError_t err = cudaStreamSynchronize(ctx->stream);
@@ -506,6 +562,17 @@ static int animate_range(p3cs_group grp, int first, int count, bool timed) {
   cudaEvent_t e0, e1;
   grp->prof_kind.clear();
   if (timed) CUDA_TRY(cudaEventRecord(grp->ev[0], s));
+  if (grp->mesh->use_strip) {
+    if (prof) {
+      if ((rc = prof_event(grp, pe++, &e0)) != P3CS_OK || (rc = prof_event(grp, pe++, &e1)) != P3CS_OK) return rc;
+      CUDA_TRY(cudaEventRecord(e0, s));
+    }
+    nskin = launches = launch_strip(m, grp->dev, first, count, grp->mesh->ctx->sm_count, s);
+    if (prof) {
+      CUDA_TRY(cudaEventRecord(e1, s));
+      grp->prof_kind.push_back(1);
+    }
+  } else
   for (int c0 = first; c0 < first + count; c0 += grp->chunk) {
     const int cn = std::min(grp->chunk, first + count - c0);
     if (m.num_blends > 0) {
@@ -598,8 +665,12 @@ extern "C" int p3cs_group_read_selection(p3cs_group grp, int32_t *host_dst) {
   CUDA_TRY(cudaMalloc(&sel, std::max<size_t>((size_t)m.num_rows * 4, 4)));
   GroupDev tmp = grp->dev;
   tmp.selection = sel;
-  if (m.num_blends > 0) launch_blend(m, tmp, 0, 1, s);
-  launch_skin(m, tmp, 0, 1, s);
+  if (grp->mesh->use_strip) {
+    launch_strip(m, tmp, 0, 1, grp->mesh->ctx->sm_count, s);
+  } else {
+    if (m.num_blends > 0) launch_blend(m, tmp, 0, 1, s);
+    launch_skin(m, tmp, 0, 1, s);
+  }
   cudaError_t err = cudaMemcpyAsync(host_dst, sel, (size_t)m.num_rows * 4, cudaMemcpyDeviceToHost, s);
   if (err == cudaSuccess) err = cudaStreamSynchronize(s);
   cudaFree(sel);

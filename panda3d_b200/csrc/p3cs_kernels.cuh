@@ -47,7 +47,23 @@ struct MeshDev {
   const int *morph_row_offsets;     // per-row CSR of morph entries (num_rows+1)
   const uint32_t *morph_keys;       // (dyn column << 16) | slider
   const float4 *morph_deltas;
+
+  // ---- strip kernel tables (static, built at upload): rows are cut into tiles of kTileRows;
+  // each tile lists the distinct blends its skinned rows select ("tile records") and every row
+  // stores the index of its blend in that list.
+  int num_tiles;
+  int max_tile_records;             // max distinct blends of any tile (smem sizing)
+  int tile_bytes;                   // smem bytes of one staged tile (all outputs, 128-aligned)
+  int tile_out_offset[kMaxOutputs]; // byte offset of output o inside a staged tile
+  const uint16_t *tile_local;       // per row: index into the tile's record list, 0xFFFF = not skinned
+  const int *tile_rec_offsets;      // num_tiles+1
+  const int *tile_rec_blend;        // global blend id of every tile record (selection hook)
+  const int *trec_entry_offsets;    // CSR of the blend entries, in tile-record order
+  const int *trec_transform;
+  const float *trec_weight;
 };
+
+constexpr int kTileRows = 256;
 
 struct GroupDev {
   const float *palettes;  // [n][T][16]
@@ -60,6 +76,10 @@ struct GroupDev {
 
 void launch_blend(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);
 void launch_skin(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);
+// The fused path: palette -> smem, per tile: blend records -> smem, rows via TMA bulk copies.
+// Returns the number of kernel launches issued (instances are split in grid.y chunks of 65535).
+int launch_strip(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, int sm_count, cudaStream_t stream);
+size_t strip_smem_bytes(const MeshDev &mesh);
 int skin_rows_per_tile(const MeshDev &mesh);
 
 }  // namespace p3cs
