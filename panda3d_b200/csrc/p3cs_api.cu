@@ -253,6 +253,13 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
     if (c.num_values == 4) m.full_records = 1;
   }
 
+  // column order is semantically irrelevant (columns are independent); a canonical order
+  // point(s), normal(s), vector(s) lets the strip kernel pick a specialised variant
+  std::stable_sort(m.dyn, m.dyn + m.num_dyn, [](const DynColumn &a, const DynColumn &b) {
+    auto key = [](int skin) { return skin == 1 ? 0 : skin == 3 ? 1 : 2; };
+    return key(a.skin) < key(b.skin);
+  });
+
   // ---- transform_blend index column -> dense u16/u32
   if (d->blend_column.array >= 0) {
     const p3cs_column_desc &bc = d->blend_column;

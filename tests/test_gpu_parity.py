@@ -152,7 +152,7 @@ def test_crowd_instances_are_independent(gpu_ctx):
             expect, _, _ = om.animate(pal[i], sl[i])
             compare_outputs(mesh, [out[i]], expect, f"instance {i}")
         t = grp.timings()
-        assert t.launches >= 2 and t.total_ms > 0
+        assert t.launches >= 1 and t.total_ms > 0
     finally:
         grp.close()
         dmesh.close()
