@@ -302,42 +302,59 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
           return bail(fail(P3CS_ERR_INVALID, "row %d selects blend %u but the table has %d blends", r, v, d->num_blends));
         if (!full) mask[r >> 5] |= 1u << (r & 31);
       }
-    // ---- strip-kernel tables: per tile the distinct blends, per row its slot in that list
+    // ---- strip-kernel tables: per record group the distinct blends, per row its slot in that list.
+    // Groups are as large as the shared-memory record budget allows (better lane packing and
+    // cross-tile dedup in phase A); a mesh whose rows select blends at random ends up with 1 tile.
     {
       const int nt = (N + kTileRows - 1) / kTileRows;
-      std::vector<uint16_t> local(std::max(N, 1), 0xFFFFu);
-      std::vector<int> rec_off(nt + 1, 0), rec_blend, ent_off(1, 0), ent_xf;
-      std::vector<float> ent_w;
-      std::vector<int> stamp(std::max(d->num_blends, 1), -1), slot(std::max(d->num_blends, 1), 0);
-      int max_rec = 0;
-      for (int t = 0; t < nt; ++t) {
-        const int r0 = t * kTileRows, r1 = std::min(N, r0 + kTileRows);
-        int count = 0;
-        for (int r = r0; r < r1; ++r) {
-          if (!full && !((mask[r >> 5] >> (r & 31)) & 1u)) continue;
-          const int b = (int)(wide ? idx32[r] : idx16[r]);
-          if (stamp[b] != t) {
-            stamp[b] = t;
-            slot[b] = count++;
-            rec_blend.push_back(b);
-            for (int e = d->blend_offsets[b]; e < d->blend_offsets[b + 1]; ++e) {
-              ent_xf.push_back(d->blend_transform[e]);
-              ent_w.push_back(d->blend_weight[e]);
+      const int rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
+      const int budget = 32 * 1024;
+      std::vector<uint16_t> local;
+      std::vector<int> rec_off, rec_blend, ent_off;
+      std::vector<uint2> ent;
+      std::vector<int> stamp(std::max(d->num_blends, 1)), slot(std::max(d->num_blends, 1), 0);
+      int gt = 8, ng = 0, max_rec = 0;
+      for (;; gt >>= 1) {
+        ng = (nt + gt - 1) / gt;
+        local.assign(std::max(N, 1), 0xFFFFu);
+        rec_off.assign(1, 0);
+        rec_blend.clear();
+        ent_off.assign(1, 0);
+        ent.clear();
+        std::fill(stamp.begin(), stamp.end(), -1);
+        max_rec = 0;
+        for (int g = 0; g < ng; ++g) {
+          const int r0 = g * gt * kTileRows, r1 = std::min(N, r0 + gt * kTileRows);
+          int count = 0;
+          for (int r = r0; r < r1; ++r) {
+            if (!full && !((mask[r >> 5] >> (r & 31)) & 1u)) continue;
+            const int b = (int)(wide ? idx32[r] : idx16[r]);
+            if (stamp[b] != g) {
+              stamp[b] = g;
+              slot[b] = count++;
+              rec_blend.push_back(b);
+              for (int e = d->blend_offsets[b]; e < d->blend_offsets[b + 1]; ++e) {
+                uint32_t wbits;
+                memcpy(&wbits, &d->blend_weight[e], 4);
+                ent.push_back(make_uint2((uint32_t)d->blend_transform[e], wbits));
+              }
+              ent_off.push_back((int)ent.size());
             }
-            ent_off.push_back((int)ent_xf.size());
+            local[r] = (uint16_t)slot[b];
           }
-          local[r] = (uint16_t)slot[b];
+          rec_off.push_back(rec_off.back() + count);
+          max_rec = std::max(max_rec, count);
         }
-        rec_off[t + 1] = rec_off[t] + count;
-        max_rec = std::max(max_rec, count);
+        if (gt == 1 || (size_t)max_rec * rec_bytes <= (size_t)budget) break;
       }
-      m.max_tile_records = max_rec;
-      if ((rc = upload<uint16_t>(mesh, local.data(), local.size(), &m.tile_local)) != P3CS_OK) return bail(rc);
-      if ((rc = upload<int>(mesh, rec_off.data(), rec_off.size(), &m.tile_rec_offsets)) != P3CS_OK) return bail(rc);
-      if ((rc = upload<int>(mesh, rec_blend.data(), rec_blend.size(), &m.tile_rec_blend)) != P3CS_OK) return bail(rc);
-      if ((rc = upload<int>(mesh, ent_off.data(), ent_off.size(), &m.trec_entry_offsets)) != P3CS_OK) return bail(rc);
-      if ((rc = upload<int>(mesh, ent_xf.data(), ent_xf.size(), &m.trec_transform)) != P3CS_OK) return bail(rc);
-      if ((rc = upload<float>(mesh, ent_w.data(), ent_w.size(), &m.trec_weight)) != P3CS_OK) return bail(rc);
+      m.group_tiles = gt;
+      m.num_groups = ng;
+      m.max_group_records = max_rec;
+      if ((rc = upload<uint16_t>(mesh, local.data(), local.size(), &m.row_local)) != P3CS_OK) return bail(rc);
+      if ((rc = upload<int>(mesh, rec_off.data(), rec_off.size(), &m.group_rec_offsets)) != P3CS_OK) return bail(rc);
+      if ((rc = upload<int>(mesh, rec_blend.data(), rec_blend.size(), &m.group_rec_blend)) != P3CS_OK) return bail(rc);
+      if ((rc = upload<int>(mesh, ent_off.data(), ent_off.size(), &m.grec_entry_offsets)) != P3CS_OK) return bail(rc);
+      if ((rc = upload<uint2>(mesh, ent.data(), ent.size(), &m.grec_entries)) != P3CS_OK) return bail(rc);
     }
     m.index_bytes = wide ? 4 : 2;
     const void *dev_index = nullptr;
@@ -416,9 +433,11 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
     m.tile_out_offset[o] = m.tile_bytes;
     m.tile_bytes += (int)round_up((size_t)kTileRows * m.stride[o], 128);
   }
-  if (m.tile_rec_offsets == nullptr) {  // no blend table: every tile has zero records
-    std::vector<int> zeros((size_t)m.num_tiles + 1, 0);
-    if ((rc = upload<int>(mesh, zeros.data(), zeros.size(), &m.tile_rec_offsets)) != P3CS_OK) return bail(rc);
+  if (m.group_rec_offsets == nullptr) {  // no blend table: one tile per group, zero records each
+    m.group_tiles = 1;
+    m.num_groups = m.num_tiles;
+    std::vector<int> zeros((size_t)m.num_groups + 1, 0);
+    if ((rc = upload<int>(mesh, zeros.data(), zeros.size(), &m.group_rec_offsets)) != P3CS_OK) return bail(rc);
   }
   {
     const char *path = getenv("P3CS_PATH");

@@ -34,6 +34,31 @@ __device__ __forceinline__ void blend_accumulate(LoadRow load_row, const int *xf
   }
 }
 
+// The same over entries packed as (palette index, weight bits) pairs (strip kernel tables).
+template <class LoadRow>
+__device__ __forceinline__ void blend_accumulate_packed(LoadRow load_row, const uint2 *entries, int beg, int end, Mat4 &acc) {
+  if (beg == end) {
+    set_ident4(acc);
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc.m[i][j] = 0.0f;
+  for (int e = beg; e < end; ++e) {
+    const uint2 en = __ldg(entries + e);
+    const float weight = __uint_as_float(en.y);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float4 row = load_row((int)en.x, r);
+      acc.m[r][0] += row.x * weight;
+      acc.m[r][1] += row.y * weight;
+      acc.m[r][2] += row.z * weight;
+      acc.m[r][3] += row.w * weight;
+    }
+  }
+}
+
 // Writes one record (layouts: p3cs_kernels.cuh) to global or shared memory.
 template <bool FULL>
 __device__ __forceinline__ void store_record(float *dst, const Mat4 &acc, const Mat4 &x, bool normalize) {

@@ -48,19 +48,21 @@ struct MeshDev {
   const uint32_t *morph_keys;       // (dyn column << 16) | slider
   const float4 *morph_deltas;
 
-  // ---- strip kernel tables (static, built at upload): rows are cut into tiles of kTileRows;
-  // each tile lists the distinct blends its skinned rows select ("tile records") and every row
-  // stores the index of its blend in that list.
+  // ---- strip kernel tables (static, built at upload).  Rows are cut into tiles of kTileRows
+  // (the TMA / phase-B unit) and tiles into record groups of `group_tiles` tiles (the phase-A
+  // unit): each group lists the distinct blends its skinned rows select ("group records") and
+  // every row stores the index of its blend in that list.
   int num_tiles;
-  int max_tile_records;             // max distinct blends of any tile (smem sizing)
+  int group_tiles;                  // tiles per record group (power of two, 1..8)
+  int num_groups;
+  int max_group_records;            // max distinct blends of any group (smem sizing)
   int tile_bytes;                   // smem bytes of one staged tile (all outputs, 128-aligned)
   int tile_out_offset[kMaxOutputs]; // byte offset of output o inside a staged tile
-  const uint16_t *tile_local;       // per row: index into the tile's record list, 0xFFFF = not skinned
-  const int *tile_rec_offsets;      // num_tiles+1
-  const int *tile_rec_blend;        // global blend id of every tile record (selection hook)
-  const int *trec_entry_offsets;    // CSR of the blend entries, in tile-record order
-  const int *trec_transform;
-  const float *trec_weight;
+  const uint16_t *row_local;        // per row: index into its group's record list, 0xFFFF = not skinned
+  const int *group_rec_offsets;     // num_groups+1
+  const int *group_rec_blend;       // global blend id of every group record (selection hook)
+  const int *grec_entry_offsets;    // CSR of the blend entries, in group-record order
+  const uint2 *grec_entries;        // (palette index, float weight bits) per entry
 };
 
 constexpr int kTileRows = 256;

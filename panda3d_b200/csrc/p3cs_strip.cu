@@ -25,7 +25,9 @@ namespace p3cs {
 constexpr int kStripThreads = kTileRows;  // one thread per row of a tile
 constexpr int kPalStride4 = 5;            // palette matrix stride in smem: 5 x float4 (80 B): LDS.128 without 4-way conflicts
 
-enum StripMode { kGenericCompact = 0, kGenericFull = 1, kFastP = 2, kFastPN = 3, kFastPNVV = 4 };
+// kFastPN24: the egg loader's packed [vertex(3f) normal(3f)] rows (stride 24): the whole row is
+// moved with three conflict-free 64-bit shared-memory accesses each way.
+enum StripMode { kGenericCompact = 0, kGenericFull = 1, kFastP = 2, kFastPN = 3, kFastPNVV = 4, kFastPN24 = 5 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -73,7 +75,7 @@ __host__ __device__ inline StripSmem strip_layout(const MeshDev &m) {
   s.palette_off = 16;  // two mbarriers
   s.records_off = s.palette_off + m.num_transforms * kPalStride4 * 16;
   const int rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
-  s.tiles_off = (s.records_off + (m.max_tile_records > 0 ? m.max_tile_records : 1) * rec_bytes + 127) & ~127;
+  s.tiles_off = (s.records_off + (m.max_group_records > 0 ? m.max_group_records : 1) * rec_bytes + 127) & ~127;
   s.total = s.tiles_off + 2 * m.tile_bytes;
   return s;
 }
@@ -119,8 +121,23 @@ static __device__ __noinline__ void normal_general_inverse(float m00, float m01,
 // AFFINE: every palette matrix has column 3 == (0,0,0,1) exactly, so the blended column 3 is
 // (0,0,0,sum w) and needs no multiplies (sum w is accumulated in the reference's order).
 template <bool AFFINE>
-__device__ __forceinline__ void compact_record(const float4 *pal, const int *xf, const float *w, int beg, int end, int cs,
-                                               int want_normal, float *rec) {
+__device__ __forceinline__ void accumulate_entry(const float4 *pal, uint2 e, float (&m)[4][3], float (&c3)[4]) {
+  const float weight = __uint_as_float(e.y);
+  const float4 *mat = pal + e.x * kPalStride4;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {  // LMatrix4f::accumulate, lmatrix4_src.I:1311-1336
+    const float4 row = mat[r];
+    m[r][0] += row.x * weight;
+    m[r][1] += row.y * weight;
+    m[r][2] += row.z * weight;
+    if (!AFFINE) c3[r] += row.w * weight;
+  }
+  if (AFFINE) c3[3] += weight;  // 1.0f * weight == weight
+}
+
+template <bool AFFINE>
+__device__ __forceinline__ void compact_record(const float4 *pal, const uint2 *entries, int beg, int end, int cs, int want_normal,
+                                               float *rec) {
   float m[4][3];
   float c3[4];
   if (beg == end) {  // empty TransformBlend: identity (transformBlend.I:362-366)
@@ -137,19 +154,14 @@ __device__ __forceinline__ void compact_record(const float4 *pal, const int *xf,
       for (int j = 0; j < 3; ++j) m[i][j] = 0.0f;
       c3[i] = 0.0f;
     }
-    for (int e = beg; e < end; ++e) {
-      const int t = __ldg(xf + e);
-      const float weight = __ldg(w + e);
-      const float4 *mat = pal + t * kPalStride4;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {  // LMatrix4f::accumulate, lmatrix4_src.I:1311-1336
-        const float4 row = mat[r];
-        m[r][0] += row.x * weight;
-        m[r][1] += row.y * weight;
-        m[r][2] += row.z * weight;
-        if (!AFFINE) c3[r] += row.w * weight;
-      }
-      if (AFFINE) c3[3] += weight;  // 1.0f * weight == weight
+    if (end - beg == 4) {  // the common 4-weight blend: straight-line, all loads issued up front
+      const uint2 e0 = __ldg(entries + beg), e1 = __ldg(entries + beg + 1), e2 = __ldg(entries + beg + 2), e3 = __ldg(entries + beg + 3);
+      accumulate_entry<AFFINE>(pal, e0, m, c3);
+      accumulate_entry<AFFINE>(pal, e1, m, c3);
+      accumulate_entry<AFFINE>(pal, e2, m, c3);
+      accumulate_entry<AFFINE>(pal, e3, m, c3);
+    } else {
+      for (int e = beg; e < end; ++e) accumulate_entry<AFFINE>(pal, __ldg(entries + e), m, c3);
     }
   }
   float2 *r2 = reinterpret_cast<float2 *>(rec);
@@ -242,7 +254,7 @@ __device__ __forceinline__ void fast_column(float *cell, const float (&m)[4][3],
 
 template <int MODE>
 __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
-    strip_kernel(MeshDev mesh, GroupDev grp, int first_instance, int tiles_per_cta, int want_normal) {
+    strip_kernel(MeshDev mesh, GroupDev grp, int first_instance, int groups_per_cta, int want_normal) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr bool FULL = MODE == kGenericFull;
   constexpr int REC = FULL ? kRecFull : kRecCompact;
@@ -254,9 +266,11 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
 
   const int tid = threadIdx.x;
   const int inst = first_instance + blockIdx.y;
-  const int t0 = blockIdx.x * tiles_per_cta;
-  const int t1 = min(mesh.num_tiles, t0 + tiles_per_cta);
-  if (t0 >= t1) return;
+  const int g0 = blockIdx.x * groups_per_cta;
+  const int g1 = min(mesh.num_groups, g0 + groups_per_cta);
+  if (g0 >= g1) return;
+  const int t0 = g0 * mesh.group_tiles;
+  const int t1 = min(mesh.num_tiles, g1 * mesh.group_tiles);
 
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
@@ -281,6 +295,12 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   auto issue_tile_load = [&](int t, int buf) {
     const int row0 = t * kTileRows;
     const int rows = min(kTileRows, mesh.num_rows - row0);
+    if (MODE >= kFastP) {  // single output array
+      const uint32_t bytes = (uint32_t)((rows * mesh.stride[0] + 15) & ~15);
+      mbar_expect_tx(&mbar[buf], bytes);
+      bulk_g2s(tiles + buf * mesh.tile_bytes, mesh.src[0] + (size_t)row0 * mesh.stride[0], bytes, &mbar[buf]);
+      return;
+    }
     uint32_t total = 0;
     for (int o = 0; o < mesh.num_outputs; ++o) total += (uint32_t)((rows * mesh.stride[o] + 15) & ~15);
     mbar_expect_tx(&mbar[buf], total);
@@ -292,105 +312,122 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   if (tid == 0) issue_tile_load(t0, 0);
 
   const float *sliders = grp.sliders + (size_t)inst * mesh.num_sliders;
+  int it = 0;  // tiles processed by this CTA so far (buffer / mbarrier phase bookkeeping)
 
-  for (int t = t0; t < t1; ++t) {
-    const int it = t - t0;
-    const int buf = it & 1;
-    if (tid == 0 && t + 1 < t1) {
-      bulk_wait_read_all();  // the store that last read buffer buf^1 has drained it
-      issue_tile_load(t + 1, buf ^ 1);
-    }
-
-    // ---------------- phase A: one thread per distinct blend of this tile
-    const int rbeg = __ldg(mesh.tile_rec_offsets + t);
-    const int nrec = __ldg(mesh.tile_rec_offsets + t + 1) - rbeg;
+  for (int g = g0; g < g1; ++g) {
+    // ---------------- phase A: one thread per distinct blend of this record group
+    const int rbeg = __ldg(mesh.group_rec_offsets + g);
+    const int nrec = __ldg(mesh.group_rec_offsets + g + 1) - rbeg;
     for (int b = tid; b < nrec; b += kStripThreads) {
-      const int beg = __ldg(mesh.trec_entry_offsets + rbeg + b);
-      const int end = __ldg(mesh.trec_entry_offsets + rbeg + b + 1);
+      const int beg = __ldg(mesh.grec_entry_offsets + rbeg + b);
+      const int end = __ldg(mesh.grec_entry_offsets + rbeg + b + 1);
       if (FULL) {
         Mat4 acc, x;
-        blend_accumulate([&](int j, int r) { return pal[j * kPalStride4 + r]; }, mesh.trec_transform, mesh.trec_weight, beg, end, acc);
+        blend_accumulate_packed([&](int j, int r) { return pal[j * kPalStride4 + r]; }, mesh.grec_entries, beg, end, acc);
         bool normalize = false;
         if (want_normal) normalize = normal_xform(acc, mesh.coordinate_system, x);
         else x = acc;
         store_record<true>(recs + (size_t)b * REC, acc, x, normalize);
       } else if (non_affine) {
-        compact_record<false>(pal, mesh.trec_transform, mesh.trec_weight, beg, end, mesh.coordinate_system, want_normal,
-                              recs + (size_t)b * REC);
+        compact_record<false>(pal, mesh.grec_entries, beg, end, mesh.coordinate_system, want_normal, recs + (size_t)b * REC);
       } else {
-        compact_record<true>(pal, mesh.trec_transform, mesh.trec_weight, beg, end, mesh.coordinate_system, want_normal,
-                             recs + (size_t)b * REC);
+        compact_record<true>(pal, mesh.grec_entries, beg, end, mesh.coordinate_system, want_normal, recs + (size_t)b * REC);
       }
     }
+    __syncthreads();  // every record of the group is in shared memory
 
-    // ---------------- per-row selection (integer work, bit-exact)
-    const int row = t * kTileRows + tid;
-    const bool live = row < mesh.num_rows;
-    int local = 0xFFFF;
-    if (live && mesh.index_bytes != 0) local = __ldg(mesh.tile_local + row);
-    if (live && grp.selection != nullptr && blockIdx.y == 0)
-      grp.selection[row] = local == 0xFFFF ? -1 : __ldg(mesh.tile_rec_blend + rbeg + local);
-    const bool skinned = local != 0xFFFF;
+    const int gt0 = g * mesh.group_tiles;
+    const int gt1 = min(mesh.num_tiles, gt0 + mesh.group_tiles);
+    for (int t = gt0; t < gt1; ++t, ++it) {
+      const int buf = it & 1;
+      if (tid == 0 && t + 1 < t1) {
+        bulk_wait_read_all();  // the store that last read buffer buf^1 has drained it
+        issue_tile_load(t + 1, buf ^ 1);
+      }
 
-    mbar_wait(&mbar[buf], (it >> 1) & 1);  // the tile's rows have landed
-    __syncthreads();                       // ... and every record of phase A is written
+      // -------------- per-row selection (integer work, bit-exact)
+      const int row = t * kTileRows + tid;
+      const bool live = row < mesh.num_rows;
+      int local = 0xFFFF;
+      if (live && mesh.index_bytes != 0) local = __ldg(mesh.row_local + row);
+      if (live && grp.selection != nullptr && blockIdx.y == 0)
+        grp.selection[row] = local == 0xFFFF ? -1 : __ldg(mesh.group_rec_blend + rbeg + local);
+      const bool skinned = local != 0xFFFF;
 
-    // ---------------- phase B: one thread per row, in place on the staged tile
-    uint8_t *tile = tiles + buf * mesh.tile_bytes;
-    if (MODE >= kFastP) {
-      if (live && skinned) {
-        const float2 *p = reinterpret_cast<const float2 *>(recs + (size_t)local * kRecCompact);
-        float f[22];
+      mbar_wait(&mbar[buf], (it >> 1) & 1);  // the tile's rows have landed
+
+      // -------------- phase B: one thread per row, in place on the staged tile
+      uint8_t *tile = tiles + buf * mesh.tile_bytes;
+      if (MODE >= kFastP) {
+        if (live && skinned) {
+          const float2 *p = reinterpret_cast<const float2 *>(recs + (size_t)local * kRecCompact);
+          float f[22];
 #pragma unroll
-        for (int i = 0; i < 11; ++i) {
-          const float2 v = p[i];
-          f[2 * i] = v.x;
-          f[2 * i + 1] = v.y;
+          for (int i = 0; i < 11; ++i) {
+            const float2 v = p[i];
+            f[2 * i] = v.x;
+            f[2 * i + 1] = v.y;
+          }
+          float m[4][3], n[3][3];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) m[i][j] = f[i * 3 + j];
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) n[i][j] = f[12 + i * 3 + j];
+          const bool normalize = f[21] != 0.0f;
+          if (MODE == kFastPN24) {
+            float2 *rowp = reinterpret_cast<float2 *>(tile + (size_t)tid * 24);
+            const float2 a = rowp[0], b2 = rowp[1], c = rowp[2];
+            float v[6] = {a.x, a.y, b2.x, b2.y, c.x, c.y};
+            fast_column<1>(v, m, n, normalize);
+            fast_column<3>(v + 3, m, n, normalize);
+            rowp[0] = make_float2(v[0], v[1]);
+            rowp[1] = make_float2(v[2], v[3]);
+            rowp[2] = make_float2(v[4], v[5]);
+          } else {
+            uint8_t *rowp = tile + (size_t)tid * mesh.stride[0];
+            fast_column<1>(reinterpret_cast<float *>(rowp + mesh.dyn[0].start), m, n, normalize);
+            if (MODE >= kFastPN) fast_column<3>(reinterpret_cast<float *>(rowp + mesh.dyn[1].start), m, n, normalize);
+            if (MODE >= kFastPNVV) {
+              fast_column<2>(reinterpret_cast<float *>(rowp + mesh.dyn[2].start), m, n, normalize);
+              fast_column<2>(reinterpret_cast<float *>(rowp + mesh.dyn[3].start), m, n, normalize);
+            }
+          }
         }
-        float m[4][3], n[3][3];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) m[i][j] = f[i * 3 + j];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) n[i][j] = f[12 + i * 3 + j];
-        const bool normalize = f[21] != 0.0f;
-        uint8_t *rowp = tile + (size_t)tid * mesh.stride[0];
-        fast_column<1>(reinterpret_cast<float *>(rowp + mesh.dyn[0].start), m, n, normalize);
-        if (MODE >= kFastPN) fast_column<3>(reinterpret_cast<float *>(rowp + mesh.dyn[1].start), m, n, normalize);
-        if (MODE >= kFastPNVV) {
-          fast_column<2>(reinterpret_cast<float *>(rowp + mesh.dyn[2].start), m, n, normalize);
-          fast_column<2>(reinterpret_cast<float *>(rowp + mesh.dyn[3].start), m, n, normalize);
+      } else if (live) {
+        int morph_beg = 0, morph_end = 0;
+        if (mesh.has_morphs) {
+          morph_beg = __ldg(mesh.morph_row_offsets + row);
+          morph_end = __ldg(mesh.morph_row_offsets + row + 1);
+        }
+        Record<FULL> rec;
+        if (skinned) load_record<FULL, false>(recs, (size_t)local, rec);
+        for (int c = 0; c < mesh.num_dyn; ++c) {
+          const DynColumn col = mesh.dyn[c];
+          float *cell = reinterpret_cast<float *>(tile + mesh.tile_out_offset[col.output] + (size_t)tid * mesh.stride[col.output] + col.start);
+          animate_column<FULL>(mesh, col, c, cell, morph_beg, morph_end, sliders, skinned, rec);
         }
       }
-    } else if (live) {
-      int morph_beg = 0, morph_end = 0;
-      if (mesh.has_morphs) {
-        morph_beg = __ldg(mesh.morph_row_offsets + row);
-        morph_end = __ldg(mesh.morph_row_offsets + row + 1);
-      }
-      Record<FULL> rec;
-      if (skinned) load_record<FULL, false>(recs, (size_t)local, rec);
-      for (int c = 0; c < mesh.num_dyn; ++c) {
-        const DynColumn col = mesh.dyn[c];
-        float *cell = reinterpret_cast<float *>(tile + mesh.tile_out_offset[col.output] + (size_t)tid * mesh.stride[col.output] + col.start);
-        animate_column<FULL>(mesh, col, c, cell, morph_beg, morph_end, sliders, skinned, rec);
-      }
-    }
-    fence_proxy_async();  // generic-proxy writes to the tile -> visible to the TMA store
-    __syncthreads();
+      fence_proxy_async();  // generic-proxy writes to the tile -> visible to the TMA store
+      __syncthreads();
 
-    if (tid == 0) {
-      const int row0 = t * kTileRows;
-      const int rows = min(kTileRows, mesh.num_rows - row0);
-      for (int o = 0; o < mesh.num_outputs; ++o) {
-        const uint32_t bytes = (uint32_t)((rows * mesh.stride[o] + 15) & ~15);
-        bulk_s2g(grp.out[o] + (size_t)inst * grp.pitch[o] + (size_t)row0 * mesh.stride[o],
-                 tiles + buf * mesh.tile_bytes + mesh.tile_out_offset[o], bytes);
+      if (tid == 0) {
+        const int row0 = t * kTileRows;
+        const int rows = min(kTileRows, mesh.num_rows - row0);
+        if (MODE >= kFastP) {
+          const uint32_t bytes = (uint32_t)((rows * mesh.stride[0] + 15) & ~15);
+          bulk_s2g(grp.out[0] + (size_t)inst * grp.pitch[0] + (size_t)row0 * mesh.stride[0], tile, bytes);
+        } else {
+          for (int o = 0; o < mesh.num_outputs; ++o) {
+            const uint32_t bytes = (uint32_t)((rows * mesh.stride[o] + 15) & ~15);
+            bulk_s2g(grp.out[o] + (size_t)inst * grp.pitch[o] + (size_t)row0 * mesh.stride[o], tile + mesh.tile_out_offset[o], bytes);
+          }
+        }
+        bulk_commit();
       }
-      bulk_commit();
     }
   }
   if (tid == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk store's reads
@@ -406,7 +443,8 @@ static int pick_mode(const MeshDev &mesh) {
     if (mesh.dyn[c].num_values != 3) return kGenericCompact;
   const DynColumn *d = mesh.dyn;
   if (mesh.num_dyn == 1 && d[0].skin == 1) return kFastP;
-  if (mesh.num_dyn == 2 && d[0].skin == 1 && d[1].skin == 3) return kFastPN;
+  if (mesh.num_dyn == 2 && d[0].skin == 1 && d[1].skin == 3)
+    return (mesh.stride[0] == 24 && d[0].start == 0 && d[1].start == 12) ? kFastPN24 : kFastPN;
   if (mesh.num_dyn == 4 && d[0].skin == 1 && d[1].skin == 3 && d[2].skin == 2 && d[3].skin == 2) return kFastPNVV;
   return kGenericCompact;
 }
@@ -424,13 +462,14 @@ int launch_strip(const MeshDev &mesh, const GroupDev &grp, int first_instance, i
   for (int c = 0; c < mesh.num_dyn; ++c) want_normal |= (mesh.dyn[c].skin == 3);
   const size_t smem = strip_smem_bytes(mesh);
   const int mode = pick_mode(mesh);
-  // enough strips to fill every SM several times over, as long as possible so the palette is staged rarely
+  // strips of whole record groups: enough of them to fill every SM several times over, yet as
+  // long as possible so the palette is staged rarely
   const long long target_ctas = (long long)sm_count * 24;
-  long long tpc = ((long long)mesh.num_tiles * count + target_ctas - 1) / target_ctas;
+  long long tpc = ((long long)mesh.num_groups * count + target_ctas - 1) / target_ctas;
   if (tpc < 1) tpc = 1;
-  if (tpc > mesh.num_tiles) tpc = mesh.num_tiles;
-  const int strips = (mesh.num_tiles + (int)tpc - 1) / (int)tpc;
-  tpc = (mesh.num_tiles + strips - 1) / strips;  // equal-length strips
+  if (tpc > mesh.num_groups) tpc = mesh.num_groups;
+  const int strips = (mesh.num_groups + (int)tpc - 1) / (int)tpc;
+  tpc = (mesh.num_groups + strips - 1) / strips;  // equal-length strips
   int launches = 0;
   for (int c0 = 0; c0 < count; c0 += 65535) {
     const int cn = count - c0 < 65535 ? count - c0 : 65535;
@@ -441,6 +480,7 @@ int launch_strip(const MeshDev &mesh, const GroupDev &grp, int first_instance, i
     case kFastP: launch_mode<kFastP>(mesh, grp, first, grid, smem, (int)tpc, want_normal, stream); break;
     case kFastPN: launch_mode<kFastPN>(mesh, grp, first, grid, smem, (int)tpc, want_normal, stream); break;
     case kFastPNVV: launch_mode<kFastPNVV>(mesh, grp, first, grid, smem, (int)tpc, want_normal, stream); break;
+    case kFastPN24: launch_mode<kFastPN24>(mesh, grp, first, grid, smem, (int)tpc, want_normal, stream); break;
     default: launch_mode<kGenericCompact>(mesh, grp, first, grid, smem, (int)tpc, want_normal, stream); break;
     }
     ++launches;
