@@ -355,6 +355,21 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
       if ((rc = upload<int>(mesh, rec_blend.data(), rec_blend.size(), &m.group_rec_blend)) != P3CS_OK) return bail(rc);
       if ((rc = upload<int>(mesh, ent_off.data(), ent_off.size(), &m.grec_entry_offsets)) != P3CS_OK) return bail(rc);
       if ((rc = upload<uint2>(mesh, ent.data(), ent.size(), &m.grec_entries)) != P3CS_OK) return bail(rc);
+      // fixed-width blocks: the first four entries of every group record, count in bits 16..31
+      const size_t nrec_total = rec_blend.size();
+      std::vector<uint4> blocks(std::max<size_t>(nrec_total * 2, 2), make_uint4(0, 0, 0, 0));
+      for (size_t r = 0; r < nrec_total; ++r) {
+        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int beg = ent_off[r], cnt = ent_off[r + 1] - ent_off[r];
+        for (int k = 0; k < std::min(cnt, 4); ++k) {
+          w[2 * k] = ent[beg + k].x;
+          w[2 * k + 1] = ent[beg + k].y;
+        }
+        w[0] |= (uint32_t)std::min(cnt, 0xFFFF) << 16;
+        blocks[2 * r] = make_uint4(w[0], w[1], w[2], w[3]);
+        blocks[2 * r + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      if ((rc = upload<uint4>(mesh, blocks.data(), blocks.size(), &m.grec_blocks)) != P3CS_OK) return bail(rc);
     }
     m.index_bytes = wide ? 4 : 2;
     const void *dev_index = nullptr;
@@ -441,7 +456,8 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
   }
   {
     const char *path = getenv("P3CS_PATH");
-    mesh->use_strip = strip_smem_bytes(m) <= 200 * 1024 && !(path != nullptr && strcmp(path, "wide") == 0);
+    mesh->use_strip = strip_smem_bytes(m) <= 200 * 1024 && m.num_transforms < 65536 &&
+                      !(path != nullptr && strcmp(path, "wide") == 0);
   }
   // uploads read from host vectors that die at scope exit: finish them now
   cudaError_t err = cudaStreamSynchronize(ctx->stream);

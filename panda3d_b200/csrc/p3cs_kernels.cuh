@@ -63,6 +63,8 @@ struct MeshDev {
   const int *group_rec_blend;       // global blend id of every group record (selection hook)
   const int *grec_entry_offsets;    // CSR of the blend entries, in group-record order
   const uint2 *grec_entries;        // (palette index, float weight bits) per entry
+  const uint4 *grec_blocks;         // 2 x uint4 per group record: its first four entries, the
+                                    // entry count in the high half of the first index
 };
 
 constexpr int kTileRows = 256;

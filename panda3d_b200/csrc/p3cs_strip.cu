@@ -1,12 +1,14 @@
 // p3cs_strip.cu -- the fused hot-path kernel (sm_100a): one launch animates a whole crowd.
 //
-// Work unit = a strip: `tiles_per_cta` consecutive 256-row tiles of ONE instance.  Per strip the
-// CTA stages the instance's joint-matrix palette in shared memory once; then, per tile:
-//   * the tile's rows arrive by a TMA bulk copy (cp.async.bulk global->shared, completion on an
-//     mbarrier), double buffered so the next tile is in flight while this one is computed;
-//   * phase A: one thread per DISTINCT blend of the tile accumulates sum_i w_i * M_i from the
+// Work unit = a strip: consecutive record groups (each `group_tiles` 256-row tiles) of ONE
+// instance.  Per strip the CTA stages the instance's joint-matrix palette in shared memory once;
+// then, per record group:
+//   * phase A: one thread per DISTINCT blend of the group accumulates sum_i w_i * M_i from the
 //     shared palette (TransformBlend::update_blend, panda/src/gobj/transformBlend.cxx:211-233),
 //     derives the normal matrix (geomVertexData.cxx:1811-1840) and leaves a record in smem;
+// and per tile of the group:
+//   * the tile's rows arrive by a TMA bulk copy (cp.async.bulk global->shared, completion on an
+//     mbarrier), double buffered so the next tile is in flight while this one is computed;
 //   * phase B: one thread per row applies the sparse morph deltas (geomVertexData.cxx:1462-1543)
 //     and the blend record of the row (:1558-1751) to the staged row, in place;
 //   * the finished tile leaves by a TMA bulk store (shared->global, bulk_group).
@@ -23,7 +25,6 @@
 namespace p3cs {
 
 constexpr int kStripThreads = kTileRows;  // one thread per row of a tile
-constexpr int kPalStride4 = 5;            // palette matrix stride in smem: 5 x float4 (80 B): LDS.128 without 4-way conflicts
 
 // kFastPN24: the egg loader's packed [vertex(3f) normal(3f)] rows (stride 24): the whole row is
 // moved with three conflict-free 64-bit shared-memory accesses each way.
@@ -31,14 +32,13 @@ enum StripMode { kGenericCompact = 0, kGenericFull = 1, kFastP = 2, kFastPN = 3,
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {
     asm volatile(
@@ -48,32 +48,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(bar), "r"(parity)
         : "memory");
   } while (!done);
 }
 // TMA 1-D bulk copies (SASS: UBLKCP); sizes and addresses are multiples of 16 bytes.
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src_gmem), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
-               : "memory");
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Shared-memory plan: [2 mbarriers][palette rows x cols 0..2: T x 48 B][palette column 3: T x 16 B]
+// [records][tile buffer 0][tile buffer 1].  The 48-byte palette stride keeps the LDS.128 of
+// phase A spread over all bank groups; column 3 is only read when a palette is not affine.
 struct StripSmem {
-  int palette_off, records_off, tiles_off, total;
+  int pal3_off, palc_off, records_off, tiles_off, total;
 };
 
 __host__ __device__ inline StripSmem strip_layout(const MeshDev &m) {
   StripSmem s;
-  s.palette_off = 16;  // two mbarriers
-  s.records_off = s.palette_off + m.num_transforms * kPalStride4 * 16;
+  s.pal3_off = 16;
+  s.palc_off = s.pal3_off + m.num_transforms * 48;
+  s.records_off = s.palc_off + m.num_transforms * 16;
   const int rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
   s.tiles_off = (s.records_off + (m.max_group_records > 0 ? m.max_group_records : 1) * rec_bytes + 127) & ~127;
   s.total = s.tiles_off + 2 * m.tile_bytes;
@@ -117,75 +120,73 @@ static __device__ __noinline__ void normal_general_inverse(float m00, float m01,
   rec[21] = 1.0f;
 }
 
-// One compact record (22 floats) of one blend, written to shared memory.
+// acc += M_j * weight for one entry (LMatrix4f::accumulate, lmatrix4_src.I:1311-1336).
 // AFFINE: every palette matrix has column 3 == (0,0,0,1) exactly, so the blended column 3 is
 // (0,0,0,sum w) and needs no multiplies (sum w is accumulated in the reference's order).
 template <bool AFFINE>
-__device__ __forceinline__ void accumulate_entry(const float4 *pal, uint2 e, float (&m)[4][3], float (&c3)[4]) {
-  const float weight = __uint_as_float(e.y);
-  const float4 *mat = pal + e.x * kPalStride4;
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {  // LMatrix4f::accumulate, lmatrix4_src.I:1311-1336
-    const float4 row = mat[r];
-    m[r][0] += row.x * weight;
-    m[r][1] += row.y * weight;
-    m[r][2] += row.z * weight;
-    if (!AFFINE) c3[r] += row.w * weight;
+__device__ __forceinline__ void accumulate_entry(const float4 *pal3, const float4 *palc, uint32_t j, float weight, float (&m)[12],
+                                                 float (&c3)[4]) {
+  const float4 a = pal3[j * 3], b = pal3[j * 3 + 1], c = pal3[j * 3 + 2];
+  m[0] += a.x * weight; m[1] += a.y * weight; m[2] += a.z * weight; m[3] += a.w * weight;
+  m[4] += b.x * weight; m[5] += b.y * weight; m[6] += b.z * weight; m[7] += b.w * weight;
+  m[8] += c.x * weight; m[9] += c.y * weight; m[10] += c.z * weight; m[11] += c.w * weight;
+  if (AFFINE) {
+    c3[3] += weight;  // 1.0f * weight == weight
+  } else {
+    const float4 d = palc[j];
+    c3[0] += d.x * weight; c3[1] += d.y * weight; c3[2] += d.z * weight; c3[3] += d.w * weight;
   }
-  if (AFFINE) c3[3] += weight;  // 1.0f * weight == weight
 }
 
+// One compact record (22 floats) of one blend, written to shared memory.  `q0`,`q1` hold the
+// record's fixed block of up to four (palette index, weight) entries, count in q0.x >> 16;
+// longer blends read the CSR arrays.
 template <bool AFFINE>
-__device__ __forceinline__ void compact_record(const float4 *pal, const uint2 *entries, int beg, int end, int cs, int want_normal,
-                                               float *rec) {
-  float m[4][3];
+__device__ __forceinline__ void compact_record(const float4 *pal3, const float4 *palc, uint4 q0, uint4 q1, const MeshDev &mesh,
+                                               int grec, int want_normal, float *rec) {
+  float m[12];  // m[r*3+c]: rows 0..3 x columns 0..2
   float c3[4];
-  if (beg == end) {  // empty TransformBlend: identity (transformBlend.I:362-366)
+  const uint32_t count = q0.x >> 16;
+  if (count == 0) {  // empty TransformBlend: identity (transformBlend.I:362-366)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) m[i][j] = (i == j) ? 1.0f : 0.0f;
-      c3[i] = (i == 3) ? 1.0f : 0.0f;
-    }
+    for (int i = 0; i < 12; ++i) m[i] = (i == 0 || i == 4 || i == 8) ? 1.0f : 0.0f;
+    c3[0] = c3[1] = c3[2] = 0.0f;
+    c3[3] = 1.0f;
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) m[i][j] = 0.0f;
-      c3[i] = 0.0f;
-    }
-    if (end - beg == 4) {  // the common 4-weight blend: straight-line, all loads issued up front
-      const uint2 e0 = __ldg(entries + beg), e1 = __ldg(entries + beg + 1), e2 = __ldg(entries + beg + 2), e3 = __ldg(entries + beg + 3);
-      accumulate_entry<AFFINE>(pal, e0, m, c3);
-      accumulate_entry<AFFINE>(pal, e1, m, c3);
-      accumulate_entry<AFFINE>(pal, e2, m, c3);
-      accumulate_entry<AFFINE>(pal, e3, m, c3);
+    for (int i = 0; i < 12; ++i) m[i] = 0.0f;
+    c3[0] = c3[1] = c3[2] = c3[3] = 0.0f;
+    if (count <= 4) {
+      accumulate_entry<AFFINE>(pal3, palc, q0.x & 0xffffu, __uint_as_float(q0.y), m, c3);
+      if (count > 1) accumulate_entry<AFFINE>(pal3, palc, q0.z, __uint_as_float(q0.w), m, c3);
+      if (count > 2) accumulate_entry<AFFINE>(pal3, palc, q1.x, __uint_as_float(q1.y), m, c3);
+      if (count > 3) accumulate_entry<AFFINE>(pal3, palc, q1.z, __uint_as_float(q1.w), m, c3);
     } else {
-      for (int e = beg; e < end; ++e) accumulate_entry<AFFINE>(pal, __ldg(entries + e), m, c3);
+      const int beg = __ldg(mesh.grec_entry_offsets + grec), end = __ldg(mesh.grec_entry_offsets + grec + 1);
+      for (int e = beg; e < end; ++e) {
+        const uint2 en = __ldg(mesh.grec_entries + e);
+        accumulate_entry<AFFINE>(pal3, palc, en.x, __uint_as_float(en.y), m, c3);
+      }
     }
   }
   float2 *r2 = reinterpret_cast<float2 *>(rec);
-  r2[0] = make_float2(m[0][0], m[0][1]);
-  r2[1] = make_float2(m[0][2], m[1][0]);
-  r2[2] = make_float2(m[1][1], m[1][2]);
-  r2[3] = make_float2(m[2][0], m[2][1]);
-  r2[4] = make_float2(m[2][2], m[3][0]);
-  r2[5] = make_float2(m[3][1], m[3][2]);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) r2[i] = make_float2(m[2 * i], m[2 * i + 1]);
   if (!want_normal) return;
 
   // the C_normal prelude of do_transform_vector_column, geomVertexData.cxx:1811-1840
-  const float sq0 = m[0][0] * m[0][0] + m[0][1] * m[0][1] + m[0][2] * m[0][2];
-  const float sq1 = m[1][0] * m[1][0] + m[1][1] * m[1][1] + m[1][2] * m[1][2];
-  const float sq2 = m[2][0] * m[2][0] + m[2][1] * m[2][1] + m[2][2] * m[2][2];
+  const float sq0 = m[0] * m[0] + m[1] * m[1] + m[2] * m[2];
+  const float sq1 = m[3] * m[3] + m[4] * m[4] + m[5] * m[5];
+  const float sq2 = m[6] * m[6] + m[7] * m[7] + m[8] * m[8];
   if (thr_equal(sq0, sq1, 2.0e-3f) && thr_equal(sq0, sq2, 2.0e-3f)) {
     if (thr_equal(sq0, 1.0f, 2.0e-3f)) {  // xform = mat
-      r2[6] = make_float2(m[0][0], m[0][1]);
-      r2[7] = make_float2(m[0][2], m[1][0]);
-      r2[8] = make_float2(m[1][1], m[1][2]);
-      r2[9] = make_float2(m[2][0], m[2][1]);
-      r2[10] = make_float2(m[2][2], 0.0f);
+      r2[6] = make_float2(m[0], m[1]);
+      r2[7] = make_float2(m[2], m[3]);
+      r2[8] = make_float2(m[4], m[5]);
+      r2[9] = make_float2(m[6], m[7]);
+      r2[10] = make_float2(m[8], 0.0f);
     } else {
-      normal_uniform_scale(m[0][0], m[0][1], m[0][2], m[1][0], m[1][1], m[1][2], m[2][0], m[2][1], m[2][2], cs, rec);
+      normal_uniform_scale(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], mesh.coordinate_system, rec);
     }
     return;
   }
@@ -194,13 +195,11 @@ __device__ __forceinline__ void compact_record(const float4 *pal, const uint2 *e
                              : (thr_equal(c3[0], 0.0f, P3CS_NEARLY_ZERO) && thr_equal(c3[1], 0.0f, P3CS_NEARLY_ZERO) &&
                                 thr_equal(c3[2], 0.0f, P3CS_NEARLY_ZERO) && thr_equal(c3[3], 1.0f, P3CS_NEARLY_ZERO));
   if (!affine) {
-    normal_general_inverse(m[0][0], m[0][1], m[0][2], c3[0], m[1][0], m[1][1], m[1][2], c3[1], m[2][0], m[2][1], m[2][2], c3[2],
-                           m[3][0], m[3][1], m[3][2], c3[3], rec);
+    normal_general_inverse(m[0], m[1], m[2], c3[0], m[3], m[4], m[5], c3[1], m[6], m[7], m[8], c3[2], m[9], m[10], m[11], c3[3], rec);
     return;
   }
   // LMatrix3f::invert_from (lmatrix3_src.I:917-965), transposed on the fly: N(i,j) = inv(j,i)
-  float det = (m[0][0] * det2(m[1][1], m[1][2], m[2][1], m[2][2]) - m[0][1] * det2(m[1][0], m[1][2], m[2][0], m[2][2]) +
-               m[0][2] * det2(m[1][0], m[1][1], m[2][0], m[2][1]));
+  float det = (m[0] * det2(m[4], m[5], m[7], m[8]) - m[1] * det2(m[3], m[5], m[6], m[8]) + m[2] * det2(m[3], m[4], m[6], m[7]));
   if (thr_zero(det, P3CS_NEARLY_ZERO * P3CS_NEARLY_ZERO)) {
     // singular: the reference leaves `xform` uninitialised here; we define it as the identity
     r2[6] = make_float2(1.0f, 0.0f);
@@ -211,58 +210,65 @@ __device__ __forceinline__ void compact_record(const float4 *pal, const uint2 *e
     return;
   }
   det = 1.0f / det;
-  const float i00 = det * det2(m[1][1], m[1][2], m[2][1], m[2][2]);
-  const float i10 = -det * det2(m[1][0], m[1][2], m[2][0], m[2][2]);
-  const float i20 = det * det2(m[1][0], m[1][1], m[2][0], m[2][1]);
-  const float i01 = -det * det2(m[0][1], m[0][2], m[2][1], m[2][2]);
-  const float i11 = det * det2(m[0][0], m[0][2], m[2][0], m[2][2]);
-  const float i21 = -det * det2(m[0][0], m[0][1], m[2][0], m[2][1]);
-  const float i02 = det * det2(m[0][1], m[0][2], m[1][1], m[1][2]);
-  const float i12 = -det * det2(m[0][0], m[0][2], m[1][0], m[1][2]);
-  const float i22 = det * det2(m[0][0], m[0][1], m[1][0], m[1][1]);
-  r2[6] = make_float2(i00, i10);   // N row 0 = inv column 0
-  r2[7] = make_float2(i20, i01);   // N(0,2), N(1,0)
-  r2[8] = make_float2(i11, i21);   // N(1,1), N(1,2)
-  r2[9] = make_float2(i02, i12);   // N(2,0), N(2,1)
-  r2[10] = make_float2(i22, 1.0f); // N(2,2), normalize
+  const float i00 = det * det2(m[4], m[5], m[7], m[8]);
+  const float i10 = -det * det2(m[3], m[5], m[6], m[8]);
+  const float i20 = det * det2(m[3], m[4], m[6], m[7]);
+  const float i01 = -det * det2(m[1], m[2], m[7], m[8]);
+  const float i11 = det * det2(m[0], m[2], m[6], m[8]);
+  const float i21 = -det * det2(m[0], m[1], m[6], m[7]);
+  const float i02 = det * det2(m[1], m[2], m[4], m[5]);
+  const float i12 = -det * det2(m[0], m[2], m[3], m[5]);
+  const float i22 = det * det2(m[0], m[1], m[3], m[4]);
+  r2[6] = make_float2(i00, i10);    // N row 0 = inv column 0
+  r2[7] = make_float2(i20, i01);    // N(0,2), N(1,0)
+  r2[8] = make_float2(i11, i21);    // N(1,1), N(1,2)
+  r2[9] = make_float2(i02, i12);    // N(2,0), N(2,1)
+  r2[10] = make_float2(i22, 1.0f);  // N(2,2), normalize
 }
 
 // ------------------------------------------------------------------ phase B, specialised columns
-// KIND: 1 point, 2 vector, 3 normal (float32 x 3), record already in registers.
+// KIND: 1 point, 2 vector, 3 normal (float32 x 3); f = the 22-float record in registers.
 template <int KIND>
-__device__ __forceinline__ void fast_column(float *cell, const float (&m)[4][3], const float (&n)[3][3], bool normalize) {
+__device__ __forceinline__ void fast_column(float *cell, const float (&f)[22]) {
   const float v0 = cell[0], v1 = cell[1], v2 = cell[2];
   float r0, r1, r2;
   if (KIND == 1) {  // LMatrix4f::xform_point
-    r0 = v0 * m[0][0] + v1 * m[1][0] + v2 * m[2][0] + m[3][0];
-    r1 = v0 * m[0][1] + v1 * m[1][1] + v2 * m[2][1] + m[3][1];
-    r2 = v0 * m[0][2] + v1 * m[1][2] + v2 * m[2][2] + m[3][2];
+    r0 = v0 * f[0] + v1 * f[3] + v2 * f[6] + f[9];
+    r1 = v0 * f[1] + v1 * f[4] + v2 * f[7] + f[10];
+    r2 = v0 * f[2] + v1 * f[5] + v2 * f[8] + f[11];
   } else if (KIND == 2) {  // xform_vec with the blend matrix
-    r0 = v0 * m[0][0] + v1 * m[1][0] + v2 * m[2][0];
-    r1 = v0 * m[0][1] + v1 * m[1][1] + v2 * m[2][1];
-    r2 = v0 * m[0][2] + v1 * m[1][2] + v2 * m[2][2];
+    r0 = v0 * f[0] + v1 * f[3] + v2 * f[6];
+    r1 = v0 * f[1] + v1 * f[4] + v2 * f[7];
+    r2 = v0 * f[2] + v1 * f[5] + v2 * f[8];
   } else {  // xform_vec with the normal matrix (+ normalize)
-    r0 = v0 * n[0][0] + v1 * n[1][0] + v2 * n[2][0];
-    r1 = v0 * n[0][1] + v1 * n[1][1] + v2 * n[2][1];
-    r2 = v0 * n[0][2] + v1 * n[1][2] + v2 * n[2][2];
-    if (normalize) normalize3(r0, r1, r2);
+    r0 = v0 * f[12] + v1 * f[15] + v2 * f[18];
+    r1 = v0 * f[13] + v1 * f[16] + v2 * f[19];
+    r2 = v0 * f[14] + v1 * f[17] + v2 * f[20];
+    if (f[21] != 0.0f) normalize3(r0, r1, r2);
   }
   cell[0] = r0;
   cell[1] = r1;
   cell[2] = r2;
 }
 
-template <int MODE>
+template <int MODE, bool SELECT>
 __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
     strip_kernel(MeshDev mesh, GroupDev grp, int first_instance, int groups_per_cta, int want_normal) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr bool FULL = MODE == kGenericFull;
+  constexpr bool FAST = MODE >= kFastP;
   constexpr int REC = FULL ? kRecFull : kRecCompact;
   const StripSmem lay = strip_layout(mesh);
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
-  float4 *pal = reinterpret_cast<float4 *>(smem + lay.palette_off);
+  float *pal3f = reinterpret_cast<float *>(smem + lay.pal3_off);
+  float *palcf = reinterpret_cast<float *>(smem + lay.palc_off);
+  const float4 *pal3 = reinterpret_cast<const float4 *>(pal3f);
+  const float4 *palc = reinterpret_cast<const float4 *>(palcf);
   float *recs = reinterpret_cast<float *>(smem + lay.records_off);
   uint8_t *tiles = smem + lay.tiles_off;
+  const uint32_t mbar0 = smem_u32(smem);
+  const uint32_t tiles_s = smem_u32(tiles);
+  const int tile_bytes = mesh.tile_bytes;
+  const int stride0 = mesh.stride[0];
 
   const int tid = threadIdx.x;
   const int inst = first_instance + blockIdx.y;
@@ -273,20 +279,25 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   const int t1 = min(mesh.num_tiles, g1 * mesh.group_tiles);
 
   if (tid == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
+    mbar_init(mbar0, 1);
+    mbar_init(mbar0 + 8, 1);
     fence_proxy_async();  // make the initialised barriers visible to the async (TMA) proxy
   }
-  // palette: T x 64 B, coalesced 128-bit loads, re-strided to 80 B in shared memory; on the way
-  // check whether every matrix is affine (column 3 == (0,0,0,1) exactly)
+  // palette: T x 64 B by coalesced 128-bit loads; rows x columns 0..2 packed to 48 B, column 3
+  // aside; on the way check whether every matrix is affine (column 3 == (0,0,0,1) exactly)
   int non_affine = 0;
   {
     const float4 *gp = reinterpret_cast<const float4 *>(grp.palettes + (size_t)inst * mesh.num_transforms * 16);
     const int n4 = mesh.num_transforms * 4;
     for (int i = tid; i < n4; i += kStripThreads) {
       const float4 row = __ldg(gp + i);
-      pal[(i >> 2) * kPalStride4 + (i & 3)] = row;
-      non_affine |= (row.w != ((i & 3) == 3 ? 1.0f : 0.0f));
+      const int j = i >> 2, r = i & 3;
+      float *d = pal3f + j * 12 + r * 3;
+      d[0] = row.x;
+      d[1] = row.y;
+      d[2] = row.z;
+      palcf[i] = row.w;
+      non_affine |= (row.w != (r == 3 ? 1.0f : 0.0f));
     }
   }
   non_affine = __syncthreads_or(non_affine);
@@ -295,23 +306,25 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   auto issue_tile_load = [&](int t, int buf) {
     const int row0 = t * kTileRows;
     const int rows = min(kTileRows, mesh.num_rows - row0);
-    if (MODE >= kFastP) {  // single output array
-      const uint32_t bytes = (uint32_t)((rows * mesh.stride[0] + 15) & ~15);
-      mbar_expect_tx(&mbar[buf], bytes);
-      bulk_g2s(tiles + buf * mesh.tile_bytes, mesh.src[0] + (size_t)row0 * mesh.stride[0], bytes, &mbar[buf]);
+    const uint32_t bar = mbar0 + 8 * buf;
+    if (FAST) {  // single output array
+      const uint32_t bytes = (uint32_t)((rows * stride0 + 15) & ~15);
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(tiles_s + buf * tile_bytes, mesh.src[0] + (size_t)row0 * stride0, bytes, bar);
       return;
     }
     uint32_t total = 0;
     for (int o = 0; o < mesh.num_outputs; ++o) total += (uint32_t)((rows * mesh.stride[o] + 15) & ~15);
-    mbar_expect_tx(&mbar[buf], total);
+    mbar_expect_tx(bar, total);
     for (int o = 0; o < mesh.num_outputs; ++o) {
       const uint32_t bytes = (uint32_t)((rows * mesh.stride[o] + 15) & ~15);
-      bulk_g2s(tiles + buf * mesh.tile_bytes + mesh.tile_out_offset[o], mesh.src[o] + (size_t)row0 * mesh.stride[o], bytes, &mbar[buf]);
+      bulk_g2s(tiles_s + buf * tile_bytes + mesh.tile_out_offset[o], mesh.src[o] + (size_t)row0 * mesh.stride[o], bytes, bar);
     }
   };
   if (tid == 0) issue_tile_load(t0, 0);
 
   const float *sliders = grp.sliders + (size_t)inst * mesh.num_sliders;
+  const bool has_index = mesh.index_bytes != 0;
   int it = 0;  // tiles processed by this CTA so far (buffer / mbarrier phase bookkeeping)
 
   for (int g = g0; g < g1; ++g) {
@@ -319,19 +332,21 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
     const int rbeg = __ldg(mesh.group_rec_offsets + g);
     const int nrec = __ldg(mesh.group_rec_offsets + g + 1) - rbeg;
     for (int b = tid; b < nrec; b += kStripThreads) {
-      const int beg = __ldg(mesh.grec_entry_offsets + rbeg + b);
-      const int end = __ldg(mesh.grec_entry_offsets + rbeg + b + 1);
       if (FULL) {
         Mat4 acc, x;
-        blend_accumulate_packed([&](int j, int r) { return pal[j * kPalStride4 + r]; }, mesh.grec_entries, beg, end, acc);
+        const int beg = __ldg(mesh.grec_entry_offsets + rbeg + b), end = __ldg(mesh.grec_entry_offsets + rbeg + b + 1);
+        blend_accumulate_packed(
+            [&](int j, int r) { return make_float4(pal3f[j * 12 + r * 3], pal3f[j * 12 + r * 3 + 1], pal3f[j * 12 + r * 3 + 2], palcf[j * 4 + r]); },
+            mesh.grec_entries, beg, end, acc);
         bool normalize = false;
         if (want_normal) normalize = normal_xform(acc, mesh.coordinate_system, x);
         else x = acc;
         store_record<true>(recs + (size_t)b * REC, acc, x, normalize);
-      } else if (non_affine) {
-        compact_record<false>(pal, mesh.grec_entries, beg, end, mesh.coordinate_system, want_normal, recs + (size_t)b * REC);
       } else {
-        compact_record<true>(pal, mesh.grec_entries, beg, end, mesh.coordinate_system, want_normal, recs + (size_t)b * REC);
+        const uint4 *blk = mesh.grec_blocks + (size_t)(rbeg + b) * 2;
+        const uint4 q0 = __ldg(blk), q1 = __ldg(blk + 1);
+        if (non_affine) compact_record<false>(pal3, palc, q0, q1, mesh, rbeg + b, want_normal, recs + (size_t)b * REC);
+        else compact_record<true>(pal3, palc, q0, q1, mesh, rbeg + b, want_normal, recs + (size_t)b * REC);
       }
     }
     __syncthreads();  // every record of the group is in shared memory
@@ -349,17 +364,18 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
       const int row = t * kTileRows + tid;
       const bool live = row < mesh.num_rows;
       int local = 0xFFFF;
-      if (live && mesh.index_bytes != 0) local = __ldg(mesh.row_local + row);
-      if (live && grp.selection != nullptr && blockIdx.y == 0)
-        grp.selection[row] = local == 0xFFFF ? -1 : __ldg(mesh.group_rec_blend + rbeg + local);
+      if (live && has_index) local = __ldg(mesh.row_local + row);
+      if (SELECT) {
+        if (live && blockIdx.y == 0) grp.selection[row] = local == 0xFFFF ? -1 : __ldg(mesh.group_rec_blend + rbeg + local);
+      }
       const bool skinned = local != 0xFFFF;
 
-      mbar_wait(&mbar[buf], (it >> 1) & 1);  // the tile's rows have landed
+      mbar_wait(mbar0 + 8 * buf, (it >> 1) & 1);  // the tile's rows have landed
 
       // -------------- phase B: one thread per row, in place on the staged tile
-      uint8_t *tile = tiles + buf * mesh.tile_bytes;
-      if (MODE >= kFastP) {
-        if (live && skinned) {
+      uint8_t *tile = tiles + buf * tile_bytes;
+      if (FAST) {
+        if (skinned) {
           const float2 *p = reinterpret_cast<const float2 *>(recs + (size_t)local * kRecCompact);
           float f[22];
 #pragma unroll
@@ -368,32 +384,22 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
             f[2 * i] = v.x;
             f[2 * i + 1] = v.y;
           }
-          float m[4][3], n[3][3];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) m[i][j] = f[i * 3 + j];
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) n[i][j] = f[12 + i * 3 + j];
-          const bool normalize = f[21] != 0.0f;
           if (MODE == kFastPN24) {
-            float2 *rowp = reinterpret_cast<float2 *>(tile + (size_t)tid * 24);
+            float2 *rowp = reinterpret_cast<float2 *>(tile + tid * 24);
             const float2 a = rowp[0], b2 = rowp[1], c = rowp[2];
             float v[6] = {a.x, a.y, b2.x, b2.y, c.x, c.y};
-            fast_column<1>(v, m, n, normalize);
-            fast_column<3>(v + 3, m, n, normalize);
+            fast_column<1>(v, f);
+            fast_column<3>(v + 3, f);
             rowp[0] = make_float2(v[0], v[1]);
             rowp[1] = make_float2(v[2], v[3]);
             rowp[2] = make_float2(v[4], v[5]);
           } else {
-            uint8_t *rowp = tile + (size_t)tid * mesh.stride[0];
-            fast_column<1>(reinterpret_cast<float *>(rowp + mesh.dyn[0].start), m, n, normalize);
-            if (MODE >= kFastPN) fast_column<3>(reinterpret_cast<float *>(rowp + mesh.dyn[1].start), m, n, normalize);
+            uint8_t *rowp = tile + tid * stride0;
+            fast_column<1>(reinterpret_cast<float *>(rowp + mesh.dyn[0].start), f);
+            if (MODE >= kFastPN) fast_column<3>(reinterpret_cast<float *>(rowp + mesh.dyn[1].start), f);
             if (MODE >= kFastPNVV) {
-              fast_column<2>(reinterpret_cast<float *>(rowp + mesh.dyn[2].start), m, n, normalize);
-              fast_column<2>(reinterpret_cast<float *>(rowp + mesh.dyn[3].start), m, n, normalize);
+              fast_column<2>(reinterpret_cast<float *>(rowp + mesh.dyn[2].start), f);
+              fast_column<2>(reinterpret_cast<float *>(rowp + mesh.dyn[3].start), f);
             }
           }
         }
@@ -417,13 +423,14 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
       if (tid == 0) {
         const int row0 = t * kTileRows;
         const int rows = min(kTileRows, mesh.num_rows - row0);
-        if (MODE >= kFastP) {
-          const uint32_t bytes = (uint32_t)((rows * mesh.stride[0] + 15) & ~15);
-          bulk_s2g(grp.out[0] + (size_t)inst * grp.pitch[0] + (size_t)row0 * mesh.stride[0], tile, bytes);
+        const uint32_t tile_s = tiles_s + buf * tile_bytes;
+        if (FAST) {
+          const uint32_t bytes = (uint32_t)((rows * stride0 + 15) & ~15);
+          bulk_s2g(grp.out[0] + (size_t)inst * grp.pitch[0] + (size_t)row0 * stride0, tile_s, bytes);
         } else {
           for (int o = 0; o < mesh.num_outputs; ++o) {
             const uint32_t bytes = (uint32_t)((rows * mesh.stride[o] + 15) & ~15);
-            bulk_s2g(grp.out[o] + (size_t)inst * grp.pitch[o] + (size_t)row0 * mesh.stride[o], tile + mesh.tile_out_offset[o], bytes);
+            bulk_s2g(grp.out[o] + (size_t)inst * grp.pitch[o] + (size_t)row0 * mesh.stride[o], tile_s + mesh.tile_out_offset[o], bytes);
           }
         }
         bulk_commit();
@@ -450,10 +457,21 @@ static int pick_mode(const MeshDev &mesh) {
 }
 
 template <int MODE>
-static void launch_mode(const MeshDev &mesh, const GroupDev &grp, int first, dim3 grid, size_t smem, int tpc, int want_normal,
+static void launch_mode(const MeshDev &mesh, const GroupDev &grp, int first, dim3 grid, size_t smem, int gpc, int want_normal,
                         cudaStream_t stream) {
-  cudaFuncSetAttribute(strip_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  strip_kernel<MODE><<<grid, kStripThreads, smem, stream>>>(mesh, grp, first, tpc, want_normal);
+  if (grp.selection != nullptr) {
+    cudaFuncSetAttribute(strip_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    strip_kernel<MODE, true><<<grid, kStripThreads, smem, stream>>>(mesh, grp, first, gpc, want_normal);
+  } else {
+    static thread_local int configured_device = -1;  // the attribute is sticky per function and device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != configured_device) {
+      cudaFuncSetAttribute(strip_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      configured_device = dev;
+    }
+    strip_kernel<MODE, false><<<grid, kStripThreads, smem, stream>>>(mesh, grp, first, gpc, want_normal);
+  }
 }
 
 int launch_strip(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, int sm_count, cudaStream_t stream) {
@@ -465,23 +483,23 @@ int launch_strip(const MeshDev &mesh, const GroupDev &grp, int first_instance, i
   // strips of whole record groups: enough of them to fill every SM several times over, yet as
   // long as possible so the palette is staged rarely
   const long long target_ctas = (long long)sm_count * 24;
-  long long tpc = ((long long)mesh.num_groups * count + target_ctas - 1) / target_ctas;
-  if (tpc < 1) tpc = 1;
-  if (tpc > mesh.num_groups) tpc = mesh.num_groups;
-  const int strips = (mesh.num_groups + (int)tpc - 1) / (int)tpc;
-  tpc = (mesh.num_groups + strips - 1) / strips;  // equal-length strips
+  long long gpc = ((long long)mesh.num_groups * count + target_ctas - 1) / target_ctas;
+  if (gpc < 1) gpc = 1;
+  if (gpc > mesh.num_groups) gpc = mesh.num_groups;
+  const int strips = (mesh.num_groups + (int)gpc - 1) / (int)gpc;
+  gpc = (mesh.num_groups + strips - 1) / strips;  // equal-length strips
   int launches = 0;
   for (int c0 = 0; c0 < count; c0 += 65535) {
     const int cn = count - c0 < 65535 ? count - c0 : 65535;
     const dim3 grid(strips, cn);
     const int first = first_instance + c0;
     switch (mode) {
-    case kGenericFull: launch_mode<kGenericFull>(mesh, grp, first, grid, smem, (int)tpc, want_normal, stream); break;
-    case kFastP: launch_mode<kFastP>(mesh, grp, first, grid, smem, (int)tpc, want_normal, stream); break;
-    case kFastPN: launch_mode<kFastPN>(mesh, grp, first, grid, smem, (int)tpc, want_normal, stream); break;
-    case kFastPNVV: launch_mode<kFastPNVV>(mesh, grp, first, grid, smem, (int)tpc, want_normal, stream); break;
-    case kFastPN24: launch_mode<kFastPN24>(mesh, grp, first, grid, smem, (int)tpc, want_normal, stream); break;
-    default: launch_mode<kGenericCompact>(mesh, grp, first, grid, smem, (int)tpc, want_normal, stream); break;
+    case kGenericFull: launch_mode<kGenericFull>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
+    case kFastP: launch_mode<kFastP>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
+    case kFastPN: launch_mode<kFastPN>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
+    case kFastPNVV: launch_mode<kFastPNVV>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
+    case kFastPN24: launch_mode<kFastPN24>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
+    default: launch_mode<kGenericCompact>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
     }
     ++launches;
   }
