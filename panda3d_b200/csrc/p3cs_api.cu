@@ -357,7 +357,8 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
       if ((rc = upload<uint2>(mesh, ent.data(), ent.size(), &m.grec_entries)) != P3CS_OK) return bail(rc);
       // fixed-width blocks: the first four entries of every group record, count in bits 16..31
       const size_t nrec_total = rec_blend.size();
-      std::vector<uint4> blocks(std::max<size_t>(nrec_total * 2, 2), make_uint4(0, 0, 0, 0));
+      // padded by one CTA's worth of records: the kernel prefetches block (group start + tid)
+      std::vector<uint4> blocks((nrec_total + kTileRows) * 2, make_uint4(0, 0, 0, 0));
       for (size_t r = 0; r < nrec_total; ++r) {
         uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const int beg = ent_off[r], cnt = ent_off[r + 1] - ent_off[r];

@@ -25,6 +25,7 @@
 namespace p3cs {
 
 constexpr int kStripThreads = kTileRows;  // one thread per row of a tile
+constexpr int kTileBufs = 3;              // staged tiles in flight: loading / computing / storing
 
 // kFastPN24: the egg loader's packed [vertex(3f) normal(3f)] rows (stride 24): the whole row is
 // moved with three conflict-free 64-bit shared-memory accesses each way.
@@ -63,10 +64,14 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, uint32_t src_smem, uint
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Shared-memory plan: [2 mbarriers][palette rows x cols 0..2: T x 48 B][palette column 3: T x 16 B]
-// [records][tile buffer 0][tile buffer 1].  The 48-byte palette stride keeps the LDS.128 of
+// Shared-memory plan: [2 x kTileBufs mbarriers][palette rows x cols 0..2: T x 48 B][palette column 3: T x 16 B]
+// [records][kTileBufs tile buffers].  The 48-byte palette stride keeps the LDS.128 of
 // phase A spread over all bank groups; column 3 is only read when a palette is not affine.
 struct StripSmem {
   int pal3_off, palc_off, records_off, tiles_off, total;
@@ -74,12 +79,12 @@ struct StripSmem {
 
 __host__ __device__ inline StripSmem strip_layout(const MeshDev &m) {
   StripSmem s;
-  s.pal3_off = 16;
+  s.pal3_off = 64;
   s.palc_off = s.pal3_off + m.num_transforms * 48;
   s.records_off = s.palc_off + m.num_transforms * 16;
   const int rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
   s.tiles_off = (s.records_off + (m.max_group_records > 0 ? m.max_group_records : 1) * rec_bytes + 127) & ~127;
-  s.total = s.tiles_off + 2 * m.tile_bytes;
+  s.total = s.tiles_off + kTileBufs * m.tile_bytes;
   return s;
 }
 
@@ -278,9 +283,13 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   const int t0 = g0 * mesh.group_tiles;
   const int t1 = min(mesh.num_tiles, g1 * mesh.group_tiles);
 
+  const int lane = tid & 31;
   if (tid == 0) {
-    mbar_init(mbar0, 1);
-    mbar_init(mbar0 + 8, 1);
+#pragma unroll
+    for (int k = 0; k < kTileBufs; ++k) {
+      mbar_init(mbar0 + 8 * k, 1);                                    // full[k]: the tile's bytes have landed
+      mbar_init(mbar0 + 8 * (kTileBufs + k), kStripThreads / 32);     // done[k]: every warp finished phase B
+    }
     fence_proxy_async();  // make the initialised barriers visible to the async (TMA) proxy
   }
   // palette: T x 64 B by coalesced 128-bit loads; rows x columns 0..2 packed to 48 B, column 3
@@ -325,12 +334,26 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
 
   const float *sliders = grp.sliders + (size_t)inst * mesh.num_sliders;
   const bool has_index = mesh.index_bytes != 0;
-  int it = 0;  // tiles processed by this CTA so far (buffer / mbarrier phase bookkeeping)
+  int it = 0;       // tiles processed by this CTA so far
+  int buf = 0;      // it % kTileBufs
+  uint32_t ph = 0;  // (it / kTileBufs) & 1: mbarrier phase parity of the current buffer
+
+  // software prefetch (hides the L2 latency of the static tables): the row's record slot for the
+  // next tile, and this thread's first entry block of the next record group
+  int next_local = 0xFFFF;
+  if (has_index && t0 * kTileRows + tid < mesh.num_rows) next_local = __ldg(mesh.row_local + t0 * kTileRows + tid);
+  int rbeg = __ldg(mesh.group_rec_offsets + g0);
+  int rend = __ldg(mesh.group_rec_offsets + g0 + 1);
+  uint4 pq0 = make_uint4(0, 0, 0, 0), pq1 = pq0;
+  if (!FULL) {  // the table is padded by kStripThreads records, so this never reads out of bounds
+    pq0 = __ldg(mesh.grec_blocks + (size_t)(rbeg + tid) * 2);
+    pq1 = __ldg(mesh.grec_blocks + (size_t)(rbeg + tid) * 2 + 1);
+  }
 
   for (int g = g0; g < g1; ++g) {
     // ---------------- phase A: one thread per distinct blend of this record group
-    const int rbeg = __ldg(mesh.group_rec_offsets + g);
-    const int nrec = __ldg(mesh.group_rec_offsets + g + 1) - rbeg;
+    const int nrec = rend - rbeg;
+    if (g != g0) __syncthreads();  // every warp is done reading the previous group's records
     for (int b = tid; b < nrec; b += kStripThreads) {
       if (FULL) {
         Mat4 acc, x;
@@ -343,34 +366,49 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
         else x = acc;
         store_record<true>(recs + (size_t)b * REC, acc, x, normalize);
       } else {
-        const uint4 *blk = mesh.grec_blocks + (size_t)(rbeg + b) * 2;
-        const uint4 q0 = __ldg(blk), q1 = __ldg(blk + 1);
+        uint4 q0 = pq0, q1 = pq1;
+        if (b != tid) {
+          const uint4 *blk = mesh.grec_blocks + (size_t)(rbeg + b) * 2;
+          q0 = __ldg(blk);
+          q1 = __ldg(blk + 1);
+        }
         if (non_affine) compact_record<false>(pal3, palc, q0, q1, mesh, rbeg + b, want_normal, recs + (size_t)b * REC);
         else compact_record<true>(pal3, palc, q0, q1, mesh, rbeg + b, want_normal, recs + (size_t)b * REC);
       }
     }
     __syncthreads();  // every record of the group is in shared memory
+    const int cur_rbeg = rbeg;
+    if (g + 1 < g1) {  // prefetch for the next group; consumed after this group's tiles
+      rbeg = rend;
+      rend = __ldg(mesh.group_rec_offsets + g + 2);
+      if (!FULL) {
+        pq0 = __ldg(mesh.grec_blocks + (size_t)(rbeg + tid) * 2);
+        pq1 = __ldg(mesh.grec_blocks + (size_t)(rbeg + tid) * 2 + 1);
+      }
+    }
 
     const int gt0 = g * mesh.group_tiles;
     const int gt1 = min(mesh.num_tiles, gt0 + mesh.group_tiles);
-    for (int t = gt0; t < gt1; ++t, ++it) {
-      const int buf = it & 1;
+    for (int t = gt0; t < gt1; ++t) {
       if (tid == 0 && t + 1 < t1) {
-        bulk_wait_read_all();  // the store that last read buffer buf^1 has drained it
-        issue_tile_load(t + 1, buf ^ 1);
+        // the buffer tile t+1 lands in was last read by the store of tile t-2: let the newest
+        // store (tile t-1) stay in flight
+        bulk_wait_read_1();
+        issue_tile_load(t + 1, buf + 1 == kTileBufs ? 0 : buf + 1);
       }
 
       // -------------- per-row selection (integer work, bit-exact)
       const int row = t * kTileRows + tid;
       const bool live = row < mesh.num_rows;
-      int local = 0xFFFF;
-      if (live && has_index) local = __ldg(mesh.row_local + row);
+      const int local = next_local;
+      next_local = 0xFFFF;
+      if (has_index && t + 1 < t1 && row + kTileRows < mesh.num_rows) next_local = __ldg(mesh.row_local + row + kTileRows);
       if (SELECT) {
-        if (live && blockIdx.y == 0) grp.selection[row] = local == 0xFFFF ? -1 : __ldg(mesh.group_rec_blend + rbeg + local);
+        if (live && blockIdx.y == 0) grp.selection[row] = local == 0xFFFF ? -1 : __ldg(mesh.group_rec_blend + cur_rbeg + local);
       }
       const bool skinned = local != 0xFFFF;
 
-      mbar_wait(mbar0 + 8 * buf, (it >> 1) & 1);  // the tile's rows have landed
+      mbar_wait(mbar0 + 8 * buf, ph);  // the tile's rows have landed
 
       // -------------- phase B: one thread per row, in place on the staged tile
       uint8_t *tile = tiles + buf * tile_bytes;
@@ -417,10 +455,14 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
           animate_column<FULL>(mesh, col, c, cell, morph_beg, morph_end, sliders, skinned, rec);
         }
       }
-      fence_proxy_async();  // generic-proxy writes to the tile -> visible to the TMA store
-      __syncthreads();
-
+      // hand the finished tile to the TMA store: every writer orders its generic-proxy writes
+      // before the async proxy, each warp arrives once on done[buf]; no block-wide barrier, so
+      // warps run ahead into the next tile (a different buffer)
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(mbar0 + 8 * (kTileBufs + buf));
       if (tid == 0) {
+        mbar_wait(mbar0 + 8 * (kTileBufs + buf), ph);
         const int row0 = t * kTileRows;
         const int rows = min(kTileRows, mesh.num_rows - row0);
         const uint32_t tile_s = tiles_s + buf * tile_bytes;
@@ -434,6 +476,11 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
           }
         }
         bulk_commit();
+      }
+      ++it;
+      if (++buf == kTileBufs) {
+        buf = 0;
+        ph ^= 1;
       }
     }
   }
