@@ -303,51 +303,63 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
         if (!full) mask[r >> 5] |= 1u << (r & 31);
       }
     // ---- strip-kernel tables: per record group the distinct blends, per row its slot in that list.
-    // Groups are as large as the shared-memory record budget allows (better lane packing and
-    // cross-tile dedup in phase A); a mesh whose rows select blends at random ends up with 1 tile.
+    // Groups are grown greedily, tile by tile, while their distinct blends fit one phase-A pass
+    // (one thread per record) and the shared-memory record budget.
     {
       const int nt = (N + kTileRows - 1) / kTileRows;
       const int rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
-      const int budget = 32 * 1024;
-      std::vector<uint16_t> local;
-      std::vector<int> rec_off, rec_blend, ent_off;
+      const int cap = std::min(kTileRows, (32 * 1024) / rec_bytes);
+      std::vector<uint16_t> local(std::max(N, 1), 0xFFFFu);
+      std::vector<int> rec_off(1, 0), rec_blend, ent_off(1, 0), tile_off(1, 0);
       std::vector<uint2> ent;
-      std::vector<int> stamp(std::max(d->num_blends, 1)), slot(std::max(d->num_blends, 1), 0);
-      int gt = 8, ng = 0, max_rec = 0;
-      for (;; gt >>= 1) {
-        ng = (nt + gt - 1) / gt;
-        local.assign(std::max(N, 1), 0xFFFFu);
-        rec_off.assign(1, 0);
-        rec_blend.clear();
-        ent_off.assign(1, 0);
-        ent.clear();
-        std::fill(stamp.begin(), stamp.end(), -1);
-        max_rec = 0;
-        for (int g = 0; g < ng; ++g) {
-          const int r0 = g * gt * kTileRows, r1 = std::min(N, r0 + gt * kTileRows);
-          int count = 0;
-          for (int r = r0; r < r1; ++r) {
-            if (!full && !((mask[r >> 5] >> (r & 31)) & 1u)) continue;
-            const int b = (int)(wide ? idx32[r] : idx16[r]);
-            if (stamp[b] != g) {
-              stamp[b] = g;
-              slot[b] = count++;
-              rec_blend.push_back(b);
-              for (int e = d->blend_offsets[b]; e < d->blend_offsets[b + 1]; ++e) {
-                uint32_t wbits;
-                memcpy(&wbits, &d->blend_weight[e], 4);
-                ent.push_back(make_uint2((uint32_t)d->blend_transform[e], wbits));
-              }
-              ent_off.push_back((int)ent.size());
-            }
-            local[r] = (uint16_t)slot[b];
+      std::vector<int> stamp(std::max(d->num_blends, 1), -1), slot(std::max(d->num_blends, 1), 0);
+      int ng = 0, max_rec = 0, count = 0;
+      std::vector<int> fresh;  // blends first seen in the tile being added
+      for (int t = 0; t < nt; ++t) {
+        const int r0 = t * kTileRows, r1 = std::min(N, r0 + kTileRows);
+        // distinct blends this tile would add to the open group
+        fresh.clear();
+        for (int r = r0; r < r1; ++r) {
+          if (!full && !((mask[r >> 5] >> (r & 31)) & 1u)) continue;
+          const int b = (int)(wide ? idx32[r] : idx16[r]);
+          if (stamp[b] != ng && stamp[b] != -2 - ng) {
+            stamp[b] = -2 - ng;  // tentatively seen
+            fresh.push_back(b);
           }
+        }
+        if (tile_off.back() != t && count + (int)fresh.size() > cap) {  // close the group before this tile
+          for (int b : fresh) stamp[b] = -1;
           rec_off.push_back(rec_off.back() + count);
           max_rec = std::max(max_rec, count);
+          tile_off.push_back(t);
+          ++ng;
+          count = 0;
+          --t;  // redo this tile in the new group
+          continue;
         }
-        if (gt == 1 || (size_t)max_rec * rec_bytes <= (size_t)budget) break;
+        for (int b : fresh) {
+          stamp[b] = ng;
+          slot[b] = count++;
+          rec_blend.push_back(b);
+          for (int e = d->blend_offsets[b]; e < d->blend_offsets[b + 1]; ++e) {
+            uint32_t wbits;
+            memcpy(&wbits, &d->blend_weight[e], 4);
+            ent.push_back(make_uint2((uint32_t)d->blend_transform[e], wbits));
+          }
+          ent_off.push_back((int)ent.size());
+        }
+        for (int r = r0; r < r1; ++r) {
+          if (!full && !((mask[r >> 5] >> (r & 31)) & 1u)) continue;
+          local[r] = (uint16_t)slot[(int)(wide ? idx32[r] : idx16[r])];
+        }
       }
-      m.group_tiles = gt;
+      if (nt > 0) {
+        rec_off.push_back(rec_off.back() + count);
+        max_rec = std::max(max_rec, count);
+        tile_off.push_back(nt);
+        ++ng;
+      }
+      if ((rc = upload<int>(mesh, tile_off.data(), tile_off.size(), &m.group_tile_offsets)) != P3CS_OK) return bail(rc);
       m.num_groups = ng;
       m.max_group_records = max_rec;
       if ((rc = upload<uint16_t>(mesh, local.data(), local.size(), &m.row_local)) != P3CS_OK) return bail(rc);
@@ -442,18 +454,19 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
     if ((rc = upload<uint32_t>(mesh, keys.data(), keys.size(), &m.morph_keys)) != P3CS_OK) return bail(rc);
     if ((rc = upload<float4>(mesh, deltas.data(), deltas.size(), &m.morph_deltas)) != P3CS_OK) return bail(rc);
   }
-  // ---- tile geometry of the strip kernel
+  // ---- slice geometry of the strip kernel (a slice = the 32 rows one warp stages at a time)
   m.num_tiles = (N + kTileRows - 1) / kTileRows;
-  m.tile_bytes = 0;
+  m.slice_bytes = 0;
   for (int o = 0; o < m.num_outputs; ++o) {
-    m.tile_out_offset[o] = m.tile_bytes;
-    m.tile_bytes += (int)round_up((size_t)kTileRows * m.stride[o], 128);
+    m.slice_out_offset[o] = m.slice_bytes;
+    m.slice_bytes += (int)round_up((size_t)32 * m.stride[o], 128);
   }
   if (m.group_rec_offsets == nullptr) {  // no blend table: one tile per group, zero records each
-    m.group_tiles = 1;
     m.num_groups = m.num_tiles;
-    std::vector<int> zeros((size_t)m.num_groups + 1, 0);
+    std::vector<int> zeros((size_t)m.num_groups + 1, 0), iota((size_t)m.num_groups + 1);
+    for (size_t i = 0; i < iota.size(); ++i) iota[i] = (int)i;
     if ((rc = upload<int>(mesh, zeros.data(), zeros.size(), &m.group_rec_offsets)) != P3CS_OK) return bail(rc);
+    if ((rc = upload<int>(mesh, iota.data(), iota.size(), &m.group_tile_offsets)) != P3CS_OK) return bail(rc);
   }
   {
     const char *path = getenv("P3CS_PATH");

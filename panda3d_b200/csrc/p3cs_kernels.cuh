@@ -49,15 +49,15 @@ struct MeshDev {
   const float4 *morph_deltas;
 
   // ---- strip kernel tables (static, built at upload).  Rows are cut into tiles of kTileRows
-  // (the TMA / phase-B unit) and tiles into record groups of `group_tiles` tiles (the phase-A
+  // (the phase-B unit) and consecutive tiles into record groups (the phase-A
   // unit): each group lists the distinct blends its skinned rows select ("group records") and
   // every row stores the index of its blend in that list.
   int num_tiles;
-  int group_tiles;                  // tiles per record group (power of two, 1..8)
+  const int *group_tile_offsets;    // num_groups+1: group g covers tiles [off[g], off[g+1])
   int num_groups;
   int max_group_records;            // max distinct blends of any group (smem sizing)
-  int tile_bytes;                   // smem bytes of one staged tile (all outputs, 128-aligned)
-  int tile_out_offset[kMaxOutputs]; // byte offset of output o inside a staged tile
+  int slice_bytes;                  // smem bytes of one staged 32-row slice (all outputs, 128-aligned)
+  int slice_out_offset[kMaxOutputs];// byte offset of output o inside a staged slice
   const uint16_t *row_local;        // per row: index into its group's record list, 0xFFFF = not skinned
   const int *group_rec_offsets;     // num_groups+1
   const int *group_rec_blend;       // global blend id of every group record (selection hook)
