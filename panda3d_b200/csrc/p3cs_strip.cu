@@ -1,18 +1,17 @@
 // p3cs_strip.cu -- the fused hot-path kernel (sm_100a): one launch animates a whole crowd.
 //
-// Work unit = a strip: consecutive record groups (each `group_tiles` 256-row tiles) of ONE
+// Work unit = a strip: consecutive record groups (runs of 256-row tiles sharing one record list) of ONE
 // instance.  Per strip the CTA stages the instance's joint-matrix palette in shared memory once;
 // then, per record group:
 //   * phase A: one thread per DISTINCT blend of the group accumulates sum_i w_i * M_i from the
 //     shared palette (TransformBlend::update_blend, panda/src/gobj/transformBlend.cxx:211-233),
 //     derives the normal matrix (geomVertexData.cxx:1811-1840) and leaves a record in smem;
 // and per tile of the group:
-//   * every warp runs its own TMA pipeline over its 32-row slice of the tile: the slice arrives
-//     by a bulk copy (cp.async.bulk global->shared, completion on the warp's mbarrier), kDepth
-//     slices deep, so loads run two tiles ahead of the math and no block-wide barrier is needed;
+//   * the tile's rows arrive by a TMA bulk copy (cp.async.bulk global->shared, completion on an
+//     mbarrier), double buffered so the next tile is in flight while this one is computed;
 //   * phase B: one thread per row applies the sparse morph deltas (geomVertexData.cxx:1462-1543)
 //     and the blend record of the row (:1558-1751) to the staged row, in place;
-//   * the finished slice leaves by a TMA bulk store (shared->global, bulk_group).
+//   * the finished tile leaves by a TMA bulk store (shared->global, bulk_group).
 // Blend records never touch HBM, the static mesh is read through L2 (shared by every instance),
 // so the compulsory HBM traffic of a crowd is the output rows plus one palette per instance.
 // Global accesses of rows are whole-tile bulk copies; every layout-dependent access (arbitrary
@@ -26,9 +25,6 @@
 namespace p3cs {
 
 constexpr int kStripThreads = kTileRows;  // one thread per row of a tile
-constexpr int kWarps = kStripThreads / 32;
-constexpr int kDepth = 4;                 // slice buffers per warp: 2 loading, 1 computing, 1 storing
-constexpr int kAhead = 2;                 // tiles a warp's loads run ahead of its math
 
 // kFastPN24: the egg loader's packed [vertex(3f) normal(3f)] rows (stride 24): the whole row is
 // moved with three conflict-free 64-bit shared-memory accesses each way.
@@ -67,15 +63,10 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, uint32_t src_smem, uint
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Shared-memory plan: [kWarps x kDepth mbarriers][palette rows x cols 0..2: T x 48 B][palette column 3: T x 16 B]
-// [records][kWarps x kDepth slice buffers].  The 48-byte palette stride keeps the LDS.128 of
+// Shared-memory plan: [2 mbarriers][palette rows x cols 0..2: T x 48 B][palette column 3: T x 16 B]
+// [records][tile buffer 0][tile buffer 1].  The 48-byte palette stride keeps the LDS.128 of
 // phase A spread over all bank groups; column 3 is only read when a palette is not affine.
 struct StripSmem {
   int pal3_off, palc_off, records_off, tiles_off, total;
@@ -83,12 +74,12 @@ struct StripSmem {
 
 __host__ __device__ inline StripSmem strip_layout(const MeshDev &m) {
   StripSmem s;
-  s.pal3_off = kWarps * kDepth * 8;
+  s.pal3_off = 16;
   s.palc_off = s.pal3_off + m.num_transforms * 48;
   s.records_off = s.palc_off + m.num_transforms * 16;
   const int rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
   s.tiles_off = (s.records_off + (m.max_group_records > 0 ? m.max_group_records : 1) * rec_bytes + 127) & ~127;
-  s.total = s.tiles_off + kWarps * kDepth * m.slice_bytes;
+  s.total = s.tiles_off + 2 * 8 * m.slice_bytes;  // a tile = 8 contiguous 32-row slices
   return s;
 }
 
@@ -275,12 +266,11 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   float *recs = reinterpret_cast<float *>(smem + lay.records_off);
   uint8_t *tiles = smem + lay.tiles_off;
   const uint32_t mbar0 = smem_u32(smem);
-  const int slice_bytes = mesh.slice_bytes;
+  const uint32_t tiles_s = smem_u32(tiles);
+  const int tile_bytes = 8 * mesh.slice_bytes;
   const int stride0 = mesh.stride[0];
 
   const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
   const int inst = first_instance + blockIdx.y;
   const int g0 = blockIdx.x * groups_per_cta;
   const int g1 = min(mesh.num_groups, g0 + groups_per_cta);
@@ -289,7 +279,8 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   const int t1 = __ldg(mesh.group_tile_offsets + g1);
 
   if (tid == 0) {
-    for (int k = 0; k < kWarps * kDepth; ++k) mbar_init(mbar0 + 8 * k, 1);
+    mbar_init(mbar0, 1);
+    mbar_init(mbar0 + 8, 1);
     fence_proxy_async();  // make the initialised barriers visible to the async (TMA) proxy
   }
   // palette: T x 64 B by coalesced 128-bit loads; rows x columns 0..2 packed to 48 B, column 3
@@ -311,21 +302,15 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   }
   non_affine = __syncthreads_or(non_affine);
 
-  // ---- the warp's private TMA pipeline over its 32-row slices (lane 0 issues)
-  uint8_t *my_slices = tiles + (size_t)warp * kDepth * slice_bytes;
-  const uint32_t my_slices_s = smem_u32(my_slices);
-  const uint32_t my_bars = mbar0 + 8 * warp * kDepth;
-  const int warp_row = warp * 32;
-  auto slice_rows = [&](int t) { return min(32, mesh.num_rows - (t * kTileRows + warp_row)); };
-  auto issue_slice_load = [&](int t, int k) {
-    const int rows = slice_rows(t);
-    if (rows <= 0) return;
-    const size_t row0 = (size_t)t * kTileRows + warp_row;
-    const uint32_t bar = my_bars + 8 * k;
+  // one elected thread drives the TMA traffic
+  auto issue_tile_load = [&](int t, int buf) {
+    const int row0 = t * kTileRows;
+    const int rows = min(kTileRows, mesh.num_rows - row0);
+    const uint32_t bar = mbar0 + 8 * buf;
     if (FAST) {  // single output array
       const uint32_t bytes = (uint32_t)((rows * stride0 + 15) & ~15);
       mbar_expect_tx(bar, bytes);
-      bulk_g2s(my_slices_s + k * slice_bytes, mesh.src[0] + row0 * stride0, bytes, bar);
+      bulk_g2s(tiles_s + buf * tile_bytes, mesh.src[0] + (size_t)row0 * stride0, bytes, bar);
       return;
     }
     uint32_t total = 0;
@@ -333,19 +318,14 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
     mbar_expect_tx(bar, total);
     for (int o = 0; o < mesh.num_outputs; ++o) {
       const uint32_t bytes = (uint32_t)((rows * mesh.stride[o] + 15) & ~15);
-      bulk_g2s(my_slices_s + k * slice_bytes + mesh.slice_out_offset[o], mesh.src[o] + row0 * mesh.stride[o], bytes, bar);
+      bulk_g2s(tiles_s + buf * tile_bytes + 8 * mesh.slice_out_offset[o], mesh.src[o] + (size_t)row0 * mesh.stride[o], bytes, bar);
     }
   };
-  if (lane == 0) {
-#pragma unroll
-    for (int d = 0; d < kAhead; ++d)
-      if (t0 + d < t1) issue_slice_load(t0 + d, d);
-  }
+  if (tid == 0) issue_tile_load(t0, 0);
 
   const float *sliders = grp.sliders + (size_t)inst * mesh.num_sliders;
   const bool has_index = mesh.index_bytes != 0;
-  int k = 0;        // slice buffer of the current tile: (t - t0) % kDepth
-  uint32_t ph = 0;  // its mbarrier phase parity: ((t - t0) / kDepth) & 1
+  int it = 0;  // tiles processed by this CTA so far (buffer / mbarrier phase bookkeeping)
 
   // software prefetch (hides the L2 latency of the static tables): the row's record slot for the
   // next tile, and this thread's entry block of the next record group
@@ -363,8 +343,8 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   int t = t0;
   for (int g = g0; g < g1; ++g) {
     // ---------------- phase A: one thread per distinct blend of this record group
+    // (the tile loop's trailing barrier guarantees nobody still reads the previous records)
     const int nrec = rend - rbeg;
-    if (g != g0) __syncthreads();  // every warp is done reading the previous group's records
     for (int b = tid; b < nrec; b += kStripThreads) {
       if (FULL) {
         Mat4 acc, x;
@@ -400,13 +380,11 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
       }
     }
 
-    for (; t < cur_gt1; ++t) {
-      if (lane == 0 && t + kAhead < t1) {
-        // the buffer tile t+kAhead lands in was last read by this warp's store of tile
-        // t+kAhead-kDepth; newer stores may stay in flight
-        bulk_wait_read<kDepth - kAhead - 1>();
-        const int kk = k + kAhead;
-        issue_slice_load(t + kAhead, kk >= kDepth ? kk - kDepth : kk);
+    for (; t < cur_gt1; ++t, ++it) {
+      const int buf = it & 1;
+      if (tid == 0 && t + 1 < t1) {
+        bulk_wait_read_all();  // the store that last read buffer buf^1 has drained it
+        issue_tile_load(t + 1, buf ^ 1);
       }
 
       // -------------- per-row selection (integer work, bit-exact)
@@ -419,81 +397,75 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
         if (live && blockIdx.y == 0) grp.selection[row] = local == 0xFFFF ? -1 : __ldg(mesh.group_rec_blend + cur_rbeg + local);
       }
       const bool skinned = local != 0xFFFF;
-      const int rows = slice_rows(t);  // warp-uniform
-      if (rows > 0) {
-        mbar_wait(my_bars + 8 * k, ph);  // the slice's rows have landed
 
-        // ------------ phase B: one thread per row, in place on the staged slice
-        uint8_t *slice = my_slices + k * slice_bytes;
-        if (FAST) {
-          if (skinned) {
-            const float2 *p = reinterpret_cast<const float2 *>(recs + (size_t)local * kRecCompact);
-            float f[22];
+      mbar_wait(mbar0 + 8 * buf, (it >> 1) & 1);  // the tile's rows have landed
+
+      // -------------- phase B: one thread per row, in place on the staged tile
+      uint8_t *tile = tiles + buf * tile_bytes;
+      if (FAST) {
+        if (skinned) {
+          const float2 *p = reinterpret_cast<const float2 *>(recs + (size_t)local * kRecCompact);
+          float f[22];
 #pragma unroll
-            for (int i = 0; i < 11; ++i) {
-              const float2 v = p[i];
-              f[2 * i] = v.x;
-              f[2 * i + 1] = v.y;
-            }
-            if (MODE == kFastPN24) {
-              float2 *rowp = reinterpret_cast<float2 *>(slice + lane * 24);
-              const float2 a = rowp[0], b2 = rowp[1], c = rowp[2];
-              float v[6] = {a.x, a.y, b2.x, b2.y, c.x, c.y};
-              fast_column<1>(v, f);
-              fast_column<3>(v + 3, f);
-              rowp[0] = make_float2(v[0], v[1]);
-              rowp[1] = make_float2(v[2], v[3]);
-              rowp[2] = make_float2(v[4], v[5]);
-            } else {
-              uint8_t *rowp = slice + lane * stride0;
-              fast_column<1>(reinterpret_cast<float *>(rowp + mesh.dyn[0].start), f);
-              if (MODE >= kFastPN) fast_column<3>(reinterpret_cast<float *>(rowp + mesh.dyn[1].start), f);
-              if (MODE >= kFastPNVV) {
-                fast_column<2>(reinterpret_cast<float *>(rowp + mesh.dyn[2].start), f);
-                fast_column<2>(reinterpret_cast<float *>(rowp + mesh.dyn[3].start), f);
-              }
-            }
+          for (int i = 0; i < 11; ++i) {
+            const float2 v = p[i];
+            f[2 * i] = v.x;
+            f[2 * i + 1] = v.y;
           }
-        } else if (live) {
-          int morph_beg = 0, morph_end = 0;
-          if (mesh.has_morphs) {
-            morph_beg = __ldg(mesh.morph_row_offsets + row);
-            morph_end = __ldg(mesh.morph_row_offsets + row + 1);
-          }
-          Record<FULL> rec;
-          if (skinned) load_record<FULL, false>(recs, (size_t)local, rec);
-          for (int c = 0; c < mesh.num_dyn; ++c) {
-            const DynColumn col = mesh.dyn[c];
-            float *cell = reinterpret_cast<float *>(slice + mesh.slice_out_offset[col.output] + (size_t)lane * mesh.stride[col.output] + col.start);
-            animate_column<FULL>(mesh, col, c, cell, morph_beg, morph_end, sliders, skinned, rec);
+          if (MODE == kFastPN24) {
+            float2 *rowp = reinterpret_cast<float2 *>(tile + tid * 24);
+            const float2 a = rowp[0], b2 = rowp[1], c = rowp[2];
+            float v[6] = {a.x, a.y, b2.x, b2.y, c.x, c.y};
+            fast_column<1>(v, f);
+            fast_column<3>(v + 3, f);
+            rowp[0] = make_float2(v[0], v[1]);
+            rowp[1] = make_float2(v[2], v[3]);
+            rowp[2] = make_float2(v[4], v[5]);
+          } else {
+            uint8_t *rowp = tile + tid * stride0;
+            fast_column<1>(reinterpret_cast<float *>(rowp + mesh.dyn[0].start), f);
+            if (MODE >= kFastPN) fast_column<3>(reinterpret_cast<float *>(rowp + mesh.dyn[1].start), f);
+            if (MODE >= kFastPNVV) {
+              fast_column<2>(reinterpret_cast<float *>(rowp + mesh.dyn[2].start), f);
+              fast_column<2>(reinterpret_cast<float *>(rowp + mesh.dyn[3].start), f);
+            }
           }
         }
-        // hand the finished slice to the TMA store: every lane orders its generic-proxy writes
-        // before the async proxy, then lane 0 issues the bulk store
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          const size_t row0 = (size_t)t * kTileRows + warp_row;
-          const uint32_t slice_s = my_slices_s + k * slice_bytes;
-          if (FAST) {
-            const uint32_t bytes = (uint32_t)((rows * stride0 + 15) & ~15);
-            bulk_s2g(grp.out[0] + (size_t)inst * grp.pitch[0] + row0 * stride0, slice_s, bytes);
-          } else {
-            for (int o = 0; o < mesh.num_outputs; ++o) {
-              const uint32_t bytes = (uint32_t)((rows * mesh.stride[o] + 15) & ~15);
-              bulk_s2g(grp.out[o] + (size_t)inst * grp.pitch[o] + row0 * mesh.stride[o], slice_s + mesh.slice_out_offset[o], bytes);
-            }
-          }
-          bulk_commit();
+      } else if (live) {
+        int morph_beg = 0, morph_end = 0;
+        if (mesh.has_morphs) {
+          morph_beg = __ldg(mesh.morph_row_offsets + row);
+          morph_end = __ldg(mesh.morph_row_offsets + row + 1);
+        }
+        Record<FULL> rec;
+        if (skinned) load_record<FULL, false>(recs, (size_t)local, rec);
+        for (int c = 0; c < mesh.num_dyn; ++c) {
+          const DynColumn col = mesh.dyn[c];
+          float *cell = reinterpret_cast<float *>(tile + 8 * mesh.slice_out_offset[col.output] + (size_t)tid * mesh.stride[col.output] + col.start);
+          animate_column<FULL>(mesh, col, c, cell, morph_beg, morph_end, sliders, skinned, rec);
         }
       }
-      if (++k == kDepth) {
-        k = 0;
-        ph ^= 1;
+      fence_proxy_async();  // generic-proxy writes to the tile -> visible to the TMA store
+      __syncthreads();
+
+      if (tid == 0) {
+        const int row0 = t * kTileRows;
+        const int rows = min(kTileRows, mesh.num_rows - row0);
+        const uint32_t tile_s = tiles_s + buf * tile_bytes;
+        if (FAST) {
+          const uint32_t bytes = (uint32_t)((rows * stride0 + 15) & ~15);
+          bulk_s2g(grp.out[0] + (size_t)inst * grp.pitch[0] + (size_t)row0 * stride0, tile_s, bytes);
+        } else {
+          for (int o = 0; o < mesh.num_outputs; ++o) {
+            const uint32_t bytes = (uint32_t)((rows * mesh.stride[o] + 15) & ~15);
+            bulk_s2g(grp.out[o] + (size_t)inst * grp.pitch[o] + (size_t)row0 * mesh.stride[o], tile_s + 8 * mesh.slice_out_offset[o], bytes);
+          }
+        }
+        bulk_commit();
       }
     }
   }
-  if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last bulk store's reads
+  if (tid == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk store's reads
 }
 
 size_t strip_smem_bytes(const MeshDev &mesh) { return (size_t)strip_layout(mesh).total; }
