@@ -1,0 +1,114 @@
+"""Crowds of independent Character instances over the GPUs of one box.
+
+The path shards naturally: an instance (its palette, slider values and output arrays) depends on
+nothing outside itself, so instances are dealt to ranks with no data-path collective.  The only
+exchange is the gather of finished vertex arrays to the rendering GPU, done with NCCL through
+`torch.distributed` (plumbing) on the very buffers the kernel writes.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def shard_instances(num_instances: int, world_size: int, rank: int) -> range:
+    """Round-robin deal: instance i lives on rank i % world_size."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank outside the world")
+    return range(rank, num_instances, world_size)
+
+
+def shard_sizes(num_instances: int, world_size: int) -> List[int]:
+    return [len(shard_instances(num_instances, world_size, r)) for r in range(world_size)]
+
+
+def balance_mixed_crowd(vertices_per_instance: Sequence[int], world_size: int) -> List[List[int]]:
+    """Mixed crowds (BASELINE configs[4]): longest-processing-time bin packing on vertex counts, so
+    every GPU gets about the same number of vertices per frame.  Returns instance ids per rank."""
+    order = sorted(range(len(vertices_per_instance)), key=lambda i: (-vertices_per_instance[i], i))
+    loads = [0] * world_size
+    bins: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (loads[k], k))
+        bins[r].append(i)
+        loads[r] += vertices_per_instance[i]
+    for b in bins:
+        b.sort()
+    return bins
+
+
+def global_order(num_instances: int, world_size: int) -> np.ndarray:
+    """Position of every instance in the rank-major gathered buffer: gathered[r, j] holds instance
+    r + j * world_size.  Returns an index array `pos` with gathered.reshape(-1)[pos[i]] = instance i
+    when every rank's block is padded to ceil(num_instances / world_size) rows."""
+    per = -(-num_instances // world_size)
+    i = np.arange(num_instances)
+    return (i % world_size) * per + i // world_size
+
+
+def gather_outputs(local, num_instances: int, root: int = 0, group=None):
+    """Gathers every rank's finished output rows ([n_local, row_bytes] uint8 tensor, device or CPU)
+    to `root` with one collective and returns them there in instance order
+    ([num_instances, row_bytes]); other ranks get None.  Shards are padded to equal length because
+    the collective wants equal contributions."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    per = -(-num_instances // world)
+    n_local = len(shard_instances(num_instances, world, rank))
+    if local.shape[0] != n_local:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} instances, expected {n_local}")
+    if n_local < per:
+        pad = torch.zeros((per - n_local,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        send = torch.cat([local, pad], 0)
+    else:
+        send = local.contiguous()
+    if rank == root:
+        recv = [torch.empty_like(send) for _ in range(world)]
+        dist.gather(send, recv, dst=root, group=group)
+        stacked = torch.stack(recv, 0).reshape((world * per,) + tuple(local.shape[1:]))
+        pos = torch.as_tensor(global_order(num_instances, world), device=local.device)
+        return stacked.index_select(0, pos)
+    dist.gather(send, None, dst=root, group=group)
+    return None
+
+
+class CrowdShard:
+    """The instances of one mesh that live on this rank's GPU: device buffers owned by torch
+    (so NCCL can send them), animation through the C-ABI group."""
+
+    def __init__(self, ctx, flat_mesh, num_instances: int, world_size: int = 1, rank: int = 0):
+        import torch
+        from . import _capi
+
+        self.num_instances = num_instances
+        self.world_size, self.rank = world_size, rank
+        self.instances = shard_instances(num_instances, world_size, rank)
+        self.n_local = len(self.instances)
+        self.mesh = _capi.Mesh(ctx, flat_mesh)
+        self.flat = flat_mesh
+        dev = torch.device("cuda", ctx.device)
+        T = flat_mesh.num_transforms
+        self.palettes = torch.empty((max(self.n_local, 1), T * 16), dtype=torch.float32, device=dev)
+        self.outputs = []
+        for o, stride in enumerate(self.mesh.out_strides):
+            pitch = (flat_mesh.num_rows * stride + 255) // 256 * 256
+            self.outputs.append(torch.empty((max(self.n_local, 1), pitch), dtype=torch.uint8, device=dev))
+        self.group = _capi.Group(self.mesh, max(self.n_local, 1), palettes_dev=self.palettes.data_ptr(),
+                                 outputs_dev=[t.data_ptr() for t in self.outputs]) if self.n_local else None
+
+    def animate(self) -> None:
+        if self.group is not None:
+            self.group.animate()
+
+    def gather(self, output: int = 0, root: int = 0):
+        """NCCL gather of this output array to the rendering GPU (instance order, padded rows)."""
+        return gather_outputs(self.outputs[output][:self.n_local], self.num_instances, root)
+
+    def close(self) -> None:
+        if self.group is not None:
+            self.group.close()
+        self.mesh.close()

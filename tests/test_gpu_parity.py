@@ -206,3 +206,59 @@ def test_unsupported_and_invalid_inputs_fail_loudly(gpu_ctx):
     with pytest.raises(_capi.P3csError) as e:
         _capi.Mesh(gpu_ctx, bad2)
     assert e.value.code == _capi.P3CS_ERR_INVALID
+
+
+def test_mirror_animate_vertices_semantics(gpu_ctx):
+    """The host-side mirror of GeomVertexData::animate_vertices (panda3d_b200/gobj.py): written the way a
+    test against panda3d.core would be (cf. the survey's probe, SURVEY.md 8c): morph first, then skin;
+    rows outside TransformBlendTable::get_rows() untouched; the SAME output object is returned, unchanged
+    while nothing is modified and mutated in place when a slider moves (geomVertexData.cxx:895-960)."""
+    from panda3d_b200 import gobj
+    from panda3d_b200.gobj import (GeomEnums, GeomVertexAnimationSpec, GeomVertexArrayFormat, GeomVertexData,
+                                   GeomVertexFormat, InternalName, SliderTable, SparseArray, TransformBlend,
+                                   TransformBlendTable, UserVertexSlider, UserVertexTransform)
+    gobj._Backend.ctx = gpu_ctx
+    af = GeomVertexArrayFormat()
+    af.add_column(InternalName.get_vertex(), 3, GeomEnums.NT_float32, GeomEnums.C_point)
+    af.add_column(InternalName.get_normal(), 3, GeomEnums.NT_float32, GeomEnums.C_normal)
+    af.add_column(InternalName.get_texcoord(), 2, GeomEnums.NT_float32, GeomEnums.C_texcoord)
+    bf = GeomVertexArrayFormat()
+    bf.add_column(InternalName.get_transform_blend(), 1, GeomEnums.NT_uint16, GeomEnums.C_index, 0, 2)
+    dname = InternalName.get_morph(InternalName.get_vertex(), "smile")
+    bf.add_column(dname, 3, GeomEnums.NT_float32, GeomEnums.C_morph_delta)
+    f = GeomVertexFormat(af)
+    f.add_array(bf)
+    spec = GeomVertexAnimationSpec()
+    spec.set_panda()
+    f.set_animation(spec)
+    fmt = GeomVertexFormat.register_format(f)
+    vd = GeomVertexData("probe", fmt, GeomEnums.UH_static)
+    vd.set_num_rows(4)
+    t0 = UserVertexTransform("j0")
+    scale_translate = np.diag([1, 2, 3, 1]).astype(np.float32)
+    scale_translate[3, 0] = 1.0                                  # scale(1,2,3) * translate(1,0,0)
+    t0.set_matrix(scale_translate)
+    tbt = TransformBlendTable()
+    b0 = tbt.add_blend(TransformBlend(t0, 1.0))
+    tbt.set_rows(SparseArray.range(1, 3))                        # rows 1..3 only
+    vd.set_transform_blend_table(tbt)
+    sl = UserVertexSlider("smile")
+    st = SliderTable()
+    st.add_slider(sl, SparseArray.range(2, 2))                   # rows 2, 3
+    vd.set_slider_table(SliderTable.register_table(st))
+    vd.set_column("vertex", [[i, 1, 1] for i in range(4)])
+    vd.set_column("normal", [[0, 0, 1]] * 4)
+    vd.set_column("transform_blend", [[b0]] * 4)
+    vd.set_column(dname, [[0, 10, 0]] * 4)
+    sl.set_slider(0.5)
+    out = vd.animate_vertices(True)
+    assert out is not vd and out.get_format().get_num_arrays() == 1
+    v, n = out.get_column("vertex"), out.get_column("normal")
+    # the reference's own results for this probe (SURVEY.md 8c)
+    assert np.array_equal(v, [[0, 1, 1], [2, 2, 3], [3, 12, 3], [4, 12, 3]])
+    assert np.allclose(n[1:], [[0, 0, 1]] * 3) and np.array_equal(n[0], [0, 0, 1])
+    assert vd.animate_vertices(True) is out                      # nothing modified: cached
+    sl.set_slider(1.0)
+    out2 = vd.animate_vertices(True)
+    assert out2 is out                                           # same object, mutated in place
+    assert np.array_equal(out2.get_column("vertex")[3], [4, 22, 3])
