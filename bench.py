@@ -303,6 +303,23 @@ def run_gpu_arm(args):
             g, e = got.view(np.float32).astype(np.float64), expect[0].view(np.float32).astype(np.float64)
             check = {"instance": inst, "max_abs_err": float(np.abs(g - e).max()), "differing_bytes": int((got != expect[0]).sum())}
 
+        # ---------------- optional: NCCL gather of the finished arrays to the rendering GPU (rank 0)
+        gather = None
+        if dist is not None:
+            from panda3d_b200 import crowd
+            view = out_dev[:n_local]
+            crowd.gather_outputs(view, args.instances, root=0)
+            barrier()
+            e0.record(stream)
+            for _ in range(3):
+                crowd.gather_outputs(view, args.instances, root=0)
+            e1.record(stream)
+            barrier()
+            g_ms = max_over_ranks(e0.elapsed_time(e1) / 3)
+            inbound = (args.instances - n_local) * pitch if rank == 0 else 0
+            gather = {"ms_per_step": g_ms, "inbound_bytes_rank0": int(sum_over_ranks(float(inbound))),
+                      "note": "dist.gather (NCCL) of every rank's [instances, pitch] uint8 rows to rank 0, not part of `value`"}
+
     total_verts = float(sum_over_ranks(float(n_local * flat.skinned_rows())))
     value = total_verts / (ms * 1e-3)
     e2e_value = total_verts / (e2e_ms * 1e-3)
@@ -314,18 +331,27 @@ def run_gpu_arm(args):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-        # dominant kernel = skin (K2).  Algorithmic bytes per vertex of an instanced crowd: the source
-        # mesh is shared (L2), so the compulsory HBM traffic is the output row (stride bytes); K2 also
-        # gathers blend records from the L2-resident scratch, which is not counted.
+        # dominant (only) kernel = strip_kernel: one launch per step.  Algorithmic bytes of an instanced
+        # crowd: the source mesh and its tables are shared by all instances and
+        # served from L2, so the compulsory HBM traffic per instance is its output rows (stride bytes per
+        # vertex) plus its palette (T x 64 B); blend records never leave shared memory.
         skin_s = statistics.mean(skin_ms) * 1e-3
-        alg_bytes_per_step = n_local * rows * stride
+        alg_bytes_per_step = n_local * (rows * stride + T * 64)
         logical_bytes_per_step = n_local * rows * (2 * stride + 2)
         achieved = alg_bytes_per_step / skin_s / 1e9
-        roofline = {"bound": "hbm", "kernel": "skin_kernel (K2)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "r01_strip_kernel_c3.json")
+        if os.path.exists(prof):
+            pj = json.load(open(prof))
+            if pj.get("instances") == n_local:
+                traffic = pj.get("dram_bytes_per_launch")
+        roofline = {"bound": "hbm", "kernel": "p3cs::strip_kernel<kFastPN24>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "launches_per_step": skin_launches, "avg_launch_ms": 1e3 * skin_s / max(1, skin_launches),
-                    "algorithmic_bytes_per_vertex": stride, "logical_gbs": logical_bytes_per_step / skin_s / 1e9,
-                    "blend_kernel_ms_per_step": statistics.mean(blend_ms), "skin_kernel_ms_per_step": statistics.mean(skin_ms)}
+                    "algorithmic_bytes_per_launch": alg_bytes_per_step,
+                    "algorithmic_bytes_per_vertex": alg_bytes_per_step / (n_local * rows),
+                    "logical_gbs": logical_bytes_per_step / skin_s / 1e9,
+                    "note": "compute/shared-memory-issue bound on this 24 B/vertex crowd: see DESIGN.md"}
         cpu = None
         if world == 1 and not args.no_cpu:
             workers = os.cpu_count() or 1
@@ -340,6 +366,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                     "ms_per_step": e2e_ms, "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps, "clocks": sampler.summary(), "check": check,
+            "gather": gather,
         }
         print(json.dumps(line), flush=True)
     grp.close()
