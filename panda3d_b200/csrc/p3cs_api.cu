@@ -467,6 +467,8 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
     for (size_t i = 0; i < iota.size(); ++i) iota[i] = (int)i;
     if ((rc = upload<int>(mesh, zeros.data(), zeros.size(), &m.group_rec_offsets)) != P3CS_OK) return bail(rc);
     if ((rc = upload<int>(mesh, iota.data(), iota.size(), &m.group_tile_offsets)) != P3CS_OK) return bail(rc);
+    std::vector<uint4> blocks((size_t)kTileRows * 2, make_uint4(0, 0, 0, 0));  // the kernel prefetches block [tid]
+    if ((rc = upload<uint4>(mesh, blocks.data(), blocks.size(), &m.grec_blocks)) != P3CS_OK) return bail(rc);
   }
   {
     const char *path = getenv("P3CS_PATH");

@@ -262,3 +262,94 @@ def test_mirror_animate_vertices_semantics(gpu_ctx):
     out2 = vd.animate_vertices(True)
     assert out2 is out                                           # same object, mutated in place
     assert np.array_equal(out2.get_column("vertex")[3], [4, 22, 3])
+
+
+# ---- code paths the BASELINE shapes do not reach ---------------------------------------------------
+
+def _check_against_oracle(gpu_ctx, mesh, pal, sl=None, what=""):
+    om = oracle.OracleMesh(mesh)
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, 1)
+    try:
+        assert np.array_equal(grp.read_selection(), expected_selection(mesh))
+        expect, eb, _ = om.animate(pal, sl, want_blends=True)
+        got = grp.animate_vertices(pal, sl)
+        max_abs, nb = compare_outputs(mesh, got, expect, what)
+        print(f"{what}: max-abs error {max_abs:.3e}, differing bytes {nb}")
+        return nb
+    finally:
+        grp.close()
+        dmesh.close()
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 6, 9])
+def test_blends_with_other_than_four_weights(gpu_ctx, k):
+    """TransformBlend is not limited to 4 entries on the CPU path: 1..3 use the
+    fixed entry block partially, > 4 take the CSR fallback of the strip kernel."""
+    sm = synth.make_mesh(5_000, 24, 24 if k == 1 else 400, seed=40 + k, weights_per_blend=k, index_order="runs")
+    pal = synth.make_palettes(24, 1, 50 + k, jitter=0.2)[0]
+    assert _check_against_oracle(gpu_ctx, sm.flat, pal, what=f"{k}-weight blends") == 0
+
+
+def test_non_affine_palette_takes_the_general_inverse(gpu_ctx):
+    """Column 3 != (0,0,0,1): LMatrix4f::invert_from falls to the LU branch (lmatrix4_src.I:1225-1246)."""
+    sm = synth.make_mesh(3_000, 16, 300, seed=61, index_order="runs")
+    pal = synth.make_palettes(16, 1, 62, scale=(1.0, 1.3, 0.7))[0].reshape(16, 4, 4).copy()
+    pal[:, 0, 3] = 0.01
+    pal[:, 2, 3] = -0.02
+    pal[:, 3, 3] = 1.05
+    _check_against_oracle(gpu_ctx, sm.flat, pal.reshape(16, 16), what="non-affine palette")
+
+
+def test_sliders_without_blend_table(gpu_ctx):
+    """A vertex data with a SliderTable only: morphs apply, nothing is skinned (geomVertexData.cxx:947-948)."""
+    sm = synth.make_mesh(2_000, 4, 8, seed=63, num_sliders=5, slider_band=0.4, morph_columns=("vertex", "normal"))
+    mesh = sm.flat
+    mesh = F.FlatMesh(**{**mesh.__dict__})
+    mesh.blend_column = None
+    mesh.skin_columns = []
+    mesh.num_transforms = 0
+    mesh.blend_offsets = np.zeros(1, np.int32)
+    mesh.blend_transform = np.zeros(0, np.int32)
+    mesh.blend_weight = np.zeros(0, np.float32)
+    mesh.row_ranges = np.zeros((0, 2), np.int32)
+    sl = synth.make_sliders(5, 1, 64)[0]
+    assert _check_against_oracle(gpu_ctx, mesh, np.zeros((0, 16), np.float32), sl, what="sliders only") == 0
+
+
+def test_singular_and_zero_matrices_do_not_poison_neighbours(gpu_ctx):
+    """A zero joint matrix makes its blends singular; rows using other blends must still be exact and
+    nothing may read out of bounds (the reference's own result for the singular rows is undefined)."""
+    sm = synth.make_mesh(2_000, 8, 8, seed=65, weights_per_blend=1, index_order="sorted")
+    mesh = sm.flat
+    pal = synth.make_palettes(8, 1, 66, scale=(1.0, 1.4, 0.6))[0].copy()
+    pal[3] = 0.0
+    om = oracle.OracleMesh(mesh)
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, 1)
+    try:
+        got = grp.animate_vertices(pal)[0]
+        expect = om.animate(pal)[0][0]
+        ok_rows = mesh.blend_indices() != 3
+        assert np.array_equal(got[ok_rows], expect[ok_rows])
+        assert np.array_equal(got[~ok_rows][:, :12], expect[~ok_rows][:, :12])   # positions are defined (all zero)
+    finally:
+        grp.close()
+        dmesh.close()
+
+
+def test_wide_path_matches_strip_path(gpu_ctx, monkeypatch):
+    """The two-kernel fallback (P3CS_PATH=wide) and the fused strip kernel agree byte for byte."""
+    sm = synth.make_mesh(9_000, 48, 900, seed=67, tbn=True, texcoord=True, index_order="runs", num_sliders=3, slider_band=0.2)
+    mesh = sm.flat
+    pal = synth.make_palettes(48, 1, 68)[0]
+    sl = synth.make_sliders(3, 1, 69)[0]
+    outs = []
+    for path in ("strip", "wide"):
+        monkeypatch.setenv("P3CS_PATH", path)
+        dmesh = _capi.Mesh(gpu_ctx, mesh)
+        grp = _capi.Group(dmesh, 1)
+        outs.append(grp.animate_vertices(pal, sl)[0])
+        grp.close()
+        dmesh.close()
+    assert np.array_equal(outs[0], outs[1])
