@@ -25,6 +25,7 @@
 namespace p3cs {
 
 constexpr int kStripThreads = kTileRows;  // one thread per row of a tile
+constexpr int kTileBufs = 3;              // staged tiles: one loading, one computing, one draining
 
 // kFastPN24: the egg loader's packed [vertex(3f) normal(3f)] rows (stride 24): the whole row is
 // moved with three conflict-free 64-bit shared-memory accesses each way.
@@ -63,6 +64,7 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, uint32_t src_smem, uint
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Shared-memory plan: [2 mbarriers][palette rows x cols 0..2: T x 48 B][palette column 3: T x 16 B]
@@ -74,12 +76,12 @@ struct StripSmem {
 
 __host__ __device__ inline StripSmem strip_layout(const MeshDev &m) {
   StripSmem s;
-  s.pal3_off = 16;
+  s.pal3_off = 32;
   s.palc_off = s.pal3_off + m.num_transforms * 48;
   s.records_off = s.palc_off + m.num_transforms * 16;
   const int rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
   s.tiles_off = (s.records_off + (m.max_group_records > 0 ? m.max_group_records : 1) * rec_bytes + 127) & ~127;
-  s.total = s.tiles_off + 2 * 8 * m.slice_bytes;  // a tile = 8 contiguous 32-row slices
+  s.total = s.tiles_off + kTileBufs * 8 * m.slice_bytes;  // a tile = 8 contiguous 32-row slices
   return s;
 }
 
@@ -270,7 +272,8 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   const int tile_bytes = 8 * mesh.slice_bytes;
   const int stride0 = mesh.stride[0];
 
-  const int tid = threadIdx.x;
+  int tid;  // read once and kept in a register: the compiler otherwise re-reads SR_TID.X (long-latency S2R) per tile
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
   const int inst = first_instance + blockIdx.y;
   const int g0 = blockIdx.x * groups_per_cta;
   const int g1 = min(mesh.num_groups, g0 + groups_per_cta);
@@ -279,8 +282,8 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   const int t1 = __ldg(mesh.group_tile_offsets + g1);
 
   if (tid == 0) {
-    mbar_init(mbar0, 1);
-    mbar_init(mbar0 + 8, 1);
+#pragma unroll
+    for (int k = 0; k < kTileBufs; ++k) mbar_init(mbar0 + 8 * k, 1);
     fence_proxy_async();  // make the initialised barriers visible to the async (TMA) proxy
   }
   // palette: T x 64 B by coalesced 128-bit loads; rows x columns 0..2 packed to 48 B, column 3
@@ -325,7 +328,8 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
 
   const float *sliders = grp.sliders + (size_t)inst * mesh.num_sliders;
   const bool has_index = mesh.index_bytes != 0;
-  int it = 0;  // tiles processed by this CTA so far (buffer / mbarrier phase bookkeeping)
+  int buf = 0;      // (tiles processed so far) % kTileBufs
+  uint32_t ph = 0;  // mbarrier phase parity of buffer `buf`
 
   // software prefetch (hides the L2 latency of the static tables): the row's record slot for the
   // next tile, and this thread's entry block of the next record group
@@ -380,11 +384,12 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
       }
     }
 
-    for (; t < cur_gt1; ++t, ++it) {
-      const int buf = it & 1;
+    for (; t < cur_gt1; ++t) {
       if (tid == 0 && t + 1 < t1) {
-        bulk_wait_read_all();  // the store that last read buffer buf^1 has drained it
-        issue_tile_load(t + 1, buf ^ 1);
+        // tile t+1 lands in the buffer last read by the store of tile t-2; the newest store
+        // (tile t-1) may still be draining
+        bulk_wait_read_1();
+        issue_tile_load(t + 1, buf + 1 == kTileBufs ? 0 : buf + 1);
       }
 
       // -------------- per-row selection (integer work, bit-exact)
@@ -398,7 +403,7 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
       }
       const bool skinned = local != 0xFFFF;
 
-      mbar_wait(mbar0 + 8 * buf, (it >> 1) & 1);  // the tile's rows have landed
+      mbar_wait(mbar0 + 8 * buf, ph);  // the tile's rows have landed
 
       // -------------- phase B: one thread per row, in place on the staged tile
       uint8_t *tile = tiles + buf * tile_bytes;
@@ -462,6 +467,10 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
           }
         }
         bulk_commit();
+      }
+      if (++buf == kTileBufs) {
+        buf = 0;
+        ph ^= 1;
       }
     }
   }
