@@ -302,13 +302,23 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
           return bail(fail(P3CS_ERR_INVALID, "row %d selects blend %u but the table has %d blends", r, v, d->num_blends));
         if (!full) mask[r >> 5] |= 1u << (r & 31);
       }
+    // ---- tile size: two rows per thread (512-row tiles) halve the per-tile bookkeeping, as long as
+    // the bigger staged tiles still leave room for four CTAs per SM
+    {
+      size_t slice = 0;
+      for (int o = 0; o < m.num_outputs; ++o) slice += round_up((size_t)32 * m.stride[o], 128);
+      const size_t rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
+      const size_t est = (size_t)d->num_transforms * 64 + (size_t)kStripThreads * rec_bytes + 2 * 16 * slice;
+      m.rows_per_thread = (!m.full_records && est <= 56 * 1024) ? 2 : 1;
+    }
+    const int kTileRows = kStripThreads * m.rows_per_thread;
     // ---- strip-kernel tables: per record group the distinct blends, per row its slot in that list.
     // Groups are grown greedily, tile by tile, while their distinct blends fit one phase-A pass
     // (one thread per record) and the shared-memory record budget.
     {
       const int nt = (N + kTileRows - 1) / kTileRows;
       const int rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
-      const int cap = std::min(kTileRows, (32 * 1024) / rec_bytes);
+      const int cap = std::min(kStripThreads, (32 * 1024) / rec_bytes);  // one phase-A pass: a thread per record
       std::vector<uint16_t> local(std::max(N, 1), 0xFFFFu);
       std::vector<int> rec_off(1, 0), rec_blend, ent_off(1, 0), tile_off(1, 0);
       std::vector<uint2> ent;
@@ -370,7 +380,7 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
       // fixed-width blocks: the first four entries of every group record, count in bits 16..31
       const size_t nrec_total = rec_blend.size();
       // padded by one CTA's worth of records: the kernel prefetches block (group start + tid)
-      std::vector<uint4> blocks((nrec_total + kTileRows) * 2, make_uint4(0, 0, 0, 0));
+      std::vector<uint4> blocks((nrec_total + kStripThreads) * 2, make_uint4(0, 0, 0, 0));
       for (size_t r = 0; r < nrec_total; ++r) {
         uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const int beg = ent_off[r], cnt = ent_off[r + 1] - ent_off[r];
@@ -455,7 +465,8 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
     if ((rc = upload<float4>(mesh, deltas.data(), deltas.size(), &m.morph_deltas)) != P3CS_OK) return bail(rc);
   }
   // ---- slice geometry of the strip kernel (a slice = the 32 rows one warp stages at a time)
-  m.num_tiles = (N + kTileRows - 1) / kTileRows;
+  if (m.rows_per_thread == 0) m.rows_per_thread = 1;
+  m.num_tiles = (N + kStripThreads * m.rows_per_thread - 1) / (kStripThreads * m.rows_per_thread);
   m.slice_bytes = 0;
   for (int o = 0; o < m.num_outputs; ++o) {
     m.slice_out_offset[o] = m.slice_bytes;
@@ -467,7 +478,7 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
     for (size_t i = 0; i < iota.size(); ++i) iota[i] = (int)i;
     if ((rc = upload<int>(mesh, zeros.data(), zeros.size(), &m.group_rec_offsets)) != P3CS_OK) return bail(rc);
     if ((rc = upload<int>(mesh, iota.data(), iota.size(), &m.group_tile_offsets)) != P3CS_OK) return bail(rc);
-    std::vector<uint4> blocks((size_t)kTileRows * 2, make_uint4(0, 0, 0, 0));  // the kernel prefetches block [tid]
+    std::vector<uint4> blocks((size_t)kStripThreads * 2, make_uint4(0, 0, 0, 0));  // the kernel prefetches block [tid]
     if ((rc = upload<uint4>(mesh, blocks.data(), blocks.size(), &m.grec_blocks)) != P3CS_OK) return bail(rc);
   }
   {

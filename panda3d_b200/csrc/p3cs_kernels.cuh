@@ -48,11 +48,12 @@ struct MeshDev {
   const uint32_t *morph_keys;       // (dyn column << 16) | slider
   const float4 *morph_deltas;
 
-  // ---- strip kernel tables (static, built at upload).  Rows are cut into tiles of kTileRows
+  // ---- strip kernel tables (static, built at upload).  Rows are cut into tiles of kStripThreads * rows_per_thread rows
   // (the phase-B unit) and consecutive tiles into record groups (the phase-A
   // unit): each group lists the distinct blends its skinned rows select ("group records") and
   // every row stores the index of its blend in that list.
   int num_tiles;
+  int rows_per_thread;              // 1 or 2: rows a thread animates per staged tile (tile = 256 or 512 rows)
   const int *group_tile_offsets;    // num_groups+1: group g covers tiles [off[g], off[g+1])
   int num_groups;
   int max_group_records;            // max distinct blends of any group (smem sizing)
@@ -67,7 +68,7 @@ struct MeshDev {
                                     // entry count in the high half of the first index
 };
 
-constexpr int kTileRows = 256;
+constexpr int kStripThreads = 256;  // threads of a strip-kernel CTA; a tile is kStripThreads * rows_per_thread rows
 
 struct GroupDev {
   const float *palettes;  // [n][T][16]

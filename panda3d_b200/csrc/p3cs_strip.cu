@@ -24,8 +24,6 @@
 
 namespace p3cs {
 
-constexpr int kStripThreads = kTileRows;  // one thread per row of a tile
-constexpr int kTileBufs = 3;              // staged tiles: one loading, one computing, one draining
 
 // kFastPN24: the egg loader's packed [vertex(3f) normal(3f)] rows (stride 24): the whole row is
 // moved with three conflict-free 64-bit shared-memory accesses each way.
@@ -81,7 +79,8 @@ __host__ __device__ inline StripSmem strip_layout(const MeshDev &m) {
   s.records_off = s.palc_off + m.num_transforms * 16;
   const int rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
   s.tiles_off = (s.records_off + (m.max_group_records > 0 ? m.max_group_records : 1) * rec_bytes + 127) & ~127;
-  s.total = s.tiles_off + kTileBufs * 8 * m.slice_bytes;  // a tile = 8 contiguous 32-row slices
+  // staged tiles (contiguous 32-row slices): 3 in flight for 256-row tiles, 2 for 512-row tiles
+  s.total = s.tiles_off + (m.rows_per_thread == 1 ? 3 : 2) * (kStripThreads * m.rows_per_thread / 32) * m.slice_bytes;
   return s;
 }
 
@@ -253,10 +252,13 @@ __device__ __forceinline__ void fast_column(float *cell, const float (&f)[22]) {
   cell[2] = r2;
 }
 
-template <int MODE, bool SELECT>
+template <int MODE, int kRowsPerThread, bool SELECT>
 __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
     strip_kernel(MeshDev mesh, GroupDev grp, int first_instance, int groups_per_cta, int want_normal) {
   extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int kTileRows = kStripThreads * kRowsPerThread;
+  constexpr int kSlicesPerTile = kTileRows / 32;
+  constexpr int kTileBufs = kRowsPerThread == 1 ? 3 : 2;
   constexpr bool FULL = MODE == kGenericFull;
   constexpr bool FAST = MODE >= kFastP;
   constexpr int REC = FULL ? kRecFull : kRecCompact;
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   uint8_t *tiles = smem + lay.tiles_off;
   const uint32_t mbar0 = smem_u32(smem);
   const uint32_t tiles_s = smem_u32(tiles);
-  const int tile_bytes = 8 * mesh.slice_bytes;
+  const int tile_bytes = kSlicesPerTile * mesh.slice_bytes;
   const int stride0 = mesh.stride[0];
 
   int tid;  // read once and kept in a register: the compiler otherwise re-reads SR_TID.X (long-latency S2R) per tile
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
     mbar_expect_tx(bar, total);
     for (int o = 0; o < mesh.num_outputs; ++o) {
       const uint32_t bytes = (uint32_t)((rows * mesh.stride[o] + 15) & ~15);
-      bulk_g2s(tiles_s + buf * tile_bytes + 8 * mesh.slice_out_offset[o], mesh.src[o] + (size_t)row0 * mesh.stride[o], bytes, bar);
+      bulk_g2s(tiles_s + buf * tile_bytes + kSlicesPerTile * mesh.slice_out_offset[o], mesh.src[o] + (size_t)row0 * mesh.stride[o], bytes, bar);
     }
   };
   if (tid == 0) issue_tile_load(t0, 0);
@@ -333,8 +335,12 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
 
   // software prefetch (hides the L2 latency of the static tables): the row's record slot for the
   // next tile, and this thread's entry block of the next record group
-  int next_local = 0xFFFF;
-  if (has_index && t0 * kTileRows + tid < mesh.num_rows) next_local = __ldg(mesh.row_local + t0 * kTileRows + tid);
+  int next_local[kRowsPerThread];
+#pragma unroll
+  for (int rr = 0; rr < kRowsPerThread; ++rr) {
+    const int row = t0 * kTileRows + rr * kStripThreads + tid;
+    next_local[rr] = (has_index && row < mesh.num_rows) ? (int)__ldg(mesh.row_local + row) : 0xFFFF;
+  }
   int rbeg = __ldg(mesh.group_rec_offsets + g0);
   int rend = __ldg(mesh.group_rec_offsets + g0 + 1);
   int gt1 = __ldg(mesh.group_tile_offsets + g0 + 1);
@@ -386,68 +392,77 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
 
     for (; t < cur_gt1; ++t) {
       if (tid == 0 && t + 1 < t1) {
-        // tile t+1 lands in the buffer last read by the store of tile t-2; the newest store
-        // (tile t-1) may still be draining
-        bulk_wait_read_1();
+        // tile t+1 lands in the buffer last read by the store of tile t+1-kTileBufs
+        if (kTileBufs >= 3) bulk_wait_read_1();
+        else bulk_wait_read_all();
         issue_tile_load(t + 1, buf + 1 == kTileBufs ? 0 : buf + 1);
       }
 
-      // -------------- per-row selection (integer work, bit-exact)
-      const int row = t * kTileRows + tid;
-      const bool live = row < mesh.num_rows;
-      const int local = next_local;
-      next_local = 0xFFFF;
-      if (has_index && t + 1 < t1 && row + kTileRows < mesh.num_rows) next_local = __ldg(mesh.row_local + row + kTileRows);
-      if (SELECT) {
-        if (live && blockIdx.y == 0) grp.selection[row] = local == 0xFFFF ? -1 : __ldg(mesh.group_rec_blend + cur_rbeg + local);
+      // -------------- per-row selection (integer work, bit-exact); the next tile's slots are prefetched
+      int local[kRowsPerThread];
+#pragma unroll
+      for (int rr = 0; rr < kRowsPerThread; ++rr) {
+        const int row = t * kTileRows + rr * kStripThreads + tid;
+        local[rr] = next_local[rr];
+        next_local[rr] = (has_index && t + 1 < t1 && row + kTileRows < mesh.num_rows) ? (int)__ldg(mesh.row_local + row + kTileRows) : 0xFFFF;
+        if (SELECT) {
+          if (row < mesh.num_rows && blockIdx.y == 0)
+            grp.selection[row] = local[rr] == 0xFFFF ? -1 : __ldg(mesh.group_rec_blend + cur_rbeg + local[rr]);
+        }
       }
-      const bool skinned = local != 0xFFFF;
 
       mbar_wait(mbar0 + 8 * buf, ph);  // the tile's rows have landed
 
-      // -------------- phase B: one thread per row, in place on the staged tile
+      // -------------- phase B: kRowsPerThread rows per thread, in place on the staged tile
       uint8_t *tile = tiles + buf * tile_bytes;
-      if (FAST) {
-        if (skinned) {
-          const float2 *p = reinterpret_cast<const float2 *>(recs + (size_t)local * kRecCompact);
-          float f[22];
 #pragma unroll
-          for (int i = 0; i < 11; ++i) {
-            const float2 v = p[i];
-            f[2 * i] = v.x;
-            f[2 * i + 1] = v.y;
-          }
-          if (MODE == kFastPN24) {
-            float2 *rowp = reinterpret_cast<float2 *>(tile + tid * 24);
-            const float2 a = rowp[0], b2 = rowp[1], c = rowp[2];
-            float v[6] = {a.x, a.y, b2.x, b2.y, c.x, c.y};
-            fast_column<1>(v, f);
-            fast_column<3>(v + 3, f);
-            rowp[0] = make_float2(v[0], v[1]);
-            rowp[1] = make_float2(v[2], v[3]);
-            rowp[2] = make_float2(v[4], v[5]);
-          } else {
-            uint8_t *rowp = tile + tid * stride0;
-            fast_column<1>(reinterpret_cast<float *>(rowp + mesh.dyn[0].start), f);
-            if (MODE >= kFastPN) fast_column<3>(reinterpret_cast<float *>(rowp + mesh.dyn[1].start), f);
-            if (MODE >= kFastPNVV) {
-              fast_column<2>(reinterpret_cast<float *>(rowp + mesh.dyn[2].start), f);
-              fast_column<2>(reinterpret_cast<float *>(rowp + mesh.dyn[3].start), f);
+      for (int rr = 0; rr < kRowsPerThread; ++rr) {
+        const int trow = rr * kStripThreads + tid;  // row within the tile
+        const int row = t * kTileRows + trow;
+        const bool skinned = local[rr] != 0xFFFF;
+        if (FAST) {
+          if (skinned) {
+            const float2 *p = reinterpret_cast<const float2 *>(recs + (size_t)local[rr] * kRecCompact);
+            float f[22];
+#pragma unroll
+            for (int i = 0; i < 11; ++i) {
+              const float2 v = p[i];
+              f[2 * i] = v.x;
+              f[2 * i + 1] = v.y;
+            }
+            if (MODE == kFastPN24) {
+              float2 *rowp = reinterpret_cast<float2 *>(tile + trow * 24);
+              const float2 a = rowp[0], b2 = rowp[1], c = rowp[2];
+              float v[6] = {a.x, a.y, b2.x, b2.y, c.x, c.y};
+              fast_column<1>(v, f);
+              fast_column<3>(v + 3, f);
+              rowp[0] = make_float2(v[0], v[1]);
+              rowp[1] = make_float2(v[2], v[3]);
+              rowp[2] = make_float2(v[4], v[5]);
+            } else {
+              uint8_t *rowp = tile + trow * stride0;
+              fast_column<1>(reinterpret_cast<float *>(rowp + mesh.dyn[0].start), f);
+              if (MODE >= kFastPN) fast_column<3>(reinterpret_cast<float *>(rowp + mesh.dyn[1].start), f);
+              if (MODE >= kFastPNVV) {
+                fast_column<2>(reinterpret_cast<float *>(rowp + mesh.dyn[2].start), f);
+                fast_column<2>(reinterpret_cast<float *>(rowp + mesh.dyn[3].start), f);
+              }
             }
           }
-        }
-      } else if (live) {
-        int morph_beg = 0, morph_end = 0;
-        if (mesh.has_morphs) {
-          morph_beg = __ldg(mesh.morph_row_offsets + row);
-          morph_end = __ldg(mesh.morph_row_offsets + row + 1);
-        }
-        Record<FULL> rec;
-        if (skinned) load_record<FULL, false>(recs, (size_t)local, rec);
-        for (int c = 0; c < mesh.num_dyn; ++c) {
-          const DynColumn col = mesh.dyn[c];
-          float *cell = reinterpret_cast<float *>(tile + 8 * mesh.slice_out_offset[col.output] + (size_t)tid * mesh.stride[col.output] + col.start);
-          animate_column<FULL>(mesh, col, c, cell, morph_beg, morph_end, sliders, skinned, rec);
+        } else if (row < mesh.num_rows) {
+          int morph_beg = 0, morph_end = 0;
+          if (mesh.has_morphs) {
+            morph_beg = __ldg(mesh.morph_row_offsets + row);
+            morph_end = __ldg(mesh.morph_row_offsets + row + 1);
+          }
+          Record<FULL> rec;
+          if (skinned) load_record<FULL, false>(recs, (size_t)local[rr], rec);
+          for (int c = 0; c < mesh.num_dyn; ++c) {
+            const DynColumn col = mesh.dyn[c];
+            float *cell = reinterpret_cast<float *>(tile + kSlicesPerTile * mesh.slice_out_offset[col.output] +
+                                                    (size_t)trow * mesh.stride[col.output] + col.start);
+            animate_column<FULL>(mesh, col, c, cell, morph_beg, morph_end, sliders, skinned, rec);
+          }
         }
       }
       fence_proxy_async();  // generic-proxy writes to the tile -> visible to the TMA store
@@ -463,7 +478,7 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
         } else {
           for (int o = 0; o < mesh.num_outputs; ++o) {
             const uint32_t bytes = (uint32_t)((rows * mesh.stride[o] + 15) & ~15);
-            bulk_s2g(grp.out[o] + (size_t)inst * grp.pitch[o] + (size_t)row0 * mesh.stride[o], tile_s + 8 * mesh.slice_out_offset[o], bytes);
+            bulk_s2g(grp.out[o] + (size_t)inst * grp.pitch[o] + (size_t)row0 * mesh.stride[o], tile_s + kSlicesPerTile * mesh.slice_out_offset[o], bytes);
           }
         }
         bulk_commit();
@@ -493,22 +508,29 @@ static int pick_mode(const MeshDev &mesh) {
   return kGenericCompact;
 }
 
-template <int MODE>
-static void launch_mode(const MeshDev &mesh, const GroupDev &grp, int first, dim3 grid, size_t smem, int gpc, int want_normal,
-                        cudaStream_t stream) {
+template <int MODE, int R>
+static void launch_mode_r(const MeshDev &mesh, const GroupDev &grp, int first, dim3 grid, size_t smem, int gpc, int want_normal,
+                          cudaStream_t stream) {
   if (grp.selection != nullptr) {
-    cudaFuncSetAttribute(strip_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    strip_kernel<MODE, true><<<grid, kStripThreads, smem, stream>>>(mesh, grp, first, gpc, want_normal);
+    cudaFuncSetAttribute(strip_kernel<MODE, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    strip_kernel<MODE, R, true><<<grid, kStripThreads, smem, stream>>>(mesh, grp, first, gpc, want_normal);
   } else {
     static thread_local int configured_device = -1;  // the attribute is sticky per function and device
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev != configured_device) {
-      cudaFuncSetAttribute(strip_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(strip_kernel<MODE, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       configured_device = dev;
     }
-    strip_kernel<MODE, false><<<grid, kStripThreads, smem, stream>>>(mesh, grp, first, gpc, want_normal);
+    strip_kernel<MODE, R, false><<<grid, kStripThreads, smem, stream>>>(mesh, grp, first, gpc, want_normal);
   }
+}
+
+template <int MODE>
+static void launch_mode(const MeshDev &mesh, const GroupDev &grp, int first, dim3 grid, size_t smem, int gpc, int want_normal,
+                        cudaStream_t stream) {
+  if (MODE != kGenericFull && mesh.rows_per_thread == 2) launch_mode_r<MODE, 2>(mesh, grp, first, grid, smem, gpc, want_normal, stream);
+  else launch_mode_r<MODE, 1>(mesh, grp, first, grid, smem, gpc, want_normal, stream);
 }
 
 int launch_strip(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, int sm_count, cudaStream_t stream) {
