@@ -308,17 +308,52 @@ def run_gpu_arm(args):
         if dist is not None:
             from panda3d_b200 import crowd
             view = out_dev[:n_local]
-            crowd.gather_outputs(view, args.instances, root=0)
+            per = -(-args.instances // world)
+            recv = torch.empty((world, per, pitch), dtype=torch.uint8, device="cuda") if rank == 0 else None
+            crowd.gather_outputs(view, args.instances, root=0, recv=recv, reorder=False)
             barrier()
             e0.record(stream)
             for _ in range(3):
-                crowd.gather_outputs(view, args.instances, root=0)
+                crowd.gather_outputs(view, args.instances, root=0, recv=recv, reorder=False)
             e1.record(stream)
             barrier()
             g_ms = max_over_ranks(e0.elapsed_time(e1) / 3)
             inbound = (args.instances - n_local) * pitch if rank == 0 else 0
             gather = {"ms_per_step": g_ms, "inbound_bytes_rank0": int(sum_over_ranks(float(inbound))),
                       "note": "dist.gather (NCCL) of every rank's [instances, pitch] uint8 rows to rank 0, not part of `value`"}
+
+        # ---------------- optional: fused skin + gather -- every rank's kernel stores its finished tiles
+        # straight into the rendering GPU's buffer over NVLink (peer-mapped output, no collective)
+        fused = None
+        if dist is not None and not args.no_fused:
+            try:
+                from panda3d_b200 import crowd
+                per = -(-args.instances // world)
+                ctx.enable_peer_access(0)
+                target, keep = crowd.open_render_target(world, rank, per, pitch, root=0)
+                grp2 = _capi.Group(dmesh, n_local, palettes_dev=pal_dev.data_ptr(), outputs_dev=[target[rank].data_ptr()])
+                for _ in range(3):
+                    grp2.animate()
+                barrier()
+                e0.record(stream)
+                for _ in range(args.steps):
+                    grp2.animate()
+                e1.record(stream)
+                barrier()
+                f_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+                ok = None
+                if rank == 0 and world > 1 and not args.no_check:
+                    from oracle import oracle
+                    n1 = len(range(1, args.instances, world))
+                    pal1 = synth.make_palettes(T, n1, 1000 + 1)[n1 // 2]
+                    expect, _, _ = oracle.OracleMesh(flat).animate(pal1)
+                    got = target[1][n1 // 2][:rows * stride].cpu().numpy().reshape(rows, stride)
+                    ok = bool(np.array_equal(got, expect[0]))
+                fused = {"ms_per_step": f_ms, "remote_instance_matches_oracle": ok,
+                         "note": "animate with outputs peer-mapped on GPU 0: skinning and the gather to the rendering GPU in one kernel"}
+                grp2.close()
+            except Exception as exc:  # reported, never hidden
+                fused = {"error": repr(exc)}
 
     total_verts = float(sum_over_ranks(float(n_local * flat.skinned_rows())))
     value = total_verts / (ms * 1e-3)
@@ -366,7 +401,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                     "ms_per_step": e2e_ms, "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps, "clocks": sampler.summary(), "check": check,
-            "gather": gather,
+            "gather": gather, "fused_gather": fused,
         }
         print(json.dumps(line), flush=True)
     grp.close()
@@ -387,6 +422,7 @@ def main():
     ap.add_argument("--cpu-characters", type=int, default=4, help="characters per CPU worker process per step")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="skip the peer-memory fused skin+gather measurement (N>1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

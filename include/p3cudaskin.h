@@ -199,6 +199,12 @@ P3CS_EXPORT int p3cs_context_create(int device, void *stream, p3cs_context *out)
 P3CS_EXPORT int p3cs_context_destroy(p3cs_context ctx);
 /* Blocks until all work queued on the context stream is done. */
 P3CS_EXPORT int p3cs_context_sync(p3cs_context ctx);
+/* Lets kernels of this context store into memory that lives on `peer_device`
+ * (NVLink / NVSwitch peer access).  With it, the output buffers handed to
+ * p3cs_group_create may be peer-mapped memory of the rendering GPU: every rank
+ * then writes its finished tiles straight into the renderer's buffer, the gather
+ * overlaps the skinning tile by tile and needs no separate collective. */
+P3CS_EXPORT int p3cs_context_enable_peer_access(p3cs_context ctx, int peer_device);
 /* The cudaStream_t of the context (for CUDA-event timing by the caller). */
 P3CS_EXPORT void *p3cs_context_stream(p3cs_context ctx);
 

@@ -23,6 +23,7 @@ P3CS_OK, P3CS_ERR_INVALID, P3CS_ERR_UNSUPPORTED, P3CS_ERR_CUDA, P3CS_ERR_NOMEM, 
 EXPORTED_SYMBOLS = [
     "p3cs_api_version", "p3cs_device_count", "p3cs_last_error",
     "p3cs_context_create", "p3cs_context_destroy", "p3cs_context_sync", "p3cs_context_stream",
+    "p3cs_context_enable_peer_access",
     "p3cs_mesh_create", "p3cs_mesh_destroy", "p3cs_mesh_num_outputs", "p3cs_mesh_output_stride", "p3cs_mesh_num_rows",
     "p3cs_group_create", "p3cs_group_destroy", "p3cs_group_output_pitch", "p3cs_group_palettes_device",
     "p3cs_group_sliders_device", "p3cs_group_output_device", "p3cs_group_set_palettes", "p3cs_group_set_sliders",
@@ -94,6 +95,7 @@ def lib():
         L.p3cs_context_destroy.argtypes = [C.c_void_p]
         L.p3cs_context_sync.argtypes = [C.c_void_p]
         L.p3cs_context_stream.argtypes = [C.c_void_p]
+        L.p3cs_context_enable_peer_access.argtypes = [C.c_void_p, C.c_int]
         L.p3cs_mesh_create.argtypes = [C.c_void_p, C.POINTER(_MeshDesc), C.POINTER(C.c_void_p)]
         L.p3cs_mesh_destroy.argtypes = [C.c_void_p]
         L.p3cs_mesh_num_outputs.argtypes = [C.c_void_p]
@@ -149,6 +151,9 @@ class Context:
 
     def sync(self) -> None:
         _check(lib().p3cs_context_sync(self.handle))
+
+    def enable_peer_access(self, peer_device: int) -> None:
+        _check(lib().p3cs_context_enable_peer_access(self.handle, peer_device))
 
     def close(self) -> None:
         if self.handle:

@@ -47,11 +47,13 @@ def global_order(num_instances: int, world_size: int) -> np.ndarray:
     return (i % world_size) * per + i // world_size
 
 
-def gather_outputs(local, num_instances: int, root: int = 0, group=None):
+def gather_outputs(local, num_instances: int, root: int = 0, group=None, recv=None, reorder: bool = True):
     """Gathers every rank's finished output rows ([n_local, row_bytes] uint8 tensor, device or CPU)
-    to `root` with one collective and returns them there in instance order
-    ([num_instances, row_bytes]); other ranks get None.  Shards are padded to equal length because
-    the collective wants equal contributions."""
+    to `root` with one collective.  Shards are padded to equal length because the collective wants
+    equal contributions.  On `root` returns the rows in instance order ([num_instances, row_bytes]),
+    or with reorder=False the raw rank-major buffer [world, ceil(n/world), row_bytes] (instance i
+    is at [i % world, i // world]: a renderer can index that directly and skip the extra copy).
+    `recv` may pass a preallocated rank-major buffer.  Other ranks get None."""
     import torch
     import torch.distributed as dist
 
@@ -67,13 +69,38 @@ def gather_outputs(local, num_instances: int, root: int = 0, group=None):
     else:
         send = local.contiguous()
     if rank == root:
-        recv = [torch.empty_like(send) for _ in range(world)]
-        dist.gather(send, recv, dst=root, group=group)
-        stacked = torch.stack(recv, 0).reshape((world * per,) + tuple(local.shape[1:]))
+        if recv is None:
+            recv = torch.empty((world, per) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.gather(send, [recv[r] for r in range(world)], dst=root, group=group)
+        if not reorder:
+            return recv
         pos = torch.as_tensor(global_order(num_instances, world), device=local.device)
-        return stacked.index_select(0, pos)
+        return recv.reshape((world * per,) + tuple(local.shape[1:])).index_select(0, pos)
     dist.gather(send, None, dst=root, group=group)
     return None
+
+
+def open_render_target(world_size: int, rank: int, per_rank: int, row_bytes: int, root: int = 0, group=None):
+    """The fused gather: ONE buffer [world, per_rank, row_bytes] in the rendering GPU's HBM, mapped into
+    every rank's address space (CUDA IPC through torch's shared-tensor plumbing).  Each rank hands its
+    slab `target[rank]` to p3cs_group_create as the output buffer, so the strip kernel's TMA bulk stores
+    travel over NVLink straight into the renderer's memory while the next tiles are being computed; no
+    collective follows.  Returns (target tensor, keep-alive)."""
+    import torch
+    import torch.distributed as dist
+    from torch.multiprocessing.reductions import reduce_tensor
+
+    payload = [None]
+    target = None
+    if rank == root:
+        target = torch.empty((world_size, per_rank, row_bytes), dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+        payload[0] = reduce_tensor(target)
+    dist.broadcast_object_list(payload, src=root, group=group)
+    if rank != root:
+        rebuild, args = payload[0]
+        target = rebuild(*args)
+    dist.barrier(group)
+    return target, payload
 
 
 class CrowdShard:

@@ -162,6 +162,22 @@ extern "C" int p3cs_context_sync(p3cs_context ctx) {
   return P3CS_OK;
 }
 
+extern "C" int p3cs_context_enable_peer_access(p3cs_context ctx, int peer_device) {
+  if (ctx == nullptr) return fail(P3CS_ERR_INVALID, "context is NULL");
+  if (peer_device == ctx->device) return P3CS_OK;
+  DeviceGuard g(ctx->device);
+  int can = 0;
+  CUDA_TRY(cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+  if (!can) return fail(P3CS_ERR_UNSUPPORTED, "device %d cannot access device %d", ctx->device, peer_device);
+  cudaError_t err = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (err == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return P3CS_OK;
+  }
+  if (err != cudaSuccess) return fail(P3CS_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(err));
+  return P3CS_OK;
+}
+
 extern "C" void *p3cs_context_stream(p3cs_context ctx) { return ctx ? ctx->stream : nullptr; }
 
 // ------------------------------------------------------------------ mesh
