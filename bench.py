@@ -329,9 +329,8 @@ def run_gpu_arm(args):
             try:
                 from panda3d_b200 import crowd
                 per = -(-args.instances // world)
-                ctx.enable_peer_access(0)
-                target, keep = crowd.open_render_target(world, rank, per, pitch, root=0)
-                grp2 = _capi.Group(dmesh, n_local, palettes_dev=pal_dev.data_ptr(), outputs_dev=[target[rank].data_ptr()])
+                target = crowd.RenderTarget(ctx, world, rank, per, pitch, root=0)
+                grp2 = _capi.Group(dmesh, n_local, palettes_dev=pal_dev.data_ptr(), outputs_dev=[target.slab_ptr])
                 for _ in range(3):
                     grp2.animate()
                 barrier()
@@ -347,11 +346,13 @@ def run_gpu_arm(args):
                     n1 = len(range(1, args.instances, world))
                     pal1 = synth.make_palettes(T, n1, 1000 + 1)[n1 // 2]
                     expect, _, _ = oracle.OracleMesh(flat).animate(pal1)
-                    got = target[1][n1 // 2][:rows * stride].cpu().numpy().reshape(rows, stride)
+                    got = target.read_row(1, n1 // 2, rows * stride).reshape(rows, stride)
                     ok = bool(np.array_equal(got, expect[0]))
                 fused = {"ms_per_step": f_ms, "remote_instance_matches_oracle": ok,
                          "note": "animate with outputs peer-mapped on GPU 0: skinning and the gather to the rendering GPU in one kernel"}
                 grp2.close()
+                barrier()
+                target.close()
             except Exception as exc:  # reported, never hidden
                 fused = {"error": repr(exc)}
 

@@ -205,6 +205,16 @@ P3CS_EXPORT int p3cs_context_sync(p3cs_context ctx);
  * then writes its finished tiles straight into the renderer's buffer, the gather
  * overlaps the skinning tile by tile and needs no separate collective. */
 P3CS_EXPORT int p3cs_context_enable_peer_access(p3cs_context ctx, int peer_device);
+/* A render target: plain device memory on the context's GPU that other processes can map.
+ * p3cs_ipc_export fills a 64-byte handle (cudaIpcMemHandle_t) for a pointer returned by
+ * p3cs_device_alloc; another rank's context opens it with p3cs_ipc_open (peer access is
+ * enabled lazily) and passes the mapped pointer as an output buffer of p3cs_group_create. */
+P3CS_EXPORT int p3cs_device_alloc(p3cs_context ctx, size_t bytes, void **out);
+P3CS_EXPORT int p3cs_device_free(p3cs_context ctx, void *ptr);
+P3CS_EXPORT int p3cs_device_read(p3cs_context ctx, const void *device_src, void *host_dst, size_t bytes);
+P3CS_EXPORT int p3cs_ipc_export(p3cs_context ctx, void *ptr, unsigned char handle[64]);
+P3CS_EXPORT int p3cs_ipc_open(p3cs_context ctx, const unsigned char handle[64], void **out);
+P3CS_EXPORT int p3cs_ipc_close(p3cs_context ctx, void *ptr);
 /* The cudaStream_t of the context (for CUDA-event timing by the caller). */
 P3CS_EXPORT void *p3cs_context_stream(p3cs_context ctx);
 

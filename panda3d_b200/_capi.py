@@ -23,7 +23,8 @@ P3CS_OK, P3CS_ERR_INVALID, P3CS_ERR_UNSUPPORTED, P3CS_ERR_CUDA, P3CS_ERR_NOMEM, 
 EXPORTED_SYMBOLS = [
     "p3cs_api_version", "p3cs_device_count", "p3cs_last_error",
     "p3cs_context_create", "p3cs_context_destroy", "p3cs_context_sync", "p3cs_context_stream",
-    "p3cs_context_enable_peer_access",
+    "p3cs_context_enable_peer_access", "p3cs_device_alloc", "p3cs_device_free", "p3cs_device_read",
+    "p3cs_ipc_export", "p3cs_ipc_open", "p3cs_ipc_close",
     "p3cs_mesh_create", "p3cs_mesh_destroy", "p3cs_mesh_num_outputs", "p3cs_mesh_output_stride", "p3cs_mesh_num_rows",
     "p3cs_group_create", "p3cs_group_destroy", "p3cs_group_output_pitch", "p3cs_group_palettes_device",
     "p3cs_group_sliders_device", "p3cs_group_output_device", "p3cs_group_set_palettes", "p3cs_group_set_sliders",
@@ -96,6 +97,12 @@ def lib():
         L.p3cs_context_sync.argtypes = [C.c_void_p]
         L.p3cs_context_stream.argtypes = [C.c_void_p]
         L.p3cs_context_enable_peer_access.argtypes = [C.c_void_p, C.c_int]
+        L.p3cs_device_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.p3cs_device_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.p3cs_device_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.p3cs_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.p3cs_ipc_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.p3cs_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
         L.p3cs_mesh_create.argtypes = [C.c_void_p, C.POINTER(_MeshDesc), C.POINTER(C.c_void_p)]
         L.p3cs_mesh_destroy.argtypes = [C.c_void_p]
         L.p3cs_mesh_num_outputs.argtypes = [C.c_void_p]
@@ -154,6 +161,33 @@ class Context:
 
     def enable_peer_access(self, peer_device: int) -> None:
         _check(lib().p3cs_context_enable_peer_access(self.handle, peer_device))
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        _check(lib().p3cs_device_alloc(self.handle, nbytes, C.byref(p)))
+        return int(p.value)
+
+    def device_free(self, ptr: int) -> None:
+        _check(lib().p3cs_device_free(self.handle, ptr))
+
+    def device_read(self, ptr: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, np.uint8)
+        _check(lib().p3cs_device_read(self.handle, ptr, out.ctypes.data, nbytes))
+        return out
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        _check(lib().p3cs_ipc_export(self.handle, ptr, buf))
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        _check(lib().p3cs_ipc_open(self.handle, buf, C.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, ptr: int) -> None:
+        _check(lib().p3cs_ipc_close(self.handle, ptr))
 
     def close(self) -> None:
         if self.handle:

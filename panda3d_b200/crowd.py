@@ -80,27 +80,46 @@ def gather_outputs(local, num_instances: int, root: int = 0, group=None, recv=No
     return None
 
 
-def open_render_target(world_size: int, rank: int, per_rank: int, row_bytes: int, root: int = 0, group=None):
+class RenderTarget:
     """The fused gather: ONE buffer [world, per_rank, row_bytes] in the rendering GPU's HBM, mapped into
-    every rank's address space (CUDA IPC through torch's shared-tensor plumbing).  Each rank hands its
-    slab `target[rank]` to p3cs_group_create as the output buffer, so the strip kernel's TMA bulk stores
-    travel over NVLink straight into the renderer's memory while the next tiles are being computed; no
-    collective follows.  Returns (target tensor, keep-alive)."""
-    import torch
-    import torch.distributed as dist
-    from torch.multiprocessing.reductions import reduce_tensor
+    every rank's address space with CUDA IPC (cudaIpcMemLazyEnablePeerAccess).  Each rank hands its slab
+    (`slab_ptr`) to p3cs_group_create as the output buffer, so the strip kernel's TMA bulk stores travel
+    over NVLink straight into the renderer's memory while the next tiles are being computed; no collective
+    follows.  The 64-byte IPC handle is exchanged through torch.distributed (plumbing)."""
 
-    payload = [None]
-    target = None
-    if rank == root:
-        target = torch.empty((world_size, per_rank, row_bytes), dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
-        payload[0] = reduce_tensor(target)
-    dist.broadcast_object_list(payload, src=root, group=group)
-    if rank != root:
-        rebuild, args = payload[0]
-        target = rebuild(*args)
-    dist.barrier(group)
-    return target, payload
+    def __init__(self, ctx, world_size: int, rank: int, per_rank: int, row_bytes: int, root: int = 0, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.ctx, self.rank, self.root = ctx, rank, root
+        self.per_rank, self.row_bytes, self.world_size = per_rank, row_bytes, world_size
+        self.slab_bytes = per_rank * row_bytes
+        handle = torch.zeros(64, dtype=torch.uint8)
+        self.base = 0
+        if rank == root:
+            self.base = ctx.device_alloc(world_size * self.slab_bytes)
+            handle = torch.frombuffer(bytearray(ctx.ipc_export(self.base)), dtype=torch.uint8).clone()
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        h = handle.to(dev)
+        dist.broadcast(h, src=root, group=group)
+        if rank != root:
+            self.base = ctx.ipc_open(bytes(h.cpu().numpy().tobytes()))
+        dist.barrier(group)
+
+    @property
+    def slab_ptr(self) -> int:
+        return self.base + self.rank * self.slab_bytes
+
+    def read_row(self, slab: int, index: int, nbytes: int) -> np.ndarray:
+        return self.ctx.device_read(self.base + slab * self.slab_bytes + index * self.row_bytes, nbytes)
+
+    def close(self) -> None:
+        if self.base:
+            if self.rank == self.root:
+                self.ctx.device_free(self.base)
+            else:
+                self.ctx.ipc_close(self.base)
+            self.base = 0
 
 
 class CrowdShard:

@@ -178,6 +178,54 @@ extern "C" int p3cs_context_enable_peer_access(p3cs_context ctx, int peer_device
   return P3CS_OK;
 }
 
+extern "C" int p3cs_device_alloc(p3cs_context ctx, size_t bytes, void **out) {
+  if (ctx == nullptr || out == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_device_alloc: NULL argument");
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaMalloc(out, bytes > 0 ? bytes : 256));
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_device_free(p3cs_context ctx, void *ptr) {
+  if (ctx == nullptr) return fail(P3CS_ERR_INVALID, "context is NULL");
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaFree(ptr));
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_device_read(p3cs_context ctx, const void *device_src, void *host_dst, size_t bytes) {
+  if (ctx == nullptr || device_src == nullptr || host_dst == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_device_read: NULL argument");
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaMemcpyAsync(host_dst, device_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_ipc_export(p3cs_context ctx, void *ptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (ctx == nullptr || ptr == nullptr || handle == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_ipc_export: NULL argument");
+  DeviceGuard g(ctx->device);
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle, &h, 64);
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_ipc_open(p3cs_context ctx, const unsigned char handle[64], void **out) {
+  if (ctx == nullptr || handle == nullptr || out == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_ipc_open: NULL argument");
+  DeviceGuard g(ctx->device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_ipc_close(p3cs_context ctx, void *ptr) {
+  if (ctx == nullptr) return fail(P3CS_ERR_INVALID, "context is NULL");
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return P3CS_OK;
+}
+
 extern "C" void *p3cs_context_stream(p3cs_context ctx) { return ctx ? ctx->stream : nullptr; }
 
 // ------------------------------------------------------------------ mesh

@@ -18,13 +18,12 @@ mine = list(crowd.shard_instances(n_total, world, rank))
 stream = torch.cuda.Stream()
 with torch.cuda.stream(stream):
     ctx = _capi.Context(rank, stream.cuda_stream)
-    ctx.enable_peer_access(0)
     dm = _capi.Mesh(ctx, flat)
     pitch = (flat.num_rows * 24 + 255) // 256 * 256
     per = -(-n_total // world)
-    target, keep = crowd.open_render_target(world, rank, per, pitch, root=0)
+    target = crowd.RenderTarget(ctx, world, rank, per, pitch, root=0)
     pal = synth.make_palettes(flat.num_transforms, n_total, 5)
-    g = _capi.Group(dm, len(mine), outputs_dev=[target[rank].data_ptr()])
+    g = _capi.Group(dm, len(mine), outputs_dev=[target.slab_ptr])
     g.set_palettes(pal[mine])
     g.animate()
     ctx.sync()
@@ -35,9 +34,11 @@ with torch.cuda.stream(stream):
         ok = True
         for i in range(n_total):
             r, j = i % world, i // world
-            got = target[r][j][: flat.num_rows * 24].cpu().numpy().reshape(flat.num_rows, 24)
+            got = target.read_row(r, j, flat.num_rows * 24).reshape(flat.num_rows, 24)
             ok &= bool(np.array_equal(got, om.animate(pal[i])[0][0]))
         print("PEER_PROBE path=%s ok=%s" % (os.environ.get("P3CS_PATH", "strip"), ok), flush=True)
     g.close(); dm.close()
+    dist.barrier()
+    target.close()
 dist.barrier()
 dist.destroy_process_group()
