@@ -347,8 +347,11 @@ def run_gpu_arm(args):
                     pal1 = synth.make_palettes(T, n1, 1000 + 1)[n1 // 2]
                     expect, _, _ = oracle.OracleMesh(flat).animate(pal1)
                     got = target.read_row(1, n1 // 2, rows * stride).reshape(rows, stride)
-                    ok = bool(np.array_equal(got, expect[0]))
-                fused = {"ms_per_step": f_ms, "remote_instance_matches_oracle": ok,
+                    gf = got.view(np.float32).astype(np.float64)
+                    ef = expect[0].view(np.float32).astype(np.float64)
+                    rel = float((np.abs(gf - ef) / np.maximum(np.abs(ef).max(axis=1, keepdims=True), 1e-30)).max())
+                    ok = {"max_rel_err": rel, "differing_bytes": int((got != expect[0]).sum()), "within_1e-5": bool(rel <= 1e-5)}
+                fused = {"ms_per_step": f_ms, "remote_instance_vs_oracle": ok,
                          "note": "animate with outputs peer-mapped on GPU 0: skinning and the gather to the rendering GPU in one kernel"}
                 grp2.close()
                 barrier()
