@@ -183,3 +183,24 @@ def have_ref() -> bool:
 def ref_run(recipe_path: str, golden_path: str) -> None:
     """Runs the UNMODIFIED reference's animate_vertices on a recipe (oracle/ref_harness.cxx)."""
     subprocess.run([REF_HARNESS, "run", recipe_path, golden_path], check=True, capture_output=True)
+
+
+class _Skeleton(C.Structure):
+    _fields_ = [("num_joints", C.c_int32), ("coordinate_system", C.c_int32),
+                ("parent", C.c_void_p), ("has_channel", C.c_void_p), ("table_length", C.c_void_p),
+                ("table_offset", C.c_void_p), ("tables", C.c_void_p), ("default_value", C.c_void_p),
+                ("initial_inverse", C.c_void_p), ("root_xform", C.c_void_p)]
+
+
+def pose(skel, frame: int) -> np.ndarray:
+    """CharacterJoint::_skinning_matrix of every joint at `frame` ([J,16]); palette = result[skel.palette_joint]."""
+    arrs = [np.ascontiguousarray(a) for a in (skel.parent, skel.has_channel, skel.table_length, skel.table_offset,
+                                              skel.tables if skel.tables.size else np.zeros(1, np.float32),
+                                              skel.default_value, skel.initial_inverse, skel.root_xform)]
+    s = _Skeleton(skel.num_joints, skel.coordinate_system, *[a.ctypes.data for a in arrs])
+    out = np.empty((skel.num_joints, 16), np.float32)
+    lib().p3o_pose.restype = C.c_int
+    rc = lib().p3o_pose(C.byref(s), C.c_int(int(frame)), out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError(f"oracle pose failed rc={rc}")
+    return out

@@ -36,6 +36,12 @@
 #include "animControlCollection.h"
 #include "coordinateSystem.h"
 #include "load_prc_file.h"
+#include "characterJoint.h"
+#include "characterJointBundle.h"
+#include "jointVertexTransform.h"
+#include "animChannelMatrixXfmTable.h"
+#include "partBundle.h"
+#include "movingPartMatrix.h"
 
 #include <algorithm>
 #include <chrono>
@@ -409,6 +415,69 @@ static int cmd_run(const char *in_path, const char *out_path) {
   return write_case(out_path, out) ? 0 : 1;
 }
 
+// ------------------------------------------------- skeleton export ("next" row f1)
+// Joints in depth-first order (a parent always precedes its children), with what
+// MovingPartBase::do_update / CharacterJoint::update_internals read per joint.
+static void collect_joints(PartGroup *part, int parent_joint, std::vector<CharacterJoint *> &joints, std::vector<int32_t> &parents) {
+  int me = parent_joint;
+  if (part->is_character_joint()) {
+    me = (int)joints.size();
+    joints.push_back(DCAST(CharacterJoint, part));
+    parents.push_back(parent_joint);
+  }
+  for (int i = 0; i < part->get_num_children(); ++i) collect_joints(part->get_child(i), me, joints, parents);
+}
+
+static void export_skeleton(Character *ch, const Exported &ex, Case &c) {
+  PartBundle *bundle = ch->get_bundle(0);
+  std::vector<CharacterJoint *> joints; std::vector<int32_t> parents;
+  collect_joints(bundle, -1, joints, parents);
+  int J = (int)joints.size();
+  std::vector<int32_t> has_channel(J, 0), tlen(J * 12, 0), toff(J * 12, 0);
+  std::vector<float> tables, defaults(J * 16), inverse(J * 16);
+  for (int j = 0; j < J; ++j) {
+    CharacterJoint *joint = joints[j];
+    LMatrix4f dv = LCAST(float, joint->get_default_value());
+    memcpy(&defaults[j * 16], dv.get_data(), 64);
+    LMatrix4f inv = LCAST(float, joint->_initial_net_transform_inverse);
+    memcpy(&inverse[j * 16], inv.get_data(), 64);
+    AnimChannelBase *bound = joint->get_max_bound() > 0 ? joint->get_bound(0) : nullptr;
+    if (bound != nullptr && bound->is_of_type(AnimChannelMatrixXfmTable::get_class_type())) {
+      AnimChannelMatrixXfmTable *chan = DCAST(AnimChannelMatrixXfmTable, bound);
+      has_channel[j] = 1;
+      for (int i = 0; i < 12; ++i) {
+        char id = "ijkabchprxyz"[i];  // matrix_component_letters (chan/animChannelMatrixXfmTable.cxx)
+        CPTA_stdfloat t = chan->get_table(id);
+        toff[j * 12 + i] = (int32_t)tables.size();
+        tlen[j * 12 + i] = (int32_t)t.size();
+        for (size_t k = 0; k < t.size(); ++k) tables.push_back((float)t[k]);
+      }
+    }
+  }
+  std::vector<int32_t> palette_joint;
+  for (const VertexTransform *t : ex.palette) {
+    int idx = -1;
+    if (t->is_of_type(JointVertexTransform::get_class_type())) {
+      const CharacterJoint *joint = ((const JointVertexTransform *)t)->get_joint();
+      for (int j = 0; j < J; ++j) if (joints[j] == joint) idx = j;
+    }
+    palette_joint.push_back(idx);
+  }
+  LMatrix4f root = LCAST(float, bundle->get_root_xform());
+  std::vector<float> rootv(root.get_data(), root.get_data() + 16);
+  std::vector<int32_t> meta = {J, (int32_t)tables.size()};
+  c["skel_meta"] = make_blob(DT_I32, meta, {2});
+  c["skel_parent"] = make_blob(DT_I32, parents, {(uint64_t)J});
+  c["skel_has_channel"] = make_blob(DT_I32, has_channel, {(uint64_t)J});
+  c["skel_table_length"] = make_blob(DT_I32, tlen, {(uint64_t)J, 12});
+  c["skel_table_offset"] = make_blob(DT_I32, toff, {(uint64_t)J, 12});
+  c["skel_tables"] = make_blob(DT_F32, tables, {(uint64_t)tables.size()});
+  c["skel_default_value"] = make_blob(DT_F32, defaults, {(uint64_t)J, 16});
+  c["skel_initial_inverse"] = make_blob(DT_F32, inverse, {(uint64_t)J, 16});
+  c["skel_root_xform"] = make_blob(DT_F32, rootv, {16});
+  c["skel_palette_joint"] = make_blob(DT_I32, palette_joint, {(uint64_t)palette_joint.size()});
+}
+
 static int cmd_egg(int argc, char **argv) {
   const char *model_path = argv[2], *anim_path = argv[3], *out_path = argv[4];
   PT(PandaNode) model = load_egg_file(model_path);
@@ -431,6 +500,7 @@ static int cmd_egg(int argc, char **argv) {
   if (vd == nullptr) { fprintf(stderr, "no AT_panda vertex data\n"); return 1; }
   Case out;
   Exported ex = export_vertex_data(vd, out);
+  export_skeleton(ch, ex, out);
   std::vector<int32_t> frames;
   for (int i = 5; i < argc; ++i) {
     int fr = atoi(argv[i]);

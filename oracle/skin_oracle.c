@@ -730,3 +730,49 @@ int p3o_animate(const p3o_mesh *mesh, const float *palette, const float *sliders
   free(blends);
   return 0;
 }
+
+/* ---- joint hierarchy ("next" row f1) ------------------------------------------------------- */
+
+/* MATRIX4_PRODUCT, panda/src/linmath/lmatrix4_src.I:874-893: res = a * b */
+static void mul4(float *res, const float *a, const float *b) {
+  int i, j;
+  for (i = 0; i < 4; ++i)
+    for (j = 0; j < 4; ++j)
+      M4(res, i, j) = M4(a, i, 0) * M4(b, 0, j) + M4(a, i, 1) * M4(b, 1, j) + M4(a, i, 2) * M4(b, 2, j) + M4(a, i, 3) * M4(b, 3, j);
+}
+
+int p3o_pose(const p3o_skeleton *skel, int frame, float *skinning_out) {
+  int J = skel->num_joints, j, i, r, c;
+  float *net = (float *)malloc((size_t)(J > 0 ? J : 1) * 16 * sizeof(float));
+  if (!net) return -2;
+  for (j = 0; j < J; ++j) {
+    float value[16];
+    if (skel->has_channel[j]) {
+      /* AnimChannelMatrixXfmTable::get_value: components[i] = table[frame % size] or the default
+       * (1 for the scales, 0 otherwise; animChannelMatrixXfmTable.I:75-85), then compose_matrix */
+      float comp[12], up3[9];
+      for (i = 0; i < 12; ++i) {
+        int len = skel->table_length[j * 12 + i];
+        comp[i] = len == 0 ? (i < 3 ? 1.0f : 0.0f) : skel->tables[skel->table_offset[j * 12 + i] + frame % len];
+      }
+      p3o_compose3(up3, comp + 0, comp + 3, comp + 6, skel->coordinate_system);
+      /* LMatrix4f(upper3, translate), compose_matrix_src.I:18-28 */
+      for (r = 0; r < 3; ++r) {
+        for (c = 0; c < 3; ++c) M4(value, r, c) = M3(up3, r, c);
+        M4(value, r, 3) = 0.0f;
+      }
+      M4(value, 3, 0) = comp[9];
+      M4(value, 3, 1) = comp[10];
+      M4(value, 3, 2) = comp[11];
+      M4(value, 3, 3) = 1.0f;
+    } else {
+      memcpy(value, skel->default_value + (size_t)j * 16, sizeof(value));
+    }
+    /* CharacterJoint::update_internals: _net_transform = _value * parent net (or root xform) */
+    mul4(net + (size_t)j * 16, value, skel->parent[j] >= 0 ? net + (size_t)skel->parent[j] * 16 : skel->root_xform);
+    /* _skinning_matrix = _initial_net_transform_inverse * _net_transform */
+    mul4(skinning_out + (size_t)j * 16, skel->initial_inverse + (size_t)j * 16, net + (size_t)j * 16);
+  }
+  free(net);
+  return 0;
+}

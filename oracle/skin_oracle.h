@@ -76,6 +76,26 @@ typedef struct p3o_mesh {
 int p3o_animate(const p3o_mesh *mesh, const float *palette, const float *sliders,
                 uint8_t *const *out_arrays, float *blends_out, int32_t *selection_out);
 
+/* "Next" row f1: the joint hierarchy that produces the palette.  Joints are listed
+ * parents-first.  Restates, for one AnimControl without frame blending,
+ * AnimChannelMatrixXfmTable::get_value (chan/animChannelMatrixXfmTable.cxx:112-124),
+ * MovingPartMatrix::get_blend_value (chan/movingPartMatrix.cxx:52-76) and
+ * CharacterJoint::update_internals (char/characterJoint.cxx:110-150). */
+typedef struct p3o_skeleton {
+  int32_t num_joints;
+  int32_t coordinate_system;
+  const int32_t *parent;          /* -1: top-level joint (uses the bundle's root transform) */
+  const int32_t *has_channel;     /* 0: keeps MovingPartMatrix::_default_value */
+  const int32_t *table_length;    /* [J][12] i j k a b c h p r x y z; 0 = default component */
+  const int32_t *table_offset;    /* [J][12] into tables */
+  const float *tables;
+  const float *default_value;     /* [J][16] */
+  const float *initial_inverse;   /* [J][16] CharacterJoint::_initial_net_transform_inverse */
+  const float *root_xform;        /* [16] PartBundle::get_root_xform() */
+} p3o_skeleton;
+/* skinning_out: [J][16] = CharacterJoint::_skinning_matrix of every joint at `frame`. */
+int p3o_pose(const p3o_skeleton *skel, int frame, float *skinning_out);
+
 /* Individual pieces, exported for unit tests against the reference's adjacent
  * tests (tests/linmath/test_lmatrix4.py, test_compose_matrix.py). */
 void p3o_blend(const float *palette, const int32_t *xf, const float *w, int n, float *out16);

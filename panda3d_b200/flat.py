@@ -140,3 +140,36 @@ def mesh_from_case(case: Dict[str, np.ndarray]) -> FlatMesh:
         blend_weight=case["blend_weight"].astype(np.float32),
         row_ranges=case["rows"].reshape(-1, 2).astype(np.int32),
         num_sliders=int(meta[5]), morphs=morphs, coordinate_system=int(meta[6]) or CS_zup_right)
+
+
+@dataclass
+class FlatSkeleton:
+    """The joint hierarchy that produces a palette ("next" row f1): what
+    MovingPartBase::do_update / CharacterJoint::update_internals read, joints listed parents-first
+    (`p3cs_skeleton_desc` of include/p3cudaskin.h)."""
+    parent: np.ndarray            # int32 [J], -1 = top-level joint
+    has_channel: np.ndarray       # int32 [J]
+    table_length: np.ndarray      # int32 [J, 12]  (i j k a b c h p r x y z; 0 = default component)
+    table_offset: np.ndarray      # int32 [J, 12]
+    tables: np.ndarray            # float32 [*]
+    default_value: np.ndarray     # float32 [J, 16]
+    initial_inverse: np.ndarray   # float32 [J, 16]
+    root_xform: np.ndarray        # float32 [16]
+    palette_joint: np.ndarray     # int32 [T]: joint feeding each palette slot
+    coordinate_system: int = CS_zup_right
+
+    @property
+    def num_joints(self) -> int:
+        return int(len(self.parent))
+
+
+def skeleton_from_case(case: Dict[str, np.ndarray]) -> FlatSkeleton:
+    return FlatSkeleton(
+        parent=case["skel_parent"].astype(np.int32), has_channel=case["skel_has_channel"].astype(np.int32),
+        table_length=case["skel_table_length"].astype(np.int32).reshape(-1, 12),
+        table_offset=case["skel_table_offset"].astype(np.int32).reshape(-1, 12),
+        tables=case["skel_tables"].astype(np.float32), default_value=case["skel_default_value"].astype(np.float32).reshape(-1, 16),
+        initial_inverse=case["skel_initial_inverse"].astype(np.float32).reshape(-1, 16),
+        root_xform=case["skel_root_xform"].astype(np.float32).reshape(16),
+        palette_joint=case["skel_palette_joint"].astype(np.int32),
+        coordinate_system=int(case["meta"][6]) or CS_zup_right)

@@ -61,7 +61,7 @@ def main():
     model = os.path.join(REF, "models", "panda-model.egg")
     anim = os.path.join(REF, "models", "panda-walk4.egg")
     out = os.path.join(HERE, "panda_walk4.p3cs")
-    subprocess.run([HARNESS, "egg", model, anim, out, "0", "10", "37"], check=True, timeout=120,
+    subprocess.run([HARNESS, "egg", model, anim, out, "0", "10", "37", "59"], check=True, timeout=120,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     print("wrote", out, os.path.getsize(out))
 
