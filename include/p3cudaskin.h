@@ -294,6 +294,41 @@ P3CS_EXPORT int p3cs_animate_vertices(p3cs_group group, int instance,
                                       const float *host_palette, const float *host_sliders,
                                       void *const *host_outputs);
 
+/* ---- joint hierarchy on the GPU ("next" row f1 of SURVEY.md section 8f) ---- */
+
+typedef struct p3cs_skeleton_s *p3cs_skeleton;
+
+/* What PartBundle::update -> MovingPartBase::do_update -> CharacterJoint::update_internals
+ * read, flattened, joints listed parents-first (chan/movingPartBase.cxx:109-166,
+ * char/characterJoint.cxx:110-172).  Covers one AnimControl without frame blending
+ * (chan/movingPartMatrix.cxx:71-76). */
+typedef struct p3cs_skeleton_desc {
+  uint32_t struct_size;
+  int32_t num_joints;
+  int32_t coordinate_system;      /* P3CS_CS_*; convention of compose_matrix */
+  int32_t num_palette;            /* T: must equal the mesh's num_transforms */
+  const int32_t *parent;          /* [J] index of the parent CharacterJoint, -1 = top-level */
+  const int32_t *has_channel;     /* [J] 0: the joint keeps MovingPartMatrix::_default_value */
+  const int32_t *table_length;    /* [J][12] AnimChannelMatrixXfmTable tables i j k a b c h p r x y z;
+                                     0 = default component (animChannelMatrixXfmTable.I:75-85) */
+  const int32_t *table_offset;    /* [J][12] offsets into `tables` */
+  int32_t num_table_values;
+  const float *tables;
+  const float *default_value;     /* [J][16] */
+  const float *initial_inverse;   /* [J][16] CharacterJoint::_initial_net_transform_inverse */
+  const float *root_xform;        /* [16] PartBundle::get_root_xform() */
+  const int32_t *palette_joint;   /* [T] joint behind each palette slot (JointVertexTransform::get_joint) */
+} p3cs_skeleton_desc;
+
+P3CS_EXPORT int p3cs_skeleton_create(p3cs_context ctx, const p3cs_skeleton_desc *desc, p3cs_skeleton *out);
+P3CS_EXPORT int p3cs_skeleton_destroy(p3cs_skeleton skeleton);
+/* Evaluates the hierarchy of `count` instances at host_frames[i] (AnimControl::get_frame()) and
+ * writes their palettes into the group's device buffer -- replaces Character::update +
+ * p3cs_group_set_palettes: per frame the host sends one int per instance instead of T matrices. */
+P3CS_EXPORT int p3cs_group_pose(p3cs_group group, p3cs_skeleton skeleton, int first, int count, const int32_t *host_frames);
+/* Device -> host read-back of `count` palettes (count * T * 16 floats); parity hook. */
+P3CS_EXPORT int p3cs_group_read_palettes(p3cs_group group, int first, int count, float *host_dst);
+
 /* ---- plugin table (load_dso + dlsym("p3cs_get_api")) -------------------- */
 
 typedef struct p3cs_api {

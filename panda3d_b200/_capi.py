@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = [
     "p3cs_group_sliders_device", "p3cs_group_output_device", "p3cs_group_set_palettes", "p3cs_group_set_sliders",
     "p3cs_group_animate", "p3cs_group_read_output", "p3cs_group_read_selection", "p3cs_group_read_blends",
     "p3cs_group_set_profiling", "p3cs_group_last_timings", "p3cs_animate_vertices", "p3cs_get_api",
+    "p3cs_skeleton_create", "p3cs_skeleton_destroy", "p3cs_group_pose", "p3cs_group_read_palettes",
 ]
 
 
@@ -64,6 +65,14 @@ class _MeshDesc(C.Structure):
         ("num_row_ranges", C.c_int32), ("row_ranges", C.POINTER(C.c_int32)),
         ("num_sliders", C.c_int32), ("num_morphs", C.c_int32), ("morphs", C.POINTER(_MorphDesc)),
     ]
+
+
+class _SkeletonDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("num_joints", C.c_int32), ("coordinate_system", C.c_int32),
+                ("num_palette", C.c_int32), ("parent", C.c_void_p), ("has_channel", C.c_void_p),
+                ("table_length", C.c_void_p), ("table_offset", C.c_void_p), ("num_table_values", C.c_int32),
+                ("tables", C.c_void_p), ("default_value", C.c_void_p), ("initial_inverse", C.c_void_p),
+                ("root_xform", C.c_void_p), ("palette_joint", C.c_void_p)]
 
 
 class _GroupBuffers(C.Structure):
@@ -123,6 +132,10 @@ def lib():
         L.p3cs_group_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.p3cs_group_last_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
         L.p3cs_animate_vertices.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.p3cs_skeleton_create.argtypes = [C.c_void_p, C.POINTER(_SkeletonDesc), C.POINTER(C.c_void_p)]
+        L.p3cs_skeleton_destroy.argtypes = [C.c_void_p]
+        L.p3cs_group_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.p3cs_group_read_palettes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -252,6 +265,29 @@ class Mesh:
             self.handle = C.c_void_p()
 
 
+class Skeleton:
+    """p3cs_skeleton: the joint hierarchy + animation tables of a Character, resident in HBM."""
+
+    def __init__(self, ctx: Context, skel):
+        self.ctx, self.flat = ctx, skel
+        a = [np.ascontiguousarray(x) for x in (
+            skel.parent.astype(np.int32), skel.has_channel.astype(np.int32), skel.table_length.astype(np.int32),
+            skel.table_offset.astype(np.int32), skel.tables.astype(np.float32) if skel.tables.size else np.zeros(1, np.float32),
+            skel.default_value.astype(np.float32), skel.initial_inverse.astype(np.float32),
+            skel.root_xform.astype(np.float32), skel.palette_joint.astype(np.int32))]
+        self._keep = a
+        d = _SkeletonDesc(C.sizeof(_SkeletonDesc), skel.num_joints, skel.coordinate_system, len(skel.palette_joint),
+                          a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data, int(skel.tables.size),
+                          a[4].ctypes.data, a[5].ctypes.data, a[6].ctypes.data, a[7].ctypes.data, a[8].ctypes.data)
+        self.handle = C.c_void_p()
+        _check(lib().p3cs_skeleton_create(ctx.handle, C.byref(d), C.byref(self.handle)))
+
+    def close(self) -> None:
+        if self.handle:
+            lib().p3cs_skeleton_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
 class Group:
     """p3cs_group: n animated instances (a crowd of Characters) of one mesh."""
 
@@ -298,6 +334,17 @@ class Group:
         s = self.mesh.flat.num_sliders
         count = v.size // s if s else 0
         _check(lib().p3cs_group_set_sliders(self.handle, first, count, v.ctypes.data))
+
+    def pose(self, skeleton: "Skeleton", frames, first: int = 0) -> None:
+        """Joint hierarchy on the GPU: one animation frame per instance in, palettes written on the device."""
+        f = np.ascontiguousarray(frames, np.int32)
+        _check(lib().p3cs_group_pose(self.handle, skeleton.handle, first, int(f.size), f.ctypes.data))
+
+    def read_palettes(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        count = self.n - first if count is None else count
+        out = np.empty((count, self.mesh.flat.num_transforms, 16), np.float32)
+        _check(lib().p3cs_group_read_palettes(self.handle, first, count, out.ctypes.data))
+        return out
 
     # ---- the hot path
     def animate(self) -> None:

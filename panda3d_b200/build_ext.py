@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libp3cudaskin.so")
-SOURCES = ["p3cs_api.cu", "p3cs_kernels.cu", "p3cs_strip.cu"]
+SOURCES = ["p3cs_api.cu", "p3cs_kernels.cu", "p3cs_strip.cu", "p3cs_pose.cu"]
 HEADERS = ["p3cs_kernels.cuh", "p3cs_math.cuh", "p3cs_device.cuh", os.path.join("..", "..", "include", "p3cudaskin.h")]
 
 NVCC_FLAGS = [

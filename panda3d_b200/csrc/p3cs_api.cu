@@ -63,6 +63,8 @@ struct p3cs_group_s {
   std::vector<cudaEvent_t> prof;  // event pairs per launch when profiling
   std::vector<int> prof_kind;     // 0 blend, 1 skin, per pair
   bool profiling = false;
+  int *frames_dev = nullptr;  // per-instance animation frames of the last p3cs_group_pose
+  int frames_capacity = 0;
   p3cs_timings last{};
   bool timed = false;
 };
@@ -632,6 +634,7 @@ extern "C" int p3cs_group_destroy(p3cs_group grp) {
   for (auto e : grp->ev)
     if (e) cudaEventDestroy(e);
   for (auto e : grp->prof) cudaEventDestroy(e);
+  if (grp->frames_dev != nullptr) cudaFree(grp->frames_dev);
   delete grp;
   return P3CS_OK;
 }
@@ -853,6 +856,118 @@ extern "C" int p3cs_animate_vertices(p3cs_group grp, int instance, const float *
     for (int o = 0; o < m.num_outputs; ++o)
       if (host_outputs[o] != nullptr && (rc = p3cs_group_read_output(grp, o, instance, 1, host_outputs[o])) != P3CS_OK) return rc;
   return p3cs_context_sync(grp->mesh->ctx);
+}
+
+// ------------------------------------------------------------------ joint hierarchy (f1)
+struct p3cs_skeleton_s {
+  p3cs_context ctx = nullptr;
+  SkeletonDev dev{};
+  int num_palette = 0;
+  std::vector<void *> allocations;
+};
+
+template <class T>
+static int upload_skel(p3cs_skeleton sk, const T *host, size_t count, const T **out) {
+  void *d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, std::max<size_t>(count, 1) * sizeof(T)));
+  sk->allocations.push_back(d);
+  if (count > 0) CUDA_TRY(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, sk->ctx->stream));
+  *out = static_cast<const T *>(d);
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_skeleton_create(p3cs_context ctx, const p3cs_skeleton_desc *d, p3cs_skeleton *out) {
+  if (out == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_skeleton_create: out is NULL");
+  *out = nullptr;
+  if (ctx == nullptr || d == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_skeleton_create: NULL argument");
+  if (d->struct_size != sizeof(p3cs_skeleton_desc)) return fail(P3CS_ERR_INVALID, "p3cs_skeleton_desc::struct_size mismatch");
+  const int J = d->num_joints;
+  if (J < 0 || J > 3000) return fail(P3CS_ERR_UNSUPPORTED, "num_joints %d outside 0..3000", J);
+  int cs = d->coordinate_system == 0 ? P3CS_CS_ZUP_RIGHT : d->coordinate_system;
+  if (cs < P3CS_CS_ZUP_RIGHT || cs > P3CS_CS_YUP_LEFT) return fail(P3CS_ERR_INVALID, "bad coordinate_system %d", cs);
+  std::vector<int> level(std::max(J, 1), 0);
+  int max_level = 0;
+  for (int j = 0; j < J; ++j) {
+    const int p = d->parent[j];
+    if (p >= j) return fail(P3CS_ERR_INVALID, "joint %d: parent %d does not precede it (joints must be listed parents-first)", j, p);
+    level[j] = p < 0 ? 0 : level[p] + 1;
+    max_level = std::max(max_level, level[j]);
+    for (int i = 0; i < 12; ++i) {
+      const int len = d->table_length[j * 12 + i], off = d->table_offset[j * 12 + i];
+      if (len < 0 || off < 0 || off + len > d->num_table_values) return fail(P3CS_ERR_INVALID, "joint %d: table %d out of range", j, i);
+    }
+  }
+  for (int t = 0; t < d->num_palette; ++t)
+    if (d->palette_joint[t] < 0 || d->palette_joint[t] >= J) return fail(P3CS_ERR_INVALID, "palette slot %d has no joint", t);
+  DeviceGuard g(ctx->device);
+  p3cs_skeleton sk = new (std::nothrow) p3cs_skeleton_s;
+  if (sk == nullptr) return fail(P3CS_ERR_NOMEM, "out of host memory");
+  sk->ctx = ctx;
+  sk->num_palette = d->num_palette;
+  SkeletonDev &s = sk->dev;
+  s.num_joints = J;
+  s.coordinate_system = cs;
+  s.max_level = max_level;
+  int rc;
+  auto bail = [&](int code) {
+    p3cs_skeleton_destroy(sk);
+    return code;
+  };
+  if ((rc = upload_skel<int>(sk, d->parent, J, &s.parent)) != P3CS_OK) return bail(rc);
+  if ((rc = upload_skel<int>(sk, level.data(), J, &s.level)) != P3CS_OK) return bail(rc);
+  if ((rc = upload_skel<int>(sk, d->has_channel, J, &s.has_channel)) != P3CS_OK) return bail(rc);
+  if ((rc = upload_skel<int>(sk, d->table_length, (size_t)J * 12, &s.table_length)) != P3CS_OK) return bail(rc);
+  if ((rc = upload_skel<int>(sk, d->table_offset, (size_t)J * 12, &s.table_offset)) != P3CS_OK) return bail(rc);
+  if ((rc = upload_skel<float>(sk, d->tables, d->num_table_values, &s.tables)) != P3CS_OK) return bail(rc);
+  if ((rc = upload_skel<float>(sk, d->default_value, (size_t)J * 16, &s.default_value)) != P3CS_OK) return bail(rc);
+  if ((rc = upload_skel<float>(sk, d->initial_inverse, (size_t)J * 16, &s.initial_inverse)) != P3CS_OK) return bail(rc);
+  if ((rc = upload_skel<float>(sk, d->root_xform, 16, &s.root_xform)) != P3CS_OK) return bail(rc);
+  if ((rc = upload_skel<int>(sk, d->palette_joint, d->num_palette, &s.palette_joint)) != P3CS_OK) return bail(rc);
+  cudaError_t err = cudaStreamSynchronize(ctx->stream);
+  if (err != cudaSuccess) return bail(fail(P3CS_ERR_CUDA, "skeleton upload failed: %s", cudaGetErrorString(err)));
+  *out = sk;
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_skeleton_destroy(p3cs_skeleton sk) {
+  if (sk == nullptr) return P3CS_OK;
+  DeviceGuard g(sk->ctx->device);
+  for (void *p : sk->allocations) cudaFree(p);
+  delete sk;
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_group_pose(p3cs_group grp, p3cs_skeleton sk, int first, int count, const int32_t *host_frames) {
+  int rc = check_span(grp, first, count, "p3cs_group_pose");
+  if (rc != P3CS_OK) return rc;
+  if (sk == nullptr || host_frames == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_pose: NULL argument");
+  if (sk->num_palette != grp->mesh->dev.num_transforms)
+    return fail(P3CS_ERR_INVALID, "skeleton feeds %d palette slots, the mesh has %d transforms", sk->num_palette, grp->mesh->dev.num_transforms);
+  if (count == 0) return P3CS_OK;
+  DeviceGuard g(grp->mesh->ctx->device);
+  cudaStream_t s = grp->mesh->ctx->stream;
+  if (grp->frames_capacity < count) {
+    if (grp->frames_dev != nullptr) cudaFree(grp->frames_dev);
+    grp->frames_dev = nullptr;
+    CUDA_TRY(cudaMalloc(&grp->frames_dev, (size_t)count * sizeof(int)));
+    grp->frames_capacity = count;
+  }
+  CUDA_TRY(cudaMemcpyAsync(grp->frames_dev, host_frames, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, s));
+  launch_pose(sk->dev, const_cast<float *>(grp->dev.palettes), sk->num_palette, grp->frames_dev, first, count, s);
+  CUDA_TRY(cudaGetLastError());
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_group_read_palettes(p3cs_group grp, int first, int count, float *host_dst) {
+  int rc = check_span(grp, first, count, "p3cs_group_read_palettes");
+  if (rc != P3CS_OK) return rc;
+  if (host_dst == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_read_palettes: destination is NULL");
+  DeviceGuard g(grp->mesh->ctx->device);
+  const size_t per = (size_t)grp->mesh->dev.num_transforms * 16;
+  if (per * count == 0) return P3CS_OK;
+  CUDA_TRY(cudaMemcpyAsync(host_dst, grp->dev.palettes + per * first, per * count * 4, cudaMemcpyDeviceToHost, grp->mesh->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(grp->mesh->ctx->stream));
+  return P3CS_OK;
 }
 
 // ------------------------------------------------------------------ plugin table

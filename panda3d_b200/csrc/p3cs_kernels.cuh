@@ -79,6 +79,25 @@ struct GroupDev {
   int32_t *selection;     // optional [num_rows] debug/parity output (instance 0 of the launch)
 };
 
+// Joint hierarchy ("next" row f1): static description of a character's skeleton, joints parents-first.
+struct SkeletonDev {
+  int num_joints;
+  int coordinate_system;
+  int max_level;
+  const int *parent;          // -1: top-level joint
+  const int *level;           // depth in the joint tree (parents have smaller levels)
+  const int *has_channel;
+  const int *table_length;    // [J][12]
+  const int *table_offset;    // [J][12]
+  const float *tables;
+  const float *default_value; // [J][16]
+  const float *initial_inverse;
+  const float *root_xform;    // [16]
+  const int *palette_joint;   // [T]
+};
+void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, const int *frames_dev, int first_instance, int count,
+                 cudaStream_t stream);
+
 void launch_blend(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);
 void launch_skin(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);
 // The fused path: palette -> smem, per tile: blend records -> smem, rows via TMA bulk copies.

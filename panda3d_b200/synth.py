@@ -254,3 +254,38 @@ def config_c5_meshes() -> List[Tuple[SynthMesh, int]]:
     for i, (n, t, b, count) in enumerate(shapes):
         out.append((make_mesh(n, t, b, seed=500 + i, tbn=True, texcoord=True, index_order="runs", name=f"C5.{i}"), count))
     return out
+
+
+def make_skeleton(num_joints: int, num_frames: int, seed: int, *, palette_joints: Optional[int] = None,
+                  coordinate_system: int = F.CS_zup_right):
+    """A random joint tree (parents-first) animated by hpr + xyz tables of `num_frames` frames, constant
+    scale tables, no shear -- the table shapes an egg `<Xfm$Anim_S$>` bundle has (cf. panda-walk4.egg).
+    initial_inverse is the inverse of the net transform at frame 0, so frame 0 skins to the bind pose."""
+    from .flat import FlatSkeleton
+    rng = np.random.default_rng(seed)
+    J = num_joints
+    parent = np.asarray([-1] + [int(rng.integers(max(0, j - 6), j)) for j in range(1, J)], np.int32)
+    tlen = np.zeros((J, 12), np.int32)
+    toff = np.zeros((J, 12), np.int32)
+    tables = []
+    pos = 0
+    for j in range(J):
+        for i in range(12):
+            if i < 3:
+                vals = np.full(1, 1.0, np.float32)                       # constant unit scale
+            elif i < 6:
+                vals = np.zeros(0, np.float32)                           # no shear table
+            elif i < 9:
+                vals = rng.uniform(-60, 60, num_frames).astype(np.float32)  # h p r in degrees
+            else:
+                vals = (rng.uniform(-0.3, 0.3) + 0.05 * rng.standard_normal(num_frames)).astype(np.float32)
+            tlen[j, i], toff[j, i] = len(vals), pos
+            tables.append(vals)
+            pos += len(vals)
+    tables = np.concatenate(tables).astype(np.float32)
+    ident = np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (J, 1))
+    skel = FlatSkeleton(parent=parent, has_channel=np.ones(J, np.int32), table_length=tlen, table_offset=toff, tables=tables,
+                        default_value=ident.copy(), initial_inverse=ident.copy(), root_xform=np.eye(4, dtype=np.float32).reshape(16),
+                        palette_joint=np.arange(palette_joints if palette_joints is not None else J, dtype=np.int32) % J,
+                        coordinate_system=coordinate_system)
+    return skel

@@ -356,3 +356,52 @@ def test_wide_path_matches_strip_path(gpu_ctx, monkeypatch):
         grp.close()
         dmesh.close()
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_joint_hierarchy_on_gpu_panda(gpu_ctx):
+    """f1: p3cs_group_pose evaluates panda-walk4's 42-joint hierarchy on the GPU; the palette agrees with the
+    reference's CharacterJoint::_skinning_matrix (1e-5 of the matrix scale: compose_matrix goes through
+    sincosf), and pose -> animate reproduces the reference's animated vertices within the same bound."""
+    from panda3d_b200.flat import skeleton_from_case
+    case = load_case([p for p in golden_paths() if p.endswith("panda_walk4.p3cs")][0])
+    mesh, skel = mesh_from_case(case), skeleton_from_case(case)
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    dskel = _capi.Skeleton(gpu_ctx, skel)
+    frames = case["anim_frames"].astype(np.int32)
+    grp = _capi.Group(dmesh, len(frames))
+    try:
+        grp.pose(dskel, frames)
+        pal = grp.read_palettes()
+        ref = case["palette"]
+        scale = np.abs(ref).max(axis=(1, 2), keepdims=True)
+        assert (np.abs(pal - ref) / scale).max() <= REL_TOL
+        print("pose: max-abs palette error", float(np.abs(pal - ref).max()))
+        grp.animate()
+        out = grp.read_output(0)
+        for fi in range(len(frames)):
+            compare_outputs(mesh, [out[fi]], [case["expect0"][fi]], f"pose+animate frame {frames[fi]}")
+    finally:
+        grp.close()
+        dskel.close()
+        dmesh.close()
+
+
+def test_joint_hierarchy_crowd_vs_oracle(gpu_ctx):
+    """f1 at crowd scale: 300 instances x 128 joints, each instance on its own frame, against oracle.pose."""
+    sm = synth.make_mesh(2_000, 128, 400, seed=71, index_order="runs")
+    skel = synth.make_skeleton(128, 48, seed=72)
+    n = 300
+    frames = (np.arange(n) * 7 % 48).astype(np.int32)
+    dmesh = _capi.Mesh(gpu_ctx, sm.flat)
+    dskel = _capi.Skeleton(gpu_ctx, skel)
+    grp = _capi.Group(dmesh, n)
+    try:
+        grp.pose(dskel, frames)
+        pal = grp.read_palettes()
+        for i in (0, 1, 57, n - 1):
+            ref = oracle.pose(skel, int(frames[i]))[skel.palette_joint]
+            assert (np.abs(pal[i] - ref) / np.abs(ref).max()).max() <= REL_TOL
+    finally:
+        grp.close()
+        dskel.close()
+        dmesh.close()

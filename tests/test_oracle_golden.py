@@ -64,3 +64,16 @@ def test_golden_branch_coverage():
             case = load_case(p)
             got = {oracle.normal_xform(b)[0] for b in case["expect_blends"][0]}
             assert got == want[name], (name, got)
+
+
+def test_oracle_pose_matches_reference_skinning_matrices():
+    """"Next" row f1: the joint hierarchy.  oracle.pose (channel tables -> compose_matrix -> net transform
+    -> skinning matrix) reproduces bit for bit the CharacterJoint::_skinning_matrix values the reference
+    computed for panda-walk4 at every exported frame (the golden palette)."""
+    from panda3d_b200.flat import skeleton_from_case
+    case = load_case([p for p in golden_paths() if p.endswith("panda_walk4.p3cs")][0])
+    skel = skeleton_from_case(case)
+    assert skel.num_joints == 42 and len(skel.palette_joint) == 26     # SURVEY appendix: 42 <Joint>, 26 referenced
+    for fi, frame in enumerate(case["anim_frames"]):
+        skin = oracle.pose(skel, int(frame))
+        assert np.array_equal(skin[skel.palette_joint].view(np.uint32), case["palette"][fi].view(np.uint32))
