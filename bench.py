@@ -303,6 +303,37 @@ def run_gpu_arm(args):
             g, e = got.view(np.float32).astype(np.float64), expect[0].view(np.float32).astype(np.float64)
             check = {"instance": inst, "max_abs_err": float(np.abs(g - e).max()), "differing_bytes": int((got != expect[0]).sum())}
 
+        # ---------------- "next" row f1: joint hierarchy on the GPU -- the host sends one frame number per
+        # instance (40 KB) instead of the palettes (82 MB); pose + animate timed together on the device
+        joints = None
+        if not args.no_pose:
+            skel = synth.make_skeleton(T, 64, seed=4321)
+            dskel = _capi.Skeleton(ctx, skel)
+            frames_host = (np.arange(n_local, dtype=np.int32) * 7 + 3) % 64
+            for _ in range(3):
+                grp.pose(dskel, frames_host)
+                grp.animate()
+            barrier()
+            e0.record(stream)
+            for k in range(args.steps):
+                grp.pose(dskel, (frames_host + k) % 64)
+                grp.animate()
+            e1.record(stream)
+            barrier()
+            j_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+            e0.record(stream)
+            for k in range(args.steps):
+                grp.pose(dskel, (frames_host + k) % 64)
+            e1.record(stream)
+            barrier()
+            p_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+            joints = {"pose_plus_animate_ms_per_step": j_ms, "pose_only_ms_per_step": p_ms, "joints_per_step": int(n_local * T),
+                      "h2d_bytes_per_step": int(n_local * 4), "note": "p3cs_group_pose: channel tables -> compose_matrix -> "
+                      "net transforms -> skinning matrices on the GPU (one AnimControl, no frame blending)"}
+            pal_dev.copy_(pal_host, non_blocking=True)   # restore the palettes the checks below expect
+            stream.synchronize()
+            dskel.close()
+
         # ---------------- optional: NCCL gather of the finished arrays to the rendering GPU (rank 0)
         gather = None
         if dist is not None:
@@ -405,7 +436,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                     "ms_per_step": e2e_ms, "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps, "clocks": sampler.summary(), "check": check,
-            "gather": gather, "fused_gather": fused,
+            "gather": gather, "fused_gather": fused, "joints_on_gpu": joints,
         }
         print(json.dumps(line), flush=True)
     grp.close()
@@ -426,6 +457,7 @@ def main():
     ap.add_argument("--cpu-characters", type=int, default=4, help="characters per CPU worker process per step")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-pose", action="store_true", help="skip the joint-hierarchy-on-GPU measurement")
     ap.add_argument("--no-fused", action="store_true", help="skip the peer-memory fused skin+gather measurement (N>1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
