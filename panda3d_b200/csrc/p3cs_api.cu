@@ -914,7 +914,15 @@ extern "C" int p3cs_skeleton_create(p3cs_context ctx, const p3cs_skeleton_desc *
     return code;
   };
   if ((rc = upload_skel<int>(sk, d->parent, J, &s.parent)) != P3CS_OK) return bail(rc);
-  if ((rc = upload_skel<int>(sk, level.data(), J, &s.level)) != P3CS_OK) return bail(rc);
+  std::vector<int> order(std::max(J, 1), 0), begin(max_level + 2, 0);
+  for (int j = 0; j < J; ++j) begin[level[j] + 1]++;
+  for (int l = 0; l <= max_level; ++l) begin[l + 1] += begin[l];
+  {
+    std::vector<int> cursor(begin.begin(), begin.end() - 1);
+    for (int j = 0; j < J; ++j) order[cursor[level[j]]++] = j;
+  }
+  if ((rc = upload_skel<int>(sk, order.data(), J, &s.level_order)) != P3CS_OK) return bail(rc);
+  if ((rc = upload_skel<int>(sk, begin.data(), begin.size(), &s.level_begin)) != P3CS_OK) return bail(rc);
   if ((rc = upload_skel<int>(sk, d->has_channel, J, &s.has_channel)) != P3CS_OK) return bail(rc);
   if ((rc = upload_skel<int>(sk, d->table_length, (size_t)J * 12, &s.table_length)) != P3CS_OK) return bail(rc);
   if ((rc = upload_skel<int>(sk, d->table_offset, (size_t)J * 12, &s.table_offset)) != P3CS_OK) return bail(rc);

@@ -85,7 +85,8 @@ struct SkeletonDev {
   int coordinate_system;
   int max_level;
   const int *parent;          // -1: top-level joint
-  const int *level;           // depth in the joint tree (parents have smaller levels)
+  const int *level_order;     // joint indices sorted by depth in the tree
+  const int *level_begin;     // [max_level+2] ranges of level_order
   const int *has_channel;
   const int *table_length;    // [J][12]
   const int *table_offset;    // [J][12]

@@ -264,7 +264,7 @@ def make_skeleton(num_joints: int, num_frames: int, seed: int, *, palette_joints
     from .flat import FlatSkeleton
     rng = np.random.default_rng(seed)
     J = num_joints
-    parent = np.asarray([-1] + [int(rng.integers(max(0, j - 6), j)) for j in range(1, J)], np.int32)
+    parent = np.asarray([-1] + [int(rng.integers(max(0, j - 16), j)) for j in range(1, J)], np.int32)   # depth ~ J/8, like a humanoid rig
     tlen = np.zeros((J, 12), np.int32)
     toff = np.zeros((J, 12), np.int32)
     tables = []
