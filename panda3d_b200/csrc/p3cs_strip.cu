@@ -252,7 +252,7 @@ __device__ __forceinline__ void fast_column(float *cell, const float (&f)[22]) {
   cell[2] = r2;
 }
 
-template <int MODE, int kRowsPerThread, bool SELECT>
+template <int MODE, int kRowsPerThread, bool SELECT, bool MORPH>
 __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
     strip_kernel(MeshDev mesh, GroupDev grp, int first_instance, int groups_per_cta, int want_normal) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -421,6 +421,23 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
         const int row = t * kTileRows + trow;
         const bool skinned = local[rr] != 0xFFFF;
         if (FAST) {
+          if (MORPH && row < mesh.num_rows) {
+            // sparse morph deltas, added in place in the reference's order (3-component branch,
+            // geomVertexData.cxx:1531-1535); columns are independent, so walking the row's
+            // entries once is the same arithmetic as the reference's per-column passes
+            const int mb = __ldg(mesh.morph_row_offsets + row), me = __ldg(mesh.morph_row_offsets + row + 1);
+            uint8_t *rowp = tile + trow * stride0;
+            for (int e = mb; e < me; ++e) {
+              const uint32_t key = __ldg(mesh.morph_keys + e);
+              const float value = __ldg(sliders + (key & 0xffffu));
+              if (value == 0.0f) continue;  // `if (slider_value != 0.0f)`, :1483
+              const float4 d = __ldg(mesh.morph_deltas + e);
+              float *cell = reinterpret_cast<float *>(rowp + mesh.dyn[key >> 16].start);
+              cell[0] = cell[0] + d.x * value;
+              cell[1] = cell[1] + d.y * value;
+              cell[2] = cell[2] + d.z * value;
+            }
+          }
           if (skinned) {
             const float2 *p = reinterpret_cast<const float2 *>(recs + (size_t)local[rr] * kRecCompact);
             float f[22];
@@ -497,7 +514,7 @@ size_t strip_smem_bytes(const MeshDev &mesh) { return (size_t)strip_layout(mesh)
 // Which specialisation fits this mesh (see the header comment).
 static int pick_mode(const MeshDev &mesh) {
   if (mesh.full_records) return kGenericFull;
-  if (mesh.num_outputs != 1 || mesh.has_morphs || mesh.index_bytes == 0) return kGenericCompact;
+  if (mesh.num_outputs != 1 || mesh.index_bytes == 0) return kGenericCompact;
   for (int c = 0; c < mesh.num_dyn; ++c)
     if (mesh.dyn[c].num_values != 3) return kGenericCompact;
   const DynColumn *d = mesh.dyn;
@@ -508,22 +525,31 @@ static int pick_mode(const MeshDev &mesh) {
   return kGenericCompact;
 }
 
-template <int MODE, int R>
-static void launch_mode_r(const MeshDev &mesh, const GroupDev &grp, int first, dim3 grid, size_t smem, int gpc, int want_normal,
-                          cudaStream_t stream) {
+template <int MODE, int R, bool MORPH>
+static void launch_mode_rm(const MeshDev &mesh, const GroupDev &grp, int first, dim3 grid, size_t smem, int gpc, int want_normal,
+                           cudaStream_t stream) {
   if (grp.selection != nullptr) {
-    cudaFuncSetAttribute(strip_kernel<MODE, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    strip_kernel<MODE, R, true><<<grid, kStripThreads, smem, stream>>>(mesh, grp, first, gpc, want_normal);
+    cudaFuncSetAttribute(strip_kernel<MODE, R, true, MORPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    strip_kernel<MODE, R, true, MORPH><<<grid, kStripThreads, smem, stream>>>(mesh, grp, first, gpc, want_normal);
   } else {
     static thread_local int configured_device = -1;  // the attribute is sticky per function and device
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev != configured_device) {
-      cudaFuncSetAttribute(strip_kernel<MODE, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(strip_kernel<MODE, R, false, MORPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       configured_device = dev;
     }
-    strip_kernel<MODE, R, false><<<grid, kStripThreads, smem, stream>>>(mesh, grp, first, gpc, want_normal);
+    strip_kernel<MODE, R, false, MORPH><<<grid, kStripThreads, smem, stream>>>(mesh, grp, first, gpc, want_normal);
   }
+}
+
+// The specialised modes carry the morph loop only when the mesh has morphs (the generic modes
+// test MeshDev::has_morphs at run time).
+template <int MODE, int R>
+static void launch_mode_r(const MeshDev &mesh, const GroupDev &grp, int first, dim3 grid, size_t smem, int gpc, int want_normal,
+                          cudaStream_t stream) {
+  if (MODE >= kFastP && mesh.has_morphs) launch_mode_rm<MODE, R, (MODE >= kFastP)>(mesh, grp, first, grid, smem, gpc, want_normal, stream);
+  else launch_mode_rm<MODE, R, false>(mesh, grp, first, grid, smem, gpc, want_normal, stream);
 }
 
 template <int MODE>

@@ -70,6 +70,8 @@ def main():
                 specs = [(synth.config_c2("random").flat, 1000)]
             elif name == "c4":
                 specs, small = [(synth.config_c4().flat, 1)], True
+            elif name == "c4x":   # the morph mesh as a crowd of 200 faces (bandwidth-bound variant)
+                specs = [(synth.config_c4().flat, 200)]
             elif name == "c5":
                 specs = [(sm.flat, count) for sm, count in synth.config_c5_meshes()]
             elif name == "c5x":   # the same 4 character types, 100x the crowd
