@@ -522,6 +522,9 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
           memcpy(v, dbase + (size_t)r * dstride, (size_t)dn * 4);
           const int e = cursor[r]++;
           keys[e] = ((uint32_t)morph_dyn[mi] << 16) | (uint32_t)mo.slider;
+          // a delta whose 4th component is never read carries its key there (one load per entry
+          // in the specialised strip modes)
+          if (!(mo.base.num_values == 4 && !m.dyn[morph_dyn[mi]].homogeneous)) memcpy(&v[3], &keys[e], 4);
           deltas[e] = make_float4(v[0], v[1], v[2], v[3]);
         }
     }

@@ -341,6 +341,16 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
     const int row = t0 * kTileRows + rr * kStripThreads + tid;
     next_local[rr] = (has_index && row < mesh.num_rows) ? (int)__ldg(mesh.row_local + row) : 0xFFFF;
   }
+  int next_mb[kRowsPerThread], next_me[kRowsPerThread];  // the rows' morph entry ranges, prefetched the same way
+#pragma unroll
+  for (int rr = 0; rr < kRowsPerThread; ++rr) {
+    const int row = t0 * kTileRows + rr * kStripThreads + tid;
+    next_mb[rr] = next_me[rr] = 0;
+    if (MORPH && FAST && row < mesh.num_rows) {
+      next_mb[rr] = __ldg(mesh.morph_row_offsets + row);
+      next_me[rr] = __ldg(mesh.morph_row_offsets + row + 1);
+    }
+  }
   int rbeg = __ldg(mesh.group_rec_offsets + g0);
   int rend = __ldg(mesh.group_rec_offsets + g0 + 1);
   int gt1 = __ldg(mesh.group_tile_offsets + g0 + 1);
@@ -410,6 +420,20 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
             grp.selection[row] = local[rr] == 0xFFFF ? -1 : __ldg(mesh.group_rec_blend + cur_rbeg + local[rr]);
         }
       }
+      int mb[kRowsPerThread], me[kRowsPerThread];
+#pragma unroll
+      for (int rr = 0; rr < kRowsPerThread; ++rr) {
+        mb[rr] = next_mb[rr];
+        me[rr] = next_me[rr];
+        if (MORPH && FAST) {
+          const int nrow = (t + 1) * kTileRows + rr * kStripThreads + tid;
+          next_mb[rr] = next_me[rr] = 0;
+          if (t + 1 < t1 && nrow < mesh.num_rows) {
+            next_mb[rr] = __ldg(mesh.morph_row_offsets + nrow);
+            next_me[rr] = __ldg(mesh.morph_row_offsets + nrow + 1);
+          }
+        }
+      }
 
       mbar_wait(mbar0 + 8 * buf, ph);  // the tile's rows have landed
 
@@ -425,13 +449,12 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
             // sparse morph deltas, added in place in the reference's order (3-component branch,
             // geomVertexData.cxx:1531-1535); columns are independent, so walking the row's
             // entries once is the same arithmetic as the reference's per-column passes
-            const int mb = __ldg(mesh.morph_row_offsets + row), me = __ldg(mesh.morph_row_offsets + row + 1);
             uint8_t *rowp = tile + trow * stride0;
-            for (int e = mb; e < me; ++e) {
-              const uint32_t key = __ldg(mesh.morph_keys + e);
+            for (int e = mb[rr]; e < me[rr]; ++e) {
+              const float4 d = __ldg(mesh.morph_deltas + e);  // .w carries the key of a 3-component delta
+              const uint32_t key = __float_as_uint(d.w);
               const float value = __ldg(sliders + (key & 0xffffu));
               if (value == 0.0f) continue;  // `if (slider_value != 0.0f)`, :1483
-              const float4 d = __ldg(mesh.morph_deltas + e);
               float *cell = reinterpret_cast<float *>(rowp + mesh.dyn[key >> 16].start);
               cell[0] = cell[0] + d.x * value;
               cell[1] = cell[1] + d.y * value;
