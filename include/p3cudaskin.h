@@ -128,7 +128,7 @@ typedef struct p3cs_mesh_desc {
 
   /* Columns transformed by the blend matrices: GeomVertexFormat::get_point(i)
    * then get_vector(i) of the post-animated format (geomVertexData.cxx:1582,
-   * 1622).  contents is C_POINT, C_VECTOR or C_NORMAL; float32 x 3 or x 4. */
+   * 1622).  contents is C_POINT, C_VECTOR or C_NORMAL; float32 or float64, x 3 or x 4 (float64 takes the GeomVertexRewriter branches, :1782-1799, 1862-1879). */
   int32_t num_skin_columns;
   const p3cs_column_desc *skin_columns;
 

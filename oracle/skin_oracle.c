@@ -549,16 +549,35 @@ static int read_index(const uint8_t *p, int numeric_type) {
   }
 }
 
+/* GeomVertexReader::get_data3/4 and GeomVertexWriter::set_data3/4 on a float64 column with
+ * PN_stdfloat = float: components pass through float (geomVertexColumn.cxx:668-673, 1805-1811). */
+static void get_f64(const uint8_t *p, int n, float *v) {
+  int k;
+  for (k = 0; k < n; ++k) { double d; memcpy(&d, p + 8 * k, 8); v[k] = (float)d; }
+}
+static void set_f64(uint8_t *p, int n, const float *v) {
+  int k;
+  for (k = 0; k < n; ++k) { double d = (double)v[k]; memcpy(p + 8 * k, &d, 8); }
+}
+
 /* do_transform_point_column / do_transform_vector_column for one run
  * [begin,end) sharing one blend matrix (geomVertexData.cxx:1758-1880). */
 static void transform_run(const p3o_mesh *mesh, const p3o_column *col, uint8_t *out, int stride,
                           const float *mat, int begin, int end) {
   int nv = col->num_values, i;
+  int f64 = col->numeric_type == P3O_NT_FLOAT64;
   uint8_t *datat = out + col->start + (size_t)begin * stride;
   if (col->contents == P3O_C_POINT) {
     for (i = 0; i < end - begin; ++i) {
-      float *v = (float *)(datat + (size_t)i * stride);
-      if (nv == 3) xform_point3(v, mat); else xform_vec4(v, mat);
+      if (!f64) {
+        float *v = (float *)(datat + (size_t)i * stride);
+        if (nv == 3) xform_point3(v, mat); else xform_vec4(v, mat);
+      } else {  /* GeomVertexRewriter branches :1782-1799 */
+        float v[4];
+        get_f64(datat + (size_t)i * stride, nv, v);
+        if (nv == 3) xform_point3(v, mat); else xform_vec4(v, mat);
+        set_f64(datat + (size_t)i * stride, nv, v);
+      }
     }
   } else {
     float xform[16];
@@ -569,26 +588,27 @@ static void transform_run(const p3o_mesh *mesh, const p3o_column *col, uint8_t *
       memcpy(xform, mat, sizeof(xform));
     }
     for (i = 0; i < end - begin; ++i) {
-      float *v = (float *)(datat + (size_t)i * stride);
-      if (normalize) {          /* table_xform_normal3f, also for 4-component columns */
+      if (!f64) {
+        float *v = (float *)(datat + (size_t)i * stride);
+        if (normalize) {          /* table_xform_normal3f, also for 4-component columns */
+          xform_vec3(v, xform);
+          normalize3(v);
+        } else if (nv == 3) {
+          xform_vec3(v, xform);
+        } else {
+          xform_vec4(v, xform);
+        }
+      } else {  /* :1862-1879: get_data3 / set_data3; on 4 values Packer::set_data3f stores w = 0
+                 * (geomVertexColumn.cxx:1848-1850) */
+        float v[4];
+        get_f64(datat + (size_t)i * stride, 3, v);
         xform_vec3(v, xform);
-        normalize3(v);
-      } else if (nv == 3) {
-        xform_vec3(v, xform);
-      } else {
-        xform_vec4(v, xform);
+        if (normalize) normalize3(v);
+        v[3] = 0.0f;
+        set_f64(datat + (size_t)i * stride, nv, v);
       }
     }
   }
-}
-
-/* float32 column read in the manner of GeomVertexReader::get_data3 / get_data4
- * for plain float columns: missing components read as 0 (w as 1 for get_data4). */
-static void get3(const uint8_t *p, int nv, float *v) {
-  const float *f = (const float *)p;
-  v[0] = nv > 0 ? f[0] : 0.0f;
-  v[1] = nv > 1 ? f[1] : 0.0f;
-  v[2] = nv > 2 ? f[2] : 0.0f;
 }
 
 static int output_index(const p3o_mesh *mesh, int array) {
@@ -605,7 +625,7 @@ int p3o_animate(const p3o_mesh *mesh, const float *palette, const float *sliders
   /* validate: only the float32 fast paths are restated */
   for (ci = 0; ci < mesh->num_skin_columns; ++ci) {
     const p3o_column *c = &mesh->skin_columns[ci];
-    if (c->numeric_type != P3O_NT_FLOAT32 || (c->num_values != 3 && c->num_values != 4)) return -1;
+    if ((c->numeric_type != P3O_NT_FLOAT32 && c->numeric_type != P3O_NT_FLOAT64) || (c->num_values != 3 && c->num_values != 4)) return -1;
     if (output_index(mesh, c->array) < 0) return -1;
   }
 
@@ -627,7 +647,8 @@ int p3o_animate(const p3o_mesh *mesh, const float *palette, const float *sliders
     int bstride, dstride;
     uint8_t *bdata;
     const uint8_t *ddata;
-    if (bo < 0 || m->base.numeric_type != P3O_NT_FLOAT32 || m->delta.numeric_type != P3O_NT_FLOAT32) return -1;
+    int bf64 = m->base.numeric_type == P3O_NT_FLOAT64, df64 = m->delta.numeric_type == P3O_NT_FLOAT64;
+    if (bo < 0 || (!bf64 && m->base.numeric_type != P3O_NT_FLOAT32) || (!df64 && m->delta.numeric_type != P3O_NT_FLOAT32)) return -1;
     if (slider_value == 0.0f) continue;
     bstride = mesh->array_stride[m->base.array];
     dstride = mesh->array_stride[m->delta.array];
@@ -636,34 +657,32 @@ int p3o_animate(const p3o_mesh *mesh, const float *palette, const float *sliders
     for (i = 0; i < m->num_row_ranges; ++i) {
       int begin = m->row_ranges[2 * i], end = m->row_ranges[2 * i + 1];
       for (j = begin; j < end; ++j) {
-        float *vertex = (float *)(bdata + (size_t)j * bstride);
+        uint8_t *vp = bdata + (size_t)j * bstride;
         const uint8_t *dp = ddata + (size_t)j * dstride;
-        float d[4];
-        if (m->base.num_values == 4) {
+        float vertex[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        int bn = m->base.num_values, dn = m->delta.num_values, k;
+        /* the base / delta values as get_data3/4 return them; default Packer::get_data3f/4f
+         * pad missing components with 0 (geomVertexColumn.cxx:608-737) */
+        if (bf64) get_f64(vp, bn, vertex); else memcpy(vertex, vp, (size_t)bn * 4);
+        if (df64) get_f64(dp, dn < 4 ? dn : 4, d); else memcpy(d, dp, (size_t)(dn < 4 ? dn : 4) * 4);
+        if (bn == 4) {
           int homogeneous = (m->base.contents == P3O_C_POINT || m->base.contents == P3O_C_TEXCOORD);
           if (homogeneous) {
-            /* :1499-1507  d *= slider_value * vertex[3] */
+            /* :1499-1507  d(3) *= slider_value * vertex[3] */
             float s = slider_value * vertex[3];
-            get3(dp, m->delta.num_values, d);
             d[0] *= s; d[1] *= s; d[2] *= s;
             vertex[0] = vertex[0] + d[0];
             vertex[1] = vertex[1] + d[1];
             vertex[2] = vertex[2] + d[2];
           } else {
             /* :1516-1520  vertex + d * slider_value (4 components) */
-            const float *f = (const float *)dp;
-            int k;
-            /* default Packer::get_data4f pads missing components with 0
-             * (geomVertexColumn.cxx:718-737) */
-            for (k = 0; k < 4; ++k) d[k] = k < m->delta.num_values ? f[k] : 0.0f;
             for (k = 0; k < 4; ++k) vertex[k] = vertex[k] + d[k] * slider_value;
           }
         } else {
           /* :1531-1535  vertex + d * slider_value (<= 3 components) */
-          int k, nv = m->base.num_values;
-          get3(dp, m->delta.num_values, d);
-          for (k = 0; k < nv && k < 3; ++k) vertex[k] = vertex[k] + d[k] * slider_value;
+          for (k = 0; k < bn && k < 3; ++k) vertex[k] = vertex[k] + d[k] * slider_value;
         }
+        if (bf64) set_f64(vp, bn, vertex); else memcpy(vp, vertex, (size_t)bn * 4);
       }
     }
   }

@@ -26,6 +26,7 @@ extern "C" {
 #define P3O_NT_UINT16 1
 #define P3O_NT_UINT32 2
 #define P3O_NT_FLOAT32 5
+#define P3O_NT_FLOAT64 6
 #define P3O_C_POINT 1
 #define P3O_C_VECTOR 3
 #define P3O_C_TEXCOORD 4

@@ -304,8 +304,8 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
     const p3cs_column_desc &c = d->skin_columns[i];
     if ((rc = check_column(d, c, "skin column")) != P3CS_OK) return bail(rc);
     if (out_of_array[c.array] < 0) return bail(fail(P3CS_ERR_INVALID, "skin column %d lives in a non-output array", i));
-    if (c.numeric_type != P3CS_NT_FLOAT32 || (c.num_values != 3 && c.num_values != 4))
-      return bail(fail(P3CS_ERR_UNSUPPORTED, "skin column %d: only float32 x 3 / x 4 columns are supported (got type %d x %d)", i, c.numeric_type, c.num_values));
+    if ((c.numeric_type != P3CS_NT_FLOAT32 && c.numeric_type != P3CS_NT_FLOAT64) || (c.num_values != 3 && c.num_values != 4))
+      return bail(fail(P3CS_ERR_UNSUPPORTED, "skin column %d: only float32 / float64 x 3 / x 4 columns are supported (got type %d x %d)", i, c.numeric_type, c.num_values));
     if (c.start % 4 != 0) return bail(fail(P3CS_ERR_UNSUPPORTED, "skin column %d: start %d not 4-byte aligned", i, c.start));
     int skin = c.contents == P3CS_C_POINT ? 1 : c.contents == P3CS_C_VECTOR ? 2 : c.contents == P3CS_C_NORMAL ? 3 : 0;
     if (skin == 0) return bail(fail(P3CS_ERR_INVALID, "skin column %d: contents %d is not point/vector/normal", i, c.contents));
@@ -316,6 +316,7 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
     dc.num_values = (int8_t)c.num_values;
     dc.skin = (int8_t)skin;
     dc.homogeneous = 0;
+    dc.f64 = c.numeric_type == P3CS_NT_FLOAT64 ? 1 : 0;
     if (c.num_values == 4) m.full_records = 1;
   }
 
@@ -489,9 +490,10 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
       if ((rc = check_column(d, mo.delta, "morph delta column")) != P3CS_OK) return bail(rc);
       if ((rc = check_ranges(mo.row_ranges, mo.num_row_ranges, N, "slider rows")) != P3CS_OK) return bail(rc);
       if (out_of_array[mo.base.array] < 0) return bail(fail(P3CS_ERR_INVALID, "morph %d: base column in a non-output array", mi));
-      if (mo.base.numeric_type != P3CS_NT_FLOAT32 || mo.delta.numeric_type != P3CS_NT_FLOAT32 || mo.base.num_values > 4 ||
+      auto is_float = [](int nt) { return nt == P3CS_NT_FLOAT32 || nt == P3CS_NT_FLOAT64; };
+      if (!is_float(mo.base.numeric_type) || !is_float(mo.delta.numeric_type) || mo.base.num_values > 4 ||
           mo.base.start % 4 != 0 || mo.delta.start % 4 != 0)
-        return bail(fail(P3CS_ERR_UNSUPPORTED, "morph %d: only 4-byte aligned float32 base/delta columns are supported", mi));
+        return bail(fail(P3CS_ERR_UNSUPPORTED, "morph %d: only 4-byte aligned float32 / float64 base and delta columns are supported", mi));
       int c = find_dyn(out_of_array[mo.base.array], mo.base.start);
       if (c < 0) {
         if (m.num_dyn >= kMaxDynColumns) return bail(fail(P3CS_ERR_UNSUPPORTED, "more than %d animated columns", kMaxDynColumns));
@@ -500,6 +502,7 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
         m.dyn[c].start = (int16_t)mo.base.start;
         m.dyn[c].num_values = (int8_t)mo.base.num_values;
         m.dyn[c].skin = 0;
+        m.dyn[c].f64 = mo.base.numeric_type == P3CS_NT_FLOAT64 ? 1 : 0;
       }
       m.dyn[c].homogeneous = (mo.base.num_values == 4 && (mo.base.contents == P3CS_C_POINT || mo.base.contents == P3CS_C_TEXCOORD)) ? 1 : 0;
       morph_dyn[mi] = c;
@@ -519,7 +522,13 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
       for (int i = 0; i < mo.num_row_ranges; ++i)
         for (int r = mo.row_ranges[2 * i]; r < mo.row_ranges[2 * i + 1]; ++r) {
           float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // Packer::get_data3f/4f pad with 0 (geomVertexColumn.cxx:718-737)
-          memcpy(v, dbase + (size_t)r * dstride, (size_t)dn * 4);
+          if (mo.delta.numeric_type == P3CS_NT_FLOAT64) {  // read as float, like GeomVertexReader::get_data3/4
+            double dv[4];
+            memcpy(dv, dbase + (size_t)r * dstride, (size_t)dn * 8);
+            for (int k = 0; k < dn; ++k) v[k] = (float)dv[k];
+          } else {
+            memcpy(v, dbase + (size_t)r * dstride, (size_t)dn * 4);
+          }
           const int e = cursor[r]++;
           keys[e] = ((uint32_t)morph_dyn[mi] << 16) | (uint32_t)mo.slider;
           // a delta whose 4th component is never read carries its key there (one load per entry

@@ -154,15 +154,27 @@ __device__ __forceinline__ void xform_vec4(float *v, const float m[4][4]) {
 
 // One dynamic column of one row, in shared memory: morph deltas first
 // (geomVertexData.cxx:1462-1543), then the blend transform (:1758-1880).
+// float64 columns take the reference's GeomVertexRewriter branches (:1782-1799, :1862-1879): components
+// are read as float (get_data3/4 with PN_stdfloat = float), 3-component vector math even on 4-component
+// columns, and only the components set_data3/4 touches are written back.
 template <bool FULL>
 __device__ __forceinline__ void animate_column(const MeshDev &mesh, const DynColumn &col, int dyn_index, float *cell,
                                                int morph_beg, int morph_end, const float *sliders, bool skinned,
                                                const Record<FULL> &rec) {
   const int nv = col.num_values;
+  const bool f64 = col.f64 != 0;
   float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (!f64) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (k < nv) v[k] = cell[k];
+    for (int k = 0; k < 4; ++k)
+      if (k < nv) v[k] = cell[k];
+  } else {  // the row stride is only 4-byte aligned: assemble the doubles from 32-bit halves
+    const int *w = reinterpret_cast<const int *>(cell);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < nv) v[k] = (float)__hiloint2double(w[2 * k + 1], w[2 * k]);
+  }
+  bool dirty3 = false, dirty4 = false;  // what set_data3 / set_data4 rewrote (matters for float64 only)
 
   for (int e = morph_beg; e < morph_end; ++e) {
     const uint32_t key = __ldg(mesh.morph_keys + e);
@@ -170,7 +182,9 @@ __device__ __forceinline__ void animate_column(const MeshDev &mesh, const DynCol
     const float value = __ldg(sliders + (key & 0xffffu));
     if (value == 0.0f) continue;  // `if (slider_value != 0.0f)`, :1483
     const float4 d = __ldg(mesh.morph_deltas + e);
+    dirty3 = true;
     if (nv == 4) {
+      dirty4 = true;
       if (col.homogeneous) {  // :1499-1507
         const float s = value * v[3];
         v[0] = v[0] + d.x * s;
@@ -190,26 +204,42 @@ __device__ __forceinline__ void animate_column(const MeshDev &mesh, const DynCol
   }
 
   if (skinned && col.skin != 0) {
+    dirty3 = true;
     if (col.skin == 1) {  // C_point
       if (nv == 3) xform_point3(v, rec.m);
-      else if (FULL) xform_vec4(v, rec.m);
+      else if (FULL) { xform_vec4(v, rec.m); dirty4 = true; }
     } else if (col.skin == 2) {  // C_vector: xform = mat
-      if (nv == 3) xform_vec3(v, rec.m);
+      if (nv == 3 || f64) xform_vec3(v, rec.m);
       else if (FULL) xform_vec4(v, rec.m);
     } else {  // C_normal
       if (rec.normalize) {  // table_xform_normal3f, also on 4-component columns (:1854-1855)
         xform_vec3(v, rec.x);
         normalize3(v[0], v[1], v[2]);
-      } else if (nv == 3) {
+      } else if (nv == 3 || f64) {
         xform_vec3(v, rec.x);
       } else if (FULL) {
         xform_vec4(v, rec.x);
       }
     }
+    if (f64 && nv == 4 && col.skin != 1) {  // Packer::set_data3f on 4 values stores w = 0 (geomVertexColumn.cxx:1848-1850)
+      v[3] = 0.0f;
+      dirty4 = true;
+    }
   }
+  if (!f64) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (k < nv) cell[k] = v[k];
+    for (int k = 0; k < 4; ++k)
+      if (k < nv) cell[k] = v[k];
+  } else {
+    int *w = reinterpret_cast<int *>(cell);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < nv && (k < 3 ? dirty3 : dirty4)) {
+        const double dv = (double)v[k];
+        w[2 * k] = __double2loint(dv);
+        w[2 * k + 1] = __double2hiint(dv);
+      }
+  }
 }
 
 }  // namespace p3cs

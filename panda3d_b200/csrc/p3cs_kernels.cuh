@@ -22,7 +22,7 @@ struct DynColumn {
   int8_t num_values;   // 1..4
   int8_t skin;         // 0 none, 1 point, 2 vector, 3 normal
   int8_t homogeneous;  // morph: scale deltas by w (C_point / C_texcoord with 4 values)
-  int8_t pad;
+  int8_t f64;          // NT_float64 components: read/written through float like GeomVertexRewriter::get_data3/set_data3
 };
 
 struct MeshDev {

@@ -128,9 +128,13 @@ def make_mesh(num_rows: int, num_transforms: int, num_blends: int, *, seed: int 
               rows: Optional[Sequence[Tuple[int, int]]] = None,
               num_sliders: int = 0, morph_columns: Sequence[str] = ("vertex",),
               slider_band: float = 0.04, coordinate_system: int = F.CS_zup_right,
-              name: str = "synthetic") -> SynthMesh:
+              float64: bool = False, name: str = "synthetic") -> SynthMesh:
+    """`float64`: the animated and morph-delta columns are NT_float64 (a `vertices-float64` style
+    format): the reference then takes its GeomVertexRewriter branches (geomVertexData.cxx:1782-1799)."""
     rng = np.random.default_rng(seed)
     nv = 4 if align16 else 3
+    fnt = F.NT_float64 if float64 else F.NT_float32
+    fb = 8 if float64 else 4
     cols: List[Tuple[str, Column]] = []
     start = 0
 
@@ -142,20 +146,27 @@ def make_mesh(num_rows: int, num_transforms: int, num_blends: int, *, seed: int 
         start += n * F.NUMERIC_BYTES[nt]
         return c
 
-    al = 16 if align16 else 4
-    c_vertex = add("vertex", nv, F.C_point, align=al)
-    c_normal = add("normal", nv, F.C_normal, align=al)
+    al = 16 if align16 else fb
+    c_vertex = add("vertex", nv, F.C_point, nt=fnt, align=al)
+    c_normal = add("normal", nv, F.C_normal, nt=fnt, align=al)
     if texcoord:
         add("texcoord", 2, F.C_texcoord)
     c_tan = c_bin = None
     if tbn:
-        c_tan = add("tangent", nv, F.C_vector, align=al)
-        c_bin = add("binormal", nv, F.C_vector, align=al)
+        c_tan = add("tangent", nv, F.C_vector, nt=fnt, align=al)
+        c_bin = add("binormal", nv, F.C_vector, nt=fnt, align=al)
     stride0 = (start + al - 1) // al * al
     arr0 = np.zeros((num_rows, stride0), np.uint8)
     f0 = arr0.view(np.float32)
 
     def put(col: Column, data: np.ndarray, w: float):
+        if float64:   # doubles that are NOT float-representable, so float round trips would show
+            vals = np.zeros((num_rows, col.num_values), np.float64)
+            vals[:, :3] = data.astype(np.float64) * (1.0 + 1e-9)
+            if col.num_values == 4:
+                vals[:, 3] = w * (1.0 + 1e-9)
+            arr0[:, col.start:col.start + 8 * col.num_values] = vals.view(np.uint8)
+            return
         o = col.start // 4
         f0[:, o:o + 3] = data
         if col.num_values == 4:
@@ -184,8 +195,8 @@ def make_mesh(num_rows: int, num_transforms: int, num_blends: int, *, seed: int 
         b0 = min(num_rows - 1, s * num_rows // max(1, num_sliders))
         slider_rows.append(np.asarray([[b0, min(num_rows, b0 + band)]], np.int32))
         for base in morph_columns:
-            morph_cols.append((s, base, add(f"{base}.morph.{sname}", 3, F.C_morph_delta, array=1)))
-    stride1 = max(ib, (start + 3) // 4 * 4) if morph_cols else ib
+            morph_cols.append((s, base, add(f"{base}.morph.{sname}", 3, F.C_morph_delta, array=1, nt=fnt, align=fb)))
+    stride1 = max(ib, (start + fb - 1) // fb * fb) if morph_cols else ib
     arr1 = np.zeros((num_rows, stride1), np.uint8)
 
     if index_order == "sorted":
@@ -206,7 +217,10 @@ def make_mesh(num_rows: int, num_transforms: int, num_blends: int, *, seed: int 
         d = np.zeros((num_rows, 3), np.float32)
         b0, b1 = int(r[0, 0]), int(r[0, 1])
         d[b0:b1] = rng.uniform(-0.05, 0.05, (b1 - b0, 3)).astype(np.float32)
-        arr1[:, dcol.start:dcol.start + 12] = d.view(np.uint8)
+        if float64:
+            arr1[:, dcol.start:dcol.start + 24] = (d.astype(np.float64) * (1.0 + 1e-9)).view(np.uint8)
+        else:
+            arr1[:, dcol.start:dcol.start + 12] = d.view(np.uint8)
         morphs.append(Morph(s, base_by_name[base], dcol, r))
     # the reference iterates morph column outer, slider inner; the harness re-exports its own
     # order, which only matters when two morphs hit the same base value of one row

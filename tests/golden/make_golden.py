@@ -43,6 +43,11 @@ def cases():
     yield "rows_u32", mk(900, 12, 100, seed=6, rows=[(10, 300), (450, 451), (600, 899)], index_type="u32"), P(12, 2, 15), None
     yield "u8_align16_morph", mk(300, 12, 100, seed=7, index_type="u8", align16=True, num_sliders=3, slider_band=0.5), \
         P(12, 2, 16), S(3, 2, 17)
+    # NT_float64 columns: the reference's GeomVertexRewriter branches (geomVertexData.cxx:1782-1799, 1862-1879)
+    yield "f64", mk(300, 12, 60, seed=71, float64=True, tbn=True, index_order="runs"), P(12, 2, 72), None
+    yield "f64_uniform_scale", mk(200, 8, 8, seed=73, float64=True, weights_per_blend=1), P(8, 1, 74, scale=0.8), None
+    yield "f64_align16_morph", mk(300, 12, 60, seed=75, float64=True, align16=True, tbn=True, num_sliders=4, slider_band=0.4,
+                                  morph_columns=("vertex", "normal"), rows=[(5, 250)]), P(12, 2, 76), S(4, 2, 77)
     for cs, csname in ((2, "yup_right"), (3, "zup_left"), (4, "yup_left")):
         yield "cs_" + csname, mk(300, 8, 8, seed=8, weights_per_blend=1, coordinate_system=cs), P(8, 1, 18, scale=0.5), None
 

@@ -21,15 +21,16 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-5  # north_star: float32 positions/normals agree within 1e-5 relative
 
 
-def dynamic_float_mask(mesh):
-    """Byte mask per output array of the float columns the path may modify."""
+def dynamic_float_mask(mesh, numeric_type=None):
+    """Byte mask per output array of the float columns the path may modify (all of them, or those of one numeric type)."""
+    from panda3d_b200.flat import NUMERIC_BYTES
     masks = []
     for a in mesh.output_arrays:
         m = np.zeros(mesh.strides[a], bool)
         cols = list(mesh.skin_columns) + [mo.base for mo in mesh.morphs]
         for c in cols:
-            if c.array == a:
-                m[c.start:c.start + 4 * c.num_values] = True
+            if c.array == a and (numeric_type is None or c.numeric_type == numeric_type):
+                m[c.start:c.start + NUMERIC_BYTES[c.numeric_type] * c.num_values] = True
         masks.append(m)
     return masks
 
@@ -37,23 +38,28 @@ def dynamic_float_mask(mesh):
 def compare_outputs(mesh, got, expect, what=""):
     """Static bytes identical; dynamic floats within REL_TOL (relative to the vector magnitude
     scale, floor 1e-30).  Returns (max_abs_error, number_of_differing_bytes)."""
+    from panda3d_b200.flat import NT_float32, NT_float64
     max_abs, nbytes = 0.0, 0
-    for o, (g, e, mask) in enumerate(zip(got, expect, dynamic_float_mask(mesh))):
+    all_masks = dynamic_float_mask(mesh)
+    typed = [(np.float32, dynamic_float_mask(mesh, NT_float32)), (np.float64, dynamic_float_mask(mesh, NT_float64))]
+    for o, (g, e, mask) in enumerate(zip(got, expect, all_masks)):
         g = np.asarray(g).reshape(mesh.num_rows, -1)
         e = np.asarray(e).reshape(mesh.num_rows, -1)
         assert g.shape == e.shape
         assert np.array_equal(g[:, ~mask], e[:, ~mask]), f"{what}: static bytes of output {o} differ"
         nbytes += int((g != e).sum())
-        gf = np.ascontiguousarray(g[:, mask]).view(np.float32).astype(np.float64)
-        ef = np.ascontiguousarray(e[:, mask]).view(np.float32).astype(np.float64)
-        if gf.size:
-            err = np.abs(gf - ef)
-            max_abs = max(max_abs, float(err.max()))
-            scale = np.maximum(np.abs(ef), 1e-30)
-            # per component class: relative to the component, with the row's vector magnitude as floor
-            row_scale = np.maximum(scale, np.abs(ef).max(axis=1, keepdims=True))
-            rel = (err / row_scale).max()
-            assert rel <= REL_TOL, f"{what}: output {o} relative error {rel:.3e} > {REL_TOL}"
+        for dt, masks in typed:
+            tm = masks[o]
+            gf = np.ascontiguousarray(g[:, tm]).view(dt).astype(np.float64)
+            ef = np.ascontiguousarray(e[:, tm]).view(dt).astype(np.float64)
+            if gf.size:
+                err = np.abs(gf - ef)
+                max_abs = max(max_abs, float(err.max()))
+                scale = np.maximum(np.abs(ef), 1e-30)
+                # per component class: relative to the component, with the row's vector magnitude as floor
+                row_scale = np.maximum(scale, np.abs(ef).max(axis=1, keepdims=True))
+                rel = (err / row_scale).max()
+                assert rel <= REL_TOL, f"{what}: output {o} relative error {rel:.3e} > {REL_TOL}"
     return max_abs, nbytes
 
 
@@ -107,6 +113,10 @@ SYNTH_CASES = {
     "u32_index": dict(num_rows=70_001, num_transforms=32, num_blends=66_000, index_type="u32"),
     "one_row": dict(num_rows=1, num_transforms=4, num_blends=1),
     "align16": dict(num_rows=4_099, num_transforms=32, num_blends=700, align16=True, tbn=True),
+    "float64_columns": dict(num_rows=6_001, num_transforms=32, num_blends=900, float64=True, tbn=True, index_order="runs",
+                            num_sliders=6, slider_band=0.2, morph_columns=("vertex", "normal")),
+    "float64_align16": dict(num_rows=3_001, num_transforms=16, num_blends=500, float64=True, align16=True,
+                            rows=[(3, 2900)], num_sliders=2, slider_band=0.6),
 }
 
 
@@ -195,7 +205,7 @@ def test_unsupported_and_invalid_inputs_fail_loudly(gpu_ctx):
     sm = synth.make_mesh(100, 4, 8, seed=1)
     mesh = sm.flat
     bad = F.FlatMesh(**{**mesh.__dict__})
-    bad.skin_columns = [F.Column(0, 0, 3, F.NT_float64, F.C_point)]
+    bad.skin_columns = [F.Column(0, 0, 3, F.NT_int16, F.C_point)]
     with pytest.raises(_capi.P3csError) as e:
         _capi.Mesh(gpu_ctx, bad)
     assert e.value.code in (_capi.P3CS_ERR_UNSUPPORTED, _capi.P3CS_ERR_INVALID)
