@@ -334,6 +334,28 @@ def run_gpu_arm(args):
             stream.synchronize()
             dskel.close()
 
+        # ---------------- "next" row f4: animated tight bounds reduced by the same kernel
+        bounds = None
+        if not args.no_pose:
+            grp.enable_bounds()
+            for _ in range(3):
+                grp.animate()
+            barrier()
+            e0.record(stream)
+            for _ in range(args.steps):
+                grp.animate()
+            e1.record(stream)
+            barrier()
+            b_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+            b = grp.read_bounds(n_local // 2, 1)[0]
+            grp.read_output_ptr(0, n_local // 2, 1, out_host.data_ptr())
+            ctx.sync()
+            v = out_host[0].numpy().reshape(rows, stride)[:, :12].copy().view(np.float32)
+            ok = bool(np.array_equal(b[:3], v.min(axis=0)) and np.array_equal(b[3:6], v.max(axis=0)))
+            bounds = {"animate_with_bounds_ms_per_step": b_ms, "launches_per_step": int(grp.timings().launches), "exact": ok,
+                      "note": "p3cs_group_enable_bounds: min/max/|v|^2max of the animated vertex column per instance, fused"}
+            grp.enable_bounds(enable=False)
+
         # ---------------- optional: NCCL gather of the finished arrays to the rendering GPU (rank 0)
         gather = None
         if dist is not None:
@@ -436,7 +458,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                     "ms_per_step": e2e_ms, "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps, "clocks": sampler.summary(), "check": check,
-            "gather": gather, "fused_gather": fused, "joints_on_gpu": joints,
+            "gather": gather, "fused_gather": fused, "joints_on_gpu": joints, "tight_bounds": bounds,
         }
         print(json.dumps(line), flush=True)
     grp.close()

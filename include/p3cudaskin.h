@@ -329,6 +329,19 @@ P3CS_EXPORT int p3cs_group_pose(p3cs_group group, p3cs_skeleton skeleton, int fi
 /* Device -> host read-back of `count` palettes (count * T * 16 floats); parity hook. */
 P3CS_EXPORT int p3cs_group_read_palettes(p3cs_group group, int first, int count, float *host_dst);
 
+/* ---- "next" row f4: animated tight bounds ------------------
+ * Replaces the CPU walk over the animated vertices behind Character::calc_tight_bounds
+ * (char/character.cxx:218-238 -> GeomNode / Geom::calc_tight_bounds ->
+ * GeomPrimitive::calc_tight_bounds, gobj/geomPrimitive.cxx:1646-1830, the non-indexed branch without
+ * matrix): while a group is animated, the kernel also reduces min / max of `vertex_column` (a float32 x 3
+ * column of an output array, normally InternalName::get_vertex()) and max length_squared() over ALL rows of
+ * every instance.  NaN components never win a comparison, as with std::min/max there.
+ * p3cs_group_enable_bounds(group, NULL) switches it off again. */
+P3CS_EXPORT int p3cs_group_enable_bounds(p3cs_group group, const p3cs_column_desc *vertex_column);
+/* count x 8 floats: min x y z, max x y z, sq_center_dist (max |v|^2), found_any (1.0 / 0.0); of the
+ * last p3cs_group_animate.  Synchronous. */
+P3CS_EXPORT int p3cs_group_read_bounds(p3cs_group group, int first, int count, float *host_dst);
+
 /* ---- plugin table (load_dso + dlsym("p3cs_get_api")) -------------------- */
 
 typedef struct p3cs_api {

@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = [
     "p3cs_group_animate", "p3cs_group_read_output", "p3cs_group_read_selection", "p3cs_group_read_blends",
     "p3cs_group_set_profiling", "p3cs_group_last_timings", "p3cs_animate_vertices", "p3cs_get_api",
     "p3cs_skeleton_create", "p3cs_skeleton_destroy", "p3cs_group_pose", "p3cs_group_read_palettes",
+    "p3cs_group_enable_bounds", "p3cs_group_read_bounds",
 ]
 
 
@@ -136,6 +137,8 @@ def lib():
         L.p3cs_skeleton_destroy.argtypes = [C.c_void_p]
         L.p3cs_group_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.p3cs_group_read_palettes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.p3cs_group_enable_bounds.argtypes = [C.c_void_p, C.POINTER(_ColumnDesc)]
+        L.p3cs_group_read_bounds.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -344,6 +347,23 @@ class Group:
         count = self.n - first if count is None else count
         out = np.empty((count, self.mesh.flat.num_transforms, 16), np.float32)
         _check(lib().p3cs_group_read_palettes(self.handle, first, count, out.ctypes.data))
+        return out
+
+    # ---- "next" row f4: animated tight bounds, reduced by the same kernel
+    def enable_bounds(self, vertex_column=None, enable: bool = True) -> None:
+        """`vertex_column`: a flat.Column (default: the first animated C_point column)."""
+        if not enable:
+            _check(lib().p3cs_group_enable_bounds(self.handle, None))
+            return
+        col = vertex_column if vertex_column is not None else self.mesh.flat.skin_columns[0]
+        desc = _ColumnDesc(*col.as_tuple())
+        _check(lib().p3cs_group_enable_bounds(self.handle, C.byref(desc)))
+
+    def read_bounds(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """[count, 8]: min xyz, max xyz, max |v|^2, found_any -- of the last animate()."""
+        count = self.n - first if count is None else count
+        out = np.empty((count, 8), np.float32)
+        _check(lib().p3cs_group_read_bounds(self.handle, first, count, out.ctypes.data))
         return out
 
     # ---- the hot path

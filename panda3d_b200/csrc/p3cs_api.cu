@@ -51,6 +51,7 @@ struct p3cs_mesh_s {
   MeshDev dev{};
   std::vector<void *> allocations;
   bool use_strip = true;  // fused strip kernel (p3cs_strip.cu); false: blend + skin kernels
+  std::vector<int> out_of_array;  // source array -> output index (-1: not an output)
 };
 
 struct p3cs_group_s {
@@ -63,6 +64,7 @@ struct p3cs_group_s {
   std::vector<cudaEvent_t> prof;  // event pairs per launch when profiling
   std::vector<int> prof_kind;     // 0 blend, 1 skin, per pair
   bool profiling = false;
+  float *bounds_buf = nullptr;  // [n][8] animated tight bounds (p3cs_group_enable_bounds)
   int *frames_dev = nullptr;  // per-instance animation frames of the last p3cs_group_pose
   int frames_capacity = 0;
   p3cs_timings last{};
@@ -567,6 +569,7 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
   // uploads read from host vectors that die at scope exit: finish them now
   cudaError_t err = cudaStreamSynchronize(ctx->stream);
   if (err != cudaSuccess) return bail(fail(P3CS_ERR_CUDA, "mesh upload failed: %s", cudaGetErrorString(err)));
+  mesh->out_of_array = out_of_array;
   *out = mesh;
   return P3CS_OK;
 }
@@ -715,7 +718,12 @@ static int animate_range(p3cs_group grp, int first, int count, bool timed) {
       if ((rc = prof_event(grp, pe++, &e0)) != P3CS_OK || (rc = prof_event(grp, pe++, &e1)) != P3CS_OK) return rc;
       CUDA_TRY(cudaEventRecord(e0, s));
     }
-    nskin = launches = launch_strip(m, grp->dev, first, count, grp->mesh->ctx->sm_count, s);
+    if (grp->dev.bounds != nullptr && strip_ctas_per_instance(m, count, grp->mesh->ctx->sm_count) != 1) {
+      launch_bounds_init(grp->dev, first, count, s);  // several CTAs per instance merge with atomics
+      ++launches;
+    }
+    nskin = launch_strip(m, grp->dev, first, count, grp->mesh->ctx->sm_count, s);
+    launches += nskin;
     if (prof) {
       CUDA_TRY(cudaEventRecord(e1, s));
       grp->prof_kind.push_back(1);
@@ -747,6 +755,11 @@ static int animate_range(p3cs_group grp, int first, int count, bool timed) {
     }
     ++launches;
     ++nskin;
+  }
+  if (!grp->mesh->use_strip && grp->dev.bounds != nullptr) {
+    launch_bounds_init(grp->dev, first, count, s);
+    launch_bounds_scan(m, grp->dev, first, count, s);
+    launches += 2;
   }
   if (timed) CUDA_TRY(cudaEventRecord(grp->ev[1], s));
   CUDA_TRY(cudaGetLastError());
@@ -788,6 +801,47 @@ extern "C" int p3cs_group_last_timings(p3cs_group grp, p3cs_timings *out) {
     }
   }
   *out = grp->last;
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_group_enable_bounds(p3cs_group grp, const p3cs_column_desc *vertex_column) {
+  if (grp == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_enable_bounds: group is NULL");
+  if (vertex_column == nullptr) {  // off (the buffer stays allocated until the group is destroyed)
+    grp->dev.bounds = nullptr;
+    return P3CS_OK;
+  }
+  const p3cs_mesh_s *mesh = grp->mesh;
+  const MeshDev &m = mesh->dev;
+  const p3cs_column_desc &c = *vertex_column;
+  if (c.array < 0 || c.array >= (int)mesh->out_of_array.size() || mesh->out_of_array[c.array] < 0)
+    return fail(P3CS_ERR_INVALID, "p3cs_group_enable_bounds: column is not in an output array");
+  const int o = mesh->out_of_array[c.array];
+  // GeomVertexReader::get_data3 on anything else divides by w or converts (geomVertexColumn.cxx:2800-2808)
+  if (c.numeric_type != P3CS_NT_FLOAT32 || c.num_values != 3 || c.start < 0 || c.start % 4 != 0 || c.start + 12 > m.stride[o])
+    return fail(P3CS_ERR_UNSUPPORTED, "p3cs_group_enable_bounds: only a 4-byte aligned float32 x 3 column is supported");
+  DeviceGuard g(mesh->ctx->device);
+  if (grp->bounds_buf == nullptr) {
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, std::max<size_t>((size_t)grp->n * 32, 256)));
+    grp->allocations.push_back(p);
+    grp->bounds_buf = static_cast<float *>(p);
+    launch_bounds_init(GroupDev{nullptr, nullptr, nullptr, {}, {}, nullptr, grp->bounds_buf, 0, 0}, 0, grp->n, mesh->ctx->stream);
+  }
+  grp->dev.bounds = grp->bounds_buf;
+  grp->dev.bounds_output = o;
+  grp->dev.bounds_start = c.start;
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_group_read_bounds(p3cs_group grp, int first, int count, float *host_dst) {
+  int rc = check_span(grp, first, count, "p3cs_group_read_bounds");
+  if (rc != P3CS_OK) return rc;
+  if (host_dst == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_read_bounds: destination is NULL");
+  if (grp->dev.bounds == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_read_bounds: bounds are not enabled (p3cs_group_enable_bounds)");
+  if (count == 0) return P3CS_OK;
+  DeviceGuard g(grp->mesh->ctx->device);
+  CUDA_TRY(cudaMemcpyAsync(host_dst, grp->dev.bounds + (size_t)first * 8, (size_t)count * 32, cudaMemcpyDeviceToHost, grp->mesh->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(grp->mesh->ctx->stream));
   return P3CS_OK;
 }
 

@@ -242,4 +242,97 @@ __device__ __forceinline__ void animate_column(const MeshDev &mesh, const DynCol
   }
 }
 
+// ---- animated tight bounds (GeomPrimitive::calc_tight_bounds, gobj/geomPrimitive.cxx:1646-1830, non-indexed
+// no-matrix branch): running min / max of the vertex column and max of length_squared(); NaN components
+// never win a comparison there (std::min/max) nor here (fminf/fmaxf).
+struct BoundsAcc {
+  float lo[3], hi[3], sq;
+  __device__ __forceinline__ void reset() {
+    lo[0] = lo[1] = lo[2] = __int_as_float(0x7f800000);
+    hi[0] = hi[1] = hi[2] = __int_as_float(0xff800000);
+    sq = 0.0f;
+  }
+  __device__ __forceinline__ void add(float x, float y, float z) {
+    lo[0] = fminf(lo[0], x); lo[1] = fminf(lo[1], y); lo[2] = fminf(lo[2], z);
+    hi[0] = fmaxf(hi[0], x); hi[1] = fmaxf(hi[1], y); hi[2] = fmaxf(hi[2], z);
+    sq = fmaxf(sq, x * x + y * y + z * z);  // LVecBase3f::length_squared = dot(*this), left to right
+  }
+  __device__ __forceinline__ void merge(const BoundsAcc &o) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = fminf(lo[k], o.lo[k]);
+      hi[k] = fmaxf(hi[k], o.hi[k]);
+    }
+    sq = fmaxf(sq, o.sq);
+  }
+  __device__ __forceinline__ void warp_reduce() {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      BoundsAcc o;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        o.lo[k] = __shfl_xor_sync(0xffffffffu, lo[k], off);
+        o.hi[k] = __shfl_xor_sync(0xffffffffu, hi[k], off);
+      }
+      o.sq = __shfl_xor_sync(0xffffffffu, sq, off);
+      merge(o);
+    }
+  }
+};
+
+// float atomic min / max through the integer ordering of IEEE bit patterns (-0 is folded into +0 first)
+__device__ __forceinline__ void atomic_min_float(float *addr, float v) {
+  v = v + 0.0f;
+  if (v != v) return;
+  if (v >= 0.0f) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
+  v = v + 0.0f;
+  if (v != v) return;
+  if (v >= 0.0f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+// One CTA's contribution to the bounds of one instance: warp shuffles, then `scratch` (>= 8 warps x 7 floats of
+// shared memory nobody else uses any more), then thread 0 stores (a CTA owning the whole instance) or merges.
+__device__ __forceinline__ void bounds_commit(BoundsAcc acc, float *scratch, float *dst, bool whole_instance, int tid, int nthreads) {
+  acc.warp_reduce();
+  const int warp = tid >> 5, nwarps = nthreads >> 5;
+  if ((tid & 31) == 0) {
+    float *w = scratch + warp * 7;
+    w[0] = acc.lo[0]; w[1] = acc.lo[1]; w[2] = acc.lo[2];
+    w[3] = acc.hi[0]; w[4] = acc.hi[1]; w[5] = acc.hi[2];
+    w[6] = acc.sq;
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  for (int i = 1; i < nwarps; ++i) {
+    const float *w = scratch + i * 7;
+    BoundsAcc o;
+    o.lo[0] = w[0]; o.lo[1] = w[1]; o.lo[2] = w[2];
+    o.hi[0] = w[3]; o.hi[1] = w[4]; o.hi[2] = w[5];
+    o.sq = w[6];
+    acc.merge(o);
+  }
+  const bool found = acc.lo[0] <= acc.hi[0] || acc.lo[1] <= acc.hi[1] || acc.lo[2] <= acc.hi[2];
+  if (whole_instance) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      dst[k] = acc.lo[k] + 0.0f;
+      dst[3 + k] = acc.hi[k] + 0.0f;
+    }
+    dst[6] = acc.sq;
+    dst[7] = found ? 1.0f : 0.0f;
+  } else if (found) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      atomic_min_float(dst + k, acc.lo[k]);
+      atomic_max_float(dst + 3 + k, acc.hi[k]);
+    }
+    atomic_max_float(dst + 6, acc.sq);
+    dst[7] = 1.0f;
+  }
+}
+
 }  // namespace p3cs

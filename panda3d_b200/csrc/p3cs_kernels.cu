@@ -145,4 +145,42 @@ void launch_skin(const MeshDev &mesh, const GroupDev &grp, int first_instance, i
   }
 }
 
+// ---- animated tight bounds for the two-kernel path; the strip kernel fuses the reduction
+__global__ void bounds_init_kernel(float *bounds, int first, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count * 8) return;
+  const int k = i & 7;
+  bounds[(size_t)first * 8 + i] = k < 3 ? __int_as_float(0x7f800000) : k < 6 ? __int_as_float(0xff800000) : 0.0f;
+}
+
+__global__ void __launch_bounds__(256) bounds_scan_kernel(MeshDev mesh, GroupDev grp, int first_instance, int rows_per_cta) {
+  __shared__ float scratch[8 * 7];
+  const int inst = first_instance + blockIdx.y;
+  const int o = grp.bounds_output;
+  const uint8_t *base = grp.out[o] + (size_t)inst * grp.pitch[o] + grp.bounds_start;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(mesh.num_rows, r0 + rows_per_cta);
+  BoundsAcc acc;
+  acc.reset();
+  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+    const float *c = reinterpret_cast<const float *>(base + (size_t)r * mesh.stride[o]);
+    acc.add(c[0], c[1], c[2]);
+  }
+  bounds_commit(acc, scratch, grp.bounds + (size_t)inst * 8, false, threadIdx.x, blockDim.x);
+}
+
+void launch_bounds_init(const GroupDev &grp, int first_instance, int count, cudaStream_t stream) {
+  if (grp.bounds == nullptr || count == 0) return;
+  bounds_init_kernel<<<(count * 8 + 255) / 256, 256, 0, stream>>>(grp.bounds, first_instance, count);
+}
+
+void launch_bounds_scan(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream) {
+  if (grp.bounds == nullptr || count == 0 || mesh.num_rows == 0) return;
+  const int rows_per_cta = 8192;
+  for (int c0 = 0; c0 < count; c0 += 65535) {
+    const int cn = count - c0 < 65535 ? count - c0 : 65535;
+    dim3 grid((mesh.num_rows + rows_per_cta - 1) / rows_per_cta, cn);
+    bounds_scan_kernel<<<grid, 256, 0, stream>>>(mesh, grp, first_instance + c0, rows_per_cta);
+  }
+}
+
 }  // namespace p3cs

@@ -77,6 +77,10 @@ struct GroupDev {
   uint8_t *out[kMaxOutputs];
   size_t pitch[kMaxOutputs];
   int32_t *selection;     // optional [num_rows] debug/parity output (instance 0 of the launch)
+  // optional animated tight bounds ("next" row f4): [n][8] = min xyz, max xyz, max |v|^2, found_any
+  float *bounds;
+  int bounds_output;      // output array of the float32 x 3 column the bounds are taken over
+  int bounds_start;       // its byte offset in the row
 };
 
 // Joint hierarchy ("next" row f1): static description of a character's skeleton, joints parents-first.
@@ -104,6 +108,11 @@ void launch_skin(const MeshDev &mesh, const GroupDev &grp, int first_instance, i
 // The fused path: palette -> smem, per tile: blend records -> smem, rows via TMA bulk copies.
 // Returns the number of kernel launches issued (instances are split in grid.y chunks of 65535).
 int launch_strip(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, int sm_count, cudaStream_t stream);
+// CTAs per instance launch_strip will use (1 => bounds are stored directly, no initialisation pass needed)
+int strip_ctas_per_instance(const MeshDev &mesh, int count, int sm_count);
+// bounds: reset [first, first+count) to (+inf, -inf, 0, 0); scan the finished output arrays (two-kernel path)
+void launch_bounds_init(const GroupDev &grp, int first_instance, int count, cudaStream_t stream);
+void launch_bounds_scan(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);
 size_t strip_smem_bytes(const MeshDev &mesh);
 int skin_rows_per_tile(const MeshDev &mesh);
 

@@ -78,7 +78,8 @@ __host__ __device__ inline StripSmem strip_layout(const MeshDev &m) {
   s.palc_off = s.pal3_off + m.num_transforms * 48;
   s.records_off = s.palc_off + m.num_transforms * 16;
   const int rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
-  s.tiles_off = (s.records_off + (m.max_group_records > 0 ? m.max_group_records : 1) * rec_bytes + 127) & ~127;
+  const int recs_bytes = m.max_group_records * rec_bytes > 256 ? m.max_group_records * rec_bytes : 256;  // >= the bounds scratch
+  s.tiles_off = (s.records_off + recs_bytes + 127) & ~127;
   // staged tiles (contiguous 32-row slices): 3 in flight for 256-row tiles, 2 for 512-row tiles
   s.total = s.tiles_off + (m.rows_per_thread == 1 ? 3 : 2) * (kStripThreads * m.rows_per_thread / 32) * m.slice_bytes;
   return s;
@@ -252,10 +253,13 @@ __device__ __forceinline__ void fast_column(float *cell, const float (&f)[22]) {
   cell[2] = r2;
 }
 
-template <int MODE, int kRowsPerThread, bool SELECT, bool MORPH>
+// AUX: 0 plain, 1 also writes the per-row selection (parity hook), 2 also reduces the animated tight bounds
+template <int MODE, int kRowsPerThread, int AUX, bool MORPH>
 __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
     strip_kernel(MeshDev mesh, GroupDev grp, int first_instance, int groups_per_cta, int want_normal) {
   extern __shared__ __align__(128) uint8_t smem[];
+  constexpr bool SELECT = AUX == 1;
+  constexpr bool BOUNDS = AUX == 2;
   constexpr int kTileRows = kStripThreads * kRowsPerThread;
   constexpr int kSlicesPerTile = kTileRows / 32;
   constexpr int kTileBufs = kRowsPerThread == 1 ? 3 : 2;
@@ -359,6 +363,11 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
     pq0 = __ldg(mesh.grec_blocks + (size_t)(rbeg + tid) * 2);
     pq1 = __ldg(mesh.grec_blocks + (size_t)(rbeg + tid) * 2 + 1);
   }
+
+  BoundsAcc bounds;
+  bounds.reset();
+  const int bounds_off = BOUNDS ? kSlicesPerTile * mesh.slice_out_offset[grp.bounds_output] + grp.bounds_start : 0;
+  const int bounds_stride = BOUNDS ? mesh.stride[grp.bounds_output] : 0;
 
   int t = t0;
   for (int g = g0; g < g1; ++g) {
@@ -505,6 +514,16 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
           }
         }
       }
+      if (BOUNDS) {  // the animated vertex column of this thread's rows, as just written to the tile
+#pragma unroll
+        for (int rr = 0; rr < kRowsPerThread; ++rr) {
+          const int trow = rr * kStripThreads + tid;
+          if (t * kTileRows + trow < mesh.num_rows) {
+            const float *c = reinterpret_cast<const float *>(tile + bounds_off + (size_t)trow * bounds_stride);
+            bounds.add(c[0], c[1], c[2]);
+          }
+        }
+      }
       fence_proxy_async();  // generic-proxy writes to the tile -> visible to the TMA store
       __syncthreads();
 
@@ -529,6 +548,8 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
       }
     }
   }
+  if (BOUNDS)  // the records area is free after the last tile's barrier
+    bounds_commit(bounds, recs, grp.bounds + (size_t)inst * 8, gridDim.x == 1, tid, kStripThreads);
   if (tid == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk store's reads
 }
 
@@ -552,17 +573,20 @@ template <int MODE, int R, bool MORPH>
 static void launch_mode_rm(const MeshDev &mesh, const GroupDev &grp, int first, dim3 grid, size_t smem, int gpc, int want_normal,
                            cudaStream_t stream) {
   if (grp.selection != nullptr) {
-    cudaFuncSetAttribute(strip_kernel<MODE, R, true, MORPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    strip_kernel<MODE, R, true, MORPH><<<grid, kStripThreads, smem, stream>>>(mesh, grp, first, gpc, want_normal);
+    cudaFuncSetAttribute(strip_kernel<MODE, R, 1, MORPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    strip_kernel<MODE, R, 1, MORPH><<<grid, kStripThreads, smem, stream>>>(mesh, grp, first, gpc, want_normal);
+  } else if (grp.bounds != nullptr) {
+    cudaFuncSetAttribute(strip_kernel<MODE, R, 2, MORPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    strip_kernel<MODE, R, 2, MORPH><<<grid, kStripThreads, smem, stream>>>(mesh, grp, first, gpc, want_normal);
   } else {
     static thread_local int configured_device = -1;  // the attribute is sticky per function and device
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev != configured_device) {
-      cudaFuncSetAttribute(strip_kernel<MODE, R, false, MORPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(strip_kernel<MODE, R, 0, MORPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       configured_device = dev;
     }
-    strip_kernel<MODE, R, false, MORPH><<<grid, kStripThreads, smem, stream>>>(mesh, grp, first, gpc, want_normal);
+    strip_kernel<MODE, R, 0, MORPH><<<grid, kStripThreads, smem, stream>>>(mesh, grp, first, gpc, want_normal);
   }
 }
 
@@ -582,20 +606,32 @@ static void launch_mode(const MeshDev &mesh, const GroupDev &grp, int first, dim
   else launch_mode_r<MODE, 1>(mesh, grp, first, grid, smem, gpc, want_normal, stream);
 }
 
+// strips of whole record groups: enough of them to fill every SM several times over, yet as
+// long as possible so the palette is staged rarely
+static int strip_partition(const MeshDev &mesh, int count, int sm_count, int *groups_per_cta) {
+  const long long target_ctas = (long long)sm_count * 24;
+  long long gpc = ((long long)mesh.num_groups * count + target_ctas - 1) / target_ctas;
+  if (gpc < 1) gpc = 1;
+  if (gpc > mesh.num_groups) gpc = mesh.num_groups;
+  const int strips = (mesh.num_groups + (int)gpc - 1) / (int)gpc;
+  *groups_per_cta = (mesh.num_groups + strips - 1) / strips;  // equal-length strips
+  return strips;
+}
+
+int strip_ctas_per_instance(const MeshDev &mesh, int count, int sm_count) {
+  if (mesh.num_rows == 0 || count == 0 || mesh.num_tiles == 0) return 0;
+  int gpc;
+  return strip_partition(mesh, count, sm_count, &gpc);
+}
+
 int launch_strip(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, int sm_count, cudaStream_t stream) {
   if (mesh.num_rows == 0 || count == 0 || mesh.num_tiles == 0) return 0;
   int want_normal = 0;
   for (int c = 0; c < mesh.num_dyn; ++c) want_normal |= (mesh.dyn[c].skin == 3);
   const size_t smem = strip_smem_bytes(mesh);
   const int mode = pick_mode(mesh);
-  // strips of whole record groups: enough of them to fill every SM several times over, yet as
-  // long as possible so the palette is staged rarely
-  const long long target_ctas = (long long)sm_count * 24;
-  long long gpc = ((long long)mesh.num_groups * count + target_ctas - 1) / target_ctas;
-  if (gpc < 1) gpc = 1;
-  if (gpc > mesh.num_groups) gpc = mesh.num_groups;
-  const int strips = (mesh.num_groups + (int)gpc - 1) / (int)gpc;
-  gpc = (mesh.num_groups + strips - 1) / strips;  // equal-length strips
+  int gpc;
+  const int strips = strip_partition(mesh, count, sm_count, &gpc);
   int launches = 0;
   for (int c0 = 0; c0 < count; c0 += 65535) {
     const int cn = count - c0 < 65535 ? count - c0 : 65535;

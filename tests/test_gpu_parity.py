@@ -415,3 +415,93 @@ def test_joint_hierarchy_crowd_vs_oracle(gpu_ctx):
         grp.close()
         dskel.close()
         dmesh.close()
+
+
+def _expected_bounds(out_array, col):
+    """GeomPrimitive::calc_tight_bounds (gobj/geomPrimitive.cxx:1646-1700, non-indexed, no matrix) over the animated
+    vertex column: component-wise min / max and max of length_squared() = (x*x + y*y) + z*z in float32."""
+    v = np.ascontiguousarray(out_array[:, col.start:col.start + 12]).view(np.float32).reshape(-1, 3)
+    with np.errstate(invalid="ignore"):
+        sq = (v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]) + v[:, 2] * v[:, 2]
+        return np.concatenate([np.nanmin(v, axis=0), np.nanmax(v, axis=0), [np.nanmax(sq)], [1.0]]).astype(np.float32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["strip", "wide"])
+def test_animated_tight_bounds(gpu_ctx, monkeypatch, path):
+    """f4: the bounds the kernel reduces while skinning equal a CPU walk over its own animated vertices exactly
+    (min / max are exact), for a crowd (one CTA per instance), a single mesh (several CTAs, atomics), a
+    morph-only mesh with an explicit vertex column, and rows holding NaN."""
+    monkeypatch.setenv("P3CS_PATH", path)
+    # (1) crowd: 300 instances, generic layout with morphs
+    sm = synth.make_mesh(3_000, 24, 400, seed=81, tbn=True, index_order="runs", num_sliders=3, slider_band=0.3)
+    mesh = sm.flat
+    n = 300
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, n)
+    try:
+        grp.set_palettes(synth.make_palettes(24, n, 82).reshape(n, -1))
+        grp.set_sliders(synth.make_sliders(3, n, 83))
+        grp.enable_bounds()
+        grp.animate()
+        got = grp.read_bounds()
+        out = grp.read_output(0)
+        for i in (0, 1, 17, n - 1):
+            assert np.array_equal(got[i], _expected_bounds(out[i], mesh.skin_columns[0])), f"instance {i}"
+        # against the oracle's vertices: within the float contract
+        expect, _, _ = oracle.animate(mesh, grp.read_palettes(0, 1)[0], synth.make_sliders(3, n, 83)[0])
+        eb = _expected_bounds(expect[0], mesh.skin_columns[0])
+        assert np.allclose(got[0], eb, rtol=REL_TOL, atol=1e-6)
+        # a second animate with other palettes replaces (does not accumulate into) the bounds
+        grp.set_palettes(synth.make_palettes(24, n, 84, scale=0.25).reshape(n, -1))
+        grp.animate()
+        got2 = grp.read_bounds()
+        out2 = grp.read_output(0)
+        assert np.array_equal(got2[5], _expected_bounds(out2[5], mesh.skin_columns[0]))
+        grp.enable_bounds(enable=False)
+        grp.animate()
+        with pytest.raises(_capi.P3csError):
+            grp.read_bounds()
+    finally:
+        grp.close()
+        dmesh.close()
+    # (2) one big packed mesh (specialised mode, many CTAs for the one instance), with NaN rows
+    sm = synth.make_mesh(70_000, 32, 3000, seed=85, index_order="runs")
+    mesh = sm.flat
+    f = mesh.arrays[0].view(np.float32)
+    f[123, 0] = np.nan
+    f[50_000, 0:3] = np.nan
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, 1)
+    try:
+        grp.set_palettes(synth.make_palettes(32, 1, 86).reshape(1, -1))
+        grp.enable_bounds()
+        grp.animate()
+        assert np.array_equal(grp.read_bounds()[0], _expected_bounds(grp.read_output(0)[0], mesh.skin_columns[0]))
+    finally:
+        grp.close()
+        dmesh.close()
+    # (3) sliders only (nothing skinned): the vertex column is named explicitly
+    sm = synth.make_mesh(2_000, 4, 8, seed=87, num_sliders=5, slider_band=0.4)
+    mesh = F.FlatMesh(**{**sm.flat.__dict__})
+    vertex = mesh.skin_columns[0]
+    mesh.skin_columns, mesh.blend_column = [], None
+    mesh.blend_offsets = np.zeros(1, np.int32)
+    mesh.blend_transform, mesh.blend_weight = np.zeros(0, np.int32), np.zeros(0, np.float32)
+    mesh.num_transforms = 0
+    mesh.row_ranges = np.zeros((0, 2), np.int32)
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, 2)
+    try:
+        grp.set_sliders(synth.make_sliders(5, 2, 88))
+        grp.enable_bounds(vertex)
+        grp.animate()
+        out = grp.read_output(0)
+        got = grp.read_bounds()
+        for i in range(2):
+            assert np.array_equal(got[i], _expected_bounds(out[i], vertex))
+        with pytest.raises(_capi.P3csError):   # a float64 / 4-component column is refused, not misread
+            grp.enable_bounds(F.Column(0, 0, 4, F.NT_float32, F.C_point))
+    finally:
+        grp.close()
+        dmesh.close()
