@@ -485,6 +485,7 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
               float v[6] = {a.x, a.y, b2.x, b2.y, c.x, c.y};
               fast_column<1>(v, f);
               fast_column<3>(v + 3, f);
+              if (BOUNDS && bounds_off == 0) bounds.add(v[0], v[1], v[2]);  // the vertex column, straight from the registers
               rowp[0] = make_float2(v[0], v[1]);
               rowp[1] = make_float2(v[2], v[3]);
               rowp[2] = make_float2(v[4], v[5]);
@@ -518,7 +519,8 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
 #pragma unroll
         for (int rr = 0; rr < kRowsPerThread; ++rr) {
           const int trow = rr * kStripThreads + tid;
-          if (t * kTileRows + trow < mesh.num_rows) {
+          const bool in_registers = MODE == kFastPN24 && local[rr] != 0xFFFF && bounds_off == 0;
+          if (t * kTileRows + trow < mesh.num_rows && !in_registers) {
             const float *c = reinterpret_cast<const float *>(tile + bounds_off + (size_t)trow * bounds_stride);
             bounds.add(c[0], c[1], c[2]);
           }
