@@ -265,6 +265,11 @@ P3CS_EXPORT int p3cs_group_set_sliders(p3cs_group group, int first, int count,
  * 1550-1556), applies morphs (1462-1543) and skins every point / vector /
  * normal column (1558-1751) of all instances.  Asynchronous. */
 P3CS_EXPORT int p3cs_group_animate(p3cs_group group);
+/* A frame's worth of groups (a mixed crowd: one group per character type, what the per-Geom loop of
+ * CullableObject::munge_geom, pgraph/cullableObject.cxx:170-175, visits one by one): the groups are independent,
+ * so their kernels are forked over side streams of the context and joined back into its stream -- small
+ * per-type launches overlap instead of queueing behind each other.  All groups must share one context. */
+P3CS_EXPORT int p3cs_animate_groups(p3cs_group const *groups, int num_groups);
 
 /* Device -> host copy of `count` instances of one output array into
  * host_dst (count * num_rows * stride bytes, tightly packed = the byte image

@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "p3cs_group_animate", "p3cs_group_read_output", "p3cs_group_read_selection", "p3cs_group_read_blends",
     "p3cs_group_set_profiling", "p3cs_group_last_timings", "p3cs_animate_vertices", "p3cs_get_api",
     "p3cs_skeleton_create", "p3cs_skeleton_destroy", "p3cs_group_pose", "p3cs_group_read_palettes",
-    "p3cs_group_enable_bounds", "p3cs_group_read_bounds",
+    "p3cs_group_enable_bounds", "p3cs_group_read_bounds", "p3cs_animate_groups",
 ]
 
 
@@ -139,6 +139,7 @@ def lib():
         L.p3cs_group_read_palettes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.p3cs_group_enable_bounds.argtypes = [C.c_void_p, C.POINTER(_ColumnDesc)]
         L.p3cs_group_read_bounds.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.p3cs_animate_groups.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         _lib = L
     return _lib
 
@@ -415,3 +416,9 @@ class Group:
         if self.handle:
             lib().p3cs_group_destroy(self.handle)
             self.handle = C.c_void_p()
+
+
+def animate_groups(groups) -> None:
+    """p3cs_animate_groups: one frame of a mixed crowd; independent groups overlap on side streams."""
+    arr = (C.c_void_p * len(groups))(*[g.handle.value for g in groups])
+    _check(lib().p3cs_animate_groups(arr, len(groups)))

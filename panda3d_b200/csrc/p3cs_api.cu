@@ -44,6 +44,11 @@ struct p3cs_context_s {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   bool owns_stream = false;
+  // fork / join plumbing of p3cs_animate_groups: independent groups run on side streams
+  static constexpr int kSideStreams = 3;
+  cudaStream_t side[kSideStreams] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fork_ev = nullptr;
+  cudaEvent_t join_ev[kSideStreams] = {nullptr, nullptr, nullptr};
 };
 
 struct p3cs_mesh_s {
@@ -155,6 +160,11 @@ extern "C" int p3cs_context_destroy(p3cs_context ctx) {
   if (ctx == nullptr) return P3CS_OK;
   DeviceGuard g(ctx->device);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+  for (auto st : ctx->side)
+    if (st) cudaStreamDestroy(st);
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+  for (auto e : ctx->join_ev)
+    if (e) cudaEventDestroy(e);
   delete ctx;
   return P3CS_OK;
 }
@@ -704,9 +714,9 @@ static int prof_event(p3cs_group grp, size_t i, cudaEvent_t *out) {
   return P3CS_OK;
 }
 
-static int animate_range(p3cs_group grp, int first, int count, bool timed) {
+static int animate_range(p3cs_group grp, int first, int count, bool timed, cudaStream_t stream_override = nullptr) {
   const MeshDev &m = grp->mesh->dev;
-  cudaStream_t s = grp->mesh->ctx->stream;
+  cudaStream_t s = stream_override != nullptr ? stream_override : grp->mesh->ctx->stream;
   const bool prof = timed && grp->profiling;
   int launches = 0, nblend = 0, nskin = 0, rc;
   size_t pe = 0;
@@ -775,6 +785,41 @@ extern "C" int p3cs_group_animate(p3cs_group grp) {
   if (grp == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_animate: group is NULL");
   DeviceGuard g(grp->mesh->ctx->device);
   return animate_range(grp, 0, grp->n, true);
+}
+
+extern "C" int p3cs_animate_groups(p3cs_group const *groups, int num_groups) {
+  if (num_groups < 0 || (num_groups > 0 && groups == nullptr)) return fail(P3CS_ERR_INVALID, "p3cs_animate_groups: bad arguments");
+  if (num_groups == 0) return P3CS_OK;
+  p3cs_context ctx = nullptr;
+  for (int i = 0; i < num_groups; ++i) {
+    if (groups[i] == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_animate_groups: group %d is NULL", i);
+    if (ctx == nullptr) ctx = groups[i]->mesh->ctx;
+    else if (groups[i]->mesh->ctx != ctx) return fail(P3CS_ERR_INVALID, "p3cs_animate_groups: group %d belongs to another context", i);
+  }
+  DeviceGuard g(ctx->device);
+  if (num_groups == 1) return animate_range(groups[0], 0, groups[0]->n, true);
+  if (ctx->fork_ev == nullptr) {
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+    for (int k = 0; k < p3cs_context_s::kSideStreams; ++k) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming));
+    }
+  }
+  // fork: group i runs on lane i % (1 + kSideStreams); lane 0 is the context's own stream
+  const int lanes = std::min(num_groups, 1 + p3cs_context_s::kSideStreams);
+  CUDA_TRY(cudaEventRecord(ctx->fork_ev, ctx->stream));
+  for (int k = 1; k < lanes; ++k) CUDA_TRY(cudaStreamWaitEvent(ctx->side[k - 1], ctx->fork_ev, 0));
+  int rc = P3CS_OK;
+  for (int i = 0; i < num_groups && rc == P3CS_OK; ++i) {
+    const int lane = i % lanes;
+    rc = animate_range(groups[i], 0, groups[i]->n, true, lane == 0 ? ctx->stream : ctx->side[lane - 1]);
+  }
+  // join (also on failure, so the side streams never run ahead of the context's stream)
+  for (int k = 1; k < lanes; ++k) {
+    cudaEventRecord(ctx->join_ev[k - 1], ctx->side[k - 1]);
+    cudaStreamWaitEvent(ctx->stream, ctx->join_ev[k - 1], 0);
+  }
+  return rc;
 }
 
 extern "C" int p3cs_group_set_profiling(p3cs_group grp, int enable) {

@@ -505,3 +505,40 @@ def test_animated_tight_bounds(gpu_ctx, monkeypatch, path):
     finally:
         grp.close()
         dmesh.close()
+
+
+@pytest.mark.gpu
+def test_animate_groups_mixed_crowd(gpu_ctx):
+    """p3cs_animate_groups (independent groups forked over side streams) == animating the groups one by one,
+    byte for byte, on a C5-style mixed crowd of 6 character types (more groups than side streams)."""
+    shapes = [(900, 8, 100, 7), (2_000, 16, 300, 5), (5_000, 32, 700, 3), (300, 4, 20, 11), (1_200, 12, 200, 2), (4_099, 24, 512, 1)]
+    meshes, groups, expect = [], [], []
+    try:
+        for i, (rows, t, b, n) in enumerate(shapes):
+            sm = synth.make_mesh(rows, t, b, seed=900 + i, tbn=(i % 2 == 0), index_order="runs",
+                                 num_sliders=2 if i == 2 else 0, slider_band=0.3)
+            dm = _capi.Mesh(gpu_ctx, sm.flat)
+            g = _capi.Group(dm, n)
+            g.set_palettes(synth.make_palettes(t, n, 950 + i).reshape(n, -1))
+            if sm.flat.num_sliders:
+                g.set_sliders(synth.make_sliders(2, n, 960 + i))
+            meshes.append(dm)
+            groups.append(g)
+        for g in groups:
+            g.animate()
+            expect.append(g.read_output(0).copy())
+        for _ in range(3):   # repeated frames: the join must order every side stream before the read-back
+            for g in groups:  # scribble over the outputs so a skipped group would show
+                g.set_palettes(np.zeros((g.n, g.mesh.flat.num_transforms * 16), np.float32))
+                g.animate()
+            for i, g in enumerate(groups):
+                g.set_palettes(synth.make_palettes(shapes[i][1], shapes[i][3], 950 + i).reshape(shapes[i][3], -1))
+            _capi.animate_groups(groups)
+            for g, e in zip(groups, expect):
+                assert np.array_equal(g.read_output(0), e)
+        assert all(g.timings().launches >= 1 for g in groups)
+    finally:
+        for g in groups:
+            g.close()
+        for dm in meshes:
+            dm.close()

@@ -14,8 +14,16 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def time_groups(torch, stream, groups, steps, warmup, flush=None):
+def time_groups(torch, stream, groups, steps, warmup, flush=None, together=False):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if together:   # one p3cs_animate_groups call per step (independent groups overlap on side streams)
+        from panda3d_b200 import _capi
+
+        class _All:
+            def animate(self):
+                _capi.animate_groups(groups)
+        groups_iter = [_All()]
+        return time_groups(torch, stream, groups_iter, steps, warmup, flush)
     for _ in range(warmup):
         for g in groups:
             g.animate()
@@ -100,6 +108,9 @@ def main():
                 logical += n * flat.num_rows * (2 * dyn + 2)
             ctx.sync()
             ms = time_groups(torch, stream, groups, args.steps, args.warmup, flush if small else None)
+            if len(groups) > 1:
+                ms_together = time_groups(torch, stream, groups, args.steps, args.warmup, flush if small else None, together=True)
+                print(json.dumps({"config": name + "+animate_groups", "ms_per_step": ms_together, "gverts_per_s": verts / ms_together / 1e6}), flush=True)
             print(json.dumps({"config": name, "ms_per_step": ms, "vertices": verts, "gverts_per_s": verts / ms / 1e6,
                               "out_gbs": out_bytes / ms / 1e6, "logical_gbs": logical / ms / 1e6,
                               "l2_flush_between_steps": small, "launches": sum(g.timings().launches for g in groups)}), flush=True)
