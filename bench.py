@@ -412,6 +412,12 @@ def run_gpu_arm(args):
             except Exception as exc:  # reported, never hidden
                 fused = {"error": repr(exc)}
 
+        # ---------------- the other BASELINE.json configurations, device time per animate call (rank 0, N=1):
+        # parity-test cases, not bench lines -- reported so the single-mesh latencies sit next to the crowd number
+        others = None
+        if world == 1 and not args.no_configs:
+            others = other_configs(torch, ctx, stream, _capi, synth)
+
     total_verts = float(sum_over_ranks(float(n_local * flat.skinned_rows())))
     value = total_verts / (ms * 1e-3)
     e2e_value = total_verts / (e2e_ms * 1e-3)
@@ -438,7 +444,7 @@ def run_gpu_arm(args):
             if pj.get("instances") == n_local:
                 traffic = pj.get("dram_bytes_per_launch")
         roofline = {"bound": "hbm", "kernel": "p3cs::strip_kernel<kFastPN24>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic, "peak_source": peak_src,
                     "launches_per_step": skin_launches, "avg_launch_ms": 1e3 * skin_s / max(1, skin_launches),
                     "algorithmic_bytes_per_launch": alg_bytes_per_step,
                     "algorithmic_bytes_per_vertex": alg_bytes_per_step / (n_local * rows),
@@ -447,9 +453,10 @@ def run_gpu_arm(args):
         cpu = None
         if world == 1 and not args.no_cpu:
             workers = os.cpu_count() or 1
-            r = cpu_reference_run(sm, 5, 2, max(1, args.cpu_characters), workers)
-            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-                   "sample": f"{args.cpu_characters} character(s) x {workers} worker processes x 5 iterations of the same mesh"}
+            r = cpu_reference_run(sm, 100, 3, max(1, args.cpu_characters), workers)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "wall_s": r.get("wall_s"),
+                   "sample": f"{args.cpu_characters} character(s) x {workers} worker processes x 100 iterations of the same mesh "
+                             f"(every joint matrix changed per iteration)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -458,7 +465,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                     "ms_per_step": e2e_ms, "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps, "clocks": sampler.summary(), "check": check,
-            "gather": gather, "fused_gather": fused, "joints_on_gpu": joints, "tight_bounds": bounds,
+            "gather": gather, "fused_gather": fused, "joints_on_gpu": joints, "tight_bounds": bounds, "other_configs": others,
         }
         print(json.dumps(line), flush=True)
     grp.close()
@@ -466,6 +473,50 @@ def run_gpu_arm(args):
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def other_configs(torch, ctx, stream, _capi, synth):
+    """Device time per animate call of configs[1], [3], [4] (C2 single mesh, C4 morph mesh, C5 mixed crowd), L2
+    flushed between calls (a 256 MB buffer is rewritten), CUDA events on the launch stream."""
+    flush = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = {}
+    specs = {
+        "c2_100k_single_mesh": [(synth.config_c2("random").flat, 1)],
+        "c4_250k_morph_mesh": [(synth.config_c4().flat, 1)],
+        "c5_mixed_crowd_2M": [(m.flat, n) for m, n in synth.config_c5_meshes()],
+    }
+    for name, spec in specs.items():
+        meshes, groups, verts = [], [], 0
+        for i, (fm, n) in enumerate(spec):
+            dm = _capi.Mesh(ctx, fm)
+            g = _capi.Group(dm, n)
+            g.set_palettes(synth.make_palettes(fm.num_transforms, n, 31 + i).reshape(n, -1))
+            if fm.num_sliders:
+                g.set_sliders(synth.make_sliders(fm.num_sliders, n, 41 + i))
+            meshes.append(dm)
+            groups.append(g)
+            verts += n * fm.skinned_rows()
+        for _ in range(3):
+            _capi.animate_groups(groups)
+        stream.synchronize()
+        total, reps = 0.0, 20
+        for _ in range(reps):
+            flush.add_(1)
+            e0.record(stream)
+            _capi.animate_groups(groups)
+            e1.record(stream)
+            stream.synchronize()
+            total += e0.elapsed_time(e1)
+        us = total / reps * 1e3
+        out[name] = {"us_per_call": us, "vertices": verts, "vertices_per_s": verts / (us * 1e-6),
+                     "launches": int(sum(g.timings().launches for g in groups))}
+        for g in groups:
+            g.close()
+        for dm in meshes:
+            dm.close()
+    del flush
+    return out
 
 
 def main():
@@ -476,10 +527,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--instances", type=int, default=TOTAL_INSTANCES)
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-characters", type=int, default=4, help="characters per CPU worker process per step")
+    ap.add_argument("--cpu-characters", type=int, default=32, help="characters per CPU worker process per step")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--no-pose", action="store_true", help="skip the joint-hierarchy-on-GPU measurement")
+    ap.add_argument("--no-configs", action="store_true", help="skip the device timings of the other BASELINE configurations")
     ap.add_argument("--no-fused", action="store_true", help="skip the peer-memory fused skin+gather measurement (N>1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
