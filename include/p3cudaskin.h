@@ -298,6 +298,13 @@ P3CS_EXPORT int p3cs_group_last_timings(p3cs_group group, p3cs_timings *out);
 P3CS_EXPORT int p3cs_animate_vertices(p3cs_group group, int instance,
                                       const float *host_palette, const float *host_sliders,
                                       void *const *host_outputs);
+/* Page-locks and device-maps a host buffer (e.g. the result GeomVertexArrayData's VertexDataBuffer, once, as
+ * long as it is not reallocated).  When every host_outputs[i] of p3cs_animate_vertices is such a buffer, 16-byte
+ * aligned with rows*stride a multiple of 16, the kernel stores the animated rows straight into it over PCIe
+ * and no device->host copy follows (the group's device copy of that instance is then left untouched).
+ * Unregister before the buffer is freed. */
+P3CS_EXPORT int p3cs_host_register(p3cs_context ctx, void *host_ptr, size_t bytes);
+P3CS_EXPORT int p3cs_host_unregister(p3cs_context ctx, void *host_ptr);
 
 /* ---- joint hierarchy on the GPU ("next" row f1 of SURVEY.md section 8f) ---- */
 

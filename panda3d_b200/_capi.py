@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = [
     "p3cs_group_set_profiling", "p3cs_group_last_timings", "p3cs_animate_vertices", "p3cs_get_api",
     "p3cs_skeleton_create", "p3cs_skeleton_destroy", "p3cs_group_pose", "p3cs_group_read_palettes",
     "p3cs_group_enable_bounds", "p3cs_group_read_bounds", "p3cs_animate_groups",
+    "p3cs_host_register", "p3cs_host_unregister",
 ]
 
 
@@ -140,6 +141,8 @@ def lib():
         L.p3cs_group_enable_bounds.argtypes = [C.c_void_p, C.POINTER(_ColumnDesc)]
         L.p3cs_group_read_bounds.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.p3cs_animate_groups.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.p3cs_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.p3cs_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -196,6 +199,13 @@ class Context:
         buf = (C.c_ubyte * 64)()
         _check(lib().p3cs_ipc_export(self.handle, ptr, buf))
         return bytes(buf)
+
+    def host_register(self, array: np.ndarray) -> None:
+        """Page-locks + maps a numpy buffer so p3cs_animate_vertices can store into it directly."""
+        _check(lib().p3cs_host_register(self.handle, array.ctypes.data, array.nbytes))
+
+    def host_unregister(self, array: np.ndarray) -> None:
+        _check(lib().p3cs_host_unregister(self.handle, array.ctypes.data))
 
     def ipc_open(self, handle: bytes) -> int:
         buf = (C.c_ubyte * 64).from_buffer_copy(handle)
@@ -402,11 +412,14 @@ class Group:
         _check(lib().p3cs_group_read_blends(self.handle, instance, b.ctypes.data))
         return b
 
-    def animate_vertices(self, palette: np.ndarray, sliders: Optional[np.ndarray] = None, instance: int = 0) -> List[np.ndarray]:
-        """GeomVertexData::animate_vertices(force=True) with host buffers, one instance, synchronous."""
+    def animate_vertices(self, palette: np.ndarray, sliders: Optional[np.ndarray] = None, instance: int = 0,
+                         outs: Optional[List[np.ndarray]] = None) -> List[np.ndarray]:
+        """GeomVertexData::animate_vertices(force=True) with host buffers, one instance, synchronous.
+        `outs`: destination arrays to reuse (e.g. buffers registered with Context.host_register)."""
         pal = np.ascontiguousarray(palette, np.float32)
         sl = np.ascontiguousarray(sliders, np.float32) if sliders is not None else None
-        outs = [np.empty((self.mesh.num_rows, s), np.uint8) for s in self.mesh.out_strides]
+        if outs is None:
+            outs = [np.empty((self.mesh.num_rows, s), np.uint8) for s in self.mesh.out_strides]
         ptrs = (C.c_void_p * max(1, len(outs)))(*[o.ctypes.data for o in outs])
         _check(lib().p3cs_animate_vertices(self.handle, instance, pal.ctypes.data,
                                            sl.ctypes.data if sl is not None else None, ptrs))

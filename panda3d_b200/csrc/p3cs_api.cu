@@ -714,8 +714,10 @@ static int prof_event(p3cs_group grp, size_t i, cudaEvent_t *out) {
   return P3CS_OK;
 }
 
-static int animate_range(p3cs_group grp, int first, int count, bool timed, cudaStream_t stream_override = nullptr) {
+static int animate_range(p3cs_group grp, int first, int count, bool timed, cudaStream_t stream_override = nullptr,
+                         const GroupDev *dev_override = nullptr) {
   const MeshDev &m = grp->mesh->dev;
+  const GroupDev &gd = dev_override != nullptr ? *dev_override : grp->dev;
   cudaStream_t s = stream_override != nullptr ? stream_override : grp->mesh->ctx->stream;
   const bool prof = timed && grp->profiling;
   int launches = 0, nblend = 0, nskin = 0, rc;
@@ -728,11 +730,11 @@ static int animate_range(p3cs_group grp, int first, int count, bool timed, cudaS
       if ((rc = prof_event(grp, pe++, &e0)) != P3CS_OK || (rc = prof_event(grp, pe++, &e1)) != P3CS_OK) return rc;
       CUDA_TRY(cudaEventRecord(e0, s));
     }
-    if (grp->dev.bounds != nullptr && strip_ctas_per_instance(m, count, grp->mesh->ctx->sm_count) != 1) {
-      launch_bounds_init(grp->dev, first, count, s);  // several CTAs per instance merge with atomics
+    if (gd.bounds != nullptr && strip_ctas_per_instance(m, count, grp->mesh->ctx->sm_count) != 1) {
+      launch_bounds_init(gd, first, count, s);  // several CTAs per instance merge with atomics
       ++launches;
     }
-    nskin = launch_strip(m, grp->dev, first, count, grp->mesh->ctx->sm_count, s);
+    nskin = launch_strip(m, gd, first, count, grp->mesh->ctx->sm_count, s);
     launches += nskin;
     if (prof) {
       CUDA_TRY(cudaEventRecord(e1, s));
@@ -746,7 +748,7 @@ static int animate_range(p3cs_group grp, int first, int count, bool timed, cudaS
         if ((rc = prof_event(grp, pe++, &e0)) != P3CS_OK || (rc = prof_event(grp, pe++, &e1)) != P3CS_OK) return rc;
         CUDA_TRY(cudaEventRecord(e0, s));
       }
-      launch_blend(m, grp->dev, c0, cn, s);
+      launch_blend(m, gd, c0, cn, s);
       if (prof) {
         CUDA_TRY(cudaEventRecord(e1, s));
         grp->prof_kind.push_back(0);
@@ -758,7 +760,7 @@ static int animate_range(p3cs_group grp, int first, int count, bool timed, cudaS
       if ((rc = prof_event(grp, pe++, &e0)) != P3CS_OK || (rc = prof_event(grp, pe++, &e1)) != P3CS_OK) return rc;
       CUDA_TRY(cudaEventRecord(e0, s));
     }
-    launch_skin(m, grp->dev, c0, cn, s);
+    launch_skin(m, gd, c0, cn, s);
     if (prof) {
       CUDA_TRY(cudaEventRecord(e1, s));
       grp->prof_kind.push_back(1);
@@ -766,9 +768,9 @@ static int animate_range(p3cs_group grp, int first, int count, bool timed, cudaS
     ++launches;
     ++nskin;
   }
-  if (!grp->mesh->use_strip && grp->dev.bounds != nullptr) {
-    launch_bounds_init(grp->dev, first, count, s);
-    launch_bounds_scan(m, grp->dev, first, count, s);
+  if (!grp->mesh->use_strip && gd.bounds != nullptr) {
+    launch_bounds_init(gd, first, count, s);
+    launch_bounds_scan(m, gd, first, count, s);
     launches += 2;
   }
   if (timed) CUDA_TRY(cudaEventRecord(grp->ev[1], s));
@@ -962,11 +964,46 @@ extern "C" int p3cs_animate_vertices(p3cs_group grp, int instance, const float *
   if (m.num_transforms > 0 && (rc = p3cs_group_set_palettes(grp, instance, 1, host_palette)) != P3CS_OK) return rc;
   if (m.num_sliders > 0 && (rc = p3cs_group_set_sliders(grp, instance, 1, host_sliders)) != P3CS_OK) return rc;
   DeviceGuard g(grp->mesh->ctx->device);
+  // Page-locked, device-mapped destinations (p3cs_host_register / cudaHostRegister): the kernel's row stores go
+  // straight to host memory, no device->host copy afterwards.  The bulk stores move 16-byte units, hence the
+  // alignment and size conditions; anything else takes the copy below.
+  if (host_outputs != nullptr && m.num_outputs > 0) {
+    GroupDev direct = grp->dev;
+    bool ok = true;
+    for (int o = 0; o < m.num_outputs && ok; ++o) {
+      cudaPointerAttributes attr{};
+      const size_t bytes = (size_t)m.num_rows * m.stride[o];
+      ok = host_outputs[o] != nullptr && bytes % 16 == 0 && reinterpret_cast<uintptr_t>(host_outputs[o]) % 16 == 0 &&
+           cudaPointerGetAttributes(&attr, host_outputs[o]) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+           attr.devicePointer != nullptr;
+      if (ok) direct.out[o] = reinterpret_cast<uint8_t *>(reinterpret_cast<uintptr_t>(attr.devicePointer) - (uintptr_t)instance * grp->dev.pitch[o]);
+    }
+    cudaGetLastError();  // cudaPointerGetAttributes on plain malloc memory may leave a sticky-free error behind
+    if (ok) {
+      if ((rc = animate_range(grp, instance, 1, false, nullptr, &direct)) != P3CS_OK) return rc;
+      return p3cs_context_sync(grp->mesh->ctx);
+    }
+  }
   if ((rc = animate_range(grp, instance, 1, false)) != P3CS_OK) return rc;
   if (host_outputs != nullptr)
     for (int o = 0; o < m.num_outputs; ++o)
       if (host_outputs[o] != nullptr && (rc = p3cs_group_read_output(grp, o, instance, 1, host_outputs[o])) != P3CS_OK) return rc;
   return p3cs_context_sync(grp->mesh->ctx);
+}
+
+extern "C" int p3cs_host_register(p3cs_context ctx, void *host_ptr, size_t bytes) {
+  if (ctx == nullptr || host_ptr == nullptr || bytes == 0) return fail(P3CS_ERR_INVALID, "p3cs_host_register: bad arguments");
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaHostRegister(host_ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_host_unregister(p3cs_context ctx, void *host_ptr) {
+  if (ctx == nullptr || host_ptr == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_host_unregister: bad arguments");
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(cudaHostUnregister(host_ptr));
+  return P3CS_OK;
 }
 
 // ------------------------------------------------------------------ joint hierarchy (f1)

@@ -542,3 +542,52 @@ def test_animate_groups_mixed_crowd(gpu_ctx):
             g.close()
         for dm in meshes:
             dm.close()
+
+
+@pytest.mark.gpu
+def test_registered_host_outputs_are_written_directly(gpu_ctx):
+    """p3cs_animate_vertices into page-locked, mapped host arrays (p3cs_host_register): same bytes as the copying
+    path, for the packed specialised mode, a several-array generic mesh and a mesh whose size is not a multiple of
+    16 bytes (which must quietly take the copying path)."""
+    cases = [synth.make_mesh(1_338, 26, 197, seed=91, index_order="runs"),
+             synth.make_mesh(4_000, 16, 300, seed=92, tbn=True, texcoord=True, num_sliders=3, slider_band=0.3),
+             synth.make_mesh(1_001, 8, 50, seed=93, tbn=True)]   # 1001 x 48 bytes: multiple of 16; see below
+    for k, sm in enumerate(cases):
+        mesh = sm.flat
+        pal = synth.make_palettes(mesh.num_transforms, 2, 94 + k)
+        sl = synth.make_sliders(mesh.num_sliders, 2, 97) if mesh.num_sliders else [None, None]
+        dmesh = _capi.Mesh(gpu_ctx, mesh)
+        grp = _capi.Group(dmesh, 3)
+        outs = [np.full((mesh.num_rows, s), 0xEE, np.uint8) for s in dmesh.out_strides]
+        try:
+            expect = [grp.animate_vertices(pal[f], sl[f], instance=1) for f in range(2)]
+            for o in outs:
+                gpu_ctx.host_register(o)
+            for f in range(2):
+                got = grp.animate_vertices(pal[f], sl[f], instance=1, outs=outs)
+                for g, e in zip(got, expect[f]):
+                    assert np.array_equal(g, e), f"case {k} frame {f}"
+        finally:
+            for o in outs:
+                gpu_ctx.host_unregister(o)
+            grp.close()
+            dmesh.close()
+    # rows * stride not a multiple of 16 (1001 x 24): the registered buffer is still filled, through the copy
+    sm = synth.make_mesh(1_001, 8, 50, seed=95)
+    mesh = sm.flat
+    assert (mesh.num_rows * mesh.strides[0]) % 16 != 0
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, 1)
+    guard = np.full(mesh.num_rows * mesh.strides[0] + 64, 0xAB, np.uint8)
+    out = guard[:mesh.num_rows * mesh.strides[0]].reshape(mesh.num_rows, -1)
+    try:
+        pal = synth.make_palettes(8, 1, 96)[0]
+        expect = grp.animate_vertices(pal)[0]
+        gpu_ctx.host_register(guard)
+        got = grp.animate_vertices(pal, outs=[out])[0]
+        assert np.array_equal(got, expect)
+        assert (guard[mesh.num_rows * mesh.strides[0]:] == 0xAB).all(), "bytes past the array were written"
+    finally:
+        gpu_ctx.host_unregister(guard)
+        grp.close()
+        dmesh.close()
