@@ -48,7 +48,7 @@ extern "C" {
 #define P3CS_EXPORT __attribute__((visibility("default")))
 #endif
 
-#define P3CS_API_VERSION 1
+#define P3CS_API_VERSION 2
 
 typedef enum p3cs_status {
   P3CS_OK = 0,
@@ -372,6 +372,10 @@ typedef struct p3cs_api {
   int (*group_animate)(p3cs_group);
   int (*group_read_output)(p3cs_group, int, int, int, void *);
   int (*animate_vertices)(p3cs_group, int, const float *, const float *, void *const *);
+  /* version 2 */
+  int (*host_register)(p3cs_context, void *, size_t);
+  int (*host_unregister)(p3cs_context, void *);
+  int (*animate_groups)(p3cs_group const *, int);
 } p3cs_api;
 
 P3CS_EXPORT const p3cs_api *p3cs_get_api(void);

@@ -7,6 +7,7 @@
 #include "config_gobj.h"
 #include "config_putil.h"
 #include "configVariableInt.h"
+#include "configVariableBool.h"
 #include "configVariableString.h"
 #include "coordinateSystem.h"
 #include "geomVertexArrayData.h"
@@ -37,6 +38,10 @@ static ConfigVariableString cuda_skinning_library
  PRC_DESC("Name of the CUDA skinning plugin, loaded as lib<name>.so from plugin-path."));
 static ConfigVariableInt cuda_skinning_device
 ("cuda-skinning-device", 0, PRC_DESC("CUDA device ordinal that animates vertices (the rendering GPU)."));
+static ConfigVariableBool cuda_skinning_register_outputs
+("cuda-skinning-register-outputs", true,
+ PRC_DESC("Page-lock the animated GeomVertexArrayData buffers (cudaHostRegister) so the kernel stores "
+          "the animated rows straight into them instead of copying device->host afterwards."));
 
 CudaSkinBackend::CudaSkinBackend(void *dso, const p3cs_api *api, p3cs_context ctx) :
   _dso(dso), _api(api), _ctx(ctx), _lock("CudaSkinBackend") {
@@ -87,6 +92,12 @@ get_global_ptr() {
 
 void CudaSkinBackend::
 free_entry(Entry &entry) {
+  for (auto &reg : entry._registered) {
+    if (reg.first != nullptr) {
+      _api->host_unregister(_ctx, reg.first);
+    }
+  }
+  entry._registered.clear();
   if (entry._group != nullptr) {
     _api->group_destroy(entry._group);
   }
@@ -327,8 +338,26 @@ animate_vertices(const GeomVertexData *source, bool force, Thread *current_threa
   pvector<void *> out_pointers;
   for (size_t o = 0; o < entry._out_arrays.size(); ++o) {
     PT(GeomVertexArrayDataHandle) handle = result->modify_array_handle(o);
-    out_pointers.push_back(handle->get_write_pointer());
+    void *pointer = handle->get_write_pointer();
+    out_pointers.push_back(pointer);
     out_handles.push_back(handle);
+    // Page-lock the result's buffer once (again only if Panda reallocated it): the kernel then stores the
+    // animated rows straight into it, no device->host copy.  A failed registration just keeps the copy.
+    if (cuda_skinning_register_outputs) {
+      if (entry._registered.size() <= o) {
+        entry._registered.resize(o + 1, std::make_pair((void *)nullptr, (size_t)0));
+      }
+      size_t bytes = (size_t)handle->get_data_size_bytes();
+      if (entry._registered[o].first != pointer || entry._registered[o].second != bytes) {
+        if (entry._registered[o].first != nullptr) {
+          _api->host_unregister(_ctx, entry._registered[o].first);
+        }
+        entry._registered[o] = std::make_pair((void *)nullptr, (size_t)0);
+        if (bytes > 0 && _api->host_register(_ctx, pointer, bytes) == P3CS_OK) {
+          entry._registered[o] = std::make_pair(pointer, bytes);
+        }
+      }
+    }
   }
   if (_api->animate_vertices(entry._group, 0, entry._palette_values.data(), entry._slider_values.data(),
                              out_pointers.data()) != P3CS_OK) {

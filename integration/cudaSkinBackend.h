@@ -63,6 +63,8 @@ private:
     PT(GeomVertexData) _animated;
     UpdateSeq _animated_modified;
     pvector<float> _palette_values, _slider_values;
+    // result arrays page-locked + mapped (p3cs_host_register) so the kernel stores into them directly
+    pvector<std::pair<void *, size_t> > _registered;
   };
   bool upload(const GeomVertexData *source, Entry &entry, Thread *current_thread);
   void free_entry(Entry &entry);

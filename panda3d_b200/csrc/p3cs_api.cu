@@ -1131,6 +1131,7 @@ extern "C" const p3cs_api *p3cs_get_api(void) {
   static const p3cs_api api = {
       P3CS_API_VERSION,        p3cs_device_count,  p3cs_last_error,        p3cs_context_create, p3cs_context_destroy,
       p3cs_context_sync,       p3cs_mesh_create,   p3cs_mesh_destroy,      p3cs_group_create,   p3cs_group_destroy,
-      p3cs_group_set_palettes, p3cs_group_set_sliders, p3cs_group_animate, p3cs_group_read_output, p3cs_animate_vertices};
+      p3cs_group_set_palettes, p3cs_group_set_sliders, p3cs_group_animate, p3cs_group_read_output, p3cs_animate_vertices,
+      p3cs_host_register,      p3cs_host_unregister, p3cs_animate_groups};
   return &api;
 }

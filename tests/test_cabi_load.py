@@ -27,7 +27,7 @@ def test_header_symbols_all_exported(library):
 
 
 def test_api_version_and_plugin_table(library):
-    assert library.p3cs_api_version() == 1
+    assert library.p3cs_api_version() == 2
     assert library.p3cs_get_api()  # non-NULL table of function pointers (dlsym("p3cs_get_api") convention)
 
 
