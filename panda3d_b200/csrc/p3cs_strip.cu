@@ -25,9 +25,69 @@
 namespace p3cs {
 
 
-// kFastPN24: the egg loader's packed [vertex(3f) normal(3f)] rows (stride 24): the whole row is
-// moved with three conflict-free 64-bit shared-memory accesses each way.
-enum StripMode { kGenericCompact = 0, kGenericFull = 1, kFastP = 2, kFastPN = 3, kFastPNVV = 4, kFastPN24 = 5 };
+// kRow24 / kRow32 / kRow48 / kRow56: the loader's usual row layouts ([vertex normal], + texcoord, + tangent
+// binormal, + both).  The whole row lives in registers and moves between them and the staged tile with the
+// widest shared-memory accesses that are bank-conflict free for that stride: 64-bit when the stride is an odd
+// number of 8-byte units (24, 56), 128-bit when it is an odd number of 16-byte units (48), and for the
+// power-of-two stride 32 two 128-bit accesses whose order alternates every four rows.
+enum StripMode { kGenericCompact = 0, kGenericFull = 1, kFastP = 2, kFastPN = 3, kFastPNVV = 4, kRow24 = 5, kRow32 = 6, kRow48 = 7, kRow56 = 8 };
+
+// Row layouts of the kRow modes, in 32-bit words: row length W, access width VEC, column offsets (-1: absent).
+template <int MODE> struct RowLayout { static constexpr int W = 2, VEC = 2, P = 0, N = -1, T = -1, B = -1; };
+template <> struct RowLayout<kRow24> { static constexpr int W = 6, VEC = 2, P = 0, N = 3, T = -1, B = -1; };
+template <> struct RowLayout<kRow32> { static constexpr int W = 8, VEC = 4, P = 0, N = 3, T = -1, B = -1; };
+template <> struct RowLayout<kRow48> { static constexpr int W = 12, VEC = 4, P = 0, N = 3, T = 6, B = 9; };
+template <> struct RowLayout<kRow56> { static constexpr int W = 14, VEC = 2, P = 0, N = 3, T = 8, B = 11; };
+
+// does the access unit [u*VEC, (u+1)*VEC) of the row hold a word some animated column writes?
+template <class L>
+__device__ __forceinline__ constexpr bool row_unit_dirty(int u) {
+  const int lo = u * L::VEC, hi = lo + L::VEC;
+  return (L::P >= 0 && L::P < hi && L::P + 3 > lo) || (L::N >= 0 && L::N < hi && L::N + 3 > lo) ||
+         (L::T >= 0 && L::T < hi && L::T + 3 > lo) || (L::B >= 0 && L::B < hi && L::B + 3 > lo);
+}
+
+template <class L>
+__device__ __forceinline__ void row_load(const uint8_t *rowp, int trow, float (&r)[L::W]) {
+  if (L::W == 8) {  // stride 32: rows r and r+4 share their banks, so rows 4..7 of every eight start with the upper half
+    const int sel = (trow >> 2) & 1;
+    const float4 a = *reinterpret_cast<const float4 *>(rowp + sel * 16);
+    const float4 b = *reinterpret_cast<const float4 *>(rowp + (sel ^ 1) * 16);
+    const float4 lo = sel ? b : a, hi = sel ? a : b;
+    r[0] = lo.x; r[1] = lo.y; r[2] = lo.z; r[3] = lo.w;
+    r[4] = hi.x; r[5] = hi.y; r[6] = hi.z; r[7] = hi.w;
+  } else if (L::VEC == 4) {
+#pragma unroll
+    for (int u = 0; u < L::W / 4; ++u) {
+      const float4 v = reinterpret_cast<const float4 *>(rowp)[u];
+      r[4 * u] = v.x; r[4 * u + 1] = v.y; r[4 * u + 2] = v.z; r[4 * u + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < L::W / 2; ++u) {
+      const float2 v = reinterpret_cast<const float2 *>(rowp)[u];
+      r[2 * u] = v.x; r[2 * u + 1] = v.y;
+    }
+  }
+}
+
+template <class L>
+__device__ __forceinline__ void row_store(uint8_t *rowp, int trow, const float (&r)[L::W]) {
+  if (L::W == 8) {
+    const int sel = (trow >> 2) & 1;
+    const float4 lo = make_float4(r[0], r[1], r[2], r[3]), hi = make_float4(r[4], r[5], r[6], r[7]);
+    *reinterpret_cast<float4 *>(rowp + sel * 16) = sel ? hi : lo;
+    *reinterpret_cast<float4 *>(rowp + (sel ^ 1) * 16) = sel ? lo : hi;
+  } else if (L::VEC == 4) {
+#pragma unroll
+    for (int u = 0; u < L::W / 4; ++u)
+      if (row_unit_dirty<L>(u)) reinterpret_cast<float4 *>(rowp)[u] = make_float4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+  } else {
+#pragma unroll
+    for (int u = 0; u < L::W / 2; ++u)
+      if (row_unit_dirty<L>(u)) reinterpret_cast<float2 *>(rowp)[u] = make_float2(r[2 * u], r[2 * u + 1]);
+  }
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -265,6 +325,7 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   constexpr int kTileBufs = kRowsPerThread == 1 ? 3 : 2;
   constexpr bool FULL = MODE == kGenericFull;
   constexpr bool FAST = MODE >= kFastP;
+  constexpr bool ROWREG = MODE >= kRow24;  // the row is held in registers (RowLayout<MODE>)
   constexpr int REC = FULL ? kRecFull : kRecCompact;
   const StripSmem lay = strip_layout(mesh);
   float *pal3f = reinterpret_cast<float *>(smem + lay.pal3_off);
@@ -479,16 +540,17 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
               f[2 * i] = v.x;
               f[2 * i + 1] = v.y;
             }
-            if (MODE == kFastPN24) {
-              float2 *rowp = reinterpret_cast<float2 *>(tile + trow * 24);
-              const float2 a = rowp[0], b2 = rowp[1], c = rowp[2];
-              float v[6] = {a.x, a.y, b2.x, b2.y, c.x, c.y};
-              fast_column<1>(v, f);
-              fast_column<3>(v + 3, f);
+            if (ROWREG) {
+              using L = RowLayout<MODE>;
+              uint8_t *rowp = tile + trow * (L::W * 4);
+              float v[L::W];
+              row_load<L>(rowp, trow, v);
+              fast_column<1>(v + L::P, f);
+              if (L::N >= 0) fast_column<3>(v + (L::N >= 0 ? L::N : 0), f);
+              if (L::T >= 0) fast_column<2>(v + (L::T >= 0 ? L::T : 0), f);
+              if (L::B >= 0) fast_column<2>(v + (L::B >= 0 ? L::B : 0), f);
               if (BOUNDS && bounds_off == 0) bounds.add(v[0], v[1], v[2]);  // the vertex column, straight from the registers
-              rowp[0] = make_float2(v[0], v[1]);
-              rowp[1] = make_float2(v[2], v[3]);
-              rowp[2] = make_float2(v[4], v[5]);
+              row_store<L>(rowp, trow, v);
             } else {
               uint8_t *rowp = tile + trow * stride0;
               fast_column<1>(reinterpret_cast<float *>(rowp + mesh.dyn[0].start), f);
@@ -519,7 +581,7 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
 #pragma unroll
         for (int rr = 0; rr < kRowsPerThread; ++rr) {
           const int trow = rr * kStripThreads + tid;
-          const bool in_registers = MODE == kFastPN24 && local[rr] != 0xFFFF && bounds_off == 0;
+          const bool in_registers = ROWREG && local[rr] != 0xFFFF && bounds_off == 0;
           if (t * kTileRows + trow < mesh.num_rows && !in_registers) {
             const float *c = reinterpret_cast<const float *>(tile + bounds_off + (size_t)trow * bounds_stride);
             bounds.add(c[0], c[1], c[2]);
@@ -565,9 +627,18 @@ static int pick_mode(const MeshDev &mesh) {
     if (mesh.dyn[c].num_values != 3 || mesh.dyn[c].f64) return kGenericCompact;
   const DynColumn *d = mesh.dyn;
   if (mesh.num_dyn == 1 && d[0].skin == 1) return kFastP;
-  if (mesh.num_dyn == 2 && d[0].skin == 1 && d[1].skin == 3)
-    return (mesh.stride[0] == 24 && d[0].start == 0 && d[1].start == 12) ? kFastPN24 : kFastPN;
-  if (mesh.num_dyn == 4 && d[0].skin == 1 && d[1].skin == 3 && d[2].skin == 2 && d[3].skin == 2) return kFastPNVV;
+  const int stride = mesh.stride[0];
+  if (mesh.num_dyn == 2 && d[0].skin == 1 && d[1].skin == 3) {
+    if (d[0].start == 0 && d[1].start == 12 && stride == 24) return kRow24;
+    if (d[0].start == 0 && d[1].start == 12 && stride == 32) return kRow32;
+    return kFastPN;
+  }
+  if (mesh.num_dyn == 4 && d[0].skin == 1 && d[1].skin == 3 && d[2].skin == 2 && d[3].skin == 2) {
+    const int t = d[2].start < d[3].start ? d[2].start : d[3].start, b = d[2].start < d[3].start ? d[3].start : d[2].start;
+    if (d[0].start == 0 && d[1].start == 12 && t == 24 && b == 36 && stride == 48) return kRow48;
+    if (d[0].start == 0 && d[1].start == 12 && t == 32 && b == 44 && stride == 56) return kRow56;
+    return kFastPNVV;
+  }
   return kGenericCompact;
 }
 
@@ -644,7 +715,10 @@ int launch_strip(const MeshDev &mesh, const GroupDev &grp, int first_instance, i
     case kFastP: launch_mode<kFastP>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
     case kFastPN: launch_mode<kFastPN>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
     case kFastPNVV: launch_mode<kFastPNVV>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
-    case kFastPN24: launch_mode<kFastPN24>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
+    case kRow24: launch_mode<kRow24>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
+    case kRow32: launch_mode<kRow32>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
+    case kRow48: launch_mode<kRow48>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
+    case kRow56: launch_mode<kRow56>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
     default: launch_mode<kGenericCompact>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
     }
     ++launches;

@@ -113,6 +113,11 @@ SYNTH_CASES = {
     "u32_index": dict(num_rows=70_001, num_transforms=32, num_blends=66_000, index_type="u32"),
     "one_row": dict(num_rows=1, num_transforms=4, num_blends=1),
     "align16": dict(num_rows=4_099, num_transforms=32, num_blends=700, align16=True, tbn=True),
+    "row32_layout": dict(num_rows=7_013, num_transforms=48, num_blends=1500, texcoord=True, index_order="runs"),
+    "row48_layout": dict(num_rows=7_013, num_transforms=48, num_blends=1500, tbn=True, index_order="runs",
+                         rows=[(9, 7000)]),
+    "row32_morphs": dict(num_rows=3_000, num_transforms=16, num_blends=300, texcoord=True, num_sliders=4, slider_band=0.3,
+                         morph_columns=("vertex", "normal")),
     "float64_columns": dict(num_rows=6_001, num_transforms=32, num_blends=900, float64=True, tbn=True, index_order="runs",
                             num_sliders=6, slider_band=0.2, morph_columns=("vertex", "normal")),
     "float64_align16": dict(num_rows=3_001, num_transforms=16, num_blends=500, float64=True, align16=True,

@@ -70,6 +70,12 @@ def main():
             small = False
             if name == "c3":
                 specs = [(synth.config_c3_mesh().flat, args.instances)]
+            elif name == "c3uv":   # the C3 character with a texcoord column: stride 32, the egg loader's usual layout
+                specs = [(synth.make_mesh(20_000, 128, 4096, seed=33, texcoord=True, index_order="runs").flat, args.instances)]
+            elif name == "c3tb":   # ... with tangent + binormal, no texcoord: stride 48
+                specs = [(synth.make_mesh(20_000, 128, 4096, seed=33, tbn=True, index_order="runs").flat, args.instances)]
+            elif name == "c3tbuv":  # ... with texcoord, tangent, binormal: stride 56 (the C5 layout)
+                specs = [(synth.make_mesh(20_000, 128, 4096, seed=33, tbn=True, texcoord=True, index_order="runs").flat, args.instances)]
             elif name == "c2r":
                 specs, small = [(synth.config_c2("random").flat, 1)], True
             elif name == "c2s":
