@@ -416,7 +416,7 @@ def run_gpu_arm(args):
         # parity-test cases, not bench lines -- reported so the single-mesh latencies sit next to the crowd number
         others = None
         if world == 1 and not args.no_configs:
-            others = other_configs(torch, ctx, stream, _capi, synth)
+            others = other_configs(torch, ctx, stream, _capi, synth, args.instances, hbm_peak()[0])
 
     total_verts = float(sum_over_ranks(float(n_local * flat.skinned_rows())))
     value = total_verts / (ms * 1e-3)
@@ -424,11 +424,7 @@ def run_gpu_arm(args):
     h2d_total, d2h_total = int(sum_over_ranks(float(h2d))), int(sum_over_ranks(float(d2h)))
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
-        else:
-            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        peak, peak_src = hbm_peak()
         # dominant (only) kernel = strip_kernel: one launch per step.  Algorithmic bytes of an instanced
         # crowd: the source mesh and its tables are shared by all instances and
         # served from L2, so the compulsory HBM traffic per instance is its output rows (stride bytes per
@@ -443,7 +439,7 @@ def run_gpu_arm(args):
             pj = json.load(open(prof))
             if pj.get("instances") == n_local:
                 traffic = pj.get("dram_bytes_per_launch")
-        roofline = {"bound": "hbm", "kernel": "p3cs::strip_kernel<kFastPN24>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": "p3cs::strip_kernel<kRow24>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic, "peak_source": peak_src,
                     "launches_per_step": skin_launches, "avg_launch_ms": 1e3 * skin_s / max(1, skin_launches),
                     "algorithmic_bytes_per_launch": alg_bytes_per_step,
@@ -475,7 +471,14 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
-def other_configs(torch, ctx, stream, _capi, synth):
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def other_configs(torch, ctx, stream, _capi, synth, instances, peak_gbs):
     """Device time per animate call of configs[1], [3], [4] (C2 single mesh, C4 morph mesh, C5 mixed crowd), L2
     flushed between calls (a 256 MB buffer is rewritten), CUDA events on the launch stream."""
     flush = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")
@@ -486,6 +489,10 @@ def other_configs(torch, ctx, stream, _capi, synth):
         "c4_250k_morph_mesh": [(synth.config_c4().flat, 1)],
         "c5_mixed_crowd_2M": [(m.flat, n) for m, n in synth.config_c5_meshes()],
     }
+    # the same crowd with the loader's full row layout (vertex normal texcoord tangent binormal, stride 56):
+    # 2.3x the bytes per vertex, where the kernel IS bound by HBM
+    specs["c3_crowd_stride56_pos_normal_uv_tangent_binormal"] = [
+        (synth.make_mesh(20_000, 128, 4096, seed=33, tbn=True, texcoord=True, index_order="runs").flat, instances)]
     for name, spec in specs.items():
         meshes, groups, verts = [], [], 0
         for i, (fm, n) in enumerate(spec):
@@ -509,8 +516,10 @@ def other_configs(torch, ctx, stream, _capi, synth):
             stream.synchronize()
             total += e0.elapsed_time(e1)
         us = total / reps * 1e3
+        alg = sum(g.n * (g.mesh.num_rows * sum(g.mesh.out_strides) + g.mesh.flat.num_transforms * 64) for g in groups)
         out[name] = {"us_per_call": us, "vertices": verts, "vertices_per_s": verts / (us * 1e-6),
-                     "launches": int(sum(g.timings().launches for g in groups))}
+                     "launches": int(sum(g.timings().launches for g in groups)),
+                     "crowd_algorithmic_gbs": alg / (us * 1e-6) / 1e9, "frac_of_hbm_peak": alg / (us * 1e-6) / 1e9 / peak_gbs}
         for g in groups:
             g.close()
         for dm in meshes:
