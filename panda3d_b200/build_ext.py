@@ -13,14 +13,18 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libp3cudaskin.so")
-SOURCES = ["p3cs_api.cu", "p3cs_kernels.cu", "p3cs_strip.cu", "p3cs_pose.cu"]
-HEADERS = ["p3cs_kernels.cuh", "p3cs_math.cuh", "p3cs_device.cuh", os.path.join("..", "..", "include", "p3cudaskin.h")]
+SOURCES = ["p3cs_api.cu", "p3cs_kernels.cu", "p3cs_pose.cu", "p3cs_strip.cu",
+           "p3cs_strip_inst_a.cu", "p3cs_strip_inst_b.cu", "p3cs_strip_inst_c.cu", "p3cs_strip_inst_d.cu"]
+HEADERS = ["p3cs_kernels.cuh", "p3cs_math.cuh", "p3cs_device.cuh", "p3cs_strip.cuh",
+           os.path.join("..", "..", "include", "p3cudaskin.h")]
+OBJ_DIR = os.path.join(HERE, "_obj")   # git-ignored and gpurun-ignored: only the .so travels
 
-NVCC_FLAGS = [
+COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
-    "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xfatbin", "-compress-all",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-Xcompiler", "-fPIC"]
 
 
 def nvcc_path() -> str:
@@ -39,16 +43,32 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles every translation unit in parallel (the strip kernel's modes are spread over several), then links."""
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = nvcc_path()
+
+    def compile_one(src: str):
+        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + COMPILE_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        return obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    failed = [r for _, r in results if r.returncode != 0]
+    if failed:
+        for r in failed:
+            sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building libp3cudaskin.so")
     if verbose:
-        sys.stderr.write(res.stderr)
+        for _, r in results:
+            sys.stderr.write(r.stderr)
+    res = subprocess.run([nvcc] + LINK_FLAGS + ["-o", LIB] + [o for o, _ in results], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed linking libp3cudaskin.so")
     return LIB
 
 
