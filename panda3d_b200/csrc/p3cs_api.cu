@@ -401,34 +401,78 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
       std::vector<uint16_t> local(std::max(N, 1), 0xFFFFu);
       std::vector<int> rec_off(1, 0), rec_blend, ent_off(1, 0), tile_off(1, 0);
       std::vector<uint2> ent;
-      std::vector<int> stamp(std::max(d->num_blends, 1), -1), slot(std::max(d->num_blends, 1), 0);
-      int ng = 0, max_rec = 0, count = 0;
+      std::vector<int> in_group(std::max(d->num_blends, 1), -1), seen_in_tile(std::max(d->num_blends, 1), -1),
+          slot(std::max(d->num_blends, 1), 0);
+      int ng = 0, max_rec = 0;
+      std::vector<int> open;   // distinct blends of the open group, first-seen order
       std::vector<int> fresh;  // blends first seen in the tile being added
-      for (int t = 0; t < nt; ++t) {
-        const int r0 = t * kTileRows, r1 = std::min(N, r0 + kTileRows);
-        // distinct blends this tile would add to the open group
-        fresh.clear();
-        for (int r = r0; r < r1; ++r) {
-          if (!full && !((mask[r >> 5] >> (r & 31)) & 1u)) continue;
-          const int b = (int)(wide ? idx32[r] : idx16[r]);
-          if (stamp[b] != ng && stamp[b] != -2 - ng) {
-            stamp[b] = -2 - ng;  // tentatively seen
-            fresh.push_back(b);
+      auto row_live = [&](int r) { return full || ((mask[r >> 5] >> (r & 31)) & 1u); };
+      auto row_blend = [&](int r) { return (int)(wide ? idx32[r] : idx16[r]); };
+
+      // Order of the records inside a group.  Phase A runs one thread per record and gathers the record's
+      // first four palette matrices with 128-bit shared-memory loads, eight lanes per wavefront; two lanes
+      // collide when their joints differ but agree modulo 8 (48-byte palette rows).  The order of a group's
+      // records is free (rows address them through their slot), so they are packed first-fit into
+      // eight-lane cells whose k-th joints are pairwise distinct modulo 8 (or equal: a broadcast).
+      auto pack_group = [&](std::vector<int> &blends) {
+        const int n = (int)blends.size();
+        const int cells = (n + 7) / 8;
+        std::vector<int> occ((size_t)cells * 32, -1), fill(cells, 0), cell_of(n, -1);
+        std::vector<int> leftover;
+        int first_open = 0;
+        for (int i = 0; i < n; ++i) {
+          const int b = blends[i];
+          const int e0 = d->blend_offsets[b], cnt = std::min(4, d->blend_offsets[b + 1] - e0);
+          int placed = -1;
+          for (int c = first_open; c < cells && placed < 0; ++c) {
+            if (fill[c] >= 8) continue;
+            bool ok = true;
+            for (int k = 0; k < cnt && ok; ++k) {
+              const int j = d->blend_transform[e0 + k];
+              const int o = occ[(size_t)c * 32 + k * 8 + (j & 7)];
+              ok = o < 0 || o == j;
+            }
+            if (ok) placed = c;
           }
+          if (placed < 0) {
+            leftover.push_back(i);
+            continue;
+          }
+          for (int k = 0; k < cnt; ++k) {
+            const int j = d->blend_transform[e0 + k];
+            occ[(size_t)placed * 32 + k * 8 + (j & 7)] = j;
+          }
+          cell_of[i] = placed;
+          ++fill[placed];
+          while (first_open < cells && fill[first_open] >= 8) ++first_open;
         }
-        if (tile_off.back() != t && count + (int)fresh.size() > cap) {  // close the group before this tile
-          for (int b : fresh) stamp[b] = -1;
-          rec_off.push_back(rec_off.back() + count);
-          max_rec = std::max(max_rec, count);
-          tile_off.push_back(t);
-          ++ng;
-          count = 0;
-          --t;  // redo this tile in the new group
-          continue;
+        int c = 0;
+        for (int i : leftover) {  // whatever did not fit conflict-free fills the remaining lanes
+          while (fill[c] >= 8) ++c;
+          cell_of[i] = c;
+          ++fill[c];
         }
-        for (int b : fresh) {
-          stamp[b] = ng;
-          slot[b] = count++;
+        // dense positions: cells in order; only the last cell may be short, so move its surplus forward
+        std::vector<std::vector<int>> by_cell(cells);
+        for (int i = 0; i < n; ++i) by_cell[cell_of[i]].push_back(blends[i]);
+        for (int cc = 0; cc + 1 < cells; ++cc)
+          while ((int)by_cell[cc].size() < 8) {
+            int donor = cells - 1;
+            while (donor > cc && by_cell[donor].empty()) --donor;
+            if (donor == cc) break;
+            by_cell[cc].push_back(by_cell[donor].back());
+            by_cell[donor].pop_back();
+          }
+        blends.clear();
+        for (auto &v : by_cell) blends.insert(blends.end(), v.begin(), v.end());
+      };
+
+      auto close_group = [&](int t_end) {
+        pack_group(open);
+        const int n = (int)open.size();
+        for (int p = 0; p < n; ++p) {
+          const int b = open[p];
+          slot[b] = p;
           rec_blend.push_back(b);
           for (int e = d->blend_offsets[b]; e < d->blend_offsets[b + 1]; ++e) {
             uint32_t wbits;
@@ -437,17 +481,39 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
           }
           ent_off.push_back((int)ent.size());
         }
+        const int r0 = tile_off.back() * kTileRows, r1 = std::min(N, t_end * kTileRows);
+        for (int r = r0; r < r1; ++r)
+          if (row_live(r)) local[r] = (uint16_t)slot[row_blend(r)];
+        rec_off.push_back(rec_off.back() + n);
+        max_rec = std::max(max_rec, n);
+        tile_off.push_back(t_end);
+        ++ng;
+        open.clear();
+      };
+
+      for (int t = 0; t < nt; ++t) {
+        const int r0 = t * kTileRows, r1 = std::min(N, r0 + kTileRows);
+        fresh.clear();  // distinct blends this tile would add to the open group
         for (int r = r0; r < r1; ++r) {
-          if (!full && !((mask[r >> 5] >> (r & 31)) & 1u)) continue;
-          local[r] = (uint16_t)slot[(int)(wide ? idx32[r] : idx16[r])];
+          if (!row_live(r)) continue;
+          const int b = row_blend(r);
+          if (in_group[b] != ng && seen_in_tile[b] != t) {
+            seen_in_tile[b] = t;
+            fresh.push_back(b);
+          }
+        }
+        if (tile_off.back() != t && (int)open.size() + (int)fresh.size() > cap) {  // close the group before this tile
+          close_group(t);
+          for (int b : fresh) seen_in_tile[b] = -1;
+          --t;  // redo this tile in the new group
+          continue;
+        }
+        for (int b : fresh) {
+          in_group[b] = ng;
+          open.push_back(b);
         }
       }
-      if (nt > 0) {
-        rec_off.push_back(rec_off.back() + count);
-        max_rec = std::max(max_rec, count);
-        tile_off.push_back(nt);
-        ++ng;
-      }
+      if (nt > 0) close_group(nt);
       if ((rc = upload<int>(mesh, tile_off.data(), tile_off.size(), &m.group_tile_offsets)) != P3CS_OK) return bail(rc);
       m.num_groups = ng;
       m.max_group_records = max_rec;
