@@ -381,14 +381,36 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
           return bail(fail(P3CS_ERR_INVALID, "row %d selects blend %u but the table has %d blends", r, v, d->num_blends));
         if (!full) mask[r >> 5] |= 1u << (r & 31);
       }
-    // ---- tile size: two rows per thread (512-row tiles) halve the per-tile bookkeeping, as long as
-    // the bigger staged tiles still leave room for four CTAs per SM
+    // ---- shared-memory plan of the strip kernel.  Four CTAs per SM (the register-file limit) need <= ~55 KB each:
+    // palette + records + staged tiles.  Preference: two rows per thread (512-row tiles halve the per-tile
+    // bookkeeping), else 256-row tiles with three, then two buffers, then a smaller record group.
     {
       size_t slice = 0;
       for (int o = 0; o < m.num_outputs; ++o) slice += round_up((size_t)32 * m.stride[o], 128);
       const size_t rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
-      const size_t est = (size_t)d->num_transforms * 64 + (size_t)kStripThreads * rec_bytes + 2 * 16 * slice;
-      m.rows_per_thread = (!m.full_records && est <= 56 * 1024) ? 2 : 1;
+      const size_t fixed = 32 + (size_t)d->num_transforms * 64 + 128;
+      const size_t budget = 55 * 1024;
+      const int full_cap = std::min(kStripThreads, (int)((32 * 1024) / rec_bytes));  // one phase-A pass: a thread per record
+      auto fits = [&](int r, int bufs, int cap) { return fixed + (size_t)cap * rec_bytes + (size_t)bufs * 8 * r * slice <= budget; };
+      m.rows_per_thread = 1;
+      m.tile_bufs = 3;
+      m.group_record_cap = full_cap;
+      if (!m.full_records) {
+        if (fits(2, 2, full_cap)) {
+          m.rows_per_thread = 2;
+          m.tile_bufs = 2;
+        } else if (fits(1, 3, full_cap)) {
+        } else if (fits(1, 2, full_cap)) {
+          m.tile_bufs = 2;
+        } else {
+          int cap = full_cap;
+          while (cap > 128 && !fits(1, 2, cap)) cap -= 8;
+          if (fits(1, 2, cap)) {
+            m.tile_bufs = 2;
+            m.group_record_cap = cap;
+          }
+        }
+      }
     }
     const int kTileRows = kStripThreads * m.rows_per_thread;
     // ---- strip-kernel tables: per record group the distinct blends, per row its slot in that list.
@@ -397,7 +419,7 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
     {
       const int nt = (N + kTileRows - 1) / kTileRows;
       const int rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
-      const int cap = std::min(kStripThreads, (32 * 1024) / rec_bytes);  // one phase-A pass: a thread per record
+      const int cap = m.group_record_cap;
       std::vector<uint16_t> local(std::max(N, 1), 0xFFFFu);
       std::vector<int> rec_off(1, 0), rec_blend, ent_off(1, 0), tile_off(1, 0);
       std::vector<uint2> ent;
@@ -622,6 +644,7 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
   }
   // ---- slice geometry of the strip kernel (a slice = the 32 rows one warp stages at a time)
   if (m.rows_per_thread == 0) m.rows_per_thread = 1;
+  if (m.tile_bufs == 0) m.tile_bufs = 3;
   m.num_tiles = (N + kStripThreads * m.rows_per_thread - 1) / (kStripThreads * m.rows_per_thread);
   m.slice_bytes = 0;
   for (int o = 0; o < m.num_outputs; ++o) {

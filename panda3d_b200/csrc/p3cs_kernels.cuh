@@ -54,6 +54,8 @@ struct MeshDev {
   // every row stores the index of its blend in that list.
   int num_tiles;
   int rows_per_thread;              // 1 or 2: rows a thread animates per staged tile (tile = 256 or 512 rows)
+  int tile_bufs;                    // 2 or 3 staged tiles in flight per CTA
+  int group_record_cap;             // most records a record group may hold (sizes the shared-memory record area)
   const int *group_tile_offsets;    // num_groups+1: group g covers tiles [off[g], off[g+1])
   int num_groups;
   int max_group_records;            // max distinct blends of any group (smem sizing)

@@ -141,8 +141,8 @@ __host__ __device__ inline StripSmem strip_layout(const MeshDev &m) {
   const int rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
   const int recs_bytes = m.max_group_records * rec_bytes > 256 ? m.max_group_records * rec_bytes : 256;  // >= the bounds scratch
   s.tiles_off = (s.records_off + recs_bytes + 127) & ~127;
-  // staged tiles (contiguous 32-row slices): 3 in flight for 256-row tiles, 2 for 512-row tiles
-  s.total = s.tiles_off + (m.rows_per_thread == 1 ? 3 : 2) * (kStripThreads * m.rows_per_thread / 32) * m.slice_bytes;
+  // staged tiles (contiguous 32-row slices), tile_bufs of them in flight
+  s.total = s.tiles_off + m.tile_bufs * (kStripThreads * m.rows_per_thread / 32) * m.slice_bytes;
   return s;
 }
 
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   constexpr bool BOUNDS = AUX == 2;
   constexpr int kTileRows = kStripThreads * kRowsPerThread;
   constexpr int kSlicesPerTile = kTileRows / 32;
-  constexpr int kTileBufs = kRowsPerThread == 1 ? 3 : 2;
+  const int kTileBufs = kRowsPerThread == 2 ? 2 : mesh.tile_bufs;  // 512-row tiles: always 2; else the host's plan (2 or 3)
   constexpr bool FULL = MODE == kGenericFull;
   constexpr bool FAST = MODE >= kFastP;
   constexpr bool ROWREG = MODE >= kRow24;  // the row is held in registers (RowLayout<MODE>)
