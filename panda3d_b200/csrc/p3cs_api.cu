@@ -475,18 +475,37 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
           ++fill[c];
         }
         // dense positions: cells in order; only the last cell may be short, so move its surplus forward
-        std::vector<std::vector<int>> by_cell(cells);
-        for (int i = 0; i < n; ++i) by_cell[cell_of[i]].push_back(blends[i]);
-        for (int cc = 0; cc + 1 < cells; ++cc)
-          while ((int)by_cell[cc].size() < 8) {
-            int donor = cells - 1;
-            while (donor > cc && by_cell[donor].empty()) --donor;
-            if (donor == cc) break;
-            by_cell[cc].push_back(by_cell[donor].back());
-            by_cell[donor].pop_back();
+        std::vector<int> count_in(cells, 0);
+        for (int i = 0; i < n; ++i) ++count_in[cell_of[i]];
+        for (int cc = 0, donor = cells - 1; cc < donor; ++cc)
+          while (count_in[cc] < 8 && cc < donor) {
+            if (count_in[donor] == 0) { --donor; continue; }
+            for (int i = n - 1; i >= 0; --i)
+              if (cell_of[i] == donor) { cell_of[i] = cc; break; }
+            --count_in[donor];
+            ++count_in[cc];
           }
-        blends.clear();
-        for (auto &v : by_cell) blends.insert(blends.end(), v.begin(), v.end());
+        // Lane inside the cell.  Phase B reads a row's record with 64-bit loads, sixteen rows per wavefront; the
+        // records of neighbouring runs (adjacent in first-seen order) collide there when their slots agree
+        // modulo 16, so each record takes a free lane whose slot differs from its two predecessors' modulo 16.
+        std::vector<int> slot_of(n, -1);
+        std::vector<uint8_t> used((size_t)cells, 0);
+        for (int i = 0; i < n; ++i) {
+          const int c = cell_of[i];
+          int best = -1;
+          for (int pass = 0; pass < 2 && best < 0; ++pass)
+            for (int p = 0; p < count_in[c]; ++p) {
+              if ((used[c] >> p) & 1) continue;
+              const int sl = 8 * c + p;
+              const bool clash = (i >= 1 && ((slot_of[i - 1] ^ sl) & 15) == 0) || (i >= 2 && ((slot_of[i - 2] ^ sl) & 15) == 0);
+              if (pass == 1 || !clash) { best = p; break; }
+            }
+          used[c] |= (uint8_t)(1u << best);
+          slot_of[i] = 8 * c + best;
+        }
+        std::vector<int> ordered(n);
+        for (int i = 0; i < n; ++i) ordered[slot_of[i]] = blends[i];
+        blends.swap(ordered);
       };
 
       auto close_group = [&](int t_end) {
