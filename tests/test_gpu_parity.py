@@ -596,3 +596,54 @@ def test_registered_host_outputs_are_written_directly(gpu_ctx):
         gpu_ctx.host_unregister(guard)
         grp.close()
         dmesh.close()
+
+
+@pytest.mark.gpu
+def test_edge_sizes(gpu_ctx):
+    """Sizes at the edges of the launch geometry: an empty vertex data, a single instance of a mesh smaller than a
+    warp, a palette too large for shared memory (automatic two-kernel path), more instances than one grid
+    dimension holds (70 000 > 65 535), and TransformBlendTable::get_rows() empty."""
+    # (a) zero rows
+    sm = synth.make_mesh(8, 2, 2, seed=1)
+    empty = F.FlatMesh(**{**sm.flat.__dict__})
+    empty.num_rows = 0
+    empty.arrays = [a[:0] for a in sm.flat.arrays]
+    empty.row_ranges = np.zeros((0, 2), np.int32)
+    dmesh = _capi.Mesh(gpu_ctx, empty)
+    grp = _capi.Group(dmesh, 2)
+    grp.set_palettes(synth.make_palettes(2, 2, 3).reshape(2, -1))
+    grp.animate()
+    assert grp.read_output(0).shape == (2, 0, empty.strides[0])
+    grp.close(); dmesh.close()
+    # (b) 5 rows
+    sm = synth.make_mesh(5, 3, 4, seed=2)
+    assert _check_against_oracle(gpu_ctx, sm.flat, synth.make_palettes(3, 1, 4)[0], None, what="5 rows") >= 0
+    # (c) 4000 joints: 256 KB of palette cannot be staged in shared memory
+    sm = synth.make_mesh(6_000, 4000, 5000, seed=3, index_order="runs")
+    assert _check_against_oracle(gpu_ctx, sm.flat, synth.make_palettes(4000, 1, 5)[0], None, what="4000 joints") >= 0
+    # (d) 70 000 instances of a 40-row mesh: two launches (grid.y <= 65535); spot-check both halves
+    sm = synth.make_mesh(40, 6, 10, seed=6)
+    mesh = sm.flat
+    n = 70_000
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, n)
+    try:
+        base = synth.make_palettes(6, 50, 7).reshape(50, -1)
+        grp.set_palettes(np.tile(base, (n // 50, 1)))
+        grp.enable_bounds()
+        grp.animate()
+        om = oracle.OracleMesh(mesh)
+        for i in (0, 49, 65_534, 65_535, 65_536, n - 1):
+            expect, _, _ = om.animate(base[i % 50])
+            got = grp.read_output(0, i, 1)[0]
+            compare_outputs(mesh, [got], expect, f"instance {i}")
+            assert np.array_equal(grp.read_bounds(i, 1)[0], _expected_bounds(got, mesh.skin_columns[0]))
+        assert grp.timings().launches >= 2
+    finally:
+        grp.close()
+        dmesh.close()
+    # (e) a blend table whose rows set is empty: plain copy
+    sm = synth.make_mesh(300, 4, 8, seed=8)
+    mesh = F.FlatMesh(**{**sm.flat.__dict__})
+    mesh.row_ranges = np.zeros((0, 2), np.int32)
+    assert _check_against_oracle(gpu_ctx, mesh, synth.make_palettes(4, 1, 9)[0], None, what="empty rows") == 0
