@@ -215,6 +215,20 @@ P3CS_EXPORT int p3cs_device_read(p3cs_context ctx, const void *device_src, void 
 P3CS_EXPORT int p3cs_ipc_export(p3cs_context ctx, void *ptr, unsigned char handle[64]);
 P3CS_EXPORT int p3cs_ipc_open(p3cs_context ctx, const unsigned char handle[64], void **out);
 P3CS_EXPORT int p3cs_ipc_close(p3cs_context ctx, void *ptr);
+
+/* ---- "next" row f2: zero-copy hand-off to the renderer ------
+ * Today the animated array goes host -> GL every frame (glBufferData / glBufferSubData,
+ * glstuff/glGraphicsStateGuardian_src.cxx:7150-7215, driven by the array's _modified stamp,
+ * gobj/geomVertexArrayData.cxx:601-606).  p3cs_shareable_alloc returns device memory together with a POSIX
+ * file descriptor the renderer imports as its vertex buffer (Vulkan VK_KHR_external_memory_fd, OpenGL
+ * GL_EXT_memory_object_fd: glImportMemoryFdEXT + glNamedBufferStorageMemEXT); passed as
+ * p3cs_group_buffers::outputs, the animated rows are born inside that buffer.  *allocated_bytes is the size
+ * the importer must quote (bytes rounded up to the allocation granularity).  The caller owns the fd
+ * (close() it once imported).  p3cs_shareable_import is the CUDA-side import of such an fd (another
+ * process or context; also what the tests use to play the renderer). */
+P3CS_EXPORT int p3cs_shareable_alloc(p3cs_context ctx, size_t bytes, void **out_ptr, int *out_fd, size_t *allocated_bytes);
+P3CS_EXPORT int p3cs_shareable_import(p3cs_context ctx, int fd, size_t allocated_bytes, void **out_ptr);
+P3CS_EXPORT int p3cs_shareable_free(p3cs_context ctx, void *ptr);
 /* The cudaStream_t of the context (for CUDA-event timing by the caller). */
 P3CS_EXPORT void *p3cs_context_stream(p3cs_context ctx);
 

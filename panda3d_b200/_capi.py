@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "p3cs_skeleton_create", "p3cs_skeleton_destroy", "p3cs_group_pose", "p3cs_group_read_palettes",
     "p3cs_group_enable_bounds", "p3cs_group_read_bounds", "p3cs_animate_groups",
     "p3cs_host_register", "p3cs_host_unregister",
+    "p3cs_shareable_alloc", "p3cs_shareable_import", "p3cs_shareable_free",
 ]
 
 
@@ -143,6 +144,9 @@ def lib():
         L.p3cs_animate_groups.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         L.p3cs_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.p3cs_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
+        L.p3cs_shareable_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+        L.p3cs_shareable_import.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.p3cs_shareable_free.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -199,6 +203,21 @@ class Context:
         buf = (C.c_ubyte * 64)()
         _check(lib().p3cs_ipc_export(self.handle, ptr, buf))
         return bytes(buf)
+
+    # ---- "next" row f2: memory a renderer can import through a POSIX fd
+    def shareable_alloc(self, nbytes: int):
+        """Returns (device pointer, fd, allocated bytes)."""
+        p, fd, size = C.c_void_p(), C.c_int(-1), C.c_size_t(0)
+        _check(lib().p3cs_shareable_alloc(self.handle, nbytes, C.byref(p), C.byref(fd), C.byref(size)))
+        return int(p.value), int(fd.value), int(size.value)
+
+    def shareable_import(self, fd: int, allocated_bytes: int) -> int:
+        p = C.c_void_p()
+        _check(lib().p3cs_shareable_import(self.handle, fd, allocated_bytes, C.byref(p)))
+        return int(p.value)
+
+    def shareable_free(self, ptr: int) -> None:
+        _check(lib().p3cs_shareable_free(self.handle, ptr))
 
     def host_register(self, array: np.ndarray) -> None:
         """Page-locks + maps a numpy buffer so p3cs_animate_vertices can store into it directly."""

@@ -7,6 +7,8 @@ Bars (BASELINE.json north_star): blend-index / row selection bit-exact; float32 
 FMA contraction, so in practice every byte matches except through the sinf/cosf/atan2f of the
 uniform-scale normal branch; the tests assert the contract and report the max-abs error.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -647,3 +649,44 @@ def test_edge_sizes(gpu_ctx):
     mesh = F.FlatMesh(**{**sm.flat.__dict__})
     mesh.row_ranges = np.zeros((0, 2), np.int32)
     assert _check_against_oracle(gpu_ctx, mesh, synth.make_palettes(4, 1, 9)[0], None, what="empty rows") == 0
+
+
+@pytest.mark.gpu
+def test_shareable_output_reaches_another_process(gpu_ctx):
+    """f2: the group animates straight into memory exported as a POSIX fd; a second process (the "renderer",
+    tests/renderer_import_helper.py) imports the fd and finds the same bytes the oracle-checked copy path returns."""
+    import hashlib
+    import subprocess
+    import sys
+    sm = synth.make_mesh(5_000, 24, 600, seed=111, texcoord=True, index_order="runs")
+    mesh = sm.flat
+    n = 3
+    pal = synth.make_palettes(24, n, 112).reshape(n, -1)
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    plain = _capi.Group(dmesh, n)
+    pitch = plain.output_pitch(0)
+    ptr, fd, allocated = gpu_ctx.shareable_alloc(n * pitch)
+    shared = _capi.Group(dmesh, n, outputs_dev=[ptr])
+    try:
+        assert allocated >= n * pitch and fd >= 0
+        for g in (plain, shared):
+            g.set_palettes(pal)
+            g.animate()
+        expect = plain.read_output(0)
+        got = shared.read_output(0)
+        assert np.array_equal(got, expect)
+        oracle_out, _, _ = oracle.animate(mesh, pal[1].reshape(-1, 16))
+        compare_outputs(mesh, [got[1]], oracle_out, "shareable output, instance 1")
+        gpu_ctx.sync()
+        mine = hashlib.sha256(bytes(gpu_ctx.device_read(ptr, n * pitch))).hexdigest()
+        helper = os.path.join(os.path.dirname(os.path.abspath(__file__)), "renderer_import_helper.py")
+        res = subprocess.run([sys.executable, helper, str(fd), str(allocated), str(n * pitch)], pass_fds=[fd],
+                             capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        assert res.stdout.strip().splitlines()[-1] == mine, "the importing process sees different bytes"
+    finally:
+        shared.close()
+        plain.close()
+        dmesh.close()
+        gpu_ctx.shareable_free(ptr)
+        os.close(fd)
