@@ -275,10 +275,8 @@ def run_gpu_arm(args):
         h2d = n_local * T * 64
         d2h = n_local * rows * stride
 
-        def e2e_step():
-            grp.set_palettes_ptr(pal_host.data_ptr(), 0, n_local)
-            grp.animate()
-            grp.read_output_ptr(0, 0, n_local, out_host.data_ptr())
+        def e2e_step():   # p3cs_group_animate_host: upload / kernels / download pipelined in chunks of instances
+            grp.animate_host_ptr(pal_host.data_ptr(), None, [out_host.data_ptr()])
             ctx.sync()
 
         e2e_step()

@@ -312,6 +312,14 @@ P3CS_EXPORT int p3cs_group_last_timings(p3cs_group group, p3cs_timings *out);
 P3CS_EXPORT int p3cs_animate_vertices(p3cs_group group, int instance,
                                       const float *host_palette, const float *host_sliders,
                                       void *const *host_outputs);
+/* The same for a whole crowd: host palettes (n * T * 16 floats) and sliders (n * S floats, may be NULL) in,
+ * host_outputs[i] (n * rows * stride bytes, tightly packed; entries or the array may be NULL) out, for all n
+ * instances of the group.  Uploads, kernels and downloads are software-pipelined in chunks of
+ * `chunk_instances` instances (<= 0: chosen by the library) over three streams, so after the first chunk the
+ * PCIe download never waits.  Asynchronous with respect to the host: follow with p3cs_context_sync.  Host
+ * buffers should be page-locked (cudaHostAlloc / p3cs_host_register) or the copies serialise. */
+P3CS_EXPORT int p3cs_group_animate_host(p3cs_group group, const float *host_palettes, const float *host_sliders,
+                                        void *const *host_outputs, int chunk_instances);
 /* Page-locks and device-maps a host buffer (e.g. the result GeomVertexArrayData's VertexDataBuffer, once, as
  * long as it is not reallocated).  When every host_outputs[i] of p3cs_animate_vertices is such a buffer, 16-byte
  * aligned with rows*stride a multiple of 16, the kernel stores the animated rows straight into it over PCIe

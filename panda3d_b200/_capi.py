@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "p3cs_skeleton_create", "p3cs_skeleton_destroy", "p3cs_group_pose", "p3cs_group_read_palettes",
     "p3cs_group_enable_bounds", "p3cs_group_read_bounds", "p3cs_animate_groups",
     "p3cs_host_register", "p3cs_host_unregister",
-    "p3cs_shareable_alloc", "p3cs_shareable_import", "p3cs_shareable_free",
+    "p3cs_shareable_alloc", "p3cs_shareable_import", "p3cs_shareable_free", "p3cs_group_animate_host",
 ]
 
 
@@ -147,6 +147,7 @@ def lib():
         L.p3cs_shareable_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
         L.p3cs_shareable_import.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
         L.p3cs_shareable_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.p3cs_group_animate_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int]
         _lib = L
     return _lib
 
@@ -442,6 +443,20 @@ class Group:
         ptrs = (C.c_void_p * max(1, len(outs)))(*[o.ctypes.data for o in outs])
         _check(lib().p3cs_animate_vertices(self.handle, instance, pal.ctypes.data,
                                            sl.ctypes.data if sl is not None else None, ptrs))
+        return outs
+
+    def animate_host_ptr(self, palettes_ptr: int, sliders_ptr: Optional[int], output_ptrs: List[int], chunk: int = 0) -> None:
+        """p3cs_group_animate_host on raw host pointers (page-locked for full overlap); asynchronous."""
+        outs = (C.c_void_p * max(1, len(output_ptrs)))(*output_ptrs)
+        _check(lib().p3cs_group_animate_host(self.handle, palettes_ptr, sliders_ptr, outs, chunk))
+
+    def animate_host(self, palettes: np.ndarray, sliders: Optional[np.ndarray] = None, chunk: int = 0) -> List[np.ndarray]:
+        """The crowd form of animate_vertices: every instance, host buffers in and out, pipelined; synchronous."""
+        pal = np.ascontiguousarray(palettes, np.float32)
+        sl = np.ascontiguousarray(sliders, np.float32) if sliders is not None else None
+        outs = [np.empty((self.n, self.mesh.num_rows, s), np.uint8) for s in self.mesh.out_strides]
+        self.animate_host_ptr(pal.ctypes.data, sl.ctypes.data if sl is not None else None, [o.ctypes.data for o in outs], chunk)
+        self.mesh.ctx.sync()
         return outs
 
     def close(self) -> None:

@@ -53,6 +53,7 @@ struct p3cs_context_s {
   cudaStream_t side[kSideStreams] = {nullptr, nullptr, nullptr};
   cudaEvent_t fork_ev = nullptr;
   cudaEvent_t join_ev[kSideStreams] = {nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> pipe_ev;  // chunk hand-off events of p3cs_group_animate_host
 };
 
 struct p3cs_mesh_s {
@@ -169,6 +170,7 @@ extern "C" int p3cs_context_destroy(p3cs_context ctx) {
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   for (auto e : ctx->join_ev)
     if (e) cudaEventDestroy(e);
+  for (auto e : ctx->pipe_ev) cudaEventDestroy(e);
   delete ctx;
   return P3CS_OK;
 }
@@ -1061,6 +1063,80 @@ extern "C" int p3cs_group_animate(p3cs_group grp) {
   return animate_range(grp, 0, grp->n, true);
 }
 
+static int copy_output_rows(p3cs_group grp, int o, int first, int count, void *host_dst, cudaStream_t stream);
+
+static int ensure_side_streams(p3cs_context ctx) {
+  if (ctx->fork_ev != nullptr) return P3CS_OK;
+  CUDA_TRY(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+  for (int k = 0; k < p3cs_context_s::kSideStreams; ++k) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming));
+  }
+  return P3CS_OK;
+}
+
+// The crowd form of p3cs_animate_vertices: host palettes / sliders in, host arrays out, for ALL instances of the
+// group, software-pipelined in chunks of instances over three streams (upload, kernels, download) so that the
+// PCIe download -- the bound of this call -- never waits for an upload or a kernel after the first chunk.
+extern "C" int p3cs_group_animate_host(p3cs_group grp, const float *host_palettes, const float *host_sliders,
+                                       void *const *host_outputs, int chunk_instances) {
+  if (grp == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_animate_host: group is NULL");
+  const MeshDev &m = grp->mesh->dev;
+  p3cs_context ctx = grp->mesh->ctx;
+  if (m.num_transforms > 0 && host_palettes == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_animate_host: palettes are NULL");
+  if (grp->n == 0) return P3CS_OK;
+  DeviceGuard g(ctx->device);
+  int rc = ensure_side_streams(ctx);
+  if (rc != P3CS_OK) return rc;
+  int chunk = chunk_instances;
+  if (chunk <= 0) {  // ~256 MB of output per chunk: long enough to run the link at full rate, short enough to overlap
+    size_t per = 0;
+    for (int o = 0; o < m.num_outputs; ++o) per += (size_t)m.num_rows * m.stride[o];
+    chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)grp->n, (256u << 20) / std::max<size_t>(per, 1)));
+  }
+  const int nchunks = (grp->n + chunk - 1) / chunk;
+  while ((int)ctx->pipe_ev.size() < 2 * nchunks) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->pipe_ev.push_back(e);
+  }
+  cudaStream_t up = ctx->side[0], down = ctx->side[1], run = ctx->stream;
+  CUDA_TRY(cudaEventRecord(ctx->fork_ev, run));  // both copy streams start after whatever the context did before
+  CUDA_TRY(cudaStreamWaitEvent(up, ctx->fork_ev, 0));
+  CUDA_TRY(cudaStreamWaitEvent(down, ctx->fork_ev, 0));
+  const size_t pal_per = (size_t)m.num_transforms * 16, sl_per = (size_t)m.num_sliders;
+  int total_launches = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    const int first = c * chunk, count = std::min(chunk, grp->n - first);
+    if (pal_per > 0)
+      CUDA_TRY(cudaMemcpyAsync(const_cast<float *>(grp->dev.palettes) + pal_per * first, host_palettes + pal_per * first,
+                               pal_per * count * 4, cudaMemcpyHostToDevice, up));
+    if (sl_per > 0 && host_sliders != nullptr)
+      CUDA_TRY(cudaMemcpyAsync(const_cast<float *>(grp->dev.sliders) + sl_per * first, host_sliders + sl_per * first,
+                               sl_per * count * 4, cudaMemcpyHostToDevice, up));
+    CUDA_TRY(cudaEventRecord(ctx->pipe_ev[2 * c], up));
+    CUDA_TRY(cudaStreamWaitEvent(run, ctx->pipe_ev[2 * c], 0));
+    if ((rc = animate_range(grp, first, count, false)) != P3CS_OK) break;
+    total_launches += grp->last.launches;
+    CUDA_TRY(cudaEventRecord(ctx->pipe_ev[2 * c + 1], run));
+    if (host_outputs != nullptr) {
+      CUDA_TRY(cudaStreamWaitEvent(down, ctx->pipe_ev[2 * c + 1], 0));
+      for (int o = 0; o < m.num_outputs; ++o)
+        if (host_outputs[o] != nullptr) {
+          uint8_t *dst = static_cast<uint8_t *>(host_outputs[o]) + (size_t)m.num_rows * m.stride[o] * first;
+          if ((rc = copy_output_rows(grp, o, first, count, dst, down)) != P3CS_OK) break;
+        }
+    }
+  }
+  // join: the context's stream (what p3cs_context_sync waits for) ends after the last download
+  cudaEventRecord(ctx->join_ev[0], up);
+  cudaEventRecord(ctx->join_ev[1], down);
+  cudaStreamWaitEvent(run, ctx->join_ev[0], 0);
+  cudaStreamWaitEvent(run, ctx->join_ev[1], 0);
+  grp->last.launches = total_launches;
+  return rc;
+}
+
 extern "C" int p3cs_animate_groups(p3cs_group const *groups, int num_groups) {
   if (num_groups < 0 || (num_groups > 0 && groups == nullptr)) return fail(P3CS_ERR_INVALID, "p3cs_animate_groups: bad arguments");
   if (num_groups == 0) return P3CS_OK;
@@ -1072,12 +1148,9 @@ extern "C" int p3cs_animate_groups(p3cs_group const *groups, int num_groups) {
   }
   DeviceGuard g(ctx->device);
   if (num_groups == 1) return animate_range(groups[0], 0, groups[0]->n, true);
-  if (ctx->fork_ev == nullptr) {
-    CUDA_TRY(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
-    for (int k = 0; k < p3cs_context_s::kSideStreams; ++k) {
-      CUDA_TRY(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
-      CUDA_TRY(cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming));
-    }
+  {
+    const int rc0 = ensure_side_streams(ctx);
+    if (rc0 != P3CS_OK) return rc0;
   }
   // fork: group i runs on lane i % (1 + kSideStreams); lane 0 is the context's own stream
   const int lanes = std::min(num_groups, 1 + p3cs_context_s::kSideStreams);
@@ -1164,6 +1237,18 @@ extern "C" int p3cs_group_read_bounds(p3cs_group grp, int first, int count, floa
   return P3CS_OK;
 }
 
+// Device -> host copy of `count` instances of output `o`, tightly packed at the destination.  When the device
+// pitch equals the packed size (rows * stride a multiple of 256) the span is one linear copy, which the copy
+// engine moves faster than a pitched one.
+static int copy_output_rows(p3cs_group grp, int o, int first, int count, void *host_dst, cudaStream_t stream) {
+  const MeshDev &m = grp->mesh->dev;
+  const size_t row_bytes = (size_t)m.num_rows * m.stride[o];
+  const uint8_t *src = grp->dev.out[o] + grp->dev.pitch[o] * first;
+  if (grp->dev.pitch[o] == row_bytes) CUDA_TRY(cudaMemcpyAsync(host_dst, src, row_bytes * count, cudaMemcpyDeviceToHost, stream));
+  else CUDA_TRY(cudaMemcpy2DAsync(host_dst, row_bytes, src, grp->dev.pitch[o], row_bytes, count, cudaMemcpyDeviceToHost, stream));
+  return P3CS_OK;
+}
+
 extern "C" int p3cs_group_read_output(p3cs_group grp, int o, int first, int count, void *host_dst) {
   int rc = check_span(grp, first, count, "p3cs_group_read_output");
   if (rc != P3CS_OK) return rc;
@@ -1172,9 +1257,7 @@ extern "C" int p3cs_group_read_output(p3cs_group grp, int o, int first, int coun
   DeviceGuard g(grp->mesh->ctx->device);
   const size_t row_bytes = (size_t)m.num_rows * m.stride[o];
   if (row_bytes == 0 || count == 0) return P3CS_OK;
-  CUDA_TRY(cudaMemcpy2DAsync(host_dst, row_bytes, grp->dev.out[o] + grp->dev.pitch[o] * first, grp->dev.pitch[o], row_bytes, count,
-                             cudaMemcpyDeviceToHost, grp->mesh->ctx->stream));
-  return P3CS_OK;
+  return copy_output_rows(grp, o, first, count, host_dst, grp->mesh->ctx->stream);
 }
 
 extern "C" int p3cs_group_read_selection(p3cs_group grp, int32_t *host_dst) {

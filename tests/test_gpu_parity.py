@@ -690,3 +690,27 @@ def test_shareable_output_reaches_another_process(gpu_ctx):
         dmesh.close()
         gpu_ctx.shareable_free(ptr)
         os.close(fd)
+
+
+@pytest.mark.gpu
+def test_animate_host_pipelined_crowd(gpu_ctx):
+    """p3cs_group_animate_host (chunks pipelined over upload / kernel / download streams) returns, for every
+    instance, the bytes of the one-instance call -- with chunk sizes that do and do not divide the crowd."""
+    sm = synth.make_mesh(2_500, 16, 300, seed=121, tbn=True, num_sliders=3, slider_band=0.3, index_order="runs")
+    mesh = sm.flat
+    n = 37
+    pal = synth.make_palettes(16, n, 122)
+    sl = synth.make_sliders(3, n, 123)
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, n)
+    try:
+        single = [grp.animate_vertices(pal[i], sl[i], instance=i)[0] for i in (0, 17, n - 1)]
+        for chunk in (0, 1, 5, 37, 100):
+            outs = grp.animate_host(pal.reshape(n, -1), sl, chunk=chunk)
+            for k, i in enumerate((0, 17, n - 1)):
+                assert np.array_equal(outs[0][i], single[k]), f"chunk {chunk}, instance {i}"
+        expect, _, _ = oracle.animate(mesh, pal[17], sl[17])
+        compare_outputs(mesh, [outs[0][17]], expect, "animate_host instance 17")
+    finally:
+        grp.close()
+        dmesh.close()
