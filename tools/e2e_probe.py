@@ -22,3 +22,13 @@ with torch.cuda.stream(stream):
             g.animate_host_ptr(pal.data_ptr(), None, [out.data_ptr()], chunk); ctx.sync()
         ms = (time.perf_counter() - t0) / 4 * 1e3
         print("chunk", chunk, "ms/step %.2f" % ms, "GB/s out %.1f" % (out.numel() / ms / 1e6), flush=True)
+    # kernel storing straight into page-locked host memory (no download step at all)
+    g2 = _capi.Group(dm, n, outputs_dev=[out.data_ptr()])
+    out.zero_()
+    for _ in range(2):
+        g2.set_palettes_ptr(pal.data_ptr(), 0, n); g2.animate(); ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        g2.set_palettes_ptr(pal.data_ptr(), 0, n); g2.animate(); ctx.sync()
+    ms = (time.perf_counter() - t0) / 4 * 1e3
+    print("direct stores to host: ms/step %.2f" % ms, "GB/s out %.1f" % (out.numel() / ms / 1e6), "nonzero", int(out[n // 2].count_nonzero()), flush=True)
