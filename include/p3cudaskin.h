@@ -376,6 +376,24 @@ P3CS_EXPORT int p3cs_group_enable_bounds(p3cs_group group, const p3cs_column_des
  * last p3cs_group_animate.  Synchronous. */
 P3CS_EXPORT int p3cs_group_read_bounds(p3cs_group group, int first, int count, float *host_dst);
 
+/* ---- "next" row f3: the AT_hardware upload format (host side, no device work) ----
+ * p3cs_hardware_from_blends restates GeomVertexData::copy_from's Panda-table -> hardware-table conversion
+ * (gobj/geomVertexData.cxx:574-648, indexed branch): per row (every row, like the reference's loop) the
+ * blend's weights and TransformTable slots, <= 4 per vertex -- blends with more entries are cut with
+ * TransformBlend::limit_transforms(4) + normalize_weights() (gobj/transformBlend.cxx:95-140); `table`
+ * receives, per TransformTable slot in first-use order, the palette index it holds (capacity
+ * desc->num_transforms).  Only arrays[blend_column.array] and the blend CSR of `desc` are read. */
+P3CS_EXPORT int p3cs_hardware_from_blends(const p3cs_mesh_desc *desc, float *weights /* [num_rows][4] */,
+                                          int32_t *indices /* [num_rows][4] */, int32_t *table, int32_t *table_size);
+/* The way back, so a mesh stored in the hardware format can feed p3cs_mesh_create: a row's non-zero slots,
+ * in slot order, become one blend (identical rows share it).  Capacities: row_blend[num_rows] (write it
+ * into a uint32 transform_blend column), blend_offsets[num_rows + 1], blend_transform / blend_weight
+ * [4 * num_rows].  For columns produced from <= 4-entry blends the animated result is bit-identical to the
+ * original table's. */
+P3CS_EXPORT int p3cs_blends_from_hardware(int32_t num_rows, const float *weights, const int32_t *indices, const int32_t *table,
+                                          int32_t table_size, int32_t *row_blend, int32_t *blend_offsets,
+                                          int32_t *blend_transform, float *blend_weight, int32_t *num_blends);
+
 /* ---- plugin table (load_dso + dlsym("p3cs_get_api")) -------------------- */
 
 typedef struct p3cs_api {

@@ -19,6 +19,9 @@
 #include "geomVertexArrayData.h"
 #include "transformBlendTable.h"
 #include "transformBlend.h"
+#include "transformTable.h"
+#include "geomVertexReader.h"
+#include "geomVertexAnimationSpec.h"
 #include "userVertexTransform.h"
 #include "userVertexSlider.h"
 #include "sliderTable.h"
@@ -540,10 +543,51 @@ static int cmd_bench(const char *in_path, int iters, int warmup, int copies) {
   return 0;
 }
 
+// ------------------------------------------------- AT_hardware conversion ("next" row f3)
+// Runs the reference's own Panda-table -> hardware-table conversion (GeomVertexData::copy_from,
+// gobj/geomVertexData.cxx:574-648, indexed branch) through convert_to() and exports what it wrote: the
+// transform_weight / transform_index columns and the TransformTable order.
+static int cmd_hw(const char *in_path, const char *out_path) {
+  Case in; if (!read_case(in_path, in)) return 1;
+  Built b; if (!build_from_recipe(in, b)) return 1;
+  int num_rows = in.at("meta").i32()[0];
+  PT(GeomVertexFormat) f = new GeomVertexFormat(*b.vd->get_format());
+  f->remove_column(InternalName::get_transform_blend());
+  PT(GeomVertexArrayFormat) af = new GeomVertexArrayFormat;
+  af->add_column(InternalName::get_transform_weight(), 4, GeomEnums::NT_float32, GeomEnums::C_other);
+  af->add_column(InternalName::get_transform_index(), 4, GeomEnums::NT_uint16, GeomEnums::C_index);
+  f->add_array(af);
+  GeomVertexAnimationSpec spec; spec.set_hardware(4, true); f->set_animation(spec);
+  CPT(GeomVertexFormat) fmt = GeomVertexFormat::register_format(f);
+  CPT(GeomVertexData) hw = b.vd->convert_to(fmt);
+  if (hw->get_transform_table() == nullptr) { fprintf(stderr, "no TransformTable after convert_to\n"); return 1; }
+  std::vector<float> weights((size_t)num_rows * 4);
+  std::vector<int32_t> indices((size_t)num_rows * 4);
+  GeomVertexReader rw(hw, InternalName::get_transform_weight()), ri(hw, InternalName::get_transform_index());
+  for (int r = 0; r < num_rows; ++r) {
+    LVecBase4 w = rw.get_data4();
+    LVecBase4i i = ri.get_data4i();
+    for (int k = 0; k < 4; ++k) { weights[(size_t)r * 4 + k] = (float)w[k]; indices[(size_t)r * 4 + k] = i[k]; }
+  }
+  const TransformTable *tt = hw->get_transform_table();
+  std::vector<int32_t> table;
+  for (size_t t = 0; t < tt->get_num_transforms(); ++t) {
+    int found = -1;
+    for (size_t j = 0; j < b.transforms.size(); ++j) if (b.transforms[j].p() == tt->get_transform(t)) found = (int)j;
+    table.push_back(found);
+  }
+  Case out;
+  out["hw_weight"] = make_blob(DT_F32, weights, {(uint64_t)num_rows, 4});
+  out["hw_index"] = make_blob(DT_I32, indices, {(uint64_t)num_rows, 4});
+  out["hw_table"] = make_blob(DT_I32, table, {(uint64_t)table.size()});
+  return write_case(out_path, out) ? 0 : 1;
+}
+
 int main(int argc, char **argv) {
+  if (argc >= 4 && strcmp(argv[1], "hw") == 0) return cmd_hw(argv[2], argv[3]);
   if (argc >= 4 && strcmp(argv[1], "run") == 0) return cmd_run(argv[2], argv[3]);
   if (argc >= 6 && strcmp(argv[1], "egg") == 0) return cmd_egg(argc, argv);
   if (argc >= 5 && strcmp(argv[1], "bench") == 0) return cmd_bench(argv[2], atoi(argv[3]), atoi(argv[4]), argc > 5 ? atoi(argv[5]) : 1);
-  fprintf(stderr, "usage: ref_harness run <recipe> <golden> | egg <model> <anim> <golden> <frame>... | bench <recipe> <iters> <warmup> [characters]\n");
+  fprintf(stderr, "usage: ref_harness run <recipe> <golden> | hw <recipe> <out> | egg <model> <anim> <golden> <frame>... | bench <recipe> <iters> <warmup> [characters]\n");
   return 2;
 }

@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = [
     "p3cs_group_enable_bounds", "p3cs_group_read_bounds", "p3cs_animate_groups",
     "p3cs_host_register", "p3cs_host_unregister",
     "p3cs_shareable_alloc", "p3cs_shareable_import", "p3cs_shareable_free", "p3cs_group_animate_host",
+    "p3cs_hardware_from_blends", "p3cs_blends_from_hardware",
 ]
 
 
@@ -277,6 +278,44 @@ def mesh_desc(mesh: FlatMesh, keep: list) -> _MeshDesc:
     d.num_morphs = len(mesh.morphs)
     d.morphs = C.cast(morphs, C.POINTER(_MorphDesc))
     return d
+
+
+def hardware_from_blends(mesh: FlatMesh):
+    """p3cs_hardware_from_blends: (weights [rows,4] f32, indices [rows,4] i32, table [n] i32) -- what
+    GeomVertexData::copy_from writes when converting to an indexed AT_hardware format."""
+    keep: list = []
+    d = mesh_desc(mesh, keep)
+    w = np.empty((mesh.num_rows, 4), np.float32)
+    ix = np.empty((mesh.num_rows, 4), np.int32)
+    table = np.empty(max(1, mesh.num_transforms), np.int32)
+    n = C.c_int32(0)
+    L = lib()
+    L.p3cs_hardware_from_blends.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+    rc = L.p3cs_hardware_from_blends(C.byref(d), w.ctypes.data, ix.ctypes.data, table.ctypes.data, C.byref(n))
+    if rc != P3CS_OK:
+        raise P3csError(rc, "p3cs_hardware_from_blends failed")
+    return w, ix, table[:n.value].copy()
+
+
+def blends_from_hardware(weights: np.ndarray, indices: np.ndarray, table: np.ndarray):
+    """p3cs_blends_from_hardware: (row_blend [rows] i32, blend_offsets, blend_transform, blend_weight)."""
+    w = np.ascontiguousarray(weights, np.float32).reshape(-1, 4)
+    ix = np.ascontiguousarray(indices, np.int32).reshape(-1, 4)
+    tb = np.ascontiguousarray(table, np.int32)
+    rows = w.shape[0]
+    row_blend = np.empty(rows, np.int32)
+    off = np.empty(rows + 1, np.int32)
+    xf = np.empty(4 * max(rows, 1), np.int32)
+    bw = np.empty(4 * max(rows, 1), np.float32)
+    nb = C.c_int32(0)
+    L = lib()
+    L.p3cs_blends_from_hardware.argtypes = [C.c_int32] + [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 4 + [C.POINTER(C.c_int32)]
+    rc = L.p3cs_blends_from_hardware(rows, w.ctypes.data, ix.ctypes.data, tb.ctypes.data, int(tb.size), row_blend.ctypes.data,
+                                     off.ctypes.data, xf.ctypes.data, bw.ctypes.data, C.byref(nb))
+    if rc != P3CS_OK:
+        raise P3csError(rc, "p3cs_blends_from_hardware failed")
+    n = nb.value
+    return row_blend, off[:n + 1].copy(), xf[:off[n]].copy(), bw[:off[n]].copy()
 
 
 class Mesh:

@@ -52,10 +52,35 @@ def cases():
         yield "cs_" + csname, mk(300, 8, 8, seed=8, weights_per_blend=1, coordinate_system=cs), P(8, 1, 18, scale=0.5), None
 
 
+def hardware_cases():
+    """Inputs of the AT_hardware conversion fixtures (tests/golden/hardware/): <= 4 entries per blend, more than 4
+    (limit_transforms + normalize_weights), 1..3 entries with a u8 index and a rows subset."""
+    mk = synth.make_mesh
+    yield "hw_four", mk(700, 20, 150, seed=201, index_order="runs")
+    yield "hw_six", mk(500, 16, 90, seed=202, weights_per_blend=6)
+    yield "hw_two_u8", mk(300, 9, 40, seed=203, weights_per_blend=2, index_type="u8", rows=[(3, 200)])
+
+
+def make_hardware_fixtures(tmp):
+    from panda3d_b200.casefile import load_case
+    os.makedirs(os.path.join(HERE, "hardware"), exist_ok=True)
+    for name, sm in hardware_cases():
+        recipe = os.path.join(tmp, name + ".recipe")
+        case = sm.recipe(synth.make_palettes(sm.flat.num_transforms, 1, 7))
+        save_case(recipe, case)
+        raw = os.path.join(tmp, name + ".hw")
+        subprocess.run([HARNESS, "hw", recipe, raw], check=True, timeout=120, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        case.update(load_case(raw))   # the recipe (inputs) + hw_weight / hw_index / hw_table (what the reference wrote)
+        out = os.path.join(HERE, "hardware", name + ".p3cs")
+        save_case(out, case)
+        print("wrote", out, os.path.getsize(out))
+
+
 def main():
     if not os.path.exists(HARNESS):
         sys.exit("oracle/_ref/bin/ref_harness missing: run `bash oracle/build_ref.sh` first")
     with tempfile.TemporaryDirectory() as tmp:
+        make_hardware_fixtures(tmp)
         for name, sm, pal, sl in cases():
             recipe = os.path.join(tmp, name + ".recipe")
             save_case(recipe, sm.recipe(pal, sl))
