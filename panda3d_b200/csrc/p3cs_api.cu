@@ -547,13 +547,24 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
           return bail(fail(P3CS_ERR_INVALID, "row %d selects blend %u but the table has %d blends", r, v, d->num_blends));
         if (!full) mask[r >> 5] |= 1u << (r & 31);
       }
+    // ---- vertex-animation-align-16 layout (gobj/config_gobj.cxx:286-300, geomVertexArrayFormat.cxx:349-373): the
+    // strip kernel's kAligned modes
+    {
+      const DynColumn *c = m.dyn;
+      bool ok = m.full_records && m.num_outputs == 1 && d->num_morphs == 0 && m.stride[0] % 16 == 0 &&
+                ((m.num_dyn == 2 && c[0].skin == 1 && c[1].skin == 3) ||
+                 (m.num_dyn == 4 && c[0].skin == 1 && c[1].skin == 3 && c[2].skin == 2 && c[3].skin == 2));
+      for (int i = 0; ok && i < m.num_dyn; ++i) ok = c[i].num_values == 4 && !c[i].f64 && c[i].start % 16 == 0;
+      m.aligned = ok ? 1 : 0;
+    }
+    m.strip_rec_floats = m.aligned ? kRecAligned : m.full_records ? kRecFull : kRecCompact;
     // ---- shared-memory plan of the strip kernel.  Four CTAs per SM (the register-file limit) need <= ~55 KB each:
     // palette + records + staged tiles.  Preference: two rows per thread (512-row tiles halve the per-tile
     // bookkeeping), else 256-row tiles with three, then two buffers, then a smaller record group.
     {
       size_t slice = 0;
       for (int o = 0; o < m.num_outputs; ++o) slice += round_up((size_t)32 * m.stride[o], 128);
-      const size_t rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
+      const size_t rec_bytes = (size_t)m.strip_rec_floats * 4;
       const size_t fixed = 32 + (size_t)d->num_transforms * 64 + 128;
       const size_t budget = 55 * 1024;
       const int full_cap = std::min(kStripThreads, (int)((32 * 1024) / rec_bytes));  // one phase-A pass: a thread per record
@@ -561,7 +572,7 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
       m.rows_per_thread = 1;
       m.tile_bufs = 3;
       m.group_record_cap = full_cap;
-      if (!m.full_records) {
+      if (!m.full_records || m.aligned) {
         if (fits(2, 2, full_cap)) {
           m.rows_per_thread = 2;
           m.tile_bufs = 2;
@@ -584,7 +595,6 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
     // (one thread per record) and the shared-memory record budget.
     {
       const int nt = (N + kTileRows - 1) / kTileRows;
-      const int rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
       const int cap = m.group_record_cap;
       std::vector<uint16_t> local(std::max(N, 1), 0xFFFFu);
       std::vector<int> rec_off(1, 0), rec_blend, ent_off(1, 0), tile_off(1, 0);
@@ -830,6 +840,7 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
   // ---- slice geometry of the strip kernel (a slice = the 32 rows one warp stages at a time)
   if (m.rows_per_thread == 0) m.rows_per_thread = 1;
   if (m.tile_bufs == 0) m.tile_bufs = 3;
+  if (m.strip_rec_floats == 0) m.strip_rec_floats = m.full_records ? kRecFull : kRecCompact;
   m.num_tiles = (N + kStripThreads * m.rows_per_thread - 1) / (kStripThreads * m.rows_per_thread);
   m.slice_bytes = 0;
   for (int o = 0; o < m.num_outputs; ++o) {

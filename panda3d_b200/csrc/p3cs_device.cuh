@@ -125,7 +125,7 @@ __device__ __forceinline__ void load_record(const float *records, size_t index, 
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int j = 0; j < 3; ++j) r.x[i][j] = f[12 + i * 3 + j];
-    r.normalize = f[21] != 0.0f;
+    r.normalize = f[21] == 1.0f;  // 2 = identity scale: x equals the blend matrix (strip kernel's aligned modes)
   }
 }
 

@@ -12,7 +12,9 @@ constexpr int kMaxDynColumns = 12;  // skinned and/or morphed columns per mesh
 //   compact (no 4-component skin column): 12 floats M (rows 0..3 x cols 0..2), 9 floats N
 //   (normal matrix 3x3), 1 float flag (normalize) = 22 floats = 88 bytes;
 //   full: 16 floats M, 16 floats X, flag, padded to 36 floats = 144 bytes.
+//   aligned (strip kernel, align-16 layouts): the compact record + column 3 of M = 26 floats = 104 bytes.
 constexpr int kRecCompact = 22;
+constexpr int kRecAligned = 26;
 constexpr int kRecFull = 36;
 
 // A column that changes per frame: skinned (point/vector/normal) and/or a morph base.
@@ -56,6 +58,9 @@ struct MeshDev {
   int rows_per_thread;              // 1 or 2: rows a thread animates per staged tile (tile = 256 or 512 rows)
   int tile_bufs;                    // 2 or 3 staged tiles in flight per CTA
   int group_record_cap;             // most records a record group may hold (sizes the shared-memory record area)
+  int aligned;                      // vertex-animation-align-16 layout: one output array, every animated column float32 x 4
+                                    // on a 16-byte boundary, no morphs -> the strip kernel's kAligned modes
+  int strip_rec_floats;             // floats per shared-memory blend record of the strip kernel (22, 26 or 36)
   const int *group_tile_offsets;    // num_groups+1: group g covers tiles [off[g], off[g+1])
   int num_groups;
   int max_group_records;            // max distinct blends of any group (smem sizing)

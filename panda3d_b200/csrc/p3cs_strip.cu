@@ -15,12 +15,15 @@ P3CS_EXTERN_MODE(kRow24)
 P3CS_EXTERN_MODE(kRow32)
 P3CS_EXTERN_MODE(kRow48)
 P3CS_EXTERN_MODE(kRow56)
+P3CS_EXTERN_MODE(kAlignedPN)
+P3CS_EXTERN_MODE(kAlignedPNVV)
 #undef P3CS_EXTERN_MODE
 
 size_t strip_smem_bytes(const MeshDev &mesh) { return (size_t)strip_layout(mesh).total; }
 
 // Which specialisation fits this mesh (see the header comment).
 static int pick_mode(const MeshDev &mesh) {
+  if (mesh.aligned) return mesh.num_dyn == 2 ? kAlignedPN : kAlignedPNVV;
   if (mesh.full_records) return kGenericFull;
   if (mesh.num_outputs != 1 || mesh.index_bytes == 0) return kGenericCompact;
   for (int c = 0; c < mesh.num_dyn; ++c)
@@ -82,6 +85,8 @@ int launch_strip(const MeshDev &mesh, const GroupDev &grp, int first_instance, i
     case kRow32: launch_mode<kRow32>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
     case kRow48: launch_mode<kRow48>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
     case kRow56: launch_mode<kRow56>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
+    case kAlignedPN: launch_mode<kAlignedPN>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
+    case kAlignedPNVV: launch_mode<kAlignedPNVV>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
     default: launch_mode<kGenericCompact>(mesh, grp, first, grid, smem, (int)gpc, want_normal, stream); break;
     }
     ++launches;

@@ -31,7 +31,12 @@ namespace p3cs {
 // widest shared-memory accesses that are bank-conflict free for that stride: 64-bit when the stride is an odd
 // number of 8-byte units (24, 56), 128-bit when it is an odd number of 16-byte units (48), and for the
 // power-of-two stride 32 two 128-bit accesses whose order alternates every four rows.
-enum StripMode { kGenericCompact = 0, kGenericFull = 1, kFastP = 2, kFastPN = 3, kFastPNVV = 4, kRow24 = 5, kRow32 = 6, kRow48 = 7, kRow56 = 8 };
+// kAlignedPN / kAlignedPNVV: the vertex-animation-align-16 layouts of Eigen builds (every animated column float32 x 4
+// on a 16-byte boundary): one 128-bit access per column, compact records extended by column 3 of the blend.
+enum StripMode {
+  kGenericCompact = 0, kGenericFull = 1, kFastP = 2, kFastPN = 3, kFastPNVV = 4, kRow24 = 5, kRow32 = 6, kRow48 = 7, kRow56 = 8,
+  kAlignedPN = 9, kAlignedPNVV = 10
+};
 
 // Row layouts of the kRow modes, in 32-bit words: row length W, access width VEC, column offsets (-1: absent).
 template <int MODE> struct RowLayout { static constexpr int W = 2, VEC = 2, P = 0, N = -1, T = -1, B = -1; };
@@ -138,7 +143,7 @@ __host__ __device__ inline StripSmem strip_layout(const MeshDev &m) {
   s.pal3_off = 32;
   s.palc_off = s.pal3_off + m.num_transforms * 48;
   s.records_off = s.palc_off + m.num_transforms * 16;
-  const int rec_bytes = (m.full_records ? kRecFull : kRecCompact) * 4;
+  const int rec_bytes = m.strip_rec_floats * 4;
   const int recs_bytes = m.max_group_records * rec_bytes > 256 ? m.max_group_records * rec_bytes : 256;  // >= the bounds scratch
   s.tiles_off = (s.records_off + recs_bytes + 127) & ~127;
   // staged tiles (contiguous 32-row slices), tile_bufs of them in flight
@@ -206,7 +211,7 @@ __device__ __forceinline__ void accumulate_entry(const float4 *pal3, const float
 // longer blends read the CSR arrays.
 template <bool AFFINE>
 __device__ __forceinline__ void compact_record(const float4 *pal3, const float4 *palc, uint4 q0, uint4 q1, const MeshDev &mesh,
-                                               int grec, int want_normal, float *rec) {
+                                               int grec, int want_normal, bool store_c3, float *rec) {
   float m[12];  // m[r*3+c]: rows 0..3 x columns 0..2
   float c3[4];
   const uint32_t count = q0.x >> 16;
@@ -235,6 +240,10 @@ __device__ __forceinline__ void compact_record(const float4 *pal3, const float4 
   float2 *r2 = reinterpret_cast<float2 *>(rec);
 #pragma unroll
   for (int i = 0; i < 6; ++i) r2[i] = make_float2(m[2 * i], m[2 * i + 1]);
+  if (store_c3) {  // aligned modes: column 3 of the blend, for the 4-component products
+    r2[11] = make_float2(c3[0], c3[1]);
+    r2[12] = make_float2(c3[2], c3[3]);
+  }
   if (!want_normal) return;
 
   // the C_normal prelude of do_transform_vector_column, geomVertexData.cxx:1811-1840
@@ -247,7 +256,7 @@ __device__ __forceinline__ void compact_record(const float4 *pal3, const float4 
       r2[7] = make_float2(m[2], m[3]);
       r2[8] = make_float2(m[4], m[5]);
       r2[9] = make_float2(m[6], m[7]);
-      r2[10] = make_float2(m[8], 0.0f);
+      r2[10] = make_float2(m[8], 2.0f);  // flag 2: the normal matrix IS the blend matrix (4-component normals need all of it)
     } else {
       normal_uniform_scale(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], mesh.coordinate_system, rec);
     }
@@ -289,6 +298,39 @@ __device__ __forceinline__ void compact_record(const float4 *pal3, const float4 
   r2[10] = make_float2(i22, 1.0f);  // N(2,2), normalize
 }
 
+// ------------------------------------------------------------------ phase B, align-16 columns
+// LMatrix4f::xform (VECTOR4_MATRIX4_PRODUCT, lmatrix4_src.I:703-725) with the blend matrix of a 26-float record:
+// f[r*3+c] = M(r,c) for c < 3, f[22+r] = M(r,3).
+__device__ __forceinline__ float4 aligned_xform_blend(const float4 v, const float (&f)[26]) {
+  float4 r;
+  r.x = v.x * f[0] + v.y * f[3] + v.z * f[6] + v.w * f[9];
+  r.y = v.x * f[1] + v.y * f[4] + v.z * f[7] + v.w * f[10];
+  r.z = v.x * f[2] + v.y * f[5] + v.z * f[8] + v.w * f[11];
+  r.w = v.x * f[22] + v.y * f[23] + v.z * f[24] + v.w * f[25];
+  return r;
+}
+// A C_normal column of four values (do_transform_vector_column, geomVertexData.cxx:1811-1858): normalize ->
+// table_xform_normal3f on the first three values; else table_xform_vecbase4f with the 4x4 `xform`, which is the
+// blend matrix itself (flag 2) or compose_matrix(unit scale, shear, hpr, zero translation) (flag 0: the 3x3 in
+// f[12..20], row 3 = (0,0,0,1), column 3 = (0,0,0,1) -- the products with those constants are evaluated, not
+// folded, so signed zeros and non-finite inputs come out as on the CPU).
+__device__ __forceinline__ float4 aligned_normal(const float4 v, const float (&f)[26]) {
+  if (f[21] == 1.0f) {
+    float r0 = v.x * f[12] + v.y * f[15] + v.z * f[18];
+    float r1 = v.x * f[13] + v.y * f[16] + v.z * f[19];
+    float r2 = v.x * f[14] + v.y * f[17] + v.z * f[20];
+    normalize3(r0, r1, r2);
+    return make_float4(r0, r1, r2, v.w);
+  }
+  if (f[21] == 2.0f) return aligned_xform_blend(v, f);
+  float4 r;
+  r.x = v.x * f[12] + v.y * f[15] + v.z * f[18] + v.w * 0.0f;
+  r.y = v.x * f[13] + v.y * f[16] + v.z * f[19] + v.w * 0.0f;
+  r.z = v.x * f[14] + v.y * f[17] + v.z * f[20] + v.w * 0.0f;
+  r.w = v.x * 0.0f + v.y * 0.0f + v.z * 0.0f + v.w * 1.0f;
+  return r;
+}
+
 // ------------------------------------------------------------------ phase B, specialised columns
 // KIND: 1 point, 2 vector, 3 normal (float32 x 3); f = the 22-float record in registers.
 template <int KIND>
@@ -307,7 +349,7 @@ __device__ __forceinline__ void fast_column(float *cell, const float (&f)[22]) {
     r0 = v0 * f[12] + v1 * f[15] + v2 * f[18];
     r1 = v0 * f[13] + v1 * f[16] + v2 * f[19];
     r2 = v0 * f[14] + v1 * f[17] + v2 * f[20];
-    if (f[21] != 0.0f) normalize3(r0, r1, r2);
+    if (f[21] == 1.0f) normalize3(r0, r1, r2);
   }
   cell[0] = r0;
   cell[1] = r1;
@@ -326,8 +368,9 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   const int kTileBufs = kRowsPerThread == 2 ? 2 : mesh.tile_bufs;  // 512-row tiles: always 2; else the host's plan (2 or 3)
   constexpr bool FULL = MODE == kGenericFull;
   constexpr bool FAST = MODE >= kFastP;
-  constexpr bool ROWREG = MODE >= kRow24;  // the row is held in registers (RowLayout<MODE>)
-  constexpr int REC = FULL ? kRecFull : kRecCompact;
+  constexpr bool ALIGNED = MODE >= kAlignedPN;                   // float32 x 4 columns on 16-byte boundaries
+  constexpr bool ROWREG = MODE >= kRow24 && MODE <= kRow56;  // the row is held in registers (RowLayout<MODE>)
+  constexpr int REC = FULL ? kRecFull : ALIGNED ? kRecAligned : kRecCompact;
   const StripSmem lay = strip_layout(mesh);
   float *pal3f = reinterpret_cast<float *>(smem + lay.pal3_off);
   float *palcf = reinterpret_cast<float *>(smem + lay.palc_off);
@@ -454,8 +497,8 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
           q0 = __ldg(blk);
           q1 = __ldg(blk + 1);
         }
-        if (non_affine) compact_record<false>(pal3, palc, q0, q1, mesh, rbeg + b, want_normal, recs + (size_t)b * REC);
-        else compact_record<true>(pal3, palc, q0, q1, mesh, rbeg + b, want_normal, recs + (size_t)b * REC);
+        if (non_affine) compact_record<false>(pal3, palc, q0, q1, mesh, rbeg + b, want_normal, ALIGNED, recs + (size_t)b * REC);
+        else compact_record<true>(pal3, palc, q0, q1, mesh, rbeg + b, want_normal, ALIGNED, recs + (size_t)b * REC);
       }
     }
     __syncthreads();  // every record of the group is in shared memory
@@ -532,7 +575,41 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
               cell[2] = cell[2] + d.z * value;
             }
           }
-          if (skinned) {
+          if (ALIGNED) {
+            if (skinned) {
+              const float2 *p = reinterpret_cast<const float2 *>(recs + (size_t)local[rr] * kRecAligned);
+              float f[26];
+#pragma unroll
+              for (int i = 0; i < 13; ++i) {
+                const float2 v = p[i];
+                f[2 * i] = v.x;
+                f[2 * i + 1] = v.y;
+              }
+              uint8_t *rowp = tile + trow * stride0;
+              if (MODE == kAlignedPN && stride0 == 32) {
+                // [vertex normal] rows of 32 bytes: rows r and r+4 share their banks, so rows 4..7 of every
+                // eight touch the normal first (as in kRow32)
+                const int sel = (trow >> 2) & 1;
+                const float4 a = *reinterpret_cast<const float4 *>(rowp + sel * 16);
+                const float4 b = *reinterpret_cast<const float4 *>(rowp + (sel ^ 1) * 16);
+                const float4 pv = aligned_xform_blend(sel ? b : a, f);
+                const float4 nv = aligned_normal(sel ? a : b, f);
+                *reinterpret_cast<float4 *>(rowp + sel * 16) = sel ? nv : pv;
+                *reinterpret_cast<float4 *>(rowp + (sel ^ 1) * 16) = sel ? pv : nv;
+              } else {
+                float4 *c0 = reinterpret_cast<float4 *>(rowp + mesh.dyn[0].start);
+                float4 *c1 = reinterpret_cast<float4 *>(rowp + mesh.dyn[1].start);
+                *c0 = aligned_xform_blend(*c0, f);
+                *c1 = aligned_normal(*c1, f);
+                if (MODE == kAlignedPNVV) {
+                  float4 *c2 = reinterpret_cast<float4 *>(rowp + mesh.dyn[2].start);
+                  float4 *c3p = reinterpret_cast<float4 *>(rowp + mesh.dyn[3].start);
+                  *c2 = aligned_xform_blend(*c2, f);
+                  *c3p = aligned_xform_blend(*c3p, f);
+                }
+              }
+            }
+          } else if (skinned) {
             const float2 *p = reinterpret_cast<const float2 *>(recs + (size_t)local[rr] * kRecCompact);
             float f[22];
 #pragma unroll

@@ -76,6 +76,10 @@ def main():
                 specs = [(synth.make_mesh(20_000, 128, 4096, seed=33, tbn=True, index_order="runs").flat, args.instances)]
             elif name == "c3tbuv":  # ... with texcoord, tangent, binormal: stride 56 (the C5 layout)
                 specs = [(synth.make_mesh(20_000, 128, 4096, seed=33, tbn=True, texcoord=True, index_order="runs").flat, args.instances)]
+            elif name == "c3a16":  # vertex-animation-align-16 layout (Eigen builds): 4-component columns on 16-byte boundaries
+                specs = [(synth.make_mesh(20_000, 128, 4096, seed=33, align16=True, index_order="runs").flat, args.instances)]
+            elif name == "c3a16tb":
+                specs = [(synth.make_mesh(20_000, 128, 4096, seed=33, align16=True, tbn=True, index_order="runs").flat, args.instances)]
             elif name == "c2r":
                 specs, small = [(synth.config_c2("random").flat, 1)], True
             elif name == "c2s":
