@@ -78,6 +78,10 @@ def main():
                 specs = [(synth.make_mesh(20_000, 128, 4096, seed=33, tbn=True, texcoord=True, index_order="runs").flat, args.instances)]
             elif name == "c3a16":  # vertex-animation-align-16 layout (Eigen builds): 4-component columns on 16-byte boundaries
                 specs = [(synth.make_mesh(20_000, 128, 4096, seed=33, align16=True, index_order="runs").flat, args.instances)]
+            elif name == "c3a16uv":
+                specs = [(synth.make_mesh(20_000, 128, 4096, seed=33, align16=True, texcoord=True, index_order="runs").flat, args.instances)]
+            elif name == "c3a16tbuv":
+                specs = [(synth.make_mesh(20_000, 128, 4096, seed=33, align16=True, tbn=True, texcoord=True, index_order="runs").flat, args.instances)]
             elif name == "c3a16tb":
                 specs = [(synth.make_mesh(20_000, 128, 4096, seed=33, align16=True, tbn=True, index_order="runs").flat, args.instances)]
             elif name == "c2r":
