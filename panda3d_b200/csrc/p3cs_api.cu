@@ -551,10 +551,15 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
     // strip kernel's kAligned modes
     {
       const DynColumn *c = m.dyn;
-      bool ok = m.full_records && m.num_outputs == 1 && d->num_morphs == 0 && m.stride[0] % 16 == 0 &&
+      bool ok = m.full_records && m.num_outputs == 1 && m.stride[0] % 16 == 0 &&
                 ((m.num_dyn == 2 && c[0].skin == 1 && c[1].skin == 3) ||
                  (m.num_dyn == 4 && c[0].skin == 1 && c[1].skin == 3 && c[2].skin == 2 && c[3].skin == 2));
       for (int i = 0; ok && i < m.num_dyn; ++i) ok = c[i].num_values == 4 && !c[i].f64 && c[i].start % 16 == 0;
+      for (int mi = 0; ok && mi < d->num_morphs; ++mi) {  // morphs only on those columns (no morph-only column)
+        const p3cs_column_desc &b = d->morphs[mi].base;
+        ok = b.array >= 0 && b.array < d->num_arrays && out_of_array[b.array] == 0 && b.num_values == 4 &&
+             b.numeric_type == P3CS_NT_FLOAT32 && find_dyn(0, b.start) >= 0;
+      }
       m.aligned = ok ? 1 : 0;
     }
     m.strip_rec_floats = m.aligned ? kRecAligned : m.full_records ? kRecFull : kRecCompact;

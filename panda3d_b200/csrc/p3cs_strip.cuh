@@ -566,13 +566,27 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
             uint8_t *rowp = tile + trow * stride0;
             for (int e = mb[rr]; e < me[rr]; ++e) {
               const float4 d = __ldg(mesh.morph_deltas + e);  // .w carries the key of a 3-component delta
-              const uint32_t key = __float_as_uint(d.w);
+              // four-component columns may have a real fourth delta component: their key comes from its own table
+              const uint32_t key = ALIGNED ? __ldg(mesh.morph_keys + e) : __float_as_uint(d.w);
               const float value = __ldg(sliders + (key & 0xffffu));
               if (value == 0.0f) continue;  // `if (slider_value != 0.0f)`, :1483
-              float *cell = reinterpret_cast<float *>(rowp + mesh.dyn[key >> 16].start);
-              cell[0] = cell[0] + d.x * value;
-              cell[1] = cell[1] + d.y * value;
-              cell[2] = cell[2] + d.z * value;
+              const DynColumn col = mesh.dyn[key >> 16];
+              float *cell = reinterpret_cast<float *>(rowp + col.start);
+              if (!ALIGNED) {
+                cell[0] = cell[0] + d.x * value;
+                cell[1] = cell[1] + d.y * value;
+                cell[2] = cell[2] + d.z * value;
+              } else if (col.homogeneous) {  // :1499-1507: the delta is scaled by the homogeneous coordinate
+                const float sc = value * cell[3];
+                cell[0] = cell[0] + d.x * sc;
+                cell[1] = cell[1] + d.y * sc;
+                cell[2] = cell[2] + d.z * sc;
+              } else {  // :1516-1520
+                cell[0] = cell[0] + d.x * value;
+                cell[1] = cell[1] + d.y * value;
+                cell[2] = cell[2] + d.z * value;
+                cell[3] = cell[3] + d.w * value;
+              }
             }
           }
           if (ALIGNED) {

@@ -120,6 +120,10 @@ SYNTH_CASES = {
                          rows=[(9, 7000)]),
     "row32_morphs": dict(num_rows=3_000, num_transforms=16, num_blends=300, texcoord=True, num_sliders=4, slider_band=0.3,
                          morph_columns=("vertex", "normal")),
+    "align16_morphs": dict(num_rows=5_001, num_transforms=24, num_blends=600, align16=True, texcoord=True, index_order="runs",
+                           num_sliders=5, slider_band=0.3, morph_columns=("vertex", "normal")),
+    "align16_uv_tbn": dict(num_rows=6_007, num_transforms=40, num_blends=900, align16=True, texcoord=True, tbn=True,
+                           index_order="runs", rows=[(2, 6000)]),
     "float64_columns": dict(num_rows=6_001, num_transforms=32, num_blends=900, float64=True, tbn=True, index_order="runs",
                             num_sliders=6, slider_band=0.2, morph_columns=("vertex", "normal")),
     "float64_align16": dict(num_rows=3_001, num_transforms=16, num_blends=500, float64=True, align16=True,
