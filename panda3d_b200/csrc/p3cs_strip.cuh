@@ -1,6 +1,6 @@
 // p3cs_strip.cuh -- the fused hot-path kernel (sm_100a): one launch animates a whole crowd.
 //
-// Work unit = a strip: consecutive record groups (runs of 256-row tiles sharing one record list) of ONE
+// Work unit = a strip: consecutive record groups (runs of 256- or 512-row tiles sharing one record list) of ONE
 // instance.  Per strip the CTA stages the instance's joint-matrix palette in shared memory once;
 // then, per record group:
 //   * phase A: one thread per DISTINCT blend of the group accumulates sum_i w_i * M_i from the
@@ -8,8 +8,8 @@
 //     derives the normal matrix (geomVertexData.cxx:1811-1840) and leaves a record in smem;
 // and per tile of the group:
 //   * the tile's rows arrive by a TMA bulk copy (cp.async.bulk global->shared, completion on an
-//     mbarrier), double buffered so the next tile is in flight while this one is computed;
-//   * phase B: one thread per row applies the sparse morph deltas (geomVertexData.cxx:1462-1543)
+//     mbarrier), two or three buffers so the next tile is in flight while this one is computed;
+//   * phase B: one thread per row (one or two rows per thread and tile) applies the sparse morph deltas (geomVertexData.cxx:1462-1543)
 //     and the blend record of the row (:1558-1751) to the staged row, in place;
 //   * the finished tile leaves by a TMA bulk store (shared->global, bulk_group).
 // Blend records never touch HBM, the static mesh is read through L2 (shared by every instance),
@@ -17,14 +17,14 @@
 // Global accesses of rows are whole-tile bulk copies; every layout-dependent access (arbitrary
 // stride / column offsets of GeomVertexArrayFormat) happens on shared memory.
 //
-// Kernel variants (template MODE): the loader's common formats -- one output array, float32 x 3
-// columns, no morphs -- get phase B code specialised on the column kinds (point / normal /
-// vector); everything else runs the generic column loop.
+// Kernel variants (template MODE, see StripMode): the loader's common formats -- one output array, float32 x 3 or
+// aligned float32 x 4 columns -- get phase B code specialised on the column kinds (point / normal / vector) and,
+// for the usual strides, on the row layout; everything else runs the generic column loop.  AUX adds the
+// selection read-back (parity hook) or the fused tight-bounds reduction, MORPH the sparse morph-delta loop.
 #pragma once
 #include "p3cs_device.cuh"
 
 namespace p3cs {
-
 
 // kRow24 / kRow32 / kRow48 / kRow56: the loader's usual row layouts ([vertex normal], + texcoord, + tangent
 // binormal, + both).  The whole row lives in registers and moves between them and the staged tile with the
