@@ -668,7 +668,7 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
           }
         // Lane inside the cell.  Phase B reads a row's record with 64-bit loads, sixteen rows per wavefront; the
         // records of neighbouring runs (adjacent in first-seen order) collide there when their slots agree
-        // modulo 16, so each record takes a free lane whose slot differs from its two predecessors' modulo 16.
+        // modulo 16, so each record takes a free lane whose slot differs from its three predecessors' modulo 16.
         std::vector<int> slot_of(n, -1);
         std::vector<uint8_t> used((size_t)cells, 0);
         for (int i = 0; i < n; ++i) {
@@ -678,7 +678,8 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
             for (int p = 0; p < count_in[c]; ++p) {
               if ((used[c] >> p) & 1) continue;
               const int sl = 8 * c + p;
-              const bool clash = (i >= 1 && ((slot_of[i - 1] ^ sl) & 15) == 0) || (i >= 2 && ((slot_of[i - 2] ^ sl) & 15) == 0);
+              bool clash = false;  // against the records of the three preceding runs (a half-warp of rows spans about that many)
+              for (int back = 1; back <= 3 && back <= i; ++back) clash = clash || ((slot_of[i - back] ^ sl) & 15) == 0;
               if (pass == 1 || !clash) { best = p; break; }
             }
           used[c] |= (uint8_t)(1u << best);
