@@ -279,6 +279,10 @@ P3CS_EXPORT int p3cs_group_set_sliders(p3cs_group group, int first, int count,
  * 1550-1556), applies morphs (1462-1543) and skins every point / vector /
  * normal column (1558-1751) of all instances.  Asynchronous. */
 P3CS_EXPORT int p3cs_group_animate(p3cs_group group);
+/* The same for a subset: only the listed instances (in any order) are recomputed, the others keep their
+ * arrays -- the crowd form of the UpdateSeq test in GeomVertexData::animate_vertices
+ * (geomVertexData.cxx:937-946), where a character whose joints did not move is not re-animated. */
+P3CS_EXPORT int p3cs_group_animate_instances(p3cs_group group, const int32_t *host_instances, int count);
 /* A frame's worth of groups (a mixed crowd: one group per character type, what the per-Geom loop of
  * CullableObject::munge_geom, pgraph/cullableObject.cxx:170-175, visits one by one): the groups are independent,
  * so their kernels are forked over side streams of the context and joined back into its stream -- small

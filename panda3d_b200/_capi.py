@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = [
     "p3cs_group_enable_bounds", "p3cs_group_read_bounds", "p3cs_animate_groups",
     "p3cs_host_register", "p3cs_host_unregister",
     "p3cs_shareable_alloc", "p3cs_shareable_import", "p3cs_shareable_free", "p3cs_group_animate_host",
-    "p3cs_hardware_from_blends", "p3cs_blends_from_hardware",
+    "p3cs_hardware_from_blends", "p3cs_blends_from_hardware", "p3cs_group_animate_instances",
 ]
 
 
@@ -439,6 +439,13 @@ class Group:
     # ---- the hot path
     def animate(self) -> None:
         _check(lib().p3cs_group_animate(self.handle))
+
+    def animate_instances(self, instances) -> None:
+        """p3cs_group_animate_instances: recompute only the listed instances."""
+        idx = np.ascontiguousarray(instances, np.int32)
+        L = lib()
+        L.p3cs_group_animate_instances.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        _check(L.p3cs_group_animate_instances(self.handle, idx.ctypes.data, int(idx.size)))
 
     def set_profiling(self, enable: bool) -> None:
         _check(lib().p3cs_group_set_profiling(self.handle, 1 if enable else 0))

@@ -75,6 +75,8 @@ struct p3cs_group_s {
   std::vector<int> prof_kind;     // 0 blend, 1 skin, per pair
   bool profiling = false;
   float *bounds_buf = nullptr;  // [n][8] animated tight bounds (p3cs_group_enable_bounds)
+  int *list_dev = nullptr;      // instance list of the last p3cs_group_animate_instances
+  int list_capacity = 0;
   int *frames_dev = nullptr;  // per-instance animation frames of the last p3cs_group_pose
   int frames_capacity = 0;
   p3cs_timings last{};
@@ -951,6 +953,7 @@ extern "C" int p3cs_group_destroy(p3cs_group grp) {
     if (e) cudaEventDestroy(e);
   for (auto e : grp->prof) cudaEventDestroy(e);
   if (grp->frames_dev != nullptr) cudaFree(grp->frames_dev);
+  if (grp->list_dev != nullptr) cudaFree(grp->list_dev);
   delete grp;
   return P3CS_OK;
 }
@@ -1186,6 +1189,35 @@ extern "C" int p3cs_animate_groups(p3cs_group const *groups, int num_groups) {
   return rc;
 }
 
+// Only the instances that changed: what the UpdateSeq test of GeomVertexData::animate_vertices
+// (geomVertexData.cxx:937-946) does per character, for a crowd.
+extern "C" int p3cs_group_animate_instances(p3cs_group grp, const int32_t *host_instances, int count) {
+  if (grp == nullptr || count < 0 || (count > 0 && host_instances == nullptr)) return fail(P3CS_ERR_INVALID, "p3cs_group_animate_instances: bad arguments");
+  for (int i = 0; i < count; ++i)
+    if (host_instances[i] < 0 || host_instances[i] >= grp->n)
+      return fail(P3CS_ERR_INVALID, "p3cs_group_animate_instances: entry %d = %d outside the group of %d", i, host_instances[i], grp->n);
+  if (count == 0) return P3CS_OK;
+  DeviceGuard g(grp->mesh->ctx->device);
+  if (!grp->mesh->use_strip) {  // two-kernel path: its record scratch is indexed by launch position, go one by one
+    int rc = P3CS_OK;
+    for (int i = 0; i < count && rc == P3CS_OK; ++i) rc = animate_range(grp, host_instances[i], 1, false);
+    return rc;
+  }
+  if (grp->list_capacity < count) {
+    if (grp->list_dev != nullptr) {
+      CUDA_TRY(cudaStreamSynchronize(grp->mesh->ctx->stream));
+      CUDA_TRY(cudaFree(grp->list_dev));
+      grp->list_dev = nullptr;
+    }
+    CUDA_TRY(cudaMalloc(&grp->list_dev, (size_t)count * 4));
+    grp->list_capacity = count;
+  }
+  CUDA_TRY(cudaMemcpyAsync(grp->list_dev, host_instances, (size_t)count * 4, cudaMemcpyHostToDevice, grp->mesh->ctx->stream));
+  GroupDev listed = grp->dev;
+  listed.instance_list = grp->list_dev;
+  return animate_range(grp, 0, count, true, nullptr, &listed);
+}
+
 extern "C" int p3cs_group_set_profiling(p3cs_group grp, int enable) {
   if (grp == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_set_profiling: group is NULL");
   grp->profiling = enable != 0;
@@ -1234,7 +1266,7 @@ extern "C" int p3cs_group_enable_bounds(p3cs_group grp, const p3cs_column_desc *
     CUDA_TRY(cudaMalloc(&p, std::max<size_t>((size_t)grp->n * 32, 256)));
     grp->allocations.push_back(p);
     grp->bounds_buf = static_cast<float *>(p);
-    launch_bounds_init(GroupDev{nullptr, nullptr, nullptr, {}, {}, nullptr, grp->bounds_buf, 0, 0}, 0, grp->n, mesh->ctx->stream);
+    launch_bounds_init(GroupDev{nullptr, nullptr, nullptr, {}, {}, nullptr, grp->bounds_buf, 0, 0, nullptr}, 0, grp->n, mesh->ctx->stream);
   }
   grp->dev.bounds = grp->bounds_buf;
   grp->dev.bounds_output = o;
@@ -1476,6 +1508,7 @@ extern "C" int p3cs_group_pose(p3cs_group grp, p3cs_skeleton sk, int first, int 
   cudaStream_t s = grp->mesh->ctx->stream;
   if (grp->frames_capacity < count) {
     if (grp->frames_dev != nullptr) cudaFree(grp->frames_dev);
+  if (grp->list_dev != nullptr) cudaFree(grp->list_dev);
     grp->frames_dev = nullptr;
     CUDA_TRY(cudaMalloc(&grp->frames_dev, (size_t)count * sizeof(int)));
     grp->frames_capacity = count;

@@ -146,11 +146,12 @@ void launch_skin(const MeshDev &mesh, const GroupDev &grp, int first_instance, i
 }
 
 // ---- animated tight bounds for the two-kernel path; the strip kernel fuses the reduction
-__global__ void bounds_init_kernel(float *bounds, int first, int count) {
+__global__ void bounds_init_kernel(float *bounds, const int *instance_list, int first, int count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count * 8) return;
   const int k = i & 7;
-  bounds[(size_t)first * 8 + i] = k < 3 ? __int_as_float(0x7f800000) : k < 6 ? __int_as_float(0xff800000) : 0.0f;
+  const int inst = instance_list != nullptr ? instance_list[first + (i >> 3)] : first + (i >> 3);
+  bounds[(size_t)inst * 8 + k] = k < 3 ? __int_as_float(0x7f800000) : k < 6 ? __int_as_float(0xff800000) : 0.0f;
 }
 
 __global__ void __launch_bounds__(256) bounds_scan_kernel(MeshDev mesh, GroupDev grp, int first_instance, int rows_per_cta) {
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(256) bounds_scan_kernel(MeshDev mesh, GroupDev
 
 void launch_bounds_init(const GroupDev &grp, int first_instance, int count, cudaStream_t stream) {
   if (grp.bounds == nullptr || count == 0) return;
-  bounds_init_kernel<<<(count * 8 + 255) / 256, 256, 0, stream>>>(grp.bounds, first_instance, count);
+  bounds_init_kernel<<<(count * 8 + 255) / 256, 256, 0, stream>>>(grp.bounds, grp.instance_list, first_instance, count);
 }
 
 void launch_bounds_scan(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream) {

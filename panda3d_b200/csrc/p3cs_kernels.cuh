@@ -88,6 +88,8 @@ struct GroupDev {
   float *bounds;
   int bounds_output;      // output array of the float32 x 3 column the bounds are taken over
   int bounds_start;       // its byte offset in the row
+  // optional: the instances to animate (p3cs_group_animate_instances); NULL = first_instance + blockIdx.y
+  const int *instance_list;
 };
 
 // Joint hierarchy ("next" row f1): static description of a character's skeleton, joints parents-first.
@@ -118,7 +120,7 @@ int launch_strip(const MeshDev &mesh, const GroupDev &grp, int first_instance, i
 // CTAs per instance launch_strip will use (1 => bounds are stored directly, no initialisation pass needed)
 int strip_ctas_per_instance(const MeshDev &mesh, int count, int sm_count);
 // bounds: reset [first, first+count) to (+inf, -inf, 0, 0); scan the finished output arrays (two-kernel path)
-void launch_bounds_init(const GroupDev &grp, int first_instance, int count, cudaStream_t stream);
+void launch_bounds_init(const GroupDev &grp, int first_instance, int count, cudaStream_t stream);  // honours instance_list
 void launch_bounds_scan(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);
 size_t strip_smem_bytes(const MeshDev &mesh);
 int skin_rows_per_tile(const MeshDev &mesh);

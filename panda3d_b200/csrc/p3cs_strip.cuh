@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
 
   int tid;  // read once and kept in a register: the compiler otherwise re-reads SR_TID.X (long-latency S2R) per tile
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-  const int inst = first_instance + blockIdx.y;
+  const int inst = grp.instance_list != nullptr ? __ldg(grp.instance_list + first_instance + blockIdx.y) : first_instance + (int)blockIdx.y;
   const int g0 = blockIdx.x * groups_per_cta;
   const int g1 = min(mesh.num_groups, g0 + groups_per_cta);
   if (g0 >= g1) return;

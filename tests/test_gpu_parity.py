@@ -718,3 +718,41 @@ def test_animate_host_pipelined_crowd(gpu_ctx):
     finally:
         grp.close()
         dmesh.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["strip", "wide"])
+def test_animate_only_the_listed_instances(gpu_ctx, monkeypatch, path):
+    """p3cs_group_animate_instances recomputes exactly the listed instances (any order) and leaves the arrays and
+    bounds of the others as they were."""
+    monkeypatch.setenv("P3CS_PATH", path)
+    sm = synth.make_mesh(1_500, 12, 200, seed=131, texcoord=True, index_order="runs")
+    mesh = sm.flat
+    n = 40
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, n)
+    try:
+        pal0 = synth.make_palettes(12, n, 132).reshape(n, -1)
+        pal1 = synth.make_palettes(12, n, 133).reshape(n, -1)
+        grp.set_palettes(pal0)
+        grp.enable_bounds()
+        grp.animate()
+        before, bounds_before = grp.read_output(0).copy(), grp.read_bounds().copy()
+        grp.set_palettes(pal1)           # every palette changes on the device ...
+        listed = [31, 2, 17, 39, 0]
+        grp.animate_instances(listed)    # ... but only these are re-animated
+        after, bounds_after = grp.read_output(0), grp.read_bounds()
+        grp.animate()
+        full = grp.read_output(0)
+        for i in range(n):
+            if i in listed:
+                assert np.array_equal(after[i], full[i]), f"listed instance {i} was not recomputed"
+                assert np.array_equal(bounds_after[i], _expected_bounds(after[i], mesh.skin_columns[0]))
+            else:
+                assert np.array_equal(after[i], before[i]), f"instance {i} changed although it was not listed"
+                assert np.array_equal(bounds_after[i], bounds_before[i])
+        with pytest.raises(_capi.P3csError):
+            grp.animate_instances([0, n])
+    finally:
+        grp.close()
+        dmesh.close()
