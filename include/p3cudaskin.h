@@ -364,6 +364,14 @@ P3CS_EXPORT int p3cs_skeleton_destroy(p3cs_skeleton skeleton);
  * writes their palettes into the group's device buffer -- replaces Character::update +
  * p3cs_group_set_palettes: per frame the host sends one int per instance instead of T matrices. */
 P3CS_EXPORT int p3cs_group_pose(p3cs_group group, p3cs_skeleton skeleton, int first, int count, const int32_t *host_frames);
+/* The same with PartBundle::set_frame_blend_flag(true): per instance AnimControl::get_frame(), get_next_frame() and
+ * (float)get_frac(); every joint takes MovingPartMatrix::get_blend_value's blend of the two frames' values
+ * (chan/movingPartMatrix.cxx:78-198) with the bundle's blend type -- PartBundle::BlendType values; the PRC default
+ * (anim-blend-type) is normalized-linear.  One AnimControl of effect 1. */
+#define P3CS_BT_LINEAR 0
+#define P3CS_BT_NORMALIZED_LINEAR 1
+P3CS_EXPORT int p3cs_group_pose_blend(p3cs_group group, p3cs_skeleton skeleton, int first, int count, const int32_t *host_frames,
+                                      const int32_t *host_next_frames, const float *host_fracs, int blend_type);
 /* Device -> host read-back of `count` palettes (count * T * 16 floats); parity hook. */
 P3CS_EXPORT int p3cs_group_read_palettes(p3cs_group group, int first, int count, float *host_dst);
 

@@ -192,15 +192,18 @@ class _Skeleton(C.Structure):
                 ("initial_inverse", C.c_void_p), ("root_xform", C.c_void_p)]
 
 
-def pose(skel, frame: int) -> np.ndarray:
-    """CharacterJoint::_skinning_matrix of every joint at `frame` ([J,16]); palette = result[skel.palette_joint]."""
+def pose(skel, frame: int, next_frame: Optional[int] = None, frac: float = 0.0, blend_type: int = 1) -> np.ndarray:
+    """CharacterJoint::_skinning_matrix of every joint at `frame` ([J,16]); palette = result[skel.palette_joint].
+    With `next_frame` the bundle's frame-blend flag is on: values blend towards next_frame by `frac`
+    (blend_type 0 = BT_linear, 1 = BT_normalized_linear, the reference's default)."""
     arrs = [np.ascontiguousarray(a) for a in (skel.parent, skel.has_channel, skel.table_length, skel.table_offset,
                                               skel.tables if skel.tables.size else np.zeros(1, np.float32),
                                               skel.default_value, skel.initial_inverse, skel.root_xform)]
     s = _Skeleton(skel.num_joints, skel.coordinate_system, *[a.ctypes.data for a in arrs])
     out = np.empty((skel.num_joints, 16), np.float32)
-    lib().p3o_pose.restype = C.c_int
-    rc = lib().p3o_pose(C.byref(s), C.c_int(int(frame)), out.ctypes.data_as(C.c_void_p))
+    lib().p3o_pose_blend.restype = C.c_int
+    rc = lib().p3o_pose_blend(C.byref(s), C.c_int(int(frame)), C.c_int(int(frame if next_frame is None else next_frame)),
+                              C.c_float(float(frac)), C.c_int(0 if next_frame is None else 1), C.c_int(int(blend_type)), out.ctypes.data_as(C.c_void_p))
     if rc != 0:
         raise RuntimeError(f"oracle pose failed rc={rc}")
     return out

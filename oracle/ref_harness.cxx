@@ -504,15 +504,36 @@ static int cmd_egg(int argc, char **argv) {
   Case out;
   Exported ex = export_vertex_data(vd, out);
   export_skeleton(ch, ex, out);
-  std::vector<int32_t> frames;
+  // Frames with a fractional part switch on PartBundle::set_frame_blend_flag: the joints then take
+  // MovingPartMatrix::get_blend_value's BT_linear branch between get_frame() and get_next_frame()
+  // (chan/movingPartMatrix.cxx:78-113); what AnimControl reports is exported so the same triple can be replayed.
+  std::vector<int32_t> frames, next_frames;
+  std::vector<float> fracs;
+  bool blend = false;
+  for (int i = 5; i < argc; ++i) blend = blend || strchr(argv[i], '.') != nullptr;
+  if (blend) ch->get_bundle(0)->set_frame_blend_flag(true);
+  const char *bt = getenv("P3CS_BLEND_TYPE");   // "linear": PartBundle::BT_linear instead of the PRC default
+  int blend_type = 1;
+  if (bt != nullptr && strcmp(bt, "linear") == 0) {
+    ch->get_bundle(0)->set_blend_type(PartBundle::BT_linear);
+    blend_type = 0;
+  }
+  AnimControl *control = ctrls.get_anim(0);
   for (int i = 5; i < argc; ++i) {
-    int fr = atoi(argv[i]);
-    ctrls.get_anim(0)->pose(fr);
+    double fr = atof(argv[i]);
+    control->pose(fr);
     ch->force_update();
     record_frame(vd, ex, out, (int)frames.size());
-    frames.push_back(fr);
+    frames.push_back(control->get_frame());
+    next_frames.push_back(control->get_next_frame());
+    fracs.push_back((float)(PN_stdfloat)control->get_frac());
   }
   out["anim_frames"] = make_blob(DT_I32, frames, {(uint64_t)frames.size()});
+  if (blend) {
+    out["anim_next_frames"] = make_blob(DT_I32, next_frames, {(uint64_t)frames.size()});
+    out["anim_fracs"] = make_blob(DT_F32, fracs, {(uint64_t)frames.size()});
+    out["anim_blend_type"] = make_blob(DT_I32, std::vector<int32_t>{blend_type}, {1});
+  }
   fprintf(stderr, "egg: rows=%d transforms=%d blends=%d frames=%d\n", vd->get_num_rows(), (int)ex.palette.size(),
           (int)vd->get_transform_blend_table()->get_num_blends(), (int)frames.size());
   return write_case(out_path, out) ? 0 : 1;

@@ -760,32 +760,115 @@ static void mul4(float *res, const float *a, const float *b) {
       M4(res, i, j) = M4(a, i, 0) * M4(b, 0, j) + M4(a, i, 1) * M4(b, 1, j) + M4(a, i, 2) * M4(b, 2, j) + M4(a, i, 3) * M4(b, 3, j);
 }
 
-int p3o_pose(const p3o_skeleton *skel, int frame, float *skinning_out) {
-  int J = skel->num_joints, j, i, r, c;
+/* AnimChannelMatrixXfmTable::get_value (chan/animChannelMatrixXfmTable.cxx:112-124): components[i] =
+ * table[frame % size] or the default (1 for the scales, 0 otherwise; animChannelMatrixXfmTable.I:75-85),
+ * then compose_matrix -> LMatrix4f(upper3, translate) (compose_matrix_src.I:18-28). */
+static void channel_value(const p3o_skeleton *skel, int j, int frame, float *value) {
+  float comp[12], up3[9];
+  int i, r, c;
+  for (i = 0; i < 12; ++i) {
+    int len = skel->table_length[j * 12 + i];
+    comp[i] = len == 0 ? (i < 3 ? 1.0f : 0.0f) : skel->tables[skel->table_offset[j * 12 + i] + frame % len];
+  }
+  p3o_compose3(up3, comp + 0, comp + 3, comp + 6, skel->coordinate_system);
+  for (r = 0; r < 3; ++r) {
+    for (c = 0; c < 3; ++c) M4(value, r, c) = M3(up3, r, c);
+    M4(value, r, 3) = 0.0f;
+  }
+  M4(value, 3, 0) = comp[9];
+  M4(value, 3, 1) = comp[10];
+  M4(value, 3, 2) = comp[11];
+  M4(value, 3, 3) = 1.0f;
+}
+
+/* One table component at a frame (AnimChannelMatrixXfmTable::get_scale / get_shear / get_value). */
+static float channel_component(const p3o_skeleton *skel, int j, int i, int frame) {
+  int len = skel->table_length[j * 12 + i];
+  return len == 0 ? (i < 3 ? 1.0f : 0.0f) : skel->tables[skel->table_offset[j * 12 + i] + frame % len];
+}
+
+/* AnimChannelMatrixXfmTable::get_value_no_scale_shear (animChannelMatrixXfmTable.cxx:131-149) */
+static void channel_value_no_scale_shear(const p3o_skeleton *skel, int j, int frame, float *value) {
+  float comp[12], up3[9];
+  int i, r, c;
+  comp[0] = comp[1] = comp[2] = 1.0f;
+  comp[3] = comp[4] = comp[5] = 0.0f;
+  for (i = 6; i < 12; ++i) comp[i] = channel_component(skel, j, i, frame);
+  p3o_compose3(up3, comp + 0, comp + 3, comp + 6, skel->coordinate_system);
+  for (r = 0; r < 3; ++r) {
+    for (c = 0; c < 3; ++c) M4(value, r, c) = M3(up3, r, c);
+    M4(value, r, 3) = 0.0f;
+  }
+  M4(value, 3, 0) = comp[9];
+  M4(value, 3, 1) = comp[10];
+  M4(value, 3, 2) = comp[11];
+  M4(value, 3, 3) = 1.0f;
+}
+
+/* blend_type: 0 BT_linear, 1 BT_normalized_linear (PartBundle::BlendType, chan/partBundle.h; the default
+ * comes from the PRC variable anim-blend-type = normalized-linear, chan/partBundle.cxx:41-42). */
+int p3o_pose_blend(const p3o_skeleton *skel, int frame, int next_frame, float frac, int frame_blend, int blend_type,
+                   float *skinning_out) {
+  int J = skel->num_joints, j, k;
   float *net = (float *)malloc((size_t)(J > 0 ? J : 1) * 16 * sizeof(float));
   if (!net) return -2;
   for (j = 0; j < J; ++j) {
     float value[16];
-    if (skel->has_channel[j]) {
-      /* AnimChannelMatrixXfmTable::get_value: components[i] = table[frame % size] or the default
-       * (1 for the scales, 0 otherwise; animChannelMatrixXfmTable.I:75-85), then compose_matrix */
-      float comp[12], up3[9];
-      for (i = 0; i < 12; ++i) {
-        int len = skel->table_length[j * 12 + i];
-        comp[i] = len == 0 ? (i < 3 ? 1.0f : 0.0f) : skel->tables[skel->table_offset[j * 12 + i] + frame % len];
-      }
-      p3o_compose3(up3, comp + 0, comp + 3, comp + 6, skel->coordinate_system);
-      /* LMatrix4f(upper3, translate), compose_matrix_src.I:18-28 */
-      for (r = 0; r < 3; ++r) {
-        for (c = 0; c < 3; ++c) M4(value, r, c) = M3(up3, r, c);
-        M4(value, r, 3) = 0.0f;
-      }
-      M4(value, 3, 0) = comp[9];
-      M4(value, 3, 1) = comp[10];
-      M4(value, 3, 2) = comp[11];
-      M4(value, 3, 3) = 1.0f;
-    } else {
+    if (!skel->has_channel[j]) {
       memcpy(value, skel->default_value + (size_t)j * 16, sizeof(value));
+    } else if (!frame_blend) {
+      channel_value(skel, j, frame, value);  /* the single-value case, movingPartMatrix.cxx:71-76 */
+    } else {
+      /* one control of effect 1 with the frame-blend flag: weights e0 = effect * (1 - frac), e1 = effect * frac;
+       * sums start from zero and are divided by net_effect through a reciprocal (LMatrix4 / LVecBase3 operator /=) */
+      const float effect = 1.0f;
+      const float e0 = effect * (1.0f - frac), e1 = effect * frac;
+      const float recip = 1.0f / (0.0f + effect);
+      float v0[16], v1[16], nv[16];
+      if (blend_type == 0) {  /* BT_linear, movingPartMatrix.cxx:82-122 */
+        channel_value(skel, j, frame, v0);
+        channel_value(skel, j, next_frame, v1);
+        for (k = 0; k < 16; ++k) {
+          float n = 0.0f;
+          n = n + v0[k] * e0;
+          n = n + v1[k] * e1;
+          value[k] = n * recip;
+        }
+      } else {  /* BT_normalized_linear, movingPartMatrix.cxx:125-198 */
+        float scale[3], shear[3], false_scale[3], false_shear[3], hpr[3], up3[9], out3[9];
+        int r, c;
+        channel_value_no_scale_shear(skel, j, frame, v0);
+        channel_value_no_scale_shear(skel, j, next_frame, v1);
+        for (k = 0; k < 16; ++k) {
+          float n = 0.0f;
+          n = n + v0[k] * e0;
+          n = n + v1[k] * e1;
+          nv[k] = n * recip;
+        }
+        for (k = 0; k < 3; ++k) {
+          float sc = 0.0f, sh = 0.0f;
+          sc = sc + channel_component(skel, j, k, frame) * e0;
+          sc = sc + channel_component(skel, j, k, next_frame) * e1;
+          sh = sh + channel_component(skel, j, 3 + k, frame) * e0;
+          sh = sh + channel_component(skel, j, 3 + k, next_frame) * e1;
+          scale[k] = sc * recip;
+          shear[k] = sh * recip;
+        }
+        /* decompose_matrix(net_value, false_scale, false_shear, hpr, translate); compose_matrix(_value, scale,
+         * shear, hpr, translate) (compose_matrix_src.I:18-60) */
+        for (r = 0; r < 3; ++r)
+          for (c = 0; c < 3; ++c) M3(up3, r, c) = M4(nv, r, c);
+        p3o_decompose3(up3, skel->coordinate_system, false_scale, false_shear, hpr);
+        p3o_compose3(out3, scale, shear, hpr, skel->coordinate_system);
+        for (r = 0; r < 3; ++r) {
+          for (c = 0; c < 3; ++c) M4(value, r, c) = M3(out3, r, c);
+          M4(value, r, 3) = 0.0f;
+        }
+        M4(value, 3, 0) = M4(nv, 3, 0);
+        M4(value, 3, 1) = M4(nv, 3, 1);
+        M4(value, 3, 2) = M4(nv, 3, 2);
+        M4(value, 3, 3) = 1.0f;
+      }
     }
     /* CharacterJoint::update_internals: _net_transform = _value * parent net (or root xform) */
     mul4(net + (size_t)j * 16, value, skel->parent[j] >= 0 ? net + (size_t)skel->parent[j] * 16 : skel->root_xform);
@@ -794,4 +877,8 @@ int p3o_pose(const p3o_skeleton *skel, int frame, float *skinning_out) {
   }
   free(net);
   return 0;
+}
+
+int p3o_pose(const p3o_skeleton *skel, int frame, float *skinning_out) {
+  return p3o_pose_blend(skel, frame, frame, 0.0f, 0, 1, skinning_out);
 }

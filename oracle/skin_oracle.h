@@ -96,6 +96,11 @@ typedef struct p3o_skeleton {
 } p3o_skeleton;
 /* skinning_out: [J][16] = CharacterJoint::_skinning_matrix of every joint at `frame`. */
 int p3o_pose(const p3o_skeleton *skel, int frame, float *skinning_out);
+/* With PartBundle::set_frame_blend_flag(true): the values at get_frame() and get_next_frame() blended by
+ * get_frac() (MovingPartMatrix::get_blend_value with one control of effect 1; chan/movingPartMatrix.cxx:78-198).
+ * blend_type: 0 BT_linear, 1 BT_normalized_linear (the PRC default, anim-blend-type).  frame_blend = 0 is p3o_pose. */
+int p3o_pose_blend(const p3o_skeleton *skel, int frame, int next_frame, float frac, int frame_blend, int blend_type,
+                   float *skinning_out);
 
 /* Individual pieces, exported for unit tests against the reference's adjacent
  * tests (tests/linmath/test_lmatrix4.py, test_compose_matrix.py). */

@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = [
     "p3cs_host_register", "p3cs_host_unregister",
     "p3cs_shareable_alloc", "p3cs_shareable_import", "p3cs_shareable_free", "p3cs_group_animate_host",
     "p3cs_hardware_from_blends", "p3cs_blends_from_hardware", "p3cs_group_animate_instances",
+    "p3cs_group_pose_blend",
 ]
 
 
@@ -412,6 +413,16 @@ class Group:
         """Joint hierarchy on the GPU: one animation frame per instance in, palettes written on the device."""
         f = np.ascontiguousarray(frames, np.int32)
         _check(lib().p3cs_group_pose(self.handle, skeleton.handle, first, int(f.size), f.ctypes.data))
+
+    def pose_blend(self, skeleton, frames, next_frames, fracs, blend_type: int = 1, first: int = 0) -> None:
+        """p3cs_group_pose_blend: frame blending on (blend_type 0 BT_linear, 1 BT_normalized_linear)."""
+        f = np.ascontiguousarray(frames, np.int32)
+        nf = np.ascontiguousarray(next_frames, np.int32)
+        fr = np.ascontiguousarray(fracs, np.float32)
+        L = lib()
+        L.p3cs_group_pose_blend.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _check(L.p3cs_group_pose_blend(self.handle, skeleton.handle, first, int(f.size), f.ctypes.data, nf.ctypes.data, fr.ctypes.data,
+                                       int(blend_type)))
 
     def read_palettes(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
         count = self.n - first if count is None else count

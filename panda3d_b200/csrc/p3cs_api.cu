@@ -1497,26 +1497,49 @@ extern "C" int p3cs_skeleton_destroy(p3cs_skeleton sk) {
   return P3CS_OK;
 }
 
-extern "C" int p3cs_group_pose(p3cs_group grp, p3cs_skeleton sk, int first, int count, const int32_t *host_frames) {
-  int rc = check_span(grp, first, count, "p3cs_group_pose");
+static int pose_common(p3cs_group grp, p3cs_skeleton sk, int first, int count, const int32_t *host_frames,
+                       const int32_t *host_next_frames, const float *host_fracs, int blend_type, const char *what) {
+  int rc = check_span(grp, first, count, what);
   if (rc != P3CS_OK) return rc;
-  if (sk == nullptr || host_frames == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_pose: NULL argument");
+  if (sk == nullptr || host_frames == nullptr) return fail(P3CS_ERR_INVALID, "%s: NULL argument", what);
   if (sk->num_palette != grp->mesh->dev.num_transforms)
     return fail(P3CS_ERR_INVALID, "skeleton feeds %d palette slots, the mesh has %d transforms", sk->num_palette, grp->mesh->dev.num_transforms);
   if (count == 0) return P3CS_OK;
   DeviceGuard g(grp->mesh->ctx->device);
   cudaStream_t s = grp->mesh->ctx->stream;
-  if (grp->frames_capacity < count) {
-    if (grp->frames_dev != nullptr) cudaFree(grp->frames_dev);
-  if (grp->list_dev != nullptr) cudaFree(grp->list_dev);
+  if (grp->frames_capacity < count) {  // frames, next frames, fractions: three arrays of `capacity` words
+    if (grp->frames_dev != nullptr) {
+      CUDA_TRY(cudaStreamSynchronize(s));
+      CUDA_TRY(cudaFree(grp->frames_dev));
+    }
     grp->frames_dev = nullptr;
-    CUDA_TRY(cudaMalloc(&grp->frames_dev, (size_t)count * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&grp->frames_dev, (size_t)count * 3 * sizeof(int)));
     grp->frames_capacity = count;
   }
-  CUDA_TRY(cudaMemcpyAsync(grp->frames_dev, host_frames, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, s));
-  launch_pose(sk->dev, const_cast<float *>(grp->dev.palettes), sk->num_palette, grp->frames_dev, first, count, s);
+  int *frames_dev = grp->frames_dev, *next_dev = nullptr;
+  float *fracs_dev = nullptr;
+  CUDA_TRY(cudaMemcpyAsync(frames_dev, host_frames, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, s));
+  if (host_next_frames != nullptr) {
+    next_dev = grp->frames_dev + grp->frames_capacity;
+    fracs_dev = reinterpret_cast<float *>(grp->frames_dev + 2 * (size_t)grp->frames_capacity);
+    CUDA_TRY(cudaMemcpyAsync(next_dev, host_next_frames, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(fracs_dev, host_fracs, (size_t)count * sizeof(float), cudaMemcpyHostToDevice, s));
+  }
+  launch_pose(sk->dev, const_cast<float *>(grp->dev.palettes), sk->num_palette, frames_dev, next_dev, fracs_dev, blend_type, first, count, s);
   CUDA_TRY(cudaGetLastError());
   return P3CS_OK;
+}
+
+extern "C" int p3cs_group_pose(p3cs_group grp, p3cs_skeleton sk, int first, int count, const int32_t *host_frames) {
+  return pose_common(grp, sk, first, count, host_frames, nullptr, nullptr, P3CS_BT_NORMALIZED_LINEAR, "p3cs_group_pose");
+}
+
+extern "C" int p3cs_group_pose_blend(p3cs_group grp, p3cs_skeleton sk, int first, int count, const int32_t *host_frames,
+                                     const int32_t *host_next_frames, const float *host_fracs, int blend_type) {
+  if (host_next_frames == nullptr || host_fracs == nullptr) return fail(P3CS_ERR_INVALID, "p3cs_group_pose_blend: NULL argument");
+  if (blend_type != P3CS_BT_LINEAR && blend_type != P3CS_BT_NORMALIZED_LINEAR)
+    return fail(P3CS_ERR_UNSUPPORTED, "p3cs_group_pose_blend: blend type %d (only BT_linear and BT_normalized_linear)", blend_type);
+  return pose_common(grp, sk, first, count, host_frames, host_next_frames, host_fracs, blend_type, "p3cs_group_pose_blend");
 }
 
 extern "C" int p3cs_group_read_palettes(p3cs_group grp, int first, int count, float *host_dst) {

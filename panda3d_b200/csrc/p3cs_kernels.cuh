@@ -109,8 +109,8 @@ struct SkeletonDev {
   const float *root_xform;    // [16]
   const int *palette_joint;   // [T]
 };
-void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, const int *frames_dev, int first_instance, int count,
-                 cudaStream_t stream);
+void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, const int *frames_dev, const int *next_frames_dev,
+                 const float *fracs_dev, int blend_type, int first_instance, int count, cudaStream_t stream);
 
 void launch_blend(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);
 void launch_skin(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);

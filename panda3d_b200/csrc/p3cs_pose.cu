@@ -9,8 +9,9 @@
 // __syncthreads per tree level) and writes
 // the palette straight into the group's device buffer: with it a crowd needs one int per
 // instance and frame from the host instead of T x 64 bytes of matrices.
-// Covers the reference's normal case: one AnimControl, no frame blending
-// (chan/movingPartMatrix.cxx:71-76); same -fmad=false arithmetic as the rest of the library.
+// Covers one AnimControl, without frame blending (chan/movingPartMatrix.cxx:71-76) or with it
+// (PartBundle::set_frame_blend_flag: BT_linear and BT_normalized_linear, :78-198); same -fmad=false arithmetic
+// as the rest of the library.
 #include "p3cs_device.cuh"
 
 namespace p3cs {
@@ -24,8 +25,39 @@ __device__ __forceinline__ void mul4(float *res, const float *a, const float *b)
       res[i * 4 + j] = a[i * 4 + 0] * b[0 * 4 + j] + a[i * 4 + 1] * b[1 * 4 + j] + a[i * 4 + 2] * b[2 * 4 + j] + a[i * 4 + 3] * b[3 * 4 + j];
 }
 
+// One table component of a joint at a frame: table[frame % size], or the default of an empty table
+// (1 for the scales, 0 otherwise; animChannelMatrixXfmTable.I:75-85).
+__device__ __forceinline__ float channel_component(const SkeletonDev &skel, int j, int i, int frame) {
+  const int len = __ldg(skel.table_length + j * 12 + i);
+  return len == 0 ? (i < 3 ? 1.0f : 0.0f) : __ldg(skel.tables + __ldg(skel.table_offset + j * 12 + i) + frame % len);
+}
+
+// AnimChannelMatrixXfmTable::get_value (animChannelMatrixXfmTable.cxx:112-124), or get_value_no_scale_shear
+// (:131-149) with unit scale and zero shear: compose_matrix of the components -> LMatrix4f(upper3, translate).
+__device__ __forceinline__ void channel_value(const SkeletonDev &skel, int j, int frame, bool no_scale_shear, float *value) {
+  float comp[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) comp[i] = (no_scale_shear && i < 6) ? (i < 3 ? 1.0f : 0.0f) : channel_component(skel, j, i, frame);
+  Mat3 up3;
+  compose3(up3, comp + 0, comp + 3, comp + 6, skel.coordinate_system);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) value[r * 4 + c] = up3.m[r][c];
+    value[r * 4 + 3] = 0.0f;
+  }
+  value[12] = comp[9];
+  value[13] = comp[10];
+  value[14] = comp[11];
+  value[15] = 1.0f;
+}
+
+// next_frames == nullptr: one AnimControl, no frame blending (movingPartMatrix.cxx:71-76).  Otherwise the bundle's
+// frame-blend flag is on: the values at frame and next_frame are blended by frac, blend_type 0 = BT_linear
+// (:82-122), 1 = BT_normalized_linear (:125-198, the PRC default), one control of effect 1.
+template <bool BLEND>
 __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *palettes, int num_transforms, const int *frames,
-                                                    int first_instance) {
+                                                    const int *next_frames, const float *fracs, int blend_type, int first_instance) {
   extern __shared__ float smem_pose[];  // [J][16] local values, then [J][16] net transforms of this instance
   const int inst = first_instance + blockIdx.x;
   const int frame = __ldg(frames + blockIdx.x);
@@ -37,25 +69,55 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
   // (AnimChannelMatrixXfmTable::get_value -> compose_matrix, or the default value)
   for (int j = threadIdx.x; j < J; j += blockDim.x) {
     float value[16];
-    if (__ldg(skel.has_channel + j)) {
-      float comp[12];
+    if (BLEND && __ldg(skel.has_channel + j)) {
+      const int next_frame = __ldg(next_frames + blockIdx.x);
+      const float frac = __ldg(fracs + blockIdx.x);
+      // weights e0 = effect * (1 - frac), e1 = effect * frac with effect = 1; the sums start from zero and are
+      // divided by net_effect through a reciprocal (LMatrix4 / LVecBase3 operator /=)
+      const float effect = 1.0f;
+      const float e0 = effect * (1.0f - frac), e1 = effect * frac;
+      const float recip = 1.0f / (0.0f + effect);
+      float v0[16], v1[16];
+      channel_value(skel, j, frame, blend_type != 0, v0);
+      channel_value(skel, j, next_frame, blend_type != 0, v1);
 #pragma unroll
-      for (int i = 0; i < 12; ++i) {
-        const int len = __ldg(skel.table_length + j * 12 + i);
-        comp[i] = len == 0 ? (i < 3 ? 1.0f : 0.0f) : __ldg(skel.tables + __ldg(skel.table_offset + j * 12 + i) + frame % len);
+      for (int k = 0; k < 16; ++k) {
+        float n = 0.0f;
+        n = n + v0[k] * e0;
+        n = n + v1[k] * e1;
+        value[k] = n * recip;
       }
-      Mat3 up3;
-      compose3(up3, comp + 0, comp + 3, comp + 6, skel.coordinate_system);
+      if (blend_type != 0) {
+        float scale[3], shear[3], false_scale[3], false_shear[3], hpr[3];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
+        for (int k = 0; k < 3; ++k) {
+          float sc = 0.0f, sh = 0.0f;
+          sc = sc + channel_component(skel, j, k, frame) * e0;
+          sc = sc + channel_component(skel, j, k, next_frame) * e1;
+          sh = sh + channel_component(skel, j, 3 + k, frame) * e0;
+          sh = sh + channel_component(skel, j, 3 + k, next_frame) * e1;
+          scale[k] = sc * recip;
+          shear[k] = sh * recip;
+        }
+        // decompose_matrix(net_value, false_scale, false_shear, hpr, translate), then
+        // compose_matrix(_value, scale, shear, hpr, translate)
+        Mat3 up3, out3;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) value[r * 4 + c] = up3.m[r][c];
-        value[r * 4 + 3] = 0.0f;
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) up3.m[r][c] = value[r * 4 + c];
+        decompose3(up3, skel.coordinate_system, false_scale, false_shear, hpr);
+        compose3(out3, scale, shear, hpr, skel.coordinate_system);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) value[r * 4 + c] = out3.m[r][c];
+          value[r * 4 + 3] = 0.0f;
+        }
+        value[15] = 1.0f;  // translate = row 3 of the blended matrix stays
       }
-      value[12] = comp[9];
-      value[13] = comp[10];
-      value[14] = comp[11];
-      value[15] = 1.0f;
+    } else if (__ldg(skel.has_channel + j)) {
+      channel_value(skel, j, frame, false, value);
     } else {
 #pragma unroll
       for (int k = 0; k < 16; ++k) value[k] = __ldg(skel.default_value + j * 16 + k);
@@ -102,14 +164,21 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
   }
 }
 
-void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, const int *frames_dev, int first_instance, int count,
-                 cudaStream_t stream) {
+void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, const int *frames_dev, const int *next_frames_dev,
+                 const float *fracs_dev, int blend_type, int first_instance, int count, cudaStream_t stream) {
   if (count == 0 || skel.num_joints == 0) return;
   const size_t smem = (size_t)skel.num_joints * 128;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int threads = ((skel.num_joints + 31) / 32) * 32;
   if (threads > 256) threads = 256;
-  pose_kernel<<<count, threads, smem, stream>>>(skel, palettes, num_transforms, frames_dev, first_instance);
+  if (next_frames_dev != nullptr) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(pose_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pose_kernel<true><<<count, threads, smem, stream>>>(skel, palettes, num_transforms, frames_dev, next_frames_dev, fracs_dev, blend_type,
+                                                        first_instance);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(pose_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pose_kernel<false><<<count, threads, smem, stream>>>(skel, palettes, num_transforms, frames_dev, nullptr, nullptr, blend_type,
+                                                         first_instance);
+  }
 }
 
 }  // namespace p3cs

@@ -94,6 +94,13 @@ def main():
     subprocess.run([HARNESS, "egg", model, anim, out, "0", "10", "37", "59"], check=True, timeout=120,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     print("wrote", out, os.path.getsize(out))
+    # the same Actor with PartBundle::set_frame_blend_flag(true), posed between frames (joint hierarchy fixture, f1)
+    os.makedirs(os.path.join(HERE, "skeleton"), exist_ok=True)
+    for suffix, env in (("", {}), ("_linear", {"P3CS_BLEND_TYPE": "linear"})):   # anim-blend-type default, then BT_linear
+        out = os.path.join(HERE, "skeleton", f"panda_walk4_frame_blend{suffix}.p3cs")
+        subprocess.run([HARNESS, "egg", model, anim, out, "0.5", "10.25", "37.0", "58.75", "3.999"], check=True, timeout=120,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env={**os.environ, **env})
+        print("wrote", out, os.path.getsize(out))
 
 
 if __name__ == "__main__":

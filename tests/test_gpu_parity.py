@@ -756,3 +756,49 @@ def test_animate_only_the_listed_instances(gpu_ctx, monkeypatch, path):
     finally:
         grp.close()
         dmesh.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture", ["panda_walk4_frame_blend", "panda_walk4_frame_blend_linear"])
+def test_joint_hierarchy_with_frame_blending(gpu_ctx, fixture):
+    """f1 with PartBundle::set_frame_blend_flag(true): p3cs_group_pose_blend reproduces the reference's skinning
+    matrices between frames (BT_normalized_linear, the PRC default, and BT_linear) within the float contract
+    (compose / decompose go through libm), and pose -> animate the reference's animated vertices."""
+    from conftest import GOLDEN_DIR
+    from panda3d_b200.flat import skeleton_from_case
+    case = load_case(os.path.join(GOLDEN_DIR, "skeleton", fixture + ".p3cs"))
+    mesh, skel = mesh_from_case(case), skeleton_from_case(case)
+    bt = int(case["anim_blend_type"][0])
+    frames, nxt, fracs = case["anim_frames"], case["anim_next_frames"], case["anim_fracs"]
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    dskel = _capi.Skeleton(gpu_ctx, skel)
+    grp = _capi.Group(dmesh, len(frames))
+    try:
+        grp.pose_blend(dskel, frames, nxt, fracs, bt)
+        pal = grp.read_palettes()
+        ref = case["palette"]
+        scale = np.abs(ref).max(axis=(1, 2), keepdims=True)
+        assert (np.abs(pal - ref) / scale).max() <= REL_TOL
+        grp.animate()
+        out = grp.read_output(0)
+        for fi in range(len(frames)):
+            compare_outputs(mesh, [out[fi]], [case["expect0"][fi]], f"{fixture} frame {frames[fi]}+{fracs[fi]}")
+        # against the oracle on a random rig, both blend types
+        sk = synth.make_skeleton(40, 16, seed=141)
+        dsk = _capi.Skeleton(gpu_ctx, sk)
+        sm = synth.make_mesh(500, 40, 60, seed=142)
+        dm = _capi.Mesh(gpu_ctx, sm.flat)
+        g2 = _capi.Group(dm, 6)
+        f = np.arange(6, dtype=np.int32) * 3
+        n = (f + 1) % 16
+        fr = np.linspace(0.0, 0.9, 6).astype(np.float32)
+        g2.pose_blend(dsk, f, n, fr, bt)
+        got = g2.read_palettes()
+        for i in range(6):
+            want = oracle.pose(sk, int(f[i]), int(n[i]), float(fr[i]), bt)[sk.palette_joint]
+            assert (np.abs(got[i] - want) / np.abs(want).max()).max() <= REL_TOL
+        g2.close(); dm.close(); dsk.close()
+    finally:
+        grp.close()
+        dskel.close()
+        dmesh.close()

@@ -77,3 +77,25 @@ def test_oracle_pose_matches_reference_skinning_matrices():
     for fi, frame in enumerate(case["anim_frames"]):
         skin = oracle.pose(skel, int(frame))
         assert np.array_equal(skin[skel.palette_joint].view(np.uint32), case["palette"][fi].view(np.uint32))
+
+
+@pytest.mark.parametrize("fixture", ["panda_walk4_frame_blend", "panda_walk4_frame_blend_linear"])
+def test_oracle_pose_with_frame_blending_matches_reference(fixture):
+    """The same with PartBundle::set_frame_blend_flag(true) and the Actor posed BETWEEN frames
+    (tests/golden/skeleton/panda_walk4_frame_blend.p3cs: MovingPartMatrix::get_blend_value, BT_linear):
+    bit for bit the reference's skinning matrices, and the animated vertices that follow from them."""
+    import os
+    from conftest import GOLDEN_DIR
+    from panda3d_b200.flat import mesh_from_case, skeleton_from_case
+    case = load_case(os.path.join(GOLDEN_DIR, "skeleton", fixture + ".p3cs"))
+    blend_type = int(case["anim_blend_type"][0])
+    skel, mesh = skeleton_from_case(case), mesh_from_case(case)
+    fracs = case["anim_fracs"]
+    assert (fracs > 0).any() and (fracs == 0).any()
+    om = oracle.OracleMesh(mesh)
+    for fi, (frame, nxt, frac) in enumerate(zip(case["anim_frames"], case["anim_next_frames"], fracs)):
+        skin = oracle.pose(skel, int(frame), int(nxt), float(frac), blend_type)
+        pal = skin[skel.palette_joint]
+        assert np.array_equal(pal.view(np.uint32), case["palette"][fi].view(np.uint32)), f"frame {frame}+{frac}"
+        outs, _, _ = om.animate(pal)
+        assert np.array_equal(outs[0].reshape(-1), np.asarray(case["expect0"][fi]).reshape(-1))
