@@ -2,6 +2,8 @@
 // The kernel template is instantiated per mode in p3cs_strip_inst_*.cu.
 #include "p3cs_strip.cuh"
 
+#include <cstdlib>
+
 namespace p3cs {
 
 #define P3CS_EXTERN_MODE(M)                                                                                             \
@@ -48,7 +50,12 @@ static int pick_mode(const MeshDev &mesh) {
 // strips of whole record groups: enough of them to fill every SM several times over, yet as
 // long as possible so the palette is staged rarely
 static int strip_partition(const MeshDev &mesh, int count, int sm_count, int *groups_per_cta) {
-  const long long target_ctas = (long long)sm_count * 24;
+  static const int per_sm = [] {  // CTAs per SM the partition aims for (P3CS_STRIP_CTAS_PER_SM: tuning aid)
+    const char *e = getenv("P3CS_STRIP_CTAS_PER_SM");
+    const int v = e != nullptr ? atoi(e) : 0;
+    return v > 0 ? v : 24;
+  }();
+  const long long target_ctas = (long long)sm_count * per_sm;
   long long gpc = ((long long)mesh.num_groups * count + target_ctas - 1) / target_ctas;
   if (gpc < 1) gpc = 1;
   if (gpc > mesh.num_groups) gpc = mesh.num_groups;
