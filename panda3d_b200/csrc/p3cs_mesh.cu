@@ -1,0 +1,494 @@
+// p3cs_mesh.cu -- p3cs_mesh_create: the one-time flattening / upload of a GeomVertexData's static half
+// (replaces the per-frame copy_from, geomVertexData.cxx:1460) and the tables the strip kernel runs on:
+// dynamic columns, the shared-memory plan, record groups with their conflict-aware record order, the
+// per-row morph CSR.  Host C++.
+#include "p3cs_internal.h"
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace p3cs;
+
+// ------------------------------------------------------------------ mesh
+static int check_column(const p3cs_mesh_desc *d, const p3cs_column_desc &c, const char *what) {
+  if (c.array < 0 || c.array >= d->num_arrays) return p3cs_fail(P3CS_ERR_INVALID, "%s: array %d out of range", what, c.array);
+  const int stride = d->arrays[c.array].stride;
+  if (c.start < 0 || c.num_values < 1 || c.start + c.num_values * numeric_bytes(c.numeric_type) > stride)
+    return p3cs_fail(P3CS_ERR_INVALID, "%s: column [%d,+%d x %d) exceeds stride %d", what, c.start, c.num_values,
+                numeric_bytes(c.numeric_type), stride);
+  return P3CS_OK;
+}
+
+static int check_ranges(const int32_t *ranges, int count, int num_rows, const char *what) {
+  int prev_end = 0;
+  for (int i = 0; i < count; ++i) {
+    const int b = ranges[2 * i], e = ranges[2 * i + 1];
+    if (b < prev_end || e <= b || e > num_rows)
+      return p3cs_fail(P3CS_ERR_INVALID, "%s: subrange %d = [%d,%d) is not a sorted, disjoint, non-empty range within %d rows", what, i, b, e, num_rows);
+    prev_end = e;
+  }
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_mesh *out) {
+  if (out == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_mesh_create: out is NULL");
+  *out = nullptr;
+  if (ctx == nullptr || d == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_mesh_create: NULL argument");
+  if (d->struct_size != sizeof(p3cs_mesh_desc))
+    return p3cs_fail(P3CS_ERR_INVALID, "p3cs_mesh_desc::struct_size %u != %zu (header mismatch)", d->struct_size, sizeof(p3cs_mesh_desc));
+  if (d->num_rows < 0 || d->num_arrays < 0 || (d->num_arrays > 0 && d->arrays == nullptr))
+    return p3cs_fail(P3CS_ERR_INVALID, "bad num_rows / arrays");
+  int cs = d->coordinate_system == 0 ? P3CS_CS_ZUP_RIGHT : d->coordinate_system;
+  if (cs < P3CS_CS_ZUP_RIGHT || cs > P3CS_CS_YUP_LEFT) return p3cs_fail(P3CS_ERR_INVALID, "bad coordinate_system %d", cs);
+  const int N = d->num_rows;
+  DeviceGuard g(ctx->device);
+
+  p3cs_mesh mesh = new (std::nothrow) p3cs_mesh_s;
+  if (mesh == nullptr) return p3cs_fail(P3CS_ERR_NOMEM, "out of host memory");
+  mesh->ctx = ctx;
+  MeshDev &m = mesh->dev;
+  m.num_rows = N;
+  m.coordinate_system = cs;
+  m.num_transforms = d->num_transforms;
+  m.num_blends = d->num_blends;
+  m.num_sliders = d->num_sliders;
+  int rc = P3CS_OK;
+  auto bail = [&](int code) {
+    p3cs_mesh_destroy(mesh);
+    return code;
+  };
+
+  // ---- output arrays: static image uploaded once (replaces the per-frame copy_from)
+  std::vector<int> out_of_array(d->num_arrays, -1);
+  for (int a = 0; a < d->num_arrays; ++a) {
+    const p3cs_array_desc &ad = d->arrays[a];
+    if (ad.stride <= 0 || (N > 0 && ad.data == nullptr)) return bail(p3cs_fail(P3CS_ERR_INVALID, "array %d: bad stride/data", a));
+    if (!ad.is_output) continue;
+    if (m.num_outputs >= kMaxOutputs) return bail(p3cs_fail(P3CS_ERR_UNSUPPORTED, "more than %d output arrays", kMaxOutputs));
+    if (ad.stride % 4 != 0) return bail(p3cs_fail(P3CS_ERR_UNSUPPORTED, "output array %d: stride %d is not a multiple of 4", a, ad.stride));
+    out_of_array[a] = m.num_outputs;
+    m.stride[m.num_outputs] = ad.stride;
+    if ((rc = upload<uint8_t>(mesh, static_cast<const uint8_t *>(ad.data), (size_t)N * ad.stride, &m.src[m.num_outputs])) != P3CS_OK) return bail(rc);
+    ++m.num_outputs;
+  }
+
+  // ---- dynamic columns: skinned columns, then morph bases
+  auto find_dyn = [&](int output, int start) {
+    for (int c = 0; c < m.num_dyn; ++c)
+      if (m.dyn[c].output == output && m.dyn[c].start == start) return c;
+    return -1;
+  };
+  const bool has_blend = d->blend_column.array >= 0 && d->num_skin_columns > 0;
+  for (int i = 0; i < d->num_skin_columns; ++i) {
+    const p3cs_column_desc &c = d->skin_columns[i];
+    if ((rc = check_column(d, c, "skin column")) != P3CS_OK) return bail(rc);
+    if (out_of_array[c.array] < 0) return bail(p3cs_fail(P3CS_ERR_INVALID, "skin column %d lives in a non-output array", i));
+    if ((c.numeric_type != P3CS_NT_FLOAT32 && c.numeric_type != P3CS_NT_FLOAT64) || (c.num_values != 3 && c.num_values != 4))
+      return bail(p3cs_fail(P3CS_ERR_UNSUPPORTED, "skin column %d: only float32 / float64 x 3 / x 4 columns are supported (got type %d x %d)", i, c.numeric_type, c.num_values));
+    if (c.start % 4 != 0) return bail(p3cs_fail(P3CS_ERR_UNSUPPORTED, "skin column %d: start %d not 4-byte aligned", i, c.start));
+    int skin = c.contents == P3CS_C_POINT ? 1 : c.contents == P3CS_C_VECTOR ? 2 : c.contents == P3CS_C_NORMAL ? 3 : 0;
+    if (skin == 0) return bail(p3cs_fail(P3CS_ERR_INVALID, "skin column %d: contents %d is not point/vector/normal", i, c.contents));
+    if (m.num_dyn >= kMaxDynColumns) return bail(p3cs_fail(P3CS_ERR_UNSUPPORTED, "more than %d animated columns", kMaxDynColumns));
+    DynColumn &dc = m.dyn[m.num_dyn++];
+    dc.output = (int16_t)out_of_array[c.array];
+    dc.start = (int16_t)c.start;
+    dc.num_values = (int8_t)c.num_values;
+    dc.skin = (int8_t)skin;
+    dc.homogeneous = 0;
+    dc.f64 = c.numeric_type == P3CS_NT_FLOAT64 ? 1 : 0;
+    if (c.num_values == 4) m.full_records = 1;
+  }
+
+  // column order is semantically irrelevant (columns are independent); a canonical order
+  // point(s), normal(s), vector(s) lets the strip kernel pick a specialised variant
+  std::stable_sort(m.dyn, m.dyn + m.num_dyn, [](const DynColumn &a, const DynColumn &b) {
+    auto key = [](int skin) { return skin == 1 ? 0 : skin == 3 ? 1 : 2; };
+    return key(a.skin) < key(b.skin);
+  });
+
+  // ---- transform_blend index column -> dense u16/u32
+  if (d->blend_column.array >= 0) {
+    const p3cs_column_desc &bc = d->blend_column;
+    if ((rc = check_column(d, bc, "transform_blend column")) != P3CS_OK) return bail(rc);
+    if (bc.numeric_type != P3CS_NT_UINT8 && bc.numeric_type != P3CS_NT_UINT16 && bc.numeric_type != P3CS_NT_UINT32)
+      return bail(p3cs_fail(P3CS_ERR_UNSUPPORTED, "transform_blend column of numeric type %d", bc.numeric_type));
+    if (d->num_blends < 0 || d->num_transforms < 0 || d->blend_offsets == nullptr)
+      return bail(p3cs_fail(P3CS_ERR_INVALID, "blend table missing"));
+    if ((rc = check_ranges(d->row_ranges, d->num_row_ranges, N, "TransformBlendTable rows")) != P3CS_OK) return bail(rc);
+    const int nnz = d->blend_offsets[d->num_blends];
+    if (d->blend_offsets[0] != 0) return bail(p3cs_fail(P3CS_ERR_INVALID, "blend_offsets[0] != 0"));
+    for (int b = 0; b < d->num_blends; ++b)
+      if (d->blend_offsets[b + 1] < d->blend_offsets[b]) return bail(p3cs_fail(P3CS_ERR_INVALID, "blend_offsets not monotonic at %d", b));
+    for (int e = 0; e < nnz; ++e)
+      if (d->blend_transform[e] < 0 || d->blend_transform[e] >= d->num_transforms)
+        return bail(p3cs_fail(P3CS_ERR_INVALID, "blend entry %d refers to transform %d outside the palette (%d)", e, d->blend_transform[e], d->num_transforms));
+
+    const uint8_t *base = static_cast<const uint8_t *>(d->arrays[bc.array].data) + bc.start;
+    const int istride = d->arrays[bc.array].stride;
+    const bool wide = bc.numeric_type == P3CS_NT_UINT32;
+    std::vector<uint16_t> idx16;
+    std::vector<uint32_t> idx32;
+    if (wide) idx32.resize(std::max(N, 1)); else idx16.resize(std::max(N, 1));
+    for (int r = 0; r < N; ++r) {
+      const uint8_t *p = base + (size_t)r * istride;
+      uint32_t v;
+      if (bc.numeric_type == P3CS_NT_UINT8) v = *p;
+      else if (bc.numeric_type == P3CS_NT_UINT16) { uint16_t t; memcpy(&t, p, 2); v = t; }
+      else memcpy(&v, p, 4);
+      if (wide) idx32[r] = v; else idx16[r] = (uint16_t)v;
+    }
+    // every row the reference would transform must select an existing blend
+    bool full = d->num_row_ranges == 1 && d->row_ranges[0] == 0 && d->row_ranges[1] == N;
+    std::vector<uint32_t> mask;
+    if (!full) mask.assign(((size_t)N + 31) / 32 + 1, 0u);
+    for (int i = 0; i < d->num_row_ranges; ++i)
+      for (int r = d->row_ranges[2 * i]; r < d->row_ranges[2 * i + 1]; ++r) {
+        uint32_t v = wide ? idx32[r] : idx16[r];
+        if (v >= (uint32_t)d->num_blends)
+          return bail(p3cs_fail(P3CS_ERR_INVALID, "row %d selects blend %u but the table has %d blends", r, v, d->num_blends));
+        if (!full) mask[r >> 5] |= 1u << (r & 31);
+      }
+    // ---- vertex-animation-align-16 layout (gobj/config_gobj.cxx:286-300, geomVertexArrayFormat.cxx:349-373): the
+    // strip kernel's kAligned modes
+    {
+      const DynColumn *c = m.dyn;
+      bool ok = m.full_records && m.num_outputs == 1 && m.stride[0] % 16 == 0 &&
+                ((m.num_dyn == 2 && c[0].skin == 1 && c[1].skin == 3) ||
+                 (m.num_dyn == 4 && c[0].skin == 1 && c[1].skin == 3 && c[2].skin == 2 && c[3].skin == 2));
+      for (int i = 0; ok && i < m.num_dyn; ++i) ok = c[i].num_values == 4 && !c[i].f64 && c[i].start % 16 == 0;
+      for (int mi = 0; ok && mi < d->num_morphs; ++mi) {  // morphs only on those columns (no morph-only column)
+        const p3cs_column_desc &b = d->morphs[mi].base;
+        ok = b.array >= 0 && b.array < d->num_arrays && out_of_array[b.array] == 0 && b.num_values == 4 &&
+             b.numeric_type == P3CS_NT_FLOAT32 && find_dyn(0, b.start) >= 0;
+      }
+      m.aligned = ok ? 1 : 0;
+    }
+    m.strip_rec_floats = m.aligned ? kRecAligned : m.full_records ? kRecFull : kRecCompact;
+    // ---- shared-memory plan of the strip kernel.  Four CTAs per SM (the register-file limit) need <= ~55 KB each:
+    // palette + records + staged tiles.  Preference: two rows per thread (512-row tiles halve the per-tile
+    // bookkeeping), else 256-row tiles with three, then two buffers, then a smaller record group.
+    {
+      size_t slice = 0;
+      for (int o = 0; o < m.num_outputs; ++o) slice += round_up((size_t)32 * m.stride[o], 128);
+      const size_t rec_bytes = (size_t)m.strip_rec_floats * 4;
+      const size_t fixed = 32 + (size_t)d->num_transforms * 64 + 128;
+      const size_t budget = 55 * 1024;
+      const int full_cap = std::min(kStripThreads, (int)((32 * 1024) / rec_bytes));  // one phase-A pass: a thread per record
+      auto fits = [&](int r, int bufs, int cap) { return fixed + (size_t)cap * rec_bytes + (size_t)bufs * 8 * r * slice <= budget; };
+      m.rows_per_thread = 1;
+      m.tile_bufs = 3;
+      m.group_record_cap = full_cap;
+      if (!m.full_records || m.aligned) {
+        if (fits(2, 2, full_cap)) {
+          m.rows_per_thread = 2;
+          m.tile_bufs = 2;
+        } else if (fits(1, 3, full_cap)) {
+        } else if (fits(1, 2, full_cap)) {
+          m.tile_bufs = 2;
+        } else {
+          int cap = full_cap;
+          while (cap > 128 && !fits(1, 2, cap)) cap -= 8;
+          if (fits(1, 2, cap)) {
+            m.tile_bufs = 2;
+            m.group_record_cap = cap;
+          }
+        }
+      }
+    }
+    const int kTileRows = kStripThreads * m.rows_per_thread;
+    // ---- strip-kernel tables: per record group the distinct blends, per row its slot in that list.
+    // Groups are grown greedily, tile by tile, while their distinct blends fit one phase-A pass
+    // (one thread per record) and the shared-memory record budget.
+    {
+      const int nt = (N + kTileRows - 1) / kTileRows;
+      const int cap = m.group_record_cap;
+      std::vector<uint16_t> local(std::max(N, 1), 0xFFFFu);
+      std::vector<int> rec_off(1, 0), rec_blend, ent_off(1, 0), tile_off(1, 0);
+      std::vector<uint2> ent;
+      std::vector<int> in_group(std::max(d->num_blends, 1), -1), seen_in_tile(std::max(d->num_blends, 1), -1),
+          slot(std::max(d->num_blends, 1), 0);
+      int ng = 0, max_rec = 0;
+      std::vector<int> open;   // distinct blends of the open group, first-seen order
+      std::vector<int> fresh;  // blends first seen in the tile being added
+      auto row_live = [&](int r) { return full || ((mask[r >> 5] >> (r & 31)) & 1u); };
+      auto row_blend = [&](int r) { return (int)(wide ? idx32[r] : idx16[r]); };
+
+      // Order of the records inside a group.  Phase A runs one thread per record and gathers the record's
+      // first four palette matrices with 128-bit shared-memory loads, eight lanes per wavefront; two lanes
+      // collide when their joints differ but agree modulo 8 (48-byte palette rows).  The order of a group's
+      // records is free (rows address them through their slot), so they are packed first-fit into
+      // eight-lane cells whose k-th joints are pairwise distinct modulo 8 (or equal: a broadcast).
+      auto pack_group = [&](std::vector<int> &blends) {
+        const int n = (int)blends.size();
+        const int cells = (n + 7) / 8;
+        std::vector<int> occ((size_t)cells * 32, -1), fill(cells, 0), cell_of(n, -1);
+        std::vector<int> leftover;
+        int first_open = 0;
+        for (int i = 0; i < n; ++i) {
+          const int b = blends[i];
+          const int e0 = d->blend_offsets[b], cnt = std::min(4, d->blend_offsets[b + 1] - e0);
+          int placed = -1;
+          for (int c = first_open; c < cells && placed < 0; ++c) {
+            if (fill[c] >= 8) continue;
+            bool ok = true;
+            for (int k = 0; k < cnt && ok; ++k) {
+              const int j = d->blend_transform[e0 + k];
+              const int o = occ[(size_t)c * 32 + k * 8 + (j & 7)];
+              ok = o < 0 || o == j;
+            }
+            if (ok) placed = c;
+          }
+          if (placed < 0) {
+            leftover.push_back(i);
+            continue;
+          }
+          for (int k = 0; k < cnt; ++k) {
+            const int j = d->blend_transform[e0 + k];
+            occ[(size_t)placed * 32 + k * 8 + (j & 7)] = j;
+          }
+          cell_of[i] = placed;
+          ++fill[placed];
+          while (first_open < cells && fill[first_open] >= 8) ++first_open;
+        }
+        int c = 0;
+        for (int i : leftover) {  // whatever did not fit conflict-free fills the remaining lanes
+          while (fill[c] >= 8) ++c;
+          cell_of[i] = c;
+          ++fill[c];
+        }
+        // dense positions: cells in order; only the last cell may be short, so move its surplus forward
+        std::vector<int> count_in(cells, 0);
+        for (int i = 0; i < n; ++i) ++count_in[cell_of[i]];
+        for (int cc = 0, donor = cells - 1; cc < donor; ++cc)
+          while (count_in[cc] < 8 && cc < donor) {
+            if (count_in[donor] == 0) { --donor; continue; }
+            for (int i = n - 1; i >= 0; --i)
+              if (cell_of[i] == donor) { cell_of[i] = cc; break; }
+            --count_in[donor];
+            ++count_in[cc];
+          }
+        // Lane inside the cell.  Phase B reads a row's record with 64-bit loads, sixteen rows per wavefront; the
+        // records of neighbouring runs (adjacent in first-seen order) collide there when their slots agree
+        // modulo 16, so each record takes a free lane whose slot differs from its three predecessors' modulo 16.
+        std::vector<int> slot_of(n, -1);
+        std::vector<uint8_t> used((size_t)cells, 0);
+        for (int i = 0; i < n; ++i) {
+          const int c = cell_of[i];
+          int best = -1;
+          for (int pass = 0; pass < 2 && best < 0; ++pass)
+            for (int p = 0; p < count_in[c]; ++p) {
+              if ((used[c] >> p) & 1) continue;
+              const int sl = 8 * c + p;
+              bool clash = false;  // against the records of the three preceding runs (a half-warp of rows spans about that many)
+              for (int back = 1; back <= 3 && back <= i; ++back) clash = clash || ((slot_of[i - back] ^ sl) & 15) == 0;
+              if (pass == 1 || !clash) { best = p; break; }
+            }
+          used[c] |= (uint8_t)(1u << best);
+          slot_of[i] = 8 * c + best;
+        }
+        std::vector<int> ordered(n);
+        for (int i = 0; i < n; ++i) ordered[slot_of[i]] = blends[i];
+        blends.swap(ordered);
+      };
+
+      auto close_group = [&](int t_end) {
+        pack_group(open);
+        const int n = (int)open.size();
+        for (int p = 0; p < n; ++p) {
+          const int b = open[p];
+          slot[b] = p;
+          rec_blend.push_back(b);
+          for (int e = d->blend_offsets[b]; e < d->blend_offsets[b + 1]; ++e) {
+            uint32_t wbits;
+            memcpy(&wbits, &d->blend_weight[e], 4);
+            ent.push_back(make_uint2((uint32_t)d->blend_transform[e], wbits));
+          }
+          ent_off.push_back((int)ent.size());
+        }
+        const int r0 = tile_off.back() * kTileRows, r1 = std::min(N, t_end * kTileRows);
+        for (int r = r0; r < r1; ++r)
+          if (row_live(r)) local[r] = (uint16_t)slot[row_blend(r)];
+        rec_off.push_back(rec_off.back() + n);
+        max_rec = std::max(max_rec, n);
+        tile_off.push_back(t_end);
+        ++ng;
+        open.clear();
+      };
+
+      for (int t = 0; t < nt; ++t) {
+        const int r0 = t * kTileRows, r1 = std::min(N, r0 + kTileRows);
+        fresh.clear();  // distinct blends this tile would add to the open group
+        for (int r = r0; r < r1; ++r) {
+          if (!row_live(r)) continue;
+          const int b = row_blend(r);
+          if (in_group[b] != ng && seen_in_tile[b] != t) {
+            seen_in_tile[b] = t;
+            fresh.push_back(b);
+          }
+        }
+        if (tile_off.back() != t && (int)open.size() + (int)fresh.size() > cap) {  // close the group before this tile
+          close_group(t);
+          for (int b : fresh) seen_in_tile[b] = -1;
+          --t;  // redo this tile in the new group
+          continue;
+        }
+        for (int b : fresh) {
+          in_group[b] = ng;
+          open.push_back(b);
+        }
+      }
+      if (nt > 0) close_group(nt);
+      if ((rc = upload<int>(mesh, tile_off.data(), tile_off.size(), &m.group_tile_offsets)) != P3CS_OK) return bail(rc);
+      m.num_groups = ng;
+      m.max_group_records = max_rec;
+      if ((rc = upload<uint16_t>(mesh, local.data(), local.size(), &m.row_local)) != P3CS_OK) return bail(rc);
+      if ((rc = upload<int>(mesh, rec_off.data(), rec_off.size(), &m.group_rec_offsets)) != P3CS_OK) return bail(rc);
+      if ((rc = upload<int>(mesh, rec_blend.data(), rec_blend.size(), &m.group_rec_blend)) != P3CS_OK) return bail(rc);
+      if ((rc = upload<int>(mesh, ent_off.data(), ent_off.size(), &m.grec_entry_offsets)) != P3CS_OK) return bail(rc);
+      if ((rc = upload<uint2>(mesh, ent.data(), ent.size(), &m.grec_entries)) != P3CS_OK) return bail(rc);
+      // fixed-width blocks: the first four entries of every group record, count in bits 16..31
+      const size_t nrec_total = rec_blend.size();
+      // padded by one CTA's worth of records: the kernel prefetches block (group start + tid)
+      std::vector<uint4> blocks((nrec_total + kStripThreads) * 2, make_uint4(0, 0, 0, 0));
+      for (size_t r = 0; r < nrec_total; ++r) {
+        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int beg = ent_off[r], cnt = ent_off[r + 1] - ent_off[r];
+        for (int k = 0; k < std::min(cnt, 4); ++k) {
+          w[2 * k] = ent[beg + k].x;
+          w[2 * k + 1] = ent[beg + k].y;
+        }
+        w[0] |= (uint32_t)std::min(cnt, 0xFFFF) << 16;
+        blocks[2 * r] = make_uint4(w[0], w[1], w[2], w[3]);
+        blocks[2 * r + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      if ((rc = upload<uint4>(mesh, blocks.data(), blocks.size(), &m.grec_blocks)) != P3CS_OK) return bail(rc);
+    }
+    m.index_bytes = wide ? 4 : 2;
+    const void *dev_index = nullptr;
+    if (wide) { const uint32_t *p; rc = upload<uint32_t>(mesh, idx32.data(), idx32.size(), &p); dev_index = p; }
+    else { const uint16_t *p; rc = upload<uint16_t>(mesh, idx16.data(), idx16.size(), &p); dev_index = p; }
+    if (rc != P3CS_OK) return bail(rc);
+    m.index = dev_index;
+    if (!full && (rc = upload<uint32_t>(mesh, mask.data(), mask.size(), &m.rows_mask)) != P3CS_OK) return bail(rc);
+    if ((rc = upload<int>(mesh, d->blend_offsets, (size_t)d->num_blends + 1, &m.blend_offsets)) != P3CS_OK) return bail(rc);
+    if ((rc = upload<int>(mesh, d->blend_transform, (size_t)nnz, &m.blend_transform)) != P3CS_OK) return bail(rc);
+    if ((rc = upload<float>(mesh, d->blend_weight, (size_t)nnz, &m.blend_weight)) != P3CS_OK) return bail(rc);
+    (void)has_blend;
+  } else {
+    m.num_blends = 0;
+  }
+
+  // ---- morphs: dense delta columns + slider rows -> per-row CSR, in the reference's
+  // iteration order so rows hit by several morphs add up in the same order
+  if (d->num_morphs > 0) {
+    if (d->morphs == nullptr || d->num_sliders <= 0) return bail(p3cs_fail(P3CS_ERR_INVALID, "morphs without sliders"));
+    if (d->num_sliders > 65536) return bail(p3cs_fail(P3CS_ERR_UNSUPPORTED, "more than 65536 sliders"));
+    std::vector<int> counts((size_t)N + 1, 0);
+    std::vector<int> morph_dyn(d->num_morphs, -1);
+    for (int mi = 0; mi < d->num_morphs; ++mi) {
+      const p3cs_morph_desc &mo = d->morphs[mi];
+      if (mo.slider < 0 || mo.slider >= d->num_sliders) return bail(p3cs_fail(P3CS_ERR_INVALID, "morph %d: slider %d out of range", mi, mo.slider));
+      if ((rc = check_column(d, mo.base, "morph base column")) != P3CS_OK) return bail(rc);
+      if ((rc = check_column(d, mo.delta, "morph delta column")) != P3CS_OK) return bail(rc);
+      if ((rc = check_ranges(mo.row_ranges, mo.num_row_ranges, N, "slider rows")) != P3CS_OK) return bail(rc);
+      if (out_of_array[mo.base.array] < 0) return bail(p3cs_fail(P3CS_ERR_INVALID, "morph %d: base column in a non-output array", mi));
+      auto is_float = [](int nt) { return nt == P3CS_NT_FLOAT32 || nt == P3CS_NT_FLOAT64; };
+      if (!is_float(mo.base.numeric_type) || !is_float(mo.delta.numeric_type) || mo.base.num_values > 4 ||
+          mo.base.start % 4 != 0 || mo.delta.start % 4 != 0)
+        return bail(p3cs_fail(P3CS_ERR_UNSUPPORTED, "morph %d: only 4-byte aligned float32 / float64 base and delta columns are supported", mi));
+      int c = find_dyn(out_of_array[mo.base.array], mo.base.start);
+      if (c < 0) {
+        if (m.num_dyn >= kMaxDynColumns) return bail(p3cs_fail(P3CS_ERR_UNSUPPORTED, "more than %d animated columns", kMaxDynColumns));
+        c = m.num_dyn++;
+        m.dyn[c].output = (int16_t)out_of_array[mo.base.array];
+        m.dyn[c].start = (int16_t)mo.base.start;
+        m.dyn[c].num_values = (int8_t)mo.base.num_values;
+        m.dyn[c].skin = 0;
+        m.dyn[c].f64 = mo.base.numeric_type == P3CS_NT_FLOAT64 ? 1 : 0;
+      }
+      m.dyn[c].homogeneous = (mo.base.num_values == 4 && (mo.base.contents == P3CS_C_POINT || mo.base.contents == P3CS_C_TEXCOORD)) ? 1 : 0;
+      morph_dyn[mi] = c;
+      for (int i = 0; i < mo.num_row_ranges; ++i)
+        for (int r = mo.row_ranges[2 * i]; r < mo.row_ranges[2 * i + 1]; ++r) counts[r + 1]++;
+    }
+    for (int r = 0; r < N; ++r) counts[r + 1] += counts[r];
+    const size_t total = counts[N];
+    std::vector<uint32_t> keys(std::max<size_t>(total, 1));
+    std::vector<float4> deltas(std::max<size_t>(total, 1));
+    std::vector<int> cursor(counts.begin(), counts.end() - 1);
+    for (int mi = 0; mi < d->num_morphs; ++mi) {
+      const p3cs_morph_desc &mo = d->morphs[mi];
+      const uint8_t *dbase = static_cast<const uint8_t *>(d->arrays[mo.delta.array].data) + mo.delta.start;
+      const int dstride = d->arrays[mo.delta.array].stride;
+      const int dn = std::min(mo.delta.num_values, mo.base.num_values == 4 && !m.dyn[morph_dyn[mi]].homogeneous ? 4 : 3);
+      for (int i = 0; i < mo.num_row_ranges; ++i)
+        for (int r = mo.row_ranges[2 * i]; r < mo.row_ranges[2 * i + 1]; ++r) {
+          float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // Packer::get_data3f/4f pad with 0 (geomVertexColumn.cxx:718-737)
+          if (mo.delta.numeric_type == P3CS_NT_FLOAT64) {  // read as float, like GeomVertexReader::get_data3/4
+            double dv[4];
+            memcpy(dv, dbase + (size_t)r * dstride, (size_t)dn * 8);
+            for (int k = 0; k < dn; ++k) v[k] = (float)dv[k];
+          } else {
+            memcpy(v, dbase + (size_t)r * dstride, (size_t)dn * 4);
+          }
+          const int e = cursor[r]++;
+          keys[e] = ((uint32_t)morph_dyn[mi] << 16) | (uint32_t)mo.slider;
+          // a delta whose 4th component is never read carries its key there (one load per entry
+          // in the specialised strip modes)
+          if (!(mo.base.num_values == 4 && !m.dyn[morph_dyn[mi]].homogeneous)) memcpy(&v[3], &keys[e], 4);
+          deltas[e] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+    m.has_morphs = 1;
+    if ((rc = upload<int>(mesh, counts.data(), counts.size(), &m.morph_row_offsets)) != P3CS_OK) return bail(rc);
+    if ((rc = upload<uint32_t>(mesh, keys.data(), keys.size(), &m.morph_keys)) != P3CS_OK) return bail(rc);
+    if ((rc = upload<float4>(mesh, deltas.data(), deltas.size(), &m.morph_deltas)) != P3CS_OK) return bail(rc);
+  }
+  // ---- slice geometry of the strip kernel (a slice = the 32 rows one warp stages at a time)
+  if (m.rows_per_thread == 0) m.rows_per_thread = 1;
+  if (m.tile_bufs == 0) m.tile_bufs = 3;
+  if (m.strip_rec_floats == 0) m.strip_rec_floats = m.full_records ? kRecFull : kRecCompact;
+  m.num_tiles = (N + kStripThreads * m.rows_per_thread - 1) / (kStripThreads * m.rows_per_thread);
+  m.slice_bytes = 0;
+  for (int o = 0; o < m.num_outputs; ++o) {
+    m.slice_out_offset[o] = m.slice_bytes;
+    m.slice_bytes += (int)round_up((size_t)32 * m.stride[o], 128);
+  }
+  if (m.group_rec_offsets == nullptr) {  // no blend table: one tile per group, zero records each
+    m.num_groups = m.num_tiles;
+    std::vector<int> zeros((size_t)m.num_groups + 1, 0), iota((size_t)m.num_groups + 1);
+    for (size_t i = 0; i < iota.size(); ++i) iota[i] = (int)i;
+    if ((rc = upload<int>(mesh, zeros.data(), zeros.size(), &m.group_rec_offsets)) != P3CS_OK) return bail(rc);
+    if ((rc = upload<int>(mesh, iota.data(), iota.size(), &m.group_tile_offsets)) != P3CS_OK) return bail(rc);
+    std::vector<uint4> blocks((size_t)kStripThreads * 2, make_uint4(0, 0, 0, 0));  // the kernel prefetches block [tid]
+    if ((rc = upload<uint4>(mesh, blocks.data(), blocks.size(), &m.grec_blocks)) != P3CS_OK) return bail(rc);
+  }
+  {
+    const char *path = getenv("P3CS_PATH");
+    mesh->use_strip = strip_smem_bytes(m) <= 200 * 1024 && m.num_transforms < 65536 &&
+                      !(path != nullptr && strcmp(path, "wide") == 0);
+  }
+  // uploads read from host vectors that die at scope exit: finish them now
+  cudaError_t err = cudaStreamSynchronize(ctx->stream);
+  if (err != cudaSuccess) return bail(p3cs_fail(P3CS_ERR_CUDA, "mesh upload failed: %s", cudaGetErrorString(err)));
+  mesh->out_of_array = out_of_array;
+  *out = mesh;
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_mesh_destroy(p3cs_mesh mesh) {
+  if (mesh == nullptr) return P3CS_OK;
+  DeviceGuard g(mesh->ctx->device);
+  for (void *p : mesh->allocations) cudaFree(p);
+  delete mesh;
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_mesh_num_outputs(p3cs_mesh mesh) { return mesh ? mesh->dev.num_outputs : 0; }
+extern "C" int p3cs_mesh_output_stride(p3cs_mesh mesh, int o) {
+  return (mesh && o >= 0 && o < mesh->dev.num_outputs) ? mesh->dev.stride[o] : 0;
+}
+extern "C" int p3cs_mesh_num_rows(p3cs_mesh mesh) { return mesh ? mesh->dev.num_rows : 0; }
