@@ -33,6 +33,167 @@ static int check_ranges(const int32_t *ranges, int count, int num_rows, const ch
   return P3CS_OK;
 }
 
+// ------------------------------------------------------------------ record groups of the strip kernel
+// Order of the records inside a group.  Phase A runs one thread per record and gathers the record's
+// first four palette matrices with 128-bit shared-memory loads, eight lanes per wavefront; two lanes
+// collide when their joints differ but agree modulo 8 (48-byte palette rows).  The order of a group's
+// records is free (rows address them through their slot), so they are packed first-fit into
+// eight-lane cells whose k-th joints are pairwise distinct modulo 8 (or equal: a broadcast).
+static void pack_group(const p3cs_mesh_desc *d, std::vector<int> &blends) {
+  const int n = (int)blends.size();
+  const int cells = (n + 7) / 8;
+  std::vector<int> occ((size_t)cells * 32, -1), fill(cells, 0), cell_of(n, -1);
+  std::vector<int> leftover;
+  int first_open = 0;
+  for (int i = 0; i < n; ++i) {
+    const int b = blends[i];
+    const int e0 = d->blend_offsets[b], cnt = std::min(4, d->blend_offsets[b + 1] - e0);
+    int placed = -1;
+    for (int c = first_open; c < cells && placed < 0; ++c) {
+      if (fill[c] >= 8) continue;
+      bool ok = true;
+      for (int k = 0; k < cnt && ok; ++k) {
+        const int j = d->blend_transform[e0 + k];
+        const int o = occ[(size_t)c * 32 + k * 8 + (j & 7)];
+        ok = o < 0 || o == j;
+      }
+      if (ok) placed = c;
+    }
+    if (placed < 0) {
+      leftover.push_back(i);
+      continue;
+    }
+    for (int k = 0; k < cnt; ++k) {
+      const int j = d->blend_transform[e0 + k];
+      occ[(size_t)placed * 32 + k * 8 + (j & 7)] = j;
+    }
+    cell_of[i] = placed;
+    ++fill[placed];
+    while (first_open < cells && fill[first_open] >= 8) ++first_open;
+  }
+  int c = 0;
+  for (int i : leftover) {  // whatever did not fit conflict-free fills the remaining lanes
+    while (fill[c] >= 8) ++c;
+    cell_of[i] = c;
+    ++fill[c];
+  }
+  // dense positions: cells in order; only the last cell may be short, so move its surplus forward
+  std::vector<int> count_in(cells, 0);
+  for (int i = 0; i < n; ++i) ++count_in[cell_of[i]];
+  for (int cc = 0, donor = cells - 1; cc < donor; ++cc)
+    while (count_in[cc] < 8 && cc < donor) {
+      if (count_in[donor] == 0) { --donor; continue; }
+      for (int i = n - 1; i >= 0; --i)
+        if (cell_of[i] == donor) { cell_of[i] = cc; break; }
+      --count_in[donor];
+      ++count_in[cc];
+    }
+  // Lane inside the cell.  Phase B reads a row's record with 64-bit loads, sixteen rows per wavefront; the
+  // records of neighbouring runs (adjacent in first-seen order) collide there when their slots agree
+  // modulo 16, so each record takes a free lane whose slot differs from its three predecessors' modulo 16.
+  std::vector<int> slot_of(n, -1);
+  std::vector<uint8_t> used((size_t)cells, 0);
+  for (int i = 0; i < n; ++i) {
+    const int c = cell_of[i];
+    int best = -1;
+    for (int pass = 0; pass < 2 && best < 0; ++pass)
+      for (int p = 0; p < count_in[c]; ++p) {
+        if ((used[c] >> p) & 1) continue;
+        const int sl = 8 * c + p;
+        bool clash = false;  // against the records of the three preceding runs (a half-warp of rows spans about that many)
+        for (int back = 1; back <= 3 && back <= i; ++back) clash = clash || ((slot_of[i - back] ^ sl) & 15) == 0;
+        if (pass == 1 || !clash) { best = p; break; }
+      }
+    used[c] |= (uint8_t)(1u << best);
+    slot_of[i] = 8 * c + best;
+  }
+  std::vector<int> ordered(n);
+  for (int i = 0; i < n; ++i) ordered[slot_of[i]] = blends[i];
+  blends.swap(ordered);
+}
+
+// ---- strip-kernel tables: per record group the distinct blends, per row its slot in that list.
+// Groups are grown greedily, tile by tile, while their distinct blends fit one phase-A pass
+// (one thread per record) and the shared-memory record budget.
+struct StripTables {
+  std::vector<uint16_t> local;                             // per row: slot in its group's record list (0xFFFF: not skinned)
+  std::vector<int> rec_off, rec_blend, ent_off, tile_off;  // group -> records, record -> blend / entries, group -> tiles
+  std::vector<uint2> ent;                                  // (palette index, weight bits) of every record, stored order
+  int num_groups = 0, max_records = 0;
+};
+
+// `row_index`: the transform_blend value of every row; `mask`: bit per row inside TransformBlendTable::get_rows()
+// (empty = all rows); `cap`: most records a group may hold.
+static StripTables build_record_groups(const p3cs_mesh_desc *d, const std::vector<uint32_t> &row_index, const std::vector<uint32_t> &mask,
+                                       int kTileRows, int cap) {
+  const int N = d->num_rows;
+  const int nt = (N + kTileRows - 1) / kTileRows;
+  StripTables tb;
+  std::vector<uint16_t> &local = tb.local;
+  std::vector<int> &rec_off = tb.rec_off, &rec_blend = tb.rec_blend, &ent_off = tb.ent_off, &tile_off = tb.tile_off;
+  std::vector<uint2> &ent = tb.ent;
+  local.assign(std::max(N, 1), 0xFFFFu);
+  rec_off.assign(1, 0);
+  ent_off.assign(1, 0);
+  tile_off.assign(1, 0);
+  std::vector<int> in_group(std::max(d->num_blends, 1), -1), seen_in_tile(std::max(d->num_blends, 1), -1),
+      slot(std::max(d->num_blends, 1), 0);
+  int &ng = tb.num_groups, &max_rec = tb.max_records;
+  std::vector<int> open;   // distinct blends of the open group, first-seen order
+  std::vector<int> fresh;  // blends first seen in the tile being added
+  auto row_live = [&](int r) { return mask.empty() || ((mask[r >> 5] >> (r & 31)) & 1u); };
+  auto row_blend = [&](int r) { return (int)row_index[r]; };
+
+  auto close_group = [&](int t_end) {
+    pack_group(d, open);
+    const int n = (int)open.size();
+    for (int p = 0; p < n; ++p) {
+      const int b = open[p];
+      slot[b] = p;
+      rec_blend.push_back(b);
+      for (int e = d->blend_offsets[b]; e < d->blend_offsets[b + 1]; ++e) {
+        uint32_t wbits;
+        memcpy(&wbits, &d->blend_weight[e], 4);
+        ent.push_back(make_uint2((uint32_t)d->blend_transform[e], wbits));
+      }
+      ent_off.push_back((int)ent.size());
+    }
+    const int r0 = tile_off.back() * kTileRows, r1 = std::min(N, t_end * kTileRows);
+    for (int r = r0; r < r1; ++r)
+      if (row_live(r)) local[r] = (uint16_t)slot[row_blend(r)];
+    rec_off.push_back(rec_off.back() + n);
+    max_rec = std::max(max_rec, n);
+    tile_off.push_back(t_end);
+    ++ng;
+    open.clear();
+  };
+
+  for (int t = 0; t < nt; ++t) {
+    const int r0 = t * kTileRows, r1 = std::min(N, r0 + kTileRows);
+    fresh.clear();  // distinct blends this tile would add to the open group
+    for (int r = r0; r < r1; ++r) {
+      if (!row_live(r)) continue;
+      const int b = row_blend(r);
+      if (in_group[b] != ng && seen_in_tile[b] != t) {
+        seen_in_tile[b] = t;
+        fresh.push_back(b);
+      }
+    }
+    if (tile_off.back() != t && (int)open.size() + (int)fresh.size() > cap) {  // close the group before this tile
+      close_group(t);
+      for (int b : fresh) seen_in_tile[b] = -1;
+      --t;  // redo this tile in the new group
+      continue;
+    }
+    for (int b : fresh) {
+      in_group[b] = ng;
+      open.push_back(b);
+    }
+  }
+  if (nt > 0) close_group(nt);
+  return tb;
+}
+
 extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_mesh *out) {
   if (out == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_mesh_create: out is NULL");
   *out = nullptr;
@@ -199,148 +360,15 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
       }
     }
     const int kTileRows = kStripThreads * m.rows_per_thread;
-    // ---- strip-kernel tables: per record group the distinct blends, per row its slot in that list.
-    // Groups are grown greedily, tile by tile, while their distinct blends fit one phase-A pass
-    // (one thread per record) and the shared-memory record budget.
+    // ---- strip-kernel tables (build_record_groups above)
     {
-      const int nt = (N + kTileRows - 1) / kTileRows;
-      const int cap = m.group_record_cap;
-      std::vector<uint16_t> local(std::max(N, 1), 0xFFFFu);
-      std::vector<int> rec_off(1, 0), rec_blend, ent_off(1, 0), tile_off(1, 0);
-      std::vector<uint2> ent;
-      std::vector<int> in_group(std::max(d->num_blends, 1), -1), seen_in_tile(std::max(d->num_blends, 1), -1),
-          slot(std::max(d->num_blends, 1), 0);
-      int ng = 0, max_rec = 0;
-      std::vector<int> open;   // distinct blends of the open group, first-seen order
-      std::vector<int> fresh;  // blends first seen in the tile being added
-      auto row_live = [&](int r) { return full || ((mask[r >> 5] >> (r & 31)) & 1u); };
-      auto row_blend = [&](int r) { return (int)(wide ? idx32[r] : idx16[r]); };
-
-      // Order of the records inside a group.  Phase A runs one thread per record and gathers the record's
-      // first four palette matrices with 128-bit shared-memory loads, eight lanes per wavefront; two lanes
-      // collide when their joints differ but agree modulo 8 (48-byte palette rows).  The order of a group's
-      // records is free (rows address them through their slot), so they are packed first-fit into
-      // eight-lane cells whose k-th joints are pairwise distinct modulo 8 (or equal: a broadcast).
-      auto pack_group = [&](std::vector<int> &blends) {
-        const int n = (int)blends.size();
-        const int cells = (n + 7) / 8;
-        std::vector<int> occ((size_t)cells * 32, -1), fill(cells, 0), cell_of(n, -1);
-        std::vector<int> leftover;
-        int first_open = 0;
-        for (int i = 0; i < n; ++i) {
-          const int b = blends[i];
-          const int e0 = d->blend_offsets[b], cnt = std::min(4, d->blend_offsets[b + 1] - e0);
-          int placed = -1;
-          for (int c = first_open; c < cells && placed < 0; ++c) {
-            if (fill[c] >= 8) continue;
-            bool ok = true;
-            for (int k = 0; k < cnt && ok; ++k) {
-              const int j = d->blend_transform[e0 + k];
-              const int o = occ[(size_t)c * 32 + k * 8 + (j & 7)];
-              ok = o < 0 || o == j;
-            }
-            if (ok) placed = c;
-          }
-          if (placed < 0) {
-            leftover.push_back(i);
-            continue;
-          }
-          for (int k = 0; k < cnt; ++k) {
-            const int j = d->blend_transform[e0 + k];
-            occ[(size_t)placed * 32 + k * 8 + (j & 7)] = j;
-          }
-          cell_of[i] = placed;
-          ++fill[placed];
-          while (first_open < cells && fill[first_open] >= 8) ++first_open;
-        }
-        int c = 0;
-        for (int i : leftover) {  // whatever did not fit conflict-free fills the remaining lanes
-          while (fill[c] >= 8) ++c;
-          cell_of[i] = c;
-          ++fill[c];
-        }
-        // dense positions: cells in order; only the last cell may be short, so move its surplus forward
-        std::vector<int> count_in(cells, 0);
-        for (int i = 0; i < n; ++i) ++count_in[cell_of[i]];
-        for (int cc = 0, donor = cells - 1; cc < donor; ++cc)
-          while (count_in[cc] < 8 && cc < donor) {
-            if (count_in[donor] == 0) { --donor; continue; }
-            for (int i = n - 1; i >= 0; --i)
-              if (cell_of[i] == donor) { cell_of[i] = cc; break; }
-            --count_in[donor];
-            ++count_in[cc];
-          }
-        // Lane inside the cell.  Phase B reads a row's record with 64-bit loads, sixteen rows per wavefront; the
-        // records of neighbouring runs (adjacent in first-seen order) collide there when their slots agree
-        // modulo 16, so each record takes a free lane whose slot differs from its three predecessors' modulo 16.
-        std::vector<int> slot_of(n, -1);
-        std::vector<uint8_t> used((size_t)cells, 0);
-        for (int i = 0; i < n; ++i) {
-          const int c = cell_of[i];
-          int best = -1;
-          for (int pass = 0; pass < 2 && best < 0; ++pass)
-            for (int p = 0; p < count_in[c]; ++p) {
-              if ((used[c] >> p) & 1) continue;
-              const int sl = 8 * c + p;
-              bool clash = false;  // against the records of the three preceding runs (a half-warp of rows spans about that many)
-              for (int back = 1; back <= 3 && back <= i; ++back) clash = clash || ((slot_of[i - back] ^ sl) & 15) == 0;
-              if (pass == 1 || !clash) { best = p; break; }
-            }
-          used[c] |= (uint8_t)(1u << best);
-          slot_of[i] = 8 * c + best;
-        }
-        std::vector<int> ordered(n);
-        for (int i = 0; i < n; ++i) ordered[slot_of[i]] = blends[i];
-        blends.swap(ordered);
-      };
-
-      auto close_group = [&](int t_end) {
-        pack_group(open);
-        const int n = (int)open.size();
-        for (int p = 0; p < n; ++p) {
-          const int b = open[p];
-          slot[b] = p;
-          rec_blend.push_back(b);
-          for (int e = d->blend_offsets[b]; e < d->blend_offsets[b + 1]; ++e) {
-            uint32_t wbits;
-            memcpy(&wbits, &d->blend_weight[e], 4);
-            ent.push_back(make_uint2((uint32_t)d->blend_transform[e], wbits));
-          }
-          ent_off.push_back((int)ent.size());
-        }
-        const int r0 = tile_off.back() * kTileRows, r1 = std::min(N, t_end * kTileRows);
-        for (int r = r0; r < r1; ++r)
-          if (row_live(r)) local[r] = (uint16_t)slot[row_blend(r)];
-        rec_off.push_back(rec_off.back() + n);
-        max_rec = std::max(max_rec, n);
-        tile_off.push_back(t_end);
-        ++ng;
-        open.clear();
-      };
-
-      for (int t = 0; t < nt; ++t) {
-        const int r0 = t * kTileRows, r1 = std::min(N, r0 + kTileRows);
-        fresh.clear();  // distinct blends this tile would add to the open group
-        for (int r = r0; r < r1; ++r) {
-          if (!row_live(r)) continue;
-          const int b = row_blend(r);
-          if (in_group[b] != ng && seen_in_tile[b] != t) {
-            seen_in_tile[b] = t;
-            fresh.push_back(b);
-          }
-        }
-        if (tile_off.back() != t && (int)open.size() + (int)fresh.size() > cap) {  // close the group before this tile
-          close_group(t);
-          for (int b : fresh) seen_in_tile[b] = -1;
-          --t;  // redo this tile in the new group
-          continue;
-        }
-        for (int b : fresh) {
-          in_group[b] = ng;
-          open.push_back(b);
-        }
-      }
-      if (nt > 0) close_group(nt);
+      std::vector<uint32_t> row_index(std::max(N, 1));
+      for (int r = 0; r < N; ++r) row_index[r] = wide ? idx32[r] : idx16[r];
+      const StripTables tb = build_record_groups(d, row_index, full ? std::vector<uint32_t>() : mask, kTileRows, m.group_record_cap);
+      const std::vector<uint16_t> &local = tb.local;
+      const std::vector<int> &rec_off = tb.rec_off, &rec_blend = tb.rec_blend, &ent_off = tb.ent_off, &tile_off = tb.tile_off;
+      const std::vector<uint2> &ent = tb.ent;
+      const int ng = tb.num_groups, max_rec = tb.max_records;
       if ((rc = upload<int>(mesh, tile_off.data(), tile_off.size(), &m.group_tile_offsets)) != P3CS_OK) return bail(rc);
       m.num_groups = ng;
       m.max_group_records = max_rec;
