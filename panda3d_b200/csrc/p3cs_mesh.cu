@@ -242,7 +242,6 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
       if (m.dyn[c].output == output && m.dyn[c].start == start) return c;
     return -1;
   };
-  const bool has_blend = d->blend_column.array >= 0 && d->num_skin_columns > 0;
   for (int i = 0; i < d->num_skin_columns; ++i) {
     const p3cs_column_desc &c = d->skin_columns[i];
     if ((rc = check_column(d, c, "skin column")) != P3CS_OK) return bail(rc);
@@ -404,7 +403,7 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
     if ((rc = upload<int>(mesh, d->blend_offsets, (size_t)d->num_blends + 1, &m.blend_offsets)) != P3CS_OK) return bail(rc);
     if ((rc = upload<int>(mesh, d->blend_transform, (size_t)nnz, &m.blend_transform)) != P3CS_OK) return bail(rc);
     if ((rc = upload<float>(mesh, d->blend_weight, (size_t)nnz, &m.blend_weight)) != P3CS_OK) return bail(rc);
-    (void)has_blend;
+    
   } else {
     m.num_blends = 0;
   }
