@@ -39,7 +39,7 @@ static int check_ranges(const int32_t *ranges, int count, int num_rows, const ch
 // collide when their joints differ but agree modulo 8 (48-byte palette rows).  The order of a group's
 // records is free (rows address them through their slot), so they are packed first-fit into
 // eight-lane cells whose k-th joints are pairwise distinct modulo 8 (or equal: a broadcast).
-static void pack_group(const p3cs_mesh_desc *d, std::vector<int> &blends) {
+static void pack_group(const p3cs_mesh_desc *d, std::vector<int> &blends, long long *budget) {
   const int n = (int)blends.size();
   const int cells = (n + 7) / 8;
   std::vector<int> occ((size_t)cells * 32, -1), fill(cells, 0), cell_of(n, -1);
@@ -88,6 +88,75 @@ static void pack_group(const p3cs_mesh_desc *d, std::vector<int> &blends) {
       --count_in[donor];
       ++count_in[cc];
     }
+  // Refinement: records of cells that still collide are swapped with records of other cells whenever that lowers
+  // the two cells' wavefront counts (a cell costs, per entry k, the largest number of distinct joints sharing
+  // one residue).  Bounded by `*budget` swap evaluations per mesh, so upload time stays in check.
+  if (budget != nullptr && *budget > 0) {
+    auto joint = [&](int rec, int k) {
+      const int b = blends[rec], e0 = d->blend_offsets[b];
+      return k < std::min(4, d->blend_offsets[b + 1] - e0) ? d->blend_transform[e0 + k] : -1;
+    };
+    std::vector<std::vector<int>> members(cells);
+    for (int i = 0; i < n; ++i) members[cell_of[i]].push_back(i);
+    // cost of a cell's member list with member `skip` left out and record `extra` added (-1: none)
+    auto cell_cost = [&](const std::vector<int> &mem, int skip, int extra) {
+      int total = 0;
+      for (int k = 0; k < 4; ++k) {
+        int distinct[8] = {0, 0, 0, 0, 0, 0, 0, 0}, seen[9], ns = 0, worst = 0;
+        auto add = [&](int rec) {
+          const int j = joint(rec, k);
+          if (j < 0) return;
+          for (int q = 0; q < ns; ++q)
+            if (seen[q] == j) return;
+          seen[ns++] = j;
+          worst = std::max(worst, ++distinct[j & 7]);
+        };
+        for (int rec : mem)
+          if (rec != skip) add(rec);
+        if (extra >= 0) add(extra);
+        total += worst;
+      }
+      return total;
+    };
+    std::vector<int> cost(cells);
+    for (int c = 0; c < cells; ++c) cost[c] = cell_cost(members[c], -1, -1);
+    for (int round = 0; round < 3 && *budget > 0; ++round) {
+      bool improved = false;
+      for (int ca = 0; ca < cells && *budget > 0; ++ca) {
+        int floor_a = 0;  // a conflict-free cell costs one wavefront per entry index in use
+        for (int k = 0; k < 4; ++k)
+          for (int rec : members[ca])
+            if (joint(rec, k) >= 0) { ++floor_a; break; }
+        if (cost[ca] <= floor_a) continue;
+        for (size_t ia = 0; ia < members[ca].size() && *budget > 0; ++ia) {
+          int best_gain = 0, best_c = -1;
+          size_t best_i = 0;
+          for (int cb = 0; cb < cells; ++cb) {
+            if (cb == ca) continue;
+            for (size_t ib = 0; ib < members[cb].size(); ++ib) {
+              const int ra = members[ca][ia], rb = members[cb][ib];
+              const int gain = cost[ca] + cost[cb] - cell_cost(members[ca], ra, rb) - cell_cost(members[cb], rb, ra);
+              --*budget;
+              if (gain > best_gain) {
+                best_gain = gain;
+                best_c = cb;
+                best_i = ib;
+              }
+            }
+          }
+          if (best_c >= 0) {
+            std::swap(members[ca][ia], members[best_c][best_i]);
+            cost[ca] = cell_cost(members[ca], -1, -1);
+            cost[best_c] = cell_cost(members[best_c], -1, -1);
+            improved = true;
+          }
+        }
+      }
+      if (!improved) break;
+    }
+    for (int c = 0; c < cells; ++c)
+      for (int rec : members[c]) cell_of[rec] = c;
+  }
   // Lane inside the cell.  Phase B reads a row's record with 64-bit loads, sixteen rows per wavefront; the
   // records of neighbouring runs (adjacent in first-seen order) collide there when their slots agree
   // modulo 16, so each record takes a free lane whose slot differs from its three predecessors' modulo 16.
@@ -141,11 +210,12 @@ static StripTables build_record_groups(const p3cs_mesh_desc *d, const std::vecto
   int &ng = tb.num_groups, &max_rec = tb.max_records;
   std::vector<int> open;   // distinct blends of the open group, first-seen order
   std::vector<int> fresh;  // blends first seen in the tile being added
+  long long pack_budget = 1500000;  // swap evaluations of pack_group's refinement, for the whole mesh (~0.4 s at most)
   auto row_live = [&](int r) { return mask.empty() || ((mask[r >> 5] >> (r & 31)) & 1u); };
   auto row_blend = [&](int r) { return (int)row_index[r]; };
 
   auto close_group = [&](int t_end) {
-    pack_group(d, open);
+    pack_group(d, open, &pack_budget);
     const int n = (int)open.size();
     for (int p = 0; p < n; ++p) {
       const int b = open[p];
