@@ -79,6 +79,7 @@ extern "C" int p3cs_context_destroy(p3cs_context ctx) {
   for (auto e : ctx->join_ev)
     if (e) cudaEventDestroy(e);
   for (auto e : ctx->pipe_ev) cudaEventDestroy(e);
+  for (auto &gg : ctx->graphs) cudaGraphExecDestroy(gg.exec);
   delete ctx;
   return P3CS_OK;
 }
@@ -150,6 +151,15 @@ extern "C" int p3cs_group_destroy(p3cs_group grp) {
   if (grp == nullptr) return P3CS_OK;
   DeviceGuard g(grp->mesh->ctx->device);
   cudaStreamSynchronize(grp->mesh->ctx->stream);
+  auto &graphs = grp->mesh->ctx->graphs;  // captured launches of this group die with it
+  for (size_t i = 0; i < graphs.size();) {
+    if (std::find(graphs[i].groups.begin(), graphs[i].groups.end(), grp) != graphs[i].groups.end()) {
+      cudaGraphExecDestroy(graphs[i].exec);
+      graphs.erase(graphs.begin() + (long)i);
+    } else {
+      ++i;
+    }
+  }
   for (void *p : grp->allocations) cudaFree(p);
   for (auto e : grp->ev)
     if (e) cudaEventDestroy(e);
@@ -376,19 +386,74 @@ extern "C" int p3cs_animate_groups(p3cs_group const *groups, int num_groups) {
   }
   // fork: group i runs on lane i % (1 + kSideStreams); lane 0 is the context's own stream
   const int lanes = std::min(num_groups, 1 + p3cs_context_s::kSideStreams);
-  CUDA_TRY(cudaEventRecord(ctx->fork_ev, ctx->stream));
-  for (int k = 1; k < lanes; ++k) CUDA_TRY(cudaStreamWaitEvent(ctx->side[k - 1], ctx->fork_ev, 0));
-  int rc = P3CS_OK;
-  for (int i = 0; i < num_groups && rc == P3CS_OK; ++i) {
-    const int lane = i % lanes;
-    rc = animate_range(groups[i], 0, groups[i]->n, true, lane == 0 ? ctx->stream : ctx->side[lane - 1]);
+  auto fork_join = [&](bool timed) {
+    int rc = P3CS_OK;
+    if (cudaEventRecord(ctx->fork_ev, ctx->stream) != cudaSuccess) rc = p3cs_fail(P3CS_ERR_CUDA, "cudaEventRecord failed");
+    for (int k = 1; k < lanes && rc == P3CS_OK; ++k)
+      if (cudaStreamWaitEvent(ctx->side[k - 1], ctx->fork_ev, 0) != cudaSuccess) rc = p3cs_fail(P3CS_ERR_CUDA, "cudaStreamWaitEvent failed");
+    for (int i = 0; i < num_groups && rc == P3CS_OK; ++i) {
+      const int lane = i % lanes;
+      rc = animate_range(groups[i], 0, groups[i]->n, timed, lane == 0 ? ctx->stream : ctx->side[lane - 1]);
+    }
+    // join (also on failure, so the side streams never run ahead of the context's stream)
+    for (int k = 1; k < lanes; ++k) {
+      cudaEventRecord(ctx->join_ev[k - 1], ctx->side[k - 1]);
+      cudaStreamWaitEvent(ctx->stream, ctx->join_ev[k - 1], 0);
+    }
+    return rc;
+  };
+
+  // The same set of groups comes back every frame: its fork / join is captured once as a CUDA graph and replayed
+  // with one launch call (the ~14 stream calls otherwise delay the later kernels).  Profiling mode, which wants
+  // per-launch events, keeps the direct path.
+  bool profiling = false;
+  for (int i = 0; i < num_groups; ++i) profiling = profiling || groups[i]->profiling;
+  static const bool use_graphs = getenv("P3CS_NO_GRAPHS") == nullptr;
+  if (profiling || !use_graphs) return fork_join(true);
+
+  p3cs_context_s::GroupsGraph *hit = nullptr;
+  for (auto &gg : ctx->graphs) {
+    if ((int)gg.groups.size() != num_groups) continue;
+    bool same = true;
+    for (int i = 0; i < num_groups && same; ++i) same = gg.groups[i] == groups[i] && gg.epochs[i] == groups[i]->epoch;
+    if (same) hit = &gg;
   }
-  // join (also on failure, so the side streams never run ahead of the context's stream)
-  for (int k = 1; k < lanes; ++k) {
-    cudaEventRecord(ctx->join_ev[k - 1], ctx->side[k - 1]);
-    cudaStreamWaitEvent(ctx->stream, ctx->join_ev[k - 1], 0);
+  if (hit == nullptr) {
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    const int rc = fork_join(false);
+    const cudaError_t end = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc != P3CS_OK || end != cudaSuccess || graph == nullptr) {
+      if (graph != nullptr) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return rc != P3CS_OK ? rc : fork_join(true);  // capture refused (e.g. a foreign stream state): run directly
+    }
+    p3cs_context_s::GroupsGraph gg;
+    const cudaError_t inst = cudaGraphInstantiate(&gg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (inst != cudaSuccess) {
+      cudaGetLastError();
+      return fork_join(true);
+    }
+    for (int i = 0; i < num_groups; ++i) {
+      gg.groups.push_back(groups[i]);
+      gg.epochs.push_back(groups[i]->epoch);
+      gg.launches.push_back(groups[i]->last.launches);
+    }
+    if (ctx->graphs.size() >= 8) {  // a handful of crowd compositions at most; drop the oldest
+      cudaGraphExecDestroy(ctx->graphs.front().exec);
+      ctx->graphs.erase(ctx->graphs.begin());
+    }
+    ctx->graphs.push_back(gg);
+    hit = &ctx->graphs.back();
   }
-  return rc;
+  CUDA_TRY(cudaGraphLaunch(hit->exec, ctx->stream));
+  for (int i = 0; i < num_groups; ++i) {
+    groups[i]->last.launches = hit->launches[i];
+    groups[i]->last.blend_ms = groups[i]->last.skin_ms = groups[i]->last.total_ms = -1.0f;
+    groups[i]->timed = false;
+  }
+  return P3CS_OK;
 }
 
 // Only the instances that changed: what the UpdateSeq test of GeomVertexData::animate_vertices
@@ -423,6 +488,7 @@ extern "C" int p3cs_group_animate_instances(p3cs_group grp, const int32_t *host_
 extern "C" int p3cs_group_set_profiling(p3cs_group grp, int enable) {
   if (grp == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_set_profiling: group is NULL");
   grp->profiling = enable != 0;
+  ++grp->epoch;
   return P3CS_OK;
 }
 
@@ -449,6 +515,7 @@ extern "C" int p3cs_group_last_timings(p3cs_group grp, p3cs_timings *out) {
 
 extern "C" int p3cs_group_enable_bounds(p3cs_group grp, const p3cs_column_desc *vertex_column) {
   if (grp == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_enable_bounds: group is NULL");
+  ++grp->epoch;
   if (vertex_column == nullptr) {  // off (the buffer stays allocated until the group is destroyed)
     grp->dev.bounds = nullptr;
     return P3CS_OK;

@@ -32,6 +32,14 @@ struct p3cs_context_s {
   cudaEvent_t fork_ev = nullptr;
   cudaEvent_t join_ev[kSideStreams] = {nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> pipe_ev;  // chunk hand-off events of p3cs_group_animate_host
+  // p3cs_animate_groups: the fork / join of a set of groups captured once as a CUDA graph and replayed
+  struct GroupsGraph {
+    std::vector<p3cs_group> groups;
+    std::vector<unsigned> epochs;  // p3cs_group_s::epoch of every group at capture time
+    std::vector<int> launches;
+    cudaGraphExec_t exec = nullptr;
+  };
+  std::vector<GroupsGraph> graphs;
 };
 
 struct p3cs_mesh_s {
@@ -59,6 +67,7 @@ struct p3cs_group_s {
   int frames_capacity = 0;
   p3cs_timings last{};
   bool timed = false;
+  unsigned epoch = 0;  // bumped whenever what a launch of this group does changes (bounds on / off, profiling)
 };
 
 namespace p3cs {
