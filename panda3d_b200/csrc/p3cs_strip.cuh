@@ -397,26 +397,8 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
     for (int k = 0; k < kTileBufs; ++k) mbar_init(mbar0 + 8 * k, 1);
     fence_proxy_async();  // make the initialised barriers visible to the async (TMA) proxy
   }
-  // palette: T x 64 B by coalesced 128-bit loads; rows x columns 0..2 packed to 48 B, column 3
-  // aside; on the way check whether every matrix is affine (column 3 == (0,0,0,1) exactly)
-  int non_affine = 0;
-  {
-    const float4 *gp = reinterpret_cast<const float4 *>(grp.palettes + (size_t)inst * mesh.num_transforms * 16);
-    const int n4 = mesh.num_transforms * 4;
-    for (int i = tid; i < n4; i += kStripThreads) {
-      const float4 row = __ldg(gp + i);
-      const int j = i >> 2, r = i & 3;
-      float *d = pal3f + j * 12 + r * 3;
-      d[0] = row.x;
-      d[1] = row.y;
-      d[2] = row.z;
-      palcf[i] = row.w;
-      non_affine |= (row.w != (r == 3 ? 1.0f : 0.0f));
-    }
-  }
-  non_affine = __syncthreads_or(non_affine);
-
-  // one elected thread drives the TMA traffic
+  // one elected thread drives the TMA traffic; the first tile and the table prefetches below are issued before the
+  // palette is staged, so their latencies overlap it
   auto issue_tile_load = [&](int t, int buf) {
     const int row0 = t * kTileRows;
     const int rows = min(kTileRows, mesh.num_rows - row0);
@@ -473,6 +455,27 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   bounds.reset();
   const int bounds_off = BOUNDS ? kSlicesPerTile * mesh.slice_out_offset[grp.bounds_output] + grp.bounds_start : 0;
   const int bounds_stride = BOUNDS ? mesh.stride[grp.bounds_output] : 0;
+
+
+  // palette: T x 64 B by coalesced 128-bit loads; rows x columns 0..2 packed to 48 B, column 3
+  // aside; on the way check whether every matrix is affine (column 3 == (0,0,0,1) exactly)
+  int non_affine = 0;
+  {
+    const float4 *gp = reinterpret_cast<const float4 *>(grp.palettes + (size_t)inst * mesh.num_transforms * 16);
+    const int n4 = mesh.num_transforms * 4;
+    for (int i = tid; i < n4; i += kStripThreads) {
+      const float4 row = __ldg(gp + i);
+      const int j = i >> 2, r = i & 3;
+      float *d = pal3f + j * 12 + r * 3;
+      d[0] = row.x;
+      d[1] = row.y;
+      d[2] = row.z;
+      palcf[i] = row.w;
+      non_affine |= (row.w != (r == 3 ? 1.0f : 0.0f));
+    }
+  }
+  non_affine = __syncthreads_or(non_affine);
+
 
   int t = t0;
   for (int g = g0; g < g1; ++g) {
