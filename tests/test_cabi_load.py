@@ -55,3 +55,15 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "skin_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_plain_c_host_loads_the_plugin_table(tmp_path):
+    """examples/plugin_host.c: a C99 program that dlopen()s the library and walks p3cs_get_api() -- the way
+    Panda3D's load_dso / get_dso_symbol convention would.  Compiled here with gcc."""
+    import subprocess
+    exe = tmp_path / "plugin_host"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-O1", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "plugin_host.c"), "-ldl", "-o", str(exe)], check=True)
+    res = subprocess.run([str(exe), _capi.LIB_PATH], capture_output=True, text=True, timeout=60)
+    assert res.returncode == 0, res.stderr
+    assert "p3cs api version 2" in res.stdout

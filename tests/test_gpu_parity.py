@@ -802,3 +802,17 @@ def test_joint_hierarchy_with_frame_blending(gpu_ctx, fixture):
         grp.close()
         dskel.close()
         dmesh.close()
+
+
+@pytest.mark.gpu
+def test_plain_c_host_animates_through_the_plugin_table(tmp_path):
+    """examples/plugin_host.c --run: a C99 host (dlopen + p3cs_get_api, no Python, no torch) skins the survey's
+    four-vertex probe: (2,4,1) under 0.25*T(1,2,3) + 0.75*S(2) -> (3.75, 7.5, 2.5)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "plugin_host"
+    subprocess.run(["gcc", "-std=c99", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "plugin_host.c"),
+                    "-ldl", "-o", str(exe)], check=True)
+    res = subprocess.run([str(exe), _capi.LIB_PATH, "--run"], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "vertex 0 -> (3.75, 7.5, 2.5)" in res.stdout
