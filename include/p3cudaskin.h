@@ -372,6 +372,31 @@ P3CS_EXPORT int p3cs_group_pose(p3cs_group group, p3cs_skeleton skeleton, int fi
 #define P3CS_BT_NORMALIZED_LINEAR 1
 P3CS_EXPORT int p3cs_group_pose_blend(p3cs_group group, p3cs_skeleton skeleton, int first, int count, const int32_t *host_frames,
                                       const int32_t *host_next_frames, const float *host_fracs, int blend_type);
+/* Several animations on one skeleton and several AnimControls per character (PartBundle::set_anim_blend_flag,
+ * set_control_effect): p3cs_skeleton_add_animation uploads the channel tables of one more bound AnimBundle
+ * (animation 0 is the one in p3cs_skeleton_desc) and returns its index; p3cs_group_pose_controls evaluates every
+ * instance from `num_controls` control states, listed in the order PartBundle iterates its blend map (ascending
+ * AnimControl address -- the order MovingPartMatrix::get_blend_value sums in).  Per joint: no control with a channel
+ * -> the default value; exactly one and no frame blending -> its value (movingPartBase.cxx:303-333); else the blend
+ * weighted by the effects (movingPartMatrix.cxx:78-198). */
+typedef struct p3cs_animation_desc {
+  uint32_t struct_size;
+  int32_t num_table_values;
+  const int32_t *has_channel;     /* [J] */
+  const int32_t *table_length;    /* [J][12] */
+  const int32_t *table_offset;    /* [J][12] */
+  const float *tables;
+} p3cs_animation_desc;
+typedef struct p3cs_control_state {
+  int32_t anim;                   /* animation index of this control */
+  int32_t frame, next_frame;      /* AnimControl::get_frame(), get_next_frame() */
+  float frac;                     /* (float)AnimControl::get_frac(); read only with frame blending */
+  float effect;                   /* PartBundle::get_control_effect(); 0 = the control is not in the blend */
+} p3cs_control_state;
+P3CS_EXPORT int p3cs_skeleton_add_animation(p3cs_skeleton skeleton, const p3cs_animation_desc *desc, int32_t *out_index);
+P3CS_EXPORT int p3cs_group_pose_controls(p3cs_group group, p3cs_skeleton skeleton, int first, int count, int num_controls,
+                                         const p3cs_control_state *host_states /* [count][num_controls] */,
+                                         int frame_blend, int blend_type);
 /* Device -> host read-back of `count` palettes (count * T * 16 floats); parity hook. */
 P3CS_EXPORT int p3cs_group_read_palettes(p3cs_group group, int first, int count, float *host_dst);
 

@@ -207,3 +207,28 @@ def pose(skel, frame: int, next_frame: Optional[int] = None, frac: float = 0.0, 
     if rc != 0:
         raise RuntimeError(f"oracle pose failed rc={rc}")
     return out
+
+
+def pose_controls(skels, frames, next_frames, fracs, effects, frame_blend: bool, blend_type: int = 1) -> np.ndarray:
+    """Several AnimControls blended (p3o_pose_controls): skels[k] carries control k's channel tables."""
+    keep, structs = [], []
+    for skel in skels:
+        arrs = [np.ascontiguousarray(a) for a in (skel.parent, skel.has_channel, skel.table_length, skel.table_offset,
+                                                  skel.tables if skel.tables.size else np.zeros(1, np.float32),
+                                                  skel.default_value, skel.initial_inverse, skel.root_xform)]
+        keep.append(arrs)
+        structs.append(_Skeleton(skel.num_joints, skel.coordinate_system, *[a.ctypes.data for a in arrs]))
+    K = len(skels)
+    ptrs = (C.POINTER(_Skeleton) * K)(*[C.pointer(s) for s in structs])
+    f = np.ascontiguousarray(frames, np.int32)
+    nf = np.ascontiguousarray(next_frames, np.int32)
+    fr = np.ascontiguousarray(fracs, np.float32)
+    ef = np.ascontiguousarray(effects, np.float32)
+    out = np.empty((skels[0].num_joints, 16), np.float32)
+    lib().p3o_pose_controls.restype = C.c_int
+    rc = lib().p3o_pose_controls(ptrs, C.c_int(K), f.ctypes.data_as(C.c_void_p), nf.ctypes.data_as(C.c_void_p),
+                                 fr.ctypes.data_as(C.c_void_p), ef.ctypes.data_as(C.c_void_p), C.c_int(1 if frame_blend else 0),
+                                 C.c_int(int(blend_type)), out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError(f"oracle pose_controls failed rc={rc}")
+    return out

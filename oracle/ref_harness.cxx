@@ -44,6 +44,8 @@
 #include "jointVertexTransform.h"
 #include "animChannelMatrixXfmTable.h"
 #include "partBundle.h"
+#include "animBundleNode.h"
+#include "animControl.h"
 #include "movingPartMatrix.h"
 
 #include <algorithm>
@@ -481,26 +483,42 @@ static void export_skeleton(Character *ch, const Exported &ex, Case &c) {
   c["skel_palette_joint"] = make_blob(DT_I32, palette_joint, {(uint64_t)palette_joint.size()});
 }
 
-static int cmd_egg(int argc, char **argv) {
-  const char *model_path = argv[2], *anim_path = argv[3], *out_path = argv[4];
+// The Actor of config C1: model + animation loaded through the reference's egg loader and bound with auto_bind.
+struct Actor {
+  PT(PandaNode) root;
+  AnimControlCollection ctrls;
+  Character *ch = nullptr;
+  CPT(GeomVertexData) vd;
+};
+
+static bool load_actor(const char *model_path, const char *anim_path, Actor &a) {
   PT(PandaNode) model = load_egg_file(model_path);
   PT(PandaNode) anim = load_egg_file(anim_path);
-  if (!model || !anim) { fprintf(stderr, "egg load failed\n"); return 1; }
-  PT(PandaNode) root = new PandaNode("root"); root->add_child(model); root->add_child(anim);
-  AnimControlCollection ctrls; auto_bind(root, ctrls, ~0);
-  if (ctrls.get_num_anims() < 1) { fprintf(stderr, "no animation bound\n"); return 1; }
-  NodePath np(root);
-  Character *ch = DCAST(Character, np.find("**/+Character").node());
+  if (!model || !anim) { fprintf(stderr, "egg load failed\n"); return false; }
+  a.root = new PandaNode("root"); a.root->add_child(model); a.root->add_child(anim);
+  auto_bind(a.root, a.ctrls, ~0);
+  if (a.ctrls.get_num_anims() < 1) { fprintf(stderr, "no animation bound\n"); return false; }
+  NodePath np(a.root);
+  a.ch = DCAST(Character, np.find("**/+Character").node());
   NodePathCollection gns = np.find_all_matches("**/+GeomNode");
-  CPT(GeomVertexData) vd;
-  for (int g = 0; g < gns.get_num_paths() && vd == nullptr; ++g) {
+  for (int g = 0; g < gns.get_num_paths() && a.vd == nullptr; ++g) {
     GeomNode *gn = DCAST(GeomNode, gns.get_path(g).node());
     for (int i = 0; i < gn->get_num_geoms(); ++i) {
       CPT(GeomVertexData) cand = gn->get_geom(i)->get_vertex_data();
-      if (cand->get_format()->get_animation().get_animation_type() == GeomEnums::AT_panda && cand->get_transform_blend_table() != nullptr) { vd = cand; break; }
+      if (cand->get_format()->get_animation().get_animation_type() == GeomEnums::AT_panda && cand->get_transform_blend_table() != nullptr) { a.vd = cand; break; }
     }
   }
-  if (vd == nullptr) { fprintf(stderr, "no AT_panda vertex data\n"); return 1; }
+  if (a.vd == nullptr) { fprintf(stderr, "no AT_panda vertex data\n"); return false; }
+  return true;
+}
+
+static int cmd_egg(int argc, char **argv) {
+  const char *out_path = argv[4];
+  Actor actor;
+  if (!load_actor(argv[2], argv[3], actor)) return 1;
+  AnimControlCollection &ctrls = actor.ctrls;
+  Character *ch = actor.ch;
+  CPT(GeomVertexData) vd = actor.vd;
   Case out;
   Exported ex = export_vertex_data(vd, out);
   export_skeleton(ch, ex, out);
@@ -536,6 +554,59 @@ static int cmd_egg(int argc, char **argv) {
   }
   fprintf(stderr, "egg: rows=%d transforms=%d blends=%d frames=%d\n", vd->get_num_rows(), (int)ex.palette.size(),
           (int)vd->get_transform_blend_table()->get_num_blends(), (int)frames.size());
+  return write_case(out_path, out) ? 0 : 1;
+}
+
+// Several AnimControls at once (PartBundle::set_anim_blend_flag + set_control_effect): the animation is bound a
+// second time, every sample poses the two controls at their own frames with their own effects
+// ("f0:e0,f1:e1" per sample; fractional frames switch the frame-blend flag on as in cmd_egg).  The per-control
+// state is exported in the order PartBundle iterates its _blend map (ascending AnimControl address), which is the
+// order MovingPartMatrix::get_blend_value sums in (chan/movingPartMatrix.cxx:82-198).
+static int cmd_eggmulti(int argc, char **argv) {
+  const char *out_path = argv[4];
+  Actor actor;
+  if (!load_actor(argv[2], argv[3], actor)) return 1;
+  PartBundle *bundle = actor.ch->get_bundle(0);
+  NodePath np(actor.root);
+  AnimBundleNode *abn = DCAST(AnimBundleNode, np.find("**/+AnimBundleNode").node());
+  std::vector<PT(AnimControl)> controls = {actor.ctrls.get_anim(0), bundle->bind_anim(abn->get_bundle(), ~0)};
+  if (controls[1] == nullptr) { fprintf(stderr, "second bind failed\n"); return 1; }
+  std::sort(controls.begin(), controls.end(), [](const PT(AnimControl) &a, const PT(AnimControl) &b) { return a.p() < b.p(); });
+  bundle->set_anim_blend_flag(true);
+  bool blend = false;
+  for (int i = 5; i < argc; ++i) blend = blend || strchr(argv[i], '.') != nullptr;
+  if (blend) bundle->set_frame_blend_flag(true);
+  const char *bt = getenv("P3CS_BLEND_TYPE");
+  int blend_type = 1;
+  if (bt != nullptr && strcmp(bt, "linear") == 0) { bundle->set_blend_type(PartBundle::BT_linear); blend_type = 0; }
+  Case out;
+  Exported ex = export_vertex_data(actor.vd, out);
+  export_skeleton(actor.ch, ex, out);
+  std::vector<int32_t> frames, next_frames;
+  std::vector<float> fracs, effects;
+  int samples = 0;
+  for (int i = 5; i < argc; ++i, ++samples) {
+    double f[2] = {0, 0}, e[2] = {0, 0};
+    if (sscanf(argv[i], "%lf:%lf,%lf:%lf", &f[0], &e[0], &f[1], &e[1]) != 4) { fprintf(stderr, "bad sample %s\n", argv[i]); return 1; }
+    for (int k = 0; k < 2; ++k) {
+      controls[k]->pose(f[k]);
+      bundle->set_control_effect(controls[k], (PN_stdfloat)e[k]);
+    }
+    actor.ch->force_update();
+    record_frame(actor.vd, ex, out, samples);
+    for (int k = 0; k < 2; ++k) {
+      frames.push_back(controls[k]->get_frame());
+      next_frames.push_back(controls[k]->get_next_frame());
+      fracs.push_back((float)(PN_stdfloat)controls[k]->get_frac());
+      effects.push_back((float)bundle->get_control_effect(controls[k]));
+    }
+  }
+  out["ctrl_frames"] = make_blob(DT_I32, frames, {(uint64_t)samples, 2});
+  out["ctrl_next_frames"] = make_blob(DT_I32, next_frames, {(uint64_t)samples, 2});
+  out["ctrl_fracs"] = make_blob(DT_F32, fracs, {(uint64_t)samples, 2});
+  out["ctrl_effects"] = make_blob(DT_F32, effects, {(uint64_t)samples, 2});
+  out["anim_blend_type"] = make_blob(DT_I32, std::vector<int32_t>{blend_type}, {1});
+  out["anim_frame_blend"] = make_blob(DT_I32, std::vector<int32_t>{blend ? 1 : 0}, {1});
   return write_case(out_path, out) ? 0 : 1;
 }
 
@@ -608,6 +679,7 @@ int main(int argc, char **argv) {
   if (argc >= 4 && strcmp(argv[1], "hw") == 0) return cmd_hw(argv[2], argv[3]);
   if (argc >= 4 && strcmp(argv[1], "run") == 0) return cmd_run(argv[2], argv[3]);
   if (argc >= 6 && strcmp(argv[1], "egg") == 0) return cmd_egg(argc, argv);
+  if (argc >= 6 && strcmp(argv[1], "eggmulti") == 0) return cmd_eggmulti(argc, argv);
   if (argc >= 5 && strcmp(argv[1], "bench") == 0) return cmd_bench(argv[2], atoi(argv[3]), atoi(argv[4]), argc > 5 ? atoi(argv[5]) : 1);
   fprintf(stderr, "usage: ref_harness run <recipe> <golden> | hw <recipe> <out> | egg <model> <anim> <golden> <frame>... | bench <recipe> <iters> <warmup> [characters]\n");
   return 2;

@@ -806,62 +806,71 @@ static void channel_value_no_scale_shear(const p3o_skeleton *skel, int j, int fr
 }
 
 /* blend_type: 0 BT_linear, 1 BT_normalized_linear (PartBundle::BlendType, chan/partBundle.h; the default
- * comes from the PRC variable anim-blend-type = normalized-linear, chan/partBundle.cxx:41-42). */
-int p3o_pose_blend(const p3o_skeleton *skel, int frame, int next_frame, float frac, int frame_blend, int blend_type,
-                   float *skinning_out) {
-  int J = skel->num_joints, j, k;
+ * comes from the PRC variable anim-blend-type = normalized-linear, chan/partBundle.cxx:41-42).
+ *
+ * K AnimControls in the order PartBundle iterates its _blend map; ctrl_skel[k] carries the channel tables of
+ * control k's animation (hierarchy, default values and inverses are taken from ctrl_skel[0]); a control of
+ * effect 0 is not in the map.  Per joint (MovingPartBase::determine_effective_channels, movingPartBase.cxx:303-333,
+ * and MovingPartMatrix::get_blend_value, movingPartMatrix.cxx:52-198): no control with a channel -> the default
+ * value; exactly one and no frame blending -> its value; else the blend. */
+int p3o_pose_controls(const p3o_skeleton *const *ctrl_skel, int K, const int *frames, const int *next_frames, const float *fracs,
+                      const float *effects, int frame_blend, int blend_type, float *skinning_out) {
+  const p3o_skeleton *skel = ctrl_skel[0];
+  int J = skel->num_joints, j, k, c;
   float *net = (float *)malloc((size_t)(J > 0 ? J : 1) * 16 * sizeof(float));
   if (!net) return -2;
   for (j = 0; j < J; ++j) {
     float value[16];
-    if (!skel->has_channel[j]) {
+    int n_eff = 0, only = -1;
+    for (c = 0; c < K; ++c)
+      if (effects[c] != 0.0f && ctrl_skel[c]->has_channel[j]) { ++n_eff; only = c; }
+    if (n_eff == 0) {
       memcpy(value, skel->default_value + (size_t)j * 16, sizeof(value));
-    } else if (!frame_blend) {
-      channel_value(skel, j, frame, value);  /* the single-value case, movingPartMatrix.cxx:71-76 */
+    } else if (n_eff == 1 && !frame_blend) {
+      channel_value(ctrl_skel[only], j, frames[only], value);  /* the single-value case, movingPartMatrix.cxx:71-76 */
     } else {
-      /* one control of effect 1 with the frame-blend flag: weights e0 = effect * (1 - frac), e1 = effect * frac;
-       * sums start from zero and are divided by net_effect through a reciprocal (LMatrix4 / LVecBase3 operator /=) */
-      const float effect = 1.0f;
-      const float e0 = effect * (1.0f - frac), e1 = effect * frac;
-      const float recip = 1.0f / (0.0f + effect);
-      float v0[16], v1[16], nv[16];
-      if (blend_type == 0) {  /* BT_linear, movingPartMatrix.cxx:82-122 */
-        channel_value(skel, j, frame, v0);
-        channel_value(skel, j, next_frame, v1);
-        for (k = 0; k < 16; ++k) {
-          float n = 0.0f;
-          n = n + v0[k] * e0;
-          n = n + v1[k] * e1;
-          value[k] = n * recip;
+      /* sums start from zero, in map order; the division by net_effect multiplies by its reciprocal
+       * (LMatrix4 / LVecBase3 operator /=, lmatrix4_src.I:1094-1098, lvecBase3_src.I:709-718) */
+      float nv[16], scale[3] = {0.0f, 0.0f, 0.0f}, shear[3] = {0.0f, 0.0f, 0.0f}, net_effect = 0.0f, recip;
+      for (k = 0; k < 16; ++k) nv[k] = 0.0f;
+      for (c = 0; c < K; ++c) {
+        const p3o_skeleton *cs = ctrl_skel[c];
+        float v[16], effect = effects[c];
+        int pass, passes = frame_blend ? 2 : 1;
+        if (effect == 0.0f || !cs->has_channel[j]) continue;
+        for (pass = 0; pass < passes; ++pass) {
+          int fr = pass == 0 ? frames[c] : next_frames[c];
+          float e = !frame_blend ? effect : pass == 0 ? effect * (1.0f - fracs[c]) : effect * fracs[c];
+          if (blend_type == 0) channel_value(cs, j, fr, v);   /* BT_linear, :82-122 */
+          else channel_value_no_scale_shear(cs, j, fr, v);     /* BT_normalized_linear, :125-198 */
+          for (k = 0; k < 16; ++k) nv[k] = nv[k] + v[k] * e;
+          if (blend_type != 0)
+            for (k = 0; k < 3; ++k) {
+              scale[k] = scale[k] + channel_component(cs, j, k, fr) * e;
+              shear[k] = shear[k] + channel_component(cs, j, 3 + k, fr) * e;
+            }
         }
-      } else {  /* BT_normalized_linear, movingPartMatrix.cxx:125-198 */
-        float scale[3], shear[3], false_scale[3], false_shear[3], hpr[3], up3[9], out3[9];
-        int r, c;
-        channel_value_no_scale_shear(skel, j, frame, v0);
-        channel_value_no_scale_shear(skel, j, next_frame, v1);
-        for (k = 0; k < 16; ++k) {
-          float n = 0.0f;
-          n = n + v0[k] * e0;
-          n = n + v1[k] * e1;
-          nv[k] = n * recip;
-        }
-        for (k = 0; k < 3; ++k) {
-          float sc = 0.0f, sh = 0.0f;
-          sc = sc + channel_component(skel, j, k, frame) * e0;
-          sc = sc + channel_component(skel, j, k, next_frame) * e1;
-          sh = sh + channel_component(skel, j, 3 + k, frame) * e0;
-          sh = sh + channel_component(skel, j, 3 + k, next_frame) * e1;
-          scale[k] = sc * recip;
-          shear[k] = sh * recip;
-        }
+        net_effect = net_effect + effect;
+      }
+      recip = 1.0f / net_effect;
+      for (k = 0; k < 16; ++k) nv[k] = nv[k] * recip;
+      if (blend_type == 0) {
+        memcpy(value, nv, sizeof(value));
+      } else {
         /* decompose_matrix(net_value, false_scale, false_shear, hpr, translate); compose_matrix(_value, scale,
          * shear, hpr, translate) (compose_matrix_src.I:18-60) */
+        float false_scale[3], false_shear[3], hpr[3], up3[9], out3[9];
+        int r, cc;
+        for (k = 0; k < 3; ++k) {
+          scale[k] = scale[k] * recip;
+          shear[k] = shear[k] * recip;
+        }
         for (r = 0; r < 3; ++r)
-          for (c = 0; c < 3; ++c) M3(up3, r, c) = M4(nv, r, c);
+          for (cc = 0; cc < 3; ++cc) M3(up3, r, cc) = M4(nv, r, cc);
         p3o_decompose3(up3, skel->coordinate_system, false_scale, false_shear, hpr);
         p3o_compose3(out3, scale, shear, hpr, skel->coordinate_system);
         for (r = 0; r < 3; ++r) {
-          for (c = 0; c < 3; ++c) M4(value, r, c) = M3(out3, r, c);
+          for (cc = 0; cc < 3; ++cc) M4(value, r, cc) = M3(out3, r, cc);
           M4(value, r, 3) = 0.0f;
         }
         M4(value, 3, 0) = M4(nv, 3, 0);
@@ -877,6 +886,12 @@ int p3o_pose_blend(const p3o_skeleton *skel, int frame, int next_frame, float fr
   }
   free(net);
   return 0;
+}
+
+int p3o_pose_blend(const p3o_skeleton *skel, int frame, int next_frame, float frac, int frame_blend, int blend_type,
+                   float *skinning_out) {
+  const float effect = 1.0f;
+  return p3o_pose_controls(&skel, 1, &frame, &next_frame, &frac, &effect, frame_blend, blend_type, skinning_out);
 }
 
 int p3o_pose(const p3o_skeleton *skel, int frame, float *skinning_out) {

@@ -102,6 +102,12 @@ int p3o_pose(const p3o_skeleton *skel, int frame, float *skinning_out);
 int p3o_pose_blend(const p3o_skeleton *skel, int frame, int next_frame, float frac, int frame_blend, int blend_type,
                    float *skinning_out);
 
+/* Several AnimControls at once (PartBundle::set_anim_blend_flag + set_control_effect): control k poses the
+ * animation whose channel tables ctrl_skel[k] carries at frames[k] (/ next_frames[k], fracs[k]) with effects[k];
+ * order = PartBundle's _blend map order. */
+int p3o_pose_controls(const p3o_skeleton *const *ctrl_skel, int K, const int *frames, const int *next_frames, const float *fracs,
+                      const float *effects, int frame_blend, int blend_type, float *skinning_out);
+
 /* Individual pieces, exported for unit tests against the reference's adjacent
  * tests (tests/linmath/test_lmatrix4.py, test_compose_matrix.py). */
 void p3o_blend(const float *palette, const int32_t *xf, const float *w, int n, float *out16);

@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "p3cs_host_register", "p3cs_host_unregister",
     "p3cs_shareable_alloc", "p3cs_shareable_import", "p3cs_shareable_free", "p3cs_group_animate_host",
     "p3cs_hardware_from_blends", "p3cs_blends_from_hardware", "p3cs_group_animate_instances",
-    "p3cs_group_pose_blend",
+    "p3cs_group_pose_blend", "p3cs_skeleton_add_animation", "p3cs_group_pose_controls",
 ]
 
 
@@ -356,6 +356,23 @@ class Skeleton:
         self.handle = C.c_void_p()
         _check(lib().p3cs_skeleton_create(ctx.handle, C.byref(d), C.byref(self.handle)))
 
+    def add_animation(self, skel) -> int:
+        """p3cs_skeleton_add_animation: the channel tables of another animation bound to the same joints (a
+        FlatSkeleton whose table fields describe it); returns its index for p3cs_control_state::anim."""
+        a = [np.ascontiguousarray(x) for x in (
+            skel.has_channel.astype(np.int32), skel.table_length.astype(np.int32), skel.table_offset.astype(np.int32),
+            skel.tables.astype(np.float32) if skel.tables.size else np.zeros(1, np.float32))]
+
+        class _AnimDesc(C.Structure):
+            _fields_ = [("struct_size", C.c_uint32), ("num_table_values", C.c_int32), ("has_channel", C.c_void_p),
+                        ("table_length", C.c_void_p), ("table_offset", C.c_void_p), ("tables", C.c_void_p)]
+        d = _AnimDesc(C.sizeof(_AnimDesc), int(skel.tables.size), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data)
+        idx = C.c_int32(-1)
+        L = lib()
+        L.p3cs_skeleton_add_animation.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        _check(L.p3cs_skeleton_add_animation(self.handle, C.byref(d), C.byref(idx)))
+        return int(idx.value)
+
     def close(self) -> None:
         if self.handle:
             lib().p3cs_skeleton_destroy(self.handle)
@@ -423,6 +440,19 @@ class Group:
         L.p3cs_group_pose_blend.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _check(L.p3cs_group_pose_blend(self.handle, skeleton.handle, first, int(f.size), f.ctypes.data, nf.ctypes.data, fr.ctypes.data,
                                        int(blend_type)))
+
+    def pose_controls(self, skeleton, states: np.ndarray, frame_blend: bool, blend_type: int = 1, first: int = 0) -> None:
+        """p3cs_group_pose_controls: `states` = [count, K, 5] (anim, frame, next_frame, frac, effect) per control."""
+        st = np.asarray(states, np.float64)
+        count, K = st.shape[0], st.shape[1]
+        packed = np.zeros((count, K), np.dtype([("anim", np.int32), ("frame", np.int32), ("next_frame", np.int32),
+                                                  ("frac", np.float32), ("effect", np.float32)]))
+        for i, name in enumerate(("anim", "frame", "next_frame", "frac", "effect")):
+            packed[name] = st[:, :, i]
+        L = lib()
+        L.p3cs_group_pose_controls.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        _check(L.p3cs_group_pose_controls(self.handle, skeleton.handle, first, count, K, packed.ctypes.data,
+                                          1 if frame_blend else 0, int(blend_type)))
 
     def read_palettes(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
         count = self.n - first if count is None else count

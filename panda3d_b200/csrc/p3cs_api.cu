@@ -729,10 +729,11 @@ extern "C" int p3cs_skeleton_create(p3cs_context ctx, const p3cs_skeleton_desc *
   }
   if ((rc = upload_skel<int>(sk, order.data(), J, &s.level_order)) != P3CS_OK) return bail(rc);
   if ((rc = upload_skel<int>(sk, begin.data(), begin.size(), &s.level_begin)) != P3CS_OK) return bail(rc);
-  if ((rc = upload_skel<int>(sk, d->has_channel, J, &s.has_channel)) != P3CS_OK) return bail(rc);
-  if ((rc = upload_skel<int>(sk, d->table_length, (size_t)J * 12, &s.table_length)) != P3CS_OK) return bail(rc);
-  if ((rc = upload_skel<int>(sk, d->table_offset, (size_t)J * 12, &s.table_offset)) != P3CS_OK) return bail(rc);
-  if ((rc = upload_skel<float>(sk, d->tables, d->num_table_values, &s.tables)) != P3CS_OK) return bail(rc);
+  s.num_animations = 1;  // animation 0: the channel tables of the descriptor
+  if ((rc = upload_skel<int>(sk, d->has_channel, J, &s.anim[0].has_channel)) != P3CS_OK) return bail(rc);
+  if ((rc = upload_skel<int>(sk, d->table_length, (size_t)J * 12, &s.anim[0].table_length)) != P3CS_OK) return bail(rc);
+  if ((rc = upload_skel<int>(sk, d->table_offset, (size_t)J * 12, &s.anim[0].table_offset)) != P3CS_OK) return bail(rc);
+  if ((rc = upload_skel<float>(sk, d->tables, d->num_table_values, &s.anim[0].tables)) != P3CS_OK) return bail(rc);
   if ((rc = upload_skel<float>(sk, d->default_value, (size_t)J * 16, &s.default_value)) != P3CS_OK) return bail(rc);
   if ((rc = upload_skel<float>(sk, d->initial_inverse, (size_t)J * 16, &s.initial_inverse)) != P3CS_OK) return bail(rc);
   if ((rc = upload_skel<float>(sk, d->root_xform, 16, &s.root_xform)) != P3CS_OK) return bail(rc);
@@ -751,49 +752,96 @@ extern "C" int p3cs_skeleton_destroy(p3cs_skeleton sk) {
   return P3CS_OK;
 }
 
-static int pose_common(p3cs_group grp, p3cs_skeleton sk, int first, int count, const int32_t *host_frames,
-                       const int32_t *host_next_frames, const float *host_fracs, int blend_type, const char *what) {
+extern "C" int p3cs_skeleton_add_animation(p3cs_skeleton sk, const p3cs_animation_desc *d, int32_t *out_index) {
+  if (sk == nullptr || d == nullptr || out_index == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_skeleton_add_animation: NULL argument");
+  if (d->struct_size != sizeof(p3cs_animation_desc)) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_animation_desc::struct_size mismatch");
+  SkeletonDev &s = sk->dev;
+  if (s.num_animations >= kMaxAnimations) return p3cs_fail(P3CS_ERR_UNSUPPORTED, "a skeleton holds at most %d animations", kMaxAnimations);
+  const int J = s.num_joints;
+  for (int j = 0; j < J; ++j)
+    for (int i = 0; i < 12; ++i) {
+      const int len = d->table_length[j * 12 + i], off = d->table_offset[j * 12 + i];
+      if (len < 0 || off < 0 || off + len > d->num_table_values) return p3cs_fail(P3CS_ERR_INVALID, "joint %d: table %d out of range", j, i);
+    }
+  DeviceGuard g(sk->ctx->device);
+  AnimationDev an{};
+  int rc;
+  if ((rc = upload_skel<int>(sk, d->has_channel, J, &an.has_channel)) != P3CS_OK) return rc;
+  if ((rc = upload_skel<int>(sk, d->table_length, (size_t)J * 12, &an.table_length)) != P3CS_OK) return rc;
+  if ((rc = upload_skel<int>(sk, d->table_offset, (size_t)J * 12, &an.table_offset)) != P3CS_OK) return rc;
+  if ((rc = upload_skel<float>(sk, d->tables, d->num_table_values, &an.tables)) != P3CS_OK) return rc;
+  CUDA_TRY(cudaStreamSynchronize(sk->ctx->stream));
+  *out_index = s.num_animations;
+  s.anim[s.num_animations++] = an;
+  return P3CS_OK;
+}
+
+// states: [count][num_controls]; NULL = the unblended single-control form with host_frames.
+static int pose_common(p3cs_group grp, p3cs_skeleton sk, int first, int count, const int32_t *host_frames, const ControlState *states,
+                       int num_controls, int frame_blend, int blend_type, const char *what) {
   int rc = check_span(grp, first, count, what);
   if (rc != P3CS_OK) return rc;
-  if (sk == nullptr || host_frames == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "%s: NULL argument", what);
+  if (sk == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "%s: skeleton is NULL", what);
   if (sk->num_palette != grp->mesh->dev.num_transforms)
     return p3cs_fail(P3CS_ERR_INVALID, "skeleton feeds %d palette slots, the mesh has %d transforms", sk->num_palette, grp->mesh->dev.num_transforms);
   if (count == 0) return P3CS_OK;
   DeviceGuard g(grp->mesh->ctx->device);
   cudaStream_t s = grp->mesh->ctx->stream;
-  if (grp->frames_capacity < count) {  // frames, next frames, fractions: three arrays of `capacity` words
+  const size_t words = states != nullptr ? (size_t)count * num_controls * (sizeof(ControlState) / 4) : (size_t)count;
+  if ((size_t)grp->frames_capacity < words) {
     if (grp->frames_dev != nullptr) {
       CUDA_TRY(cudaStreamSynchronize(s));
       CUDA_TRY(cudaFree(grp->frames_dev));
     }
     grp->frames_dev = nullptr;
-    CUDA_TRY(cudaMalloc(&grp->frames_dev, (size_t)count * 3 * sizeof(int)));
-    grp->frames_capacity = count;
+    CUDA_TRY(cudaMalloc(&grp->frames_dev, words * 4));
+    grp->frames_capacity = (int)words;
   }
-  int *frames_dev = grp->frames_dev, *next_dev = nullptr;
-  float *fracs_dev = nullptr;
-  CUDA_TRY(cudaMemcpyAsync(frames_dev, host_frames, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, s));
-  if (host_next_frames != nullptr) {
-    next_dev = grp->frames_dev + grp->frames_capacity;
-    fracs_dev = reinterpret_cast<float *>(grp->frames_dev + 2 * (size_t)grp->frames_capacity);
-    CUDA_TRY(cudaMemcpyAsync(next_dev, host_next_frames, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(fracs_dev, host_fracs, (size_t)count * sizeof(float), cudaMemcpyHostToDevice, s));
-  }
-  launch_pose(sk->dev, const_cast<float *>(grp->dev.palettes), sk->num_palette, frames_dev, next_dev, fracs_dev, blend_type, first, count, s);
+  CUDA_TRY(cudaMemcpyAsync(grp->frames_dev, states != nullptr ? static_cast<const void *>(states) : static_cast<const void *>(host_frames),
+                           words * 4, cudaMemcpyHostToDevice, s));
+  launch_pose(sk->dev, const_cast<float *>(grp->dev.palettes), sk->num_palette, states != nullptr ? nullptr : grp->frames_dev,
+              states != nullptr ? reinterpret_cast<const ControlState *>(grp->frames_dev) : nullptr, num_controls, frame_blend, blend_type,
+              first, count, s);
   CUDA_TRY(cudaGetLastError());
   return P3CS_OK;
 }
 
+static int check_blend_type(int blend_type, const char *what) {
+  if (blend_type != P3CS_BT_LINEAR && blend_type != P3CS_BT_NORMALIZED_LINEAR)
+    return p3cs_fail(P3CS_ERR_UNSUPPORTED, "%s: blend type %d (only BT_linear and BT_normalized_linear)", what, blend_type);
+  return P3CS_OK;
+}
+
 extern "C" int p3cs_group_pose(p3cs_group grp, p3cs_skeleton sk, int first, int count, const int32_t *host_frames) {
-  return pose_common(grp, sk, first, count, host_frames, nullptr, nullptr, P3CS_BT_NORMALIZED_LINEAR, "p3cs_group_pose");
+  if (host_frames == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_pose: NULL argument");
+  return pose_common(grp, sk, first, count, host_frames, nullptr, 0, 0, P3CS_BT_NORMALIZED_LINEAR, "p3cs_group_pose");
 }
 
 extern "C" int p3cs_group_pose_blend(p3cs_group grp, p3cs_skeleton sk, int first, int count, const int32_t *host_frames,
                                      const int32_t *host_next_frames, const float *host_fracs, int blend_type) {
-  if (host_next_frames == nullptr || host_fracs == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_pose_blend: NULL argument");
-  if (blend_type != P3CS_BT_LINEAR && blend_type != P3CS_BT_NORMALIZED_LINEAR)
-    return p3cs_fail(P3CS_ERR_UNSUPPORTED, "p3cs_group_pose_blend: blend type %d (only BT_linear and BT_normalized_linear)", blend_type);
-  return pose_common(grp, sk, first, count, host_frames, host_next_frames, host_fracs, blend_type, "p3cs_group_pose_blend");
+  if (host_frames == nullptr || host_next_frames == nullptr || host_fracs == nullptr)
+    return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_pose_blend: NULL argument");
+  int rc = check_blend_type(blend_type, "p3cs_group_pose_blend");
+  if (rc != P3CS_OK) return rc;
+  std::vector<ControlState> states((size_t)std::max(count, 0));
+  for (int i = 0; i < count; ++i) states[i] = ControlState{0, host_frames[i], host_next_frames[i], host_fracs[i], 1.0f};
+  return pose_common(grp, sk, first, count, nullptr, states.data(), 1, 1, blend_type, "p3cs_group_pose_blend");
+}
+
+extern "C" int p3cs_group_pose_controls(p3cs_group grp, p3cs_skeleton sk, int first, int count, int num_controls,
+                                        const p3cs_control_state *host_states, int frame_blend, int blend_type) {
+  static_assert(sizeof(p3cs_control_state) == sizeof(ControlState), "p3cs_control_state layout");
+  if (host_states == nullptr || num_controls < 1 || num_controls > 16)
+    return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_pose_controls: bad arguments (1..16 controls)");
+  int rc = check_blend_type(blend_type, "p3cs_group_pose_controls");
+  if (rc != P3CS_OK) return rc;
+  if (sk != nullptr)
+    for (size_t i = 0; i < (size_t)std::max(count, 0) * num_controls; ++i)
+      if (host_states[i].anim < 0 || host_states[i].anim >= sk->dev.num_animations)
+        return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_pose_controls: state %zu plays animation %d, the skeleton holds %d", i,
+                         host_states[i].anim, sk->dev.num_animations);
+  return pose_common(grp, sk, first, count, nullptr, reinterpret_cast<const ControlState *>(host_states), num_controls,
+                     frame_blend != 0, blend_type, "p3cs_group_pose_controls");
 }
 
 extern "C" int p3cs_group_read_palettes(p3cs_group grp, int first, int count, float *host_dst) {

@@ -93,24 +93,41 @@ struct GroupDev {
 };
 
 // Joint hierarchy ("next" row f1): static description of a character's skeleton, joints parents-first.
+constexpr int kMaxAnimations = 8;  // animations (channel-table sets) one skeleton can hold
+
+// The channel tables of one animation bound to a skeleton (AnimBundle -> AnimChannelMatrixXfmTable per joint).
+struct AnimationDev {
+  const int *has_channel;    // [J]
+  const int *table_length;   // [J][12]
+  const int *table_offset;   // [J][12]
+  const float *tables;
+};
+
 struct SkeletonDev {
   int num_joints;
   int coordinate_system;
   int max_level;
+  int num_animations;
   const int *parent;          // -1: top-level joint
   const int *level_order;     // joint indices sorted by depth in the tree
   const int *level_begin;     // [max_level+2] ranges of level_order
-  const int *has_channel;
-  const int *table_length;    // [J][12]
-  const int *table_offset;    // [J][12]
-  const float *tables;
+  AnimationDev anim[kMaxAnimations];
   const float *default_value; // [J][16]
   const float *initial_inverse;
   const float *root_xform;    // [16]
   const int *palette_joint;   // [T]
 };
-void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, const int *frames_dev, const int *next_frames_dev,
-                 const float *fracs_dev, int blend_type, int first_instance, int count, cudaStream_t stream);
+
+// One AnimControl of one instance: which animation it plays, AnimControl::get_frame / get_next_frame / get_frac, and
+// its effect in PartBundle's blend map (0 = not in the map).  Layout of p3cs_control_state (include/p3cudaskin.h).
+struct ControlState {
+  int anim, frame, next_frame;
+  float frac, effect;
+};
+
+// frames_dev != nullptr: one control of animation 0 per instance, no blending.  Else states_dev[count][num_controls].
+void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, const int *frames_dev, const ControlState *states_dev,
+                 int num_controls, int frame_blend, int blend_type, int first_instance, int count, cudaStream_t stream);
 
 void launch_blend(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);
 void launch_skin(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);

@@ -9,9 +9,10 @@
 // __syncthreads per tree level) and writes
 // the palette straight into the group's device buffer: with it a crowd needs one int per
 // instance and frame from the host instead of T x 64 bytes of matrices.
-// Covers one AnimControl, without frame blending (chan/movingPartMatrix.cxx:71-76) or with it
-// (PartBundle::set_frame_blend_flag: BT_linear and BT_normalized_linear, :78-198); same -fmad=false arithmetic
-// as the rest of the library.
+// Covers one AnimControl without blending (chan/movingPartMatrix.cxx:71-76), the frame-blend flag
+// (PartBundle::set_frame_blend_flag) and several AnimControls blended by their effects (set_anim_blend_flag /
+// set_control_effect), for BT_linear and BT_normalized_linear (:78-198); same -fmad=false arithmetic as the rest
+// of the library.
 #include "p3cs_device.cuh"
 
 namespace p3cs {
@@ -27,19 +28,19 @@ __device__ __forceinline__ void mul4(float *res, const float *a, const float *b)
 
 // One table component of a joint at a frame: table[frame % size], or the default of an empty table
 // (1 for the scales, 0 otherwise; animChannelMatrixXfmTable.I:75-85).
-__device__ __forceinline__ float channel_component(const SkeletonDev &skel, int j, int i, int frame) {
-  const int len = __ldg(skel.table_length + j * 12 + i);
-  return len == 0 ? (i < 3 ? 1.0f : 0.0f) : __ldg(skel.tables + __ldg(skel.table_offset + j * 12 + i) + frame % len);
+__device__ __forceinline__ float channel_component(const AnimationDev &an, int j, int i, int frame) {
+  const int len = __ldg(an.table_length + j * 12 + i);
+  return len == 0 ? (i < 3 ? 1.0f : 0.0f) : __ldg(an.tables + __ldg(an.table_offset + j * 12 + i) + frame % len);
 }
 
 // AnimChannelMatrixXfmTable::get_value (animChannelMatrixXfmTable.cxx:112-124), or get_value_no_scale_shear
 // (:131-149) with unit scale and zero shear: compose_matrix of the components -> LMatrix4f(upper3, translate).
-__device__ __forceinline__ void channel_value(const SkeletonDev &skel, int j, int frame, bool no_scale_shear, float *value) {
+__device__ __forceinline__ void channel_value(const AnimationDev &an, int cs, int j, int frame, bool no_scale_shear, float *value) {
   float comp[12];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) comp[i] = (no_scale_shear && i < 6) ? (i < 3 ? 1.0f : 0.0f) : channel_component(skel, j, i, frame);
+  for (int i = 0; i < 12; ++i) comp[i] = (no_scale_shear && i < 6) ? (i < 3 ? 1.0f : 0.0f) : channel_component(an, j, i, frame);
   Mat3 up3;
-  compose3(up3, comp + 0, comp + 3, comp + 6, skel.coordinate_system);
+  compose3(up3, comp + 0, comp + 3, comp + 6, cs);
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
 #pragma unroll
@@ -52,73 +53,101 @@ __device__ __forceinline__ void channel_value(const SkeletonDev &skel, int j, in
   value[15] = 1.0f;
 }
 
-// next_frames == nullptr: one AnimControl, no frame blending (movingPartMatrix.cxx:71-76).  Otherwise the bundle's
-// frame-blend flag is on: the values at frame and next_frame are blended by frac, blend_type 0 = BT_linear
-// (:82-122), 1 = BT_normalized_linear (:125-198, the PRC default), one control of effect 1.
+// BLEND = false: one AnimControl of animation 0 per instance, no frame blending (movingPartMatrix.cxx:71-76).
+// BLEND = true: `num_controls` AnimControls per instance (PartBundle::set_anim_blend_flag / set_control_effect) in
+// the order of the bundle's blend map, and / or the frame-blend flag; per joint
+// (MovingPartBase::determine_effective_channels, movingPartBase.cxx:303-333; MovingPartMatrix::get_blend_value,
+// movingPartMatrix.cxx:52-198): no control with a channel -> the default value; exactly one and no frame blending ->
+// its value; else the blend, blend_type 0 = BT_linear (:82-122), 1 = BT_normalized_linear (:125-198, the PRC default).
 template <bool BLEND>
 __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *palettes, int num_transforms, const int *frames,
-                                                    const int *next_frames, const float *fracs, int blend_type, int first_instance) {
+                                                    const ControlState *states, int num_controls, int frame_blend, int blend_type,
+                                                    int first_instance) {
   extern __shared__ float smem_pose[];  // [J][16] local values, then [J][16] net transforms of this instance
   const int inst = first_instance + blockIdx.x;
-  const int frame = __ldg(frames + blockIdx.x);
   const int J = skel.num_joints;
   float *local = smem_pose;
   float *net = smem_pose + (size_t)J * 16;
+  const int cs = skel.coordinate_system;
 
-  // phase 1, all joints in parallel: the joint's own value at this frame
-  // (AnimChannelMatrixXfmTable::get_value -> compose_matrix, or the default value)
+  // phase 1, all joints in parallel: the joint's own value
   for (int j = threadIdx.x; j < J; j += blockDim.x) {
     float value[16];
-    if (BLEND && __ldg(skel.has_channel + j)) {
-      const int next_frame = __ldg(next_frames + blockIdx.x);
-      const float frac = __ldg(fracs + blockIdx.x);
-      // weights e0 = effect * (1 - frac), e1 = effect * frac with effect = 1; the sums start from zero and are
-      // divided by net_effect through a reciprocal (LMatrix4 / LVecBase3 operator /=)
-      const float effect = 1.0f;
-      const float e0 = effect * (1.0f - frac), e1 = effect * frac;
-      const float recip = 1.0f / (0.0f + effect);
-      float v0[16], v1[16];
-      channel_value(skel, j, frame, blend_type != 0, v0);
-      channel_value(skel, j, next_frame, blend_type != 0, v1);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        float n = 0.0f;
-        n = n + v0[k] * e0;
-        n = n + v1[k] * e1;
-        value[k] = n * recip;
+    bool have = false;
+    if (!BLEND) {
+      if (__ldg(skel.anim[0].has_channel + j)) {
+        channel_value(skel.anim[0], cs, j, __ldg(frames + blockIdx.x), false, value);
+        have = true;
       }
-      if (blend_type != 0) {
-        float scale[3], shear[3], false_scale[3], false_shear[3], hpr[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          float sc = 0.0f, sh = 0.0f;
-          sc = sc + channel_component(skel, j, k, frame) * e0;
-          sc = sc + channel_component(skel, j, k, next_frame) * e1;
-          sh = sh + channel_component(skel, j, 3 + k, frame) * e0;
-          sh = sh + channel_component(skel, j, 3 + k, next_frame) * e1;
-          scale[k] = sc * recip;
-          shear[k] = sh * recip;
-        }
-        // decompose_matrix(net_value, false_scale, false_shear, hpr, translate), then
-        // compose_matrix(_value, scale, shear, hpr, translate)
-        Mat3 up3, out3;
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) up3.m[r][c] = value[r * 4 + c];
-        decompose3(up3, skel.coordinate_system, false_scale, false_shear, hpr);
-        compose3(out3, scale, shear, hpr, skel.coordinate_system);
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) value[r * 4 + c] = out3.m[r][c];
-          value[r * 4 + 3] = 0.0f;
-        }
-        value[15] = 1.0f;  // translate = row 3 of the blended matrix stays
-      }
-    } else if (__ldg(skel.has_channel + j)) {
-      channel_value(skel, j, frame, false, value);
     } else {
+      const ControlState *st = states + (size_t)blockIdx.x * num_controls;
+      int n_eff = 0, only = -1;
+      for (int c = 0; c < num_controls; ++c)
+        if (st[c].effect != 0.0f && __ldg(skel.anim[st[c].anim].has_channel + j)) {
+          ++n_eff;
+          only = c;
+        }
+      if (n_eff == 1 && !frame_blend) {
+        channel_value(skel.anim[st[only].anim], cs, j, st[only].frame, false, value);
+        have = true;
+      } else if (n_eff > 0) {
+        // sums start from zero, in map order; the division by net_effect multiplies by its reciprocal
+        // (LMatrix4 / LVecBase3 operator /=)
+        float nv[16], scale[3] = {0.0f, 0.0f, 0.0f}, shear[3] = {0.0f, 0.0f, 0.0f}, net_effect = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) nv[k] = 0.0f;
+        for (int c = 0; c < num_controls; ++c) {
+          const ControlState cst = st[c];
+          const AnimationDev &an = skel.anim[cst.anim];
+          if (cst.effect == 0.0f || !__ldg(an.has_channel + j)) continue;
+          for (int pass = 0; pass < (frame_blend ? 2 : 1); ++pass) {
+            const int fr = pass == 0 ? cst.frame : cst.next_frame;
+            const float e = !frame_blend ? cst.effect : pass == 0 ? cst.effect * (1.0f - cst.frac) : cst.effect * cst.frac;
+            float v[16];
+            channel_value(an, cs, j, fr, blend_type != 0, v);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) nv[k] = nv[k] + v[k] * e;
+            if (blend_type != 0) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                scale[k] = scale[k] + channel_component(an, j, k, fr) * e;
+                shear[k] = shear[k] + channel_component(an, j, 3 + k, fr) * e;
+              }
+            }
+          }
+          net_effect = net_effect + cst.effect;
+        }
+        const float recip = 1.0f / net_effect;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) value[k] = nv[k] * recip;
+        if (blend_type != 0) {
+          // decompose_matrix(net_value, false_scale, false_shear, hpr, translate), then
+          // compose_matrix(_value, scale, shear, hpr, translate)
+          float false_scale[3], false_shear[3], hpr[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            scale[k] = scale[k] * recip;
+            shear[k] = shear[k] * recip;
+          }
+          Mat3 up3, out3;
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) up3.m[r][c] = value[r * 4 + c];
+          decompose3(up3, cs, false_scale, false_shear, hpr);
+          compose3(out3, scale, shear, hpr, cs);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) value[r * 4 + c] = out3.m[r][c];
+            value[r * 4 + 3] = 0.0f;
+          }
+          value[15] = 1.0f;  // translate = row 3 of the blended matrix stays
+        }
+        have = true;
+      }
+    }
+    if (!have) {
 #pragma unroll
       for (int k = 0; k < 16; ++k) value[k] = __ldg(skel.default_value + j * 16 + k);
     }
@@ -164,19 +193,19 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
   }
 }
 
-void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, const int *frames_dev, const int *next_frames_dev,
-                 const float *fracs_dev, int blend_type, int first_instance, int count, cudaStream_t stream) {
+void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, const int *frames_dev, const ControlState *states_dev,
+                 int num_controls, int frame_blend, int blend_type, int first_instance, int count, cudaStream_t stream) {
   if (count == 0 || skel.num_joints == 0) return;
   const size_t smem = (size_t)skel.num_joints * 128;
   int threads = ((skel.num_joints + 31) / 32) * 32;
   if (threads > 256) threads = 256;
-  if (next_frames_dev != nullptr) {
+  if (states_dev != nullptr) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(pose_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pose_kernel<true><<<count, threads, smem, stream>>>(skel, palettes, num_transforms, frames_dev, next_frames_dev, fracs_dev, blend_type,
-                                                        first_instance);
+    pose_kernel<true><<<count, threads, smem, stream>>>(skel, palettes, num_transforms, nullptr, states_dev, num_controls, frame_blend,
+                                                        blend_type, first_instance);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(pose_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pose_kernel<false><<<count, threads, smem, stream>>>(skel, palettes, num_transforms, frames_dev, nullptr, nullptr, blend_type,
+    pose_kernel<false><<<count, threads, smem, stream>>>(skel, palettes, num_transforms, frames_dev, nullptr, 0, 0, blend_type,
                                                          first_instance);
   }
 }

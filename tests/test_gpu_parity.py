@@ -816,3 +816,46 @@ def test_plain_c_host_animates_through_the_plugin_table(tmp_path):
     res = subprocess.run([str(exe), _capi.LIB_PATH, "--run"], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "vertex 0 -> (3.75, 7.5, 2.5)" in res.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture", ["panda_walk4_two_controls_hold", "panda_walk4_two_controls_hold_linear",
+                                     "panda_walk4_two_controls_frame_blend", "panda_walk4_two_controls_frame_blend_linear"])
+def test_joint_hierarchy_with_two_blended_controls(gpu_ctx, fixture):
+    """f1 with several AnimControls (PartBundle::set_anim_blend_flag / set_control_effect): p3cs_group_pose_controls
+    against the reference's Character posed with two controls of different frames and effects -- the second control
+    plays a second, separately uploaded copy of the animation (p3cs_skeleton_add_animation)."""
+    from conftest import GOLDEN_DIR
+    from panda3d_b200.flat import skeleton_from_case
+    case = load_case(os.path.join(GOLDEN_DIR, "skeleton", fixture + ".p3cs"))
+    mesh, skel = mesh_from_case(case), skeleton_from_case(case)
+    fb, bt = bool(case["anim_frame_blend"][0]), int(case["anim_blend_type"][0])
+    n = case["ctrl_frames"].shape[0]
+    states = np.zeros((n, 2, 5))
+    states[:, :, 1] = case["ctrl_frames"]
+    states[:, :, 2] = case["ctrl_next_frames"]
+    states[:, :, 3] = case["ctrl_fracs"]
+    states[:, :, 4] = case["ctrl_effects"]
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    dskel = _capi.Skeleton(gpu_ctx, skel)
+    states[:, 1, 0] = dskel.add_animation(skel)
+    assert states[0, 1, 0] == 1
+    grp = _capi.Group(dmesh, n)
+    try:
+        grp.pose_controls(dskel, states, fb, bt)
+        pal = grp.read_palettes()
+        ref = case["palette"]
+        scale = np.abs(ref).max(axis=(1, 2), keepdims=True)
+        assert (np.abs(pal - ref) / scale).max() <= REL_TOL
+        grp.animate()
+        out = grp.read_output(0)
+        for i in range(n):
+            compare_outputs(mesh, [out[i]], [case["expect0"][i]], f"{fixture} sample {i}")
+        bad = states.copy()
+        bad[0, 0, 0] = 7
+        with pytest.raises(_capi.P3csError):
+            grp.pose_controls(dskel, bad, fb, bt)
+    finally:
+        grp.close()
+        dskel.close()
+        dmesh.close()

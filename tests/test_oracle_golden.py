@@ -99,3 +99,25 @@ def test_oracle_pose_with_frame_blending_matches_reference(fixture):
         assert np.array_equal(pal.view(np.uint32), case["palette"][fi].view(np.uint32)), f"frame {frame}+{frac}"
         outs, _, _ = om.animate(pal)
         assert np.array_equal(outs[0].reshape(-1), np.asarray(case["expect0"][fi]).reshape(-1))
+
+
+MULTI = ["panda_walk4_two_controls_hold", "panda_walk4_two_controls_hold_linear",
+         "panda_walk4_two_controls_frame_blend", "panda_walk4_two_controls_frame_blend_linear"]
+
+
+@pytest.mark.parametrize("fixture", MULTI)
+def test_oracle_pose_with_two_controls_matches_reference(fixture):
+    """Two AnimControls blended by their effects (PartBundle::set_anim_blend_flag / set_control_effect), with the
+    frames held or blended, BT_normalized_linear and BT_linear: oracle.pose_controls reproduces the reference's
+    skinning matrices bit for bit (tests/golden/skeleton/, oracle/ref_harness.cxx `eggmulti`)."""
+    import os
+    from conftest import GOLDEN_DIR
+    from panda3d_b200.flat import skeleton_from_case
+    case = load_case(os.path.join(GOLDEN_DIR, "skeleton", fixture + ".p3cs"))
+    skel = skeleton_from_case(case)
+    fb, bt = bool(case["anim_frame_blend"][0]), int(case["anim_blend_type"][0])
+    assert (case["ctrl_effects"] == 0).any(), "one sample must drop a control from the blend"
+    for i in range(case["ctrl_frames"].shape[0]):
+        skin = oracle.pose_controls([skel, skel], case["ctrl_frames"][i], case["ctrl_next_frames"][i], case["ctrl_fracs"][i],
+                                    case["ctrl_effects"][i], fb, bt)
+        assert np.array_equal(skin[skel.palette_joint].view(np.uint32), case["palette"][i].view(np.uint32)), f"sample {i}"
