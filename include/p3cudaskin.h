@@ -356,6 +356,15 @@ typedef struct p3cs_skeleton_desc {
   const float *initial_inverse;   /* [J][16] CharacterJoint::_initial_net_transform_inverse */
   const float *root_xform;        /* [16] PartBundle::get_root_xform() */
   const int32_t *palette_joint;   /* [T] joint behind each palette slot (JointVertexTransform::get_joint) */
+  /* Morph sliders driven by scalar channels (CharacterVertexSlider -> CharacterSlider -> AnimChannelScalarTable,
+   * char/characterVertexSlider.cxx:56-59, chan/animChannelScalarTable.cxx:88-94), in SliderTable order.  0 sliders:
+   * posing leaves the group's slider values alone; otherwise num_sliders must equal the mesh's and every pose call
+   * also writes them (MovingPartScalar::get_blend_value, chan/movingPartScalar.cxx:43-105). */
+  int32_t num_sliders;
+  const int32_t *slider_has_channel;   /* [S] */
+  const int32_t *slider_table_length;  /* [S] values in `tables`; 0 = empty table (value 0) */
+  const int32_t *slider_table_offset;  /* [S] */
+  const float *slider_default;         /* [S] MovingPartScalar::_default_value */
 } p3cs_skeleton_desc;
 
 P3CS_EXPORT int p3cs_skeleton_create(p3cs_context ctx, const p3cs_skeleton_desc *desc, p3cs_skeleton *out);
@@ -386,6 +395,9 @@ typedef struct p3cs_animation_desc {
   const int32_t *table_length;    /* [J][12] */
   const int32_t *table_offset;    /* [J][12] */
   const float *tables;
+  const int32_t *slider_has_channel;   /* [S] of the skeleton; may be NULL when it has no sliders */
+  const int32_t *slider_table_length;  /* [S] */
+  const int32_t *slider_table_offset;  /* [S] */
 } p3cs_animation_desc;
 typedef struct p3cs_control_state {
   int32_t anim;                   /* animation index of this control */

@@ -189,17 +189,30 @@ class _Skeleton(C.Structure):
     _fields_ = [("num_joints", C.c_int32), ("coordinate_system", C.c_int32),
                 ("parent", C.c_void_p), ("has_channel", C.c_void_p), ("table_length", C.c_void_p),
                 ("table_offset", C.c_void_p), ("tables", C.c_void_p), ("default_value", C.c_void_p),
-                ("initial_inverse", C.c_void_p), ("root_xform", C.c_void_p)]
+                ("initial_inverse", C.c_void_p), ("root_xform", C.c_void_p),
+                ("num_sliders", C.c_int32), ("slider_has_channel", C.c_void_p), ("slider_table_length", C.c_void_p),
+                ("slider_table_offset", C.c_void_p), ("slider_default", C.c_void_p)]
+
+
+def _skeleton_struct(skel, keep: list) -> "_Skeleton":
+    """ctypes view of a FlatSkeleton; `keep` receives the arrays that must outlive the call."""
+    arrs = [np.ascontiguousarray(a) for a in (skel.parent, skel.has_channel, skel.table_length, skel.table_offset,
+                                              skel.tables if skel.tables.size else np.zeros(1, np.float32),
+                                              skel.default_value, skel.initial_inverse, skel.root_xform)]
+    S = skel.num_sliders
+    sl = [np.ascontiguousarray(a) if S else np.zeros(1, dt) for a, dt in (
+        (skel.slider_has_channel, np.int32), (skel.slider_table_length, np.int32), (skel.slider_table_offset, np.int32),
+        (skel.slider_default, np.float32))]
+    keep.append(arrs + sl)
+    return _Skeleton(skel.num_joints, skel.coordinate_system, *[a.ctypes.data for a in arrs], S, *[a.ctypes.data for a in sl])
 
 
 def pose(skel, frame: int, next_frame: Optional[int] = None, frac: float = 0.0, blend_type: int = 1) -> np.ndarray:
     """CharacterJoint::_skinning_matrix of every joint at `frame` ([J,16]); palette = result[skel.palette_joint].
     With `next_frame` the bundle's frame-blend flag is on: values blend towards next_frame by `frac`
     (blend_type 0 = BT_linear, 1 = BT_normalized_linear, the reference's default)."""
-    arrs = [np.ascontiguousarray(a) for a in (skel.parent, skel.has_channel, skel.table_length, skel.table_offset,
-                                              skel.tables if skel.tables.size else np.zeros(1, np.float32),
-                                              skel.default_value, skel.initial_inverse, skel.root_xform)]
-    s = _Skeleton(skel.num_joints, skel.coordinate_system, *[a.ctypes.data for a in arrs])
+    keep: list = []
+    s = _skeleton_struct(skel, keep)
     out = np.empty((skel.num_joints, 16), np.float32)
     lib().p3o_pose_blend.restype = C.c_int
     rc = lib().p3o_pose_blend(C.byref(s), C.c_int(int(frame)), C.c_int(int(frame if next_frame is None else next_frame)),
@@ -211,13 +224,8 @@ def pose(skel, frame: int, next_frame: Optional[int] = None, frac: float = 0.0, 
 
 def pose_controls(skels, frames, next_frames, fracs, effects, frame_blend: bool, blend_type: int = 1) -> np.ndarray:
     """Several AnimControls blended (p3o_pose_controls): skels[k] carries control k's channel tables."""
-    keep, structs = [], []
-    for skel in skels:
-        arrs = [np.ascontiguousarray(a) for a in (skel.parent, skel.has_channel, skel.table_length, skel.table_offset,
-                                                  skel.tables if skel.tables.size else np.zeros(1, np.float32),
-                                                  skel.default_value, skel.initial_inverse, skel.root_xform)]
-        keep.append(arrs)
-        structs.append(_Skeleton(skel.num_joints, skel.coordinate_system, *[a.ctypes.data for a in arrs]))
+    keep: list = []
+    structs = [_skeleton_struct(skel, keep) for skel in skels]
     K = len(skels)
     ptrs = (C.POINTER(_Skeleton) * K)(*[C.pointer(s) for s in structs])
     f = np.ascontiguousarray(frames, np.int32)
@@ -232,3 +240,20 @@ def pose_controls(skels, frames, next_frames, fracs, effects, frame_blend: bool,
     if rc != 0:
         raise RuntimeError(f"oracle pose_controls failed rc={rc}")
     return out
+
+
+def pose_sliders(skels, frames, next_frames, fracs, effects, frame_blend: bool) -> np.ndarray:
+    """Slider values of the same controls (p3o_pose_sliders): [S], SliderTable order."""
+    keep: list = []
+    structs = [_skeleton_struct(skel, keep) for skel in skels]
+    K = len(skels)
+    ptrs = (C.POINTER(_Skeleton) * K)(*[C.pointer(s) for s in structs])
+    f = np.ascontiguousarray(frames, np.int32)
+    nf = np.ascontiguousarray(next_frames, np.int32)
+    fr = np.ascontiguousarray(fracs, np.float32)
+    ef = np.ascontiguousarray(effects, np.float32)
+    out = np.empty(max(1, skels[0].num_sliders), np.float32)
+    lib().p3o_pose_sliders.restype = C.c_int
+    lib().p3o_pose_sliders(ptrs, C.c_int(K), f.ctypes.data_as(C.c_void_p), nf.ctypes.data_as(C.c_void_p), fr.ctypes.data_as(C.c_void_p),
+                           ef.ctypes.data_as(C.c_void_p), C.c_int(1 if frame_blend else 0), out.ctypes.data_as(C.c_void_p))
+    return out[:skels[0].num_sliders]

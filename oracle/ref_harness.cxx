@@ -45,6 +45,9 @@
 #include "animChannelMatrixXfmTable.h"
 #include "partBundle.h"
 #include "animBundleNode.h"
+#include "animChannelScalarTable.h"
+#include "characterSlider.h"
+#include "characterVertexSlider.h"
 #include "animControl.h"
 #include "movingPartMatrix.h"
 
@@ -140,12 +143,14 @@ static std::vector<int32_t> sparse_ranges(const SparseArray &s) {
 struct Exported {
   std::vector<const VertexTransform *> palette;  // ascending address = palette order
   std::vector<int> out_arrays;                   // source array index of each output array
+  CPT(SliderTable) slider_table;                 // the mesh's SliderTable (may be null)
 };
 
 // Flattens a source GeomVertexData into the `case` sections, reading every fact
 // back from the reference objects (formats, tables), not from any recipe.
 static Exported export_vertex_data(const GeomVertexData *vd, Case &c) {
   Exported ex;
+  ex.slider_table = vd->get_slider_table();
   const GeomVertexFormat *fmt = vd->get_format();
   CPT(GeomVertexFormat) post = fmt->get_post_animated_format();
   int num_rows = vd->get_num_rows();
@@ -468,6 +473,33 @@ static void export_skeleton(Character *ch, const Exported &ex, Case &c) {
     }
     palette_joint.push_back(idx);
   }
+  // morph sliders driven by scalar channels: per slider of the SliderTable (the order the mesh's sliders have) its
+  // CharacterSlider's bound AnimChannelScalarTable (char/characterVertexSlider.cxx:56-59, chan/animChannelScalarTable.cxx)
+  std::vector<int32_t> s_has, s_len, s_off;
+  std::vector<float> s_default;
+  if (ex.slider_table != nullptr) {
+    for (size_t si = 0; si < ex.slider_table->get_num_sliders(); ++si) {
+      const VertexSlider *vs = ex.slider_table->get_slider(si);
+      int has = 0, len = 0, off = (int)tables.size();
+      float dflt = 0.0f;
+      if (vs->is_of_type(CharacterVertexSlider::get_class_type())) {
+        const CharacterSlider *cslider = ((const CharacterVertexSlider *)vs)->get_char_slider();
+        dflt = (float)cslider->get_default_value();
+        AnimChannelBase *bound = cslider->get_max_bound() > 0 ? cslider->get_bound(0) : nullptr;
+        if (bound != nullptr && bound->is_of_type(AnimChannelScalarTable::get_class_type())) {
+          CPTA_stdfloat t = DCAST(AnimChannelScalarTable, bound)->get_table();
+          has = 1;
+          len = (int)t.size();
+          for (size_t k = 0; k < t.size(); ++k) tables.push_back((float)t[k]);
+        }
+      }
+      s_has.push_back(has); s_len.push_back(len); s_off.push_back(off); s_default.push_back(dflt);
+    }
+  }
+  c["skel_slider_has_channel"] = make_blob(DT_I32, s_has, {(uint64_t)s_has.size()});
+  c["skel_slider_table_length"] = make_blob(DT_I32, s_len, {(uint64_t)s_len.size()});
+  c["skel_slider_table_offset"] = make_blob(DT_I32, s_off, {(uint64_t)s_off.size()});
+  c["skel_slider_default"] = make_blob(DT_F32, s_default, {(uint64_t)s_default.size()});
   LMatrix4f root = LCAST(float, bundle->get_root_xform());
   std::vector<float> rootv(root.get_data(), root.get_data() + 16);
   std::vector<int32_t> meta = {J, (int32_t)tables.size()};
@@ -492,10 +524,12 @@ struct Actor {
 };
 
 static bool load_actor(const char *model_path, const char *anim_path, Actor &a) {
+  const bool one_file = strcmp(model_path, anim_path) == 0;  // e.g. models/ripple.egg: model and animation in one egg
   PT(PandaNode) model = load_egg_file(model_path);
-  PT(PandaNode) anim = load_egg_file(anim_path);
-  if (!model || !anim) { fprintf(stderr, "egg load failed\n"); return false; }
-  a.root = new PandaNode("root"); a.root->add_child(model); a.root->add_child(anim);
+  PT(PandaNode) anim = one_file ? nullptr : load_egg_file(anim_path);
+  if (!model || (!one_file && !anim)) { fprintf(stderr, "egg load failed\n"); return false; }
+  a.root = new PandaNode("root"); a.root->add_child(model);
+  if (anim != nullptr) a.root->add_child(anim);
   auto_bind(a.root, a.ctrls, ~0);
   if (a.ctrls.get_num_anims() < 1) { fprintf(stderr, "no animation bound\n"); return false; }
   NodePath np(a.root);

@@ -888,6 +888,43 @@ int p3o_pose_controls(const p3o_skeleton *const *ctrl_skel, int K, const int *fr
   return 0;
 }
 
+/* AnimChannelScalarTable::get_value (chan/animChannelScalarTable.cxx:88-94) */
+static float slider_channel_value(const p3o_skeleton *sk, int s, int frame) {
+  int len = sk->slider_table_length[s];
+  return len == 0 ? 0.0f : sk->tables[sk->slider_table_offset[s] + frame % len];
+}
+
+int p3o_pose_sliders(const p3o_skeleton *const *ctrl_skel, int K, const int *frames, const int *next_frames, const float *fracs,
+                     const float *effects, int frame_blend, float *sliders_out) {
+  const p3o_skeleton *skel = ctrl_skel[0];
+  int S = skel->num_sliders, s, c;
+  for (s = 0; s < S; ++s) {
+    int n_eff = 0, only = -1;
+    for (c = 0; c < K; ++c)
+      if (effects[c] != 0.0f && ctrl_skel[c]->slider_has_channel[s]) { ++n_eff; only = c; }
+    if (n_eff == 0) {
+      sliders_out[s] = skel->slider_default[s];
+    } else if (n_eff == 1 && !frame_blend) {
+      sliders_out[s] = slider_channel_value(ctrl_skel[only], s, frames[only]);
+    } else {  /* movingPartScalar.cxx:63-104: the sum starts from zero, `_value /= net` is a true division */
+      float value = 0.0f, net = 0.0f;
+      for (c = 0; c < K; ++c) {
+        float effect = effects[c];
+        if (effect == 0.0f || !ctrl_skel[c]->slider_has_channel[s]) continue;
+        if (!frame_blend) {
+          value = value + slider_channel_value(ctrl_skel[c], s, frames[c]) * effect;
+        } else {
+          value = value + slider_channel_value(ctrl_skel[c], s, frames[c]) * (effect * (1.0f - fracs[c]));
+          value = value + slider_channel_value(ctrl_skel[c], s, next_frames[c]) * (effect * fracs[c]);
+        }
+        net = net + effect;
+      }
+      sliders_out[s] = value / net;
+    }
+  }
+  return 0;
+}
+
 int p3o_pose_blend(const p3o_skeleton *skel, int frame, int next_frame, float frac, int frame_blend, int blend_type,
                    float *skinning_out) {
   const float effect = 1.0f;

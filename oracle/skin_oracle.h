@@ -93,6 +93,12 @@ typedef struct p3o_skeleton {
   const float *default_value;     /* [J][16] */
   const float *initial_inverse;   /* [J][16] CharacterJoint::_initial_net_transform_inverse */
   const float *root_xform;        /* [16] PartBundle::get_root_xform() */
+  /* morph sliders driven by scalar channels (CharacterSlider -> AnimChannelScalarTable), SliderTable order */
+  int32_t num_sliders;
+  const int32_t *slider_has_channel;   /* [S] */
+  const int32_t *slider_table_length;  /* [S]; 0 = empty table: value 0 (animChannelScalarTable.cxx get_value) */
+  const int32_t *slider_table_offset;  /* [S] into tables */
+  const float *slider_default;         /* [S] MovingPartScalar::_default_value */
 } p3o_skeleton;
 /* skinning_out: [J][16] = CharacterJoint::_skinning_matrix of every joint at `frame`. */
 int p3o_pose(const p3o_skeleton *skel, int frame, float *skinning_out);
@@ -107,6 +113,12 @@ int p3o_pose_blend(const p3o_skeleton *skel, int frame, int next_frame, float fr
  * order = PartBundle's _blend map order. */
 int p3o_pose_controls(const p3o_skeleton *const *ctrl_skel, int K, const int *frames, const int *next_frames, const float *fracs,
                       const float *effects, int frame_blend, int blend_type, float *skinning_out);
+
+/* The slider values of the same controls (MovingPartScalar::get_blend_value, chan/movingPartScalar.cxx:43-105;
+ * CharacterSlider::update_internals): no control with a channel -> the default value; exactly one and no frame
+ * blending -> table[frame % size]; else sum(v * effect [* (1 - frac) / frac]) / net_effect.  sliders_out: [S]. */
+int p3o_pose_sliders(const p3o_skeleton *const *ctrl_skel, int K, const int *frames, const int *next_frames, const float *fracs,
+                     const float *effects, int frame_blend, float *sliders_out);
 
 /* Individual pieces, exported for unit tests against the reference's adjacent
  * tests (tests/linmath/test_lmatrix4.py, test_compose_matrix.py). */

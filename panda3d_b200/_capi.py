@@ -77,7 +77,9 @@ class _SkeletonDesc(C.Structure):
                 ("num_palette", C.c_int32), ("parent", C.c_void_p), ("has_channel", C.c_void_p),
                 ("table_length", C.c_void_p), ("table_offset", C.c_void_p), ("num_table_values", C.c_int32),
                 ("tables", C.c_void_p), ("default_value", C.c_void_p), ("initial_inverse", C.c_void_p),
-                ("root_xform", C.c_void_p), ("palette_joint", C.c_void_p)]
+                ("root_xform", C.c_void_p), ("palette_joint", C.c_void_p),
+                ("num_sliders", C.c_int32), ("slider_has_channel", C.c_void_p), ("slider_table_length", C.c_void_p),
+                ("slider_table_offset", C.c_void_p), ("slider_default", C.c_void_p)]
 
 
 class _GroupBuffers(C.Structure):
@@ -349,10 +351,15 @@ class Skeleton:
             skel.table_offset.astype(np.int32), skel.tables.astype(np.float32) if skel.tables.size else np.zeros(1, np.float32),
             skel.default_value.astype(np.float32), skel.initial_inverse.astype(np.float32),
             skel.root_xform.astype(np.float32), skel.palette_joint.astype(np.int32))]
-        self._keep = a
+        S = getattr(skel, "num_sliders", 0)
+        sl = [np.ascontiguousarray(x) for x in (
+            skel.slider_has_channel.astype(np.int32), skel.slider_table_length.astype(np.int32),
+            skel.slider_table_offset.astype(np.int32), skel.slider_default.astype(np.float32))] if S else []
+        self._keep = a + sl
         d = _SkeletonDesc(C.sizeof(_SkeletonDesc), skel.num_joints, skel.coordinate_system, len(skel.palette_joint),
                           a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data, int(skel.tables.size),
-                          a[4].ctypes.data, a[5].ctypes.data, a[6].ctypes.data, a[7].ctypes.data, a[8].ctypes.data)
+                          a[4].ctypes.data, a[5].ctypes.data, a[6].ctypes.data, a[7].ctypes.data, a[8].ctypes.data,
+                          S, *([x.ctypes.data for x in sl] if S else [None] * 4))
         self.handle = C.c_void_p()
         _check(lib().p3cs_skeleton_create(ctx.handle, C.byref(d), C.byref(self.handle)))
 
@@ -365,8 +372,13 @@ class Skeleton:
 
         class _AnimDesc(C.Structure):
             _fields_ = [("struct_size", C.c_uint32), ("num_table_values", C.c_int32), ("has_channel", C.c_void_p),
-                        ("table_length", C.c_void_p), ("table_offset", C.c_void_p), ("tables", C.c_void_p)]
-        d = _AnimDesc(C.sizeof(_AnimDesc), int(skel.tables.size), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data)
+                        ("table_length", C.c_void_p), ("table_offset", C.c_void_p), ("tables", C.c_void_p),
+                        ("slider_has_channel", C.c_void_p), ("slider_table_length", C.c_void_p), ("slider_table_offset", C.c_void_p)]
+        S = getattr(skel, "num_sliders", 0)
+        sl = [np.ascontiguousarray(x) for x in (skel.slider_has_channel.astype(np.int32), skel.slider_table_length.astype(np.int32),
+                                                skel.slider_table_offset.astype(np.int32))] if S else []
+        d = _AnimDesc(C.sizeof(_AnimDesc), int(skel.tables.size), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data,
+                      *([x.ctypes.data for x in sl] if S else [None] * 3))
         idx = C.c_int32(-1)
         L = lib()
         L.p3cs_skeleton_add_animation.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]

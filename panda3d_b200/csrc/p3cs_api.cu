@@ -705,6 +705,13 @@ extern "C" int p3cs_skeleton_create(p3cs_context ctx, const p3cs_skeleton_desc *
   }
   for (int t = 0; t < d->num_palette; ++t)
     if (d->palette_joint[t] < 0 || d->palette_joint[t] >= J) return p3cs_fail(P3CS_ERR_INVALID, "palette slot %d has no joint", t);
+  if (d->num_sliders < 0 || (d->num_sliders > 0 && (d->slider_has_channel == nullptr || d->slider_table_length == nullptr ||
+                                                    d->slider_table_offset == nullptr || d->slider_default == nullptr)))
+    return p3cs_fail(P3CS_ERR_INVALID, "p3cs_skeleton_create: slider arrays missing");
+  for (int sl = 0; sl < d->num_sliders; ++sl) {
+    const int len = d->slider_table_length[sl], off = d->slider_table_offset[sl];
+    if (len < 0 || off < 0 || off + len > d->num_table_values) return p3cs_fail(P3CS_ERR_INVALID, "slider %d: table out of range", sl);
+  }
   DeviceGuard g(ctx->device);
   p3cs_skeleton sk = new (std::nothrow) p3cs_skeleton_s;
   if (sk == nullptr) return p3cs_fail(P3CS_ERR_NOMEM, "out of host memory");
@@ -738,6 +745,13 @@ extern "C" int p3cs_skeleton_create(p3cs_context ctx, const p3cs_skeleton_desc *
   if ((rc = upload_skel<float>(sk, d->initial_inverse, (size_t)J * 16, &s.initial_inverse)) != P3CS_OK) return bail(rc);
   if ((rc = upload_skel<float>(sk, d->root_xform, 16, &s.root_xform)) != P3CS_OK) return bail(rc);
   if ((rc = upload_skel<int>(sk, d->palette_joint, d->num_palette, &s.palette_joint)) != P3CS_OK) return bail(rc);
+  s.num_sliders = d->num_sliders;
+  if (d->num_sliders > 0) {
+    if ((rc = upload_skel<float>(sk, d->slider_default, d->num_sliders, &s.slider_default)) != P3CS_OK) return bail(rc);
+    if ((rc = upload_skel<int>(sk, d->slider_has_channel, d->num_sliders, &s.anim[0].slider_has_channel)) != P3CS_OK) return bail(rc);
+    if ((rc = upload_skel<int>(sk, d->slider_table_length, d->num_sliders, &s.anim[0].slider_table_length)) != P3CS_OK) return bail(rc);
+    if ((rc = upload_skel<int>(sk, d->slider_table_offset, d->num_sliders, &s.anim[0].slider_table_offset)) != P3CS_OK) return bail(rc);
+  }
   cudaError_t err = cudaStreamSynchronize(ctx->stream);
   if (err != cudaSuccess) return bail(p3cs_fail(P3CS_ERR_CUDA, "skeleton upload failed: %s", cudaGetErrorString(err)));
   *out = sk;
@@ -770,6 +784,17 @@ extern "C" int p3cs_skeleton_add_animation(p3cs_skeleton sk, const p3cs_animatio
   if ((rc = upload_skel<int>(sk, d->table_length, (size_t)J * 12, &an.table_length)) != P3CS_OK) return rc;
   if ((rc = upload_skel<int>(sk, d->table_offset, (size_t)J * 12, &an.table_offset)) != P3CS_OK) return rc;
   if ((rc = upload_skel<float>(sk, d->tables, d->num_table_values, &an.tables)) != P3CS_OK) return rc;
+  if (s.num_sliders > 0) {
+    if (d->slider_has_channel == nullptr || d->slider_table_length == nullptr || d->slider_table_offset == nullptr)
+      return p3cs_fail(P3CS_ERR_INVALID, "p3cs_skeleton_add_animation: the skeleton has sliders, the animation's slider arrays are missing");
+    for (int sl = 0; sl < s.num_sliders; ++sl) {
+      const int len = d->slider_table_length[sl], off = d->slider_table_offset[sl];
+      if (len < 0 || off < 0 || off + len > d->num_table_values) return p3cs_fail(P3CS_ERR_INVALID, "slider %d: table out of range", sl);
+    }
+    if ((rc = upload_skel<int>(sk, d->slider_has_channel, s.num_sliders, &an.slider_has_channel)) != P3CS_OK) return rc;
+    if ((rc = upload_skel<int>(sk, d->slider_table_length, s.num_sliders, &an.slider_table_length)) != P3CS_OK) return rc;
+    if ((rc = upload_skel<int>(sk, d->slider_table_offset, s.num_sliders, &an.slider_table_offset)) != P3CS_OK) return rc;
+  }
   CUDA_TRY(cudaStreamSynchronize(sk->ctx->stream));
   *out_index = s.num_animations;
   s.anim[s.num_animations++] = an;
@@ -784,6 +809,8 @@ static int pose_common(p3cs_group grp, p3cs_skeleton sk, int first, int count, c
   if (sk == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "%s: skeleton is NULL", what);
   if (sk->num_palette != grp->mesh->dev.num_transforms)
     return p3cs_fail(P3CS_ERR_INVALID, "skeleton feeds %d palette slots, the mesh has %d transforms", sk->num_palette, grp->mesh->dev.num_transforms);
+  if (sk->dev.num_sliders > 0 && sk->dev.num_sliders != grp->mesh->dev.num_sliders)
+    return p3cs_fail(P3CS_ERR_INVALID, "skeleton drives %d sliders, the mesh has %d", sk->dev.num_sliders, grp->mesh->dev.num_sliders);
   if (count == 0) return P3CS_OK;
   DeviceGuard g(grp->mesh->ctx->device);
   cudaStream_t s = grp->mesh->ctx->stream;
@@ -799,7 +826,8 @@ static int pose_common(p3cs_group grp, p3cs_skeleton sk, int first, int count, c
   }
   CUDA_TRY(cudaMemcpyAsync(grp->frames_dev, states != nullptr ? static_cast<const void *>(states) : static_cast<const void *>(host_frames),
                            words * 4, cudaMemcpyHostToDevice, s));
-  launch_pose(sk->dev, const_cast<float *>(grp->dev.palettes), sk->num_palette, states != nullptr ? nullptr : grp->frames_dev,
+  launch_pose(sk->dev, const_cast<float *>(grp->dev.palettes), sk->num_palette, const_cast<float *>(grp->dev.sliders),
+              states != nullptr ? nullptr : grp->frames_dev,
               states != nullptr ? reinterpret_cast<const ControlState *>(grp->frames_dev) : nullptr, num_controls, frame_blend, blend_type,
               first, count, s);
   CUDA_TRY(cudaGetLastError());

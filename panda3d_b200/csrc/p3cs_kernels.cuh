@@ -101,6 +101,9 @@ struct AnimationDev {
   const int *table_length;   // [J][12]
   const int *table_offset;   // [J][12]
   const float *tables;
+  const int *slider_has_channel;   // [S] scalar channels of the morph sliders (same `tables`)
+  const int *slider_table_length;  // [S]
+  const int *slider_table_offset;  // [S]
 };
 
 struct SkeletonDev {
@@ -116,6 +119,8 @@ struct SkeletonDev {
   const float *initial_inverse;
   const float *root_xform;    // [16]
   const int *palette_joint;   // [T]
+  int num_sliders;            // morph sliders driven by scalar channels (0: posing does not touch slider values)
+  const float *slider_default;
 };
 
 // One AnimControl of one instance: which animation it plays, AnimControl::get_frame / get_next_frame / get_frac, and
@@ -126,8 +131,9 @@ struct ControlState {
 };
 
 // frames_dev != nullptr: one control of animation 0 per instance, no blending.  Else states_dev[count][num_controls].
-void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, const int *frames_dev, const ControlState *states_dev,
-                 int num_controls, int frame_blend, int blend_type, int first_instance, int count, cudaStream_t stream);
+void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, float *sliders, const int *frames_dev,
+                 const ControlState *states_dev, int num_controls, int frame_blend, int blend_type, int first_instance, int count,
+                 cudaStream_t stream);
 
 void launch_blend(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);
 void launch_skin(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);

@@ -59,8 +59,14 @@ __device__ __forceinline__ void channel_value(const AnimationDev &an, int cs, in
 // (MovingPartBase::determine_effective_channels, movingPartBase.cxx:303-333; MovingPartMatrix::get_blend_value,
 // movingPartMatrix.cxx:52-198): no control with a channel -> the default value; exactly one and no frame blending ->
 // its value; else the blend, blend_type 0 = BT_linear (:82-122), 1 = BT_normalized_linear (:125-198, the PRC default).
+// AnimChannelScalarTable::get_value (chan/animChannelScalarTable.cxx:88-94)
+__device__ __forceinline__ float slider_channel_value(const AnimationDev &an, int s, int frame) {
+  const int len = __ldg(an.slider_table_length + s);
+  return len == 0 ? 0.0f : __ldg(an.tables + __ldg(an.slider_table_offset + s) + frame % len);
+}
+
 template <bool BLEND>
-__global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *palettes, int num_transforms, const int *frames,
+__global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *palettes, int num_transforms, float *sliders, const int *frames,
                                                     const ControlState *states, int num_controls, int frame_blend, int blend_type,
                                                     int first_instance) {
   extern __shared__ float smem_pose[];  // [J][16] local values, then [J][16] net transforms of this instance
@@ -69,6 +75,43 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
   float *local = smem_pose;
   float *net = smem_pose + (size_t)J * 16;
   const int cs = skel.coordinate_system;
+
+  // morph sliders: CharacterSlider's value from its scalar channel(s) (MovingPartScalar::get_blend_value,
+  // chan/movingPartScalar.cxx:43-105): same selection rule as the joints; the blend is a plain weighted sum from
+  // zero followed by a true division by the net effect
+  for (int sl = threadIdx.x; sl < skel.num_sliders; sl += blockDim.x) {
+    float value = __ldg(skel.slider_default + sl);
+    if (!BLEND) {
+      if (__ldg(skel.anim[0].slider_has_channel + sl)) value = slider_channel_value(skel.anim[0], sl, __ldg(frames + blockIdx.x));
+    } else {
+      const ControlState *st = states + (size_t)blockIdx.x * num_controls;
+      int n_eff = 0, only = -1;
+      for (int c = 0; c < num_controls; ++c)
+        if (st[c].effect != 0.0f && __ldg(skel.anim[st[c].anim].slider_has_channel + sl)) {
+          ++n_eff;
+          only = c;
+        }
+      if (n_eff == 1 && !frame_blend) {
+        value = slider_channel_value(skel.anim[st[only].anim], sl, st[only].frame);
+      } else if (n_eff > 0) {
+        float sum = 0.0f, net_effect = 0.0f;
+        for (int c = 0; c < num_controls; ++c) {
+          const ControlState cst = st[c];
+          const AnimationDev &an = skel.anim[cst.anim];
+          if (cst.effect == 0.0f || !__ldg(an.slider_has_channel + sl)) continue;
+          if (!frame_blend) {
+            sum = sum + slider_channel_value(an, sl, cst.frame) * cst.effect;
+          } else {
+            sum = sum + slider_channel_value(an, sl, cst.frame) * (cst.effect * (1.0f - cst.frac));
+            sum = sum + slider_channel_value(an, sl, cst.next_frame) * (cst.effect * cst.frac);
+          }
+          net_effect = net_effect + cst.effect;
+        }
+        value = sum / net_effect;
+      }
+    }
+    sliders[(size_t)inst * skel.num_sliders + sl] = value;
+  }
 
   // phase 1, all joints in parallel: the joint's own value
   for (int j = threadIdx.x; j < J; j += blockDim.x) {
@@ -193,19 +236,20 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
   }
 }
 
-void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, const int *frames_dev, const ControlState *states_dev,
-                 int num_controls, int frame_blend, int blend_type, int first_instance, int count, cudaStream_t stream) {
+void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, float *sliders, const int *frames_dev,
+                 const ControlState *states_dev, int num_controls, int frame_blend, int blend_type, int first_instance, int count,
+                 cudaStream_t stream) {
   if (count == 0 || skel.num_joints == 0) return;
   const size_t smem = (size_t)skel.num_joints * 128;
   int threads = ((skel.num_joints + 31) / 32) * 32;
   if (threads > 256) threads = 256;
   if (states_dev != nullptr) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(pose_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pose_kernel<true><<<count, threads, smem, stream>>>(skel, palettes, num_transforms, nullptr, states_dev, num_controls, frame_blend,
+    pose_kernel<true><<<count, threads, smem, stream>>>(skel, palettes, num_transforms, sliders, nullptr, states_dev, num_controls, frame_blend,
                                                         blend_type, first_instance);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(pose_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pose_kernel<false><<<count, threads, smem, stream>>>(skel, palettes, num_transforms, frames_dev, nullptr, 0, 0, blend_type,
+    pose_kernel<false><<<count, threads, smem, stream>>>(skel, palettes, num_transforms, sliders, frames_dev, nullptr, 0, 0, blend_type,
                                                          first_instance);
   }
 }

@@ -157,6 +157,15 @@ class FlatSkeleton:
     root_xform: np.ndarray        # float32 [16]
     palette_joint: np.ndarray     # int32 [T]: joint feeding each palette slot
     coordinate_system: int = CS_zup_right
+    # morph sliders driven by scalar channels (CharacterSlider / AnimChannelScalarTable), in SliderTable order
+    slider_has_channel: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    slider_table_length: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))   # 0: empty table (value 0)
+    slider_table_offset: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))   # into `tables`
+    slider_default: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))
+
+    @property
+    def num_sliders(self) -> int:
+        return int(len(self.slider_has_channel))
 
     @property
     def num_joints(self) -> int:
@@ -172,4 +181,8 @@ def skeleton_from_case(case: Dict[str, np.ndarray]) -> FlatSkeleton:
         initial_inverse=case["skel_initial_inverse"].astype(np.float32).reshape(-1, 16),
         root_xform=case["skel_root_xform"].astype(np.float32).reshape(16),
         palette_joint=case["skel_palette_joint"].astype(np.int32),
-        coordinate_system=int(case["meta"][6]) or CS_zup_right)
+        coordinate_system=int(case["meta"][6]) or CS_zup_right,
+        slider_has_channel=case.get("skel_slider_has_channel", np.zeros(0, np.int32)).astype(np.int32),
+        slider_table_length=case.get("skel_slider_table_length", np.zeros(0, np.int32)).astype(np.int32),
+        slider_table_offset=case.get("skel_slider_table_offset", np.zeros(0, np.int32)).astype(np.int32),
+        slider_default=case.get("skel_slider_default", np.zeros(0, np.float32)).astype(np.float32))

@@ -94,6 +94,13 @@ def main():
     subprocess.run([HARNESS, "egg", model, anim, out, "0", "10", "37", "59"], check=True, timeout=120,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     print("wrote", out, os.path.getsize(out))
+    # models/ripple.egg: the reference's own morph-animated character (7 <S$Anim> sliders driving <Dxyz> / <DNormal>
+    # deltas, model and animation in one egg) -- the morph path on loader-made formats
+    ripple = os.path.join(REF, "models", "ripple.egg")
+    out = os.path.join(HERE, "ripple.p3cs")
+    subprocess.run([HARNESS, "egg", ripple, ripple, out, "0", "3", "7", "20", "44"], check=True, timeout=120,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    print("wrote", out, os.path.getsize(out))
     # the same Actor with PartBundle::set_frame_blend_flag(true), posed between frames (joint hierarchy fixture, f1)
     os.makedirs(os.path.join(HERE, "skeleton"), exist_ok=True)
     for suffix, env in (("", {}), ("_linear", {"P3CS_BLEND_TYPE": "linear"})):   # anim-blend-type default, then BT_linear
@@ -110,6 +117,16 @@ def main():
             subprocess.run([HARNESS, "eggmulti", model, anim, out] + samples, check=True, timeout=120,
                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env={**os.environ, **env})
             print("wrote", out, os.path.getsize(out))
+    # ripple.egg between frames and with two controls: the morph sliders' scalar channels (MovingPartScalar)
+    out = os.path.join(HERE, "skeleton", "ripple_frame_blend.p3cs")
+    subprocess.run([HARNESS, "egg", ripple, ripple, out, "0.5", "3.25", "20.0", "43.75"], check=True, timeout=120,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    print("wrote", out, os.path.getsize(out))
+    for samples, tag in ((["3:0.7,20:0.3", "10:1.0,40:0.0", "17:0.2,18:1.3"], "hold"), (["3.5:0.7,20.25:0.3", "5.5:0.25,33.25:0.75"], "frame_blend")):
+        out = os.path.join(HERE, "skeleton", f"ripple_two_controls_{tag}.p3cs")
+        subprocess.run([HARNESS, "eggmulti", ripple, ripple, out] + samples, check=True, timeout=120,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        print("wrote", out, os.path.getsize(out))
 
 
 if __name__ == "__main__":

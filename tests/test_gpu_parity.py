@@ -859,3 +859,46 @@ def test_joint_hierarchy_with_two_blended_controls(gpu_ctx, fixture):
         grp.close()
         dskel.close()
         dmesh.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture", ["ripple", "skeleton/ripple_frame_blend", "skeleton/ripple_two_controls_hold",
+                                     "skeleton/ripple_two_controls_frame_blend"])
+def test_slider_channels_on_gpu_ripple(gpu_ctx, fixture):
+    """models/ripple.egg (7 morph sliders driven by <S$Anim> scalar channels): the pose calls also evaluate
+    CharacterSlider's values on the device -- bit for bit the reference's (table look-ups, products and one
+    division, no libm) -- and pose -> animate reproduces the reference's animated vertices."""
+    from conftest import GOLDEN_DIR
+    from panda3d_b200.flat import skeleton_from_case
+    from test_oracle_golden import _control_arrays
+    case = load_case(os.path.join(GOLDEN_DIR, fixture + ".p3cs"))
+    mesh, skel = mesh_from_case(case), skeleton_from_case(case)
+    frames, nxt, fracs, effects, fb = _control_arrays(case)
+    n, K = frames.shape
+    bt = int(case["anim_blend_type"][0]) if "anim_blend_type" in case else 1
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    dskel = _capi.Skeleton(gpu_ctx, skel)
+    grp = _capi.Group(dmesh, n)
+    try:
+        if K == 1 and not fb:
+            grp.pose(dskel, frames[:, 0])
+        elif K == 1:
+            grp.pose_blend(dskel, frames[:, 0], nxt[:, 0], fracs[:, 0], bt)
+        else:
+            states = np.zeros((n, K, 5))
+            states[:, :, 1], states[:, :, 2], states[:, :, 3], states[:, :, 4] = frames, nxt, fracs, effects
+            states[:, 1, 0] = dskel.add_animation(skel)
+            grp.pose_controls(dskel, states, fb, bt)
+        gpu_ctx.sync()
+        got = gpu_ctx.device_read(_capi.lib().p3cs_group_sliders_device(grp.handle), n * 7 * 4).view(np.float32).reshape(n, 7)
+        assert np.array_equal(got.view(np.uint32), case["sliders"].view(np.uint32)), "slider values differ from CharacterSlider's"
+        pal = grp.read_palettes()
+        assert (np.abs(pal - case["palette"]) / np.abs(case["palette"]).max()).max() <= REL_TOL
+        grp.animate()
+        out = grp.read_output(0)
+        for i in range(n):
+            compare_outputs(mesh, [out[i]], [case["expect0"][i]], f"{fixture} sample {i}")
+    finally:
+        grp.close()
+        dskel.close()
+        dmesh.close()

@@ -121,3 +121,38 @@ def test_oracle_pose_with_two_controls_matches_reference(fixture):
         skin = oracle.pose_controls([skel, skel], case["ctrl_frames"][i], case["ctrl_next_frames"][i], case["ctrl_fracs"][i],
                                     case["ctrl_effects"][i], fb, bt)
         assert np.array_equal(skin[skel.palette_joint].view(np.uint32), case["palette"][i].view(np.uint32)), f"sample {i}"
+
+
+def _control_arrays(case):
+    """(frames, next_frames, fracs, effects, frame_blend) per sample of a skeleton fixture, one or two controls."""
+    if "ctrl_frames" in case:
+        return case["ctrl_frames"], case["ctrl_next_frames"], case["ctrl_fracs"], case["ctrl_effects"], bool(case["anim_frame_blend"][0])
+    f = case["anim_frames"].reshape(-1, 1)
+    if "anim_next_frames" in case:
+        return f, case["anim_next_frames"].reshape(-1, 1), case["anim_fracs"].reshape(-1, 1), np.ones_like(f, np.float32), True
+    return f, f, np.zeros_like(f, np.float32), np.ones_like(f, np.float32), False
+
+
+@pytest.mark.parametrize("fixture", ["ripple", "skeleton/ripple_frame_blend", "skeleton/ripple_two_controls_hold",
+                                     "skeleton/ripple_two_controls_frame_blend"])
+def test_oracle_slider_channels_match_reference(fixture):
+    """models/ripple.egg, the reference's morph-animated character: the slider values CharacterSlider takes from its
+    scalar channels (MovingPartScalar::get_blend_value, chan/movingPartScalar.cxx:43-105) -- plain, between frames
+    and with two blended controls -- bit for bit, then the animated vertices that follow from palette + sliders."""
+    import os
+    from conftest import GOLDEN_DIR
+    from panda3d_b200.flat import mesh_from_case, skeleton_from_case
+    case = load_case(os.path.join(GOLDEN_DIR, fixture + ".p3cs"))
+    skel, mesh = skeleton_from_case(case), mesh_from_case(case)
+    assert skel.num_sliders == mesh.num_sliders == 7
+    frames, nxt, fracs, effects, fb = _control_arrays(case)
+    K = frames.shape[1]
+    bt = int(case["anim_blend_type"][0]) if "anim_blend_type" in case else 1
+    om = oracle.OracleMesh(mesh)
+    for i in range(frames.shape[0]):
+        sl = oracle.pose_sliders([skel] * K, frames[i], nxt[i], fracs[i], effects[i], fb)
+        assert np.array_equal(sl.view(np.uint32), case["sliders"][i].view(np.uint32)), f"sample {i}: {sl} vs {case['sliders'][i]}"
+        pal = oracle.pose_controls([skel] * K, frames[i], nxt[i], fracs[i], effects[i], fb, bt)[skel.palette_joint]
+        assert np.array_equal(pal.view(np.uint32), case["palette"][i].view(np.uint32))
+        outs, _, _ = om.animate(pal, sl)
+        assert np.array_equal(outs[0].reshape(-1), np.asarray(case["expect0"][i]).reshape(-1))
