@@ -569,6 +569,9 @@ static int cmd_egg(int argc, char **argv) {
   if (bt != nullptr && strcmp(bt, "linear") == 0) {
     ch->get_bundle(0)->set_blend_type(PartBundle::BT_linear);
     blend_type = 0;
+  } else if (bt != nullptr && strcmp(bt, "componentwise") == 0) {
+    ch->get_bundle(0)->set_blend_type(PartBundle::BT_componentwise);
+    blend_type = 2;
   }
   AnimControl *control = ctrls.get_anim(0);
   for (int i = 5; i < argc; ++i) {
@@ -613,6 +616,7 @@ static int cmd_eggmulti(int argc, char **argv) {
   const char *bt = getenv("P3CS_BLEND_TYPE");
   int blend_type = 1;
   if (bt != nullptr && strcmp(bt, "linear") == 0) { bundle->set_blend_type(PartBundle::BT_linear); blend_type = 0; }
+  else if (bt != nullptr && strcmp(bt, "componentwise") == 0) { bundle->set_blend_type(PartBundle::BT_componentwise); blend_type = 2; }
   Case out;
   Exported ex = export_vertex_data(actor.vd, out);
   export_skeleton(actor.ch, ex, out);

@@ -805,7 +805,7 @@ static void channel_value_no_scale_shear(const p3o_skeleton *skel, int j, int fr
   M4(value, 3, 3) = 1.0f;
 }
 
-/* blend_type: 0 BT_linear, 1 BT_normalized_linear (PartBundle::BlendType, chan/partBundle.h; the default
+/* blend_type: 0 BT_linear, 1 BT_normalized_linear, 2 BT_componentwise (PartBundle::BlendType, chan/partBundle.h; the default
  * comes from the PRC variable anim-blend-type = normalized-linear, chan/partBundle.cxx:41-42).
  *
  * K AnimControls in the order PartBundle iterates its _blend map; ctrl_skel[k] carries the channel tables of
@@ -832,6 +832,7 @@ int p3o_pose_controls(const p3o_skeleton *const *ctrl_skel, int K, const int *fr
       /* sums start from zero, in map order; the division by net_effect multiplies by its reciprocal
        * (LMatrix4 / LVecBase3 operator /=, lmatrix4_src.I:1094-1098, lvecBase3_src.I:709-718) */
       float nv[16], scale[3] = {0.0f, 0.0f, 0.0f}, shear[3] = {0.0f, 0.0f, 0.0f}, net_effect = 0.0f, recip;
+      float comps[12] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
       for (k = 0; k < 16; ++k) nv[k] = 0.0f;
       for (c = 0; c < K; ++c) {
         const p3o_skeleton *cs = ctrl_skel[c];
@@ -841,6 +842,10 @@ int p3o_pose_controls(const p3o_skeleton *const *ctrl_skel, int K, const int *fr
         for (pass = 0; pass < passes; ++pass) {
           int fr = pass == 0 ? frames[c] : next_frames[c];
           float e = !frame_blend ? effect : pass == 0 ? effect * (1.0f - fracs[c]) : effect * fracs[c];
+          if (blend_type == 2) {  /* BT_componentwise, :200-271: scale, shear, hpr and pos blend on their own */
+            for (k = 0; k < 12; ++k) comps[k] = comps[k] + channel_component(cs, j, k, fr) * e;
+            continue;
+          }
           if (blend_type == 0) channel_value(cs, j, fr, v);   /* BT_linear, :82-122 */
           else channel_value_no_scale_shear(cs, j, fr, v);     /* BT_normalized_linear, :125-198 */
           for (k = 0; k < 16; ++k) nv[k] = nv[k] + v[k] * e;
@@ -854,7 +859,20 @@ int p3o_pose_controls(const p3o_skeleton *const *ctrl_skel, int K, const int *fr
       }
       recip = 1.0f / net_effect;
       for (k = 0; k < 16; ++k) nv[k] = nv[k] * recip;
-      if (blend_type == 0) {
+      if (blend_type == 2) {
+        float out3[9];
+        int r, cc;
+        for (k = 0; k < 12; ++k) comps[k] = comps[k] * recip;
+        p3o_compose3(out3, comps + 0, comps + 3, comps + 6, skel->coordinate_system);
+        for (r = 0; r < 3; ++r) {
+          for (cc = 0; cc < 3; ++cc) M4(value, r, cc) = M3(out3, r, cc);
+          M4(value, r, 3) = 0.0f;
+        }
+        M4(value, 3, 0) = comps[9];
+        M4(value, 3, 1) = comps[10];
+        M4(value, 3, 2) = comps[11];
+        M4(value, 3, 3) = 1.0f;
+      } else if (blend_type == 0) {
         memcpy(value, nv, sizeof(value));
       } else {
         /* decompose_matrix(net_value, false_scale, false_shear, hpr, translate); compose_matrix(_value, scale,

@@ -58,7 +58,8 @@ __device__ __forceinline__ void channel_value(const AnimationDev &an, int cs, in
 // the order of the bundle's blend map, and / or the frame-blend flag; per joint
 // (MovingPartBase::determine_effective_channels, movingPartBase.cxx:303-333; MovingPartMatrix::get_blend_value,
 // movingPartMatrix.cxx:52-198): no control with a channel -> the default value; exactly one and no frame blending ->
-// its value; else the blend, blend_type 0 = BT_linear (:82-122), 1 = BT_normalized_linear (:125-198, the PRC default).
+// its value; else the blend, blend_type 0 = BT_linear (:82-122), 1 = BT_normalized_linear (:125-198, the PRC default),
+// 2 = BT_componentwise (:200-271).
 // AnimChannelScalarTable::get_value (chan/animChannelScalarTable.cxx:88-94)
 __device__ __forceinline__ float slider_channel_value(const AnimationDev &an, int s, int frame) {
   const int len = __ldg(an.slider_table_length + s);
@@ -137,8 +138,11 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
         // sums start from zero, in map order; the division by net_effect multiplies by its reciprocal
         // (LMatrix4 / LVecBase3 operator /=)
         float nv[16], scale[3] = {0.0f, 0.0f, 0.0f}, shear[3] = {0.0f, 0.0f, 0.0f}, net_effect = 0.0f;
+        float comps[12];  // BT_componentwise (:200-271): scale, shear, hpr and pos blend on their own
 #pragma unroll
         for (int k = 0; k < 16; ++k) nv[k] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) comps[k] = 0.0f;
         for (int c = 0; c < num_controls; ++c) {
           const ControlState cst = st[c];
           const AnimationDev &an = skel.anim[cst.anim];
@@ -146,6 +150,11 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
           for (int pass = 0; pass < (frame_blend ? 2 : 1); ++pass) {
             const int fr = pass == 0 ? cst.frame : cst.next_frame;
             const float e = !frame_blend ? cst.effect : pass == 0 ? cst.effect * (1.0f - cst.frac) : cst.effect * cst.frac;
+            if (blend_type == 2) {
+#pragma unroll
+              for (int k = 0; k < 12; ++k) comps[k] = comps[k] + channel_component(an, j, k, fr) * e;
+              continue;
+            }
             float v[16];
             channel_value(an, cs, j, fr, blend_type != 0, v);
 #pragma unroll
@@ -163,7 +172,22 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
         const float recip = 1.0f / net_effect;
 #pragma unroll
         for (int k = 0; k < 16; ++k) value[k] = nv[k] * recip;
-        if (blend_type != 0) {
+        if (blend_type == 2) {
+#pragma unroll
+          for (int k = 0; k < 12; ++k) comps[k] = comps[k] * recip;
+          Mat3 out3;
+          compose3(out3, comps + 0, comps + 3, comps + 6, cs);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) value[r * 4 + c] = out3.m[r][c];
+            value[r * 4 + 3] = 0.0f;
+          }
+          value[12] = comps[9];
+          value[13] = comps[10];
+          value[14] = comps[11];
+          value[15] = 1.0f;
+        } else if (blend_type != 0) {
           // decompose_matrix(net_value, false_scale, false_shear, hpr, translate), then
           // compose_matrix(_value, scale, shear, hpr, translate)
           float false_scale[3], false_shear[3], hpr[3];

@@ -112,7 +112,7 @@ def main():
     samples_hold = ["3:0.7,20:0.3", "10:1.0,40:0.0", "0:0.5,59:0.5", "17:0.2,18:1.3"]
     samples_blend = ["3.5:0.7,20.25:0.3", "10.75:1.0,40:0.0", "5.5:0.25,33.25:0.75"]
     for samples, tag in ((samples_hold, "hold"), (samples_blend, "frame_blend")):
-        for suffix, env in (("", {}), ("_linear", {"P3CS_BLEND_TYPE": "linear"})):
+        for suffix, env in (("", {}), ("_linear", {"P3CS_BLEND_TYPE": "linear"}), ("_componentwise", {"P3CS_BLEND_TYPE": "componentwise"})):
             out = os.path.join(HERE, "skeleton", f"panda_walk4_two_controls_{tag}{suffix}.p3cs")
             subprocess.run([HARNESS, "eggmulti", model, anim, out] + samples, check=True, timeout=120,
                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env={**os.environ, **env})

@@ -820,7 +820,9 @@ def test_plain_c_host_animates_through_the_plugin_table(tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("fixture", ["panda_walk4_two_controls_hold", "panda_walk4_two_controls_hold_linear",
-                                     "panda_walk4_two_controls_frame_blend", "panda_walk4_two_controls_frame_blend_linear"])
+                                     "panda_walk4_two_controls_hold_componentwise",
+                                     "panda_walk4_two_controls_frame_blend", "panda_walk4_two_controls_frame_blend_linear",
+                                     "panda_walk4_two_controls_frame_blend_componentwise"])
 def test_joint_hierarchy_with_two_blended_controls(gpu_ctx, fixture):
     """f1 with several AnimControls (PartBundle::set_anim_blend_flag / set_control_effect): p3cs_group_pose_controls
     against the reference's Character posed with two controls of different frames and effects -- the second control

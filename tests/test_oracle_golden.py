@@ -101,8 +101,9 @@ def test_oracle_pose_with_frame_blending_matches_reference(fixture):
         assert np.array_equal(outs[0].reshape(-1), np.asarray(case["expect0"][fi]).reshape(-1))
 
 
-MULTI = ["panda_walk4_two_controls_hold", "panda_walk4_two_controls_hold_linear",
-         "panda_walk4_two_controls_frame_blend", "panda_walk4_two_controls_frame_blend_linear"]
+MULTI = ["panda_walk4_two_controls_hold", "panda_walk4_two_controls_hold_linear", "panda_walk4_two_controls_hold_componentwise",
+         "panda_walk4_two_controls_frame_blend", "panda_walk4_two_controls_frame_blend_linear",
+         "panda_walk4_two_controls_frame_blend_componentwise"]
 
 
 @pytest.mark.parametrize("fixture", MULTI)
