@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
-from typing import List, Optional, Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 

@@ -7,7 +7,7 @@ exchange is the gather of finished vertex arrays to the rendering GPU, done with
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence
 
 import numpy as np
 

@@ -5,7 +5,7 @@ plus the flattening that hands a GeomVertexData to the C-ABI."""
 import numpy as np
 import pytest
 
-from panda3d_b200 import flat as F, synth
+from panda3d_b200 import synth
 from panda3d_b200.gobj import (GeomEnums, GeomVertexAnimationSpec, GeomVertexArrayFormat, GeomVertexData,
                                GeomVertexFormat, InternalName, SliderTable, SparseArray, TransformBlend,
                                TransformBlendTable, UpdateSeq, UserVertexSlider, UserVertexTransform, load_prc_file_data)

@@ -1,6 +1,6 @@
-import sys, os
+import sys
 sys.path.insert(0,'/root/repo')
-import numpy as np, torch
+import torch
 from panda3d_b200 import _capi, synth
 from panda3d_b200.casefile import load_case
 from panda3d_b200.flat import mesh_from_case

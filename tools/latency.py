@@ -2,7 +2,6 @@
 """End-to-end latency of ONE p3cs_animate_vertices call (host buffers in, host buffers out) for the
 single-character configurations, beside the oracle port on one core."""
 import json, os, sys, time
-import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from panda3d_b200 import _capi, synth
 from panda3d_b200.casefile import load_case
