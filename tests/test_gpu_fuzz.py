@@ -69,3 +69,11 @@ def test_random_case_matches_oracle(gpu_ctx, seed):
     finally:
         grp.close()
         dmesh.close()
+
+
+@pytest.mark.parametrize("seed", range(100, 116))
+def test_random_case_matches_oracle_on_the_two_kernel_path(gpu_ctx, monkeypatch, seed):
+    """The same sweep through blend_kernel + skin_kernel (P3CS_PATH=wide), the path meshes with palettes too large for
+    shared memory take."""
+    monkeypatch.setenv("P3CS_PATH", "wide")
+    test_random_case_matches_oracle(gpu_ctx, seed)
