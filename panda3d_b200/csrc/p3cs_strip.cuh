@@ -45,6 +45,10 @@ template <> struct RowLayout<kRow32> { static constexpr int W = 8, VEC = 4, P = 
 template <> struct RowLayout<kRow48> { static constexpr int W = 12, VEC = 4, P = 0, N = 3, T = 6, B = 9; };
 template <> struct RowLayout<kRow56> { static constexpr int W = 14, VEC = 2, P = 0, N = 3, T = 8, B = 11; };
 
+template <class L> __device__ __forceinline__ constexpr int kRowN() { return L::N >= 0 ? L::N : 0; }
+template <class L> __device__ __forceinline__ constexpr int kRowT() { return L::T >= 0 ? L::T : 0; }
+template <class L> __device__ __forceinline__ constexpr int kRowB() { return L::B >= 0 ? L::B : 0; }
+
 // does the access unit [u*VEC, (u+1)*VEC) of the row hold a word some animated column writes?
 template <class L>
 __device__ __forceinline__ constexpr bool row_unit_dirty(int u) {
@@ -562,7 +566,58 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
         const int row = t * kTileRows + trow;
         const bool skinned = local[rr] != 0xFFFF;
         if (FAST) {
-          if (MORPH && row < mesh.num_rows) {
+          if (MORPH && ROWREG) {
+            // Row-in-registers modes: the row is loaded first, the sparse morph deltas are added to the registers
+            // (reference order; 3-component branch, geomVertexData.cxx:1531-1535), then the blend record applies --
+            // no shared-memory round trip per morph entry.  Rows without entries that are not skinned stay untouched.
+            using L = RowLayout<MODE>;
+            if (row < mesh.num_rows && (skinned || me[rr] > mb[rr])) {
+              uint8_t *rowp = tile + trow * (L::W * 4);
+              float v[L::W];
+              row_load<L>(rowp, trow, v);
+              for (int e = mb[rr]; e < me[rr]; ++e) {
+                const float4 d = __ldg(mesh.morph_deltas + e);  // .w carries the key of a 3-component delta
+                const uint32_t key = __float_as_uint(d.w);
+                const float value = __ldg(sliders + (key & 0xffffu));
+                if (value == 0.0f) continue;  // `if (slider_value != 0.0f)`, :1483
+                const int c = (int)(key >> 16);  // animated columns in canonical order: point, normal, vector, vector
+                constexpr int kN = L::N >= 0 ? L::N : 0, kT = L::T >= 0 ? L::T : 0, kB = L::B >= 0 ? L::B : 0;
+                if (c == 0) {
+                  v[L::P] = v[L::P] + d.x * value;
+                  v[L::P + 1] = v[L::P + 1] + d.y * value;
+                  v[L::P + 2] = v[L::P + 2] + d.z * value;
+                } else if (L::N >= 0 && c == 1) {
+                  v[kN] = v[kN] + d.x * value;
+                  v[kN + 1] = v[kN + 1] + d.y * value;
+                  v[kN + 2] = v[kN + 2] + d.z * value;
+                } else if (L::T >= 0 && c == 2) {
+                  v[kT] = v[kT] + d.x * value;
+                  v[kT + 1] = v[kT + 1] + d.y * value;
+                  v[kT + 2] = v[kT + 2] + d.z * value;
+                } else if (L::B >= 0 && c == 3) {
+                  v[kB] = v[kB] + d.x * value;
+                  v[kB + 1] = v[kB + 1] + d.y * value;
+                  v[kB + 2] = v[kB + 2] + d.z * value;
+                }
+              }
+              if (skinned) {
+                const float2 *p = reinterpret_cast<const float2 *>(recs + (size_t)local[rr] * kRecCompact);
+                float f[22];
+#pragma unroll
+                for (int i = 0; i < 11; ++i) {
+                  const float2 q = p[i];
+                  f[2 * i] = q.x;
+                  f[2 * i + 1] = q.y;
+                }
+                fast_column<1>(v + L::P, f);
+                if (L::N >= 0) fast_column<3>(v + kRowN<L>(), f);
+                if (L::T >= 0) fast_column<2>(v + kRowT<L>(), f);
+                if (L::B >= 0) fast_column<2>(v + kRowB<L>(), f);
+              }
+              if (BOUNDS && bounds_off == 0) bounds.add(v[0], v[1], v[2]);
+              row_store<L>(rowp, trow, v);
+            }
+          } else if (MORPH && row < mesh.num_rows) {
             // sparse morph deltas, added in place in the reference's order (3-component branch,
             // geomVertexData.cxx:1531-1535); columns are independent, so walking the row's
             // entries once is the same arithmetic as the reference's per-column passes
@@ -592,7 +647,9 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
               }
             }
           }
-          if (ALIGNED) {
+          if (MORPH && ROWREG) {
+            // handled above
+          } else if (ALIGNED) {
             if (skinned) {
               const float2 *p = reinterpret_cast<const float2 *>(recs + (size_t)local[rr] * kRecAligned);
               float f[26];
@@ -676,7 +733,7 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
 #pragma unroll
         for (int rr = 0; rr < kRowsPerThread; ++rr) {
           const int trow = rr * kStripThreads + tid;
-          const bool in_registers = ROWREG && local[rr] != 0xFFFF && bounds_off == 0;
+          const bool in_registers = ROWREG && bounds_off == 0 && (local[rr] != 0xFFFF || (MORPH && me[rr] > mb[rr]));
           if (t * kTileRows + trow < mesh.num_rows && !in_registers) {
             const float *c = reinterpret_cast<const float *>(tile + bounds_off + (size_t)trow * bounds_stride);
             bounds.add(c[0], c[1], c[2]);
