@@ -20,5 +20,5 @@ for d in $DIRS; do INC="$INC -I$REF/$d -I$REFBUILD/cmake/$d -I$REFBUILD/$d"; don
 g++ -std=gnu++17 -O2 -fno-rtti -fno-exceptions $INC "$HERE/cudaSkinBackend.cxx" "$HERE/panda_cuda_check.cxx" \
     -L"$ROOT/oracle/_ref/lib" -lpandaegg -lpanda -lpandaexpress -lp3dtool -lp3prc -lpthread -ldl \
     -Wl,-rpath,'$ORIGIN/../../oracle/_ref/lib' -o "$OUT/panda_cuda_check"
-cp "$REF/models/panda-model.egg" "$REF/models/panda-walk4.egg" "$OUT/models/"
+cp "$REF/models/panda-model.egg" "$REF/models/panda-walk4.egg" "$REF/models/ripple.egg" "$OUT/models/"
 echo "built $OUT/panda_cuda_check"

@@ -35,15 +35,16 @@ int main(int argc, char **argv) {
     printf("{\"ok\": false, \"error\": \"backend unavailable (see the gobj error log)\"}\n");
     return 1;
   }
+  const bool one_file = strcmp(argv[2], argv[3]) == 0;  // e.g. models/ripple.egg holds model and animation
   PT(PandaNode) model = load_egg_file(argv[2]);
-  PT(PandaNode) anim = load_egg_file(argv[3]);
-  if (model == nullptr || anim == nullptr) {
+  PT(PandaNode) anim = one_file ? nullptr : load_egg_file(argv[3]);
+  if (model == nullptr || (!one_file && anim == nullptr)) {
     printf("{\"ok\": false, \"error\": \"egg load failed\"}\n");
     return 1;
   }
   PT(PandaNode) root = new PandaNode("root");
   root->add_child(model);
-  root->add_child(anim);
+  if (anim != nullptr) root->add_child(anim);
   AnimControlCollection controls;
   auto_bind(root, controls, ~0);
   NodePath np(root);
