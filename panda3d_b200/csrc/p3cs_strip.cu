@@ -61,6 +61,17 @@ static int strip_partition(const MeshDev &mesh, int count, int sm_count, int *gr
   if (gpc > mesh.num_groups) gpc = mesh.num_groups;
   const int strips = (mesh.num_groups + (int)gpc - 1) / (int)gpc;
   *groups_per_cta = (mesh.num_groups + strips - 1) / strips;  // equal-length strips
+  // Few CTAs in the whole launch (a single small mesh): split every group's tiles over several CTAs, which is
+  // encoded as a negative groups_per_cta (see strip_kernel).
+  if (*groups_per_cta == 1 && (long long)strips * count * 2 <= sm_count && mesh.num_groups > 0) {
+    const int tiles_per_group = (mesh.num_tiles + mesh.num_groups - 1) / mesh.num_groups;
+    int split = (int)(sm_count / ((long long)strips * count));
+    if (split > tiles_per_group) split = tiles_per_group;
+    if (split > 1) {
+      *groups_per_cta = -split;
+      return strips * split;
+    }
+  }
   return strips;
 }
 

@@ -390,11 +390,22 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   int tid;  // read once and kept in a register: the compiler otherwise re-reads SR_TID.X (long-latency S2R) per tile
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
   const int inst = grp.instance_list != nullptr ? __ldg(grp.instance_list + first_instance + blockIdx.y) : first_instance + (int)blockIdx.y;
-  const int g0 = blockIdx.x * groups_per_cta;
-  const int g1 = min(mesh.num_groups, g0 + groups_per_cta);
+  // groups_per_cta > 0: the CTA owns that many consecutive record groups.  groups_per_cta < 0 (few CTAs in the
+  // launch: a single small mesh): one group per strip, its tiles split over -groups_per_cta CTAs, each of which
+  // computes the group's records itself -- more CTAs in flight instead of one CTA walking every tile.
+  const int tile_split = groups_per_cta < 0 ? -groups_per_cta : 1;
+  const int gpc = groups_per_cta < 0 ? 1 : groups_per_cta;
+  const int g0 = ((int)blockIdx.x / tile_split) * gpc;
+  const int g1 = min(mesh.num_groups, g0 + gpc);
   if (g0 >= g1) return;
-  const int t0 = __ldg(mesh.group_tile_offsets + g0);
-  const int t1 = __ldg(mesh.group_tile_offsets + g1);
+  int t0 = __ldg(mesh.group_tile_offsets + g0);
+  int t1 = __ldg(mesh.group_tile_offsets + g1);
+  if (tile_split > 1) {
+    const int per = (t1 - t0 + tile_split - 1) / tile_split;
+    t0 += ((int)blockIdx.x % tile_split) * per;
+    t1 = min(t1, t0 + per);
+    if (t0 >= t1) return;
+  }
 
   if (tid == 0) {
 #pragma unroll
@@ -510,7 +521,7 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
     }
     __syncthreads();  // every record of the group is in shared memory
     const int cur_rbeg = rbeg;
-    const int cur_gt1 = gt1;
+    const int cur_gt1 = min(gt1, t1);
     if (g + 1 < g1) {  // prefetch for the next group; consumed after this group's tiles
       rbeg = rend;
       rend = __ldg(mesh.group_rec_offsets + g + 2);
