@@ -323,7 +323,7 @@ __device__ __forceinline__ float4 aligned_normal(const float4 v, const float (&f
     float r0 = v.x * f[12] + v.y * f[15] + v.z * f[18];
     float r1 = v.x * f[13] + v.y * f[16] + v.z * f[19];
     float r2 = v.x * f[14] + v.y * f[17] + v.z * f[20];
-    normalize3(r0, r1, r2);
+    normalize3_hot(r0, r1, r2);
     return make_float4(r0, r1, r2, v.w);
   }
   if (f[21] == 2.0f) return aligned_xform_blend(v, f);
@@ -353,7 +353,7 @@ __device__ __forceinline__ void fast_column(float *cell, const float (&f)[22]) {
     r0 = v0 * f[12] + v1 * f[15] + v2 * f[18];
     r1 = v0 * f[13] + v1 * f[16] + v2 * f[19];
     r2 = v0 * f[14] + v1 * f[17] + v2 * f[20];
-    if (f[21] == 1.0f) normalize3(r0, r1, r2);
+    if (f[21] == 1.0f) normalize3_hot(r0, r1, r2);
   }
   cell[0] = r0;
   cell[1] = r1;
