@@ -379,7 +379,8 @@ P3CS_EXPORT int p3cs_group_pose(p3cs_group group, p3cs_skeleton skeleton, int fi
  * (anim-blend-type) is normalized-linear.  One AnimControl of effect 1. */
 #define P3CS_BT_LINEAR 0
 #define P3CS_BT_NORMALIZED_LINEAR 1
-#define P3CS_BT_COMPONENTWISE 2       /* BT_componentwise_quat (3) is not supported */
+#define P3CS_BT_COMPONENTWISE 2
+#define P3CS_BT_COMPONENTWISE_QUAT 3  /* rotations blended as quaternions (chan/movingPartMatrix.cxx:273-357) */
 P3CS_EXPORT int p3cs_group_pose_blend(p3cs_group group, p3cs_skeleton skeleton, int first, int count, const int32_t *host_frames,
                                       const int32_t *host_next_frames, const float *host_fracs, int blend_type);
 /* Several animations on one skeleton and several AnimControls per character (PartBundle::set_anim_blend_flag,

@@ -572,6 +572,9 @@ static int cmd_egg(int argc, char **argv) {
   } else if (bt != nullptr && strcmp(bt, "componentwise") == 0) {
     ch->get_bundle(0)->set_blend_type(PartBundle::BT_componentwise);
     blend_type = 2;
+  } else if (bt != nullptr && strcmp(bt, "componentwise_quat") == 0) {
+    ch->get_bundle(0)->set_blend_type(PartBundle::BT_componentwise_quat);
+    blend_type = 3;
   }
   AnimControl *control = ctrls.get_anim(0);
   for (int i = 5; i < argc; ++i) {
@@ -617,6 +620,7 @@ static int cmd_eggmulti(int argc, char **argv) {
   int blend_type = 1;
   if (bt != nullptr && strcmp(bt, "linear") == 0) { bundle->set_blend_type(PartBundle::BT_linear); blend_type = 0; }
   else if (bt != nullptr && strcmp(bt, "componentwise") == 0) { bundle->set_blend_type(PartBundle::BT_componentwise); blend_type = 2; }
+  else if (bt != nullptr && strcmp(bt, "componentwise_quat") == 0) { bundle->set_blend_type(PartBundle::BT_componentwise_quat); blend_type = 3; }
   Case out;
   Exported ex = export_vertex_data(actor.vd, out);
   export_skeleton(actor.ch, ex, out);

@@ -805,7 +805,79 @@ static void channel_value_no_scale_shear(const p3o_skeleton *skel, int j, int fr
   M4(value, 3, 3) = 1.0f;
 }
 
-/* blend_type: 0 BT_linear, 1 BT_normalized_linear, 2 BT_componentwise (PartBundle::BlendType, chan/partBundle.h; the default
+/* LQuaternionf::multiply (linmath/lquaternion_src.I:78-85): a = *this, b = rhs; components (r, i, j, k) */
+static void quat_mul(float *res, const float *a, const float *b) {
+  float r = (b[0] * a[0]) - (b[1] * a[1]) - (b[2] * a[2]) - (b[3] * a[3]);
+  float i = (b[1] * a[0]) + (b[0] * a[1]) - (b[3] * a[2]) + (b[2] * a[3]);
+  float j = (b[2] * a[0]) + (b[3] * a[1]) + (b[0] * a[2]) - (b[1] * a[3]);
+  float k = (b[3] * a[0]) - (b[2] * a[1]) + (b[1] * a[2]) + (b[0] * a[3]);
+  res[0] = r; res[1] = i; res[2] = j; res[3] = k;
+}
+
+/* LQuaternionf::set_hpr (linmath/lquaternion_src.cxx:95-120): half-angle quaternions about up / right / forward
+ * (lvector3_src.I:267-322), quat_r * quat_p * quat_h on right-handed systems, invert(quat_h * quat_p * quat_r)
+ * (invert_from: the real part negated, lquaternion_src.I:474-478) on left-handed ones. */
+static void quat_set_hpr(float *q, const float *hpr, int cs) {
+  float fwd[3] = {0, 0, 0}, right[3] = {1, 0, 0}, up[3] = {0, 0, 0}, qh[4], qp[4], qr[4], t[4], a, s, c;
+  switch (cs) {
+  case P3O_CS_ZUP_RIGHT: fwd[1] = 1; up[2] = 1; break;
+  case P3O_CS_ZUP_LEFT: fwd[1] = -1; up[2] = 1; break;
+  case P3O_CS_YUP_RIGHT: fwd[2] = -1; up[1] = 1; break;
+  default: fwd[2] = 1; up[1] = 1; break;
+  }
+  a = (hpr[0] * 0.5f) * DEG_2_RAD_F; s = sinf(a); c = cosf(a);
+  qh[0] = c; qh[1] = up[0] * s; qh[2] = up[1] * s; qh[3] = up[2] * s;
+  a = (hpr[1] * 0.5f) * DEG_2_RAD_F; s = sinf(a); c = cosf(a);
+  qp[0] = c; qp[1] = right[0] * s; qp[2] = right[1] * s; qp[3] = right[2] * s;
+  a = (hpr[2] * 0.5f) * DEG_2_RAD_F; s = sinf(a); c = cosf(a);
+  qr[0] = c; qr[1] = fwd[0] * s; qr[2] = fwd[1] * s; qr[3] = fwd[2] * s;
+  if (cs == P3O_CS_ZUP_RIGHT || cs == P3O_CS_YUP_RIGHT) {
+    quat_mul(t, qr, qp);
+    quat_mul(q, t, qh);
+  } else {
+    quat_mul(t, qh, qp);
+    quat_mul(q, t, qr);
+    q[0] = -q[0];
+  }
+}
+
+/* LQuaternionf::extract_to_matrix(LMatrix4f &) (linmath/lquaternion_src.cxx:74-89) */
+static void quat_to_matrix4(float *m, const float *q) {
+  float N = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];   /* LVecBase4f::dot, left to right */
+  float s = (N == 0.0f) ? 0.0f : (2.0f / N);
+  float xs = q[1] * s, ys = q[2] * s, zs = q[3] * s;
+  float wx = q[0] * xs, wy = q[0] * ys, wz = q[0] * zs;
+  float xx = q[1] * xs, xy = q[1] * ys, xz = q[1] * zs;
+  float yy = q[2] * ys, yz = q[2] * zs, zz = q[3] * zs;
+  M4(m, 0, 0) = 1.0f - (yy + zz); M4(m, 0, 1) = xy + wz; M4(m, 0, 2) = xz - wy; M4(m, 0, 3) = 0.0f;
+  M4(m, 1, 0) = xy - wz; M4(m, 1, 1) = 1.0f - (xx + zz); M4(m, 1, 2) = yz + wx; M4(m, 1, 3) = 0.0f;
+  M4(m, 2, 0) = xz + wy; M4(m, 2, 1) = yz - wx; M4(m, 2, 2) = 1.0f - (xx + yy); M4(m, 2, 3) = 0.0f;
+  M4(m, 3, 0) = 0.0f; M4(m, 3, 1) = 0.0f; M4(m, 3, 2) = 0.0f; M4(m, 3, 3) = 1.0f;
+}
+
+/* `LMatrix4f::scale_shear_mat(scale, shear) * quat` followed by set_row(3, pos): the tail of the
+ * BT_componentwise_quat branch (chan/movingPartMatrix.cxx:345-355; operator * (LMatrix4f, LQuaternionf),
+ * lquaternion_src.I:547-561: the full 4x4 product, then row 3 and column 3 of the left matrix put back). */
+static void quat_compose_value(float *value, const float *scale, const float *shear, const float *quat, const float *pos, int cs) {
+  static const float zero_hpr[3] = {0.0f, 0.0f, 0.0f};
+  float s3[9], m[16], qm[16];
+  int r, c;
+  p3o_compose3(s3, scale, shear, zero_hpr, cs);   /* hpr == 0 skips every rotation: set_scale_shear_mat alone */
+  for (r = 0; r < 3; ++r) {
+    for (c = 0; c < 3; ++c) M4(m, r, c) = M3(s3, r, c);
+    M4(m, r, 3) = 0.0f;
+  }
+  M4(m, 3, 0) = 0.0f; M4(m, 3, 1) = 0.0f; M4(m, 3, 2) = 0.0f; M4(m, 3, 3) = 1.0f;
+  quat_to_matrix4(qm, quat);
+  mul4(value, m, qm);
+  for (c = 0; c < 4; ++c) M4(value, 3, c) = M4(m, 3, c);
+  for (r = 0; r < 4; ++r) M4(value, r, 3) = M4(m, r, 3);
+  M4(value, 3, 0) = pos[0];
+  M4(value, 3, 1) = pos[1];
+  M4(value, 3, 2) = pos[2];
+}
+
+/* blend_type: 0 BT_linear, 1 BT_normalized_linear, 2 BT_componentwise, 3 BT_componentwise_quat (PartBundle::BlendType, chan/partBundle.h; the default
  * comes from the PRC variable anim-blend-type = normalized-linear, chan/partBundle.cxx:41-42).
  *
  * K AnimControls in the order PartBundle iterates its _blend map; ctrl_skel[k] carries the channel tables of
@@ -833,6 +905,7 @@ int p3o_pose_controls(const p3o_skeleton *const *ctrl_skel, int K, const int *fr
        * (LMatrix4 / LVecBase3 operator /=, lmatrix4_src.I:1094-1098, lvecBase3_src.I:709-718) */
       float nv[16], scale[3] = {0.0f, 0.0f, 0.0f}, shear[3] = {0.0f, 0.0f, 0.0f}, net_effect = 0.0f, recip;
       float comps[12] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+      float quat[4] = {0.0f, 0.0f, 0.0f, 0.0f};
       for (k = 0; k < 16; ++k) nv[k] = 0.0f;
       for (c = 0; c < K; ++c) {
         const p3o_skeleton *cs = ctrl_skel[c];
@@ -844,6 +917,15 @@ int p3o_pose_controls(const p3o_skeleton *const *ctrl_skel, int K, const int *fr
           float e = !frame_blend ? effect : pass == 0 ? effect * (1.0f - fracs[c]) : effect * fracs[c];
           if (blend_type == 2) {  /* BT_componentwise, :200-271: scale, shear, hpr and pos blend on their own */
             for (k = 0; k < 12; ++k) comps[k] = comps[k] + channel_component(cs, j, k, fr) * e;
+            continue;
+          }
+          if (blend_type == 3) {  /* BT_componentwise_quat, :273-357: the rotation blends as a quaternion (get_quat, animChannelMatrixXfmTable.cxx:186-197) */
+            float ihpr[3], iq[4];
+            for (k = 0; k < 3; ++k) ihpr[k] = channel_component(cs, j, 6 + k, fr);
+            quat_set_hpr(iq, ihpr, skel->coordinate_system);
+            for (k = 0; k < 6; ++k) comps[k] = comps[k] + channel_component(cs, j, k, fr) * e;
+            for (k = 9; k < 12; ++k) comps[k] = comps[k] + channel_component(cs, j, k, fr) * e;
+            for (k = 0; k < 4; ++k) quat[k] = quat[k] + iq[k] * e;
             continue;
           }
           if (blend_type == 0) channel_value(cs, j, fr, v);   /* BT_linear, :82-122 */
@@ -859,7 +941,11 @@ int p3o_pose_controls(const p3o_skeleton *const *ctrl_skel, int K, const int *fr
       }
       recip = 1.0f / net_effect;
       for (k = 0; k < 16; ++k) nv[k] = nv[k] * recip;
-      if (blend_type == 2) {
+      if (blend_type == 3) {
+        for (k = 0; k < 12; ++k) comps[k] = comps[k] * recip;
+        for (k = 0; k < 4; ++k) quat[k] = quat[k] * recip;
+        quat_compose_value(value, comps + 0, comps + 3, quat, comps + 9, skel->coordinate_system);
+      } else if (blend_type == 2) {
         float out3[9];
         int r, cc;
         for (k = 0; k < 12; ++k) comps[k] = comps[k] * recip;

@@ -835,8 +835,9 @@ static int pose_common(p3cs_group grp, p3cs_skeleton sk, int first, int count, c
 }
 
 static int check_blend_type(int blend_type, const char *what) {
-  if (blend_type != P3CS_BT_LINEAR && blend_type != P3CS_BT_NORMALIZED_LINEAR && blend_type != P3CS_BT_COMPONENTWISE)
-    return p3cs_fail(P3CS_ERR_UNSUPPORTED, "%s: blend type %d (BT_componentwise_quat is not supported)", what, blend_type);
+  if (blend_type != P3CS_BT_LINEAR && blend_type != P3CS_BT_NORMALIZED_LINEAR && blend_type != P3CS_BT_COMPONENTWISE &&
+      blend_type != P3CS_BT_COMPONENTWISE_QUAT)
+    return p3cs_fail(P3CS_ERR_INVALID, "%s: blend type %d is not a PartBundle::BlendType", what, blend_type);
   return P3CS_OK;
 }
 

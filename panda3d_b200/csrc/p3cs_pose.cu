@@ -11,7 +11,7 @@
 // instance and frame from the host instead of T x 64 bytes of matrices.
 // Covers one AnimControl without blending (chan/movingPartMatrix.cxx:71-76), the frame-blend flag
 // (PartBundle::set_frame_blend_flag) and several AnimControls blended by their effects (set_anim_blend_flag /
-// set_control_effect), for BT_linear and BT_normalized_linear (:78-198); same -fmad=false arithmetic as the rest
+// set_control_effect), for all four blend types (:78-357); same -fmad=false arithmetic as the rest
 // of the library.
 #include "p3cs_device.cuh"
 
@@ -53,13 +53,80 @@ __device__ __forceinline__ void channel_value(const AnimationDev &an, int cs, in
   value[15] = 1.0f;
 }
 
+// ---- BT_componentwise_quat (chan/movingPartMatrix.cxx:273-357): the rotation blends as a quaternion
+// LQuaternionf::multiply (linmath/lquaternion_src.I:78-85): a = *this, b = rhs; components (r, i, j, k)
+__device__ __forceinline__ void quat_mul(float *res, const float *a, const float *b) {
+  const float r = (b[0] * a[0]) - (b[1] * a[1]) - (b[2] * a[2]) - (b[3] * a[3]);
+  const float i = (b[1] * a[0]) + (b[0] * a[1]) - (b[3] * a[2]) + (b[2] * a[3]);
+  const float j = (b[2] * a[0]) + (b[3] * a[1]) + (b[0] * a[2]) - (b[1] * a[3]);
+  const float k = (b[3] * a[0]) - (b[2] * a[1]) + (b[1] * a[2]) + (b[0] * a[3]);
+  res[0] = r; res[1] = i; res[2] = j; res[3] = k;
+}
+
+// LQuaternionf::set_hpr (linmath/lquaternion_src.cxx:95-120), what AnimChannelMatrixXfmTable::get_quat
+// (animChannelMatrixXfmTable.cxx:186-197) returns: half-angle quaternions about up / right / forward, multiplied
+// as quat_r * quat_p * quat_h (right-handed) or invert(quat_h * quat_p * quat_r) (left-handed; invert_from negates
+// the real part, lquaternion_src.I:474-478).
+static __device__ __noinline__ void quat_set_hpr(float *q, const float *hpr, int cs) {
+  const bool left = (cs == 3 || cs == 4), zup = (cs == 1 || cs == 3);
+  float fwd[3] = {0.0f, 0.0f, 0.0f}, up[3] = {0.0f, 0.0f, 0.0f};
+  if (zup) { fwd[1] = left ? -1.0f : 1.0f; up[2] = 1.0f; }
+  else { fwd[2] = left ? 1.0f : -1.0f; up[1] = 1.0f; }
+  float qh[4], qp[4], qr[4], t[4], sn, cn;
+  sincosf((hpr[0] * 0.5f) * P3CS_DEG_2_RAD, &sn, &cn);
+  qh[0] = cn; qh[1] = up[0] * sn; qh[2] = up[1] * sn; qh[3] = up[2] * sn;
+  sincosf((hpr[1] * 0.5f) * P3CS_DEG_2_RAD, &sn, &cn);
+  qp[0] = cn; qp[1] = 1.0f * sn; qp[2] = 0.0f * sn; qp[3] = 0.0f * sn;
+  sincosf((hpr[2] * 0.5f) * P3CS_DEG_2_RAD, &sn, &cn);
+  qr[0] = cn; qr[1] = fwd[0] * sn; qr[2] = fwd[1] * sn; qr[3] = fwd[2] * sn;
+  if (!left) {
+    quat_mul(t, qr, qp);
+    quat_mul(q, t, qh);
+  } else {
+    quat_mul(t, qh, qp);
+    quat_mul(q, t, qr);
+    q[0] = -q[0];
+  }
+}
+
+// _value = LMatrix4f::scale_shear_mat(scale, shear) * quat; _value.set_row(3, pos)  (movingPartMatrix.cxx:352-353):
+// LQuaternionf::extract_to_matrix (lquaternion_src.cxx:74-89), the full 4x4 product of operator * (LMatrix4f,
+// LQuaternionf) (lquaternion_src.I:547-561) with the left matrix' row 3 and column 3 put back, then the translation.
+static __device__ __noinline__ void quat_compose_value(float *value, const float *scale, const float *shear, const float *q, const float *pos,
+                                                       int cs) {
+  const float zero_hpr[3] = {0.0f, 0.0f, 0.0f};
+  Mat3 s3;
+  compose3(s3, scale, shear, zero_hpr, cs);  // zero angles skip every rotation: set_scale_shear_mat alone
+  float m[16], qm[16];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) m[r * 4 + c] = s3.m[r][c];
+    m[r * 4 + 3] = 0.0f;
+  }
+  m[12] = 0.0f; m[13] = 0.0f; m[14] = 0.0f; m[15] = 1.0f;
+  const float N = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  const float s = (N == 0.0f) ? 0.0f : (2.0f / N);
+  const float xs = q[1] * s, ys = q[2] * s, zs = q[3] * s;
+  const float wx = q[0] * xs, wy = q[0] * ys, wz = q[0] * zs;
+  const float xx = q[1] * xs, xy = q[1] * ys, xz = q[1] * zs;
+  const float yy = q[2] * ys, yz = q[2] * zs, zz = q[3] * zs;
+  qm[0] = 1.0f - (yy + zz); qm[1] = xy + wz; qm[2] = xz - wy; qm[3] = 0.0f;
+  qm[4] = xy - wz; qm[5] = 1.0f - (xx + zz); qm[6] = yz + wx; qm[7] = 0.0f;
+  qm[8] = xz + wy; qm[9] = yz - wx; qm[10] = 1.0f - (xx + yy); qm[11] = 0.0f;
+  qm[12] = 0.0f; qm[13] = 0.0f; qm[14] = 0.0f; qm[15] = 1.0f;
+  mul4(value, m, qm);
+  value[3] = 0.0f; value[7] = 0.0f; value[11] = 0.0f;  // column 3 and row 3 of scale_shear_mat
+  value[12] = pos[0]; value[13] = pos[1]; value[14] = pos[2]; value[15] = 1.0f;
+}
+
 // BLEND = false: one AnimControl of animation 0 per instance, no frame blending (movingPartMatrix.cxx:71-76).
 // BLEND = true: `num_controls` AnimControls per instance (PartBundle::set_anim_blend_flag / set_control_effect) in
 // the order of the bundle's blend map, and / or the frame-blend flag; per joint
 // (MovingPartBase::determine_effective_channels, movingPartBase.cxx:303-333; MovingPartMatrix::get_blend_value,
 // movingPartMatrix.cxx:52-198): no control with a channel -> the default value; exactly one and no frame blending ->
 // its value; else the blend, blend_type 0 = BT_linear (:82-122), 1 = BT_normalized_linear (:125-198, the PRC default),
-// 2 = BT_componentwise (:200-271).
+// 2 = BT_componentwise (:200-271), 3 = BT_componentwise_quat (:273-357).
 // AnimChannelScalarTable::get_value (chan/animChannelScalarTable.cxx:88-94)
 __device__ __forceinline__ float slider_channel_value(const AnimationDev &an, int s, int frame) {
   const int len = __ldg(an.slider_table_length + s);
@@ -139,6 +206,7 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
         // (LMatrix4 / LVecBase3 operator /=)
         float nv[16], scale[3] = {0.0f, 0.0f, 0.0f}, shear[3] = {0.0f, 0.0f, 0.0f}, net_effect = 0.0f;
         float comps[12];  // BT_componentwise (:200-271): scale, shear, hpr and pos blend on their own
+        float quat[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // BT_componentwise_quat (:273-357): the rotation as a quaternion
 #pragma unroll
         for (int k = 0; k < 16; ++k) nv[k] = 0.0f;
 #pragma unroll
@@ -153,6 +221,18 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
             if (blend_type == 2) {
 #pragma unroll
               for (int k = 0; k < 12; ++k) comps[k] = comps[k] + channel_component(an, j, k, fr) * e;
+              continue;
+            }
+            if (blend_type == 3) {
+              float ihpr[3], iq[4];
+#pragma unroll
+              for (int k = 0; k < 3; ++k) ihpr[k] = channel_component(an, j, 6 + k, fr);
+              quat_set_hpr(iq, ihpr, cs);
+#pragma unroll
+              for (int k = 0; k < 12; ++k)
+                if (k < 6 || k >= 9) comps[k] = comps[k] + channel_component(an, j, k, fr) * e;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) quat[k] = quat[k] + iq[k] * e;
               continue;
             }
             float v[16];
@@ -172,7 +252,13 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
         const float recip = 1.0f / net_effect;
 #pragma unroll
         for (int k = 0; k < 16; ++k) value[k] = nv[k] * recip;
-        if (blend_type == 2) {
+        if (blend_type == 3) {
+#pragma unroll
+          for (int k = 0; k < 12; ++k) comps[k] = comps[k] * recip;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) quat[k] = quat[k] * recip;
+          quat_compose_value(value, comps + 0, comps + 3, quat, comps + 9, cs);
+        } else if (blend_type == 2) {
 #pragma unroll
           for (int k = 0; k < 12; ++k) comps[k] = comps[k] * recip;
           Mat3 out3;

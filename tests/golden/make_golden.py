@@ -103,7 +103,8 @@ def main():
     print("wrote", out, os.path.getsize(out))
     # the same Actor with PartBundle::set_frame_blend_flag(true), posed between frames (joint hierarchy fixture, f1)
     os.makedirs(os.path.join(HERE, "skeleton"), exist_ok=True)
-    for suffix, env in (("", {}), ("_linear", {"P3CS_BLEND_TYPE": "linear"})):   # anim-blend-type default, then BT_linear
+    for suffix, env in (("", {}), ("_linear", {"P3CS_BLEND_TYPE": "linear"}),   # anim-blend-type default, then BT_linear
+                        ("_componentwise_quat", {"P3CS_BLEND_TYPE": "componentwise_quat"})):
         out = os.path.join(HERE, "skeleton", f"panda_walk4_frame_blend{suffix}.p3cs")
         subprocess.run([HARNESS, "egg", model, anim, out, "0.5", "10.25", "37.0", "58.75", "3.999"], check=True, timeout=120,
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env={**os.environ, **env})
@@ -112,7 +113,8 @@ def main():
     samples_hold = ["3:0.7,20:0.3", "10:1.0,40:0.0", "0:0.5,59:0.5", "17:0.2,18:1.3"]
     samples_blend = ["3.5:0.7,20.25:0.3", "10.75:1.0,40:0.0", "5.5:0.25,33.25:0.75"]
     for samples, tag in ((samples_hold, "hold"), (samples_blend, "frame_blend")):
-        for suffix, env in (("", {}), ("_linear", {"P3CS_BLEND_TYPE": "linear"}), ("_componentwise", {"P3CS_BLEND_TYPE": "componentwise"})):
+        for suffix, env in (("", {}), ("_linear", {"P3CS_BLEND_TYPE": "linear"}), ("_componentwise", {"P3CS_BLEND_TYPE": "componentwise"}),
+                            ("_componentwise_quat", {"P3CS_BLEND_TYPE": "componentwise_quat"})):
             out = os.path.join(HERE, "skeleton", f"panda_walk4_two_controls_{tag}{suffix}.p3cs")
             subprocess.run([HARNESS, "eggmulti", model, anim, out] + samples, check=True, timeout=120,
                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env={**os.environ, **env})

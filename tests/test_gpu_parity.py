@@ -325,6 +325,46 @@ def test_non_affine_palette_takes_the_general_inverse(gpu_ctx):
     _check_against_oracle(gpu_ctx, sm.flat, pal.reshape(16, 16), what="non-affine palette")
 
 
+@pytest.mark.parametrize("layout", ["packed", "texcoord", "tbn", "align16"])
+def test_normals_of_extreme_length_normalise_like_the_cpu(gpu_ctx, layout):
+    """LVecBase3f::normalize over the whole float range (lvecBase3_src.I:347-361): the kernel's short form
+    (one range test, then the in-range sqrt / reciprocal sequences) and its fallback must both reproduce the
+    CPU's correctly rounded sqrtf and 1/x -- zero, subnormal, tiny, huge, infinite and NaN lengths included.
+    Non-uniform joint scales select the normalising branch; every byte has to match the oracle."""
+    kw = dict(texcoord=layout == "texcoord", tbn=layout == "tbn", align16=layout == "align16")
+    sm = synth.make_mesh(4_096, 12, 200, seed=71, index_order="runs", **kw)
+    mesh = sm.flat
+    ncol = [c for c in mesh.skin_columns if c.contents == F.C_normal][0]
+    arr = mesh.arrays[ncol.array]
+    nrm = np.ascontiguousarray(arr[:, ncol.start:ncol.start + 12]).view(np.float32).reshape(-1, 3).copy()
+    rng = np.random.default_rng(72)
+    mags = np.array([0.0, 1e-45, 1e-40, 1e-38, 3e-31, 1e-25, 1e-19, 9.9e-16, 1e-10, 1.0, 1e10, 3e15, 1e18, 1e19, 3e19,
+                     1e25, 1e38, np.inf, np.nan], np.float32)
+    with np.errstate(all="ignore"):
+        nrm = (nrm * mags[rng.integers(0, mags.size, size=(mesh.num_rows, 1))]).astype(np.float32)
+    nrm[::97] = 0.0
+    nrm[5::131, 1] = -0.0
+    arr[:, ncol.start:ncol.start + 12] = nrm.view(np.uint8).reshape(-1, 12)
+    pal = synth.make_palettes(12, 1, 73, scale=(1.0, 1.6, 0.55))[0]
+    om = oracle.OracleMesh(mesh)
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, 1)
+    try:
+        expect = om.animate(pal)[0]
+        got = grp.animate_vertices(pal)
+        for g, e in zip(got, expect):
+            # all columns of these layouts are float32; NaN payloads are the one thing x86 and the GPU encode differently
+            g = np.ascontiguousarray(g).reshape(mesh.num_rows, -1).view(np.uint32)
+            e = np.ascontiguousarray(e).reshape(mesh.num_rows, -1).view(np.uint32)
+            both_nan = np.isnan(g.view(np.float32)) & np.isnan(e.view(np.float32))
+            bad = np.flatnonzero(((g != e) & ~both_nan).any(axis=1))
+            assert bad.size == 0, f"{layout}: {bad.size} rows differ, first {bad[:5]}"
+            assert np.isfinite(e.view(np.float32)).mean() > 0.8
+    finally:
+        grp.close()
+        dmesh.close()
+
+
 def test_sliders_without_blend_table(gpu_ctx):
     """A vertex data with a SliderTable only: morphs apply, nothing is skinned (geomVertexData.cxx:947-948)."""
     sm = synth.make_mesh(2_000, 4, 8, seed=63, num_sliders=5, slider_band=0.4, morph_columns=("vertex", "normal"))
@@ -759,7 +799,7 @@ def test_animate_only_the_listed_instances(gpu_ctx, monkeypatch, path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fixture", ["panda_walk4_frame_blend", "panda_walk4_frame_blend_linear"])
+@pytest.mark.parametrize("fixture", ["panda_walk4_frame_blend", "panda_walk4_frame_blend_linear", "panda_walk4_frame_blend_componentwise_quat"])
 def test_joint_hierarchy_with_frame_blending(gpu_ctx, fixture):
     """f1 with PartBundle::set_frame_blend_flag(true): p3cs_group_pose_blend reproduces the reference's skinning
     matrices between frames (BT_normalized_linear, the PRC default, and BT_linear) within the float contract
@@ -805,6 +845,33 @@ def test_joint_hierarchy_with_frame_blending(gpu_ctx, fixture):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("cs", [F.CS_zup_right, F.CS_yup_right, F.CS_zup_left, F.CS_yup_left])
+@pytest.mark.parametrize("bt", [2, 3])
+def test_componentwise_blends_in_every_coordinate_system(gpu_ctx, cs, bt):
+    """BT_componentwise and BT_componentwise_quat (chan/movingPartMatrix.cxx:200-357) on a random rig in each of the
+    four coordinate systems (LQuaternionf::set_hpr multiplies in the opposite order and inverts on the left-handed
+    ones; set_scale_shear_mat moves and negates the shear terms): p3cs_group_pose_blend against the oracle."""
+    sk = synth.make_skeleton(48, 12, seed=151 + cs, coordinate_system=cs)
+    sm = synth.make_mesh(400, 48, 50, seed=152, coordinate_system=cs)
+    dsk = _capi.Skeleton(gpu_ctx, sk)
+    dm = _capi.Mesh(gpu_ctx, sm.flat)
+    grp = _capi.Group(dm, 8)
+    try:
+        f = (np.arange(8, dtype=np.int32) * 5) % 12
+        n = (f + 1) % 12
+        fr = np.linspace(0.0, 0.95, 8).astype(np.float32)
+        grp.pose_blend(dsk, f, n, fr, bt)
+        got = grp.read_palettes()
+        for i in range(8):
+            want = oracle.pose(sk, int(f[i]), int(n[i]), float(fr[i]), bt)[sk.palette_joint]
+            assert (np.abs(got[i] - want) / np.abs(want).max()).max() <= REL_TOL, f"cs {cs} blend type {bt} instance {i}"
+    finally:
+        grp.close()
+        dm.close()
+        dsk.close()
+
+
+@pytest.mark.gpu
 def test_plain_c_host_animates_through_the_plugin_table(tmp_path):
     """examples/plugin_host.c --run: a C99 host (dlopen + p3cs_get_api, no Python, no torch) skins the survey's
     four-vertex probe: (2,4,1) under 0.25*T(1,2,3) + 0.75*S(2) -> (3.75, 7.5, 2.5)."""
@@ -822,7 +889,9 @@ def test_plain_c_host_animates_through_the_plugin_table(tmp_path):
 @pytest.mark.parametrize("fixture", ["panda_walk4_two_controls_hold", "panda_walk4_two_controls_hold_linear",
                                      "panda_walk4_two_controls_hold_componentwise",
                                      "panda_walk4_two_controls_frame_blend", "panda_walk4_two_controls_frame_blend_linear",
-                                     "panda_walk4_two_controls_frame_blend_componentwise"])
+                                     "panda_walk4_two_controls_frame_blend_componentwise",
+                                     "panda_walk4_two_controls_hold_componentwise_quat",
+                                     "panda_walk4_two_controls_frame_blend_componentwise_quat"])
 def test_joint_hierarchy_with_two_blended_controls(gpu_ctx, fixture):
     """f1 with several AnimControls (PartBundle::set_anim_blend_flag / set_control_effect): p3cs_group_pose_controls
     against the reference's Character posed with two controls of different frames and effects -- the second control

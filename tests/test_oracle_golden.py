@@ -79,7 +79,7 @@ def test_oracle_pose_matches_reference_skinning_matrices():
         assert np.array_equal(skin[skel.palette_joint].view(np.uint32), case["palette"][fi].view(np.uint32))
 
 
-@pytest.mark.parametrize("fixture", ["panda_walk4_frame_blend", "panda_walk4_frame_blend_linear"])
+@pytest.mark.parametrize("fixture", ["panda_walk4_frame_blend", "panda_walk4_frame_blend_linear", "panda_walk4_frame_blend_componentwise_quat"])
 def test_oracle_pose_with_frame_blending_matches_reference(fixture):
     """The same with PartBundle::set_frame_blend_flag(true) and the Actor posed BETWEEN frames
     (tests/golden/skeleton/panda_walk4_frame_blend.p3cs: MovingPartMatrix::get_blend_value, BT_linear):
@@ -103,7 +103,8 @@ def test_oracle_pose_with_frame_blending_matches_reference(fixture):
 
 MULTI = ["panda_walk4_two_controls_hold", "panda_walk4_two_controls_hold_linear", "panda_walk4_two_controls_hold_componentwise",
          "panda_walk4_two_controls_frame_blend", "panda_walk4_two_controls_frame_blend_linear",
-         "panda_walk4_two_controls_frame_blend_componentwise"]
+         "panda_walk4_two_controls_frame_blend_componentwise", "panda_walk4_two_controls_hold_componentwise_quat",
+         "panda_walk4_two_controls_frame_blend_componentwise_quat"]
 
 
 @pytest.mark.parametrize("fixture", MULTI)
