@@ -67,10 +67,12 @@ struct MeshDev {
   int slice_bytes;                  // smem bytes of one staged 32-row slice (all outputs, 128-aligned)
   int slice_out_offset[kMaxOutputs];// byte offset of output o inside a staged slice
   const uint16_t *row_local;        // per row: index into its group's record list, 0xFFFF = not skinned
+  const uint32_t *row_local2;       // rows_per_thread == 2: per (tile, thread) the slots of its two rows (t, t + 256), one load
   const int *group_rec_offsets;     // num_groups+1
   const int *group_rec_blend;       // global blend id of every group record (selection hook)
   const int *grec_entry_offsets;    // CSR of the blend entries, in group-record order
   const uint2 *grec_entries;        // (palette index, float weight bits) per entry
+  const uint4 *grec_blocks_hi;      // second uint4 of every group record (the two halves are separate arrays: coalesced loads)
   const uint4 *grec_blocks;         // 2 x uint4 per group record: its first four entries, the
                                     // entry count in the high half of the first index
 };

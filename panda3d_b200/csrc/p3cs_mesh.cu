@@ -442,6 +442,17 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
       m.num_groups = ng;
       m.max_group_records = max_rec;
       if ((rc = upload<uint16_t>(mesh, local.data(), local.size(), &m.row_local)) != P3CS_OK) return bail(rc);
+      if (m.rows_per_thread == 2) {  // thread t of a 512-row tile animates rows t and t + 256: both slots in one word
+        const int ntiles = (N + kTileRows - 1) / kTileRows;
+        std::vector<uint32_t> pairs((size_t)std::max(ntiles, 1) * kStripThreads, 0xFFFFFFFFu);
+        for (int t = 0; t < ntiles; ++t)
+          for (int k = 0; k < kStripThreads; ++k) {
+            const int r0 = t * kTileRows + k, r1 = r0 + kStripThreads;
+            const uint32_t lo = r0 < N ? local[r0] : 0xFFFFu, hi = r1 < N ? local[r1] : 0xFFFFu;
+            pairs[(size_t)t * kStripThreads + k] = lo | (hi << 16);
+          }
+        if ((rc = upload<uint32_t>(mesh, pairs.data(), pairs.size(), &m.row_local2)) != P3CS_OK) return bail(rc);
+      }
       if ((rc = upload<int>(mesh, rec_off.data(), rec_off.size(), &m.group_rec_offsets)) != P3CS_OK) return bail(rc);
       if ((rc = upload<int>(mesh, rec_blend.data(), rec_blend.size(), &m.group_rec_blend)) != P3CS_OK) return bail(rc);
       if ((rc = upload<int>(mesh, ent_off.data(), ent_off.size(), &m.grec_entry_offsets)) != P3CS_OK) return bail(rc);
@@ -449,7 +460,8 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
       // fixed-width blocks: the first four entries of every group record, count in bits 16..31
       const size_t nrec_total = rec_blend.size();
       // padded by one CTA's worth of records: the kernel prefetches block (group start + tid)
-      std::vector<uint4> blocks((nrec_total + kStripThreads) * 2, make_uint4(0, 0, 0, 0));
+      const size_t half = nrec_total + kStripThreads;  // first halves of all records, then the second halves
+      std::vector<uint4> blocks(half * 2, make_uint4(0, 0, 0, 0));
       for (size_t r = 0; r < nrec_total; ++r) {
         uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const int beg = ent_off[r], cnt = ent_off[r + 1] - ent_off[r];
@@ -458,10 +470,11 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
           w[2 * k + 1] = ent[beg + k].y;
         }
         w[0] |= (uint32_t)std::min(cnt, 0xFFFF) << 16;
-        blocks[2 * r] = make_uint4(w[0], w[1], w[2], w[3]);
-        blocks[2 * r + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+        blocks[r] = make_uint4(w[0], w[1], w[2], w[3]);
+        blocks[half + r] = make_uint4(w[4], w[5], w[6], w[7]);
       }
       if ((rc = upload<uint4>(mesh, blocks.data(), blocks.size(), &m.grec_blocks)) != P3CS_OK) return bail(rc);
+      m.grec_blocks_hi = m.grec_blocks + half;
     }
     m.index_bytes = wide ? 4 : 2;
     const void *dev_index = nullptr;
@@ -562,6 +575,7 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
     if ((rc = upload<int>(mesh, iota.data(), iota.size(), &m.group_tile_offsets)) != P3CS_OK) return bail(rc);
     std::vector<uint4> blocks((size_t)kStripThreads * 2, make_uint4(0, 0, 0, 0));  // the kernel prefetches block [tid]
     if ((rc = upload<uint4>(mesh, blocks.data(), blocks.size(), &m.grec_blocks)) != P3CS_OK) return bail(rc);
+    m.grec_blocks_hi = m.grec_blocks + kStripThreads;
   }
   {
     const char *path = getenv("P3CS_PATH");

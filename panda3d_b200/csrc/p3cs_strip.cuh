@@ -442,11 +442,17 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   // software prefetch (hides the L2 latency of the static tables): the row's record slot for the
   // next tile, and this thread's entry block of the next record group
   int next_local[kRowsPerThread];
-#pragma unroll
-  for (int rr = 0; rr < kRowsPerThread; ++rr) {
-    const int row = t0 * kTileRows + rr * kStripThreads + tid;
-    next_local[rr] = (has_index && row < mesh.num_rows) ? (int)__ldg(mesh.row_local + row) : 0xFFFF;
-  }
+  auto fetch_local = [&](int tile_index, bool live) {  // the record slots of this thread's rows of a tile
+    if (kRowsPerThread == 2) {                         // rows t and t + 256: one 32-bit load (MeshDev::row_local2)
+      const uint32_t two = (live && has_index) ? __ldg(mesh.row_local2 + (size_t)tile_index * kStripThreads + tid) : 0xFFFFFFFFu;
+      next_local[0] = (int)(two & 0xFFFFu);
+      next_local[kRowsPerThread - 1] = (int)(two >> 16);
+    } else {
+      const int row = tile_index * kTileRows + tid;
+      next_local[0] = (live && has_index && row < mesh.num_rows) ? (int)__ldg(mesh.row_local + row) : 0xFFFF;
+    }
+  };
+  fetch_local(t0, true);
   int next_mb[kRowsPerThread], next_me[kRowsPerThread];  // the rows' morph entry ranges, prefetched the same way
 #pragma unroll
   for (int rr = 0; rr < kRowsPerThread; ++rr) {
@@ -462,8 +468,8 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
   int gt1 = __ldg(mesh.group_tile_offsets + g0 + 1);
   uint4 pq0 = make_uint4(0, 0, 0, 0), pq1 = pq0;
   if (!FULL) {  // the table is padded by kStripThreads records, so this never reads out of bounds
-    pq0 = __ldg(mesh.grec_blocks + (size_t)(rbeg + tid) * 2);
-    pq1 = __ldg(mesh.grec_blocks + (size_t)(rbeg + tid) * 2 + 1);
+    pq0 = __ldg(mesh.grec_blocks + (rbeg + tid));
+    pq1 = __ldg(mesh.grec_blocks_hi + (rbeg + tid));
   }
 
   BoundsAcc bounds;
@@ -511,9 +517,8 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
       } else {
         uint4 q0 = pq0, q1 = pq1;
         if (b != tid) {
-          const uint4 *blk = mesh.grec_blocks + (size_t)(rbeg + b) * 2;
-          q0 = __ldg(blk);
-          q1 = __ldg(blk + 1);
+          q0 = __ldg(mesh.grec_blocks + (rbeg + b));
+          q1 = __ldg(mesh.grec_blocks_hi + (rbeg + b));
         }
         if (non_affine) compact_record<false>(pal3, palc, q0, q1, mesh, rbeg + b, want_normal, ALIGNED, recs + (size_t)b * REC);
         else compact_record<true>(pal3, palc, q0, q1, mesh, rbeg + b, want_normal, ALIGNED, recs + (size_t)b * REC);
@@ -527,8 +532,8 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
       rend = __ldg(mesh.group_rec_offsets + g + 2);
       gt1 = __ldg(mesh.group_tile_offsets + g + 2);
       if (!FULL) {
-        pq0 = __ldg(mesh.grec_blocks + (size_t)(rbeg + tid) * 2);
-        pq1 = __ldg(mesh.grec_blocks + (size_t)(rbeg + tid) * 2 + 1);
+        pq0 = __ldg(mesh.grec_blocks + (rbeg + tid));
+        pq1 = __ldg(mesh.grec_blocks_hi + (rbeg + tid));
       }
     }
 
@@ -543,11 +548,12 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
       // -------------- per-row selection (integer work, bit-exact); the next tile's slots are prefetched
       int local[kRowsPerThread];
 #pragma unroll
-      for (int rr = 0; rr < kRowsPerThread; ++rr) {
-        const int row = t * kTileRows + rr * kStripThreads + tid;
-        local[rr] = next_local[rr];
-        next_local[rr] = (has_index && t + 1 < t1 && row + kTileRows < mesh.num_rows) ? (int)__ldg(mesh.row_local + row + kTileRows) : 0xFFFF;
-        if (SELECT) {
+      for (int rr = 0; rr < kRowsPerThread; ++rr) local[rr] = next_local[rr];
+      fetch_local(t + 1, t + 1 < t1);
+      if (SELECT) {
+#pragma unroll
+        for (int rr = 0; rr < kRowsPerThread; ++rr) {
+          const int row = t * kTileRows + rr * kStripThreads + tid;
           if (row < mesh.num_rows && blockIdx.y == 0)
             grp.selection[row] = local[rr] == 0xFFFF ? -1 : __ldg(mesh.group_rec_blend + cur_rbeg + local[rr]);
         }
