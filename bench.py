@@ -432,18 +432,21 @@ def run_gpu_arm(args):
         logical_bytes_per_step = n_local * rows * (2 * stride + 2)
         achieved = alg_bytes_per_step / skin_s / 1e9
         traffic = None
+        pj_limiter = None   # what actually binds the kernel, from the committed ncu capture (not measured live)
         prof = os.path.join(ROOT, "profiles", "r01_strip_kernel_c3.json")
         if os.path.exists(prof):
             pj = json.load(open(prof))
             if pj.get("instances") == n_local:
                 traffic = pj.get("dram_bytes_per_launch")
+                pj_limiter = pj.get("limiter")
         roofline = {"bound": "hbm", "kernel": "p3cs::strip_kernel<kRow24>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic, "peak_source": peak_src,
                     "launches_per_step": skin_launches, "avg_launch_ms": 1e3 * skin_s / max(1, skin_launches),
                     "algorithmic_bytes_per_launch": alg_bytes_per_step,
                     "algorithmic_bytes_per_vertex": alg_bytes_per_step / (n_local * rows),
                     "logical_gbs": logical_bytes_per_step / skin_s / 1e9,
-                    "note": "compute/shared-memory-issue bound on this 24 B/vertex crowd: see DESIGN.md"}
+                    "limiter": pj_limiter,
+                    "note": "bound by the SM's L1TEX/LSU data pipe (shared-memory wavefronts), not by HBM, on this 24 B/vertex crowd: see DESIGN.md"}
         cpu = None
         if world == 1 and not args.no_cpu:
             workers = os.cpu_count() or 1
