@@ -411,6 +411,15 @@ P3CS_EXPORT int p3cs_skeleton_add_animation(p3cs_skeleton skeleton, const p3cs_a
 P3CS_EXPORT int p3cs_group_pose_controls(p3cs_group group, p3cs_skeleton skeleton, int first, int count, int num_controls,
                                          const p3cs_control_state *host_states /* [count][num_controls] */,
                                          int frame_blend, int blend_type);
+/* Forced channels -- PartBundle::freeze_joint / control_joint (chan/partBundle.h:139-142): a joint with a forced channel
+ * takes that channel's value whatever the controls play (MovingPartMatrix::get_blend_value,
+ * chan/movingPartMatrix.cxx:53-60).  p3cs_group_set_forced_joints names the joints (indices of the skeleton's joint order;
+ * num_forced = 0 releases them all, PartBundle::release_joint) -- every instance starts with the identity;
+ * p3cs_group_set_forced_values uploads, for instances [first, first + count), what each forced channel returns
+ * (AnimChannelMatrixFixed / AnimChannelMatrixDynamic::get_value: the frozen transform, or the controlling node's
+ * transform this frame) as [count][num_forced][16] floats.  Every later p3cs_group_pose* call of the group applies them. */
+P3CS_EXPORT int p3cs_group_set_forced_joints(p3cs_group group, p3cs_skeleton skeleton, int num_forced, const int32_t *joints);
+P3CS_EXPORT int p3cs_group_set_forced_values(p3cs_group group, int first, int count, const float *host_values);
 /* Device -> host read-back of `count` palettes (count * T * 16 floats); parity hook. */
 P3CS_EXPORT int p3cs_group_read_palettes(p3cs_group group, int first, int count, float *host_dst);
 

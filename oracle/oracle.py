@@ -222,8 +222,10 @@ def pose(skel, frame: int, next_frame: Optional[int] = None, frac: float = 0.0, 
     return out
 
 
-def pose_controls(skels, frames, next_frames, fracs, effects, frame_blend: bool, blend_type: int = 1) -> np.ndarray:
-    """Several AnimControls blended (p3o_pose_controls): skels[k] carries control k's channel tables."""
+def pose_controls(skels, frames, next_frames, fracs, effects, frame_blend: bool, blend_type: int = 1,
+                  forced_joints=None, forced_values=None) -> np.ndarray:
+    """Several AnimControls blended (p3o_pose_controls): skels[k] carries control k's channel tables.
+    forced_joints / forced_values ([F], [F,16]): joints with a forced channel (freeze_joint / control_joint) and its value."""
     keep: list = []
     structs = [_skeleton_struct(skel, keep) for skel in skels]
     K = len(skels)
@@ -233,10 +235,14 @@ def pose_controls(skels, frames, next_frames, fracs, effects, frame_blend: bool,
     fr = np.ascontiguousarray(fracs, np.float32)
     ef = np.ascontiguousarray(effects, np.float32)
     out = np.empty((skels[0].num_joints, 16), np.float32)
-    lib().p3o_pose_controls.restype = C.c_int
-    rc = lib().p3o_pose_controls(ptrs, C.c_int(K), f.ctypes.data_as(C.c_void_p), nf.ctypes.data_as(C.c_void_p),
-                                 fr.ctypes.data_as(C.c_void_p), ef.ctypes.data_as(C.c_void_p), C.c_int(1 if frame_blend else 0),
-                                 C.c_int(int(blend_type)), out.ctypes.data_as(C.c_void_p))
+    fj = np.ascontiguousarray(forced_joints if forced_joints is not None else [], np.int32).reshape(-1)
+    fv = np.ascontiguousarray(forced_values if forced_values is not None else [], np.float32).reshape(-1, 16)
+    assert fv.shape[0] == fj.size
+    lib().p3o_pose_controls_forced.restype = C.c_int
+    rc = lib().p3o_pose_controls_forced(ptrs, C.c_int(K), f.ctypes.data_as(C.c_void_p), nf.ctypes.data_as(C.c_void_p),
+                                        fr.ctypes.data_as(C.c_void_p), ef.ctypes.data_as(C.c_void_p), C.c_int(1 if frame_blend else 0),
+                                        C.c_int(int(blend_type)), C.c_int(int(fj.size)), fj.ctypes.data_as(C.c_void_p),
+                                        fv.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
     if rc != 0:
         raise RuntimeError(f"oracle pose_controls failed rc={rc}")
     return out

@@ -50,6 +50,8 @@
 #include "characterVertexSlider.h"
 #include "animControl.h"
 #include "movingPartMatrix.h"
+#include "transformState.h"
+#include "animChannel.h"
 
 #include <algorithm>
 #include <chrono>
@@ -577,14 +579,51 @@ static int cmd_egg(int argc, char **argv) {
     blend_type = 3;
   }
   AnimControl *control = ctrls.get_anim(0);
+  // Forced channels (MovingPartBase::_forced_channel, chan/movingPartMatrix.cxx:53-60): P3CS_FREEZE lists joints (in the
+  // exported order) frozen with PartBundle::freeze_joint(name, pos, hpr, scale), P3CS_CONTROL joints driven by a node
+  // through PartBundle::control_joint whose transform changes with every sample.  What each forced channel returns
+  // (get_value(0, mat)) is exported per sample, so the same values can be replayed.
+  std::vector<CharacterJoint *> all_joints; std::vector<int32_t> all_parents;
+  collect_joints(ch->get_bundle(0), -1, all_joints, all_parents);
+  std::vector<PT(PandaNode)> control_nodes;
+  auto parse_list = [](const char *e) { std::vector<int> v; if (e) { const char *p = e; while (*p) { v.push_back(atoi(p)); while (*p && *p != ',') ++p; if (*p) ++p; } } return v; };
+  for (int j : parse_list(getenv("P3CS_FREEZE"))) {
+    if (j < 0 || j >= (int)all_joints.size()) { fprintf(stderr, "bad joint %d\n", j); return 1; }
+    if (!ch->get_bundle(0)->freeze_joint(all_joints[j]->get_name(), LVecBase3(0.1f * j, -0.2f, 0.05f * j), LVecBase3(10.0f * j, -20.0f, 5.0f),
+                                         LVecBase3(1.0f, 1.0f + 0.01f * j, 0.9f))) { fprintf(stderr, "freeze_joint failed\n"); return 1; }
+  }
+  for (int j : parse_list(getenv("P3CS_CONTROL"))) {
+    if (j < 0 || j >= (int)all_joints.size()) { fprintf(stderr, "bad joint %d\n", j); return 1; }
+    PT(PandaNode) node = new PandaNode("control");
+    if (!ch->get_bundle(0)->control_joint(all_joints[j]->get_name(), node)) { fprintf(stderr, "control_joint failed\n"); return 1; }
+    control_nodes.push_back(node);
+  }
+  std::vector<int32_t> forced_joints;
+  for (size_t j = 0; j < all_joints.size(); ++j) if (all_joints[j]->get_forced_channel() != nullptr) forced_joints.push_back((int32_t)j);
+  std::vector<float> forced_values;
   for (int i = 5; i < argc; ++i) {
     double fr = atof(argv[i]);
+    for (size_t k = 0; k < control_nodes.size(); ++k) {
+      const float t = (float)(i - 5) + 0.25f * (float)k;
+      control_nodes[k]->set_transform(TransformState::make_pos_hpr_scale(LVecBase3(0.3f * t, 0.1f, -0.2f * t), LVecBase3(15.0f * t, 7.0f, -11.0f * t),
+                                                                         LVecBase3(1.0f, 1.0f, 1.0f + 0.05f * t)));
+    }
     control->pose(fr);
     ch->force_update();
     record_frame(vd, ex, out, (int)frames.size());
     frames.push_back(control->get_frame());
     next_frames.push_back(control->get_next_frame());
     fracs.push_back((float)(PN_stdfloat)control->get_frac());
+    for (int32_t j : forced_joints) {
+      LMatrix4 m;
+      DCAST(AnimChannelMatrix, all_joints[j]->get_forced_channel())->get_value(0, m);
+      LMatrix4f mf = LCAST(float, m);
+      forced_values.insert(forced_values.end(), mf.get_data(), mf.get_data() + 16);
+    }
+  }
+  if (!forced_joints.empty()) {
+    out["forced_joints"] = make_blob(DT_I32, forced_joints, {(uint64_t)forced_joints.size()});
+    out["forced_values"] = make_blob(DT_F32, forced_values, {(uint64_t)frames.size(), (uint64_t)forced_joints.size(), 16});
   }
   out["anim_frames"] = make_blob(DT_I32, frames, {(uint64_t)frames.size()});
   if (blend) {

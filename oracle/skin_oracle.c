@@ -887,16 +887,29 @@ static void quat_compose_value(float *value, const float *scale, const float *sh
  * value; exactly one and no frame blending -> its value; else the blend. */
 int p3o_pose_controls(const p3o_skeleton *const *ctrl_skel, int K, const int *frames, const int *next_frames, const float *fracs,
                       const float *effects, int frame_blend, int blend_type, float *skinning_out) {
+  return p3o_pose_controls_forced(ctrl_skel, K, frames, next_frames, fracs, effects, frame_blend, blend_type, 0, NULL, NULL, skinning_out);
+}
+
+/* The same with forced channels (PartBundle::freeze_joint / control_joint): a joint with a _forced_channel takes that
+ * channel's value whatever the controls say (MovingPartMatrix::get_blend_value, chan/movingPartMatrix.cxx:53-60);
+ * forced_values[f] is what the channel returns (AnimChannelMatrixFixed / AnimChannelMatrixDynamic::get_value). */
+int p3o_pose_controls_forced(const p3o_skeleton *const *ctrl_skel, int K, const int *frames, const int *next_frames, const float *fracs,
+                             const float *effects, int frame_blend, int blend_type, int num_forced, const int *forced_joints,
+                             const float *forced_values, float *skinning_out) {
   const p3o_skeleton *skel = ctrl_skel[0];
   int J = skel->num_joints, j, k, c;
   float *net = (float *)malloc((size_t)(J > 0 ? J : 1) * 16 * sizeof(float));
   if (!net) return -2;
   for (j = 0; j < J; ++j) {
     float value[16];
-    int n_eff = 0, only = -1;
+    int n_eff = 0, only = -1, forced = -1;
+    for (c = 0; c < num_forced; ++c)
+      if (forced_joints[c] == j) forced = c;
     for (c = 0; c < K; ++c)
       if (effects[c] != 0.0f && ctrl_skel[c]->has_channel[j]) { ++n_eff; only = c; }
-    if (n_eff == 0) {
+    if (forced >= 0) {
+      memcpy(value, forced_values + (size_t)forced * 16, sizeof(value));
+    } else if (n_eff == 0) {
       memcpy(value, skel->default_value + (size_t)j * 16, sizeof(value));
     } else if (n_eff == 1 && !frame_blend) {
       channel_value(ctrl_skel[only], j, frames[only], value);  /* the single-value case, movingPartMatrix.cxx:71-76 */

@@ -113,6 +113,10 @@ int p3o_pose_blend(const p3o_skeleton *skel, int frame, int next_frame, float fr
  * order = PartBundle's _blend map order. */
 int p3o_pose_controls(const p3o_skeleton *const *ctrl_skel, int K, const int *frames, const int *next_frames, const float *fracs,
                       const float *effects, int frame_blend, int blend_type, float *skinning_out);
+/* ... with forced channels (freeze_joint / control_joint): forced_values[f][16] replaces joint forced_joints[f]'s value */
+int p3o_pose_controls_forced(const p3o_skeleton *const *ctrl_skel, int K, const int *frames, const int *next_frames, const float *fracs,
+                             const float *effects, int frame_blend, int blend_type, int num_forced, const int *forced_joints,
+                             const float *forced_values, float *skinning_out);
 
 /* The slider values of the same controls (MovingPartScalar::get_blend_value, chan/movingPartScalar.cxx:43-105;
  * CharacterSlider::update_internals): no control with a channel -> the default value; exactly one and no frame

@@ -36,6 +36,7 @@ EXPORTED_SYMBOLS = [
     "p3cs_shareable_alloc", "p3cs_shareable_import", "p3cs_shareable_free", "p3cs_group_animate_host",
     "p3cs_hardware_from_blends", "p3cs_blends_from_hardware", "p3cs_group_animate_instances",
     "p3cs_group_pose_blend", "p3cs_skeleton_add_animation", "p3cs_group_pose_controls",
+    "p3cs_group_set_forced_joints", "p3cs_group_set_forced_values",
 ]
 
 
@@ -465,6 +466,20 @@ class Group:
         L.p3cs_group_pose_controls.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
         _check(L.p3cs_group_pose_controls(self.handle, skeleton.handle, first, count, K, packed.ctypes.data,
                                           1 if frame_blend else 0, int(blend_type)))
+
+    def set_forced_joints(self, skeleton, joints) -> None:
+        """p3cs_group_set_forced_joints: PartBundle::freeze_joint / control_joint on these joints (empty = release all)."""
+        j = np.ascontiguousarray(joints, np.int32).reshape(-1)
+        L = lib()
+        L.p3cs_group_set_forced_joints.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        _check(L.p3cs_group_set_forced_joints(self.handle, skeleton.handle, int(j.size), j.ctypes.data if j.size else None))
+
+    def set_forced_values(self, values, first: int = 0) -> None:
+        """p3cs_group_set_forced_values: [count, num_forced, 16] matrices the forced channels return."""
+        v = np.ascontiguousarray(values, np.float32)
+        L = lib()
+        L.p3cs_group_set_forced_values.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        _check(L.p3cs_group_set_forced_values(self.handle, first, int(v.shape[0]), v.ctypes.data))
 
     def read_palettes(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
         count = self.n - first if count is None else count

@@ -165,6 +165,8 @@ extern "C" int p3cs_group_destroy(p3cs_group grp) {
     if (e) cudaEventDestroy(e);
   for (auto e : grp->prof) cudaEventDestroy(e);
   if (grp->frames_dev != nullptr) cudaFree(grp->frames_dev);
+  if (grp->forced_slot_dev != nullptr) cudaFree(grp->forced_slot_dev);
+  if (grp->forced_values_dev != nullptr) cudaFree(grp->forced_values_dev);
   if (grp->list_dev != nullptr) cudaFree(grp->list_dev);
   delete grp;
   return P3CS_OK;
@@ -811,9 +813,13 @@ static int pose_common(p3cs_group grp, p3cs_skeleton sk, int first, int count, c
     return p3cs_fail(P3CS_ERR_INVALID, "skeleton feeds %d palette slots, the mesh has %d transforms", sk->num_palette, grp->mesh->dev.num_transforms);
   if (sk->dev.num_sliders > 0 && sk->dev.num_sliders != grp->mesh->dev.num_sliders)
     return p3cs_fail(P3CS_ERR_INVALID, "skeleton drives %d sliders, the mesh has %d", sk->dev.num_sliders, grp->mesh->dev.num_sliders);
+  if (grp->num_forced > 0 && grp->forced_num_joints != sk->dev.num_joints)
+    return p3cs_fail(P3CS_ERR_INVALID, "%s: the group's forced joints were set for a skeleton of %d joints, this one has %d", what,
+                     grp->forced_num_joints, sk->dev.num_joints);
   if (count == 0) return P3CS_OK;
   DeviceGuard g(grp->mesh->ctx->device);
   cudaStream_t s = grp->mesh->ctx->stream;
+  const ForcedDev forced{grp->forced_slot_dev, grp->forced_values_dev, grp->num_forced};
   const size_t words = states != nullptr ? (size_t)count * num_controls * (sizeof(ControlState) / 4) : (size_t)count;
   if ((size_t)grp->frames_capacity < words) {
     if (grp->frames_dev != nullptr) {
@@ -829,7 +835,7 @@ static int pose_common(p3cs_group grp, p3cs_skeleton sk, int first, int count, c
   launch_pose(sk->dev, const_cast<float *>(grp->dev.palettes), sk->num_palette, const_cast<float *>(grp->dev.sliders),
               states != nullptr ? nullptr : grp->frames_dev,
               states != nullptr ? reinterpret_cast<const ControlState *>(grp->frames_dev) : nullptr, num_controls, frame_blend, blend_type,
-              first, count, s);
+              forced, first, count, s);
   CUDA_TRY(cudaGetLastError());
   return P3CS_OK;
 }
@@ -871,6 +877,52 @@ extern "C" int p3cs_group_pose_controls(p3cs_group grp, p3cs_skeleton sk, int fi
                          host_states[i].anim, sk->dev.num_animations);
   return pose_common(grp, sk, first, count, nullptr, reinterpret_cast<const ControlState *>(host_states), num_controls,
                      frame_blend != 0, blend_type, "p3cs_group_pose_controls");
+}
+
+extern "C" int p3cs_group_set_forced_joints(p3cs_group grp, p3cs_skeleton sk, int num_forced, const int32_t *joints) {
+  if (grp == nullptr || sk == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_set_forced_joints: NULL argument");
+  if (num_forced < 0 || (num_forced > 0 && joints == nullptr)) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_set_forced_joints: bad joint list");
+  const int J = sk->dev.num_joints;
+  std::vector<int> slot((size_t)std::max(J, 1), -1);
+  for (int f = 0; f < num_forced; ++f) {
+    if (joints[f] < 0 || joints[f] >= J) return p3cs_fail(P3CS_ERR_INVALID, "forced joint %d is not a joint of the skeleton (%d joints)", joints[f], J);
+    if (slot[joints[f]] >= 0) return p3cs_fail(P3CS_ERR_INVALID, "joint %d is listed twice", joints[f]);
+    slot[joints[f]] = f;
+  }
+  DeviceGuard g(grp->mesh->ctx->device);
+  cudaStream_t s = grp->mesh->ctx->stream;
+  CUDA_TRY(cudaStreamSynchronize(s));  // a pose kernel in flight may still read the old tables
+  if (grp->forced_slot_dev != nullptr) CUDA_TRY(cudaFree(grp->forced_slot_dev));
+  if (grp->forced_values_dev != nullptr) CUDA_TRY(cudaFree(grp->forced_values_dev));
+  grp->forced_slot_dev = nullptr;
+  grp->forced_values_dev = nullptr;
+  grp->num_forced = 0;
+  grp->forced_num_joints = J;
+  if (num_forced == 0) return P3CS_OK;
+  CUDA_TRY(cudaMalloc(&grp->forced_slot_dev, slot.size() * sizeof(int)));
+  CUDA_TRY(cudaMemcpyAsync(grp->forced_slot_dev, slot.data(), slot.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  // every instance starts with identity values
+  std::vector<float> ident((size_t)grp->n * num_forced * 16, 0.0f);
+  for (size_t i = 0; i < (size_t)grp->n * num_forced; ++i) ident[i * 16] = ident[i * 16 + 5] = ident[i * 16 + 10] = ident[i * 16 + 15] = 1.0f;
+  CUDA_TRY(cudaMalloc(&grp->forced_values_dev, std::max<size_t>(ident.size(), 1) * sizeof(float)));
+  CUDA_TRY(cudaMemcpyAsync(grp->forced_values_dev, ident.data(), ident.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  grp->num_forced = num_forced;
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_group_set_forced_values(p3cs_group grp, int first, int count, const float *host_values) {
+  int rc = check_span(grp, first, count, "p3cs_group_set_forced_values");
+  if (rc != P3CS_OK) return rc;
+  if (grp->num_forced == 0) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_set_forced_values: the group has no forced joints");
+  if (count == 0) return P3CS_OK;
+  if (host_values == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_set_forced_values: values are NULL");
+  DeviceGuard g(grp->mesh->ctx->device);
+  cudaStream_t s = grp->mesh->ctx->stream;
+  const size_t per = (size_t)grp->num_forced * 16;
+  CUDA_TRY(cudaMemcpyAsync(grp->forced_values_dev + (size_t)first * per, host_values, (size_t)count * per * sizeof(float), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));  // the host buffer is the caller's again on return
+  return P3CS_OK;
 }
 
 extern "C" int p3cs_group_read_palettes(p3cs_group grp, int first, int count, float *host_dst) {

@@ -132,10 +132,18 @@ struct ControlState {
   float frac, effect;
 };
 
+// Forced channels of a group (PartBundle::freeze_joint / control_joint): slot[j] = index of joint j among the forced
+// ones or -1; values[instance][count][16] = what the forced channel returns for that instance (absolute instance index).
+struct ForcedDev {
+  const int *slot;
+  const float *values;
+  int count;
+};
+
 // frames_dev != nullptr: one control of animation 0 per instance, no blending.  Else states_dev[count][num_controls].
 void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, float *sliders, const int *frames_dev,
-                 const ControlState *states_dev, int num_controls, int frame_blend, int blend_type, int first_instance, int count,
-                 cudaStream_t stream);
+                 const ControlState *states_dev, int num_controls, int frame_blend, int blend_type, const ForcedDev &forced,
+                 int first_instance, int count, cudaStream_t stream);
 
 void launch_blend(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);
 void launch_skin(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);

@@ -136,7 +136,7 @@ __device__ __forceinline__ float slider_channel_value(const AnimationDev &an, in
 template <bool BLEND>
 __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *palettes, int num_transforms, float *sliders, const int *frames,
                                                     const ControlState *states, int num_controls, int frame_blend, int blend_type,
-                                                    int first_instance) {
+                                                    ForcedDev forced, int first_instance) {
   extern __shared__ float smem_pose[];  // [J][16] local values, then [J][16] net transforms of this instance
   const int inst = first_instance + blockIdx.x;
   const int J = skel.num_joints;
@@ -185,7 +185,17 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
   for (int j = threadIdx.x; j < J; j += blockDim.x) {
     float value[16];
     bool have = false;
-    if (!BLEND) {
+    // a forced channel (freeze_joint / control_joint) wins over whatever is playing (movingPartMatrix.cxx:53-60)
+    const int fslot = forced.count > 0 ? __ldg(forced.slot + j) : -1;
+    if (fslot >= 0) {
+      const float4 *fv = reinterpret_cast<const float4 *>(forced.values + ((size_t)inst * forced.count + fslot) * 16);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 q = __ldg(fv + r);
+        value[r * 4] = q.x; value[r * 4 + 1] = q.y; value[r * 4 + 2] = q.z; value[r * 4 + 3] = q.w;
+      }
+      have = true;
+    } else if (!BLEND) {
       if (__ldg(skel.anim[0].has_channel + j)) {
         channel_value(skel.anim[0], cs, j, __ldg(frames + blockIdx.x), false, value);
         have = true;
@@ -347,8 +357,8 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
 }
 
 void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, float *sliders, const int *frames_dev,
-                 const ControlState *states_dev, int num_controls, int frame_blend, int blend_type, int first_instance, int count,
-                 cudaStream_t stream) {
+                 const ControlState *states_dev, int num_controls, int frame_blend, int blend_type, const ForcedDev &forced,
+                 int first_instance, int count, cudaStream_t stream) {
   if (count == 0 || skel.num_joints == 0) return;
   const size_t smem = (size_t)skel.num_joints * 128;
   int threads = ((skel.num_joints + 31) / 32) * 32;
@@ -356,11 +366,11 @@ void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, f
   if (states_dev != nullptr) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(pose_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     pose_kernel<true><<<count, threads, smem, stream>>>(skel, palettes, num_transforms, sliders, nullptr, states_dev, num_controls, frame_blend,
-                                                        blend_type, first_instance);
+                                                        blend_type, forced, first_instance);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(pose_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     pose_kernel<false><<<count, threads, smem, stream>>>(skel, palettes, num_transforms, sliders, frames_dev, nullptr, 0, 0, blend_type,
-                                                         first_instance);
+                                                         forced, first_instance);
   }
 }
 

@@ -109,6 +109,12 @@ def main():
         subprocess.run([HARNESS, "egg", model, anim, out, "0.5", "10.25", "37.0", "58.75", "3.999"], check=True, timeout=120,
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env={**os.environ, **env})
         print("wrote", out, os.path.getsize(out))
+    # forced channels: PartBundle::freeze_joint on joints 6 and 24, control_joint on joint 29 (its node moves every sample)
+    for suffix, frames_ in (("", ["0", "10", "37"]), ("_frame_blend", ["0.5", "10.25", "37.0"])):
+        out = os.path.join(HERE, "skeleton", f"panda_walk4_forced{suffix}.p3cs")
+        subprocess.run([HARNESS, "egg", model, anim, out] + frames_, check=True, timeout=120, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, env={**os.environ, "P3CS_FREEZE": "6,24", "P3CS_CONTROL": "29"})
+        print("wrote", out, os.path.getsize(out))
     # two AnimControls blended by their effects (PartBundle::set_anim_blend_flag): hold-frame and frame-blend, both blend types
     samples_hold = ["3:0.7,20:0.3", "10:1.0,40:0.0", "0:0.5,59:0.5", "17:0.2,18:1.3"]
     samples_blend = ["3.5:0.7,20.25:0.3", "10.75:1.0,40:0.0", "5.5:0.25,33.25:0.75"]

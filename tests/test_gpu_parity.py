@@ -872,6 +872,56 @@ def test_componentwise_blends_in_every_coordinate_system(gpu_ctx, cs, bt):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fixture", ["panda_walk4_forced", "panda_walk4_forced_frame_blend"])
+def test_joint_hierarchy_with_forced_channels(gpu_ctx, fixture):
+    """f1 with PartBundle::freeze_joint (two joints) and control_joint (a third, its node moving every frame):
+    p3cs_group_set_forced_joints / p3cs_group_set_forced_values + the pose calls reproduce the reference's skinning
+    matrices and animated vertices; releasing the joints gives the plain animation back."""
+    from conftest import GOLDEN_DIR
+    from panda3d_b200.flat import skeleton_from_case
+    case = load_case(os.path.join(GOLDEN_DIR, "skeleton", fixture + ".p3cs"))
+    plain = load_case(os.path.join(GOLDEN_DIR, "panda_walk4.p3cs"))
+    mesh, skel = mesh_from_case(case), skeleton_from_case(case)
+    frames = case["anim_frames"]
+    fb = "anim_next_frames" in case
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    dskel = _capi.Skeleton(gpu_ctx, skel)
+    grp = _capi.Group(dmesh, len(frames))
+    try:
+        grp.set_forced_joints(dskel, case["forced_joints"])
+        grp.set_forced_values(case["forced_values"])
+        if fb:
+            grp.pose_blend(dskel, frames, case["anim_next_frames"], case["anim_fracs"], int(case["anim_blend_type"][0]))
+        else:
+            grp.pose(dskel, frames)
+        pal = grp.read_palettes()
+        ref = case["palette"]
+        scale = np.abs(ref).max(axis=(1, 2), keepdims=True)
+        assert (np.abs(pal - ref) / scale).max() <= REL_TOL
+        grp.animate()
+        out = grp.read_output(0)
+        for fi in range(len(frames)):
+            compare_outputs(mesh, [out[fi]], [case["expect0"][fi]], f"{fixture} frame {frames[fi]}")
+        with pytest.raises(_capi.P3csError):
+            grp.set_forced_joints(dskel, [3, 3])
+        with pytest.raises(_capi.P3csError):
+            grp.set_forced_joints(dskel, [skel.num_joints])
+        if not fb:   # release_joint: frames 0 / 10 / 37 of the plain fixture
+            grp.set_forced_joints(dskel, [])
+            grp.pose(dskel, frames)
+            pal = grp.read_palettes()
+            ref = plain["palette"][:3]
+            assert list(plain["anim_frames"][:3]) == list(frames)
+            assert (np.abs(pal - ref) / np.abs(ref).max(axis=(1, 2), keepdims=True)).max() <= REL_TOL
+            with pytest.raises(_capi.P3csError):
+                grp.set_forced_values(case["forced_values"])
+    finally:
+        grp.close()
+        dskel.close()
+        dmesh.close()
+
+
+@pytest.mark.gpu
 def test_plain_c_host_animates_through_the_plugin_table(tmp_path):
     """examples/plugin_host.c --run: a C99 host (dlopen + p3cs_get_api, no Python, no torch) skins the survey's
     four-vertex probe: (2,4,1) under 0.25*T(1,2,3) + 0.75*S(2) -> (3.75, 7.5, 2.5)."""

@@ -101,6 +101,28 @@ def test_oracle_pose_with_frame_blending_matches_reference(fixture):
         assert np.array_equal(outs[0].reshape(-1), np.asarray(case["expect0"][fi]).reshape(-1))
 
 
+@pytest.mark.parametrize("fixture", ["panda_walk4_forced", "panda_walk4_forced_frame_blend"])
+def test_oracle_pose_with_forced_channels_matches_reference(fixture):
+    """PartBundle::freeze_joint on two joints and control_joint on a third (oracle/ref_harness.cxx, P3CS_FREEZE /
+    P3CS_CONTROL): a joint with a forced channel takes that channel's value whatever is playing
+    (chan/movingPartMatrix.cxx:53-60); the oracle reproduces the reference's skinning matrices bit for bit."""
+    import os
+    from conftest import GOLDEN_DIR
+    from panda3d_b200.flat import skeleton_from_case
+    case = load_case(os.path.join(GOLDEN_DIR, "skeleton", fixture + ".p3cs"))
+    skel = skeleton_from_case(case)
+    fb = "anim_next_frames" in case
+    bt = int(case["anim_blend_type"][0]) if fb else 1
+    assert case["forced_joints"].size == 3
+    for fi, frame in enumerate(case["anim_frames"]):
+        nxt = case["anim_next_frames"][fi] if fb else frame
+        frac = case["anim_fracs"][fi] if fb else 0.0
+        skin = oracle.pose_controls([skel], [frame], [nxt], [frac], [1.0], fb, bt, case["forced_joints"], case["forced_values"][fi])
+        assert np.array_equal(skin[skel.palette_joint].view(np.uint32), case["palette"][fi].view(np.uint32)), f"frame {frame}"
+        plain = oracle.pose_controls([skel], [frame], [nxt], [frac], [1.0], fb, bt)
+        assert not np.array_equal(plain[skel.palette_joint], case["palette"][fi])
+
+
 MULTI = ["panda_walk4_two_controls_hold", "panda_walk4_two_controls_hold_linear", "panda_walk4_two_controls_hold_componentwise",
          "panda_walk4_two_controls_frame_blend", "panda_walk4_two_controls_frame_blend_linear",
          "panda_walk4_two_controls_frame_blend_componentwise", "panda_walk4_two_controls_hold_componentwise_quat",
