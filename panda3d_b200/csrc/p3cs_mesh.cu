@@ -5,6 +5,7 @@
 #include "p3cs_internal.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdint>
 #include <cstring>
 #include <new>
@@ -39,7 +40,9 @@ static int check_ranges(const int32_t *ranges, int count, int num_rows, const ch
 // collide when their joints differ but agree modulo 8 (48-byte palette rows).  The order of a group's
 // records is free (rows address them through their slot), so they are packed first-fit into
 // eight-lane cells whose k-th joints are pairwise distinct modulo 8 (or equal: a broadcast).
-static void pack_group(const p3cs_mesh_desc *d, std::vector<int> &blends, long long *budget) {
+// `windows`: for every half-warp of rows (16 consecutive rows of the group) the positions in `blends` of the records
+// those rows select -- the records one phase-B record read touches together.
+static void pack_group(const p3cs_mesh_desc *d, std::vector<int> &blends, long long *budget, const std::vector<std::vector<int>> &windows) {
   const int n = (int)blends.size();
   const int cells = (n + 7) / 8;
   std::vector<int> occ((size_t)cells * 32, -1), fill(cells, 0), cell_of(n, -1);
@@ -157,24 +160,78 @@ static void pack_group(const p3cs_mesh_desc *d, std::vector<int> &blends, long l
     for (int c = 0; c < cells; ++c)
       for (int rec : members[c]) cell_of[rec] = c;
   }
-  // Lane inside the cell.  Phase B reads a row's record with 64-bit loads, sixteen rows per wavefront; the
-  // records of neighbouring runs (adjacent in first-seen order) collide there when their slots agree
-  // modulo 16, so each record takes a free lane whose slot differs from its three predecessors' modulo 16.
+  // Lane inside the cell.  Phase B reads a row's record with 64-bit loads, sixteen rows per wavefront; two records read
+  // by the same half-warp collide there when their slots agree modulo 16 (record stride = an odd number of 8-byte
+  // units).  The records that meet in a half-warp are known (`windows`), so this is a colouring of that graph with the
+  // 16 residues, greedy in first-seen order: each record takes the free lane of its cell whose slot collides with the
+  // fewest already placed neighbours.
+  std::vector<std::vector<int>> nbr(n);
+  for (const std::vector<int> &w : windows)
+    for (int a : w)
+      for (int b : w)
+        if (a != b) nbr[a].push_back(b);
   std::vector<int> slot_of(n, -1);
   std::vector<uint8_t> used((size_t)cells, 0);
   for (int i = 0; i < n; ++i) {
     const int c = cell_of[i];
-    int best = -1;
-    for (int pass = 0; pass < 2 && best < 0; ++pass)
-      for (int p = 0; p < count_in[c]; ++p) {
-        if ((used[c] >> p) & 1) continue;
-        const int sl = 8 * c + p;
-        bool clash = false;  // against the records of the three preceding runs (a half-warp of rows spans about that many)
-        for (int back = 1; back <= 3 && back <= i; ++back) clash = clash || ((slot_of[i - back] ^ sl) & 15) == 0;
-        if (pass == 1 || !clash) { best = p; break; }
+    int best = -1, best_cost = 1 << 30;
+    for (int p = 0; p < count_in[c]; ++p) {
+      if ((used[c] >> p) & 1) continue;
+      const int sl = 8 * c + p;
+      int cost = 0;
+      for (int o : nbr[i])
+        if (slot_of[o] >= 0 && ((slot_of[o] ^ sl) & 15) == 0) ++cost;
+      if (cost < best_cost) {
+        best_cost = cost;
+        best = p;
+        if (cost == 0) break;
       }
+    }
     used[c] |= (uint8_t)(1u << best);
     slot_of[i] = 8 * c + best;
+  }
+  // ... then improved by swapping the lanes of two records of one cell while that lowers the number of collisions
+  {
+    auto cost_at = [&](int i, int sl, int ignore) {
+      int cost = 0;
+      for (int o : nbr[i])
+        if (o != ignore && ((slot_of[o] ^ sl) & 15) == 0) ++cost;
+      return cost;
+    };
+    std::vector<std::vector<int>> members(cells);
+    for (int i = 0; i < n; ++i) members[cell_of[i]].push_back(i);
+    for (int pass = 0; pass < 4; ++pass) {
+      bool improved = false;
+      for (int i = 0; i < n; ++i) {
+        const int ci = cost_at(i, slot_of[i], -1);
+        if (ci == 0) continue;
+        int best_k = -1, best_delta = 0;
+        for (int k : members[cell_of[i]]) {
+          if (k == i) continue;
+          const int before = ci + cost_at(k, slot_of[k], -1);
+          const int after = cost_at(i, slot_of[k], k) + cost_at(k, slot_of[i], i);
+          if (after - before < best_delta) {
+            best_delta = after - before;
+            best_k = k;
+          }
+        }
+        if (best_k >= 0) {
+          std::swap(slot_of[i], slot_of[best_k]);
+          improved = true;
+        }
+      }
+      if (!improved) break;
+    }
+  }
+  if (getenv("P3CS_DEBUG_PACK") != nullptr) {  // predicted extra wavefronts of the record reads, by window
+    long long extra = 0;
+    for (const std::vector<int> &w : windows) {
+      int cnt[16] = {0};
+      int worst = 0;
+      for (int a : w) worst = std::max(worst, ++cnt[slot_of[a] & 15]);
+      extra += worst - 1;
+    }
+    fprintf(stderr, "pack_group: %d records, %zu windows, predicted extra wavefronts per record load %lld\n", n, windows.size(), extra);
   }
   std::vector<int> ordered(n);
   for (int i = 0; i < n; ++i) ordered[slot_of[i]] = blends[i];
@@ -214,8 +271,24 @@ static StripTables build_record_groups(const p3cs_mesh_desc *d, const std::vecto
   auto row_live = [&](int r) { return mask.empty() || ((mask[r >> 5] >> (r & 31)) & 1u); };
   auto row_blend = [&](int r) { return (int)row_index[r]; };
 
+  std::vector<int> pos_in_open(std::max(d->num_blends, 1), -1);
   auto close_group = [&](int t_end) {
-    pack_group(d, open, &pack_budget);
+    // the records each half-warp of rows reads together (distinct, as positions in `open`)
+    std::vector<std::vector<int>> windows;
+    {
+      for (size_t p = 0; p < open.size(); ++p) pos_in_open[open[p]] = (int)p;
+      const int w0 = tile_off.back() * kTileRows, w1 = std::min(N, t_end * kTileRows);
+      for (int base = w0; base < w1; base += 16) {
+        std::vector<int> w;
+        for (int r = base; r < std::min(w1, base + 16); ++r) {
+          if (!row_live(r)) continue;
+          const int q = pos_in_open[row_blend(r)];
+          if (std::find(w.begin(), w.end(), q) == w.end()) w.push_back(q);
+        }
+        if (w.size() > 1) windows.push_back(std::move(w));
+      }
+    }
+    pack_group(d, open, &pack_budget, windows);
     const int n = (int)open.size();
     for (int p = 0; p < n; ++p) {
       const int b = open[p];
