@@ -31,6 +31,9 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line: whatever NCCL_DEBUG makes NCCL say ("NCCL version ...") goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
