@@ -31,8 +31,14 @@ import time
 
 import numpy as np
 
-# stdout carries exactly one JSON line: whatever NCCL_DEBUG makes NCCL say ("NCCL version ...") goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line: file descriptor 1 is pointed at stderr for the whole run (NCCL prints its
+# "NCCL version ..." banner there from native code) and the line is written to the saved descriptor at the end
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -188,7 +194,7 @@ def run_reference_arm(args):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -467,7 +473,7 @@ def run_gpu_arm(args):
             "gpu_launches": launches_per_step * args.steps, "clocks": sampler.summary(), "check": check,
             "gather": gather, "fused_gather": fused, "joints_on_gpu": joints, "tight_bounds": bounds, "other_configs": others,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     grp.close()
     dmesh.close()
     ctx.close()
