@@ -432,6 +432,11 @@ P3CS_EXPORT int p3cs_group_read_palettes(p3cs_group group, int first, int count,
  * every instance.  NaN components never win a comparison, as with std::min/max there.
  * p3cs_group_enable_bounds(group, NULL) switches it off again. */
 P3CS_EXPORT int p3cs_group_enable_bounds(p3cs_group group, const p3cs_column_desc *vertex_column);
+/* Restricts the bounds to the rows the Geom's primitives reference -- GeomPrimitive::calc_tight_bounds walks the
+ * primitive's vertex indices (gobj/geomPrimitive.cxx:1646-1830, indexed branch), so an unreferenced vertex does not
+ * count: bit (r & 31) of host_row_bits[r >> 5] = row r is referenced ((rows + 31) / 32 words, copied).  NULL = every
+ * row again. */
+P3CS_EXPORT int p3cs_group_set_bounds_rows(p3cs_group group, const uint32_t *host_row_bits);
 /* count x 8 floats: min x y z, max x y z, sq_center_dist (max |v|^2), found_any (1.0 / 0.0); of the
  * last p3cs_group_animate.  Synchronous. */
 P3CS_EXPORT int p3cs_group_read_bounds(p3cs_group group, int first, int count, float *host_dst);

@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = [
     "p3cs_shareable_alloc", "p3cs_shareable_import", "p3cs_shareable_free", "p3cs_group_animate_host",
     "p3cs_hardware_from_blends", "p3cs_blends_from_hardware", "p3cs_group_animate_instances",
     "p3cs_group_pose_blend", "p3cs_skeleton_add_animation", "p3cs_group_pose_controls",
-    "p3cs_group_set_forced_joints", "p3cs_group_set_forced_values",
+    "p3cs_group_set_forced_joints", "p3cs_group_set_forced_values", "p3cs_group_set_bounds_rows",
 ]
 
 
@@ -496,6 +496,18 @@ class Group:
         col = vertex_column if vertex_column is not None else self.mesh.flat.skin_columns[0]
         desc = _ColumnDesc(*col.as_tuple())
         _check(lib().p3cs_group_enable_bounds(self.handle, C.byref(desc)))
+
+    def set_bounds_rows(self, referenced=None) -> None:
+        """p3cs_group_set_bounds_rows: `referenced` = bool per row (the vertices the Geom's primitives index); None = all."""
+        L = lib()
+        L.p3cs_group_set_bounds_rows.argtypes = [C.c_void_p, C.c_void_p]
+        if referenced is None:
+            _check(L.p3cs_group_set_bounds_rows(self.handle, None))
+            return
+        r = np.asarray(referenced, bool).reshape(-1)
+        assert r.size == self.mesh.flat.num_rows
+        bits = np.packbits(np.pad(r, (0, (-r.size) % 32)), bitorder="little").view(np.uint32).copy()
+        _check(L.p3cs_group_set_bounds_rows(self.handle, bits.ctypes.data))
 
     def read_bounds(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
         """[count, 8]: min xyz, max xyz, max |v|^2, found_any -- of the last animate()."""

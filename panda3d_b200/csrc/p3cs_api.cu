@@ -166,6 +166,7 @@ extern "C" int p3cs_group_destroy(p3cs_group grp) {
   for (auto e : grp->prof) cudaEventDestroy(e);
   if (grp->frames_dev != nullptr) cudaFree(grp->frames_dev);
   if (grp->forced_slot_dev != nullptr) cudaFree(grp->forced_slot_dev);
+  if (grp->bounds_rows_dev != nullptr) cudaFree(grp->bounds_rows_dev);
   if (grp->forced_values_dev != nullptr) cudaFree(grp->forced_values_dev);
   if (grp->list_dev != nullptr) cudaFree(grp->list_dev);
   delete grp;
@@ -542,6 +543,24 @@ extern "C" int p3cs_group_enable_bounds(p3cs_group grp, const p3cs_column_desc *
   grp->dev.bounds = grp->bounds_buf;
   grp->dev.bounds_output = o;
   grp->dev.bounds_start = c.start;
+  return P3CS_OK;
+}
+
+extern "C" int p3cs_group_set_bounds_rows(p3cs_group grp, const uint32_t *host_row_bits) {
+  if (grp == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_set_bounds_rows: group is NULL");
+  ++grp->epoch;
+  DeviceGuard g(grp->mesh->ctx->device);
+  cudaStream_t s = grp->mesh->ctx->stream;
+  if (host_row_bits == nullptr) {  // back to "every row"; the buffer stays until the group goes
+    grp->dev.bounds_rows = nullptr;
+    return P3CS_OK;
+  }
+  const size_t words = ((size_t)grp->mesh->dev.num_rows + 31) / 32;
+  if (grp->bounds_rows_dev == nullptr) CUDA_TRY(cudaMalloc(&grp->bounds_rows_dev, std::max<size_t>(words, 1) * 4));
+  else CUDA_TRY(cudaStreamSynchronize(s));  // an animate in flight may still read the old bits
+  CUDA_TRY(cudaMemcpyAsync(grp->bounds_rows_dev, host_row_bits, words * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  grp->dev.bounds_rows = grp->bounds_rows_dev;
   return P3CS_OK;
 }
 

@@ -65,6 +65,7 @@ struct p3cs_group_s {
   int list_capacity = 0;
   int *frames_dev = nullptr;  // per-instance animation frames of the last p3cs_group_pose
   int frames_capacity = 0;
+  uint32_t *bounds_rows_dev = nullptr;  // p3cs_group_set_bounds_rows
   int *forced_slot_dev = nullptr;      // p3cs_group_set_forced_joints: [joints of the skeleton] slot or -1
   float *forced_values_dev = nullptr;  // [n][num_forced][16]
   int num_forced = 0, forced_num_joints = 0;

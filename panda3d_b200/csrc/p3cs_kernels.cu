@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) bounds_scan_kernel(MeshDev mesh, GroupDev
   acc.reset();
   for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
     const float *c = reinterpret_cast<const float *>(base + (size_t)r * mesh.stride[o]);
-    acc.add(c[0], c[1], c[2]);
+    if (bounds_wants(grp, r)) acc.add(c[0], c[1], c[2]);
   }
   bounds_commit(acc, scratch, grp.bounds + (size_t)inst * 8, false, threadIdx.x, blockDim.x);
 }

@@ -92,7 +92,13 @@ struct GroupDev {
   int bounds_start;       // its byte offset in the row
   // optional: the instances to animate (p3cs_group_animate_instances); NULL = first_instance + blockIdx.y
   const int *instance_list;
+  // optional: bit r = row r is referenced by a primitive and counts for the bounds (p3cs_group_set_bounds_rows); NULL = every row
+  const uint32_t *bounds_rows;
 };
+
+__device__ __forceinline__ bool bounds_wants(const GroupDev &grp, int row) {
+  return grp.bounds_rows == nullptr || ((__ldg(grp.bounds_rows + (row >> 5)) >> (row & 31)) & 1u) != 0;
+}
 
 // Joint hierarchy ("next" row f1): static description of a character's skeleton, joints parents-first.
 constexpr int kMaxAnimations = 8;  // animations (channel-table sets) one skeleton can hold

@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
                 if (L::T >= 0) fast_column<2>(v + kRowT<L>(), f);
                 if (L::B >= 0) fast_column<2>(v + kRowB<L>(), f);
               }
-              if (BOUNDS && bounds_off == 0) bounds.add(v[0], v[1], v[2]);
+              if (BOUNDS && bounds_off == 0 && bounds_wants(grp, row)) bounds.add(v[0], v[1], v[2]);
               row_store<L>(rowp, trow, v);
             }
           } else if (MORPH && row < mesh.num_rows) {
@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
               if (L::N >= 0) fast_column<3>(v + (L::N >= 0 ? L::N : 0), f);
               if (L::T >= 0) fast_column<2>(v + (L::T >= 0 ? L::T : 0), f);
               if (L::B >= 0) fast_column<2>(v + (L::B >= 0 ? L::B : 0), f);
-              if (BOUNDS && bounds_off == 0) bounds.add(v[0], v[1], v[2]);  // the vertex column, straight from the registers
+              if (BOUNDS && bounds_off == 0 && bounds_wants(grp, row)) bounds.add(v[0], v[1], v[2]);  // the vertex column, straight from the registers
               row_store<L>(rowp, trow, v);
             } else {
               uint8_t *rowp = tile + trow * stride0;
@@ -751,7 +751,7 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
         for (int rr = 0; rr < kRowsPerThread; ++rr) {
           const int trow = rr * kStripThreads + tid;
           const bool in_registers = ROWREG && bounds_off == 0 && (local[rr] != 0xFFFF || (MORPH && me[rr] > mb[rr]));
-          if (t * kTileRows + trow < mesh.num_rows && !in_registers) {
+          if (t * kTileRows + trow < mesh.num_rows && !in_registers && bounds_wants(grp, t * kTileRows + trow)) {
             const float *c = reinterpret_cast<const float *>(tile + bounds_off + (size_t)trow * bounds_stride);
             bounds.add(c[0], c[1], c[2]);
           }

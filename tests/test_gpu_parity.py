@@ -559,6 +559,49 @@ def test_animated_tight_bounds(gpu_ctx, monkeypatch, path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("path", ["strip", "wide"])
+@pytest.mark.parametrize("layout", ["packed", "tbn_morph"])
+def test_tight_bounds_over_referenced_rows_only(gpu_ctx, monkeypatch, path, layout):
+    """f4, indexed primitives: GeomPrimitive::calc_tight_bounds walks the vertices the primitive references
+    (gobj/geomPrimitive.cxx:1646-1830), so rows no primitive indexes must not widen the bounds --
+    p3cs_group_set_bounds_rows; exact against a CPU walk over the referenced rows of the kernel's own output."""
+    monkeypatch.setenv("P3CS_PATH", path)
+    kw = dict(tbn=True, num_sliders=3, slider_band=0.3) if layout == "tbn_morph" else {}
+    sm = synth.make_mesh(5_003, 24, 400, seed=91, index_order="runs", **kw)
+    mesh = sm.flat
+    rng = np.random.default_rng(92)
+    referenced = rng.uniform(size=mesh.num_rows) < 0.4
+    referenced[4990:] = False
+    # the extreme vertices are exactly the unreferenced ones
+    f = mesh.arrays[0][:, :12].copy().view(np.float32).reshape(-1, 3)
+    f[~referenced] *= 50.0
+    mesh.arrays[0][:, :12] = f.view(np.uint8).reshape(-1, 12)
+    n = 40
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, n)
+    try:
+        grp.set_palettes(synth.make_palettes(24, n, 93).reshape(n, -1))
+        if mesh.num_sliders:
+            grp.set_sliders(synth.make_sliders(3, n, 94))
+        grp.enable_bounds()
+        grp.set_bounds_rows(referenced)
+        grp.animate()
+        got, out = grp.read_bounds(), grp.read_output(0)
+        for i in (0, 7, n - 1):
+            assert np.array_equal(got[i], _expected_bounds(out[i][referenced], mesh.skin_columns[0])), f"instance {i}"
+            assert not np.array_equal(got[i], _expected_bounds(out[i], mesh.skin_columns[0]))
+        grp.set_bounds_rows(None)
+        grp.animate()
+        assert np.array_equal(grp.read_bounds()[3], _expected_bounds(grp.read_output(0)[3], mesh.skin_columns[0]))
+        grp.set_bounds_rows(np.zeros(mesh.num_rows, bool))   # nothing referenced: found_any stays 0
+        grp.animate()
+        assert grp.read_bounds()[0][7] == 0.0
+    finally:
+        grp.close()
+        dmesh.close()
+
+
+@pytest.mark.gpu
 def test_animate_groups_mixed_crowd(gpu_ctx):
     """p3cs_animate_groups (independent groups forked over side streams) == animating the groups one by one,
     byte for byte, on a C5-style mixed crowd of 6 character types (more groups than side streams)."""
