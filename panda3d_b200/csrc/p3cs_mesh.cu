@@ -485,7 +485,8 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
       m.tile_bufs = 3;
       m.group_record_cap = full_cap;
       if (!m.full_records || m.aligned) {
-        if (fits(2, 2, full_cap)) {
+        const char *force_r = getenv("P3CS_ROWS_PER_THREAD");  // tuning aid: "1" keeps 256-row tiles
+        if (fits(2, 2, full_cap) && !(force_r != nullptr && atoi(force_r) == 1)) {
           m.rows_per_thread = 2;
           m.tile_bufs = 2;
         } else if (fits(1, 3, full_cap)) {
