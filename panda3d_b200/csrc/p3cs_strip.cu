@@ -61,11 +61,16 @@ static int strip_partition(const MeshDev &mesh, int count, int sm_count, int *gr
   if (gpc > mesh.num_groups) gpc = mesh.num_groups;
   const int strips = (mesh.num_groups + (int)gpc - 1) / (int)gpc;
   *groups_per_cta = (mesh.num_groups + strips - 1) / strips;  // equal-length strips
-  // Few CTAs in the whole launch (a single small mesh): split every group's tiles over several CTAs, which is
-  // encoded as a negative groups_per_cta (see strip_kernel).
-  if (*groups_per_cta == 1 && (long long)strips * count * 2 <= sm_count && mesh.num_groups > 0) {
+  // Few CTAs in the whole launch (a single mesh, fewer than two CTAs per SM): split every group's tiles over several
+  // CTAs, up to about four CTAs per SM, which is encoded as a negative groups_per_cta (see strip_kernel).
+  static const int split_target = [] {  // CTAs per SM below which groups are split (P3CS_STRIP_SPLIT_PER_SM: tuning aid)
+    const char *e = getenv("P3CS_STRIP_SPLIT_PER_SM");
+    const int v = e != nullptr ? atoi(e) : 0;
+    return v > 0 ? v : 4;  // measured: the 250 k-vertex morph mesh 28.2 -> 24.4 us; nothing gained beyond, small crowds lose at 6
+  }();
+  if (*groups_per_cta == 1 && (long long)strips * count * 2 <= (long long)sm_count * split_target && mesh.num_groups > 0) {
     const int tiles_per_group = (mesh.num_tiles + mesh.num_groups - 1) / mesh.num_groups;
-    int split = (int)(sm_count / ((long long)strips * count));
+    int split = (int)(((long long)sm_count * split_target) / ((long long)strips * count));
     if (split > tiles_per_group) split = tiles_per_group;
     if (split > 1) {
       *groups_per_cta = -split;
