@@ -143,6 +143,17 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
   float *local = smem_pose;
   float *net = smem_pose + (size_t)J * 16;
   const int cs = skel.coordinate_system;
+  // The tree's level structure goes to shared memory first: the level loop below is a chain of barriers, and three
+  // dependent global loads per level (range, joint, parent) were most of its length.
+  int *s_order = reinterpret_cast<int *>(smem_pose + (size_t)J * 32);  // [J] joints sorted by level
+  int *s_parent = s_order + J;                                         // [J] parent of s_order[k]
+  int *s_begin = s_parent + J;                                         // [max_level + 2] level ranges
+  for (int k = threadIdx.x; k < J; k += blockDim.x) {
+    const int j = __ldg(skel.level_order + k);
+    s_order[k] = j;
+    s_parent[k] = __ldg(skel.parent + j);
+  }
+  for (int l = threadIdx.x; l < skel.max_level + 2; l += blockDim.x) s_begin[l] = __ldg(skel.level_begin + l);
 
   // morph sliders: CharacterSlider's value from its scalar channel(s) (MovingPartScalar::get_blend_value,
   // chan/movingPartScalar.cxx:43-105): same selection rule as the joints; the blend is a plain weighted sum from
@@ -323,10 +334,10 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
   // phase 2, level by level: _net_transform = _value * parent's _net_transform (or the root transform).
   // Joints are stored sorted by level, so level L is the contiguous range [level_begin[L], level_begin[L+1]).
   for (int level = 0; level <= skel.max_level; ++level) {
-    const int lb = __ldg(skel.level_begin + level), le = __ldg(skel.level_begin + level + 1);
+    const int lb = s_begin[level], le = s_begin[level + 1];
     for (int k = lb + threadIdx.x; k < le; k += blockDim.x) {
-      const int j = __ldg(skel.level_order + k);
-      const int parent = __ldg(skel.parent + j);
+      const int j = s_order[k];
+      const int parent = s_parent[k];
       float value[16], par[16], out[16];
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
@@ -360,7 +371,7 @@ void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, f
                  const ControlState *states_dev, int num_controls, int frame_blend, int blend_type, const ForcedDev &forced,
                  int first_instance, int count, cudaStream_t stream) {
   if (count == 0 || skel.num_joints == 0) return;
-  const size_t smem = (size_t)skel.num_joints * 128;
+  const size_t smem = (size_t)skel.num_joints * 128 + ((size_t)skel.num_joints * 2 + skel.max_level + 2) * sizeof(int);
   int threads = ((skel.num_joints + 31) / 32) * 32;
   if (threads > 256) threads = 256;
   if (states_dev != nullptr) {
