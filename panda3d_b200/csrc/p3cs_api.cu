@@ -757,6 +757,21 @@ extern "C" int p3cs_skeleton_create(p3cs_context ctx, const p3cs_skeleton_desc *
   }
   if ((rc = upload_skel<int>(sk, order.data(), J, &s.level_order)) != P3CS_OK) return bail(rc);
   if ((rc = upload_skel<int>(sk, begin.data(), begin.size(), &s.level_begin)) != P3CS_OK) return bail(rc);
+  {
+    // every joint's chain of ancestors, outermost first: the kernel multiplies down the chain per joint instead of
+    // synchronising the CTA once per tree level
+    std::vector<int> poff((size_t)J + 1, 0), pj;
+    std::vector<int> chain;
+    for (int j = 0; j < J; ++j) {
+      chain.clear();
+      for (int a = j; a >= 0; a = d->parent[a]) chain.push_back(a);
+      pj.insert(pj.end(), chain.rbegin(), chain.rend());
+      poff[j + 1] = (int)pj.size();
+    }
+    if (pj.empty()) pj.push_back(0);
+    if ((rc = upload_skel<int>(sk, poff.data(), poff.size(), &s.path_offsets)) != P3CS_OK) return bail(rc);
+    if ((rc = upload_skel<int>(sk, pj.data(), pj.size(), &s.path_joints)) != P3CS_OK) return bail(rc);
+  }
   s.num_animations = 1;  // animation 0: the channel tables of the descriptor
   if ((rc = upload_skel<int>(sk, d->has_channel, J, &s.anim[0].has_channel)) != P3CS_OK) return bail(rc);
   if ((rc = upload_skel<int>(sk, d->table_length, (size_t)J * 12, &s.anim[0].table_length)) != P3CS_OK) return bail(rc);

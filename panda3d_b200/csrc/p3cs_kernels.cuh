@@ -122,6 +122,8 @@ struct SkeletonDev {
   const int *parent;          // -1: top-level joint
   const int *level_order;     // joint indices sorted by depth in the tree
   const int *level_begin;     // [max_level+2] ranges of level_order
+  const int *path_offsets;    // [J+1]: joint j's chain of ancestors, outermost first, j itself last, is
+  const int *path_joints;     //        path_joints[path_offsets[j] .. path_offsets[j+1])
   AnimationDev anim[kMaxAnimations];
   const float *default_value; // [J][16]
   const float *initial_inverse;

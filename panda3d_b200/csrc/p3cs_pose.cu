@@ -143,18 +143,6 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
   float *local = smem_pose;
   float *net = smem_pose + (size_t)J * 16;
   const int cs = skel.coordinate_system;
-  // The tree's level structure goes to shared memory first: the level loop below is a chain of barriers, and three
-  // dependent global loads per level (range, joint, parent) were most of its length.
-  int *s_order = reinterpret_cast<int *>(smem_pose + (size_t)J * 32);  // [J] joints sorted by level
-  int *s_parent = s_order + J;                                         // [J] parent of s_order[k]
-  int *s_begin = s_parent + J;                                         // [max_level + 2] level ranges
-  for (int k = threadIdx.x; k < J; k += blockDim.x) {
-    const int j = __ldg(skel.level_order + k);
-    s_order[k] = j;
-    s_parent[k] = __ldg(skel.parent + j);
-  }
-  for (int l = threadIdx.x; l < skel.max_level + 2; l += blockDim.x) s_begin[l] = __ldg(skel.level_begin + l);
-
   // morph sliders: CharacterSlider's value from its scalar channel(s) (MovingPartScalar::get_blend_value,
   // chan/movingPartScalar.cxx:43-105): same selection rule as the joints; the blend is a plain weighted sum from
   // zero followed by a true division by the net effect
@@ -331,25 +319,32 @@ __global__ void __launch_bounds__(256) pose_kernel(SkeletonDev skel, float *pale
   }
   __syncthreads();
 
-  // phase 2, level by level: _net_transform = _value * parent's _net_transform (or the root transform).
-  // Joints are stored sorted by level, so level L is the contiguous range [level_begin[L], level_begin[L+1]).
-  for (int level = 0; level <= skel.max_level; ++level) {
-    const int lb = s_begin[level], le = s_begin[level + 1];
-    for (int k = lb + threadIdx.x; k < le; k += blockDim.x) {
-      const int j = s_order[k];
-      const int parent = s_parent[k];
-      float value[16], par[16], out[16];
+  // phase 2: _net_transform = _value * parent's _net_transform (or the root transform), CharacterJoint::update_internals.
+  // Every joint multiplies down its own chain of ancestors, outermost first -- the same products in the same order as
+  // the parents-first walk of the reference (each thread recomputes its ancestors' net transforms, bit for bit what
+  // their own threads compute), without a CTA-wide barrier per tree level.
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    float cur[16];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        value[q] = local[j * 16 + q];
-        par[q] = parent >= 0 ? net[parent * 16 + q] : __ldg(skel.root_xform + q);
+    for (int q = 0; q < 16; ++q) cur[q] = __ldg(skel.root_xform + q);
+    const int pb = __ldg(skel.path_offsets + j), pe = __ldg(skel.path_offsets + j + 1);
+    for (int e = pb; e < pe; ++e) {
+      const float4 *v4 = reinterpret_cast<const float4 *>(local + __ldg(skel.path_joints + e) * 16);
+      float value[16], out[16];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 q = v4[r];
+        value[r * 4] = q.x; value[r * 4 + 1] = q.y; value[r * 4 + 2] = q.z; value[r * 4 + 3] = q.w;
       }
-      mul4(out, value, par);
+      mul4(out, value, cur);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) net[j * 16 + q] = out[q];
+      for (int q = 0; q < 16; ++q) cur[q] = out[q];
     }
-    __syncthreads();
+    float4 *dst = reinterpret_cast<float4 *>(net + j * 16);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) dst[r] = make_float4(cur[r * 4], cur[r * 4 + 1], cur[r * 4 + 2], cur[r * 4 + 3]);
   }
+  __syncthreads();
   // _skinning_matrix = _initial_net_transform_inverse * _net_transform, gathered in palette order
   float *pal = palettes + (size_t)inst * num_transforms * 16;
   for (int t = threadIdx.x; t < num_transforms; t += blockDim.x) {
@@ -371,7 +366,7 @@ void launch_pose(const SkeletonDev &skel, float *palettes, int num_transforms, f
                  const ControlState *states_dev, int num_controls, int frame_blend, int blend_type, const ForcedDev &forced,
                  int first_instance, int count, cudaStream_t stream) {
   if (count == 0 || skel.num_joints == 0) return;
-  const size_t smem = (size_t)skel.num_joints * 128 + ((size_t)skel.num_joints * 2 + skel.max_level + 2) * sizeof(int);
+  const size_t smem = (size_t)skel.num_joints * 128;
   int threads = ((skel.num_joints + 31) / 32) * 32;
   if (threads > 256) threads = 256;
   if (states_dev != nullptr) {
