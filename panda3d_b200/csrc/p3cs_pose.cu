@@ -5,8 +5,8 @@
 //                                          12 table components -> compose_matrix),
 //   CharacterJoint::update_internals      (panda/src/char/characterJoint.cxx:110-150:
 //                                          net = value * parent net, skinning = initial^-1 * net)
-// (local values for all joints in parallel, then the net transforms level by level: one
-// __syncthreads per tree level) and writes
+// (local values for all joints in parallel, then every joint's net transform as the product down its own chain of
+// ancestors, outermost first -- the reference's products in the reference's order, no barrier per tree level) and writes
 // the palette straight into the group's device buffer: with it a crowd needs one int per
 // instance and frame from the host instead of T x 64 bytes of matrices.
 // Covers one AnimControl without blending (chan/movingPartMatrix.cxx:71-76), the frame-blend flag
