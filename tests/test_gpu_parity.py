@@ -602,6 +602,43 @@ def test_tight_bounds_over_referenced_rows_only(gpu_ctx, monkeypatch, path, layo
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("plan", ["1,3,256", "1,2,256", "2,2,256", "2,2,168", "1,2,136", "2,2,64", "1,3,8"])
+@pytest.mark.parametrize("layout", ["packed", "texcoord", "tbn_uv", "align16"])
+def test_every_shared_memory_plan_gives_the_same_bytes(gpu_ctx, monkeypatch, plan, layout):
+    """The strip kernel's shared-memory plan (rows per thread, tile buffers, record-group size; p3cs_mesh.cu) only
+    changes how the work is cut: forced through the P3CS_STRIP_PLAN tuning aid, every plan must give the very bytes of
+    the default plan -- 256- and 512-row tiles, two and three buffers, record groups from 256 blends down to 8 -- and
+    those agree with the oracle (one blend of this seed is nearly uniformly scaled: libm branch, within the contract)."""
+    kw = {"packed": {}, "texcoord": dict(texcoord=True), "tbn_uv": dict(tbn=True, texcoord=True), "align16": dict(align16=True)}[layout]
+    sm = synth.make_mesh(6_011, 40, 900, seed=101, index_order="runs", num_sliders=2, slider_band=0.2, **kw)
+    mesh = sm.flat
+    pal = synth.make_palettes(40, 3, 102, scale=(1.0, 1.2, 0.8))
+    sl = synth.make_sliders(2, 3, 103)
+
+    def run():
+        dmesh = _capi.Mesh(gpu_ctx, mesh)
+        grp = _capi.Group(dmesh, 3)
+        try:
+            assert np.array_equal(grp.read_selection(), expected_selection(mesh))
+            grp.set_palettes(pal.reshape(3, -1))
+            grp.set_sliders(sl)
+            grp.animate()
+            return grp.read_output(0).copy()
+        finally:
+            grp.close()
+            dmesh.close()
+
+    monkeypatch.delenv("P3CS_STRIP_PLAN", raising=False)
+    reference = run()
+    monkeypatch.setenv("P3CS_STRIP_PLAN", plan)
+    forced = run()
+    assert np.array_equal(forced, reference), f"plan {plan} layout {layout}"
+    om = oracle.OracleMesh(mesh)
+    for i in range(3):
+        compare_outputs(mesh, [forced[i]], [om.animate(pal[i], sl[i])[0][0]], f"plan {plan} layout {layout} instance {i}")
+
+
+@pytest.mark.gpu
 def test_animate_groups_mixed_crowd(gpu_ctx):
     """p3cs_animate_groups (independent groups forked over side streams) == animating the groups one by one,
     byte for byte, on a C5-style mixed crowd of 6 character types (more groups than side streams)."""
