@@ -50,7 +50,7 @@ extern "C" int p3cs_context_create(int device, void *stream, p3cs_context *out) 
   int n = p3cs_device_count();
   if (n <= 0) return p3cs_fail(P3CS_ERR_NO_DEVICE, "no CUDA device available (this backend has no CPU fallback)");
   if (device < 0 || device >= n) return p3cs_fail(P3CS_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
-  CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard g(device);  // the caller's current device is restored on return
   p3cs_context ctx = new (std::nothrow) p3cs_context_s;
   if (ctx == nullptr) return p3cs_fail(P3CS_ERR_NOMEM, "out of host memory");
   ctx->device = device;
@@ -301,12 +301,14 @@ extern "C" int p3cs_group_animate(p3cs_group grp) {
 static int copy_output_rows(p3cs_group grp, int o, int first, int count, void *host_dst, cudaStream_t stream);
 
 static int ensure_side_streams(p3cs_context ctx) {
-  if (ctx->fork_ev != nullptr) return P3CS_OK;
-  CUDA_TRY(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+  if (ctx->side_ready) return P3CS_OK;
+  // created one by one, marked ready only when all exist: a partial failure is retried (and reported) by the next call
+  if (ctx->fork_ev == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
   for (int k = 0; k < p3cs_context_s::kSideStreams; ++k) {
-    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming));
+    if (ctx->side[k] == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
+    if (ctx->join_ev[k] == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming));
   }
+  ctx->side_ready = true;
   return P3CS_OK;
 }
 
@@ -341,25 +343,35 @@ extern "C" int p3cs_group_animate_host(p3cs_group grp, const float *host_palette
   CUDA_TRY(cudaStreamWaitEvent(down, ctx->fork_ev, 0));
   const size_t pal_per = (size_t)m.num_transforms * 16, sl_per = (size_t)m.num_sliders;
   int total_launches = 0;
-  for (int c = 0; c < nchunks; ++c) {
+  // From here on the three streams are forked: every failure falls through to the join below (never an early return),
+  // so the copy streams cannot run ahead of the context's stream.
+  auto cuda_step = [&](cudaError_t err, const char *what) {
+    if (err != cudaSuccess && rc == P3CS_OK)
+      rc = p3cs_fail(err == cudaErrorMemoryAllocation ? P3CS_ERR_NOMEM : P3CS_ERR_CUDA, "p3cs_group_animate_host: %s failed: %s", what,
+                     cudaGetErrorString(err));
+    return rc == P3CS_OK;
+  };
+  for (int c = 0; c < nchunks && rc == P3CS_OK; ++c) {
     const int first = c * chunk, count = std::min(chunk, grp->n - first);
-    if (pal_per > 0)
-      CUDA_TRY(cudaMemcpyAsync(const_cast<float *>(grp->dev.palettes) + pal_per * first, host_palettes + pal_per * first,
-                               pal_per * count * 4, cudaMemcpyHostToDevice, up));
-    if (sl_per > 0 && host_sliders != nullptr)
-      CUDA_TRY(cudaMemcpyAsync(const_cast<float *>(grp->dev.sliders) + sl_per * first, host_sliders + sl_per * first,
-                               sl_per * count * 4, cudaMemcpyHostToDevice, up));
-    CUDA_TRY(cudaEventRecord(ctx->pipe_ev[2 * c], up));
-    CUDA_TRY(cudaStreamWaitEvent(run, ctx->pipe_ev[2 * c], 0));
+    if (pal_per > 0 &&
+        !cuda_step(cudaMemcpyAsync(const_cast<float *>(grp->dev.palettes) + pal_per * first, host_palettes + pal_per * first,
+                                   pal_per * count * 4, cudaMemcpyHostToDevice, up), "palette upload"))
+      break;
+    if (sl_per > 0 && host_sliders != nullptr &&
+        !cuda_step(cudaMemcpyAsync(const_cast<float *>(grp->dev.sliders) + sl_per * first, host_sliders + sl_per * first,
+                                   sl_per * count * 4, cudaMemcpyHostToDevice, up), "slider upload"))
+      break;
+    if (!cuda_step(cudaEventRecord(ctx->pipe_ev[2 * c], up), "cudaEventRecord")) break;
+    if (!cuda_step(cudaStreamWaitEvent(run, ctx->pipe_ev[2 * c], 0), "cudaStreamWaitEvent")) break;
     if ((rc = animate_range(grp, first, count, false)) != P3CS_OK) break;
     total_launches += grp->last.launches;
-    CUDA_TRY(cudaEventRecord(ctx->pipe_ev[2 * c + 1], run));
+    if (!cuda_step(cudaEventRecord(ctx->pipe_ev[2 * c + 1], run), "cudaEventRecord")) break;
     if (host_outputs != nullptr) {
-      CUDA_TRY(cudaStreamWaitEvent(down, ctx->pipe_ev[2 * c + 1], 0));
-      for (int o = 0; o < m.num_outputs; ++o)
+      if (!cuda_step(cudaStreamWaitEvent(down, ctx->pipe_ev[2 * c + 1], 0), "cudaStreamWaitEvent")) break;
+      for (int o = 0; o < m.num_outputs && rc == P3CS_OK; ++o)
         if (host_outputs[o] != nullptr) {
           uint8_t *dst = static_cast<uint8_t *>(host_outputs[o]) + (size_t)m.num_rows * m.stride[o] * first;
-          if ((rc = copy_output_rows(grp, o, first, count, dst, down)) != P3CS_OK) break;
+          rc = copy_output_rows(grp, o, first, count, dst, down);
         }
     }
   }
@@ -709,7 +721,10 @@ extern "C" int p3cs_skeleton_create(p3cs_context ctx, const p3cs_skeleton_desc *
   if (ctx == nullptr || d == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_skeleton_create: NULL argument");
   if (d->struct_size != sizeof(p3cs_skeleton_desc)) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_skeleton_desc::struct_size mismatch");
   const int J = d->num_joints;
-  if (J < 0 || J > 3000) return p3cs_fail(P3CS_ERR_UNSUPPORTED, "num_joints %d outside 0..3000", J);
+  // pose_kernel keeps the local and the net transform of every joint of an instance in shared memory (128 B per
+  // joint, 227 KB per CTA on sm_100a)
+  constexpr int kMaxPoseJoints = (227 * 1024) / 128;
+  if (J < 0 || J > kMaxPoseJoints) return p3cs_fail(P3CS_ERR_UNSUPPORTED, "num_joints %d outside 0..%d", J, kMaxPoseJoints);
   int cs = d->coordinate_system == 0 ? P3CS_CS_ZUP_RIGHT : d->coordinate_system;
   if (cs < P3CS_CS_ZUP_RIGHT || cs > P3CS_CS_YUP_LEFT) return p3cs_fail(P3CS_ERR_INVALID, "bad coordinate_system %d", cs);
   std::vector<int> level(std::max(J, 1), 0);

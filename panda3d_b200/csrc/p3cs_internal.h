@@ -30,6 +30,7 @@ struct p3cs_context_s {
   static constexpr int kSideStreams = 3;
   cudaStream_t side[kSideStreams] = {nullptr, nullptr, nullptr};
   cudaEvent_t fork_ev = nullptr;
+  bool side_ready = false;  // every side stream / event above exists (ensure_side_streams)
   cudaEvent_t join_ev[kSideStreams] = {nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> pipe_ev;  // chunk hand-off events of p3cs_group_animate_host
   // p3cs_animate_groups: the fork / join of a set of groups captured once as a CUDA graph and replayed

@@ -407,9 +407,13 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
 
   // column order is semantically irrelevant (columns are independent); a canonical order
   // point(s), normal(s), vector(s) lets the strip kernel pick a specialised variant
+  // ... and, inside a kind, by position (output array, byte offset): the row-layout modes (kRow48 / kRow56) address
+  // "the lower vector column" and "the upper one" by their dyn index, whatever order the caller listed them in
   std::stable_sort(m.dyn, m.dyn + m.num_dyn, [](const DynColumn &a, const DynColumn &b) {
     auto key = [](int skin) { return skin == 1 ? 0 : skin == 3 ? 1 : 2; };
-    return key(a.skin) < key(b.skin);
+    if (key(a.skin) != key(b.skin)) return key(a.skin) < key(b.skin);
+    if (a.output != b.output) return a.output < b.output;
+    return a.start < b.start;
   });
 
   // ---- transform_blend index column -> dense u16/u32

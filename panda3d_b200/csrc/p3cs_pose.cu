@@ -26,11 +26,18 @@ __device__ __forceinline__ void mul4(float *res, const float *a, const float *b)
       res[i * 4 + j] = a[i * 4 + 0] * b[0 * 4 + j] + a[i * 4 + 1] * b[1 * 4 + j] + a[i * 4 + 2] * b[2 * 4 + j] + a[i * 4 + 3] * b[3 * 4 + j];
 }
 
+// frame % len as the reference evaluates it on AnimControl's non-negative frames; a negative frame handed in by a
+// careless host wraps into the table instead of reading in front of it
+__device__ __forceinline__ int wrap_frame(int frame, int len) {
+  const int r = frame % len;
+  return r < 0 ? r + len : r;
+}
+
 // One table component of a joint at a frame: table[frame % size], or the default of an empty table
 // (1 for the scales, 0 otherwise; animChannelMatrixXfmTable.I:75-85).
 __device__ __forceinline__ float channel_component(const AnimationDev &an, int j, int i, int frame) {
   const int len = __ldg(an.table_length + j * 12 + i);
-  return len == 0 ? (i < 3 ? 1.0f : 0.0f) : __ldg(an.tables + __ldg(an.table_offset + j * 12 + i) + frame % len);
+  return len == 0 ? (i < 3 ? 1.0f : 0.0f) : __ldg(an.tables + __ldg(an.table_offset + j * 12 + i) + wrap_frame(frame, len));
 }
 
 // AnimChannelMatrixXfmTable::get_value (animChannelMatrixXfmTable.cxx:112-124), or get_value_no_scale_shear
@@ -130,7 +137,7 @@ static __device__ __noinline__ void quat_compose_value(float *value, const float
 // AnimChannelScalarTable::get_value (chan/animChannelScalarTable.cxx:88-94)
 __device__ __forceinline__ float slider_channel_value(const AnimationDev &an, int s, int frame) {
   const int len = __ldg(an.slider_table_length + s);
-  return len == 0 ? 0.0f : __ldg(an.tables + __ldg(an.slider_table_offset + s) + frame % len);
+  return len == 0 ? 0.0f : __ldg(an.tables + __ldg(an.slider_table_offset + s) + wrap_frame(frame, len));
 }
 
 template <bool BLEND>

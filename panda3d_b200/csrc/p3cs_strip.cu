@@ -39,7 +39,7 @@ static int pick_mode(const MeshDev &mesh) {
     return kFastPN;
   }
   if (mesh.num_dyn == 4 && d[0].skin == 1 && d[1].skin == 3 && d[2].skin == 2 && d[3].skin == 2) {
-    const int t = d[2].start < d[3].start ? d[2].start : d[3].start, b = d[2].start < d[3].start ? d[3].start : d[2].start;
+    const int t = d[2].start, b = d[3].start;  // p3cs_mesh_create sorts same-kind columns by offset: dyn[2] is the lower one
     if (d[0].start == 0 && d[1].start == 12 && t == 24 && b == 36 && stride == 48) return kRow48;
     if (d[0].start == 0 && d[1].start == 12 && t == 32 && b == 44 && stride == 56) return kRow56;
     return kFastPNVV;

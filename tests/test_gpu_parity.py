@@ -38,30 +38,42 @@ def dynamic_float_mask(mesh, numeric_type=None):
 
 
 def compare_outputs(mesh, got, expect, what=""):
-    """Static bytes identical; dynamic floats within REL_TOL (relative to the vector magnitude
-    scale, floor 1e-30).  Returns (max_abs_error, number_of_differing_bytes)."""
-    from panda3d_b200.flat import NT_float32, NT_float64
+    """Static bytes identical; every dynamic column within REL_TOL, judged PER COLUMN (SURVEY 8d "per component
+    class"): a component's error is taken relative to max(|component|, largest |component| of the SAME column in
+    that row) -- a normal is never measured against the position's magnitude.  Returns (max_abs_error,
+    number_of_differing_bytes)."""
+    from panda3d_b200.flat import NT_float64, NUMERIC_BYTES
     max_abs, nbytes = 0.0, 0
     all_masks = dynamic_float_mask(mesh)
-    typed = [(np.float32, dynamic_float_mask(mesh, NT_float32)), (np.float64, dynamic_float_mask(mesh, NT_float64))]
+    columns = []
+    for c in list(mesh.skin_columns) + [mo.base for mo in mesh.morphs]:
+        key = (c.array, c.start, c.num_values, c.numeric_type)
+        if key not in [k for k, _ in columns]:
+            columns.append((key, c))
     for o, (g, e, mask) in enumerate(zip(got, expect, all_masks)):
         g = np.asarray(g).reshape(mesh.num_rows, -1)
         e = np.asarray(e).reshape(mesh.num_rows, -1)
         assert g.shape == e.shape
         assert np.array_equal(g[:, ~mask], e[:, ~mask]), f"{what}: static bytes of output {o} differ"
         nbytes += int((g != e).sum())
-        for dt, masks in typed:
-            tm = masks[o]
-            gf = np.ascontiguousarray(g[:, tm]).view(dt).astype(np.float64)
-            ef = np.ascontiguousarray(e[:, tm]).view(dt).astype(np.float64)
-            if gf.size:
+        for _, c in columns:
+            if c.array != mesh.output_arrays[o]:
+                continue
+            dt = np.float64 if c.numeric_type == NT_float64 else np.float32
+            width = NUMERIC_BYTES[c.numeric_type] * c.num_values
+            gf = np.ascontiguousarray(g[:, c.start:c.start + width]).view(dt).astype(np.float64)
+            ef = np.ascontiguousarray(e[:, c.start:c.start + width]).view(dt).astype(np.float64)
+            if not gf.size:
+                continue
+            same = np.ascontiguousarray(g[:, c.start:c.start + width]) == np.ascontiguousarray(e[:, c.start:c.start + width])
+            with np.errstate(invalid="ignore"):
                 err = np.abs(gf - ef)
-                max_abs = max(max_abs, float(err.max()))
-                scale = np.maximum(np.abs(ef), 1e-30)
-                # per component class: relative to the component, with the row's vector magnitude as floor
-                row_scale = np.maximum(scale, np.abs(ef).max(axis=1, keepdims=True))
-                rel = (err / row_scale).max()
-                assert rel <= REL_TOL, f"{what}: output {o} relative error {rel:.3e} > {REL_TOL}"
+            err[same.reshape(gf.shape[0], c.num_values, -1).all(axis=2)] = 0.0   # identical bit patterns (inf, NaN included)
+            assert np.isfinite(err).all(), f"{what}: output {o} column @{c.start}: non-finite values differ"
+            max_abs = max(max_abs, float(err.max()))
+            col_scale = np.maximum(np.abs(np.where(np.isfinite(ef), ef, 0.0)).max(axis=1, keepdims=True), 1e-30)
+            rel = (err / np.maximum(np.abs(ef), col_scale)).max()
+            assert rel <= REL_TOL, f"{what}: output {o} column @{c.start} relative error {rel:.3e} > {REL_TOL}"
     return max_abs, nbytes
 
 
@@ -72,6 +84,12 @@ def expected_selection(mesh):
         for b, e in np.asarray(mesh.row_ranges).reshape(-1, 2):
             sel[b:e] = bi[b:e]
     return sel
+
+
+# Fixtures built to hit the uniform-scale normal branch (decompose_matrix / compose_matrix, geomVertexData.cxx:1825-1827):
+# sinf / cosf / atan2f differ in the last place between libm and CUDA, so these agree within REL_TOL only.  EVERY other
+# fixture must come out byte for byte as the reference wrote it -- asserted below.
+NOT_BYTE_EXACT = {"rigid_uniform_scale", "align16_uniform_scale", "f64_uniform_scale", "cs_zup_left", "cs_yup_right", "cs_yup_left"}
 
 
 @pytest.mark.parametrize("path", golden_paths(), ids=golden_ids())
@@ -96,6 +114,9 @@ def test_golden_fixture_parity(gpu_ctx, path):
             assert np.array_equal(blends[:, cols].view(np.uint32), eb.reshape(-1, 16)[:, cols].view(np.uint32)), \
                 "blended matrices are not bit-identical to TransformBlend::get_blend"
         print(f"{path.rsplit('/', 1)[1]}: differing bytes vs reference = {total_diff}")
+        name = os.path.splitext(os.path.basename(path))[0]
+        if name not in NOT_BYTE_EXACT:
+            assert total_diff == 0, f"{name}: {total_diff} bytes differ from the reference's output (must be byte-identical)"
     finally:
         grp.close()
         dmesh.close()
@@ -149,6 +170,34 @@ def test_synthetic_parity_vs_oracle(gpu_ctx, name):
             got = grp.animate_vertices(pal[fr], sl[fr] if sl is not None else None)
             max_abs, nb = compare_outputs(mesh, got, expect, f"{name} frame {fr}")
             print(f"{name} frame {fr}: max-abs error {max_abs:.3e}, differing bytes {nb}")
+    finally:
+        grp.close()
+        dmesh.close()
+
+
+@pytest.mark.parametrize("texcoord", [False, True])
+def test_vector_columns_listed_binormal_first(gpu_ctx, texcoord):
+    """Skin columns handed over as vertex, normal, BINORMAL, TANGENT (the order of a caller's column list is free),
+    with morphs on both vector columns: the row-layout modes (strides 48 / 56) must still add every delta to the
+    column it belongs to (the kRow48 / kRow56 morph loop keyed columns by dyn index)."""
+    sm = synth.make_mesh(4_000, 24, 500, seed=61, tbn=True, texcoord=texcoord, index_order="runs", num_sliders=3, slider_band=0.4,
+                         morph_columns=("tangent", "binormal", "vertex"))
+    mesh = sm.flat
+    v, n, t, b = mesh.skin_columns
+    assert t.start < b.start
+    mesh.skin_columns = [v, n, b, t]
+    pal = synth.make_palettes(mesh.num_transforms, 2, 62)
+    sl = synth.make_sliders(3, 2, 63)
+    sl[:, 0] = 0.75   # never all zero
+    om = oracle.OracleMesh(mesh)
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, 1)
+    try:
+        for fr in range(2):
+            expect, _, _ = om.animate(pal[fr], sl[fr])
+            got = grp.animate_vertices(pal[fr], sl[fr])
+            max_abs, nb = compare_outputs(mesh, got, expect, f"binormal-first frame {fr}")
+            assert nb == 0, f"{nb} bytes differ from the oracle"
     finally:
         grp.close()
         dmesh.close()
