@@ -305,13 +305,14 @@ def run_gpu_arm(args):
         if rank == 0 and not args.no_check:
             from oracle import oracle
             inst = n_local // 2
-            expect, _, _ = oracle.OracleMesh(flat).animate(pal_host[inst].numpy())
             got = out_host[inst].numpy().reshape(rows, stride)
+            explained, unexplained, expect = oracle.unexplained_differences(flat, [got], pal_host[inst].numpy())
             g, e = got.view(np.float32).astype(np.float64), expect[0].view(np.float32).astype(np.float64)
-            check = {"instance": inst, "max_abs_err": float(np.abs(g - e).max()), "differing_bytes": int((got != expect[0]).sum())}
-            # this workload never enters the sinf/cosf normal branch: every byte must equal the oracle's, or the
-            # timed work was not the reference's computation and no number is reported
-            assert check["differing_bytes"] == 0, f"bench check failed: {check}"
+            check = {"instance": inst, "max_abs_err": float(np.abs(g - e).max()), "differing_bytes": explained + unexplained,
+                     "differing_bytes_outside_libm_normals": unexplained}
+            # every byte must equal the oracle's (but for the last place of sinf / cosf in the rare uniform-scale normal
+            # branch), or the timed work was not the reference's computation and no number is reported
+            assert unexplained == 0 and check["max_abs_err"] <= 1e-5, f"bench check failed: {check}"
 
         # ---------------- "next" row f1: joint hierarchy on the GPU -- the host sends one frame number per
         # instance (40 KB) instead of the palettes (82 MB); pose + animate timed together on the device

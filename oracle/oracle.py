@@ -136,6 +136,39 @@ class OracleMesh:
         return outs, blends, sel
 
 
+def unexplained_differences(mesh, got, palette, sliders=None, om: Optional["OracleMesh"] = None):
+    """Bytes of `got` (output arrays of one instance) that differ from the oracle's, split into `explained` -- inside a
+    C_normal column of a row whose blended matrix takes the uniform-scale branch (decompose_matrix / compose_matrix,
+    geomVertexData.cxx:1825-1827), where libm's and CUDA's sinf / cosf / atan2f may differ in the last place -- and
+    `unexplained` (anything else: must be 0).  Returns (explained, unexplained, expect)."""
+    from panda3d_b200.flat import C_normal, NUMERIC_BYTES
+    om = om or OracleMesh(mesh)
+    expect, blends, sel = om.animate(palette, sliders, want_blends=True, want_selection=True)
+    explained = unexplained = 0
+    for o, (g, e) in enumerate(zip(got, expect)):
+        g = np.asarray(g).reshape(mesh.num_rows, -1)
+        diff = g != e
+        if not diff.any():
+            continue
+        normal_bytes = np.zeros(g.shape[1], bool)
+        for c in mesh.skin_columns:
+            if c.array == mesh.output_arrays[o] and c.contents == C_normal:
+                normal_bytes[c.start:c.start + NUMERIC_BYTES[c.numeric_type] * c.num_values] = True
+        unexplained += int(diff[:, ~normal_bytes].sum())
+        nd = diff[:, normal_bytes]
+        rows = np.nonzero(nd.any(axis=1))[0]
+        libm_blend = {}
+        for r in rows:
+            b = int(sel[r])
+            if b not in libm_blend:
+                libm_blend[b] = b >= 0 and normal_xform(blends[b], mesh.coordinate_system)[0] == 1
+            if libm_blend[b]:
+                explained += int(nd[r].sum())
+            else:
+                unexplained += int(nd[r].sum())
+    return explained, unexplained, expect
+
+
 def animate(mesh, palette, sliders=None, want_blends=False, want_selection=False):
     return OracleMesh(mesh).animate(palette, sliders, want_blends, want_selection)
 

@@ -1,8 +1,9 @@
 """GPU parity at the FULL sizes of BASELINE.json configs[2..4] (C3, C4, C5), through the C-ABI, against the oracle
 (oracle/skin_oracle.c, itself pinned bit-exact to the reference by tests/test_oracle_golden.py).
 
-The synthetic palettes put every 4-weight blend into the inverse-transpose normal branch (no sinf/cosf), so every byte
-must equal the oracle's -- asserted, not printed.  Tolerances (REL_TOL, per column) still come from compare_outputs.
+Every byte must equal the oracle's -- asserted -- except the normals of the rare blends that land in the uniform-scale
+branch, where libm and CUDA differ in the last place of sinf / cosf / atan2f (assert_bytes_equal_except_libm checks
+that every differing row really is such a row).  Tolerances (REL_TOL, per column) come from compare_outputs.
 """
 import numpy as np
 import pytest
@@ -14,6 +15,16 @@ from test_gpu_parity import compare_outputs, expected_selection
 pytestmark = pytest.mark.gpu
 
 C3_INSTANCES = 10_000
+
+
+def assert_bytes_equal_except_libm(mesh, om, palette, sliders, got, what):
+    """Every byte equals the oracle's, except inside C_normal columns of rows whose blended matrix takes the
+    uniform-scale branch (oracle.unexplained_differences; a random 4-weight blend lands there about once in 10^4).
+    REL_TOL is enforced on all of it by compare_outputs.  Returns the number of such bytes."""
+    explained, unexplained, expect = oracle.unexplained_differences(mesh, got, palette, sliders, om)
+    compare_outputs(mesh, got, expect, what)
+    assert unexplained == 0, f"{what}: {unexplained} bytes differ from the oracle outside the libm-dependent normals"
+    return explained
 
 
 def _c3_sample(n):
@@ -49,13 +60,10 @@ def test_full_size_c3_crowd(gpu_ctx, index_order):
         grp.set_palettes(pal)
         grp.animate()
         assert grp.timings().launches == 1
-        worst = 0.0
-        for k, i in enumerate(sample):
+        libm_bytes = 0
+        for i in sample:
             got = grp.read_output(0, i, 1)[0]
-            expect, _, _ = om.animate(pal[i].reshape(T, 16))
-            max_abs, nb = compare_outputs(mesh, [got], expect, f"C3/{index_order} instance {i}")
-            assert nb == 0, f"C3/{index_order} instance {i}: {nb} bytes differ from the oracle"
-            worst = max(worst, max_abs)
+            libm_bytes += assert_bytes_equal_except_libm(mesh, om, pal[i].reshape(T, 16), None, [got], f"C3/{index_order} instance {i}")
         # instances sharing a palette must share their bytes (covers every instance of the launch cheaply):
         # a checksum per instance, equal within each palette class
         out = grp.read_output(0)
@@ -66,7 +74,8 @@ def test_full_size_c3_crowd(gpu_ctx, index_order):
         for c in range(64):
             s = sums[plain & (cls == c)]
             assert (s == s[0]).all(), f"instances of palette class {c} differ among themselves"
-        print(f"C3/{index_order}: {len(sample)} instances byte-identical to the oracle, max-abs {worst:.3e}")
+        assert libm_bytes <= 64 * len(sample)
+        print(f"C3/{index_order}: {len(sample)} instances equal to the oracle but for {libm_bytes} bytes in uniform-scale normals")
     finally:
         grp.close()
         dmesh.close()
@@ -91,17 +100,13 @@ def test_full_size_c4_morph_mesh_and_crowd(gpu_ctx):
         assert np.array_equal(single.read_selection(), expected_selection(mesh))
         for fr in range(2):
             got = single.animate_vertices(pal[fr], sl[fr])
-            expect, _, _ = om.animate(pal[fr], sl[fr])
-            max_abs, nb = compare_outputs(mesh, got, expect, f"C4 single frame {fr}")
-            assert nb == 0, f"C4 single mesh frame {fr}: {nb} bytes differ from the oracle"
+            assert_bytes_equal_except_libm(mesh, om, pal[fr], sl[fr], got, f"C4 single frame {fr}")
         crowd.set_palettes(pal.reshape(n, -1))
         crowd.set_sliders(sl)
         crowd.animate()
         for i in (0, 1, n // 2, n - 1):
-            expect, _, _ = om.animate(pal[i], sl[i])
             got = crowd.read_output(0, i, 1)[0]
-            max_abs, nb = compare_outputs(mesh, [got], expect, f"C4 crowd instance {i}")
-            assert nb == 0, f"C4 crowd instance {i}: {nb} bytes differ from the oracle"
+            assert_bytes_equal_except_libm(mesh, om, pal[i], sl[i], [got], f"C4 crowd instance {i}")
         # all sliders zero: the morph pass must be a no-op (bytes equal to the same palette without sliders)
         zero = np.zeros(S, np.float32)
         a = single.animate_vertices(pal[0], zero)[0].copy()
@@ -135,10 +140,8 @@ def test_full_size_c5_mixed_crowd(gpu_ctx):
         for g, (sm, count), p in zip(groups, spec, pals):
             om = oracle.OracleMesh(sm.flat)
             for i in sorted({0, count // 2, count - 1}):
-                expect, _, _ = om.animate(p[i])
                 got = g.read_output(0, i, 1)[0]
-                max_abs, nb = compare_outputs(sm.flat, [got], expect, f"{sm.name} instance {i}")
-                assert nb == 0, f"{sm.name} instance {i}: {nb} bytes differ from the oracle"
+                assert_bytes_equal_except_libm(sm.flat, om, p[i], None, [got], f"{sm.name} instance {i}")
     finally:
         for g in groups:
             g.close()
