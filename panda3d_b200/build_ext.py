@@ -14,8 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libp3cudaskin.so")
 SOURCES = ["p3cs_api.cu", "p3cs_mesh.cu", "p3cs_interop.cu", "p3cs_kernels.cu", "p3cs_pose.cu", "p3cs_format.cu", "p3cs_strip.cu",
+           "p3cs_run_inst_a.cu", "p3cs_run_inst_b.cu",
            "p3cs_strip_inst_a.cu", "p3cs_strip_inst_b.cu", "p3cs_strip_inst_c.cu", "p3cs_strip_inst_d.cu", "p3cs_strip_inst_e.cu"]
-HEADERS = ["p3cs_internal.h", "p3cs_kernels.cuh", "p3cs_math.cuh", "p3cs_device.cuh", "p3cs_strip.cuh",
+HEADERS = ["p3cs_internal.h", "p3cs_kernels.cuh", "p3cs_math.cuh", "p3cs_device.cuh", "p3cs_strip.cuh", "p3cs_run.cuh", "p3cs_runplan.h",
            os.path.join("..", "..", "include", "p3cudaskin.h")]
 OBJ_DIR = os.path.join(HERE, "_obj")   # git-ignored and gpurun-ignored: only the .so travels
 
@@ -23,7 +24,7 @@ COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xfatbin", "-compress-all",
-]
+] + [f"-D{d}" for d in os.environ.get("P3CS_DEFINES", "").split() if d]   # experiments: P3CS_DEFINES="P3CS_RUN_CTAS_PER_SM=3"
 LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-Xcompiler", "-fPIC"]
 
 

@@ -27,6 +27,22 @@ struct DynColumn {
   int8_t f64;          // NT_float64 components: read/written through float like GeomVertexRewriter::get_data3/set_data3
 };
 
+// A plan of the run kernel (p3cs_run.cuh; built by p3cs_runplan.h at upload): tiles of `tile_rows` rows, per tile a
+// range of 32-lane slots, per lane of a slot one item = up to `max_item_rows` consecutive rows selecting one blend.
+struct RunPlanDev {
+  int tile_rows;                  // 0: no plan
+  int tile_bufs;                  // 2 or 3 staged tiles in flight per CTA
+  int num_tiles;
+  int max_item_rows;
+  const int *tile_slot_offsets;   // [num_tiles + 1]
+  // per lane of a slot, 2 x 16 bytes in two arrays (coalesced 512-byte loads per warp):
+  //   a = { item word, joint0 | joint1 << 16, joint2 | joint3 << 16, weight0 },  b = { weight1, weight2, weight3, blend id }
+  // item word: first row in the tile | rows << 13 | skinned << 18 | entries << 19 (0..4; 5: more than four, walk the
+  // TransformBlendTable's CSR by blend id); 0 = idle lane.  Padded by 8 slots (the kernel prefetches unconditionally).
+  const uint4 *item_a;
+  const uint4 *item_b;
+};
+
 struct MeshDev {
   int num_rows;
   int num_blends;
@@ -75,6 +91,10 @@ struct MeshDev {
   const uint4 *grec_blocks_hi;      // second uint4 of every group record (the two halves are separate arrays: coalesced loads)
   const uint4 *grec_blocks;         // 2 x uint4 per group record: its first four entries, the
                                     // entry count in the high half of the first index
+
+  // ---- run kernel (p3cs_run.cuh): the row-layout modes kRow24 / 32 / 48 / 56
+  int run_mode;                     // StripMode the run kernel handles this mesh in, 0: none
+  RunPlanDev run_plan[2];           // [0] crowds (large tiles), [1] launches of a few instances (small tiles, many CTAs)
 };
 
 constexpr int kStripThreads = 256;  // threads of a strip-kernel CTA; a tile is kStripThreads * rows_per_thread rows
@@ -164,6 +184,9 @@ int strip_ctas_per_instance(const MeshDev &mesh, int count, int sm_count);
 void launch_bounds_init(const GroupDev &grp, int first_instance, int count, cudaStream_t stream);  // honours instance_list
 void launch_bounds_scan(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, cudaStream_t stream);
 size_t strip_smem_bytes(const MeshDev &mesh);
+// StripMode the strip kernel would run this mesh in (p3cs_strip.cu); the kRow modes are the run kernel's
+int strip_pick_mode(const MeshDev &mesh);
+int strip_mode_row_bytes(int mode);  // row stride of a kRow mode, 0 for the others
 int skin_rows_per_tile(const MeshDev &mesh);
 
 }  // namespace p3cs

@@ -3,6 +3,7 @@
 // dynamic columns, the shared-memory plan, record groups with their conflict-aware record order, the
 // per-row morph CSR.  Host C++.
 #include "p3cs_internal.h"
+#include "p3cs_run.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -337,6 +338,83 @@ static StripTables build_record_groups(const p3cs_mesh_desc *d, const std::vecto
   return tb;
 }
 
+// ---- run-kernel plans: items of <= K consecutive rows selecting one blend, dealt to 32-lane slots (p3cs_runplan.h),
+// plus per item its first four (palette index, weight) entries.  Two plans per mesh: [0] large tiles for crowds
+// (as many rows as two tile buffers of a CTA hold with four CTAs per SM), [1] 256-row tiles for launches of a few
+// instances, where many small CTAs fill the machine better.
+static int upload_run_plan(p3cs_mesh mesh, const p3cs_mesh_desc *d, const RunPlanHost &hp, int tile_bufs, RunPlanDev *out) {
+  int rc;
+  const size_t used = hp.items.size();
+  const size_t n = used + 8 * 32;  // padded by a CTA's worth of slots: the kernel prefetches the warp's next slot unconditionally
+  std::vector<uint4> a(n, make_uint4(0, 0, 0, 0)), b(n, make_uint4(0, 0, 0, 0xFFFFFFFFu));
+  for (size_t i = 0; i < used; ++i) {
+    const int blend = hp.item_blend[i];
+    uint32_t item = hp.items[i], joints[4] = {0, 0, 0, 0}, w[4] = {0, 0, 0, 0};
+    if (blend >= 0) {
+      const int beg = d->blend_offsets[blend], cnt = d->blend_offsets[blend + 1] - beg;
+      for (int k = 0; k < std::min(cnt, 4); ++k) {
+        joints[k] = (uint32_t)d->blend_transform[beg + k];
+        memcpy(&w[k], &d->blend_weight[beg + k], 4);
+      }
+      item |= (uint32_t)std::min(cnt, 5) << kItemEntriesShift;
+    }
+    a[i] = make_uint4(item, joints[0] | (joints[1] << 16), joints[2] | (joints[3] << 16), w[0]);
+    b[i] = make_uint4(w[1], w[2], w[3], (uint32_t)blend);
+  }
+  out->tile_rows = hp.tile_rows;
+  out->tile_bufs = tile_bufs;
+  out->num_tiles = hp.num_tiles;
+  out->max_item_rows = hp.max_item_rows;
+  if ((rc = upload<int>(mesh, hp.tile_slot_offsets.data(), hp.tile_slot_offsets.size(), &out->tile_slot_offsets)) != P3CS_OK) return rc;
+  if ((rc = upload<uint4>(mesh, a.data(), n, &out->item_a)) != P3CS_OK) return rc;
+  if ((rc = upload<uint4>(mesh, b.data(), n, &out->item_b)) != P3CS_OK) return rc;
+  // the uploads read host vectors that die with this frame
+  if (cudaStreamSynchronize(mesh->ctx->stream) != cudaSuccess) return p3cs_fail(P3CS_ERR_CUDA, "run plan upload failed");
+  return P3CS_OK;
+}
+
+static int build_run_plans(p3cs_mesh mesh, const p3cs_mesh_desc *d, const std::vector<uint32_t> &row_index, const std::vector<uint32_t> &mask) {
+  MeshDev &m = mesh->dev;
+  m.run_mode = 0;
+  if (m.num_rows == 0 || m.index_bytes == 0 || m.num_transforms >= 65536) return P3CS_OK;
+  const int mode = strip_pick_mode(m);
+  const int row_bytes = strip_mode_row_bytes(mode);
+  if (row_bytes == 0) return P3CS_OK;
+  if (d->num_sliders > 65536) return P3CS_OK;
+  const int fixed = ((64 + m.num_transforms * 64 + 127) & ~127);
+  // kRunCtasPerSm CTAs per SM: 228 KB per SM, 1 KB reserved per CTA
+  int budget = (228 * 1024 / kRunCtasPerSm - 1024) - fixed;
+  if (budget < 2 * 128 * row_bytes) budget = 113 * 1024 - fixed;   // very large palettes: two CTAs per SM
+  if (budget < 2 * 64 * row_bytes) return P3CS_OK;                 // does not fit: the strip kernel's own fallbacks apply
+  int tile_rows = std::min(4096, (budget / 2 / row_bytes) & ~15), bufs = 2, K = 8;
+  if (const char *e = getenv("P3CS_RUN_PLAN")) {  // tuning aid: "tile_rows,tile_bufs,max_item_rows"
+    int a = 0, b = 0, c = 0;
+    if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a >= 16 && a <= 8176 && a % 16 == 0 && b >= 2 && b <= 4 && c >= 1 && c <= kItemMaxRows &&
+        fixed + (size_t)b * (((size_t)a * row_bytes + 127) & ~(size_t)127) <= 200 * 1024) {
+      tile_rows = a;
+      bufs = b;
+      K = c;
+    }
+  }
+  RunPlanInput in;
+  in.num_rows = m.num_rows;
+  in.row_blend = row_index.data();
+  in.live_mask = mask.empty() ? nullptr : mask.data();
+  int rc;
+  {
+    const RunPlanHost hp = build_run_plan(in, tile_rows, K);
+    if (getenv("P3CS_DEBUG_PLAN") != nullptr) print_run_plan_stats(hp, m.num_rows, stderr);
+    if ((rc = upload_run_plan(mesh, d, hp, bufs, &m.run_plan[0])) != P3CS_OK) return rc;
+  }
+  if (tile_rows > 256) {
+    const int small_bufs = fixed + 3 * 256 * row_bytes <= 228 * 1024 / kRunCtasPerSm - 1024 ? 3 : 2;
+    const RunPlanHost hp = build_run_plan(in, 256, K);
+    if ((rc = upload_run_plan(mesh, d, hp, small_bufs, &m.run_plan[1])) != P3CS_OK) return rc;
+  }
+  m.run_mode = mode;
+  return P3CS_OK;
+}
+
 extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_mesh *out) {
   if (out == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_mesh_create: out is NULL");
   *out = nullptr;
@@ -417,6 +495,7 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
   });
 
   // ---- transform_blend index column -> dense u16/u32
+  std::vector<uint32_t> plan_row_index, plan_mask;  // kept for the run-kernel plans built after the morph tables
   if (d->blend_column.array >= 0) {
     const p3cs_column_desc &bc = d->blend_column;
     if ((rc = check_column(d, bc, "transform_blend column")) != P3CS_OK) return bail(rc);
@@ -531,6 +610,8 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
       std::vector<uint32_t> row_index(std::max(N, 1));
       for (int r = 0; r < N; ++r) row_index[r] = wide ? idx32[r] : idx16[r];
       const StripTables tb = build_record_groups(d, row_index, full ? std::vector<uint32_t>() : mask, kTileRows, m.group_record_cap);
+      plan_row_index = row_index;
+      if (!full) plan_mask = mask;
       const std::vector<uint16_t> &local = tb.local;
       const std::vector<int> &rec_off = tb.rec_off, &rec_blend = tb.rec_blend, &ent_off = tb.ent_off, &tile_off = tb.tile_off;
       const std::vector<uint2> &ent = tb.ent;
@@ -654,6 +735,8 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
     if ((rc = upload<uint32_t>(mesh, keys.data(), keys.size(), &m.morph_keys)) != P3CS_OK) return bail(rc);
     if ((rc = upload<float4>(mesh, deltas.data(), deltas.size(), &m.morph_deltas)) != P3CS_OK) return bail(rc);
   }
+  // ---- run-kernel plans (p3cs_run.cuh) for the row-layout modes
+  if ((rc = build_run_plans(mesh, d, plan_row_index, plan_mask)) != P3CS_OK) return bail(rc);
   // ---- slice geometry of the strip kernel (a slice = the 32 rows one warp stages at a time)
   if (m.rows_per_thread == 0) m.rows_per_thread = 1;
   if (m.tile_bufs == 0) m.tile_bufs = 3;

@@ -27,7 +27,9 @@ namespace p3cs {
 constexpr int kItemStartBits = 13;  // first row of the item inside its tile (tile_rows <= 8192)
 constexpr int kItemCountBits = 5;   // rows of the item (1..31); 0 = idle lane
 constexpr int kItemMaxRows = (1 << kItemCountBits) - 1;
-constexpr uint32_t kItemSkinned = 1u << (kItemStartBits + kItemCountBits);  // rows inside TransformBlendTable::get_rows()
+constexpr int kItemEntriesShift = kItemStartBits + kItemCountBits + 1;  // entries of the blend: 0..4, 5 = more than four
+constexpr uint32_t kItemSkinned = 1u << (kItemStartBits + kItemCountBits);  // rows inside TransformBlendTable::get_rows(); clear: rows
+                                                                              // only sliders (and the bounds) touch
 
 struct RunPlanHost {
   int tile_rows = 0;
@@ -44,7 +46,6 @@ struct RunPlanInput {
   int num_rows = 0;
   const uint32_t *row_blend = nullptr;    // transform_blend value of every row
   const uint32_t *live_mask = nullptr;    // bit per row inside get_rows(); nullptr = every row
-  const int *morph_row_offsets = nullptr; // per-row CSR offsets of the morph entries; nullptr = no morphs
   bool has_blend_table = true;            // false: no transform_blend column (morph-only meshes)
 };
 
@@ -65,7 +66,6 @@ inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max
   p.num_tiles = (N + tile_rows - 1) / tile_rows;
   p.tile_slot_offsets.assign(1, 0);
   auto live = [&](int r) { return in.has_blend_table && (in.live_mask == nullptr || ((in.live_mask[r >> 5] >> (r & 31)) & 1u)); };
-  auto morphed = [&](int r) { return in.morph_row_offsets != nullptr && in.morph_row_offsets[r + 1] > in.morph_row_offsets[r]; };
 
   struct Item {
     int start, count, blend;
@@ -77,14 +77,11 @@ inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max
     for (auto &b : bucket) b.clear();
     // runs of the tile -> items
     int r = r0;
-    while (r < r1) {
-      int blend;
-      if (live(r)) blend = (int)in.row_blend[r];
-      else if (morphed(r)) blend = -1;  // not skinned, but a slider moves it
-      else { ++r; continue; }
+    while (r < r1) {  // every row belongs to exactly one item: skinned runs, and stretches outside get_rows() (blend -1)
+      const int blend = live(r) ? (int)in.row_blend[r] : -1;
       int e = r + 1;
       if (blend >= 0) while (e < r1 && live(e) && (int)in.row_blend[e] == blend) ++e;
-      else while (e < r1 && !live(e) && morphed(e)) ++e;
+      else while (e < r1 && !live(e)) ++e;
       split_run(e - r, K, pieces);
       int s = r;
       for (int len : pieces) {

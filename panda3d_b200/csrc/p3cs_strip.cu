@@ -1,8 +1,9 @@
 // p3cs_strip.cu -- host side of the fused strip kernel (p3cs_strip.cuh): mode choice, strip partition, launch.
 // The kernel template is instantiated per mode in p3cs_strip_inst_*.cu.
-#include "p3cs_strip.cuh"
+#include "p3cs_run.cuh"
 
 #include <cstdlib>
+#include <cstring>
 
 namespace p3cs {
 
@@ -21,10 +22,19 @@ P3CS_EXTERN_MODE(kAlignedPN)
 P3CS_EXTERN_MODE(kAlignedPNVV)
 #undef P3CS_EXTERN_MODE
 
+// run kernel (p3cs_run.cuh), instantiated in p3cs_run_inst_*.cu
+#define P3CS_EXTERN_RUN(M)                                                                                                          \
+  extern template void launch_run_mode<M>(const MeshDev &, const RunPlanDev &, const GroupDev &, int, dim3, size_t, int, int, cudaStream_t);
+P3CS_EXTERN_RUN(kRow24)
+P3CS_EXTERN_RUN(kRow32)
+P3CS_EXTERN_RUN(kRow48)
+P3CS_EXTERN_RUN(kRow56)
+#undef P3CS_EXTERN_RUN
+
 size_t strip_smem_bytes(const MeshDev &mesh) { return (size_t)strip_layout(mesh).total; }
 
 // Which specialisation fits this mesh (see the header comment).
-static int pick_mode(const MeshDev &mesh) {
+int strip_pick_mode(const MeshDev &mesh) {
   if (mesh.aligned) return mesh.num_dyn == 2 ? kAlignedPN : kAlignedPNVV;
   if (mesh.full_records) return kGenericFull;
   if (mesh.num_outputs != 1 || mesh.index_bytes == 0) return kGenericCompact;
@@ -80,18 +90,78 @@ static int strip_partition(const MeshDev &mesh, int count, int sm_count, int *gr
   return strips;
 }
 
+int strip_mode_row_bytes(int mode) {
+  switch (mode) {
+  case kRow24: return 24;
+  case kRow32: return 32;
+  case kRow48: return 48;
+  case kRow56: return 56;
+  default: return 0;
+  }
+}
+
+// ---- run kernel: which plan, how many CTAs per instance
+static bool use_run_kernel(const MeshDev &mesh) {
+  static const bool on = [] {  // P3CS_PATH=run: the run kernel takes the kRow modes (until it beats the strip kernel on every layout)
+    const char *e = getenv("P3CS_PATH");
+    return e != nullptr && strcmp(e, "run") == 0;
+  }();
+  return mesh.run_mode != 0 && on;
+}
+
+struct RunLaunch {
+  int plan, ctas_per_instance, tiles_per_cta;
+};
+
+static RunLaunch run_partition(const MeshDev &mesh, int count, int sm_count) {
+  RunLaunch r{0, 1, 1};
+  // the crowd plan (large tiles) needs enough instances to fill every SM four times over; else the small tiles
+  const RunPlanDev &big = mesh.run_plan[0];
+  if (mesh.run_plan[1].tile_rows != 0 && (long long)big.num_tiles * count < 4LL * sm_count) r.plan = 1;
+  const RunPlanDev &p = mesh.run_plan[r.plan];
+  const long long target = 24LL * sm_count;  // CTAs in the launch (as strip_partition)
+  long long cpi = (target + count - 1) / count;
+  if (cpi < 1) cpi = 1;
+  if (cpi > p.num_tiles) cpi = p.num_tiles;
+  r.tiles_per_cta = (p.num_tiles + (int)cpi - 1) / (int)cpi;
+  r.ctas_per_instance = (p.num_tiles + r.tiles_per_cta - 1) / r.tiles_per_cta;
+  return r;
+}
+
 int strip_ctas_per_instance(const MeshDev &mesh, int count, int sm_count) {
   if (mesh.num_rows == 0 || count == 0 || mesh.num_tiles == 0) return 0;
+  if (use_run_kernel(mesh)) return run_partition(mesh, count, sm_count).ctas_per_instance;
   int gpc;
   return strip_partition(mesh, count, sm_count, &gpc);
+}
+
+static int launch_run(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, int sm_count, int want_normal, cudaStream_t stream) {
+  const RunLaunch rl = run_partition(mesh, count, sm_count);
+  const RunPlanDev &plan = mesh.run_plan[rl.plan];
+  const size_t smem = (size_t)run_layout(mesh.num_transforms, plan.tile_rows, strip_mode_row_bytes(mesh.run_mode), plan.tile_bufs).total;
+  int launches = 0;
+  for (int c0 = 0; c0 < count; c0 += 65535) {
+    const int cn = count - c0 < 65535 ? count - c0 : 65535;
+    const dim3 grid(rl.ctas_per_instance, cn);
+    const int first = first_instance + c0;
+    switch (mesh.run_mode) {
+    case kRow24: launch_run_mode<kRow24>(mesh, plan, grp, first, grid, smem, rl.tiles_per_cta, want_normal, stream); break;
+    case kRow32: launch_run_mode<kRow32>(mesh, plan, grp, first, grid, smem, rl.tiles_per_cta, want_normal, stream); break;
+    case kRow48: launch_run_mode<kRow48>(mesh, plan, grp, first, grid, smem, rl.tiles_per_cta, want_normal, stream); break;
+    default: launch_run_mode<kRow56>(mesh, plan, grp, first, grid, smem, rl.tiles_per_cta, want_normal, stream); break;
+    }
+    ++launches;
+  }
+  return launches;
 }
 
 int launch_strip(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, int sm_count, cudaStream_t stream) {
   if (mesh.num_rows == 0 || count == 0 || mesh.num_tiles == 0) return 0;
   int want_normal = 0;
   for (int c = 0; c < mesh.num_dyn; ++c) want_normal |= (mesh.dyn[c].skin == 3);
+  if (use_run_kernel(mesh)) return launch_run(mesh, grp, first_instance, count, sm_count, want_normal, stream);
   const size_t smem = strip_smem_bytes(mesh);
-  const int mode = pick_mode(mesh);
+  const int mode = strip_pick_mode(mesh);
   int gpc;
   const int strips = strip_partition(mesh, count, sm_count, &gpc);
   int launches = 0;

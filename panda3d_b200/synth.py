@@ -206,6 +206,9 @@ def make_mesh(num_rows: int, num_transforms: int, num_blends: int, *, seed: int 
         bidx = np.repeat(runs, rng.integers(1, 13, size=runs.size))[:num_rows]
         if bidx.size < num_rows:
             bidx = np.resize(bidx, num_rows)
+    elif index_order.startswith("fixed"):   # runs of exactly N rows, e.g. "fixed5" (kernel experiments)
+        n = int(index_order[5:])
+        bidx = np.repeat(rng.integers(0, num_blends, size=num_rows // n + 1), n)[:num_rows]
     else:
         bidx = rng.integers(0, num_blends, size=num_rows)
     dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[ib]

@@ -70,6 +70,10 @@ def main():
             small = False
             if name == "c3":
                 specs = [(synth.config_c3_mesh().flat, args.instances)]
+            elif name == "c3rand":   # the C3 character with a random blend index per vertex (no runs)
+                specs = [(synth.config_c3_mesh(index_order="random").flat, args.instances)]
+            elif name.startswith("c3fixed"):   # runs of exactly N rows, e.g. c3fixed5
+                specs = [(synth.config_c3_mesh(index_order=name[2:]).flat, args.instances)]
             elif name == "c3uv":   # the C3 character with a texcoord column: stride 32, the egg loader's usual layout
                 specs = [(synth.make_mesh(20_000, 128, 4096, seed=33, texcoord=True, index_order="runs").flat, args.instances)]
             elif name == "c3tb":   # ... with tangent + binormal, no texcoord: stride 48
