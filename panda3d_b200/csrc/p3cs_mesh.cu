@@ -386,7 +386,7 @@ static int build_run_plans(p3cs_mesh mesh, const p3cs_mesh_desc *d, const std::v
   int budget = (228 * 1024 / kRunCtasPerSm - 1024) - fixed;
   if (budget < 2 * 128 * row_bytes) budget = 113 * 1024 - fixed;   // very large palettes: two CTAs per SM
   if (budget < 2 * 64 * row_bytes) return P3CS_OK;                 // does not fit: the strip kernel's own fallbacks apply
-  int tile_rows = std::min(4096, (budget / 2 / row_bytes) & ~15), bufs = 2, K = 8;
+  int tile_rows = std::min(4096, (budget / 2 / row_bytes) & ~15), bufs = 2, K = 12;
   if (const char *e = getenv("P3CS_RUN_PLAN")) {  // tuning aid: "tile_rows,tile_bufs,max_item_rows"
     int a = 0, b = 0, c = 0;
     if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a >= 16 && a <= 8176 && a % 16 == 0 && b >= 2 && b <= 4 && c >= 1 && c <= kItemMaxRows &&
@@ -400,6 +400,8 @@ static int build_run_plans(p3cs_mesh mesh, const p3cs_mesh_desc *d, const std::v
   in.num_rows = m.num_rows;
   in.row_blend = row_index.data();
   in.live_mask = mask.empty() ? nullptr : mask.data();
+  in.blend_offsets = d->blend_offsets;
+  in.blend_transform = d->blend_transform;
   int rc;
   {
     const RunPlanHost hp = build_run_plan(in, tile_rows, K);

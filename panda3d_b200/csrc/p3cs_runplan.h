@@ -9,13 +9,15 @@
 //
 // What is planned here, once per mesh (the row -> blend map is static):
 //   * tiles of `tile_rows` consecutive rows (the unit one TMA bulk copy stages);
-//   * per tile its items, dealt to SLOTS of 32 lanes.  Lane l of a half-warp takes an item whose first row is
-//     congruent to l modulo 16: at every step k of the row walk the sixteen lanes then touch rows that are pairwise
-//     different modulo 16, which makes the 64-bit shared-memory accesses of 24- and 56-byte rows, the 128-bit
-//     accesses of 48-byte rows and the alternating 128-bit pairs of 32-byte rows bank-conflict free (see
-//     RowLayout in p3cs_strip.cuh);
-//   * items of equal length share a slot as far as possible (the lanes of a warp walk in lockstep), and slots come
-//     in descending length so the warps of a CTA can be dealt slots longest-first.
+//   * per tile its items, dealt to SLOTS of 32 lanes that walk their items in lockstep.  Lane l of a half-warp
+//     touches, at step j of the walk, a row congruent to l + j modulo 16: its item starts d = (first row - l) mod 16
+//     steps late (`delay`).  The sixteen lanes of a half-warp are then on pairwise different rows modulo 16 at
+//     every step, which makes the 64-bit shared-memory accesses of 24- and 56-byte rows, the 128-bit accesses of
+//     48-byte rows and the alternating 128-bit pairs of 32-byte rows bank-conflict free (RowLayout, p3cs_strip.cuh);
+//   * a slot lasts as long as its longest delay + item, so items are placed longest first, each into the lane that
+//     keeps its slot shortest; among equally good lanes the one whose palette indices collide least, modulo 8, with
+//     the items already in the same quarter-warp (the palette gather is a 128-bit load per lane, eight lanes per
+//     wavefront, 48-byte palette rows: two different joints collide when they agree modulo 8).
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -28,6 +30,7 @@ constexpr int kItemStartBits = 13;  // first row of the item inside its tile (ti
 constexpr int kItemCountBits = 5;   // rows of the item (1..31); 0 = idle lane
 constexpr int kItemMaxRows = (1 << kItemCountBits) - 1;
 constexpr int kItemEntriesShift = kItemStartBits + kItemCountBits + 1;  // entries of the blend: 0..4, 5 = more than four
+constexpr int kItemDelayShift = kItemEntriesShift + 3;                  // steps the lane waits before its first row (0..15)
 constexpr uint32_t kItemSkinned = 1u << (kItemStartBits + kItemCountBits);  // rows inside TransformBlendTable::get_rows(); clear: rows
                                                                               // only sliders (and the bounds) touch
 
@@ -36,10 +39,10 @@ struct RunPlanHost {
   int max_item_rows = 0;
   int num_tiles = 0;
   std::vector<int> tile_slot_offsets;  // [num_tiles + 1]
-  std::vector<uint32_t> items;         // [slots * 32]: start | count << 13 | skinned << 18
+  std::vector<uint32_t> items;         // [slots * 32]: start | count << 13 | skinned << 18 | delay << 22 (entries << 19 added at upload)
   std::vector<int32_t> item_blend;     // [slots * 32]: blend id of the item (-1: rows outside get_rows())
   // statistics (tools/plan_stats, P3CS_DEBUG_PLAN)
-  long long num_items = 0, num_slots = 0, lane_steps = 0, warp_steps = 0, row_conflict_steps = 0, idle_lanes = 0;
+  long long num_items = 0, num_slots = 0, lane_steps = 0, warp_steps = 0, idle_lanes = 0, gather_wavefronts = 0, gather_ideal = 0;
 };
 
 struct RunPlanInput {
@@ -47,6 +50,9 @@ struct RunPlanInput {
   const uint32_t *row_blend = nullptr;    // transform_blend value of every row
   const uint32_t *live_mask = nullptr;    // bit per row inside get_rows(); nullptr = every row
   bool has_blend_table = true;            // false: no transform_blend column (morph-only meshes)
+  // the TransformBlendTable (CSR), for the palette-gather term of the placement; may be null
+  const int *blend_offsets = nullptr;
+  const int *blend_transform = nullptr;
 };
 
 // Splits a run of `len` rows into ceil(len / K) pieces of nearly equal length.
@@ -56,6 +62,11 @@ inline void split_run(int len, int K, std::vector<int> &pieces) {
   const int base = len / n, extra = len % n;
   for (int i = 0; i < n; ++i) pieces.push_back(base + (i < extra ? 1 : 0));
 }
+
+// Relative costs the placement weighs (issue slots + load/store wavefronts of the run kernel, measured with ncu):
+constexpr int kPlanSlotCost = 380;   // opening a slot: blending a matrix per lane, 12 gather loads, bookkeeping
+constexpr int kPlanStepCost = 82;    // one more step of a slot: a row per lane
+constexpr int kPlanGatherCost = 3;   // one more wavefront of a palette gather (three 128-bit loads per entry)
 
 inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max_item_rows) {
   RunPlanHost p;
@@ -69,15 +80,57 @@ inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max
 
   struct Item {
     int start, count, blend;
+    int joint[4];  // first four palette indices, -1 beyond the blend's entries
   };
-  std::vector<Item> bucket[16];
+  struct Slot {
+    int steps = 0;         // max over its lanes of delay + count
+    int used = 0;          // occupied lanes
+    int lane_item[32];     // index into `items`, -1 free
+    int lane_delay[32];
+    // per quarter-warp (4) x entry (4) x residue (8): the distinct joints seen (up to 8 each) -- for the gather term
+    int seen[4][4][8][8];
+    int nseen[4][4][8];
+  };
+  std::vector<Item> items;
   std::vector<int> pieces;
+  std::vector<int> bucket[16];
+  std::vector<Slot> slots;
+  auto gather_extra = [&](const Slot &sl, int quarter, const Item &it) {  // extra gather wavefronts if `it` joins this quarter-warp
+    int extra = 0;
+    for (int k = 0; k < 4; ++k) {
+      const int j = it.joint[k];
+      if (j < 0) break;
+      const int res = j & 7;
+      bool known = false;
+      for (int q = 0; q < sl.nseen[quarter][k][res]; ++q) known = known || sl.seen[quarter][k][res][q] == j;
+      if (known) continue;  // same joint: a broadcast
+      int worst = 0;
+      for (int r8 = 0; r8 < 8; ++r8) worst = std::max(worst, sl.nseen[quarter][k][r8]);
+      if (sl.nseen[quarter][k][res] + 1 > std::max(worst, 1)) ++extra;
+    }
+    return extra;
+  };
+  auto place = [&](Slot &sl, int lane, int idx, int delay) {
+    const Item &it = items[idx];
+    sl.lane_item[lane] = idx;
+    sl.lane_delay[lane] = delay;
+    sl.steps = std::max(sl.steps, delay + it.count);
+    ++sl.used;
+    const int quarter = lane >> 3;
+    for (int k = 0; k < 4 && it.joint[k] >= 0; ++k) {
+      const int j = it.joint[k], res = j & 7;
+      bool known = false;
+      for (int q = 0; q < sl.nseen[quarter][k][res]; ++q) known = known || sl.seen[quarter][k][res][q] == j;
+      if (!known && sl.nseen[quarter][k][res] < 8) sl.seen[quarter][k][res][sl.nseen[quarter][k][res]++] = j;
+    }
+  };
+
   for (int t = 0; t < p.num_tiles; ++t) {
     const int r0 = t * tile_rows, r1 = std::min(N, r0 + tile_rows);
-    for (auto &b : bucket) b.clear();
-    // runs of the tile -> items
+    items.clear();
+    // runs of the tile -> items: every row belongs to exactly one item (skinned runs; stretches outside get_rows(): blend -1)
     int r = r0;
-    while (r < r1) {  // every row belongs to exactly one item: skinned runs, and stretches outside get_rows() (blend -1)
+    while (r < r1) {
       const int blend = live(r) ? (int)in.row_blend[r] : -1;
       int e = r + 1;
       if (blend >= 0) while (e < r1 && live(e) && (int)in.row_blend[e] == blend) ++e;
@@ -85,41 +138,155 @@ inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max
       split_run(e - r, K, pieces);
       int s = r;
       for (int len : pieces) {
-        bucket[(s - r0) & 15].push_back(Item{s - r0, len, blend});
+        Item it{s - r0, len, blend, {-1, -1, -1, -1}};
+        if (blend >= 0 && in.blend_offsets != nullptr) {
+          const int beg = in.blend_offsets[blend], cnt = in.blend_offsets[blend + 1] - beg;
+          for (int k = 0; k < std::min(cnt, 4); ++k) it.joint[k] = in.blend_transform[beg + k];
+        }
+        items.push_back(it);
         s += len;
-        ++p.num_items;
       }
       r = e;
     }
-    // longest first inside every residue class, then half-warp h takes the h-th item of each class
-    size_t halves = 0;
-    for (auto &b : bucket) {
-      std::stable_sort(b.begin(), b.end(), [](const Item &x, const Item &y) { return x.count > y.count; });
-      halves = std::max(halves, b.size());
-    }
-    const size_t slots = (halves + 1) / 2;
-    const size_t base = p.items.size();
-    p.items.resize(base + slots * 32, 0u);
-    p.item_blend.resize(base + slots * 32, -1);
-    for (size_t h = 0; h < slots * 2; ++h) {
-      for (int l = 0; l < 16; ++l) {
-        const size_t at = base + h * 16 + l;
-        if (h < bucket[l].size()) {
-          const Item &it = bucket[l][h];
-          p.items[at] = (uint32_t)it.start | ((uint32_t)it.count << kItemStartBits) | (it.blend >= 0 ? kItemSkinned : 0u);
-          p.item_blend[at] = it.blend;
-          p.lane_steps += it.count;
-        } else {
-          ++p.idle_lanes;
+    p.num_items += (long long)items.size();
+    // Half-warp by half-warp, longest items first.  A half-warp lasts c steps, c = the longest item still unplaced.
+    // Its sixteen lanes are filled best fit first: for waste w = 0, 1, 2, ... every free lane l looks for an unplaced
+    // item of exactly c - w rows whose first row is congruent to l + d for some delay d <= w (so the item ends within
+    // the c steps); among several, the one whose joints collide least with the quarter-warp's, then the least delay.
+    for (auto &bk : bucket) bk.clear();
+    for (size_t i = 0; i < items.size(); ++i) bucket[items[i].start & 15].push_back((int)i);
+    for (auto &bk : bucket) std::stable_sort(bk.begin(), bk.end(), [&](int x, int y) { return items[x].count > items[y].count; });
+    size_t remaining = items.size();
+    slots.clear();
+    int half = 0;  // half-warps filled so far
+    while (remaining > 0) {
+      if ((half & 1) == 0) {
+        slots.emplace_back();
+        Slot &ns = slots.back();
+        for (int l = 0; l < 32; ++l) ns.lane_item[l] = -1, ns.lane_delay[l] = 0;
+        for (auto &a : ns.nseen) for (auto &b : a) for (int &c : b) c = 0;
+      }
+      Slot &sl = slots.back();
+      const int lane0 = (half & 1) * 16;
+      int c = sl.steps;  // the second half-warp of a slot lasts at least as long as the first
+      for (auto &bk : bucket) if (!bk.empty()) c = std::max(c, items[bk.front()].count);
+      int free_lanes = 16;
+      for (int w = 0; w < c && free_lanes > 0 && remaining > 0; ++w) {
+        const int want = c - w;
+        for (int l = 0; l < 16 && remaining > 0; ++l) {
+          if (sl.lane_item[lane0 + l] >= 0) continue;
+          int best_pos = -1, best_bucket = -1, best_d = 0, best_extra = 1 << 30;
+          for (int d = 0; d <= std::min(w, 15); ++d) {
+            std::vector<int> &bk = bucket[(l + d) & 15];
+            // bucket sorted by count, descending: the stretch of items with exactly `want` rows
+            size_t lo = 0;
+            while (lo < bk.size() && items[bk[lo]].count > want) ++lo;
+            for (size_t q = lo; q < bk.size() && items[bk[q]].count == want && q < lo + 6; ++q) {
+              const int extra = gather_extra(sl, (lane0 + l) >> 3, items[bk[q]]);
+              if (extra < best_extra) {
+                best_extra = extra;
+                best_pos = (int)q;
+                best_bucket = (l + d) & 15;
+                best_d = d;
+              }
+            }
+            if (best_extra == 0) break;
+          }
+          if (best_pos < 0) continue;
+          std::vector<int> &bk = bucket[best_bucket];
+          place(sl, lane0 + l, bk[best_pos], best_d);
+          bk.erase(bk.begin() + best_pos);
+          --remaining;
+          --free_lanes;
         }
       }
+      // Lanes still free: no unplaced item ends within c steps from them.  Letting the slot grow by g steps admits
+      // items with delay + rows = c + g; every step costs the whole slot kPlanStepCost, every item placed saves its share
+      // of some later slot.  Tentatively fill for g = 1, 2, ..., keep the prefix with the best balance.
+      if (free_lanes > 0 && remaining > 0) {
+        struct Tentative {
+          int lane, bucket, item, d, g;
+        };
+        std::vector<Tentative> tent;
+        std::vector<char> taken_lane(16, 0);
+        std::vector<std::vector<char>> taken(16);
+        for (int r16 = 0; r16 < 16; ++r16) taken[r16].assign(bucket[r16].size(), 0);
+        // rows per cost of the half-warp (half a slot's opening cost + its steps): keep the growth that maximises it
+        long long rows = 0;
+        for (int l = 0; l < 16; ++l)
+          if (sl.lane_item[lane0 + l] >= 0) rows += items[sl.lane_item[lane0 + l]].count;
+        auto cost_of = [&](int steps) { return (double)(kPlanSlotCost / 2 + steps * kPlanStepCost / 2); };
+        double best_ratio = rows > 0 ? (double)rows / cost_of(c) : 0.0;
+        size_t best_prefix = 0;
+        for (int g = 1; g <= 15; ++g) {
+          for (int l = 0; l < 16; ++l) {
+            if (sl.lane_item[lane0 + l] >= 0 || taken_lane[l]) continue;
+            // the longest unplaced item with delay + rows == c + g
+            int bi = -1, bb = -1, bd = 0;
+            for (int d = 0; d <= 15; ++d) {
+              const int want = c + g - d;
+              if (want < 1) break;
+              const std::vector<int> &bk = bucket[(l + d) & 15];
+              for (size_t q = 0; q < bk.size(); ++q) {
+                if (items[bk[q]].count > want) continue;
+                if (items[bk[q]].count < want) break;
+                if (!taken[(l + d) & 15][q]) {
+                  bi = (int)q, bb = (l + d) & 15, bd = d;
+                  break;
+                }
+              }
+              if (bi >= 0) break;
+            }
+            if (bi < 0) continue;
+            taken[bb][bi] = 1;
+            taken_lane[l] = 1;
+            tent.push_back(Tentative{l, bb, bucket[bb][bi], bd, g});
+            rows += items[bucket[bb][bi]].count;
+          }
+          const double ratio = (double)rows / cost_of(c + g);
+          if (ratio > best_ratio * 1.0001) {
+            best_ratio = ratio;
+            best_prefix = tent.size();
+          }
+        }
+        for (size_t q = 0; q < best_prefix; ++q) {
+          place(sl, lane0 + tent[q].lane, tent[q].item, tent[q].d);
+          std::vector<int> &bk = bucket[tent[q].bucket];
+          bk.erase(std::find(bk.begin(), bk.end(), tent[q].item));
+          --remaining;
+        }
+      }
+      ++half;
     }
-    for (size_t s = 0; s < slots; ++s) {
-      int longest = 0;
-      for (int l = 0; l < 32; ++l) longest = std::max(longest, (int)((p.items[base + s * 32 + l] >> kItemStartBits) & kItemMaxRows));
-      p.warp_steps += longest;
+    // longest slot first (the kernel deals a tile's slots to its warps in order)
+    std::stable_sort(slots.begin(), slots.end(), [](const Slot &x, const Slot &y) { return x.steps > y.steps; });
+    const size_t base = p.items.size();
+    p.items.resize(base + slots.size() * 32, 0u);
+    p.item_blend.resize(base + slots.size() * 32, -1);
+    for (size_t si = 0; si < slots.size(); ++si) {
+      const Slot &sl = slots[si];
+      for (int l = 0; l < 32; ++l) {
+        const size_t at = base + si * 32 + l;
+        if (sl.lane_item[l] < 0) {
+          ++p.idle_lanes;
+          continue;
+        }
+        const Item &it = items[sl.lane_item[l]];
+        p.items[at] = (uint32_t)it.start | ((uint32_t)it.count << kItemStartBits) | (it.blend >= 0 ? kItemSkinned : 0u) |
+                      ((uint32_t)sl.lane_delay[l] << kItemDelayShift);
+        p.item_blend[at] = it.blend;
+        p.lane_steps += it.count;
+      }
+      p.warp_steps += sl.steps;
+      for (int q = 0; q < 4; ++q)
+        for (int k = 0; k < 4; ++k) {
+          int worst = 0, any = 0;
+          for (int r8 = 0; r8 < 8; ++r8) worst = std::max(worst, sl.nseen[q][k][r8]), any += sl.nseen[q][k][r8];
+          p.gather_wavefronts += 3 * worst;
+          p.gather_ideal += any ? 3 : 0;
+        }
     }
-    p.num_slots += (long long)slots;
+    p.num_slots += (long long)slots.size();
     p.tile_slot_offsets.push_back((int)(p.items.size() / 32));
   }
   return p;
@@ -128,10 +295,10 @@ inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max
 inline void print_run_plan_stats(const RunPlanHost &p, int num_rows, FILE *f) {
   fprintf(f,
           "run plan: %d rows, tiles of %d rows (%d tiles), items of <= %d rows: %lld items (%.2f rows each), %lld slots (%.2f per tile), "
-          "idle lanes %.1f %%, lockstep efficiency %.1f %% (%lld lane steps / %lld warp steps x 32)\n",
+          "idle lanes %.1f %%, lockstep efficiency %.1f %% (%lld lane steps / %lld warp steps x 32), gather wavefronts %lld (conflict-free: %lld)\n",
           num_rows, p.tile_rows, p.num_tiles, p.max_item_rows, p.num_items, p.num_items ? (double)p.lane_steps / p.num_items : 0.0, p.num_slots,
           p.num_tiles ? (double)p.num_slots / p.num_tiles : 0.0, p.num_slots ? 100.0 * p.idle_lanes / (p.num_slots * 32.0) : 0.0,
-          p.warp_steps ? 100.0 * p.lane_steps / (p.warp_steps * 32.0) : 0.0, p.lane_steps, p.warp_steps);
+          p.warp_steps ? 100.0 * p.lane_steps / (p.warp_steps * 32.0) : 0.0, p.lane_steps, p.warp_steps, p.gather_wavefronts, p.gather_ideal);
 }
 
 }  // namespace p3cs

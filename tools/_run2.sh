@@ -1,3 +1,4 @@
-CMD="python tools/kbench.py --configs c3fixed5,c3 --steps 1 --warmup 1 --instances 2000"
-$CMD > gpurun_out/r2_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:run_kernel -c 4 -o gpurun_out/r2_run_v1 $CMD > gpurun_out/r2_ncu.log 2>&1
+export P3CS_PATH=run
+CMD="python tools/kbench.py --configs c3fixed5,c3 --steps 1 --warmup 1 --instances 2960"
+$CMD > gpurun_out/r2_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:run_kernel -c 4 -o gpurun_out/r2_run_v2 $CMD > gpurun_out/r2_ncu.log 2>&1
 tail -3 gpurun_out/r2_ncu.log
