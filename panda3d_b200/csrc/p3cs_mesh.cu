@@ -381,7 +381,7 @@ static int build_run_plans(p3cs_mesh mesh, const p3cs_mesh_desc *d, const std::v
   const int row_bytes = strip_mode_row_bytes(mode);
   if (row_bytes == 0) return P3CS_OK;
   if (d->num_sliders > 65536) return P3CS_OK;
-  const int fixed = ((64 + m.num_transforms * 64 + 127) & ~127);
+  const int fixed = run_layout(m.num_transforms, 16, row_bytes, 1).tiles_off;
   // kRunCtasPerSm CTAs per SM: 228 KB per SM, 1 KB reserved per CTA
   int budget = (228 * 1024 / kRunCtasPerSm - 1024) - fixed;
   if (budget < 2 * 128 * row_bytes) budget = 113 * 1024 - fixed;   // very large palettes: two CTAs per SM

@@ -181,7 +181,7 @@ inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max
             // bucket sorted by count, descending: the stretch of items with exactly `want` rows
             size_t lo = 0;
             while (lo < bk.size() && items[bk[lo]].count > want) ++lo;
-            for (size_t q = lo; q < bk.size() && items[bk[q]].count == want && q < lo + 6; ++q) {
+            for (size_t q = lo; q < bk.size() && items[bk[q]].count == want && q < lo + 48; ++q) {
               const int extra = gather_extra(sl, (lane0 + l) >> 3, items[bk[q]]);
               if (extra < best_extra) {
                 best_extra = extra;

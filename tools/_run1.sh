@@ -1,6 +1,5 @@
 export P3CS_PATH=run
 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py tests/test_gpu_fuzz.py -m gpu -q -x 2>&1 | tail -15 > gpurun_out/r2_t3.log
 tail -3 gpurun_out/r2_t3.log
-P3CS_DEBUG_PLAN=1 python tools/kbench.py --configs c3,c3rand,c3fixed5,c3tbuv,c3uv,c3tb,c2x > gpurun_out/r2_k1.log 2>&1
-for plan in 1424,2,8 944,3,12 1424,2,16; do echo "plan $plan" >> gpurun_out/r2_k1.log; P3CS_RUN_PLAN=$plan python tools/kbench.py --configs c3 >> gpurun_out/r2_k1.log 2>&1; done
+python tools/kbench.py --configs c3,c3rand,c3fixed5,c3,c3tbuv,c3uv,c3tb,c2x,c3 > gpurun_out/r2_k1.log 2>&1
 cut -c1-330 gpurun_out/r2_k1.log | sed 's/"vertices".*//'
