@@ -94,6 +94,7 @@ struct MeshDev {
 
   // ---- run kernel (p3cs_run.cuh): the row-layout modes kRow24 / 32 / 48 / 56
   int run_mode;                     // StripMode the run kernel handles this mesh in, 0: none
+  int run_lockstep_pct;             // lane steps / (32 x warp steps) of the crowd plan, in percent (kernel choice)
   RunPlanDev run_plan[2];           // [0] crowds (large tiles), [1] launches of a few instances (small tiles, many CTAs)
 };
 

@@ -396,6 +396,7 @@ static int build_run_plans(p3cs_mesh mesh, const p3cs_mesh_desc *d, const std::v
       K = c;
     }
   }
+  const int trim = getenv("P3CS_RUN_TRIM") != nullptr ? atoi(getenv("P3CS_RUN_TRIM")) : 4;  // see build_run_plan
   RunPlanInput in;
   in.num_rows = m.num_rows;
   in.row_blend = row_index.data();
@@ -404,13 +405,14 @@ static int build_run_plans(p3cs_mesh mesh, const p3cs_mesh_desc *d, const std::v
   in.blend_transform = d->blend_transform;
   int rc;
   {
-    const RunPlanHost hp = build_run_plan(in, tile_rows, K);
+    const RunPlanHost hp = build_run_plan(in, tile_rows, K, trim);
     if (getenv("P3CS_DEBUG_PLAN") != nullptr) print_run_plan_stats(hp, m.num_rows, stderr);
+    m.run_lockstep_pct = hp.warp_steps > 0 ? (int)(100 * hp.lane_steps / (32 * hp.warp_steps)) : 0;
     if ((rc = upload_run_plan(mesh, d, hp, bufs, &m.run_plan[0])) != P3CS_OK) return rc;
   }
   if (tile_rows > 256) {
     const int small_bufs = fixed + 3 * 256 * row_bytes <= 228 * 1024 / kRunCtasPerSm - 1024 ? 3 : 2;
-    const RunPlanHost hp = build_run_plan(in, 256, K);
+    const RunPlanHost hp = build_run_plan(in, 256, K, trim);
     if ((rc = upload_run_plan(mesh, d, hp, small_bufs, &m.run_plan[1])) != P3CS_OK) return rc;
   }
   m.run_mode = mode;

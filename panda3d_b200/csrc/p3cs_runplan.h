@@ -68,7 +68,7 @@ constexpr int kPlanSlotCost = 380;   // opening a slot: blending a matrix per la
 constexpr int kPlanStepCost = 82;    // one more step of a slot: a row per lane
 constexpr int kPlanGatherCost = 3;   // one more wavefront of a palette gather (three 128-bit loads per entry)
 
-inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max_item_rows) {
+inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max_item_rows, int trim_below = 0) {
   RunPlanHost p;
   p.tile_rows = tile_rows;
   p.max_item_rows = std::min(max_item_rows, kItemMaxRows);
@@ -169,6 +169,41 @@ inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max
       Slot &sl = slots.back();
       const int lane0 = (half & 1) * 16;
       int c = sl.steps;  // the second half-warp of a slot lasts at least as long as the first
+      if ((half & 1) == 0 && trim_below > 0) {
+        // A new slot lasts as long as the longest item left.  If only a few items are that long, the slot's other lanes
+        // idle for their sake: cut their last row off (it becomes an item of its own, which finds an idle lane in one of
+        // the short slots at the end of the tile) until the longest class is worth a slot.
+        for (;;) {
+          int longest = 0, n_longest = 0;
+          for (auto &bk : bucket)
+            if (!bk.empty()) {
+              const int top = items[bk.front()].count;
+              if (top > longest) longest = top, n_longest = 0;
+              if (top == longest)
+                for (size_t q = 0; q < bk.size() && items[bk[q]].count == longest; ++q) ++n_longest;
+            }
+          if (longest <= 2 || n_longest >= trim_below) break;
+          for (int r16 = 0; r16 < 16; ++r16) {
+            std::vector<int> &bk = bucket[r16];
+            size_t q = 0;
+            while (q < bk.size() && items[bk[q]].count == longest) {
+              Item &it = items[bk[q]];
+              --it.count;
+              Item tail = it;
+              tail.start = it.start + it.count;
+              tail.count = 1;
+              items.push_back(tail);
+              const int ti = (int)items.size() - 1;
+              std::vector<int> &tb = bucket[tail.start & 15];
+              tb.push_back(ti);  // one-row items sort last
+              ++remaining;
+              ++p.num_items;
+              ++q;
+            }
+            // the trimmed items now tie with the next class: the bucket stays sorted (descending, stable)
+          }
+        }
+      }
       for (auto &bk : bucket) if (!bk.empty()) c = std::max(c, items[bk.front()].count);
       int free_lanes = 16;
       for (int w = 0; w < c && free_lanes > 0 && remaining > 0; ++w) {

@@ -101,12 +101,17 @@ int strip_mode_row_bytes(int mode) {
 }
 
 // ---- run kernel: which plan, how many CTAs per instance
-static bool use_run_kernel(const MeshDev &mesh) {
-  static const bool on = [] {  // P3CS_PATH=run: the run kernel takes the kRow modes (until it beats the strip kernel on every layout)
-    const char *e = getenv("P3CS_PATH");
-    return e != nullptr && strcmp(e, "run") == 0;
-  }();
-  return mesh.run_mode != 0 && on;
+// Which kernel takes a launch of `count` instances.  The run kernel (p3cs_run.cuh) wins where the strip kernel is
+// bound by its per-row record reads: 24-, 32- and 48-byte rows without morphs (measured on B200, crowds of the C3
+// character: 1.25 / 1.81 / 2.14 ms against 1.46 / 1.86 / 2.42 ms).  The strip kernel keeps 56-byte rows (2.24 ms against
+// 2.39), meshes with morph sliders (its per-row morph ranges are prefetched a tile ahead), plans that walk badly in
+// lockstep, and launches of a few thousand rows.  P3CS_PATH=run / strip forces one of them (A/B runs, parity tests).
+static bool use_run_kernel(const MeshDev &mesh, int count) {
+  const char *e = getenv("P3CS_PATH");  // read per launch: the parity tests switch it between calls
+  const int forced = e == nullptr ? 0 : strcmp(e, "run") == 0 ? 1 : strcmp(e, "strip") == 0 ? -1 : 0;
+  if (mesh.run_mode == 0 || forced < 0) return false;
+  if (forced > 0) return true;
+  return mesh.run_mode != kRow56 && !mesh.has_morphs && mesh.run_lockstep_pct >= 62 && (long long)mesh.num_rows * count >= 8192;
 }
 
 struct RunLaunch {
@@ -130,7 +135,7 @@ static RunLaunch run_partition(const MeshDev &mesh, int count, int sm_count) {
 
 int strip_ctas_per_instance(const MeshDev &mesh, int count, int sm_count) {
   if (mesh.num_rows == 0 || count == 0 || mesh.num_tiles == 0) return 0;
-  if (use_run_kernel(mesh)) return run_partition(mesh, count, sm_count).ctas_per_instance;
+  if (use_run_kernel(mesh, count)) return run_partition(mesh, count, sm_count).ctas_per_instance;
   int gpc;
   return strip_partition(mesh, count, sm_count, &gpc);
 }
@@ -159,7 +164,7 @@ int launch_strip(const MeshDev &mesh, const GroupDev &grp, int first_instance, i
   if (mesh.num_rows == 0 || count == 0 || mesh.num_tiles == 0) return 0;
   int want_normal = 0;
   for (int c = 0; c < mesh.num_dyn; ++c) want_normal |= (mesh.dyn[c].skin == 3);
-  if (use_run_kernel(mesh)) return launch_run(mesh, grp, first_instance, count, sm_count, want_normal, stream);
+  if (use_run_kernel(mesh, count)) return launch_run(mesh, grp, first_instance, count, sm_count, want_normal, stream);
   const size_t smem = strip_smem_bytes(mesh);
   const int mode = strip_pick_mode(mesh);
   int gpc;

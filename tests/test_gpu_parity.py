@@ -1152,3 +1152,84 @@ def test_slider_channels_on_gpu_ripple(gpu_ctx, fixture):
         grp.close()
         dskel.close()
         dmesh.close()
+
+
+RUN_KERNEL_CASES = {
+    # layout -> make_mesh keywords; every case also runs with sparse rows, blends of 1..6 entries and a non-affine palette
+    "packed": dict(),
+    "texcoord": dict(texcoord=True),
+    "tbn": dict(tbn=True),
+    "tbn_uv": dict(tbn=True, texcoord=True),
+    "packed_morph": dict(num_sliders=3, slider_band=0.4, morph_columns=("vertex", "normal")),
+    "tbn_uv_morph": dict(tbn=True, texcoord=True, num_sliders=3, slider_band=0.4, morph_columns=("vertex", "tangent")),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", ["runs", "random", "fixed4", "sorted"])
+@pytest.mark.parametrize("layout", sorted(RUN_KERNEL_CASES))
+def test_run_kernel_and_strip_kernel_agree(gpu_ctx, monkeypatch, layout, order):
+    """The two kernels of the row-layout modes (p3cs_run.cuh: one thread per run of rows; p3cs_strip.cuh: one thread per
+    row) give the same bytes, and the oracle's, on crowds of every layout: runs / random / aligned runs / long runs of
+    the blend index, rows outside get_rows(), blends of 1..6 entries, selection read-back, tight bounds, instance lists."""
+    kw = dict(RUN_KERNEL_CASES[layout])
+    rows = 4_571
+    sm = synth.make_mesh(rows, 40, 700, seed=300 + len(layout), index_order=order, rows=[(3, 1500), (1507, 4000), (4100, rows)], **kw)
+    mesh = sm.flat
+    # blends of 1..6 entries: re-cut the CSR (entries stay in ascending transform order)
+    rng = np.random.default_rng(7)
+    offs, xf, w = [0], [], []
+    for b in range(mesh.num_blends):
+        k = int(rng.integers(1, 7))
+        j = np.sort(rng.choice(mesh.num_transforms, size=k, replace=False))
+        ww = rng.uniform(0.05, 1.0, k).astype(np.float32)
+        ww = (ww / ww.sum(dtype=np.float32)).astype(np.float32)
+        xf += list(j)
+        w += list(ww)
+        offs.append(len(xf))
+    mesh.blend_offsets = np.asarray(offs, np.int32)
+    mesh.blend_transform = np.asarray(xf, np.int32)
+    mesh.blend_weight = np.asarray(w, np.float32)
+    n = 9
+    pal = synth.make_palettes(mesh.num_transforms, n, 41).reshape(n, mesh.num_transforms, 16).copy()
+    pal[4, :, 15] = 1.0
+    pal[4, 5, 3] = 0.25      # instance 4: a palette that is not affine (general 4x4 inverse branch)
+    sl = synth.make_sliders(mesh.num_sliders, n, 42) if mesh.num_sliders else None
+    om = oracle.OracleMesh(mesh)
+    results = {}
+    for path in ("run", "strip"):
+        monkeypatch.setenv("P3CS_PATH", path)
+        dmesh = _capi.Mesh(gpu_ctx, mesh)
+        grp = _capi.Group(dmesh, n)
+        try:
+            assert np.array_equal(grp.read_selection(), expected_selection(mesh)), f"{path}: selection differs"
+            grp.set_palettes(pal.reshape(n, -1))
+            if sl is not None:
+                grp.set_sliders(sl)
+            grp.enable_bounds()
+            grp.animate()
+            out = grp.read_output(0).copy()
+            bounds = grp.read_bounds().copy()
+            grp.enable_bounds(enable=False)
+            # scribble, then recompute only three instances
+            grp.set_palettes(np.zeros((n, mesh.num_transforms * 16), np.float32))
+            grp.animate()
+            grp.set_palettes(pal.reshape(n, -1))
+            grp.animate_instances([7, 0, 4])
+            listed = grp.read_output(0).copy()
+            results[path] = (out, bounds, listed)
+        finally:
+            grp.close()
+            dmesh.close()
+    out_r, bounds_r, listed_r = results["run"]
+    out_s, bounds_s, listed_s = results["strip"]
+    assert np.array_equal(out_r, out_s), "run kernel and strip kernel differ"
+    assert np.array_equal(bounds_r.view(np.uint32), bounds_s.view(np.uint32)), "tight bounds differ between the kernels"
+    assert np.array_equal(listed_r, listed_s)
+    for i in (0, 4, 7):
+        assert np.array_equal(listed_r[i], out_r[i])
+    for i in range(n):
+        expect, _, _ = om.animate(pal[i].reshape(-1, 16), sl[i] if sl is not None else None)
+        compare_outputs(mesh, [out_r[i]], expect, f"{layout}/{order} instance {i}")
+        v = out_r[i].reshape(rows, -1)[:, :12].copy().view(np.float32)
+        assert np.array_equal(bounds_r[i][:3], v.min(axis=0)) and np.array_equal(bounds_r[i][3:6], v.max(axis=0))

@@ -22,7 +22,7 @@ int main(int argc, char **argv) {
   in.blend_offsets = off.data();
   in.blend_transform = xf.data();
   auto t0 = std::chrono::steady_clock::now();
-  p3cs::RunPlanHost p = p3cs::build_run_plan(in, atoi(argv[4]), atoi(argv[5]));
+  p3cs::RunPlanHost p = p3cs::build_run_plan(in, atoi(argv[4]), atoi(argv[5]), argc > 6 ? atoi(argv[6]) : 0);
   double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   p3cs::print_run_plan_stats(p, in.num_rows, stdout);
   const long long issue = p.num_slots * 330 + p.warp_steps * 70, lsu = p.gather_wavefronts + p.warp_steps * 12;
