@@ -381,9 +381,11 @@ static int build_run_plans(p3cs_mesh mesh, const p3cs_mesh_desc *d, const std::v
   const int row_bytes = strip_mode_row_bytes(mode);
   if (row_bytes == 0) return P3CS_OK;
   if (d->num_sliders > 65536) return P3CS_OK;
-  const int fixed = run_layout(m.num_transforms, 16, row_bytes, 1).tiles_off;
-  // kRunCtasPerSm CTAs per SM: 228 KB per SM, 1 KB reserved per CTA
-  int budget = (228 * 1024 / kRunCtasPerSm - 1024) - fixed;
+  int threads, ctas;
+  run_shape(mode, &threads, &ctas);
+  const int fixed = run_layout(m.num_transforms, 16, row_bytes, 1, threads).tiles_off;
+  // `ctas` CTAs per SM: 228 KB per SM, 1 KB reserved per CTA
+  int budget = (228 * 1024 / ctas - 1024) - fixed;
   if (budget < 2 * 128 * row_bytes) budget = 113 * 1024 - fixed;   // very large palettes: two CTAs per SM
   if (budget < 2 * 64 * row_bytes) return P3CS_OK;                 // does not fit: the strip kernel's own fallbacks apply
   int tile_rows = std::min(4096, (budget / 2 / row_bytes) & ~15), bufs = 2, K = 12;
@@ -411,7 +413,7 @@ static int build_run_plans(p3cs_mesh mesh, const p3cs_mesh_desc *d, const std::v
     if ((rc = upload_run_plan(mesh, d, hp, bufs, &m.run_plan[0])) != P3CS_OK) return rc;
   }
   if (tile_rows > 256) {
-    const int small_bufs = fixed + 3 * 256 * row_bytes <= 228 * 1024 / kRunCtasPerSm - 1024 ? 3 : 2;
+    const int small_bufs = fixed + 3 * 256 * row_bytes <= 228 * 1024 / ctas - 1024 ? 3 : 2;
     const RunPlanHost hp = build_run_plan(in, 256, K, trim);
     if ((rc = upload_run_plan(mesh, d, hp, small_bufs, &m.run_plan[1])) != P3CS_OK) return rc;
   }

@@ -143,7 +143,9 @@ int strip_ctas_per_instance(const MeshDev &mesh, int count, int sm_count) {
 static int launch_run(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, int sm_count, int want_normal, cudaStream_t stream) {
   const RunLaunch rl = run_partition(mesh, count, sm_count);
   const RunPlanDev &plan = mesh.run_plan[rl.plan];
-  const size_t smem = (size_t)run_layout(mesh.num_transforms, plan.tile_rows, strip_mode_row_bytes(mesh.run_mode), plan.tile_bufs).total;
+  int threads, ctas;
+  run_shape(mesh.run_mode, &threads, &ctas);
+  const size_t smem = (size_t)run_layout(mesh.num_transforms, plan.tile_rows, strip_mode_row_bytes(mesh.run_mode), plan.tile_bufs, threads).total;
   int launches = 0;
   for (int c0 = 0; c0 < count; c0 += 65535) {
     const int cn = count - c0 < 65535 ? count - c0 : 65535;

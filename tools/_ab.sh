@@ -7,7 +7,5 @@ for rep in 1 2; do for v in A B; do
   echo "== $v" >> gpurun_out/r2_ab.log
   timeout 200 python tools/kbench.py --configs $1 >> gpurun_out/r2_ab.log 2>&1
 done; done
-echo "== B trim 0" >> gpurun_out/r2_ab.log
-P3CS_RUN_TRIM=0 timeout 200 python tools/kbench.py --configs $1 >> gpurun_out/r2_ab.log 2>&1
 cp /tmp/keep.so panda3d_b200/libp3cudaskin.so
 sed 's/"vertices".*//' gpurun_out/r2_ab.log
