@@ -48,7 +48,7 @@ extern "C" {
 #define P3CS_EXPORT __attribute__((visibility("default")))
 #endif
 
-#define P3CS_API_VERSION 2
+#define P3CS_API_VERSION 3
 
 typedef enum p3cs_status {
   P3CS_OK = 0,
@@ -459,6 +459,15 @@ P3CS_EXPORT int p3cs_blends_from_hardware(int32_t num_rows, const float *weights
                                           int32_t table_size, int32_t *row_blend, int32_t *blend_offsets,
                                           int32_t *blend_transform, float *blend_weight, int32_t *num_blends);
 
+/* Per-instance destinations of output array `output`: instance i's animated rows (num_rows * stride bytes) go to
+ * ptrs[i] instead of the group's own [n][pitch] buffer.  Every pointer is device memory, or host memory page-locked
+ * with p3cs_host_register (the kernel's bulk stores then write it over PCIe), 16-byte aligned.  This is how a frame's
+ * worth of Characters that share one mesh -- each with its own result GeomVertexData, the `_animated_vertices` the
+ * reference reuses in place (panda/src/gobj/geomVertexData.cxx:1448-1453) -- is animated by ONE launch straight into
+ * those objects' arrays.  `ptrs` holds n entries and is copied; NULL restores the group's buffer.  The destinations
+ * must stay valid until the animate call that uses them has been synchronised. */
+P3CS_EXPORT int p3cs_group_set_output_pointers(p3cs_group grp, int output, void *const *ptrs);
+
 /* ---- plugin table (load_dso + dlsym("p3cs_get_api")) -------------------- */
 
 typedef struct p3cs_api {
@@ -481,6 +490,9 @@ typedef struct p3cs_api {
   int (*host_register)(p3cs_context, void *, size_t);
   int (*host_unregister)(p3cs_context, void *);
   int (*animate_groups)(p3cs_group const *, int);
+  /* version 3 */
+  int (*group_set_output_pointers)(p3cs_group, int, void *const *);
+  int (*group_animate_instances)(p3cs_group, const int32_t *, int);
 } p3cs_api;
 
 P3CS_EXPORT const p3cs_api *p3cs_get_api(void);

@@ -37,6 +37,7 @@ EXPORTED_SYMBOLS = [
     "p3cs_hardware_from_blends", "p3cs_blends_from_hardware", "p3cs_group_animate_instances",
     "p3cs_group_pose_blend", "p3cs_skeleton_add_animation", "p3cs_group_pose_controls",
     "p3cs_group_set_forced_joints", "p3cs_group_set_forced_values", "p3cs_group_set_bounds_rows",
+    "p3cs_group_set_output_pointers",
 ]
 
 
@@ -517,6 +518,17 @@ class Group:
         return out
 
     # ---- the hot path
+    def set_output_pointers(self, pointers, o: int = 0) -> None:
+        """p3cs_group_set_output_pointers: per-instance destinations (device or page-locked host addresses) of output `o`;
+        None restores the group's own buffer."""
+        L = lib()
+        L.p3cs_group_set_output_pointers.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        if pointers is None:
+            _check(L.p3cs_group_set_output_pointers(self.handle, o, None))
+            return
+        arr = (C.c_void_p * self.n)(*[int(p) for p in pointers])
+        _check(L.p3cs_group_set_output_pointers(self.handle, o, arr))
+
     def animate(self) -> None:
         _check(lib().p3cs_group_animate(self.handle))
 

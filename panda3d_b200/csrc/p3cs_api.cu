@@ -500,6 +500,44 @@ extern "C" int p3cs_group_animate_instances(p3cs_group grp, const int32_t *host_
   return animate_range(grp, 0, count, true, nullptr, &listed);
 }
 
+extern "C" int p3cs_group_set_output_pointers(p3cs_group grp, int output, void *const *ptrs) {
+  if (grp == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_set_output_pointers: group is NULL");
+  const MeshDev &m = grp->mesh->dev;
+  if (output < 0 || output >= m.num_outputs) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_set_output_pointers: output %d out of range", output);
+  DeviceGuard g(grp->mesh->ctx->device);
+  cudaStream_t s = grp->mesh->ctx->stream;
+  ++grp->epoch;
+  if (ptrs == nullptr) {
+    grp->dev.out_ptrs[output] = nullptr;
+    return P3CS_OK;
+  }
+  std::vector<void *> dev((size_t)grp->n);
+  for (int i = 0; i < grp->n; ++i) {
+    if (ptrs[i] == nullptr || reinterpret_cast<uintptr_t>(ptrs[i]) % 16 != 0)
+      return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_set_output_pointers: destination %d is NULL or not 16-byte aligned", i);
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, ptrs[i]) != cudaSuccess || attr.devicePointer == nullptr ||
+        (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeHost && attr.type != cudaMemoryTypeManaged)) {
+      cudaGetLastError();
+      return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_set_output_pointers: destination %d is neither device memory nor page-locked host memory "
+                       "(p3cs_host_register)", i);
+    }
+    dev[(size_t)i] = attr.devicePointer;
+  }
+  if (grp->out_ptrs_dev[output] == nullptr) {
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, (size_t)grp->n * sizeof(void *)));
+    grp->allocations.push_back(p);
+    grp->out_ptrs_dev[output] = static_cast<void **>(p);
+  } else {
+    CUDA_TRY(cudaStreamSynchronize(s));  // an animate in flight may still read the old table
+  }
+  CUDA_TRY(cudaMemcpyAsync(grp->out_ptrs_dev[output], dev.data(), dev.size() * sizeof(void *), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));  // `dev` dies with this frame
+  grp->dev.out_ptrs[output] = reinterpret_cast<uint8_t *const *>(grp->out_ptrs_dev[output]);
+  return P3CS_OK;
+}
+
 extern "C" int p3cs_group_set_profiling(p3cs_group grp, int enable) {
   if (grp == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_set_profiling: group is NULL");
   grp->profiling = enable != 0;
@@ -550,7 +588,9 @@ extern "C" int p3cs_group_enable_bounds(p3cs_group grp, const p3cs_column_desc *
     CUDA_TRY(cudaMalloc(&p, std::max<size_t>((size_t)grp->n * 32, 256)));
     grp->allocations.push_back(p);
     grp->bounds_buf = static_cast<float *>(p);
-    launch_bounds_init(GroupDev{nullptr, nullptr, nullptr, {}, {}, nullptr, grp->bounds_buf, 0, 0, nullptr}, 0, grp->n, mesh->ctx->stream);
+    GroupDev only_bounds{};
+    only_bounds.bounds = grp->bounds_buf;
+    launch_bounds_init(only_bounds, 0, grp->n, mesh->ctx->stream);
   }
   grp->dev.bounds = grp->bounds_buf;
   grp->dev.bounds_output = o;
@@ -605,6 +645,8 @@ extern "C" int p3cs_group_read_output(p3cs_group grp, int o, int first, int coun
   if (rc != P3CS_OK) return rc;
   const MeshDev &m = grp->mesh->dev;
   if (o < 0 || o >= m.num_outputs || host_dst == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_read_output: bad output / destination");
+  if (grp->dev.out_ptrs[o] != nullptr)
+    return p3cs_fail(P3CS_ERR_INVALID, "p3cs_group_read_output: output %d goes to per-instance destinations (p3cs_group_set_output_pointers)", o);
   DeviceGuard g(grp->mesh->ctx->device);
   const size_t row_bytes = (size_t)m.num_rows * m.stride[o];
   if (row_bytes == 0 || count == 0) return P3CS_OK;
@@ -683,6 +725,7 @@ extern "C" int p3cs_animate_vertices(p3cs_group grp, int instance, const float *
            cudaPointerGetAttributes(&attr, host_outputs[o]) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
            attr.devicePointer != nullptr;
       if (ok) direct.out[o] = reinterpret_cast<uint8_t *>(reinterpret_cast<uintptr_t>(attr.devicePointer) - (uintptr_t)instance * grp->dev.pitch[o]);
+      direct.out_ptrs[o] = nullptr;
     }
     cudaGetLastError();  // cudaPointerGetAttributes on plain malloc memory may leave a sticky-free error behind
     if (ok) {
@@ -992,6 +1035,7 @@ extern "C" const p3cs_api *p3cs_get_api(void) {
       P3CS_API_VERSION,        p3cs_device_count,  p3cs_last_error,        p3cs_context_create, p3cs_context_destroy,
       p3cs_context_sync,       p3cs_mesh_create,   p3cs_mesh_destroy,      p3cs_group_create,   p3cs_group_destroy,
       p3cs_group_set_palettes, p3cs_group_set_sliders, p3cs_group_animate, p3cs_group_read_output, p3cs_animate_vertices,
-      p3cs_host_register,      p3cs_host_unregister, p3cs_animate_groups};
+      p3cs_host_register,      p3cs_host_unregister, p3cs_animate_groups,
+      p3cs_group_set_output_pointers, p3cs_group_animate_instances};
   return &api;
 }

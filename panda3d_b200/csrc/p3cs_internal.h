@@ -62,6 +62,7 @@ struct p3cs_group_s {
   std::vector<int> prof_kind;     // 0 blend, 1 skin, per pair
   bool profiling = false;
   float *bounds_buf = nullptr;  // [n][8] animated tight bounds (p3cs_group_enable_bounds)
+  void **out_ptrs_dev[p3cs::kMaxOutputs] = {nullptr, nullptr, nullptr, nullptr};  // p3cs_group_set_output_pointers
   int *list_dev = nullptr;      // instance list of the last p3cs_group_animate_instances
   int list_capacity = 0;
   int *frames_dev = nullptr;  // per-instance animation frames of the last p3cs_group_pose

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kSkinThreads) skin_kernel(MeshDev mesh, GroupD
       const size_t offset = (size_t)(row0 + rbase) * stride;  // multiple of 16: row0, rbase are multiples of 64... see launch
       const int bytes = chunk_rows * stride;
       const uint8_t *src = mesh.src[o] + offset;
-      uint8_t *dst = grp.out[o] + (size_t)inst * grp.pitch[o] + offset;
+      uint8_t *dst = output_base(grp, o, inst) + offset;
 
       // -------- HBM -> smem, 128-bit coalesced (tail in 32-bit words)
       const int n16 = bytes >> 4;
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) bounds_scan_kernel(MeshDev mesh, GroupDev
   __shared__ float scratch[8 * 7];
   const int inst = first_instance + blockIdx.y;
   const int o = grp.bounds_output;
-  const uint8_t *base = grp.out[o] + (size_t)inst * grp.pitch[o] + grp.bounds_start;
+  const uint8_t *base = output_base(grp, o, inst) + grp.bounds_start;
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(mesh.num_rows, r0 + rows_per_cta);
   BoundsAcc acc;
   acc.reset();

@@ -106,6 +106,7 @@ struct GroupDev {
   float *records;         // [chunk][B][rec]
   uint8_t *out[kMaxOutputs];
   size_t pitch[kMaxOutputs];
+  uint8_t *const *out_ptrs[kMaxOutputs];  // optional per-instance destinations (p3cs_group_set_output_pointers); NULL: out + instance * pitch
   int32_t *selection;     // optional [num_rows] debug/parity output (instance 0 of the launch)
   // optional animated tight bounds ("next" row f4): [n][8] = min xyz, max xyz, max |v|^2, found_any
   float *bounds;
@@ -116,6 +117,13 @@ struct GroupDev {
   // optional: bit r = row r is referenced by a primitive and counts for the bounds (p3cs_group_set_bounds_rows); NULL = every row
   const uint32_t *bounds_rows;
 };
+
+// where instance `inst`'s rows of output `o` go
+__device__ __forceinline__ uint8_t *output_base(const GroupDev &grp, int o, int inst) {
+  if (grp.out_ptrs[o] != nullptr)
+    return reinterpret_cast<uint8_t *>(__ldg(reinterpret_cast<const unsigned long long *>(grp.out_ptrs[o]) + inst));
+  return grp.out[o] + (size_t)inst * grp.pitch[o];
+}
 
 __device__ __forceinline__ bool bounds_wants(const GroupDev &grp, int row) {
   return grp.bounds_rows == nullptr || ((__ldg(grp.bounds_rows + (row >> 5)) >> (row & 31)) & 1u) != 0;

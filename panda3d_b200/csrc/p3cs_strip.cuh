@@ -766,11 +766,11 @@ __global__ void __launch_bounds__(kStripThreads, MODE == kGenericFull ? 2 : 4)
         const uint32_t tile_s = tiles_s + buf * tile_bytes;
         if (FAST) {
           const uint32_t bytes = (uint32_t)((rows * stride0 + 15) & ~15);
-          bulk_s2g(grp.out[0] + (size_t)inst * grp.pitch[0] + (size_t)row0 * stride0, tile_s, bytes);
+          bulk_s2g(output_base(grp, 0, inst) + (size_t)row0 * stride0, tile_s, bytes);
         } else {
           for (int o = 0; o < mesh.num_outputs; ++o) {
             const uint32_t bytes = (uint32_t)((rows * mesh.stride[o] + 15) & ~15);
-            bulk_s2g(grp.out[o] + (size_t)inst * grp.pitch[o] + (size_t)row0 * mesh.stride[o], tile_s + kSlicesPerTile * mesh.slice_out_offset[o], bytes);
+            bulk_s2g(output_base(grp, o, inst) + (size_t)row0 * mesh.stride[o], tile_s + kSlicesPerTile * mesh.slice_out_offset[o], bytes);
           }
         }
         bulk_commit();

@@ -27,7 +27,7 @@ def test_header_symbols_all_exported(library):
 
 
 def test_api_version_and_plugin_table(library):
-    assert library.p3cs_api_version() == 2
+    assert library.p3cs_api_version() == 3
     assert library.p3cs_get_api()  # non-NULL table of function pointers (dlsym("p3cs_get_api") convention)
 
 
@@ -66,4 +66,4 @@ def test_plain_c_host_loads_the_plugin_table(tmp_path):
                     os.path.join(ROOT, "examples", "plugin_host.c"), "-ldl", "-o", str(exe)], check=True)
     res = subprocess.run([str(exe), _capi.LIB_PATH], capture_output=True, text=True, timeout=60)
     assert res.returncode == 0, res.stderr
-    assert "p3cs api version 2" in res.stdout
+    assert "p3cs api version 3" in res.stdout

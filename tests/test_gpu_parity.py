@@ -1233,3 +1233,47 @@ def test_run_kernel_and_strip_kernel_agree(gpu_ctx, monkeypatch, layout, order):
         compare_outputs(mesh, [out_r[i]], expect, f"{layout}/{order} instance {i}")
         v = out_r[i].reshape(rows, -1)[:, :12].copy().view(np.float32)
         assert np.array_equal(bounds_r[i][:3], v.min(axis=0)) and np.array_equal(bounds_r[i][3:6], v.max(axis=0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["packed", "tbn_uv", "align16"])
+def test_per_instance_output_pointers(gpu_ctx, layout):
+    """p3cs_group_set_output_pointers: one launch animates a crowd straight into per-instance destinations -- separately
+    page-locked host arrays (the `_animated_vertices` arrays of a frame's Characters) -- byte for byte what the group's
+    own buffer receives; NULL restores that buffer."""
+    kw = dict(packed={}, tbn_uv=dict(tbn=True, texcoord=True), align16=dict(align16=True))[layout]
+    sm = synth.make_mesh(2_501, 24, 300, seed=77, index_order="runs", **kw)
+    mesh = sm.flat
+    n = 13
+    pal = synth.make_palettes(mesh.num_transforms, n, 78).reshape(n, -1)
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, n)
+    stride = dmesh.out_strides[0]
+    nbytes = (mesh.num_rows * stride + 15) // 16 * 16   # the kernel's bulk stores move whole 16-byte units
+    hosts = [np.zeros(nbytes + 64, np.uint8) for _ in range(n)]
+    views = []
+    try:
+        grp.set_palettes(pal)
+        grp.animate()
+        expect = grp.read_output(0).copy()
+        for h in hosts:
+            off = (-h.ctypes.data) % 16
+            v = h[off:off + nbytes]
+            gpu_ctx.host_register(v)
+            views.append(v)
+        grp.set_output_pointers([v.ctypes.data for v in views])
+        grp.animate()
+        gpu_ctx.sync()
+        for i, v in enumerate(views):
+            assert np.array_equal(v[:mesh.num_rows * stride].reshape(mesh.num_rows, stride), expect[i]), f"instance {i}"
+        with pytest.raises(_capi.P3csError):
+            grp.read_output(0)
+        grp.set_output_pointers(None)
+        grp.set_palettes(pal[::-1].copy())
+        grp.animate()
+        assert np.array_equal(grp.read_output(0), expect[::-1])
+    finally:
+        for v in views:
+            gpu_ctx.host_unregister(v)
+        grp.close()
+        dmesh.close()

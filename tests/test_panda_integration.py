@@ -1,5 +1,6 @@
 """The drop-in inside real Panda3D: integration/_build/panda_cuda_check (built here by
-integration/build.sh against the unmodified reference, shipped to the GPU box) loads
+integration/build.sh against the reference + the 27-line hook of integration/geomVertexData.patch, shipped to the GPU
+box) loads
 models/panda-model.egg + panda-walk4.egg (BASELINE configs[0]) through the reference's own egg
 loader, poses frames, and compares the reference's GeomVertexData::animate_vertices with the shim
 (integration/cudaSkinBackend.cxx -> C-ABI -> B200) byte for byte in the same process."""
@@ -28,8 +29,11 @@ def test_real_panda_actor_through_the_shim():
     assert out["ok"], out
     assert out["frames"] == len(frames) and out["rows"] == 1338
     assert out["same_result_object"]            # same output object reused / cached (geomVertexData.cxx:895-960)
-    assert out["max_rel_err"] <= 1e-5           # north_star tolerance; in practice every byte matches
-    assert out["differing_bytes"] <= out["bytes_compared"] * 1e-3
+    assert out["stock_callers_agree"]           # Geom::get_animated_vertex_data lands on the same object (gobj/geom.cxx:287-288)
+    assert out["animate_vertices_request"]      # ... and so does AnimateVerticesRequest (gobj/animateVerticesRequest.cxx:28)
+    assert out["entries_before_clear"] == 1 and out["entries_after_clear"] == 0   # clear_animated_vertices releases the device copy
+    assert out["max_rel_err"] <= 1e-5           # north_star tolerance
+    assert out["differing_bytes"] <= 16         # a blend of frame 13 takes the sinf / cosf normal branch (last-place differences)
 
 
 @pytest.mark.gpu
@@ -51,6 +55,30 @@ def test_real_morph_character_through_the_shim():
     assert out["frames"] == len(frames) and out["rows"] == 641
     assert out["same_result_object"]
     assert out["differing_bytes"] == 0          # morphs + one rigid joint: no libm on this path
+
+
+@pytest.mark.gpu
+def test_crowd_of_panda_actors_is_one_launch_per_frame():
+    """1000 copies of the panda Actor (NodePath::copy_to: own joints, own vertex data and TransformBlendTable, shared
+    arrays), each on its own frame: CudaSkinBackend::animate_frame animates all of them with ONE kernel launch into
+    their own result objects; the stock Geom::get_animated_vertex_data calls then hit the cache.  Bytes equal to the
+    reference's CPU loops run in the same process on the same objects."""
+    if not os.path.exists(CHECK):
+        pytest.skip("integration/_build/panda_cuda_check not built (needs the reference tree: integration/build.sh)")
+    models = os.path.join(ROOT, "integration", "_build", "models")
+    res = subprocess.run([CHECK, os.path.join(ROOT, "panda3d_b200"), os.path.join(models, "panda-model.egg"),
+                          os.path.join(models, "panda-walk4.egg"), "--crowd", "1000", "8"], capture_output=True, text=True, timeout=600)
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert line, res.stdout + res.stderr
+    out = json.loads(line[-1])
+    print(out)
+    assert out["ok"], out
+    assert out["crowd"] == 1000 and out["rows"] == 1338
+    assert out["device_meshes"] == 1            # every copy is an instance of ONE device mesh
+    assert out["launches_last_frame"] == 1 and out["batched_last_frame"] == 1000
+    assert out["max_rel_err"] <= 1e-5 and out["differing_bytes"] <= out["bytes_compared"] * 1e-5   # (sinf / cosf normal branch)
+    assert out["bytes_compared"] >= 1000 * 1338 * 32
+    assert out["cuda_ms_per_frame_e2e"] < out["cpu_ms_per_frame"]
 
 
 def test_shim_sources_cite_the_reference():

@@ -1,0 +1,5 @@
+M=integration/_build/models
+timeout 120 integration/_build/panda_cuda_check panda3d_b200 $M/panda-model.egg $M/panda-walk4.egg 0 7 10 20 33 45 60 2>&1 | tail -3
+timeout 120 integration/_build/panda_cuda_check panda3d_b200 $M/ripple.egg $M/ripple.egg 0 3 7 20 31 44 2>&1 | tail -3
+timeout 300 integration/_build/panda_cuda_check panda3d_b200 $M/panda-model.egg $M/panda-walk4.egg --crowd 1000 8 2>&1 | tail -3
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "per_instance" 2>&1 | tail -3
