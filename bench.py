@@ -120,6 +120,36 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+# ------------------------------------------------------------------------------------ host binding
+def bind_to_gpu_cpus(torch, local_rank: int):
+    """Binds this rank to the CPUs next to its GPU (sysfs local_cpulist) BEFORE any page-locked buffer is allocated, so
+    the buffers the PCIe copies target are first touched on the GPU's own NUMA node."""
+    info = {"bound": False}
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), getattr(props, "pci_bus_id", 0), getattr(props, "pci_device_id", 0))
+        base = f"/sys/bus/pci/devices/{bus}"
+        info["pci"] = bus
+        info["numa_node"] = open(base + "/numa_node").read().strip()
+        cpulist = open(base + "/local_cpulist").read().strip()
+        info["local_cpulist"] = cpulist
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus |= set(range(int(a), int(b) + 1))
+            elif part.strip():
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        if cpus & allowed and (cpus & allowed) != allowed:
+            os.sched_setaffinity(0, cpus & allowed)
+            info["bound"] = True
+        info["cpus"] = len(os.sched_getaffinity(0))
+    except Exception as exc:   # a box without that sysfs entry: run unbound, say so
+        info["error"] = repr(exc)
+    return info
+
+
 # ------------------------------------------------------------------------------------ CPU arms
 def cpu_reference_run(mesh_synth, steps: int, warmup: int, characters_per_worker: int, workers: int):
     """Times the reference's own animate_vertices (oracle/_ref/bin/ref_harness bench) with one worker
@@ -209,6 +239,7 @@ def run_gpu_arm(args):
         args.gpus = world
     dist = None
     torch.cuda.set_device(local_rank)
+    binding = bind_to_gpu_cpus(torch, local_rank)
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
@@ -297,6 +328,16 @@ def run_gpu_arm(args):
         e1.record(stream)
         barrier()
         e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / e2e_steps)
+        # the same bytes as bare copies (palettes up, arrays down, back to back on one stream), all ranks at once: what
+        # the PCIe links and the host memory of this box give a program that does nothing else
+        barrier()
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            pal_dev.copy_(pal_host, non_blocking=True)
+            out_host.copy_(out_dev[:, :rows * stride] if pitch != rows * stride else out_dev, non_blocking=True)
+        e1.record(stream)
+        barrier()
+        bare_ms = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
         sampler.stop_flag.set()
         sampler.join(timeout=2)
 
@@ -423,6 +464,85 @@ def run_gpu_arm(args):
             except Exception as exc:  # reported, never hidden
                 fused = {"error": repr(exc)}
 
+        # ---------------- skin + gather with a SINK-AWARE split: the rendering GPU keeps the share of the crowd that makes its
+        # compute time equal to the time the other ranks' rows need on its inbound NVLink (crowd.sink_aware_split)
+        gathered = None
+        if dist is not None and not args.no_fused and isinstance(fused, dict) and "ms_per_step" in fused:
+            try:
+                from panda3d_b200 import crowd
+                total_bytes = args.instances * pitch
+                remote_even = (args.instances - len(range(0, args.instances, world))) * pitch
+                ingress_gbs = remote_even / (fused["ms_per_step"] * 1e-3) / 1e9      # measured: the even deal is link-bound
+                compute_ms_all = ms * world                                              # one GPU, whole crowd
+                gather_ms_all = total_bytes / (ingress_gbs * 1e9) * 1e3
+                def run_split(counts, steps):
+                    n_w = counts[rank]
+                    target = crowd.RenderTarget(ctx, world, rank, 0, pitch, root=0, counts=counts)
+                    reps = -(-max(n_w, 1) // n_local)
+                    pal_w = pal_dev.repeat(reps, 1)[:max(n_w, 1)].contiguous()           # weighted instance j plays palette j % n_local
+                    grp3 = _capi.Group(dmesh, max(n_w, 1), palettes_dev=pal_w.data_ptr(), outputs_dev=[target.slab_ptr]) if n_w > 0 else None
+                    for _ in range(3):
+                        if grp3 is not None:
+                            grp3.animate()
+                    barrier()
+                    e0.record(stream)
+                    for _ in range(steps):
+                        if grp3 is not None:
+                            grp3.animate()
+                    e1.record(stream)
+                    barrier()
+                    own = e0.elapsed_time(e1) / steps
+                    return target, grp3, pal_w, max_over_ranks(own), own
+
+                # first pass with the model's rates, second pass with the rates the first pass measured (the per-rank time
+                # of the even deal carries its launch overhead, which overstates what the whole crowd costs one GPU)
+                counts = crowd.sink_aware_split(args.instances, world, compute_ms_all, gather_ms_all, root=0)
+                target, grp3, pal_w, g_ms, own_ms = run_split(counts, max(3, args.steps // 2))
+                root_ms = own_ms if rank == 0 else 0.0
+                remote_ms = own_ms if rank != 0 else 0.0
+                root_ms, remote_ms = sum_over_ranks(root_ms), max_over_ranks(remote_ms)
+                if counts[0] > 0 and counts[0] < args.instances and root_ms > 0 and remote_ms > 0:
+                    compute_ms_all = root_ms * args.instances / counts[0]
+                    gather_ms_all = remote_ms * args.instances / (args.instances - counts[0])
+                    refined = crowd.sink_aware_split(args.instances, world, compute_ms_all, gather_ms_all, root=0)
+                    if refined != counts:
+                        if grp3 is not None:
+                            grp3.close()
+                        barrier()
+                        target.close()
+                        counts = refined
+                        target, grp3, pal_w, g_ms, own_ms = run_split(counts, args.steps)
+                ok = None
+                if rank == 0 and not args.no_check:
+                    from oracle import oracle
+                    om = oracle.OracleMesh(flat)
+                    ok = {}
+                    for r_chk, j in ((0, counts[0] - 1), (1, counts[1] // 2), (world - 1, counts[world - 1] - 1)):
+                        if counts[r_chk] == 0:
+                            continue
+                        n_r = len(range(r_chk, args.instances, world))
+                        pal_r = synth.make_palettes(T, n_r, 1000 + r_chk)[j % n_r]
+                        got = target.read_row(r_chk, j, rows * stride).reshape(rows, stride)
+                        explained, unexplained, _ = oracle.unexplained_differences(flat, [got], pal_r, None, om)
+                        ok[f"rank{r_chk}_instance{j}"] = {"differing_bytes": explained + unexplained, "outside_libm_normals": unexplained}
+                        assert unexplained == 0, f"gathered check failed: {ok}"
+                gathered = {"value": args.instances * flat.skinned_rows() / (g_ms * 1e-3), "unit": UNIT, "ms_per_step": g_ms,
+                            "instances_per_rank": counts, "share_rank0": counts[0] / args.instances,
+                            "nvlink_ingress_gbs_measured_even_deal": ingress_gbs,
+                            "nvlink_ingress_frac_of_770": ingress_gbs / 770.0,
+                            "model": {"compute_ms_all_on_one_gpu": compute_ms_all, "gather_ms_all_over_the_root_link": gather_ms_all},
+                            "even_deal_ms_per_step": fused["ms_per_step"], "this_rank_ms": own_ms, "check": ok,
+                            "note": "every rank's kernel stores its rows into the rendering GPU's buffer (peer-mapped, TMA bulk stores "
+                                    "over NVLink); rank 0 keeps the share that balances its compute against its inbound link"}
+                if grp3 is not None:
+                    grp3.close()
+                barrier()
+                target.close()
+            except AssertionError:
+                raise
+            except Exception as exc:  # reported, never hidden
+                gathered = {"error": repr(exc)}
+
         # ---------------- the other BASELINE.json configurations, device time per animate call (rank 0, N=1):
         # parity-test cases, not bench lines -- reported so the single-mesh latencies sit next to the crowd number
         others = None
@@ -452,7 +572,7 @@ def run_gpu_arm(args):
             if pj.get("instances") == n_local:
                 traffic = pj.get("dram_bytes_per_launch")
                 pj_limiter = pj.get("limiter")
-        roofline = {"bound": "hbm", "kernel": "p3cs::strip_kernel<kRow24>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": "p3cs::run_kernel<kRow24>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic, "peak_source": peak_src,
                     "launches_per_step": skin_launches, "avg_launch_ms": 1e3 * skin_s / max(1, skin_launches),
                     "algorithmic_bytes_per_launch": alg_bytes_per_step,
@@ -473,9 +593,13 @@ def run_gpu_arm(args):
             "data": "synthetic", "config": config_dict(args, world),
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
-                    "ms_per_step": e2e_ms, "steps": e2e_steps},
+                    "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "pcie_roofline": {"bare_copies_ms_per_step": bare_ms, "bare_gbs_whole_job": (h2d_total + d2h_total) / bare_ms / 1e6,
+                                      "e2e_over_bare": e2e_ms / bare_ms,
+                                      "note": "the same H2D + D2H bytes as plain copies on every rank at once, no kernel: the box's PCIe / host-memory ceiling"},
+                    "host_binding": binding},
             "gpu_launches": launches_per_step * args.steps, "clocks": sampler.summary(), "check": check,
-            "gather": gather, "fused_gather": fused, "joints_on_gpu": joints, "tight_bounds": bounds, "other_configs": others,
+            "gather": gather, "fused_gather": fused, "gathered": gathered, "gathered_value": (gathered or {}).get("value"), "joints_on_gpu": joints, "tight_bounds": bounds, "other_configs": others,
         }
         emit(line)
     grp.close()

@@ -30,6 +30,29 @@ def test_mixed_crowd_is_balanced_by_vertices():
     assert max(loads) - min(loads) <= 125_000 and max(loads) <= 1.3 * (sum(verts) / 8)
 
 
+def test_sink_aware_split_balances_compute_against_the_root_link():
+    """All rows end on the rendering GPU: it keeps the share that makes its compute time equal to the time the others'
+    rows need on its inbound NVLink (an even deal was 4x slower than one GPU)."""
+    n = 10_000
+    # one GPU: 1.25 ms for the crowd; 4.8 GB over ~720 GB/s of inbound NVLink: 6.7 ms
+    counts = crowd.sink_aware_split(n, 8, 1.25, 6.7)
+    assert sum(counts) == n and len(counts) == 8
+    f = counts[0] / n
+    assert abs(f - 6.7 / (1.25 + 6.7)) < 1e-3
+    assert max(counts[1:]) - min(counts[1:]) <= 1
+    t_root, t_remote = f * 1.25, (1 - f) * 6.7
+    assert abs(t_root - t_remote) < 0.01 and t_root < 1.25          # faster than not sharding
+    assert crowd.split_firsts(counts)[0] == 0 and crowd.split_firsts(counts)[-1] == n - counts[-1]
+    # a free link degenerates into the even deal, a dead link keeps everything at home
+    even = crowd.sink_aware_split(n, 4, 4.0, 0.0)
+    assert max(even) - min(even) <= 1
+    assert crowd.sink_aware_split(n, 4, 1.0, 1e9)[0] == n
+    assert crowd.sink_aware_split(7, 1, 1.0, 1.0) == [7]
+    # any root
+    c2 = crowd.sink_aware_split(1000, 4, 1.0, 3.0, root=2)
+    assert c2[2] == max(c2) and sum(c2) == 1000
+
+
 def test_global_order_inverts_the_deal():
     n, w = 11, 4
     per = -(-n // w)
