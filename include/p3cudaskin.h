@@ -468,6 +468,43 @@ P3CS_EXPORT int p3cs_blends_from_hardware(int32_t num_rows, const float *weights
  * must stay valid until the animate call that uses them has been synchronised. */
 P3CS_EXPORT int p3cs_group_set_output_pointers(p3cs_group grp, int output, void *const *ptrs);
 
+/* ---- crowds over several GPUs of one process ----------------------------
+ * `cuda-skinning-devices 0 1 2 ...`.  A crowd is num_instances instances of one mesh
+ * dealt to the listed devices in consecutive ranges; devices[0] is the rendering GPU and owns the crowd's output
+ * buffers ([num_instances][pitch] per output array), which the other devices map over NVLink: their kernels store
+ * their finished rows straight into it (no collective, no staging copy).  The deal is sink-aware: devices[0] keeps
+ * the share that balances its compute against its inbound link (root_share <= 0: planned from link_gbs, then
+ * p3cs_crowd_tune re-splits from measured times).  One context (one stream) per device; animate returns as soon as
+ * every device's launch is queued. */
+typedef struct p3cs_crowd_s *p3cs_crowd;
+typedef struct p3cs_crowd_desc {
+  uint32_t struct_size;      /* sizeof(p3cs_crowd_desc) */
+  int32_t num_devices;
+  const int32_t *devices;    /* CUDA device ordinals; devices[0] = the rendering GPU */
+  int32_t num_instances;
+  float root_share;          /* share of the instances devices[0] keeps; <= 0: automatic */
+  float link_gbs;            /* inbound NVLink rate of devices[0] to plan with; <= 0: 720 */
+} p3cs_crowd_desc;
+
+P3CS_EXPORT int p3cs_crowd_create(const p3cs_crowd_desc *desc, const p3cs_mesh_desc *mesh, p3cs_crowd *out);
+P3CS_EXPORT int p3cs_crowd_destroy(p3cs_crowd crowd);
+P3CS_EXPORT int p3cs_crowd_num_devices(p3cs_crowd crowd);
+/* the consecutive range of instances devices[device_index] animates */
+P3CS_EXPORT int p3cs_crowd_range(p3cs_crowd crowd, int device_index, int32_t *first, int32_t *count);
+/* joint matrices / slider values of instances [first, first + count) (crowd numbering), routed to their devices */
+P3CS_EXPORT int p3cs_crowd_set_palettes(p3cs_crowd crowd, int first, int count, const float *host);
+P3CS_EXPORT int p3cs_crowd_set_sliders(p3cs_crowd crowd, int first, int count, const float *host);
+P3CS_EXPORT int p3cs_crowd_animate(p3cs_crowd crowd);
+P3CS_EXPORT int p3cs_crowd_sync(p3cs_crowd crowd);
+/* CUDA-event time of the last animate on every device (num_devices floats) */
+P3CS_EXPORT int p3cs_crowd_last_ms(p3cs_crowd crowd, float *per_device_ms);
+/* measures `steps` passes and re-splits the crowd from the times seen; set palettes / sliders again afterwards */
+P3CS_EXPORT int p3cs_crowd_tune(p3cs_crowd crowd, int steps);
+/* the gathered buffer of output array `output` on devices[0], and its pitch per instance */
+P3CS_EXPORT void *p3cs_crowd_output_device(p3cs_crowd crowd, int output);
+P3CS_EXPORT size_t p3cs_crowd_output_pitch(p3cs_crowd crowd, int output);
+P3CS_EXPORT int p3cs_crowd_read_output(p3cs_crowd crowd, int output, int first, int count, void *host_dst);
+
 /* ---- plugin table (load_dso + dlsym("p3cs_get_api")) -------------------- */
 
 typedef struct p3cs_api {

@@ -38,6 +38,9 @@ EXPORTED_SYMBOLS = [
     "p3cs_group_pose_blend", "p3cs_skeleton_add_animation", "p3cs_group_pose_controls",
     "p3cs_group_set_forced_joints", "p3cs_group_set_forced_values", "p3cs_group_set_bounds_rows",
     "p3cs_group_set_output_pointers",
+    "p3cs_crowd_create", "p3cs_crowd_destroy", "p3cs_crowd_num_devices", "p3cs_crowd_range", "p3cs_crowd_set_palettes",
+    "p3cs_crowd_set_sliders", "p3cs_crowd_animate", "p3cs_crowd_sync", "p3cs_crowd_last_ms", "p3cs_crowd_tune",
+    "p3cs_crowd_output_device", "p3cs_crowd_output_pitch", "p3cs_crowd_read_output",
 ]
 
 
@@ -600,6 +603,73 @@ class Group:
     def close(self) -> None:
         if self.handle:
             lib().p3cs_group_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+class _CrowdDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("num_devices", C.c_int32), ("devices", C.POINTER(C.c_int32)),
+                ("num_instances", C.c_int32), ("root_share", C.c_float), ("link_gbs", C.c_float)]
+
+
+class Crowd:
+    """p3cs_crowd: instances of one mesh over several GPUs of THIS process; devices[0] is the rendering GPU, whose
+    buffer every device's kernel stores its rows into (sink-aware split, see include/p3cudaskin.h)."""
+
+    def __init__(self, devices: Sequence[int], mesh: FlatMesh, num_instances: int, root_share: float = 0.0, link_gbs: float = 0.0):
+        self.flat, self.n = mesh, num_instances
+        self.handle = C.c_void_p()
+        keep: list = []
+        desc = mesh_desc(mesh, keep)
+        devs = (C.c_int32 * len(devices))(*devices)
+        cd = _CrowdDesc(C.sizeof(_CrowdDesc), len(devices), devs, num_instances, root_share, link_gbs)
+        L = lib()
+        L.p3cs_crowd_output_pitch.restype = C.c_size_t
+        L.p3cs_crowd_output_device.restype = C.c_void_p
+        _check(L.p3cs_crowd_create(C.byref(cd), C.byref(desc), C.byref(self.handle)))
+        self.num_devices = int(L.p3cs_crowd_num_devices(self.handle))
+
+    def ranges(self) -> List[Tuple[int, int]]:
+        out = []
+        for d in range(self.num_devices):
+            first, count = C.c_int32(), C.c_int32()
+            _check(lib().p3cs_crowd_range(self.handle, d, C.byref(first), C.byref(count)))
+            out.append((first.value, count.value))
+        return out
+
+    def set_palettes(self, matrices: np.ndarray, first: int = 0) -> None:
+        m = np.ascontiguousarray(matrices, np.float32)
+        count = m.size // (self.flat.num_transforms * 16)
+        _check(lib().p3cs_crowd_set_palettes(self.handle, first, count, m.ctypes.data_as(C.c_void_p)))
+
+    def set_sliders(self, values: np.ndarray, first: int = 0) -> None:
+        v = np.ascontiguousarray(values, np.float32)
+        count = v.size // max(1, self.flat.num_sliders)
+        _check(lib().p3cs_crowd_set_sliders(self.handle, first, count, v.ctypes.data_as(C.c_void_p)))
+
+    def animate(self) -> None:
+        _check(lib().p3cs_crowd_animate(self.handle))
+
+    def sync(self) -> None:
+        _check(lib().p3cs_crowd_sync(self.handle))
+
+    def tune(self, steps: int = 3) -> None:
+        _check(lib().p3cs_crowd_tune(self.handle, steps))
+
+    def last_ms(self) -> List[float]:
+        ms = (C.c_float * self.num_devices)()
+        _check(lib().p3cs_crowd_last_ms(self.handle, ms))
+        return list(ms)
+
+    def read_output(self, o: int = 0, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        count = self.n - first if count is None else count
+        stride = self.flat.strides[self.flat.output_arrays[o]]
+        out = np.empty((count, self.flat.num_rows, stride), np.uint8)
+        _check(lib().p3cs_crowd_read_output(self.handle, o, first, count, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def close(self) -> None:
+        if self.handle:
+            lib().p3cs_crowd_destroy(self.handle)
             self.handle = C.c_void_p()
 
 

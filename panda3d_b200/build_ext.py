@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libp3cudaskin.so")
-SOURCES = ["p3cs_api.cu", "p3cs_mesh.cu", "p3cs_interop.cu", "p3cs_kernels.cu", "p3cs_pose.cu", "p3cs_format.cu", "p3cs_strip.cu",
+SOURCES = ["p3cs_api.cu", "p3cs_mesh.cu", "p3cs_interop.cu", "p3cs_kernels.cu", "p3cs_pose.cu", "p3cs_format.cu", "p3cs_crowd.cu", "p3cs_strip.cu",
            "p3cs_run_inst_a.cu", "p3cs_run_inst_b.cu",
            "p3cs_strip_inst_a.cu", "p3cs_strip_inst_b.cu", "p3cs_strip_inst_c.cu", "p3cs_strip_inst_d.cu", "p3cs_strip_inst_e.cu"]
 HEADERS = ["p3cs_internal.h", "p3cs_kernels.cuh", "p3cs_math.cuh", "p3cs_device.cuh", "p3cs_strip.cuh", "p3cs_run.cuh", "p3cs_runplan.h",
