@@ -293,6 +293,61 @@ inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max
       }
       ++half;
     }
+    // Palette-gather conflicts, second pass.  Lanes l and l + 16 of a slot serve the same row residue, so their items may
+    // trade places at no cost to the row walk; that changes which quarter-warp (eight lanes = one 128-bit load wavefront)
+    // an item gathers with.  Hill-climb per slot on the number of gather wavefronts.
+    {
+      auto quarter_cost = [&](const Slot &sl, int quarter) {  // wavefronts of the quarter-warp's 4 x 3 gather loads, in units of 3
+        int total = 0;
+        for (int k = 0; k < 4; ++k) {
+          int seen[8][8], nseen[8] = {0, 0, 0, 0, 0, 0, 0, 0}, worst = 0;
+          for (int l = quarter * 8; l < quarter * 8 + 8; ++l) {
+            if (sl.lane_item[l] < 0) continue;
+            const int j = items[sl.lane_item[l]].joint[k];
+            if (j < 0) continue;
+            const int res = j & 7;
+            bool known = false;
+            for (int q = 0; q < nseen[res]; ++q) known = known || seen[res][q] == j;
+            if (!known) seen[res][nseen[res]++] = j;
+            worst = std::max(worst, nseen[res]);
+          }
+          total += worst;
+        }
+        return total;
+      };
+      for (Slot &sl : slots) {
+        for (int pass = 0; pass < 4; ++pass) {
+          bool improved = false;
+          for (int l = 0; l < 16; ++l) {
+            if (sl.lane_item[l] < 0 && sl.lane_item[l + 16] < 0) continue;
+            const int qa = l >> 3, qb = (l + 16) >> 3;
+            const int before = quarter_cost(sl, qa) + quarter_cost(sl, qb);
+            std::swap(sl.lane_item[l], sl.lane_item[l + 16]);
+            std::swap(sl.lane_delay[l], sl.lane_delay[l + 16]);
+            if (quarter_cost(sl, qa) + quarter_cost(sl, qb) < before) {
+              improved = true;
+            } else {
+              std::swap(sl.lane_item[l], sl.lane_item[l + 16]);
+              std::swap(sl.lane_delay[l], sl.lane_delay[l + 16]);
+            }
+          }
+          if (!improved) break;
+        }
+        // the statistics below read the slot's `nseen` tables: rebuild them for the final arrangement
+        for (auto &a : sl.nseen) for (auto &b : a) for (int &c : b) c = 0;
+        for (int l = 0; l < 32; ++l) {
+          if (sl.lane_item[l] < 0) continue;
+          const Item &it = items[sl.lane_item[l]];
+          const int quarter = l >> 3;
+          for (int k = 0; k < 4 && it.joint[k] >= 0; ++k) {
+            const int j = it.joint[k], res = j & 7;
+            bool known = false;
+            for (int q = 0; q < sl.nseen[quarter][k][res]; ++q) known = known || sl.seen[quarter][k][res][q] == j;
+            if (!known && sl.nseen[quarter][k][res] < 8) sl.seen[quarter][k][res][sl.nseen[quarter][k][res]++] = j;
+          }
+        }
+      }
+    }
     // longest slot first (the kernel deals a tile's slots to its warps in order)
     std::stable_sort(slots.begin(), slots.end(), [](const Slot &x, const Slot &y) { return x.steps > y.steps; });
     const size_t base = p.items.size();
