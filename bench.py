@@ -566,7 +566,7 @@ def run_gpu_arm(args):
         achieved = alg_bytes_per_step / skin_s / 1e9
         traffic = None
         pj_limiter = None   # what actually binds the kernel, from the committed ncu capture (not measured live)
-        prof = os.path.join(ROOT, "profiles", "r01_strip_kernel_c3.json")
+        prof = os.path.join(ROOT, "profiles", "r02_run_kernel_c3.json")
         if os.path.exists(prof):
             pj = json.load(open(prof))
             if pj.get("instances") == n_local:
@@ -579,7 +579,7 @@ def run_gpu_arm(args):
                     "algorithmic_bytes_per_vertex": alg_bytes_per_step / (n_local * rows),
                     "logical_gbs": logical_bytes_per_step / skin_s / 1e9,
                     "limiter": pj_limiter,
-                    "note": "bound by the SM's L1TEX/LSU data pipe (shared-memory wavefronts), not by HBM, on this 24 B/vertex crowd: see DESIGN.md"}
+                    "note": "run kernel (one thread per run of rows, blend in registers); the SM's L1TEX/LSU data pipe is the binding unit on this 24 B/vertex crowd (83 % of its peak), DRAM traffic equals the algorithmic bytes: see DESIGN.md"}
         cpu = None
         if world == 1 and not args.no_cpu:
             workers = os.cpu_count() or 1
