@@ -704,40 +704,67 @@ extern "C" int p3cs_group_read_blends(p3cs_group grp, int instance, float *host_
   return P3CS_OK;
 }
 
+// Waits for the context's stream the way a latency-bound caller wants it: polling (a blocking
+// cudaStreamSynchronize costs several microseconds of wake-up), falling back to the blocking wait for long work.
+static int sync_polling(p3cs_context ctx) {
+  for (int spin = 0; spin < 4000; ++spin) {
+    const cudaError_t q = cudaStreamQuery(ctx->stream);
+    if (q == cudaSuccess) return P3CS_OK;
+    if (q != cudaErrorNotReady) return p3cs_fail(P3CS_ERR_CUDA, "stream failed: %s", cudaGetErrorString(q));
+  }
+  return p3cs_context_sync(ctx);
+}
+
 extern "C" int p3cs_animate_vertices(p3cs_group grp, int instance, const float *host_palette, const float *host_sliders,
                                      void *const *host_outputs) {
   int rc = check_span(grp, instance, 1, "p3cs_animate_vertices");
   if (rc != P3CS_OK) return rc;
   const MeshDev &m = grp->mesh->dev;
+  p3cs_context ctx = grp->mesh->ctx;
+  if (m.num_transforms > 0 && host_palette == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_animate_vertices: palette is NULL");
+  DeviceGuard g(ctx->device);
+  GroupDev direct = grp->dev;
   if (m.num_transforms > 0 && (rc = p3cs_group_set_palettes(grp, instance, 1, host_palette)) != P3CS_OK) return rc;
   if (m.num_sliders > 0 && (rc = p3cs_group_set_sliders(grp, instance, 1, host_sliders)) != P3CS_OK) return rc;
-  DeviceGuard g(grp->mesh->ctx->device);
-  // Page-locked, device-mapped destinations (p3cs_host_register / cudaHostRegister): the kernel's row stores go
-  // straight to host memory, no device->host copy afterwards.  The bulk stores move 16-byte units, hence the
-  // alignment and size conditions; anything else takes the copy below.
+  // ---- outputs: page-locked, device-mapped destinations (p3cs_host_register / cudaHostRegister): the kernel's row stores
+  // go straight to host memory, no device->host copy afterwards.  The bulk stores move 16-byte units, hence the alignment
+  // and size conditions; anything else takes the copy below.  The destinations of the previous call are remembered.
   if (host_outputs != nullptr && m.num_outputs > 0) {
-    GroupDev direct = grp->dev;
     bool ok = true;
     for (int o = 0; o < m.num_outputs && ok; ++o) {
-      cudaPointerAttributes attr{};
       const size_t bytes = (size_t)m.num_rows * m.stride[o];
-      ok = host_outputs[o] != nullptr && bytes % 16 == 0 && reinterpret_cast<uintptr_t>(host_outputs[o]) % 16 == 0 &&
-           cudaPointerGetAttributes(&attr, host_outputs[o]) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
-           attr.devicePointer != nullptr;
-      if (ok) direct.out[o] = reinterpret_cast<uint8_t *>(reinterpret_cast<uintptr_t>(attr.devicePointer) - (uintptr_t)instance * grp->dev.pitch[o]);
+      ok = host_outputs[o] != nullptr && bytes % 16 == 0 && reinterpret_cast<uintptr_t>(host_outputs[o]) % 16 == 0;
+      if (!ok) break;
+      void *dev = nullptr;
+      if (ctx->seen_host[o] == host_outputs[o]) {
+        dev = ctx->seen_dev[o];
+      } else {
+        cudaPointerAttributes attr{};
+        ok = cudaPointerGetAttributes(&attr, host_outputs[o]) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr;
+        cudaGetLastError();  // cudaPointerGetAttributes on plain malloc memory may leave a sticky-free error behind
+        if (ok) {
+          dev = attr.devicePointer;
+          ctx->seen_host[o] = host_outputs[o];
+          ctx->seen_dev[o] = dev;
+        }
+      }
+      if (ok) direct.out[o] = reinterpret_cast<uint8_t *>(reinterpret_cast<uintptr_t>(dev) - (uintptr_t)instance * grp->dev.pitch[o]);
       direct.out_ptrs[o] = nullptr;
     }
-    cudaGetLastError();  // cudaPointerGetAttributes on plain malloc memory may leave a sticky-free error behind
     if (ok) {
       if ((rc = animate_range(grp, instance, 1, false, nullptr, &direct)) != P3CS_OK) return rc;
-      return p3cs_context_sync(grp->mesh->ctx);
+      return sync_polling(ctx);
+    }
+    for (int o = 0; o < m.num_outputs; ++o) {
+      direct.out[o] = grp->dev.out[o];
+      direct.out_ptrs[o] = grp->dev.out_ptrs[o];
     }
   }
-  if ((rc = animate_range(grp, instance, 1, false)) != P3CS_OK) return rc;
+  if ((rc = animate_range(grp, instance, 1, false, nullptr, &direct)) != P3CS_OK) return rc;
   if (host_outputs != nullptr)
     for (int o = 0; o < m.num_outputs; ++o)
       if (host_outputs[o] != nullptr && (rc = p3cs_group_read_output(grp, o, instance, 1, host_outputs[o])) != P3CS_OK) return rc;
-  return p3cs_context_sync(grp->mesh->ctx);
+  return sync_polling(ctx);
 }
 
 // ------------------------------------------------------------------ joint hierarchy (f1)

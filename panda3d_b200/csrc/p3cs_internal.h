@@ -33,6 +33,10 @@ struct p3cs_context_s {
   bool side_ready = false;  // every side stream / event above exists (ensure_side_streams)
   cudaEvent_t join_ev[kSideStreams] = {nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> pipe_ev;  // chunk hand-off events of p3cs_group_animate_host
+  // p3cs_animate_vertices: the destinations last seen are remembered with their device address (cudaPointerGetAttributes
+  // costs a microsecond per array and call)
+  const void *seen_host[4] = {nullptr, nullptr, nullptr, nullptr};
+  void *seen_dev[4] = {nullptr, nullptr, nullptr, nullptr};
   // p3cs_animate_groups: the fork / join of a set of groups captured once as a CUDA graph and replayed
   struct GroupsGraph {
     std::vector<p3cs_group> groups;

@@ -249,6 +249,8 @@ extern "C" int p3cs_host_unregister(p3cs_context ctx, void *host_ptr) {
   if (ctx == nullptr || host_ptr == nullptr) return p3cs_fail(P3CS_ERR_INVALID, "p3cs_host_unregister: bad arguments");
   DeviceGuard g(ctx->device);
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  for (int o = 0; o < 4; ++o)  // p3cs_animate_vertices remembers the destinations it has resolved
+    if (ctx->seen_host[o] == host_ptr) ctx->seen_host[o] = nullptr;
   CUDA_TRY(cudaHostUnregister(host_ptr));
   return P3CS_OK;
 }

@@ -124,9 +124,18 @@ static RunLaunch run_partition(const MeshDev &mesh, int count, int sm_count) {
   const RunPlanDev &big = mesh.run_plan[0];
   if (mesh.run_plan[1].tile_rows != 0 && (long long)big.num_tiles * count < 4LL * sm_count) r.plan = 1;
   const RunPlanDev &p = mesh.run_plan[r.plan];
-  const long long target = 24LL * sm_count;  // CTAs in the launch (as strip_partition)
+  // One CTA per instance as soon as the instances alone fill the machine about twice over (a CTA stages the instance's
+  // palette and sits out its fetch: 10 000 x C3 1.235 ms with one CTA per instance, 1.276 with two; 1250 x C3 0.179 / 0.181
+  // / 0.183 ms with 1 / 2 / 3); below that the tiles are spread over more CTAs.
+  int threads = 256, ctas = 3;
+  run_shape(mesh.run_mode, &threads, &ctas);
+  const long long target = 2LL * ctas * sm_count;
   long long cpi = (target + count - 1) / count;
   if (cpi < 1) cpi = 1;
+  if (const char *e = getenv("P3CS_RUN_CPI")) {  // tuning aid: CTAs per instance
+    const int v = atoi(e);
+    if (v > 0) cpi = v;
+  }
   if (cpi > p.num_tiles) cpi = p.num_tiles;
   r.tiles_per_cta = (p.num_tiles + (int)cpi - 1) / (int)cpi;
   r.ctas_per_instance = (p.num_tiles + r.tiles_per_cta - 1) / r.tiles_per_cta;

@@ -27,7 +27,7 @@ def test_real_panda_actor_through_the_shim():
     out = json.loads(line[-1])
     print(out)
     assert out["ok"], out
-    assert out["frames"] == len(frames) and out["rows"] == 1338
+    assert out["frames"] == len(frames) + 1 and out["rows"] == 1338   # + the frame AnimateVerticesRequest animated
     assert out["same_result_object"]            # same output object reused / cached (geomVertexData.cxx:895-960)
     assert out["stock_callers_agree"]           # Geom::get_animated_vertex_data lands on the same object (gobj/geom.cxx:287-288)
     assert out["animate_vertices_request"]      # ... and so does AnimateVerticesRequest (gobj/animateVerticesRequest.cxx:28)
@@ -52,7 +52,7 @@ def test_real_morph_character_through_the_shim():
     out = json.loads(line[-1])
     print(out)
     assert out["ok"], out
-    assert out["frames"] == len(frames) and out["rows"] == 641
+    assert out["frames"] == len(frames) + 1 and out["rows"] == 641
     assert out["same_result_object"]
     assert out["differing_bytes"] == 0          # morphs + one rigid joint: no libm on this path
 
