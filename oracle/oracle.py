@@ -153,7 +153,7 @@ def unexplained_differences(mesh, got, palette, sliders=None, om: Optional["Orac
         normal_bytes = np.zeros(g.shape[1], bool)
         for c in mesh.skin_columns:
             if c.array == mesh.output_arrays[o] and c.contents == C_normal:
-                normal_bytes[c.start:c.start + NUMERIC_BYTES[c.numeric_type] * c.num_values] = True
+                normal_bytes[c.start:c.start + c.num_bytes] = True
         unexplained += int(diff[:, ~normal_bytes].sum())
         nd = diff[:, normal_bytes]
         rows = np.nonzero(nd.any(axis=1))[0]

@@ -330,7 +330,10 @@ static bool build_from_recipe(const Case &c, Built &out) {
     for (size_t k = 0; k < cols.shape[0]; ++k) {
       const int32_t *cc = cols.i32() + k * 5;
       if (cc[0] != a) continue;
-      af->add_column(InternalName::make(names[k]), cc[2], (GeomEnums::NumericType)cc[3], (GeomEnums::Contents)cc[4], cc[1], 1);
+      // the recipe lists get_num_values(); the packed types hold 4 (3: packed_ufloat) values per component
+      const int per_component = (cc[3] == GeomEnums::NT_packed_dcba || cc[3] == GeomEnums::NT_packed_dabc) ? 4
+                                : cc[3] == GeomEnums::NT_packed_ufloat ? 3 : 1;
+      af->add_column(InternalName::make(names[k]), cc[2] / per_component, (GeomEnums::NumericType)cc[3], (GeomEnums::Contents)cc[4], cc[1], 1);
     }
     if (af->get_stride() < strides[a]) af->set_stride(strides[a]);
     if (af->get_stride() != strides[a]) { fprintf(stderr, "array %d: stride %d != recipe %d\n", a, af->get_stride(), strides[a]); return false; }

@@ -549,15 +549,221 @@ static int read_index(const uint8_t *p, int numeric_type) {
   }
 }
 
-/* GeomVertexReader::get_data3/4 and GeomVertexWriter::set_data3/4 on a float64 column with
- * PN_stdfloat = float: components pass through float (geomVertexColumn.cxx:668-673, 1805-1811). */
-static void get_f64(const uint8_t *p, int n, float *v) {
-  int k;
-  for (k = 0; k < n; ++k) { double d; memcpy(&d, p + 8 * k, 8); v[k] = (float)d; }
+/* ------------------------------------------------------------------------------------------------
+ * GeomVertexReader::get_data3/4 and GeomVertexWriter::set_data3/4 (PN_stdfloat = float) on a column of
+ * any numeric type: the GeomVertexColumn::Packer family, panda/src/gobj/geomVertexColumn.cxx.
+ *
+ * make_packer (:240-372) picks Packer_point for C_point / C_clip_point / C_texcoord, a colour packer for
+ * C_color and the plain Packer otherwise.  Packer_point differs from Packer in get_data4f on fewer than
+ * four values (w = 1, :2814-2828), in get_data3f on four values (divide by w, :2800-2808) and in the
+ * mirrored setters (:3109-3140) -- calls this path never makes: columns of four values are read and
+ * written with get_data4 / set_data4 and narrower ones with get_data3 / set_data3
+ * (geomVertexData.cxx:1489-1537, 1782-1799), so both reduce to the plain Packer here.
+ * ------------------------------------------------------------------------------------------------ */
+enum { PK_PLAIN, PK_COLOR, PK_COLOR_CLAMPED };
+
+static int packer_kind(const p3o_column *c) {
+  if (c->contents != P3O_C_COLOR) return PK_PLAIN;
+  if (c->num_values == 4 && (c->numeric_type == P3O_NT_UINT8 || c->numeric_type == P3O_NT_PACKED_DABC))
+    return PK_COLOR_CLAMPED;  /* Packer_rgba_uint8_4 / Packer_argb_packed, :304-309 */
+  return PK_COLOR;            /* Packer_color (and its float32 variants, which store the values as they are) */
 }
-static void set_f64(uint8_t *p, int n, const float *v) {
+
+/* Bytes a column occupies in its row (GeomVertexColumn::setup, :154-234: the packed types hold all
+ * their values in one 32-bit component). */
+static int column_bytes(const p3o_column *c) {
+  switch (c->numeric_type) {
+  case P3O_NT_UINT8: case P3O_NT_INT8: return c->num_values;
+  case P3O_NT_UINT16: case P3O_NT_INT16: return 2 * c->num_values;
+  case P3O_NT_FLOAT64: return 8 * c->num_values;
+  case P3O_NT_PACKED_DCBA: case P3O_NT_PACKED_DABC: case P3O_NT_PACKED_UFLOAT: return 4;
+  default: return 4 * c->num_values;
+  }
+}
+
+/* Can the reference read and write this column at all?  (The combinations its packers answer with
+ * nassert(false) are refused.) */
+static int column_supported(const p3o_column *c) {
+  int nt = c->numeric_type, nv = c->num_values;
+  if (nv < 1 || nv > 4 || nt < 0 || nt > P3O_NT_PACKED_UFLOAT || nt == P3O_NT_STDFLOAT) return 0;
+  if ((nt == P3O_NT_PACKED_DCBA || nt == P3O_NT_PACKED_DABC) && nv != 4) return 0;
+  if (nt == P3O_NT_PACKED_UFLOAT && nv != 3) return 0;
+  if (packer_kind(c) != PK_PLAIN) {
+    if (nv < 3) return 0;                                                                  /* :325-328 */
+    if (nt == P3O_NT_INT8 || nt == P3O_NT_INT16 || nt == P3O_NT_INT32) return 0;           /* :3500-3505 */
+  }
+  return 1;
+}
+
+/* `(unsigned int)x` and `(int)x` of a float as the reference's x86-64 build executes them: cvttss2si
+ * into a 64-bit register of which the low half is kept, and cvttss2si into a 32-bit register
+ * ("integer indefinite" 0x80..0 when the truncated value does not fit).  Spelled out because the plain
+ * C casts are undefined outside the target type's range. */
+static uint32_t cast_uint(float x) {
+  if (!(fabsf(x) < 9223372036854775808.0f)) return 0u;
+  return (uint32_t)(uint64_t)(int64_t)x;
+}
+static int32_t cast_int(float x) {
+  if (!(x >= -2147483648.0f && x < 2147483648.0f)) return INT32_MIN;
+  return (int32_t)x;
+}
+
+/* GeomVertexData::unpack_ufloat_a/b/c (geomVertexData.I:431-505): an unsigned float of `mbits`
+ * mantissa bits and 5 exponent bits (bias 15), given right-aligned in `field`. */
+static float ufloat_field_to_float(uint32_t field, int mbits) {
+  uint32_t exponent = field >> mbits, mantissa = field & ((1u << mbits) - 1u), bits;
+  float f;
+  if (exponent == 0) return ldexpf((float)mantissa / (float)(1u << mbits), -14);  /* denormal, zero */
+  bits = field << (23 - mbits);
+  if (exponent == 31) bits |= 0x7f800000u; else bits += 0x38000000u;             /* inf / nan; rebias 15 -> 127 */
+  memcpy(&f, &bits, 4);
+  return f;
+}
+
+/* GeomVertexData::pack_ufloat (geomVertexData.I:375-426): r11 g11 b10, per component: nan / +inf keep
+ * their top mantissa bits, values from 65536 up clamp to the largest finite one, normals are re-biased
+ * and truncated, 2^-21 .. 2^-14 become denormals, everything smaller or negative becomes 0.  The
+ * constants are the reference's; note the denormal branch keeps one mantissa bit fewer than the field
+ * holds, and a nan in the third component spills one bit into the second field. */
+static uint32_t pack_ufloat(float a, float b, float c) {
+  int32_t ia, ib, ic;
+  uint32_t word = 0;
+  memcpy(&ia, &a, 4); memcpy(&ib, &b, 4); memcpy(&ic, &c, 4);
+#define P3O_NAN_OR_INF(i) ((((i) & 0x7f800000) == 0x7f800000) && (uint32_t)(i) != 0xff800000u)
+  if (P3O_NAN_OR_INF(ia)) word |= (uint32_t)(ia >> 17) & 0x7ffu;
+  else if (ia >= 0x47800000) word |= 0x7bfu;
+  else if (ia >= 0x38800000) word |= (uint32_t)((ia >> 17) - 0x1c00);
+  else if (ia >= 0x35000000) word |= (((uint32_t)ia & 0x7c0000u) | 0x800000u) >> (130 - (ia >> 23));
+
+  if (P3O_NAN_OR_INF(ib)) word |= (uint32_t)(ib >> 6) & 0x3ff800u;
+  else if (ib >= 0x47800000) word |= 0x3df800u;
+  else if (ib >= 0x38800000) word |= (uint32_t)((ib >> 6) - 0xe00000) & 0x3ff800u;
+  else if (ib >= 0x35000000) word |= ((((uint32_t)ib & 0x7c0000u) | 0x800000u) >> (119 - (ib >> 23))) & 0x1f800u;
+
+  if (P3O_NAN_OR_INF(ic)) word |= ((uint32_t)ic & 0x0ffe0000u) << 4;
+  else if (ic >= 0x47800000) word |= 0xf7c00000u;
+  else if (ic >= 0x38800000) word |= ((uint32_t)(ic - 0x38000000) << 4) & 0xffc00000u;
+  else if (ic >= 0x35000000) word |= (((((uint32_t)ic << 3) & 0x03c00000u) | 0x04000000u) >> (112 - (ic >> 23))) & 0x07c00000u;
+#undef P3O_NAN_OR_INF
+  return word;
+}
+
+/* The column's values in the order the packers hand them out, as floats, no scaling
+ * (the switch bodies of Packer::get_data1f..4f, :457-830).  Returns how many. */
+static int raw_get(const p3o_column *c, const uint8_t *p, float *v) {
+  int k, n = c->num_values;
+  uint32_t w;
+  switch (c->numeric_type) {
+  case P3O_NT_UINT8: for (k = 0; k < n; ++k) v[k] = (float)p[k]; break;
+  case P3O_NT_INT8: for (k = 0; k < n; ++k) v[k] = (float)(int8_t)p[k]; break;
+  case P3O_NT_UINT16: for (k = 0; k < n; ++k) { uint16_t x; memcpy(&x, p + 2 * k, 2); v[k] = (float)x; } break;
+  case P3O_NT_INT16: for (k = 0; k < n; ++k) { int16_t x; memcpy(&x, p + 2 * k, 2); v[k] = (float)x; } break;
+  case P3O_NT_UINT32: for (k = 0; k < n; ++k) { uint32_t x; memcpy(&x, p + 4 * k, 4); v[k] = (float)x; } break;
+  case P3O_NT_INT32: for (k = 0; k < n; ++k) { int32_t x; memcpy(&x, p + 4 * k, 4); v[k] = (float)x; } break;
+  case P3O_NT_FLOAT32: memcpy(v, p, (size_t)n * 4); break;
+  case P3O_NT_FLOAT64: for (k = 0; k < n; ++k) { double x; memcpy(&x, p + 8 * k, 8); v[k] = (float)x; } break;
+  case P3O_NT_PACKED_DCBA:   /* d c b a = the four bytes in memory order (:787-796, unpack_abcd_* geomVertexData.I:343-370) */
+    memcpy(&w, p, 4);
+    v[0] = (float)(w & 0xffu); v[1] = (float)((w >> 8) & 0xffu); v[2] = (float)((w >> 16) & 0xffu); v[3] = (float)(w >> 24);
+    break;
+  case P3O_NT_PACKED_DABC:   /* b c d a (:798-807) */
+    memcpy(&w, p, 4);
+    v[0] = (float)((w >> 16) & 0xffu); v[1] = (float)((w >> 8) & 0xffu); v[2] = (float)(w & 0xffu); v[3] = (float)(w >> 24);
+    break;
+  case P3O_NT_PACKED_UFLOAT:  /* :700-708 */
+    memcpy(&w, p, 4);
+    v[0] = ufloat_field_to_float(w & 0x7ffu, 6);
+    v[1] = ufloat_field_to_float((w >> 11) & 0x7ffu, 6);
+    v[2] = ufloat_field_to_float(w >> 22, 5);
+    break;
+  default: break;
+  }
+  return n;
+}
+
+/* ... and back: the first `n` values of v, n <= num_values (the switch bodies of Packer::set_data1f..4f,
+ * :1582-1975; packed words take all their values at once). */
+static void raw_set(const p3o_column *c, uint8_t *p, int n, const float *v) {
   int k;
-  for (k = 0; k < n; ++k) { double d = (double)v[k]; memcpy(p + 8 * k, &d, 8); }
+  uint32_t w;
+  switch (c->numeric_type) {
+  case P3O_NT_UINT8: for (k = 0; k < n; ++k) p[k] = (uint8_t)cast_uint(v[k]); break;
+  case P3O_NT_INT8: for (k = 0; k < n; ++k) p[k] = (uint8_t)cast_int(v[k]); break;
+  case P3O_NT_UINT16: for (k = 0; k < n; ++k) { uint16_t x = (uint16_t)cast_uint(v[k]); memcpy(p + 2 * k, &x, 2); } break;
+  case P3O_NT_INT16: for (k = 0; k < n; ++k) { uint16_t x = (uint16_t)cast_int(v[k]); memcpy(p + 2 * k, &x, 2); } break;
+  case P3O_NT_UINT32: for (k = 0; k < n; ++k) { uint32_t x = cast_uint(v[k]); memcpy(p + 4 * k, &x, 4); } break;
+  case P3O_NT_INT32: for (k = 0; k < n; ++k) { int32_t x = cast_int(v[k]); memcpy(p + 4 * k, &x, 4); } break;
+  case P3O_NT_FLOAT32: memcpy(p, v, (size_t)n * 4); break;
+  case P3O_NT_FLOAT64: for (k = 0; k < n; ++k) { double x = (double)v[k]; memcpy(p + 8 * k, &x, 8); } break;
+  case P3O_NT_PACKED_DCBA:   /* pack_abcd(v3, v2, v1, v0), :1925-1927, geomVertexData.I:331-338 */
+    w = ((cast_uint(v[3]) & 0xffu) << 24) | ((cast_uint(v[2]) & 0xffu) << 16) | ((cast_uint(v[1]) & 0xffu) << 8) | (cast_uint(v[0]) & 0xffu);
+    memcpy(p, &w, 4);
+    break;
+  case P3O_NT_PACKED_DABC:   /* pack_abcd(v3, v0, v1, v2), :1929-1931 */
+    w = ((cast_uint(v[3]) & 0xffu) << 24) | ((cast_uint(v[0]) & 0xffu) << 16) | ((cast_uint(v[1]) & 0xffu) << 8) | (cast_uint(v[2]) & 0xffu);
+    memcpy(p, &w, 4);
+    break;
+  case P3O_NT_PACKED_UFLOAT:  /* :1844-1846 */
+    w = pack_ufloat(v[0], v[1], v[2]);
+    memcpy(p, &w, 4);
+    break;
+  default: break;
+  }
+}
+
+/* What a colour packer divides by on reading and multiplies by on writing (Packer_color, :3397-3590,
+ * :3851-4025; `_v4 /= 255.0f` multiplies by the rounded reciprocal, lvecBase4_src.I:735-745). */
+static float color_scale(const p3o_column *c) {
+  switch (c->numeric_type) {
+  case P3O_NT_UINT8: case P3O_NT_PACKED_DCBA: case P3O_NT_PACKED_DABC: return 255.0f;
+  case P3O_NT_UINT16: return 65535.0f;
+  case P3O_NT_UINT32: return 4294967295.0f;
+  default: return 0.0f;  /* float32, float64, packed_ufloat: stored as they are */
+  }
+}
+
+static void col_get4(const p3o_column *c, const uint8_t *p, float *v) {
+  int k, n, kind = packer_kind(c);
+  v[0] = v[1] = v[2] = v[3] = 0.0f;               /* Packer::get_data4f pads with 0, :719-737 */
+  n = raw_get(c, p, v);
+  if (kind != PK_PLAIN) {
+    float scale = color_scale(c);
+    if (scale != 0.0f) {
+      float recip = 1.0f / scale;
+      for (k = 0; k < n; ++k) v[k] = v[k] * recip;
+    }
+    if (n == 3) v[3] = 1.0f;                      /* Packer_color::get_data4f on three values, :3530-3534 */
+  }
+}
+static void col_get3(const p3o_column *c, const uint8_t *p, float *v) {
+  float t[4];
+  col_get4(c, p, t);                              /* a colour of four values is read whole and cut, :3521-3525 */
+  v[0] = t[0]; v[1] = t[1]; v[2] = t[2];
+}
+
+static void col_set4(const p3o_column *c, uint8_t *p, const float *v) {
+  int k, n = c->num_values, kind = packer_kind(c);
+  float t[4];
+  for (k = 0; k < 4; ++k) t[k] = v[k];
+  if (kind == PK_COLOR_CLAMPED) {                 /* :4493-4505, :4543-4552: std::clamp(x, 0, 1) * 255 */
+    for (k = 0; k < 4; ++k) {
+      float x = t[k];
+      x = x < 0.0f ? 0.0f : (1.0f < x ? 1.0f : x);
+      t[k] = x * 255.0f;
+    }
+  } else if (kind == PK_COLOR) {
+    float scale = color_scale(c);
+    if (scale != 0.0f)
+      for (k = 0; k < n; ++k) t[k] = t[k] * scale;  /* `scaled = data * 255.0f`, :3940 ff. */
+  }
+  raw_set(c, p, n, t);                            /* fewer than four values: the leading ones, :1863-1875 */
+}
+static void col_set3(const p3o_column *c, uint8_t *p, const float *v) {
+  float t[4];
+  t[0] = v[0]; t[1] = v[1]; t[2] = v[2];
+  /* on four values: Packer::set_data3f stores w = 0 (:1848-1850), the colour packers alpha = 1 (:3933-3935) */
+  t[3] = packer_kind(c) == PK_PLAIN ? 0.0f : 1.0f;
+  col_set4(c, p, t);
 }
 
 /* do_transform_point_column / do_transform_vector_column for one run
@@ -565,18 +771,25 @@ static void set_f64(uint8_t *p, int n, const float *v) {
 static void transform_run(const p3o_mesh *mesh, const p3o_column *col, uint8_t *out, int stride,
                           const float *mat, int begin, int end) {
   int nv = col->num_values, i;
-  int f64 = col->numeric_type == P3O_NT_FLOAT64;
+  int fast = col->numeric_type == P3O_NT_FLOAT32 && (nv == 3 || nv == 4);   /* the table_xform_* branches */
   uint8_t *datat = out + col->start + (size_t)begin * stride;
   if (col->contents == P3O_C_POINT) {
     for (i = 0; i < end - begin; ++i) {
-      if (!f64) {
+      if (fast) {
         float *v = (float *)(datat + (size_t)i * stride);
         if (nv == 3) xform_point3(v, mat); else xform_vec4(v, mat);
       } else {  /* GeomVertexRewriter branches :1782-1799 */
         float v[4];
-        get_f64(datat + (size_t)i * stride, nv, v);
-        if (nv == 3) xform_point3(v, mat); else xform_vec4(v, mat);
-        set_f64(datat + (size_t)i * stride, nv, v);
+        uint8_t *p = datat + (size_t)i * stride;
+        if (nv == 4) {
+          col_get4(col, p, v);
+          xform_vec4(v, mat);
+          col_set4(col, p, v);
+        } else {
+          col_get3(col, p, v);
+          xform_point3(v, mat);
+          col_set3(col, p, v);
+        }
       }
     }
   } else {
@@ -588,7 +801,7 @@ static void transform_run(const p3o_mesh *mesh, const p3o_column *col, uint8_t *
       memcpy(xform, mat, sizeof(xform));
     }
     for (i = 0; i < end - begin; ++i) {
-      if (!f64) {
+      if (fast) {
         float *v = (float *)(datat + (size_t)i * stride);
         if (normalize) {          /* table_xform_normal3f, also for 4-component columns */
           xform_vec3(v, xform);
@@ -598,14 +811,13 @@ static void transform_run(const p3o_mesh *mesh, const p3o_column *col, uint8_t *
         } else {
           xform_vec4(v, xform);
         }
-      } else {  /* :1862-1879: get_data3 / set_data3; on 4 values Packer::set_data3f stores w = 0
-                 * (geomVertexColumn.cxx:1848-1850) */
+      } else {  /* :1862-1879: get_data3 / set_data3 whatever the number of values */
         float v[4];
-        get_f64(datat + (size_t)i * stride, 3, v);
+        uint8_t *p = datat + (size_t)i * stride;
+        col_get3(col, p, v);
         xform_vec3(v, xform);
         if (normalize) normalize3(v);
-        v[3] = 0.0f;
-        set_f64(datat + (size_t)i * stride, nv, v);
+        col_set3(col, p, v);
       }
     }
   }
@@ -622,10 +834,11 @@ int p3o_animate(const p3o_mesh *mesh, const float *palette, const float *sliders
   int n = mesh->num_rows, a, o, ci, mi, i, j;
   float *blends = NULL;
 
-  /* validate: only the float32 fast paths are restated */
+  /* validate */
   for (ci = 0; ci < mesh->num_skin_columns; ++ci) {
     const p3o_column *c = &mesh->skin_columns[ci];
-    if ((c->numeric_type != P3O_NT_FLOAT32 && c->numeric_type != P3O_NT_FLOAT64) || (c->num_values != 3 && c->num_values != 4)) return -1;
+    if (!column_supported(c) || packer_kind(c) != PK_PLAIN) return -1;
+    if (c->start < 0 || c->start + column_bytes(c) > mesh->array_stride[c->array]) return -1;
     if (output_index(mesh, c->array) < 0) return -1;
   }
 
@@ -647,8 +860,7 @@ int p3o_animate(const p3o_mesh *mesh, const float *palette, const float *sliders
     int bstride, dstride;
     uint8_t *bdata;
     const uint8_t *ddata;
-    int bf64 = m->base.numeric_type == P3O_NT_FLOAT64, df64 = m->delta.numeric_type == P3O_NT_FLOAT64;
-    if (bo < 0 || (!bf64 && m->base.numeric_type != P3O_NT_FLOAT32) || (!df64 && m->delta.numeric_type != P3O_NT_FLOAT32)) return -1;
+    if (bo < 0 || !column_supported(&m->base) || !column_supported(&m->delta)) return -1;
     if (slider_value == 0.0f) continue;
     bstride = mesh->array_stride[m->base.array];
     dstride = mesh->array_stride[m->delta.array];
@@ -659,30 +871,33 @@ int p3o_animate(const p3o_mesh *mesh, const float *palette, const float *sliders
       for (j = begin; j < end; ++j) {
         uint8_t *vp = bdata + (size_t)j * bstride;
         const uint8_t *dp = ddata + (size_t)j * dstride;
-        float vertex[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        int bn = m->base.num_values, dn = m->delta.num_values, k;
-        /* the base / delta values as get_data3/4 return them; default Packer::get_data3f/4f
-         * pad missing components with 0 (geomVertexColumn.cxx:608-737) */
-        if (bf64) get_f64(vp, bn, vertex); else memcpy(vertex, vp, (size_t)bn * 4);
-        if (df64) get_f64(dp, dn < 4 ? dn : 4, d); else memcpy(d, dp, (size_t)(dn < 4 ? dn : 4) * 4);
-        if (bn == 4) {
+        float vertex[4], d[4];
+        int k;
+        if (m->base.num_values == 4) {
+          /* GeomVertexColumn::has_homogeneous_coord, geomVertexColumn.I:182-192 */
           int homogeneous = (m->base.contents == P3O_C_POINT || m->base.contents == P3O_C_TEXCOORD);
+          col_get4(&m->base, vp, vertex);
           if (homogeneous) {
             /* :1499-1507  d(3) *= slider_value * vertex[3] */
             float s = slider_value * vertex[3];
+            col_get3(&m->delta, dp, d);
             d[0] *= s; d[1] *= s; d[2] *= s;
             vertex[0] = vertex[0] + d[0];
             vertex[1] = vertex[1] + d[1];
             vertex[2] = vertex[2] + d[2];
           } else {
             /* :1516-1520  vertex + d * slider_value (4 components) */
+            col_get4(&m->delta, dp, d);
             for (k = 0; k < 4; ++k) vertex[k] = vertex[k] + d[k] * slider_value;
           }
+          col_set4(&m->base, vp, vertex);
         } else {
           /* :1531-1535  vertex + d * slider_value (<= 3 components) */
-          for (k = 0; k < bn && k < 3; ++k) vertex[k] = vertex[k] + d[k] * slider_value;
+          col_get3(&m->base, vp, vertex);
+          col_get3(&m->delta, dp, d);
+          for (k = 0; k < 3; ++k) vertex[k] = vertex[k] + d[k] * slider_value;
+          col_set3(&m->base, vp, vertex);
         }
-        if (bf64) set_f64(vp, bn, vertex); else memcpy(vp, vertex, (size_t)bn * 4);
       }
     }
   }

@@ -25,11 +25,19 @@ extern "C" {
 #define P3O_NT_UINT8 0
 #define P3O_NT_UINT16 1
 #define P3O_NT_UINT32 2
+#define P3O_NT_PACKED_DCBA 3
+#define P3O_NT_PACKED_DABC 4
 #define P3O_NT_FLOAT32 5
 #define P3O_NT_FLOAT64 6
+#define P3O_NT_STDFLOAT 7
+#define P3O_NT_INT8 8
+#define P3O_NT_INT16 9
+#define P3O_NT_INT32 10
+#define P3O_NT_PACKED_UFLOAT 11
 #define P3O_C_POINT 1
 #define P3O_C_VECTOR 3
 #define P3O_C_TEXCOORD 4
+#define P3O_C_COLOR 5
 #define P3O_C_NORMAL 9
 /* CoordinateSystem (panda/src/linmath/coordinateSystem.h) */
 #define P3O_CS_ZUP_RIGHT 1

@@ -27,6 +27,17 @@ NUMERIC_BYTES = {NT_uint8: 1, NT_uint16: 2, NT_uint32: 4, NT_packed_dcba: 4, NT_
                  NT_packed_ufloat: 4}
 
 
+PACKED_VALUES = {NT_packed_dcba: 4, NT_packed_dabc: 4, NT_packed_ufloat: 3}   # values held by ONE 32-bit component
+
+
+def column_bytes(numeric_type: int, num_values: int) -> int:
+    """Bytes of a column in its row (GeomVertexColumn::setup, geomVertexColumn.cxx:154-234): the packed types keep
+    all their values in one 32-bit word."""
+    if numeric_type in PACKED_VALUES:
+        return 4 * (num_values // PACKED_VALUES[numeric_type])
+    return num_values * NUMERIC_BYTES[numeric_type]
+
+
 @dataclass
 class Column:
     """One GeomVertexColumn: (array, start, num_values, numeric_type, contents)."""
@@ -38,6 +49,10 @@ class Column:
 
     def as_tuple(self) -> Tuple[int, int, int, int, int]:
         return (self.array, self.start, self.num_values, self.numeric_type, self.contents)
+
+    @property
+    def num_bytes(self) -> int:
+        return column_bytes(self.numeric_type, self.num_values)
 
 
 @dataclass
@@ -102,7 +117,7 @@ class FlatMesh:
         for c in self.skin_columns:
             if not self.is_output[c.array]:
                 raise ValueError("skin column in a non-output array")
-            if c.start + c.num_values * NUMERIC_BYTES[c.numeric_type] > self.arrays[c.array].shape[1]:
+            if c.start + c.num_bytes > self.arrays[c.array].shape[1]:
                 raise ValueError("skin column exceeds the stride")
         if self.blend_column is not None:
             bi = self.blend_indices()

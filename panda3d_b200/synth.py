@@ -237,6 +237,120 @@ def make_mesh(num_rows: int, num_transforms: int, num_blends: int, *, seed: int 
     return SynthMesh(fm, cols, slider_names, slider_rows, name)
 
 
+def _random_column(rng, num_rows: int, nv: int, nt: int, contents: int, *, delta: bool = False) -> np.ndarray:
+    """uint8 [num_rows, column bytes] of plausible values for one column: finite, and far enough inside the
+    integer types' ranges that an animated value still fits the C conversion the reference stores it with."""
+    unit = contents in (F.C_vector, F.C_normal)
+    if nt in (F.NT_float32, F.NT_float64):
+        if delta:
+            v = rng.uniform(-0.3, 0.3, (num_rows, nv))
+        elif contents == F.C_color:
+            v = rng.uniform(0, 1, (num_rows, nv))
+        elif unit:
+            v = rng.normal(size=(num_rows, nv))
+            v /= np.linalg.norm(v[:, :min(nv, 3)], axis=1, keepdims=True)
+        else:
+            v = rng.uniform(-1, 1, (num_rows, nv))
+            if nv == 4:
+                v[:, 3] = rng.uniform(0.5, 2.0, num_rows)
+        if nt == F.NT_float64:
+            return np.ascontiguousarray(v.astype(np.float32).astype(np.float64) * (1.0 + 1e-9)).view(np.uint8).reshape(num_rows, -1)
+        return np.ascontiguousarray(v.astype(np.float32)).view(np.uint8).reshape(num_rows, -1)
+    if nt in (F.NT_packed_dcba, F.NT_packed_dabc):
+        return rng.integers(0, 256, (num_rows, 4), dtype=np.uint8)
+    if nt == F.NT_packed_ufloat:
+        # r11 g11 b10 with exponents 0 (denormals, zero) .. 17: finite, and small enough to stay finite when animated
+        r = rng.integers(0, 18 << 6, num_rows).astype(np.uint32)
+        g = rng.integers(0, 18 << 6, num_rows).astype(np.uint32)
+        b = rng.integers(0, 18 << 5, num_rows).astype(np.uint32)
+        return np.ascontiguousarray(r | (g << 11) | (b << 22)).view(np.uint8).reshape(num_rows, 4)
+    dt, lo, hi = {F.NT_uint8: (np.uint8, 0, 256), F.NT_int8: (np.int8, -128, 128),
+                  F.NT_uint16: (np.uint16, 0, 40000), F.NT_int16: (np.int16, -9000, 9000),
+                  F.NT_uint32: (np.uint32, 0, 1 << 29), F.NT_int32: (np.int32, -(1 << 28), 1 << 28)}[nt]
+    if delta:
+        lo, hi = (0, 12) if lo == 0 else (-12, 12)
+    return np.ascontiguousarray(rng.integers(lo, hi, (num_rows, nv)).astype(dt)).view(np.uint8).reshape(num_rows, -1)
+
+
+def make_typed_mesh(num_rows: int, num_transforms: int, num_blends: int, *, seed: int, columns, morphs=(),
+                    num_sliders: int = 0, slider_band: float = 0.5, weights_per_blend: int = 4,
+                    index_order: str = "runs", rows: Optional[Sequence[Tuple[int, int]]] = None,
+                    coordinate_system: int = F.CS_zup_right, name: str = "typed") -> SynthMesh:
+    """A mesh whose columns are of ANY numeric type: the reference animates everything that is not float32 x 3 / x 4
+    through GeomVertexRewriter (geomVertexData.cxx:1782-1799, 1862-1879) and morphs every base column through it
+    (:1489-1537), so integer, packed and short columns go through the GeomVertexColumn::Packer family.
+
+    columns: (name, num_values, numeric_type, contents[, alignment]) of array 0, in order; C_point / C_vector /
+             C_normal columns are skinned.  num_values counts VALUES (4 for the packed colour words, 3 for packed_ufloat).
+    morphs:  (base column name, delta num_values, delta numeric_type): every slider gets one such delta column in
+             array 1, overlapping bands of rows, so rows are hit by several morphs in a row.
+    """
+    rng = np.random.default_rng(seed)
+    cols: List[Tuple[str, Column]] = []
+    by_name: Dict[str, Column] = {}
+    blocks = []
+    start = 0
+    for spec in columns:
+        cname, nv, nt, contents = spec[:4]
+        cb = F.NUMERIC_BYTES[nt]
+        align = spec[4] if len(spec) > 4 else max(cb, 4)
+        start = (start + align - 1) // align * align
+        c = Column(0, start, nv, nt, contents)
+        cols.append((cname, c))
+        by_name[cname] = c
+        blocks.append((c, _random_column(rng, num_rows, nv, nt, contents)))
+        start += c.num_bytes
+    stride0 = (start + 3) // 4 * 4
+    arr0 = np.zeros((num_rows, stride0), np.uint8)
+    for c, data in blocks:
+        arr0[:, c.start:c.start + c.num_bytes] = data
+
+    start = 0
+    c_blend = Column(1, 0, 1, F.NT_uint16, F.C_index)
+    cols.append(("transform_blend", c_blend))
+    start = 2
+    slider_names, slider_rows, morph_list, dblocks = [], [], [], []
+    band = max(1, int(round(slider_band * num_rows)))
+    for sidx in range(num_sliders):
+        sname = f"s{sidx}"
+        slider_names.append(sname)
+        b0 = min(num_rows - 1, sidx * num_rows // max(1, 2 * num_sliders))
+        r = np.asarray([[b0, min(num_rows, b0 + band)]], np.int32)
+        slider_rows.append(r)
+        for base, dnv, dnt in morphs:
+            cb = F.NUMERIC_BYTES[dnt]
+            start = (start + cb - 1) // cb * cb
+            dc = Column(1, start, dnv, dnt, F.C_morph_delta)
+            cols.append((f"{base}.morph.{sname}", dc))
+            data = _random_column(rng, num_rows, dnv, dnt, F.C_morph_delta, delta=True)
+            data[:int(r[0, 0])] = 0
+            data[int(r[0, 1]):] = 0
+            dblocks.append((dc, data))
+            morph_list.append(Morph(sidx, by_name[base], dc, r))
+            start += dc.num_bytes
+    stride1 = max(2, (start + 3) // 4 * 4) if dblocks else 2
+    arr1 = np.zeros((num_rows, stride1), np.uint8)
+    for dc, data in dblocks:
+        arr1[:, dc.start:dc.start + dc.num_bytes] = data
+
+    if index_order == "runs":
+        runs = rng.integers(0, num_blends, size=num_rows // 6 + 2)
+        bidx = np.resize(np.repeat(runs, rng.integers(1, 13, size=runs.size)), num_rows)
+    else:
+        bidx = rng.integers(0, num_blends, size=num_rows)
+    arr1[:, :2] = bidx.astype(np.uint16).reshape(-1, 1).view(np.uint8)
+
+    offsets, xf, w = make_blend_table(num_transforms, num_blends, weights_per_blend, rng)
+    order = {F.C_point: 0, F.C_normal: 1, F.C_vector: 1}
+    skin = sorted((c for _, c in cols if c.array == 0 and c.contents in order), key=lambda c: order[c.contents])
+    rr = np.asarray(rows if rows is not None else [(0, num_rows)], np.int32).reshape(-1, 2)
+    fm = FlatMesh(num_rows=num_rows, arrays=[arr0, arr1], is_output=[True, False], skin_columns=skin,
+                  blend_column=c_blend, num_transforms=num_transforms, blend_offsets=offsets,
+                  blend_transform=xf, blend_weight=w, row_ranges=rr, num_sliders=num_sliders,
+                  morphs=morph_list, coordinate_system=coordinate_system)
+    return SynthMesh(fm, cols, slider_names, slider_rows, name)
+
+
 def make_sliders(num_sliders: int, frames: int, seed: int) -> np.ndarray:
     """Slider values U(0,1) with 25 % forced to exactly 0 (the `!= 0` skip, geomVertexData.cxx:1483)."""
     rng = np.random.default_rng(seed)

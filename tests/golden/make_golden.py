@@ -48,6 +48,40 @@ def cases():
     yield "f64_uniform_scale", mk(200, 8, 8, seed=73, float64=True, weights_per_blend=1), P(8, 1, 74, scale=0.8), None
     yield "f64_align16_morph", mk(300, 12, 60, seed=75, float64=True, align16=True, tbn=True, num_sliders=4, slider_band=0.4,
                                   morph_columns=("vertex", "normal"), rows=[(5, 250)]), P(12, 2, 76), S(4, 2, 77)
+    # columns of every other numeric type, 1..4 values: the GeomVertexColumn::Packer family behind GeomVertexRewriter
+    # (geomVertexColumn.cxx:457-1975), and morphs of colour / texcoord / integer base columns (geomVertexData.cxx:1489-1537)
+    from panda3d_b200 import flat as F
+    tm = synth.make_typed_mesh
+    pt, vec, nrm, col, tex, oth = F.C_point, F.C_vector, F.C_normal, F.C_color, F.C_texcoord, F.C_other
+    yield "typed_signed", tm(300, 12, 60, seed=81, columns=[
+        ("vertex", 3, F.NT_int16, pt), ("normal", 4, F.NT_int8, nrm), ("tangent", 3, F.NT_int32, vec),
+        ("binormal", 3, F.NT_uint16, vec), ("texcoord", 2, F.NT_float32, tex)]), P(12, 2, 82), None
+    yield "typed_unsigned_point4", tm(300, 12, 60, seed=83, columns=[
+        ("vertex", 4, F.NT_uint8, pt), ("normal", 3, F.NT_uint32, nrm), ("tangent", 4, F.NT_packed_dcba, vec),
+        ("binormal", 4, F.NT_packed_dabc, vec), ("aux", 4, F.NT_int32, pt)]), P(12, 2, 84, scale=(1, 1.2, 0.8)), None
+    yield "typed_short_columns", tm(300, 10, 50, seed=85, columns=[
+        ("vertex", 2, F.NT_float32, pt), ("normal", 3, F.NT_int16, nrm, 2), ("tangent2", 2, F.NT_float64, vec, 8), ("tangent", 1, F.NT_int16, vec, 2),
+        ("binormal", 1, F.NT_float32, vec), ("aux", 2, F.NT_int16, pt, 2), ("aux2", 1, F.NT_uint32, pt)]), P(10, 2, 86), None
+    yield "typed_ufloat", tm(300, 10, 50, seed=87, columns=[
+        ("vertex", 3, F.NT_packed_ufloat, pt), ("normal", 3, F.NT_packed_ufloat, nrm), ("tangent", 3, F.NT_packed_ufloat, vec)]), \
+        P(10, 2, 88, scale=(1.5, 0.7, 1.1)), None
+    yield "typed_unaligned", tm(300, 10, 50, seed=89, columns=[
+        ("pad", 1, F.NT_uint8, oth, 1), ("vertex", 3, F.NT_uint8, pt, 1), ("normal", 3, F.NT_int16, nrm, 1),
+        ("tangent", 4, F.NT_packed_dabc, vec, 1), ("binormal", 3, F.NT_uint16, vec, 1), ("aux", 4, F.NT_int16, pt, 1)],
+        rows=[(7, 120), (150, 299)]), P(10, 2, 90), None
+    yield "typed_morph_colors", tm(300, 10, 50, seed=91, num_sliders=3, columns=[
+        ("vertex", 3, F.NT_float32, pt), ("normal", 3, F.NT_float32, nrm), ("color", 4, F.NT_uint8, col),
+        ("color.b", 4, F.NT_packed_dabc, col), ("color.c", 4, F.NT_uint16, col), ("color.d", 3, F.NT_uint32, col),
+        ("color.e", 4, F.NT_packed_dcba, col), ("color.f", 3, F.NT_packed_ufloat, col), ("color.g", 3, F.NT_uint8, col),
+        ("color.h", 4, F.NT_float32, col), ("color.i", 3, F.NT_uint16, col)],
+        morphs=[("color", 4, F.NT_float32), ("color.b", 4, F.NT_float32), ("color.c", 4, F.NT_float32), ("color.d", 3, F.NT_float32),
+                ("color.e", 4, F.NT_float32), ("color.f", 3, F.NT_float32), ("color.g", 3, F.NT_float32), ("color.h", 4, F.NT_float32),
+                ("color.i", 3, F.NT_float64)]), P(10, 3, 92), S(3, 3, 93)
+    yield "typed_morph_points", tm(300, 10, 50, seed=94, num_sliders=4, columns=[
+        ("vertex", 3, F.NT_int16, pt), ("normal", 3, F.NT_int8, nrm), ("texcoord", 2, F.NT_float32, tex),
+        ("texcoord.b", 4, F.NT_int16, tex), ("texcoord.c", 3, F.NT_uint16, tex), ("aux", 4, F.NT_int32, pt), ("aux2", 4, F.NT_int16, oth)],
+        morphs=[("vertex", 3, F.NT_int8), ("normal", 3, F.NT_float32), ("texcoord", 2, F.NT_float32), ("texcoord.b", 3, F.NT_int8),
+                ("texcoord.c", 2, F.NT_uint8), ("aux", 3, F.NT_int16), ("aux2", 4, F.NT_float32)]), P(10, 3, 95), S(4, 3, 96)
     for cs, csname in ((2, "yup_right"), (3, "zup_left"), (4, "yup_left")):
         yield "cs_" + csname, mk(300, 8, 8, seed=8, weights_per_blend=1, coordinate_system=cs), P(8, 1, 18, scale=0.5), None
 
