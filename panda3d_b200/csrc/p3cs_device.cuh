@@ -2,6 +2,7 @@
 // transforms (LMatrix4f::xform_point / xform_vec / xform) and the per-row morph + skin step.
 #pragma once
 #include "p3cs_kernels.cuh"
+#include "p3cs_packer.cuh"
 #include "p3cs_math.cuh"
 
 namespace p3cs {
@@ -152,6 +153,64 @@ __device__ __forceinline__ void xform_vec4(float *v, const float m[4][4]) {
   for (int j = 0; j < 4; ++j) v[j] = r[j];
 }
 
+// An integer or packed dynamic column of one row, in shared memory.  The reference works on the stored value:
+// every morph reads it (get_data3/4), adds its delta and stores it (set_data3/4) -- truncating to the column's
+// type each time -- and the blend transform does the same once more (geomVertexData.cxx:1489-1537, 1782-1799,
+// 1862-1879).  Four values: get_data4 / set_data4; fewer: get_data3 / set_data3; vectors always get_data3 / set_data3.
+template <bool FULL>
+__device__ __noinline__ void animate_typed_column(const MeshDev &mesh, const DynColumn &col, int dyn_index, uint8_t *cell,
+                                                  int morph_beg, int morph_end, const float *sliders, bool skinned,
+                                                  const Record<FULL> &rec) {
+  const int nv = col.num_values, typed = col.typed;
+  float v[4];
+  for (int e = morph_beg; e < morph_end; ++e) {
+    const uint32_t key = __ldg(mesh.morph_keys + e);
+    if ((int)(key >> 16) != dyn_index) continue;
+    const float value = __ldg(sliders + (key & 0xffffu));
+    if (value == 0.0f) continue;  // `if (slider_value != 0.0f)`, :1483
+    const float4 d = __ldg(mesh.morph_deltas + e);
+    typed_get4(typed, nv, cell, v);
+    if (nv == 4) {
+      if (col.homogeneous) {  // :1499-1507
+        const float s = value * v[3];
+        v[0] = v[0] + d.x * s;
+        v[1] = v[1] + d.y * s;
+        v[2] = v[2] + d.z * s;
+      } else {  // :1516-1520
+        v[0] = v[0] + d.x * value;
+        v[1] = v[1] + d.y * value;
+        v[2] = v[2] + d.z * value;
+        v[3] = v[3] + d.w * value;
+      }
+      typed_set4(typed, nv, cell, v);
+    } else {  // :1531-1535
+      v[0] = v[0] + d.x * value;
+      v[1] = v[1] + d.y * value;
+      v[2] = v[2] + d.z * value;
+      typed_set3(typed, nv, cell, v);
+    }
+  }
+  if (!skinned || col.skin == 0) return;
+  typed_get4(typed, nv, cell, v);
+  if (col.skin == 1) {  // C_point (:1782-1799)
+    if (nv == 4) {
+      if (FULL) xform_vec4(v, rec.m);
+      typed_set4(typed, nv, cell, v);
+    } else {
+      xform_point3(v, rec.m);
+      typed_set3(typed, nv, cell, v);
+    }
+  } else {  // C_vector / C_normal (:1862-1879)
+    if (col.skin == 2) {
+      xform_vec3(v, rec.m);
+    } else {
+      xform_vec3(v, rec.x);
+      if (rec.normalize) normalize3(v[0], v[1], v[2]);
+    }
+    typed_set3(typed, nv, cell, v);
+  }
+}
+
 // One dynamic column of one row, in shared memory: morph deltas first
 // (geomVertexData.cxx:1462-1543), then the blend transform (:1758-1880).
 // float64 columns take the reference's GeomVertexRewriter branches (:1782-1799, :1862-1879): components
@@ -162,6 +221,10 @@ __device__ __forceinline__ void animate_column(const MeshDev &mesh, const DynCol
                                                int morph_beg, int morph_end, const float *sliders, bool skinned,
                                                const Record<FULL> &rec) {
   const int nv = col.num_values;
+  if (col.typed != 0) {  // integer / packed column: every step reads the stored value and stores its result (p3cs_packer.cuh)
+    animate_typed_column<FULL>(mesh, col, dyn_index, reinterpret_cast<uint8_t *>(cell), morph_beg, morph_end, sliders, skinned, rec);
+    return;
+  }
   const bool f64 = col.f64 != 0;
   float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   if (!f64) {
@@ -204,18 +267,21 @@ __device__ __forceinline__ void animate_column(const MeshDev &mesh, const DynCol
   }
 
   if (skinned && col.skin != 0) {
+    // a column of fewer than three values: set_data3 stored only those, the transform reads the rest back as 0
+    if (nv < 3) v[2] = 0.0f;
+    if (nv < 2) v[1] = 0.0f;
     dirty3 = true;
-    if (col.skin == 1) {  // C_point
-      if (nv == 3) xform_point3(v, rec.m);
+    if (col.skin == 1) {  // C_point; fewer than three values: get_data3 pads with 0, set_data3 keeps the leading ones (:1793-1798)
+      if (nv < 4) xform_point3(v, rec.m);
       else if (FULL) { xform_vec4(v, rec.m); dirty4 = true; }
     } else if (col.skin == 2) {  // C_vector: xform = mat
-      if (nv == 3 || f64) xform_vec3(v, rec.m);
+      if (nv < 4 || f64) xform_vec3(v, rec.m);
       else if (FULL) xform_vec4(v, rec.m);
     } else {  // C_normal
       if (rec.normalize) {  // table_xform_normal3f, also on 4-component columns (:1854-1855)
         xform_vec3(v, rec.x);
         normalize3(v[0], v[1], v[2]);
-      } else if (nv == 3 || f64) {
+      } else if (nv < 4 || f64) {
         xform_vec3(v, rec.x);
       } else if (FULL) {
         xform_vec4(v, rec.x);

@@ -19,12 +19,13 @@ constexpr int kRecFull = 36;
 
 // A column that changes per frame: skinned (point/vector/normal) and/or a morph base.
 struct DynColumn {
-  int16_t output;      // output array index
   int16_t start;       // byte offset in the row
+  int8_t output;       // output array index
   int8_t num_values;   // 1..4
   int8_t skin;         // 0 none, 1 point, 2 vector, 3 normal
   int8_t homogeneous;  // morph: scale deltas by w (C_point / C_texcoord with 4 values)
   int8_t f64;          // NT_float64 components: read/written through float like GeomVertexRewriter::get_data3/set_data3
+  uint8_t typed;       // 0: float32 / float64; else an integer or packed column, p3cs_packer.cuh's typed_code()
 };
 
 // A plan of the run kernel (p3cs_run.cuh; built by p3cs_runplan.h at upload): tiles of `tile_rows` rows, per tile a

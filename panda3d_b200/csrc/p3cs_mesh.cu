@@ -3,9 +3,11 @@
 // dynamic columns, the shared-memory plan, record groups with their conflict-aware record order, the
 // per-row morph CSR.  Host C++.
 #include "p3cs_internal.h"
+#include "p3cs_packer.cuh"
 #include "p3cs_run.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdint>
 #include <cstring>
@@ -18,10 +20,68 @@ using namespace p3cs;
 static int check_column(const p3cs_mesh_desc *d, const p3cs_column_desc &c, const char *what) {
   if (c.array < 0 || c.array >= d->num_arrays) return p3cs_fail(P3CS_ERR_INVALID, "%s: array %d out of range", what, c.array);
   const int stride = d->arrays[c.array].stride;
-  if (c.start < 0 || c.num_values < 1 || c.start + c.num_values * numeric_bytes(c.numeric_type) > stride)
-    return p3cs_fail(P3CS_ERR_INVALID, "%s: column [%d,+%d x %d) exceeds stride %d", what, c.start, c.num_values,
-                numeric_bytes(c.numeric_type), stride);
+  if (c.start < 0 || c.num_values < 1 || c.start + column_bytes(c.numeric_type, c.num_values) > stride)
+    return p3cs_fail(P3CS_ERR_INVALID, "%s: column [%d,+%d bytes) of %d values exceeds stride %d", what, c.start,
+                column_bytes(c.numeric_type, c.num_values), c.num_values, stride);
   return P3CS_OK;
+}
+
+// Is this a column the reference itself can animate, and one the kernels address?  float32 / float64 columns are
+// handled as 32-bit words (4-byte aligned starts); the integer and packed ones byte by byte, anywhere.
+static int check_dynamic_column(const p3cs_column_desc &c, const char *what, int index) {
+  if (!column_supported(c.contents, c.numeric_type, c.num_values))
+    return p3cs_fail(P3CS_ERR_UNSUPPORTED, "%s %d: numeric type %d x %d values with contents %d is a combination the reference's "
+                     "GeomVertexColumn packers do not read or write either", what, index, c.numeric_type, c.num_values, c.contents);
+  const bool is_float = c.numeric_type == P3CS_NT_FLOAT32 || c.numeric_type == P3CS_NT_FLOAT64;
+  if (is_float && c.start % 4 != 0)
+    return p3cs_fail(P3CS_ERR_UNSUPPORTED, "%s %d: float column at byte %d is not 4-byte aligned", what, index, c.start);
+  return P3CS_OK;
+}
+static uint8_t dynamic_column_code(const p3cs_column_desc &c) {
+  if (c.numeric_type == P3CS_NT_FLOAT32 || c.numeric_type == P3CS_NT_FLOAT64) return 0;
+  return (uint8_t)typed_code(c.numeric_type, packer_kind(c.contents, c.numeric_type, c.num_values));
+}
+
+// GeomVertexReader::get_data4 on a morph delta column of any type, on the host (once, at upload): the values in the
+// packer's order as floats, padded with 0; colour types scaled (p3cs_packer.cuh has the device twin and the citations).
+static void host_get4(const p3cs_column_desc &c, const uint8_t *p, float v[4]) {
+  const int n = c.num_values;
+  auto ufloat = [](uint32_t field, int mbits) {
+    const uint32_t exponent = field >> mbits;
+    if (exponent == 0) return ldexpf((float)(field & ((1u << mbits) - 1u)) / (float)(1u << mbits), -14);
+    uint32_t bits = field << (23 - mbits);
+    bits = exponent == 31 ? (bits | 0x7f800000u) : bits + 0x38000000u;
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+  };
+  v[0] = v[1] = v[2] = v[3] = 0.0f;
+  uint32_t w = 0;
+  switch (c.numeric_type) {
+  case P3CS_NT_UINT8: for (int k = 0; k < n; ++k) v[k] = (float)p[k]; break;
+  case P3CS_NT_INT8: for (int k = 0; k < n; ++k) v[k] = (float)(int8_t)p[k]; break;
+  case P3CS_NT_UINT16: for (int k = 0; k < n; ++k) { uint16_t x; memcpy(&x, p + 2 * k, 2); v[k] = (float)x; } break;
+  case P3CS_NT_INT16: for (int k = 0; k < n; ++k) { int16_t x; memcpy(&x, p + 2 * k, 2); v[k] = (float)x; } break;
+  case P3CS_NT_UINT32: for (int k = 0; k < n; ++k) { uint32_t x; memcpy(&x, p + 4 * k, 4); v[k] = (float)x; } break;
+  case P3CS_NT_INT32: for (int k = 0; k < n; ++k) { int32_t x; memcpy(&x, p + 4 * k, 4); v[k] = (float)x; } break;
+  case P3CS_NT_FLOAT32: memcpy(v, p, (size_t)n * 4); break;
+  case P3CS_NT_FLOAT64: for (int k = 0; k < n; ++k) { double x; memcpy(&x, p + 8 * k, 8); v[k] = (float)x; } break;
+  case P3CS_NT_PACKED_DCBA: v[0] = (float)p[0]; v[1] = (float)p[1]; v[2] = (float)p[2]; v[3] = (float)p[3]; break;
+  case P3CS_NT_PACKED_DABC: v[0] = (float)p[2]; v[1] = (float)p[1]; v[2] = (float)p[0]; v[3] = (float)p[3]; break;
+  case P3CS_NT_PACKED_UFLOAT:
+    memcpy(&w, p, 4);
+    v[0] = ufloat(w & 0x7ffu, 6); v[1] = ufloat((w >> 11) & 0x7ffu, 6); v[2] = ufloat(w >> 22, 5);
+    break;
+  default: break;
+  }
+  if (packer_kind(c.contents, c.numeric_type, c.num_values) != kPackPlain) {
+    const float scale = color_scale(c.numeric_type);
+    if (scale != 0.0f) {
+      const float recip = 1.0f / scale;
+      for (int k = 0; k < n; ++k) v[k] = v[k] * recip;
+    }
+    if (n == 3) v[3] = 1.0f;
+  }
 }
 
 static int check_ranges(const int32_t *ranges, int count, int num_rows, const char *what) {
@@ -473,19 +533,18 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
     const p3cs_column_desc &c = d->skin_columns[i];
     if ((rc = check_column(d, c, "skin column")) != P3CS_OK) return bail(rc);
     if (out_of_array[c.array] < 0) return bail(p3cs_fail(P3CS_ERR_INVALID, "skin column %d lives in a non-output array", i));
-    if ((c.numeric_type != P3CS_NT_FLOAT32 && c.numeric_type != P3CS_NT_FLOAT64) || (c.num_values != 3 && c.num_values != 4))
-      return bail(p3cs_fail(P3CS_ERR_UNSUPPORTED, "skin column %d: only float32 / float64 x 3 / x 4 columns are supported (got type %d x %d)", i, c.numeric_type, c.num_values));
-    if (c.start % 4 != 0) return bail(p3cs_fail(P3CS_ERR_UNSUPPORTED, "skin column %d: start %d not 4-byte aligned", i, c.start));
     int skin = c.contents == P3CS_C_POINT ? 1 : c.contents == P3CS_C_VECTOR ? 2 : c.contents == P3CS_C_NORMAL ? 3 : 0;
     if (skin == 0) return bail(p3cs_fail(P3CS_ERR_INVALID, "skin column %d: contents %d is not point/vector/normal", i, c.contents));
+    if ((rc = check_dynamic_column(c, "skin column", i)) != P3CS_OK) return bail(rc);
     if (m.num_dyn >= kMaxDynColumns) return bail(p3cs_fail(P3CS_ERR_UNSUPPORTED, "more than %d animated columns", kMaxDynColumns));
     DynColumn &dc = m.dyn[m.num_dyn++];
-    dc.output = (int16_t)out_of_array[c.array];
+    dc.output = (int8_t)out_of_array[c.array];
     dc.start = (int16_t)c.start;
     dc.num_values = (int8_t)c.num_values;
     dc.skin = (int8_t)skin;
     dc.homogeneous = 0;
     dc.f64 = c.numeric_type == P3CS_NT_FLOAT64 ? 1 : 0;
+    dc.typed = dynamic_column_code(c);
     if (c.num_values == 4) m.full_records = 1;
   }
 
@@ -550,7 +609,7 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
       bool ok = m.full_records && m.num_outputs == 1 && m.stride[0] % 16 == 0 &&
                 ((m.num_dyn == 2 && c[0].skin == 1 && c[1].skin == 3) ||
                  (m.num_dyn == 4 && c[0].skin == 1 && c[1].skin == 3 && c[2].skin == 2 && c[3].skin == 2));
-      for (int i = 0; ok && i < m.num_dyn; ++i) ok = c[i].num_values == 4 && !c[i].f64 && c[i].start % 16 == 0;
+      for (int i = 0; ok && i < m.num_dyn; ++i) ok = c[i].num_values == 4 && !c[i].f64 && !c[i].typed && c[i].start % 16 == 0;
       for (int mi = 0; ok && mi < d->num_morphs; ++mi) {  // morphs only on those columns (no morph-only column)
         const p3cs_column_desc &b = d->morphs[mi].base;
         ok = b.array >= 0 && b.array < d->num_arrays && out_of_array[b.array] == 0 && b.num_values == 4 &&
@@ -689,19 +748,20 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
       if ((rc = check_column(d, mo.delta, "morph delta column")) != P3CS_OK) return bail(rc);
       if ((rc = check_ranges(mo.row_ranges, mo.num_row_ranges, N, "slider rows")) != P3CS_OK) return bail(rc);
       if (out_of_array[mo.base.array] < 0) return bail(p3cs_fail(P3CS_ERR_INVALID, "morph %d: base column in a non-output array", mi));
-      auto is_float = [](int nt) { return nt == P3CS_NT_FLOAT32 || nt == P3CS_NT_FLOAT64; };
-      if (!is_float(mo.base.numeric_type) || !is_float(mo.delta.numeric_type) || mo.base.num_values > 4 ||
-          mo.base.start % 4 != 0 || mo.delta.start % 4 != 0)
-        return bail(p3cs_fail(P3CS_ERR_UNSUPPORTED, "morph %d: only 4-byte aligned float32 / float64 base and delta columns are supported", mi));
+      if ((rc = check_dynamic_column(mo.base, "morph base column of morph", mi)) != P3CS_OK) return bail(rc);
+      if (!column_supported(mo.delta.contents, mo.delta.numeric_type, mo.delta.num_values))
+        return bail(p3cs_fail(P3CS_ERR_UNSUPPORTED, "morph %d: delta column of numeric type %d x %d values, contents %d", mi,
+                              mo.delta.numeric_type, mo.delta.num_values, mo.delta.contents));
       int c = find_dyn(out_of_array[mo.base.array], mo.base.start);
       if (c < 0) {
         if (m.num_dyn >= kMaxDynColumns) return bail(p3cs_fail(P3CS_ERR_UNSUPPORTED, "more than %d animated columns", kMaxDynColumns));
         c = m.num_dyn++;
-        m.dyn[c].output = (int16_t)out_of_array[mo.base.array];
+        m.dyn[c].output = (int8_t)out_of_array[mo.base.array];
         m.dyn[c].start = (int16_t)mo.base.start;
         m.dyn[c].num_values = (int8_t)mo.base.num_values;
         m.dyn[c].skin = 0;
         m.dyn[c].f64 = mo.base.numeric_type == P3CS_NT_FLOAT64 ? 1 : 0;
+        m.dyn[c].typed = dynamic_column_code(mo.base);
       }
       m.dyn[c].homogeneous = (mo.base.num_values == 4 && (mo.base.contents == P3CS_C_POINT || mo.base.contents == P3CS_C_TEXCOORD)) ? 1 : 0;
       morph_dyn[mi] = c;
@@ -717,17 +777,13 @@ extern "C" int p3cs_mesh_create(p3cs_context ctx, const p3cs_mesh_desc *d, p3cs_
       const p3cs_morph_desc &mo = d->morphs[mi];
       const uint8_t *dbase = static_cast<const uint8_t *>(d->arrays[mo.delta.array].data) + mo.delta.start;
       const int dstride = d->arrays[mo.delta.array].stride;
-      const int dn = std::min(mo.delta.num_values, mo.base.num_values == 4 && !m.dyn[morph_dyn[mi]].homogeneous ? 4 : 3);
+      // the delta is read with get_data4 when the base holds four values without a homogeneous coordinate, else get_data3
+      const bool want4 = mo.base.num_values == 4 && !m.dyn[morph_dyn[mi]].homogeneous;
       for (int i = 0; i < mo.num_row_ranges; ++i)
         for (int r = mo.row_ranges[2 * i]; r < mo.row_ranges[2 * i + 1]; ++r) {
-          float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // Packer::get_data3f/4f pad with 0 (geomVertexColumn.cxx:718-737)
-          if (mo.delta.numeric_type == P3CS_NT_FLOAT64) {  // read as float, like GeomVertexReader::get_data3/4
-            double dv[4];
-            memcpy(dv, dbase + (size_t)r * dstride, (size_t)dn * 8);
-            for (int k = 0; k < dn; ++k) v[k] = (float)dv[k];
-          } else {
-            memcpy(v, dbase + (size_t)r * dstride, (size_t)dn * 4);
-          }
+          float v[4];  // Packer::get_data3f/4f pad with 0 (geomVertexColumn.cxx:718-737)
+          host_get4(mo.delta, dbase + (size_t)r * dstride, v);
+          if (!want4) v[3] = 0.0f;
           const int e = cursor[r]++;
           keys[e] = ((uint32_t)morph_dyn[mi] << 16) | (uint32_t)mo.slider;
           // a delta whose 4th component is never read carries its key there (one load per entry

@@ -39,7 +39,7 @@ int strip_pick_mode(const MeshDev &mesh) {
   if (mesh.full_records) return kGenericFull;
   if (mesh.num_outputs != 1 || mesh.index_bytes == 0) return kGenericCompact;
   for (int c = 0; c < mesh.num_dyn; ++c)
-    if (mesh.dyn[c].num_values != 3 || mesh.dyn[c].f64) return kGenericCompact;
+    if (mesh.dyn[c].num_values != 3 || mesh.dyn[c].f64 || mesh.dyn[c].typed) return kGenericCompact;
   const DynColumn *d = mesh.dyn;
   if (mesh.num_dyn == 1 && d[0].skin == 1) return kFastP;
   const int stride = mesh.stride[0];

@@ -25,14 +25,13 @@ REL_TOL = 1e-5  # north_star: float32 positions/normals agree within 1e-5 relati
 
 def dynamic_float_mask(mesh, numeric_type=None):
     """Byte mask per output array of the float columns the path may modify (all of them, or those of one numeric type)."""
-    from panda3d_b200.flat import NUMERIC_BYTES
     masks = []
     for a in mesh.output_arrays:
         m = np.zeros(mesh.strides[a], bool)
         cols = list(mesh.skin_columns) + [mo.base for mo in mesh.morphs]
         for c in cols:
             if c.array == a and (numeric_type is None or c.numeric_type == numeric_type):
-                m[c.start:c.start + NUMERIC_BYTES[c.numeric_type] * c.num_values] = True
+                m[c.start:c.start + c.num_bytes] = True
         masks.append(m)
     return masks
 
@@ -42,7 +41,7 @@ def compare_outputs(mesh, got, expect, what=""):
     class"): a component's error is taken relative to max(|component|, largest |component| of the SAME column in
     that row) -- a normal is never measured against the position's magnitude.  Returns (max_abs_error,
     number_of_differing_bytes)."""
-    from panda3d_b200.flat import NT_float64, NUMERIC_BYTES
+    from panda3d_b200.flat import NT_float32, NT_float64
     max_abs, nbytes = 0.0, 0
     all_masks = dynamic_float_mask(mesh)
     columns = []
@@ -59,8 +58,12 @@ def compare_outputs(mesh, got, expect, what=""):
         for _, c in columns:
             if c.array != mesh.output_arrays[o]:
                 continue
+            width = c.num_bytes
+            if c.numeric_type not in (NT_float32, NT_float64):   # integer and packed columns: index / byte work, bit-exact
+                assert np.array_equal(g[:, c.start:c.start + width], e[:, c.start:c.start + width]), \
+                    f"{what}: output {o} integer/packed column @{c.start} (type {c.numeric_type}) differs"
+                continue
             dt = np.float64 if c.numeric_type == NT_float64 else np.float32
-            width = NUMERIC_BYTES[c.numeric_type] * c.num_values
             gf = np.ascontiguousarray(g[:, c.start:c.start + width]).view(dt).astype(np.float64)
             ef = np.ascontiguousarray(e[:, c.start:c.start + width]).view(dt).astype(np.float64)
             if not gf.size:
@@ -265,10 +268,18 @@ def test_unsupported_and_invalid_inputs_fail_loudly(gpu_ctx):
     sm = synth.make_mesh(100, 4, 8, seed=1)
     mesh = sm.flat
     bad = F.FlatMesh(**{**mesh.__dict__})
-    bad.skin_columns = [F.Column(0, 0, 3, F.NT_int16, F.C_point)]
+    # combinations the reference's own packers refuse (nassert): a packed colour word of three values, a signed colour
+    for column in (F.Column(0, 0, 3, F.NT_packed_dcba, F.C_point), F.Column(0, 0, 4, F.NT_packed_ufloat, F.C_vector),
+                   F.Column(0, 0, 3, F.NT_stdfloat, F.C_point), F.Column(0, 2, 3, F.NT_float32, F.C_point)):
+        bad.skin_columns = [column]
+        with pytest.raises(_capi.P3csError) as e:
+            _capi.Mesh(gpu_ctx, bad)
+        assert e.value.code == _capi.P3CS_ERR_UNSUPPORTED
+    sm_color = synth.make_typed_mesh(64, 4, 8, seed=2, num_sliders=1, columns=[("vertex", 3, F.NT_float32, F.C_point), ("color", 4, F.NT_int8, F.C_color)],
+                                     morphs=[("color", 4, F.NT_float32)])
     with pytest.raises(_capi.P3csError) as e:
-        _capi.Mesh(gpu_ctx, bad)
-    assert e.value.code in (_capi.P3CS_ERR_UNSUPPORTED, _capi.P3CS_ERR_INVALID)
+        _capi.Mesh(gpu_ctx, sm_color.flat)
+    assert e.value.code == _capi.P3CS_ERR_UNSUPPORTED
     bad2 = F.FlatMesh(**{**mesh.__dict__})
     bad2.blend_offsets = mesh.blend_offsets[:3].copy()  # fewer blends than the indices select
     bad2.blend_transform = mesh.blend_transform[:int(bad2.blend_offsets[-1])]
@@ -1275,5 +1286,104 @@ def test_per_instance_output_pointers(gpu_ctx, layout):
     finally:
         for v in views:
             gpu_ctx.host_unregister(v)
+        grp.close()
+        dmesh.close()
+
+
+# ---- columns of every numeric type: GeomVertexRewriter branches + the GeomVertexColumn packers
+
+_TYPED_NT = [F.NT_uint8, F.NT_uint16, F.NT_uint32, F.NT_int8, F.NT_int16, F.NT_int32, F.NT_float32, F.NT_float64]
+
+
+def _random_typed_mesh(seed, num_rows=4000):
+    """A random format: 3..7 skinned columns of random numeric type / width / alignment, colour and texcoord columns
+    with morphs, integer deltas."""
+    rng = np.random.default_rng(seed)
+    cols, morphs = [], []
+
+    def pick(contents, name):
+        r = int(rng.integers(0, 11))
+        if r == 8:
+            return (name, 4, F.NT_packed_dcba, contents, 1)
+        if r == 9:
+            return (name, 4, F.NT_packed_dabc, contents, int(rng.choice([1, 4])))
+        if r == 10:
+            return (name, 3, F.NT_packed_ufloat, contents, 4)
+        nt = _TYPED_NT[r]
+        nv = int(rng.integers(1, 5))
+        if contents == F.C_normal and nv < 3:
+            nv = 3
+        cb = F.NUMERIC_BYTES[nt]
+        align = max(cb, 4) if nt in (F.NT_float32, F.NT_float64) else int(rng.choice([1, cb, 4]))
+        return (name, nv, nt, contents, align)
+
+    cols.append(pick(F.C_point, "vertex"))
+    cols.append(pick(F.C_normal, "normal"))
+    for i in range(int(rng.integers(1, 5))):
+        cols.append(pick(F.C_vector if rng.random() < 0.6 else F.C_point, f"extra{i}"))
+    color_nt = [(4, F.NT_uint8), (4, F.NT_packed_dabc), (4, F.NT_packed_dcba), (4, F.NT_uint16), (3, F.NT_uint8), (3, F.NT_uint32), (4, F.NT_float32)]
+    nv, nt = color_nt[int(rng.integers(0, len(color_nt)))]
+    cols.append(("color", nv, nt, F.C_color, 4))
+    cols.append(("texcoord", int(rng.integers(2, 5)), F.NT_float32 if rng.random() < 0.5 else F.NT_int16, F.C_texcoord, 4))
+    delta_nt = [F.NT_float32, F.NT_int8, F.NT_int16, F.NT_float64]
+    for name, nv, nt, contents, _ in list(cols):
+        if nt == F.NT_packed_ufloat and rng.random() < 0.5:
+            continue
+        if rng.random() < 0.6:
+            dn = F.NT_float32 if contents == F.C_color else delta_nt[int(rng.integers(0, 4))]
+            morphs.append((name, int(rng.integers(1, 5)) if contents != F.C_color else nv, dn))
+    rows = None if rng.random() < 0.5 else [(5, num_rows // 3), (num_rows // 2, num_rows - 7)]
+    return synth.make_typed_mesh(num_rows, 24, 300, seed=1000 + seed, columns=cols, morphs=morphs, num_sliders=3 if morphs else 0,
+                                 slider_band=0.5, rows=rows)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_columns_of_every_numeric_type_vs_oracle(gpu_ctx, monkeypatch, seed):
+    """Random formats of integer / packed / short columns, a crowd of three instances, both kernels that take them (the
+    strip kernel's generic mode and the two-kernel path): every output byte equals the oracle's (palettes without the
+    uniform-scale libm branch on even seeds, non-uniformly scaled on odd ones)."""
+    from oracle import oracle
+    sm = _random_typed_mesh(seed)
+    mesh = sm.flat
+    scale = 1.0 if seed % 2 == 0 else (1.3, 0.8, 1.1)
+    pal = synth.make_palettes(24, 3, 2000 + seed, scale=scale)
+    sl = synth.make_sliders(mesh.num_sliders, 3, 3000 + seed) if mesh.num_sliders else None
+    om = oracle.OracleMesh(mesh)
+    expect = [om.animate(pal[i], None if sl is None else sl[i])[0] for i in range(3)]
+    for path in ("strip", "wide"):
+        monkeypatch.setenv("P3CS_PATH", path)
+        dmesh = _capi.Mesh(gpu_ctx, mesh)
+        grp = _capi.Group(dmesh, 3)
+        try:
+            grp.set_palettes(pal)
+            if sl is not None:
+                grp.set_sliders(sl)
+            grp.animate()
+            for i in range(3):
+                got = grp.read_output(0, i, 1)
+                assert np.array_equal(np.asarray(got).reshape(mesh.num_rows, -1), expect[i][0]), \
+                    f"seed {seed} path {path} instance {i}: {(np.asarray(got).reshape(mesh.num_rows, -1) != expect[i][0]).sum()} bytes differ"
+        finally:
+            grp.close()
+            dmesh.close()
+
+
+def test_integer_conversions_at_the_edges(gpu_ctx):
+    """Values that leave the column type's range wrap exactly as the reference's x86-64 casts do (cvttss2si: low bits
+    kept for unsigned, 0x80000000 for signed overflow): large palettes push int8 / uint8 / int16 columns far out."""
+    from oracle import oracle
+    sm = synth.make_typed_mesh(2000, 8, 40, seed=77, columns=[
+        ("vertex", 3, F.NT_int8, F.C_point, 1), ("normal", 3, F.NT_int16, F.C_normal, 2), ("t", 3, F.NT_uint8, F.C_vector, 1),
+        ("b", 4, F.NT_uint16, F.C_vector, 2), ("p4", 4, F.NT_int16, F.C_point, 2), ("w", 3, F.NT_int32, F.C_point), ("u", 3, F.NT_uint32, F.C_vector)])
+    mesh = sm.flat
+    pal = synth.make_palettes(8, 1, 78, scale=(37.0, -11.5, 3.25))[0]
+    pal[:, 12:15] *= 500.0   # translations in the hundreds
+    expect = oracle.OracleMesh(mesh).animate(pal, None)[0]
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, 1)
+    try:
+        got = grp.animate_vertices(pal, None)
+        assert np.array_equal(np.asarray(got[0]).reshape(mesh.num_rows, -1), expect[0])
+    finally:
         grp.close()
         dmesh.close()
