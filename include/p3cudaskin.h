@@ -101,14 +101,16 @@ typedef struct p3cs_array_desc {
 typedef struct p3cs_column_desc {
   int32_t array;         /* index into p3cs_mesh_desc::arrays                     */
   int32_t start;         /* GeomVertexColumn::get_start(), bytes into the row     */
-  int32_t num_values;    /* get_num_values()                                      */
+  int32_t num_values;    /* get_num_values(): 4 for a packed_dcba / packed_dabc word, 3 for packed_ufloat */
   int32_t numeric_type;  /* get_numeric_type(), P3CS_NT_*                          */
   int32_t contents;      /* get_contents(), P3CS_C_*                               */
 } p3cs_column_desc;
 
 /* One application of a morph: a (C_morph_delta column, slider) pair with the
  * slider's affected rows, in the iteration order of the reference loop
- * geomVertexData.cxx:1467-1543 (morph column outer, slider index inner). */
+ * geomVertexData.cxx:1467-1543 (morph column outer, slider index inner).  Base and
+ * delta may be of any numeric type and contents (colour, texcoord, point, ...):
+ * they are read and written like GeomVertexRewriter / GeomVertexReader do. */
 typedef struct p3cs_morph_desc {
   int32_t slider;               /* index into the SliderTable (sliderTable.I:52)  */
   p3cs_column_desc base;        /* column that is modified (array must be output) */
@@ -128,7 +130,9 @@ typedef struct p3cs_mesh_desc {
 
   /* Columns transformed by the blend matrices: GeomVertexFormat::get_point(i)
    * then get_vector(i) of the post-animated format (geomVertexData.cxx:1582,
-   * 1622).  contents is C_POINT, C_VECTOR or C_NORMAL; float32 or float64, x 3 or x 4 (float64 takes the GeomVertexRewriter branches, :1782-1799, 1862-1879). */
+   * 1622).  contents is C_POINT, C_VECTOR or C_NORMAL; any numeric type, 1..4 values: float32 x 3 / x 4 are the
+   * table_xform_* fast paths, everything else (float64, integers, packed words, narrow columns) takes the
+   * GeomVertexRewriter branches (:1782-1799, 1862-1879) with the GeomVertexColumn packers' conversions. */
   int32_t num_skin_columns;
   const p3cs_column_desc *skin_columns;
 

@@ -22,4 +22,6 @@ g++ -std=gnu++17 -O2 -fno-rtti -fno-exceptions $INC "$HERE/cudaSkinBackend.cxx" 
     -L"$ROOT/oracle/_ref/lib_hook" -lpandaegg -lpanda -lpandaexpress -lp3dtool -lp3prc -lpthread -ldl \
     -Wl,-rpath,'$ORIGIN/../../oracle/_ref/lib_hook' -o "$OUT/panda_cuda_check"
 cp "$SRC/models/panda-model.egg" "$SRC/models/panda-walk4.egg" "$SRC/models/ripple.egg" "$OUT/models/"
+# ripple.egg with <DRGBA> / <Duv> morphs added: colour and texcoord columns as morph bases (integration/make_morph_egg.py)
+python "$HERE/make_morph_egg.py" "$SRC/models/ripple.egg" "$OUT/models/ripple_rgba_uv.egg"
 echo "built $OUT/panda_cuda_check"

@@ -27,14 +27,16 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 typedef std::chrono::steady_clock Clock;
 static double micros(Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); }
 
 struct Compare {
-  long long differing = 0, total = 0;
+  long long differing = 0, total = 0, integer_differing = 0;
   double max_abs = 0.0, max_rel = 0.0;
   bool shape_ok = true;
   void add(const GeomVertexData *cpu, const GeomVertexData *gpu) {
@@ -48,14 +50,27 @@ struct Compare {
       size_t nbytes = (size_t)cpu->get_num_rows() * cpu->get_format()->get_array(o)->get_stride();
       total += (long long)nbytes;
       for (size_t i = 0; i < nbytes; ++i) differing += pc[i] != pg[i];
-      for (size_t i = 0; i + 4 <= nbytes; i += 4) {   // all columns of the test models are float32
-        float fc, fg;
-        memcpy(&fc, pc + i, 4);
-        memcpy(&fg, pg + i, 4);
-        double err = std::fabs((double)fc - (double)fg);
-        if (err > max_abs) max_abs = err;
-        double rel = err / std::fmax(std::fabs((double)fc), 1e-3);
-        if (rel > max_rel) max_rel = rel;
+      // float32 columns: numeric error per component; every other column (packed colours, integers): bytes, counted apart
+      const GeomVertexArrayFormat *af = cpu->get_format()->get_array(o);
+      const size_t stride = af->get_stride();
+      for (int ci = 0; ci < af->get_num_columns(); ++ci) {
+        const GeomVertexColumn *col = af->get_column(ci);
+        for (int row = 0; row < cpu->get_num_rows(); ++row) {
+          const size_t at = (size_t)row * stride + col->get_start();
+          if (col->get_numeric_type() != GeomEnums::NT_float32) {
+            for (int b = 0; b < col->get_total_bytes(); ++b) integer_differing += pc[at + b] != pg[at + b];
+            continue;
+          }
+          for (int k = 0; k < col->get_num_components(); ++k) {
+            float fc, fg;
+            memcpy(&fc, pc + at + 4 * k, 4);
+            memcpy(&fg, pg + at + 4 * k, 4);
+            double err = std::fabs((double)fc - (double)fg);
+            if (err > max_abs) max_abs = err;
+            double rel = err / std::fmax(std::fabs((double)fc), 1e-3);
+            if (rel > max_rel) max_rel = rel;
+          }
+        }
       }
     }
   }
@@ -87,6 +102,7 @@ int main(int argc, char **argv) {
   }
   load_prc_file_data("check", std::string("plugin-path ") + argv[1] + "\nvertex-animation-backend cuda\n"
                      "cuda-skinning-library p3cudaskin\nhardware-animated-vertices #f\n");
+  if (const char *extra = getenv("P3CS_CHECK_PRC")) load_prc_file_data("check-extra", extra);   // e.g. vertex-colors-prefer-packed 1
   CudaSkinBackend *backend = CudaSkinBackend::get_global_ptr();
   if (backend == nullptr) {
     printf("{\"ok\": false, \"error\": \"backend unavailable (see the gobj error log)\"}\n");
@@ -191,10 +207,19 @@ int main(int argc, char **argv) {
   const size_t entries_before = backend->get_num_entries();
   const_cast<GeomVertexData *>(vdata.p())->clear_animated_vertices();
   const size_t entries_after = backend->get_num_entries();
-  printf("{\"ok\": true, \"cpu_us_steady\": %.1f, \"cuda_us_steady_e2e\": %.1f, \"frames\": %d, \"rows\": %d, \"bytes_compared\": %lld, \"differing_bytes\": %lld, "
+  std::string columns;   // "vertex:3x5 normal:3x5 color:4x0 ...": name : values x GeomEnums::NumericType, animated arrays only
+  for (size_t o = 0; o < first_gpu->get_num_arrays(); ++o) {
+    const GeomVertexArrayFormat *af = first_gpu->get_format()->get_array(o);
+    for (int ci = 0; ci < af->get_num_columns(); ++ci) {
+      const GeomVertexColumn *col = af->get_column(ci);
+      columns += (columns.empty() ? "" : " ") + col->get_name()->get_name() + ":" + std::to_string(col->get_num_values()) + "x" +
+                 std::to_string((int)col->get_numeric_type());
+    }
+  }
+  printf("{\"ok\": true, \"columns\": \"%s\", \"integer_column_differing_bytes\": %lld, \"morphs\": %d, \"cpu_us_steady\": %.1f, \"cuda_us_steady_e2e\": %.1f, \"frames\": %d, \"rows\": %d, \"bytes_compared\": %lld, \"differing_bytes\": %lld, "
          "\"max_abs_err\": %.3e, \"max_rel_err\": %.3e, \"same_result_object\": %s, \"stock_callers_agree\": %s, \"animate_vertices_request\": %s, "
          "\"entries_before_clear\": %zu, \"entries_after_clear\": %zu, \"cpu_us_per_frame\": %.1f, \"cuda_us_per_frame_e2e\": %.1f}\n",
-         cpu_steady / reps, gpu_steady / reps, frames, vdata->get_num_rows(), cmp.total, cmp.differing, cmp.max_abs, cmp.max_rel,
+         columns.c_str(), cmp.integer_differing, (int)vdata->get_format()->get_num_morphs(), cpu_steady / reps, gpu_steady / reps, frames, vdata->get_num_rows(), cmp.total, cmp.differing, cmp.max_abs, cmp.max_rel,
          same_object ? "true" : "false", stock_callers_agree ? "true" : "false", request_ok ? "true" : "false", entries_before, entries_after,
          cpu_us / (frames - 1), gpu_us / (frames - 1));
   return 0;

@@ -760,6 +760,7 @@ static int cmd_hw(const char *in_path, const char *out_path) {
 }
 
 int main(int argc, char **argv) {
+  if (const char *prc = getenv("P3CS_PRC")) load_prc_file_data("harness-extra", prc);   // e.g. "vertex-colors-prefer-packed 1"
   if (argc >= 4 && strcmp(argv[1], "hw") == 0) return cmd_hw(argv[2], argv[3]);
   if (argc >= 4 && strcmp(argv[1], "run") == 0) return cmd_run(argv[2], argv[3]);
   if (argc >= 6 && strcmp(argv[1], "egg") == 0) return cmd_egg(argc, argv);

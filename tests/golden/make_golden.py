@@ -135,6 +135,16 @@ def main():
     subprocess.run([HARNESS, "egg", ripple, ripple, out, "0", "3", "7", "20", "44"], check=True, timeout=120,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     print("wrote", out, os.path.getsize(out))
+    # ripple.egg with <DRGBA> / <Duv> morphs added (integration/make_morph_egg.py): the egg loader's colour column
+    # (4 x uint8, or packed_dabc with vertex-colors-prefer-packed) and texcoord column as morph bases
+    with tempfile.TemporaryDirectory() as tmp:
+        derived = os.path.join(tmp, "ripple_rgba_uv.egg")
+        subprocess.run([sys.executable, os.path.join(ROOT, "integration", "make_morph_egg.py"), ripple, derived], check=True)
+        for suffix, env in (("", {}), ("_packed", {"P3CS_PRC": "vertex-colors-prefer-packed 1"})):
+            out = os.path.join(HERE, f"ripple_rgba_uv{suffix}.p3cs")
+            subprocess.run([HARNESS, "egg", derived, derived, out, "0", "3", "7", "20", "44"], check=True, timeout=120,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env={**os.environ, **env})
+            print("wrote", out, os.path.getsize(out))
     # the same Actor with PartBundle::set_frame_blend_flag(true), posed between frames (joint hierarchy fixture, f1)
     os.makedirs(os.path.join(HERE, "skeleton"), exist_ok=True)
     for suffix, env in (("", {}), ("_linear", {"P3CS_BLEND_TYPE": "linear"}),   # anim-blend-type default, then BT_linear

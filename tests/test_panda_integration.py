@@ -58,6 +58,32 @@ def test_real_morph_character_through_the_shim():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("packed", [False, True], ids=["rgba_uint8", "argb_packed"])
+def test_loader_made_colour_and_texcoord_morphs_through_the_shim(packed):
+    """ripple.egg with <DRGBA> / <Duv> morphs added (integration/make_morph_egg.py): the egg loader makes the colour
+    column (4 x uint8; packed_dabc with vertex-colors-prefer-packed) and the texcoord column morph bases.  Inside real
+    Panda3D the hook's result equals the CPU loops' byte for byte -- the colour packers truncate after every morph."""
+    if not os.path.exists(CHECK):
+        pytest.skip("integration/_build/panda_cuda_check not built (needs the reference tree: integration/build.sh)")
+    egg = os.path.join(ROOT, "integration", "_build", "models", "ripple_rgba_uv.egg")
+    if not os.path.exists(egg):
+        pytest.skip("integration/_build/models/ripple_rgba_uv.egg missing (re-run integration/build.sh)")
+    frames = [str(f) for f in (0, 3, 7, 20, 31, 44)]
+    env = {**os.environ, "P3CS_CHECK_PRC": "vertex-colors-prefer-packed 1\n"} if packed else dict(os.environ)
+    res = subprocess.run([CHECK, os.path.join(ROOT, "panda3d_b200"), egg, egg] + frames, capture_output=True, text=True, timeout=300, env=env)
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert line, res.stdout + res.stderr
+    out = json.loads(line[-1])
+    print(out)
+    assert out["ok"], out
+    assert ("color:4x4" if packed else "color:4x0") in out["columns"] and "texcoord:2x5" in out["columns"], out["columns"]
+    assert out["morphs"] == 28                  # 7 sliders x (vertex, normal, color, texcoord)
+    assert out["frames"] == len(frames) + 1 and out["rows"] == 641
+    assert out["same_result_object"] and out["stock_callers_agree"]
+    assert out["integer_column_differing_bytes"] == 0 and out["differing_bytes"] == 0
+
+
+@pytest.mark.gpu
 def test_crowd_of_panda_actors_is_one_launch_per_frame():
     """1000 copies of the panda Actor (NodePath::copy_to: own joints, own vertex data and TransformBlendTable, shared
     arrays), each on its own frame: CudaSkinBackend::animate_frame animates all of them with ONE kernel launch into
