@@ -18,6 +18,8 @@
 #include "lightMutexHolder.h"
 #include "load_dso.h"
 #include "pandaNode.h"
+#include "pStatCollector.h"
+#include "pStatTimer.h"
 #include "sliderTable.h"
 #include "sparseArray.h"
 #include "transformBlendTable.h"
@@ -46,6 +48,15 @@ static ConfigVariableBool cuda_skinning_register_outputs
  PRC_DESC("Page-lock the animated GeomVertexArrayData buffers (cudaHostRegister) so the kernel stores "
           "the animated rows straight into them instead of copying device->host afterwards.  The "
           "frame-batch path (one launch per shared mesh) needs it."));
+
+// PStats: the hook runs inside update_animated_vertices' own PStatTimer ("*:Animation:<character>",
+// geomVertexData.cxx:1435), so a character's GPU time shows up where its CPU time did.  The phases of the backend sit
+// beside the reference's "Skinning" / "Morphs" / "Calc blends" children (geomVertexData.cxx:37, 46-49) under the
+// same root; the frame batch, which runs outside any vertex data's timer, gets its own.
+static PStatCollector _cuda_upload_pcollector("*:Animation:CUDA:Upload mesh");
+static PStatCollector _cuda_gather_pcollector("*:Animation:CUDA:Gather joints");
+static PStatCollector _cuda_animate_pcollector("*:Animation:CUDA:Animate");
+static PStatCollector _cuda_frame_pcollector("*:Animation:CUDA:Frame batch");
 
 CudaSkinBackend::CudaSkinBackend(void *dso, const p3cs_api *api, p3cs_context ctx) :
   _dso(dso), _api(api), _ctx(ctx), _map_lock("CudaSkinBackend map"), _gpu_lock("CudaSkinBackend gpu") {
@@ -540,6 +551,7 @@ update(const GeomVertexData *source, GeomVertexData *animated, Thread *current_t
   CPT(SliderTable) sliders = source->get_slider_table();
   if (entry->_mesh == nullptr || entry->_format != source->get_format() || entry->_num_rows != source->get_num_rows() ||
       entry->_static_modified != source->get_modified(current_thread) || entry->_table != table || entry->_sliders != sliders) {
+    PStatTimer upload_timer(_cuda_upload_pcollector, current_thread);
     if (!attach(source, *entry, current_thread)) {
       animated->copy_from(source, true);   // logged; deliberately NOT computed on the CPU
       return true;
@@ -554,6 +566,7 @@ update(const GeomVertexData *source, GeomVertexData *animated, Thread *current_t
   // this thread's own copy of the joint matrices / slider values: other threads may be animating (or attaching)
   // other instances of the same mesh right now
   pvector<float> palette(entry->_palette.size() * 16), slider_values((size_t)mesh._num_sliders);
+  _cuda_gather_pcollector.start(current_thread);
   for (size_t j = 0; j < entry->_palette.size(); ++j) {
     LMatrix4 mat;
     entry->_palette[j]->get_matrix(mat);
@@ -563,6 +576,7 @@ update(const GeomVertexData *source, GeomVertexData *animated, Thread *current_t
   for (int s = 0; s < mesh._num_sliders; ++s) {
     slider_values[s] = (float)entry->_sliders->get_slider(s)->get_slider();
   }
+  _cuda_gather_pcollector.stop(current_thread);
   pvector<void *> out_pointers;
   pvector<PT(GeomVertexArrayDataHandle)> out_handles;
   for (int o = 0; o < mesh._num_outputs; ++o) {
@@ -572,6 +586,7 @@ update(const GeomVertexData *source, GeomVertexData *animated, Thread *current_t
   }
   int rc;
   {
+    PStatTimer animate_timer(_cuda_animate_pcollector, current_thread);
     LightMutexHolder gpu(_gpu_lock);   // the GPU section only: flattening above ran unlocked
     rc = _api->animate_vertices(mesh._group, entry->_slot, palette.data(), slider_values.data(), out_pointers.data());
   }
@@ -587,6 +602,7 @@ update(const GeomVertexData *source, GeomVertexData *animated, Thread *current_t
 
 int CudaSkinBackend::
 animate_frame(const GeomVertexData *const *sources, size_t count, Thread *current_thread) {
+  PStatTimer frame_timer(_cuda_frame_pcollector, current_thread);
   pvector<SharedMesh *> touched;
   _last_frame_instances = 0;
   for (size_t i = 0; i < count; ++i) {
