@@ -678,6 +678,9 @@ def other_configs(torch, ctx, stream, _capi, synth, instances, peak_gbs):
     # 2.3x the bytes per vertex, where the kernel IS bound by HBM
     specs["c3_crowd_stride56_pos_normal_uv_tangent_binormal"] = [
         (synth.make_mesh(20_000, 128, 4096, seed=33, tbn=True, texcoord=True, index_order="runs").flat, instances)]
+    # ... and with a random blend per vertex (no runs at all: SURVEY 8d lists this order for C2): every row needs its own
+    # four-matrix blend, the kernel is bound by instruction issue, not by HBM
+    specs["c3_crowd_random_blend_index_per_vertex"] = [(synth.config_c3_mesh(index_order="random").flat, instances)]
     for name, spec in specs.items():
         meshes, groups, verts = [], [], 0
         for i, (fm, n) in enumerate(spec):
@@ -710,7 +713,64 @@ def other_configs(torch, ctx, stream, _capi, synth, instances, peak_gbs):
         for dm in meshes:
             dm.close()
     del flush
+    out["single_call_latency"] = single_call_latency(torch, ctx, _capi, synth)
     return out
+
+
+def single_call_latency(torch, ctx, _capi, synth):
+    """Wall-clock microseconds of ONE synchronous p3cs_animate_vertices call (host palette in; output left on the device
+    or written into registered host memory), beside the floor of this box: launch of an empty kernel + polling wait."""
+    import ctypes as C
+    from panda3d_b200.casefile import load_case
+    from panda3d_b200.flat import mesh_from_case
+
+    def best(fn, n=300, reps=5):
+        b = 1e9
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            for it in range(n):
+                fn(it)
+            b = min(b, (time.perf_counter() - t0) / n * 1e6)
+        return b
+
+    s = torch.cuda.Stream()
+    x = torch.zeros(1, device="cuda")
+
+    def empty(it):
+        x.add_(1)
+        while not s.query():
+            pass
+    with torch.cuda.stream(s):
+        floor = best(empty)
+    res = {"empty_kernel_launch_plus_poll_us": floor,
+           "note": "best of 5 x 300 calls, time.perf_counter around the C-ABI call; a call cannot be faster than the floor"}
+    L = _capi.lib()
+    cases = {"c1_panda_walk4": mesh_from_case(load_case(os.path.join(ROOT, "tests", "golden", "panda_walk4.p3cs"))),
+             "c2_100k": synth.config_c2("random").flat}
+    for name, flat in cases.items():
+        dm = _capi.Mesh(ctx, flat)
+        g = _capi.Group(dm, 1)
+        pal = np.ascontiguousarray(synth.make_palettes(flat.num_transforms, 8, 3), np.float32)
+        pp = [pal[i].ctypes.data for i in range(8)]
+        host = np.empty((flat.num_rows, dm.out_strides[0]), np.uint8)
+        ptrs = (C.c_void_p * 1)(host.ctypes.data)
+        fn, gh = L.p3cs_animate_vertices, g.handle
+        for it in range(20):
+            fn(gh, 0, pp[it & 7], None, None)
+        on_device = best(lambda it: fn(gh, 0, pp[it & 7], None, None))
+        ctx.host_register(host)
+        try:
+            for it in range(20):
+                fn(gh, 0, pp[it & 7], None, ptrs)
+            to_host = best(lambda it: fn(gh, 0, pp[it & 7], None, ptrs))
+        finally:
+            ctx.host_unregister(host)
+        out_bytes = flat.num_rows * dm.out_strides[0]
+        res[name] = {"rows": flat.num_rows, "us_per_call_output_on_device": on_device, "us_per_call_registered_host_output": to_host,
+                     "output_bytes": out_bytes}
+        g.close()
+        dm.close()
+    return res
 
 
 def main():

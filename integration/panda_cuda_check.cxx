@@ -14,6 +14,7 @@
 #include "animateVerticesRequest.h"
 #include "asyncTaskManager.h"
 #include "auto_bind.h"
+#include "bamFile.h"
 #include "character.h"
 #include "geomNode.h"
 #include "geomVertexArrayData.h"
@@ -95,6 +96,23 @@ static bool find_animated(const NodePath &np, CPT(Geom) &geom, CPT(GeomVertexDat
 
 static int run_crowd(CudaSkinBackend *backend, PandaNode *model, PandaNode *anim, int n, int frames);
 
+// P3CS_CHECK_BAM=<dir>: the loaded subgraph goes through the reference's own .bam writer and reader first
+// (TransformBlendTable::write_datagram / fillin, gobj/transformBlendTable.cxx:210-284; SliderTable, JointVertexTransform,
+// Character likewise), so what the backend flattens is what a shipped application loads from disk.
+static PT(PandaNode) through_bam(PandaNode *node, const std::string &path) {
+  {
+    BamFile out;
+    if (!out.open_write(Filename(path)) || !out.write_object(node)) return nullptr;
+    out.close();
+  }
+  BamFile in;
+  if (!in.open_read(Filename(path))) return nullptr;
+  PT(PandaNode) back = in.read_node();
+  if (back == nullptr || !in.resolve()) return nullptr;
+  in.close();
+  return back;
+}
+
 int main(int argc, char **argv) {
   if (argc < 5) {
     fprintf(stderr, "usage: panda_cuda_check <plugin dir> <model.egg> <anim.egg> <frame>... | --crowd N [frames]\n");
@@ -114,6 +132,14 @@ int main(int argc, char **argv) {
   if (model == nullptr || (!one_file && anim == nullptr)) {
     printf("{\"ok\": false, \"error\": \"egg load failed\"}\n");
     return 1;
+  }
+  if (const char *bam_dir = getenv("P3CS_CHECK_BAM")) {
+    model = through_bam(model, std::string(bam_dir) + "/p3cs_check_model.bam");
+    if (anim != nullptr) anim = through_bam(anim, std::string(bam_dir) + "/p3cs_check_anim.bam");
+    if (model == nullptr || (!one_file && anim == nullptr)) {
+      printf("{\"ok\": false, \"error\": \"bam round trip failed\"}\n");
+      return 1;
+    }
   }
   if (strcmp(argv[4], "--crowd") == 0) {
     return run_crowd(backend, model, anim, argc > 5 ? atoi(argv[5]) : 1000, argc > 6 ? atoi(argv[6]) : 20);

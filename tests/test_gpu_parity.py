@@ -785,6 +785,40 @@ def test_registered_host_outputs_are_written_directly(gpu_ctx):
 
 
 @pytest.mark.gpu
+def test_one_call_entry_point_keeps_the_group_up_to_date(gpu_ctx):
+    """p3cs_animate_vertices back to back on different instances of a group: same bytes as the crowd path
+    (set_palettes / set_sliders / animate), and the call's palette and sliders stay behind as the instance's device
+    copies, so a later p3cs_group_animate of the whole group sees, per instance, the inputs of the last call that named it."""
+    sm = synth.make_mesh(1_338, 26, 197, seed=191, texcoord=True, index_order="runs", num_sliders=5, slider_band=0.3)
+    mesh = sm.flat
+    pal = synth.make_palettes(mesh.num_transforms, 7, 192)
+    sl = synth.make_sliders(mesh.num_sliders, 7, 193)
+    dmesh = _capi.Mesh(gpu_ctx, mesh)
+    grp = _capi.Group(dmesh, 4)
+    ref = _capi.Group(dmesh, 1)
+    try:
+        for f in range(7):
+            inst = f % 4
+            got = grp.animate_vertices(pal[f], sl[f], instance=inst)
+            ref.set_palettes(pal[f].reshape(1, -1))
+            ref.set_sliders(sl[f].reshape(1, -1))
+            ref.animate()
+            assert np.array_equal(got[0], ref.read_output(0)[0]), f"call {f}"
+            assert np.array_equal(grp.read_palettes()[inst].ravel(), pal[f].ravel()), "device palette not refreshed"
+        grp.animate()   # every instance from its device copies: instance i holds the inputs of the last call that named it
+        out = grp.read_output(0)
+        for inst, f in ((0, 4), (1, 5), (2, 6), (3, 3)):
+            ref.set_palettes(pal[f].reshape(1, -1))
+            ref.set_sliders(sl[f].reshape(1, -1))
+            ref.animate()
+            assert np.array_equal(out[inst], ref.read_output(0)[0]), f"instance {inst}"
+    finally:
+        ref.close()
+        grp.close()
+        dmesh.close()
+
+
+@pytest.mark.gpu
 def test_edge_sizes(gpu_ctx):
     """Sizes at the edges of the launch geometry: an empty vertex data, a single instance of a mesh smaller than a
     warp, a palette too large for shared memory (automatic two-kernel path), more instances than one grid

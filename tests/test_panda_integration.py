@@ -37,6 +37,34 @@ def test_real_panda_actor_through_the_shim():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("which", ["panda", "ripple"])
+def test_characters_loaded_from_bam_through_the_shim(which, tmp_path):
+    """SURVEY 8 f3, the on-disk half: the character goes through the reference's own .bam writer and reader
+    (TransformBlendTable::write_datagram / fillin, gobj/transformBlendTable.cxx:210-284, and the SliderTable /
+    JointVertexTransform / Character equivalents) before the shim flattens it -- what a shipped application loads."""
+    if not os.path.exists(CHECK):
+        pytest.skip("integration/_build/panda_cuda_check not built (needs the reference tree: integration/build.sh)")
+    models = os.path.join(ROOT, "integration", "_build", "models")
+    if which == "panda":
+        files, rows = [os.path.join(models, "panda-model.egg"), os.path.join(models, "panda-walk4.egg")], 1338
+    else:
+        files, rows = [os.path.join(models, "ripple.egg")] * 2, 641
+    frames = [str(f) for f in (0, 7, 20, 33)]
+    env = {**os.environ, "P3CS_CHECK_BAM": str(tmp_path)}
+    res = subprocess.run([CHECK, os.path.join(ROOT, "panda3d_b200")] + files + frames, capture_output=True, text=True, timeout=300, env=env)
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert line, res.stdout + res.stderr
+    out = json.loads(line[-1])
+    print(out)
+    assert out["ok"], out
+    assert os.path.getsize(os.path.join(str(tmp_path), "p3cs_check_model.bam")) > 10000     # the round trip really happened
+    assert out["frames"] == len(frames) + 1 and out["rows"] == rows
+    assert out["same_result_object"] and out["stock_callers_agree"] and out["animate_vertices_request"]
+    assert out["max_rel_err"] <= 1e-5
+    assert out["differing_bytes"] <= 16
+
+
+@pytest.mark.gpu
 def test_real_morph_character_through_the_shim():
     """models/ripple.egg: 7 CharacterVertexSliders over <Dxyz> / <DNormal> morph columns -- the shim's SliderTable /
     morph flattening against loader-made formats, compared in-process with the reference's CPU result."""

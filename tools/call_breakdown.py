@@ -31,14 +31,19 @@ for name, flat in cases.items():
     # the one-call entry point: pageable destination vs registered (direct stores)
     import ctypes as C
     ptrs = (C.c_void_p * 1)(out.ctypes.data)
+    pp = [pal[i].ctypes.data for i in range(8)]   # resolved once: numpy's .ctypes costs a microsecond
+    fn, gh = L.p3cs_animate_vertices, g.handle
     for label in ("pageable", "registered"):
         if label == "registered":
             ctx.host_register(out)
         for it in range(20):
             L.p3cs_animate_vertices(g.handle, 0, pal[it % 8].ctypes.data, None, ptrs)
-        t0 = time.perf_counter()
-        for it in range(n):
-            L.p3cs_animate_vertices(g.handle, 0, pal[it % 8].ctypes.data, None, ptrs)
-        print(name, "p3cs_animate_vertices", label, "us/call", round((time.perf_counter() - t0) / n * 1e6, 2), flush=True)
+        best = 1e9
+        for rep in range(5):
+            t0 = time.perf_counter()
+            for it in range(n):
+                fn(gh, 0, pp[it & 7], None, ptrs)
+            best = min(best, (time.perf_counter() - t0) / n * 1e6)
+        print(name, "p3cs_animate_vertices", label, "us/call (best of 5 x %d)" % n, round(best, 2), flush=True)
     ctx.host_unregister(out)
     g.close(); dm.close()
