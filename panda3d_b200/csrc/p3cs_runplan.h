@@ -17,7 +17,13 @@
 //   * a slot lasts as long as its longest delay + item, so items are placed longest first, each into the lane that
 //     keeps its slot shortest; among equally good lanes the one whose palette indices collide least, modulo 8, with
 //     the items already in the same quarter-warp (the palette gather is a 128-bit load per lane, eight lanes per
-//     wavefront, 48-byte palette rows: two different joints collide when they agree modulo 8).
+//     wavefront, 48-byte palette rows: two different joints collide when they agree modulo 8);
+//   * TWO COPIES of the palette (RunPlanInput::copy_b_base > 0): the kernel stages the instance's palette twice, the
+//     second time permuted -- joint j sits at entry j of copy A (bank group j mod 8) and at entry copy_b_base +
+//     (j mod 8) * G + j / 8 of copy B (bank group ((j mod 8) * G + j / 8) mod 8: joints that share a group in A are
+//     spread in B).  Which copy a lane reads an entry's joint from is free, and static: per quarter-warp and entry the
+//     planner picks the assignment with the fewest wavefronts (two choices per joint, a small matching problem), and
+//     the item simply carries the chosen palette INDEX.  Random joints: 2.1 wavefronts per gather load -> ~1.2.
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -41,6 +47,7 @@ struct RunPlanHost {
   std::vector<int> tile_slot_offsets;  // [num_tiles + 1]
   std::vector<uint32_t> items;         // [slots * 32]: start | count << 13 | skinned << 18 | delay << 22 (entries << 19 added at upload)
   std::vector<int32_t> item_blend;     // [slots * 32]: blend id of the item (-1: rows outside get_rows())
+  std::vector<uint8_t> item_copy;       // [slots * 32]: bit k set = entry k of the item's blend is read from palette copy B
   // statistics (tools/plan_stats, P3CS_DEBUG_PLAN)
   long long num_items = 0, num_slots = 0, lane_steps = 0, warp_steps = 0, idle_lanes = 0, gather_wavefronts = 0, gather_ideal = 0;
 };
@@ -53,7 +60,83 @@ struct RunPlanInput {
   // the TransformBlendTable (CSR), for the palette-gather term of the placement; may be null
   const int *blend_offsets = nullptr;
   const int *blend_transform = nullptr;
+  // two palette copies (see the header comment): first entry of copy B (a multiple of 8; 0 = one copy) and G = ceil(T / 8)
+  int copy_b_base = 0, copy_groups = 0;
 };
+
+// Entry of joint j in palette copy B.
+inline int palette_copy_b_index(int j, int copy_b_base, int copy_groups) { return copy_b_base + (j & 7) * copy_groups + (j >> 3); }
+
+// The fewest wavefronts of one gather load of a quarter-warp: `n` distinct joints (n <= 8), each read from copy A or
+// copy B; a wavefront serves one entry per bank group (index mod 8).  Smallest L such that every joint can take one of
+// its two groups with no group taken more than L times -- augmenting paths, capacities L.  `choice[i]`: 1 = copy B.
+inline int two_copy_gather(const int *joints, int n, int copy_b_base, int copy_groups, int *choice) {
+  if (n <= 0) return 0;
+  int ga[8], gb[8];
+  for (int i = 0; i < n; ++i) {
+    ga[i] = joints[i] & 7;
+    gb[i] = copy_b_base > 0 ? palette_copy_b_index(joints[i], copy_b_base, copy_groups) & 7 : ga[i];
+  }
+  for (int L = 1; L <= 8; ++L) {
+    int load[8] = {0, 0, 0, 0, 0, 0, 0, 0}, at[8];
+    for (int i = 0; i < n; ++i) at[i] = -1;
+    bool ok = true;
+    for (int i = 0; i < n && ok; ++i) {
+      // breadth-first search for an augmenting path from joint i to a group with spare capacity
+      int parent_joint[8], via_group[8], queue[8], qh = 0, qt = 0;
+      bool seen_group[8] = {false, false, false, false, false, false, false, false};
+      bool seen_joint[8] = {false, false, false, false, false, false, false, false};
+      queue[qt++] = i;
+      seen_joint[i] = true;
+      parent_joint[i] = -1;
+      via_group[i] = -1;
+      int end_joint = -1, end_group = -1;
+      while (qh < qt && end_joint < 0) {
+        const int u = queue[qh++];
+        const int cand[2] = {ga[u], gb[u]};
+        for (int c = 0; c < 2 && end_joint < 0; ++c) {
+          const int g = cand[c];
+          if (seen_group[g]) continue;
+          seen_group[g] = true;
+          if (load[g] < L) {
+            end_joint = u;
+            end_group = g;
+            break;
+          }
+          for (int v = 0; v < n; ++v)  // every joint sitting in g may move to its other group
+            if (at[v] == g && !seen_joint[v]) {
+              seen_joint[v] = true;
+              parent_joint[v] = u;
+              via_group[v] = g;
+              queue[qt++] = v;
+            }
+        }
+      }
+      if (end_joint < 0) {
+        ok = false;
+        break;
+      }
+      // shift along the path: end_joint takes end_group, its predecessor takes the group end_joint leaves, ...
+      int u = end_joint, g = end_group;
+      ++load[g];
+      while (u >= 0) {
+        const int left = at[u];
+        at[u] = g;
+        const int pu = parent_joint[u];
+        if (pu < 0) break;
+        g = via_group[u];  // == left: the group u sat in, now taken over by its parent
+        (void)left;
+        u = pu;
+      }
+    }
+    if (ok) {
+      for (int i = 0; i < n; ++i) choice[i] = (at[i] == ga[i]) ? 0 : 1;
+      return L;
+    }
+  }
+  for (int i = 0; i < n; ++i) choice[i] = 0;
+  return n;
+}
 
 // Splits a run of `len` rows into ceil(len / K) pieces of nearly equal length.
 inline void split_run(int len, int K, std::vector<int> &pieces) {
@@ -104,6 +187,16 @@ inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max
       bool known = false;
       for (int q = 0; q < sl.nseen[quarter][k][res]; ++q) known = known || sl.seen[quarter][k][res][q] == j;
       if (known) continue;  // same joint: a broadcast
+      if (in.copy_b_base > 0) {  // two palette copies: the best assignment with and without the newcomer
+        int distinct[9], nd = 0, choice[8];
+        for (int r8 = 0; r8 < 8; ++r8)
+          for (int q = 0; q < sl.nseen[quarter][k][r8]; ++q) distinct[nd++] = sl.seen[quarter][k][r8][q];
+        if (nd >= 8) continue;
+        const int before = two_copy_gather(distinct, nd, in.copy_b_base, in.copy_groups, choice);
+        distinct[nd] = j;
+        extra += two_copy_gather(distinct, nd + 1, in.copy_b_base, in.copy_groups, choice) - std::max(before, 1);
+        continue;
+      }
       int worst = 0;
       for (int r8 = 0; r8 < 8; ++r8) worst = std::max(worst, sl.nseen[quarter][k][r8]);
       if (sl.nseen[quarter][k][res] + 1 > std::max(worst, 1)) ++extra;
@@ -293,28 +386,36 @@ inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max
       }
       ++half;
     }
+    // wavefronts of the quarter-warp's 4 x 3 gather loads, in units of 3; with two palette copies every distinct joint
+    // takes the copy that serves the quarter-warp best (two_copy_gather); `copy_bits`: per lane, bit k = entry k from copy B
+    auto quarter_cost = [&](const Slot &sl, int quarter, uint8_t *copy_bits = nullptr) {
+      int total = 0;
+      for (int k = 0; k < 4; ++k) {
+        int distinct[8], nd = 0;
+        for (int l = quarter * 8; l < quarter * 8 + 8; ++l) {
+          if (sl.lane_item[l] < 0) continue;
+          const int j = items[sl.lane_item[l]].joint[k];
+          if (j < 0) continue;
+          bool known = false;
+          for (int q = 0; q < nd; ++q) known = known || distinct[q] == j;
+          if (!known) distinct[nd++] = j;
+        }
+        int choice[8];
+        total += two_copy_gather(distinct, nd, in.copy_b_base, in.copy_groups, choice);
+        if (copy_bits != nullptr)
+          for (int l = quarter * 8; l < quarter * 8 + 8; ++l) {
+            if (sl.lane_item[l] < 0) continue;
+            const int j = items[sl.lane_item[l]].joint[k];
+            for (int q = 0; q < nd; ++q)
+              if (distinct[q] == j && choice[q]) copy_bits[l] |= (uint8_t)(1u << k);
+          }
+      }
+      return total;
+    };
     // Palette-gather conflicts, second pass.  Lanes l and l + 16 of a slot serve the same row residue, so their items may
     // trade places at no cost to the row walk; that changes which quarter-warp (eight lanes = one 128-bit load wavefront)
     // an item gathers with.  Hill-climb per slot on the number of gather wavefronts.
     {
-      auto quarter_cost = [&](const Slot &sl, int quarter) {  // wavefronts of the quarter-warp's 4 x 3 gather loads, in units of 3
-        int total = 0;
-        for (int k = 0; k < 4; ++k) {
-          int seen[8][8], nseen[8] = {0, 0, 0, 0, 0, 0, 0, 0}, worst = 0;
-          for (int l = quarter * 8; l < quarter * 8 + 8; ++l) {
-            if (sl.lane_item[l] < 0) continue;
-            const int j = items[sl.lane_item[l]].joint[k];
-            if (j < 0) continue;
-            const int res = j & 7;
-            bool known = false;
-            for (int q = 0; q < nseen[res]; ++q) known = known || seen[res][q] == j;
-            if (!known) seen[res][nseen[res]++] = j;
-            worst = std::max(worst, nseen[res]);
-          }
-          total += worst;
-        }
-        return total;
-      };
       for (Slot &sl : slots) {
         for (int pass = 0; pass < 4; ++pass) {
           bool improved = false;
@@ -353,8 +454,10 @@ inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max
     const size_t base = p.items.size();
     p.items.resize(base + slots.size() * 32, 0u);
     p.item_blend.resize(base + slots.size() * 32, -1);
+    p.item_copy.resize(base + slots.size() * 32, 0);
     for (size_t si = 0; si < slots.size(); ++si) {
       const Slot &sl = slots[si];
+      for (int q = 0; q < 4; ++q) p.gather_wavefronts += 3 * quarter_cost(sl, q, p.item_copy.data() + base + si * 32);
       for (int l = 0; l < 32; ++l) {
         const size_t at = base + si * 32 + l;
         if (sl.lane_item[l] < 0) {
@@ -372,7 +475,7 @@ inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max
         for (int k = 0; k < 4; ++k) {
           int worst = 0, any = 0;
           for (int r8 = 0; r8 < 8; ++r8) worst = std::max(worst, sl.nseen[q][k][r8]), any += sl.nseen[q][k][r8];
-          p.gather_wavefronts += 3 * worst;
+          (void)worst;
           p.gather_ideal += any ? 3 : 0;
         }
     }

@@ -154,7 +154,7 @@ static int launch_run(const MeshDev &mesh, const GroupDev &grp, int first_instan
   const RunPlanDev &plan = mesh.run_plan[rl.plan];
   int threads, ctas;
   run_shape(mesh.run_mode, &threads, &ctas);
-  const size_t smem = (size_t)run_layout(mesh.num_transforms, plan.tile_rows, strip_mode_row_bytes(mesh.run_mode), plan.tile_bufs, threads).total;
+  const size_t smem = (size_t)run_layout(plan.pal_entries, mesh.num_transforms, plan.tile_rows, strip_mode_row_bytes(mesh.run_mode), plan.tile_bufs, threads).total;
   int launches = 0;
   for (int c0 = 0; c0 < count; c0 += 65535) {
     const int cn = count - c0 < 65535 ? count - c0 : 65535;

@@ -1242,8 +1242,11 @@ def test_run_kernel_and_strip_kernel_agree(gpu_ctx, monkeypatch, layout, order):
     sl = synth.make_sliders(mesh.num_sliders, n, 42) if mesh.num_sliders else None
     om = oracle.OracleMesh(mesh)
     results = {}
-    for path in ("run", "strip"):
-        monkeypatch.setenv("P3CS_PATH", path)
+    # "run2": the run kernel with two palette copies in shared memory (items carry palette-area indices the planner
+    # chose, p3cs_runplan.h); "run": one copy; by default the library picks per mesh
+    for path in ("run", "run2", "strip"):
+        monkeypatch.setenv("P3CS_PATH", path.rstrip("2"))
+        monkeypatch.setenv("P3CS_RUN_COPIES", "2" if path == "run2" else "1")
         dmesh = _capi.Mesh(gpu_ctx, mesh)
         grp = _capi.Group(dmesh, n)
         try:
@@ -1268,6 +1271,8 @@ def test_run_kernel_and_strip_kernel_agree(gpu_ctx, monkeypatch, layout, order):
             dmesh.close()
     out_r, bounds_r, listed_r = results["run"]
     out_s, bounds_s, listed_s = results["strip"]
+    assert np.array_equal(out_r, results["run2"][0]), "two palette copies change the run kernel's bytes"
+    assert np.array_equal(bounds_r.view(np.uint32), results["run2"][1].view(np.uint32)) and np.array_equal(listed_r, results["run2"][2])
     assert np.array_equal(out_r, out_s), "run kernel and strip kernel differ"
     assert np.array_equal(bounds_r.view(np.uint32), bounds_s.view(np.uint32)), "tight bounds differ between the kernels"
     assert np.array_equal(listed_r, listed_s)

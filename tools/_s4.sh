@@ -1,0 +1,4 @@
+timeout 900 python -m pytest tests -m gpu -q -x -k "run_kernel or fullsize or full_size or non_affine or crowd or golden or synthetic or edge or pointers" 2>&1 | tail -6 > gpurun_out/s4_tests.log
+for c in 1 2; do echo "== copies $c" >> gpurun_out/s4_k.log; P3CS_RUN_COPIES=$c timeout 300 python tools/kbench.py --configs c3,c3uv,c3tb,c3rand >> gpurun_out/s4_k.log 2>&1; done
+for c in 1 2; do echo "== copies $c, 1250" >> gpurun_out/s4_k.log; P3CS_RUN_COPIES=$c timeout 300 python tools/kbench.py --configs c3 --instances 1250 >> gpurun_out/s4_k.log 2>&1; done
+cat gpurun_out/s4_tests.log; sed 's/"vertices".*//' gpurun_out/s4_k.log

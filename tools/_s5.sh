@@ -1,0 +1,3 @@
+timeout 900 python -m pytest tests -m gpu -q -x -k "run_kernel or fullsize or full_size or non_affine or crowd or edge" 2>&1 | tail -6 > gpurun_out/s5_tests.log
+timeout 300 python tools/kbench.py --configs c3,c3uv,c3tb,c3rand > gpurun_out/s5_k.log 2>&1
+cat gpurun_out/s5_tests.log; sed 's/"vertices".*//' gpurun_out/s5_k.log

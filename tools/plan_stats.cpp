@@ -1,5 +1,5 @@
 // tools/plan_stats.cpp -- offline look at a run plan (csrc/p3cs_runplan.h): g++ -O2 -o /tmp/plan_stats tools/plan_stats.cpp
-// usage: plan_stats <rows.u32> <blend_offsets.i32> <blend_transform.i32> <tile_rows> <max_item_rows>
+// usage: plan_stats <rows.u32> <blend_offsets.i32> <blend_transform.i32> <tile_rows> <max_item_rows> [trim] [T: two palette copies]
 #include "../panda3d_b200/csrc/p3cs_runplan.h"
 #include <chrono>
 #include <cstdlib>
@@ -21,6 +21,11 @@ int main(int argc, char **argv) {
   in.row_blend = idx.data();
   in.blend_offsets = off.data();
   in.blend_transform = xf.data();
+  if (argc > 7 && atoi(argv[7]) > 0) {
+    const int T = atoi(argv[7]);
+    in.copy_b_base = (T + 7) & ~7;
+    in.copy_groups = (T + 7) / 8;
+  }
   auto t0 = std::chrono::steady_clock::now();
   p3cs::RunPlanHost p = p3cs::build_run_plan(in, atoi(argv[4]), atoi(argv[5]), argc > 6 ? atoi(argv[6]) : 0);
   double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
