@@ -42,9 +42,9 @@ struct RunPlanDev {
   // TransformBlendTable's CSR by blend id); 0 = idle lane.  Padded by 8 slots (the kernel prefetches unconditionally).
   const uint4 *item_a;
   const uint4 *item_b;
-  // two palette copies in shared memory (p3cs_runplan.h): entries of the palette area (T for one copy), first entry of
-  // copy B (0: one copy) and G = ceil(T / 8); the items' joint fields hold palette-area INDICES
-  int pal_entries, copy_b_base, copy_groups;
+  // two palette copies in shared memory (p3cs_runplan.h): entries of the palette area (T for one copy) and first entry
+  // of copy B (0: one copy); the items' joint fields hold palette-area INDICES
+  int pal_entries, copy_b_base;
 };
 
 struct MeshDev {

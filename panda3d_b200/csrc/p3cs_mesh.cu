@@ -402,8 +402,7 @@ static StripTables build_record_groups(const p3cs_mesh_desc *d, const std::vecto
 // plus per item its first four (palette index, weight) entries.  Two plans per mesh: [0] large tiles for crowds
 // (as many rows as two tile buffers of a CTA hold with four CTAs per SM), [1] 256-row tiles for launches of a few
 // instances, where many small CTAs fill the machine better.
-static int upload_run_plan(p3cs_mesh mesh, const p3cs_mesh_desc *d, const RunPlanHost &hp, int tile_bufs, int copy_b_base, int copy_groups,
-                           RunPlanDev *out) {
+static int upload_run_plan(p3cs_mesh mesh, const p3cs_mesh_desc *d, const RunPlanHost &hp, int tile_bufs, int copy_b_base, RunPlanDev *out) {
   int rc;
   const size_t used = hp.items.size();
   const size_t n = used + 8 * 32;  // padded by a CTA's worth of slots: the kernel prefetches the warp's next slot unconditionally
@@ -416,7 +415,7 @@ static int upload_run_plan(p3cs_mesh mesh, const p3cs_mesh_desc *d, const RunPla
       for (int k = 0; k < std::min(cnt, 4); ++k) {
         const int j = d->blend_transform[beg + k];
         // the entry's palette-area index: copy A = the joint itself, copy B where the planner chose it
-        joints[k] = (uint32_t)(copy_b_base > 0 && ((hp.item_copy[i] >> k) & 1u) ? palette_copy_b_index(j, copy_b_base, copy_groups) : j);
+        joints[k] = (uint32_t)(copy_b_base > 0 && ((hp.item_copy[i] >> k) & 1u) ? palette_copy_b_index(j, copy_b_base) : j);
         memcpy(&w[k], &d->blend_weight[beg + k], 4);
       }
       item |= (uint32_t)std::min(cnt, 5) << kItemEntriesShift;
@@ -429,8 +428,7 @@ static int upload_run_plan(p3cs_mesh mesh, const p3cs_mesh_desc *d, const RunPla
   out->num_tiles = hp.num_tiles;
   out->max_item_rows = hp.max_item_rows;
   out->copy_b_base = copy_b_base;
-  out->copy_groups = copy_groups;
-  out->pal_entries = copy_b_base > 0 ? copy_b_base + 8 * copy_groups : mesh->dev.num_transforms;
+  out->pal_entries = copy_b_base > 0 ? 2 * copy_b_base : mesh->dev.num_transforms;
   if ((rc = upload<int>(mesh, hp.tile_slot_offsets.data(), hp.tile_slot_offsets.size(), &out->tile_slot_offsets)) != P3CS_OK) return rc;
   if ((rc = upload<uint4>(mesh, a.data(), n, &out->item_a)) != P3CS_OK) return rc;
   if ((rc = upload<uint4>(mesh, b.data(), n, &out->item_b)) != P3CS_OK) return rc;
@@ -454,14 +452,14 @@ static int build_run_plans(p3cs_mesh mesh, const p3cs_mesh_desc *d, const std::v
   // blend per vertex 3.31 -> 3.16 ms; 32- and 48-byte rows with runs lose (1.580 -> 1.591, 2.042 -> 2.082 ms): their rows
   // carry more bytes per gathered matrix.  So: 24-byte rows, or runs shorter than three rows on average; not for tiny
   // palettes nor where both copies exceed 16 KB.  P3CS_RUN_COPIES=1 / 2 forces (A/B runs).
-  int copy_groups = (m.num_transforms + 7) / 8, copy_b_base = (m.num_transforms + 7) & ~7;
+  int copy_b_base = (m.num_transforms + 7) & ~7;  // copy B behind copy A, both whole octets of joints
   long long runs = 1;
   for (int r = 1; r < m.num_rows; ++r) runs += row_index[r] != row_index[r - 1];
-  bool two_copies = m.num_transforms >= 16 && (copy_b_base + 8 * copy_groups) * 48 <= 16 * 1024 &&
+  bool two_copies = m.num_transforms >= 16 && 2 * copy_b_base * 48 <= 16 * 1024 &&
                     (mode == kRow24 || (long long)m.num_rows < 3 * runs);
-  if (const char *e = getenv("P3CS_RUN_COPIES")) two_copies = atoi(e) == 2 && m.num_transforms >= 8 && copy_b_base + 8 * copy_groups < 65536;
-  if (!two_copies) copy_b_base = copy_groups = 0;
-  const int pal_entries = two_copies ? copy_b_base + 8 * copy_groups : m.num_transforms;
+  if (const char *e = getenv("P3CS_RUN_COPIES")) two_copies = atoi(e) == 2 && m.num_transforms >= 8 && 2 * copy_b_base < 65536;
+  if (!two_copies) copy_b_base = 0;
+  const int pal_entries = two_copies ? 2 * copy_b_base : m.num_transforms;
   const int fixed = run_layout(pal_entries, m.num_transforms, 16, row_bytes, 1, threads).tiles_off;
   // `ctas` CTAs per SM: 228 KB per SM, 1 KB reserved per CTA
   int budget = (228 * 1024 / ctas - 1024) - fixed;
@@ -485,18 +483,17 @@ static int build_run_plans(p3cs_mesh mesh, const p3cs_mesh_desc *d, const std::v
   in.blend_offsets = d->blend_offsets;
   in.blend_transform = d->blend_transform;
   in.copy_b_base = copy_b_base;
-  in.copy_groups = copy_groups;
   int rc;
   {
     const RunPlanHost hp = build_run_plan(in, tile_rows, K, trim);
     if (getenv("P3CS_DEBUG_PLAN") != nullptr) print_run_plan_stats(hp, m.num_rows, stderr);
     m.run_lockstep_pct = hp.warp_steps > 0 ? (int)(100 * hp.lane_steps / (32 * hp.warp_steps)) : 0;
-    if ((rc = upload_run_plan(mesh, d, hp, bufs, copy_b_base, copy_groups, &m.run_plan[0])) != P3CS_OK) return rc;
+    if ((rc = upload_run_plan(mesh, d, hp, bufs, copy_b_base, &m.run_plan[0])) != P3CS_OK) return rc;
   }
   if (tile_rows > 256) {
     const int small_bufs = fixed + 3 * 256 * row_bytes <= 228 * 1024 / ctas - 1024 ? 3 : 2;
     const RunPlanHost hp = build_run_plan(in, 256, K, trim);
-    if ((rc = upload_run_plan(mesh, d, hp, small_bufs, copy_b_base, copy_groups, &m.run_plan[1])) != P3CS_OK) return rc;
+    if ((rc = upload_run_plan(mesh, d, hp, small_bufs, copy_b_base, &m.run_plan[1])) != P3CS_OK) return rc;
   }
   m.run_mode = mode;
   return P3CS_OK;

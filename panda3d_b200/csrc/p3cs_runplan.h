@@ -19,9 +19,9 @@
 //     the items already in the same quarter-warp (the palette gather is a 128-bit load per lane, eight lanes per
 //     wavefront, 48-byte palette rows: two different joints collide when they agree modulo 8);
 //   * TWO COPIES of the palette (RunPlanInput::copy_b_base > 0): the kernel stages the instance's palette twice, the
-//     second time permuted -- joint j sits at entry j of copy A (bank group j mod 8) and at entry copy_b_base +
-//     (j mod 8) * G + j / 8 of copy B (bank group ((j mod 8) * G + j / 8) mod 8: joints that share a group in A are
-//     spread in B).  Which copy a lane reads an entry's joint from is free, and static: per quarter-warp and entry the
+//     second time permuted inside every octet of joints -- joint j = 8a + c sits at entry j of copy A (bank group c)
+//     and at entry copy_b_base + 8a + ((a + 3c) mod 8) of copy B (bank group (a + 3c) mod 8): two joints that share a
+//     group in one copy never share it in the other (unless they are a multiple of 64 apart).  Which copy a lane reads an entry's joint from is free, and static: per quarter-warp and entry the
 //     planner picks the assignment with the fewest wavefronts (two choices per joint, a small matching problem), and
 //     the item simply carries the chosen palette INDEX.  Random joints: 2.1 wavefronts per gather load -> ~1.2.
 #pragma once
@@ -29,6 +29,12 @@
 #include <cstdint>
 #include <cstdio>
 #include <vector>
+
+#ifdef __CUDACC__
+#define P3CS_PLAN_HD __host__ __device__
+#else
+#define P3CS_PLAN_HD
+#endif
 
 namespace p3cs {
 
@@ -60,22 +66,28 @@ struct RunPlanInput {
   // the TransformBlendTable (CSR), for the palette-gather term of the placement; may be null
   const int *blend_offsets = nullptr;
   const int *blend_transform = nullptr;
-  // two palette copies (see the header comment): first entry of copy B (a multiple of 8; 0 = one copy) and G = ceil(T / 8)
-  int copy_b_base = 0, copy_groups = 0;
+  // two palette copies (see the header comment): first entry of copy B (a multiple of 8; 0 = one copy)
+  int copy_b_base = 0;
 };
 
 // Entry of joint j in palette copy B.
-inline int palette_copy_b_index(int j, int copy_b_base, int copy_groups) { return copy_b_base + (j & 7) * copy_groups + (j >> 3); }
+P3CS_PLAN_HD inline int palette_copy_b_index(int j, int copy_b_base) { return copy_b_base + (j & ~7) + (((j >> 3) + 3 * (j & 7)) & 7); }
+// ... and back: the joint behind an index of the palette area (3 * 3 = 1 modulo 8).
+P3CS_PLAN_HD inline int palette_area_joint(int index, int copy_b_base) {
+  if (copy_b_base <= 0 || index < copy_b_base) return index;
+  const int i = index - copy_b_base;
+  return (i & ~7) + ((3 * ((i & 7) - (i >> 3))) & 7);
+}
 
 // The fewest wavefronts of one gather load of a quarter-warp: `n` distinct joints (n <= 8), each read from copy A or
 // copy B; a wavefront serves one entry per bank group (index mod 8).  Smallest L such that every joint can take one of
 // its two groups with no group taken more than L times -- augmenting paths, capacities L.  `choice[i]`: 1 = copy B.
-inline int two_copy_gather(const int *joints, int n, int copy_b_base, int copy_groups, int *choice) {
+inline int two_copy_gather(const int *joints, int n, int copy_b_base, int *choice) {
   if (n <= 0) return 0;
   int ga[8], gb[8];
   for (int i = 0; i < n; ++i) {
     ga[i] = joints[i] & 7;
-    gb[i] = copy_b_base > 0 ? palette_copy_b_index(joints[i], copy_b_base, copy_groups) & 7 : ga[i];
+    gb[i] = copy_b_base > 0 ? palette_copy_b_index(joints[i], copy_b_base) & 7 : ga[i];
   }
   for (int L = 1; L <= 8; ++L) {
     int load[8] = {0, 0, 0, 0, 0, 0, 0, 0}, at[8];
@@ -192,9 +204,9 @@ inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max
         for (int r8 = 0; r8 < 8; ++r8)
           for (int q = 0; q < sl.nseen[quarter][k][r8]; ++q) distinct[nd++] = sl.seen[quarter][k][r8][q];
         if (nd >= 8) continue;
-        const int before = two_copy_gather(distinct, nd, in.copy_b_base, in.copy_groups, choice);
+        const int before = two_copy_gather(distinct, nd, in.copy_b_base, choice);
         distinct[nd] = j;
-        extra += two_copy_gather(distinct, nd + 1, in.copy_b_base, in.copy_groups, choice) - std::max(before, 1);
+        extra += two_copy_gather(distinct, nd + 1, in.copy_b_base, choice) - std::max(before, 1);
         continue;
       }
       int worst = 0;
@@ -401,7 +413,7 @@ inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max
           if (!known) distinct[nd++] = j;
         }
         int choice[8];
-        total += two_copy_gather(distinct, nd, in.copy_b_base, in.copy_groups, choice);
+        total += two_copy_gather(distinct, nd, in.copy_b_base, choice);
         if (copy_bits != nullptr)
           for (int l = quarter * 8; l < quarter * 8 + 8; ++l) {
             if (sl.lane_item[l] < 0) continue;

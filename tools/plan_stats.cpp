@@ -24,7 +24,6 @@ int main(int argc, char **argv) {
   if (argc > 7 && atoi(argv[7]) > 0) {
     const int T = atoi(argv[7]);
     in.copy_b_base = (T + 7) & ~7;
-    in.copy_groups = (T + 7) / 8;
   }
   auto t0 = std::chrono::steady_clock::now();
   p3cs::RunPlanHost p = p3cs::build_run_plan(in, atoi(argv[4]), atoi(argv[5]), argc > 6 ? atoi(argv[6]) : 0);
