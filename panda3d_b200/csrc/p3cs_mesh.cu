@@ -448,15 +448,16 @@ static int build_run_plans(p3cs_mesh mesh, const p3cs_mesh_desc *d, const std::v
   int threads, ctas;
   run_shape(mode, &threads, &ctas);
   // Two palette copies in shared memory (p3cs_runplan.h) where the palette gather weighs enough to pay for the tile rows
-  // the second copy displaces.  Measured on B200, crowds of the C3 character: 24-byte rows 1.247 -> 1.232 ms, a random
-  // blend per vertex 3.31 -> 3.16 ms; 32- and 48-byte rows with runs lose (1.580 -> 1.591, 2.042 -> 2.082 ms): their rows
-  // carry more bytes per gathered matrix.  So: 24-byte rows, or runs shorter than three rows on average; not for tiny
-  // palettes nor where both copies exceed 16 KB.  P3CS_RUN_COPIES=1 / 2 forces (A/B runs).
+  // the second copy displaces.  Measured on B200, crowds of the C3 character (A/B on one box): 24-byte rows 1.251 ->
+  // 1.206 ms, 32-byte rows 1.590 -> 1.569 ms, a random blend per vertex 3.31 -> 3.14 ms; 48-byte rows with runs lose
+  // (2.01 -> 2.04 ms: their tiles are small already -- 672 rows -- and a row carries more bytes per gathered matrix).
+  // So: 24- and 32-byte rows, or runs shorter than three rows on average; not for tiny palettes nor where both copies
+  // exceed 16 KB.  P3CS_RUN_COPIES=1 / 2 forces (A/B runs).
   int copy_b_base = (m.num_transforms + 7) & ~7;  // copy B behind copy A, both whole octets of joints
   long long runs = 1;
   for (int r = 1; r < m.num_rows; ++r) runs += row_index[r] != row_index[r - 1];
   bool two_copies = m.num_transforms >= 16 && 2 * copy_b_base * 48 <= 16 * 1024 &&
-                    (mode == kRow24 || (long long)m.num_rows < 3 * runs);
+                    (mode == kRow24 || mode == kRow32 || (long long)m.num_rows < 3 * runs);
   if (const char *e = getenv("P3CS_RUN_COPIES")) two_copies = atoi(e) == 2 && m.num_transforms >= 8 && 2 * copy_b_base < 65536;
   if (!two_copies) copy_b_base = 0;
   const int pal_entries = two_copies ? 2 * copy_b_base : m.num_transforms;
