@@ -624,7 +624,7 @@ def run_gpu_arm(args):
                     "algorithmic_bytes_per_vertex": alg_bytes_per_step / (n_local * rows),
                     "logical_gbs": logical_bytes_per_step / skin_s / 1e9,
                     "limiter": pj_limiter,
-                    "note": "run kernel (one thread per run of rows, blend in registers); the SM's L1TEX/LSU data pipe is the binding unit on this 24 B/vertex crowd (83 % of its peak), DRAM traffic equals the algorithmic bytes: see DESIGN.md"}
+                    "note": "run kernel (one thread per run of rows, blend in registers, two palette copies); on this 24 B/vertex crowd the SM's L1TEX/LSU data pipe (80 % of its peak) and instruction issue (75 %) bind together, DRAM traffic equals the algorithmic bytes: see DESIGN.md"}
         cpu = None
         if world == 1 and not args.no_cpu:
             workers = os.cpu_count() or 1
