@@ -398,6 +398,58 @@ inline RunPlanHost build_run_plan(const RunPlanInput &in, int tile_rows, int max
       }
       ++half;
     }
+    // Clean-up: the greedy fill leaves the tile's last slot(s) nearly empty (two or three one-row items, say), and a slot
+    // costs its opening (a blend per lane) whatever it holds.  Try to dissolve the emptiest slot: every item of it moves
+    // into a free lane of another slot -- any free lane will do, the delay (first row - lane) mod 16 keeps the residue rule,
+    // at the price of the steps the host slot grows by -- and the move is kept when the growth costs less than the slot saved.
+    while (slots.size() > 1) {
+      size_t victim = 0;
+      for (size_t i = 1; i < slots.size(); ++i)
+        if (slots[i].used < slots[victim].used || (slots[i].used == slots[victim].used && slots[i].steps <= slots[victim].steps)) victim = i;
+      const Slot &vs = slots[victim];
+      if (vs.used > 24) break;
+      struct Move {
+        int item, slot, lane, delay;
+      };
+      std::vector<Move> moves;
+      std::vector<int> new_steps(slots.size());
+      std::vector<std::vector<char>> taken(slots.size(), std::vector<char>(32, 0));
+      for (size_t i = 0; i < slots.size(); ++i) new_steps[i] = slots[i].steps;
+      bool ok = true;
+      std::vector<int> order;  // longest items first: they have the fewest places to go
+      for (int l = 0; l < 32; ++l)
+        if (vs.lane_item[l] >= 0) order.push_back(vs.lane_item[l]);
+      std::sort(order.begin(), order.end(), [&](int x, int y) { return items[x].count > items[y].count; });
+      for (int idx : order) {
+        const Item &it = items[idx];
+        int best_slot = -1, best_lane = -1, best_d = 0, best_growth = 1 << 30, best_free = -1;
+        for (size_t i = 0; i < slots.size(); ++i) {
+          if (i == victim) continue;
+          for (int l = 0; l < 32; ++l) {
+            if (slots[i].lane_item[l] >= 0 || taken[i][l]) continue;
+            const int d = (it.start - l) & 15;
+            const int growth = std::max(0, d + it.count - new_steps[i]);
+            const int free_here = 32 - slots[i].used;
+            if (growth < best_growth || (growth == best_growth && free_here > best_free)) {
+              best_growth = growth, best_slot = (int)i, best_lane = l, best_d = d, best_free = free_here;
+            }
+          }
+        }
+        if (best_slot < 0) {
+          ok = false;
+          break;
+        }
+        taken[best_slot][best_lane] = 1;
+        new_steps[best_slot] = std::max(new_steps[best_slot], best_d + it.count);
+        moves.push_back(Move{idx, best_slot, best_lane, best_d});
+      }
+      if (!ok) break;
+      long long growth_cost = 0;
+      for (size_t i = 0; i < slots.size(); ++i) growth_cost += (long long)(new_steps[i] - slots[i].steps) * kPlanStepCost;
+      if (growth_cost >= kPlanSlotCost + (long long)vs.steps * kPlanStepCost) break;
+      for (const Move &mv : moves) place(slots[mv.slot], mv.lane, mv.item, mv.delay);
+      slots.erase(slots.begin() + victim);
+    }
     // wavefronts of the quarter-warp's 4 x 3 gather loads, in units of 3; with two palette copies every distinct joint
     // takes the copy that serves the quarter-warp best (two_copy_gather); `copy_bits`: per lane, bit k = entry k from copy B
     auto quarter_cost = [&](const Slot &sl, int quarter, uint8_t *copy_bits = nullptr) {
