@@ -2,6 +2,6 @@
 #include "p3cs_run.cuh"
 
 namespace p3cs {
-template void launch_run_mode<kRow24>(const MeshDev &, const RunPlanDev &, const GroupDev &, int, dim3, size_t, int, int, cudaStream_t);
-template void launch_run_mode<kRow32>(const MeshDev &, const RunPlanDev &, const GroupDev &, int, dim3, size_t, int, int, cudaStream_t);
+template void launch_run_mode<kRow24>(const MeshDev &, const RunPlanDev &, const GroupDev &, int, dim3, size_t, int, RunTail, int, cudaStream_t);
+template void launch_run_mode<kRow32>(const MeshDev &, const RunPlanDev &, const GroupDev &, int, dim3, size_t, int, RunTail, int, cudaStream_t);
 }  // namespace p3cs

@@ -24,7 +24,7 @@ P3CS_EXTERN_MODE(kAlignedPNVV)
 
 // run kernel (p3cs_run.cuh), instantiated in p3cs_run_inst_*.cu
 #define P3CS_EXTERN_RUN(M)                                                                                                          \
-  extern template void launch_run_mode<M>(const MeshDev &, const RunPlanDev &, const GroupDev &, int, dim3, size_t, int, int, cudaStream_t);
+  extern template void launch_run_mode<M>(const MeshDev &, const RunPlanDev &, const GroupDev &, int, dim3, size_t, int, RunTail, int, cudaStream_t);
 P3CS_EXTERN_RUN(kRow24)
 P3CS_EXTERN_RUN(kRow32)
 P3CS_EXTERN_RUN(kRow48)
@@ -116,10 +116,11 @@ static bool use_run_kernel(const MeshDev &mesh, int count) {
 
 struct RunLaunch {
   int plan, ctas_per_instance, tiles_per_cta;
+  RunTail tail;  // {-1, 0, 0}: none
 };
 
-static RunLaunch run_partition(const MeshDev &mesh, int count, int sm_count) {
-  RunLaunch r{0, 1, 1};
+static RunLaunch run_partition(const MeshDev &mesh, int count, int sm_count, bool grp_plain = false) {
+  RunLaunch r{0, 1, 1, {-1, 0, 0}};
   // the crowd plan (large tiles) needs enough instances to fill every SM four times over; else the small tiles
   const RunPlanDev &big = mesh.run_plan[0];
   if (mesh.run_plan[1].tile_rows != 0 && (long long)big.num_tiles * count < 4LL * sm_count) r.plan = 1;
@@ -139,6 +140,27 @@ static RunLaunch run_partition(const MeshDev &mesh, int count, int sm_count) {
   if (cpi > p.num_tiles) cpi = p.num_tiles;
   r.tiles_per_cta = (p.num_tiles + (int)cpi - 1) / (int)cpi;
   r.ctas_per_instance = (p.num_tiles + r.tiles_per_cta - 1) / r.tiles_per_cta;
+  // Tail split.  With one CTA per instance a launch drains for a good part of an instance's time (the CTAs of the last wave
+  // end one by one; an instance of the C3 character takes 55 us, a third of the whole launch at 1250 instances).  So the
+  // last `resident` instances go in two pieces each, dealt last (RunGeom): the drain shrinks with the pieces, at the price
+  // of staging those instances' palettes twice.  Measured on B200 (C3 character): 1250 instances 0.172 -> 0.167 ms, 10 000
+  // instances 1.186 -> 1.185 ms; three pieces 0.169 / 1.183, four 0.172 / 1.187, twice as many instances in three 0.174 /
+  // 1.188.  Plain launches only (no bounds, whose per-instance merge depends on the grid shape; an instance list is
+  // indexed the same way).  P3CS_RUN_TAIL="instances,parts" tunes, "0" turns off.
+  if (r.ctas_per_instance == 1 && grp_plain && p.num_tiles >= 4) {
+    int tail_instances = ctas * sm_count, parts = 2;
+    if (const char *e = getenv("P3CS_RUN_TAIL")) {
+      int a = 0, b = 0;
+      if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 0 && b >= 2) tail_instances = a, parts = b;
+      else tail_instances = 0;
+    }
+    if (tail_instances > count) tail_instances = count;
+    if (parts > p.num_tiles) parts = p.num_tiles;
+    if (tail_instances > 0) {
+      const int tpc = (p.num_tiles + parts - 1) / parts;
+      r.tail = RunTail{count - tail_instances, (p.num_tiles + tpc - 1) / tpc, tpc};
+    }
+  }
   return r;
 }
 
@@ -150,21 +172,24 @@ int strip_ctas_per_instance(const MeshDev &mesh, int count, int sm_count) {
 }
 
 static int launch_run(const MeshDev &mesh, const GroupDev &grp, int first_instance, int count, int sm_count, int want_normal, cudaStream_t stream) {
-  const RunLaunch rl = run_partition(mesh, count, sm_count);
+  const bool plain = grp.selection == nullptr && grp.bounds == nullptr;
+  const RunLaunch rl = run_partition(mesh, count, sm_count, plain);
   const RunPlanDev &plan = mesh.run_plan[rl.plan];
   int threads, ctas;
   run_shape(mesh.run_mode, &threads, &ctas);
   const size_t smem = (size_t)run_layout(plan.pal_entries, mesh.num_transforms, plan.tile_rows, strip_mode_row_bytes(mesh.run_mode), plan.tile_bufs, threads).total;
   int launches = 0;
-  for (int c0 = 0; c0 < count; c0 += 65535) {
-    const int cn = count - c0 < 65535 ? count - c0 : 65535;
-    const dim3 grid(rl.ctas_per_instance, cn);
+  const int chunk = rl.tail.whole_instances >= 0 ? count : 65535;  // the one-dimensional grid of the tail split has no 65535 limit
+  for (int c0 = 0; c0 < count; c0 += chunk) {
+    const int cn = count - c0 < chunk ? count - c0 : chunk;
+    const dim3 grid = rl.tail.whole_instances >= 0 ? dim3((unsigned)(rl.tail.whole_instances + (count - rl.tail.whole_instances) * rl.tail.parts), 1)
+                                                   : dim3(rl.ctas_per_instance, cn);
     const int first = first_instance + c0;
     switch (mesh.run_mode) {
-    case kRow24: launch_run_mode<kRow24>(mesh, plan, grp, first, grid, smem, rl.tiles_per_cta, want_normal, stream); break;
-    case kRow32: launch_run_mode<kRow32>(mesh, plan, grp, first, grid, smem, rl.tiles_per_cta, want_normal, stream); break;
-    case kRow48: launch_run_mode<kRow48>(mesh, plan, grp, first, grid, smem, rl.tiles_per_cta, want_normal, stream); break;
-    default: launch_run_mode<kRow56>(mesh, plan, grp, first, grid, smem, rl.tiles_per_cta, want_normal, stream); break;
+    case kRow24: launch_run_mode<kRow24>(mesh, plan, grp, first, grid, smem, rl.tiles_per_cta, rl.tail, want_normal, stream); break;
+    case kRow32: launch_run_mode<kRow32>(mesh, plan, grp, first, grid, smem, rl.tiles_per_cta, rl.tail, want_normal, stream); break;
+    case kRow48: launch_run_mode<kRow48>(mesh, plan, grp, first, grid, smem, rl.tiles_per_cta, rl.tail, want_normal, stream); break;
+    default: launch_run_mode<kRow56>(mesh, plan, grp, first, grid, smem, rl.tiles_per_cta, rl.tail, want_normal, stream); break;
     }
     ++launches;
   }
