@@ -484,6 +484,7 @@ static int build_run_plans(p3cs_mesh mesh, const p3cs_mesh_desc *d, const std::v
   in.blend_offsets = d->blend_offsets;
   in.blend_transform = d->blend_transform;
   in.copy_b_base = copy_b_base;
+  in.match_every_candidate = (long long)m.num_rows >= 3 * runs;  // see RunPlanInput
   int rc;
   {
     const RunPlanHost hp = build_run_plan(in, tile_rows, K, trim);

@@ -24,6 +24,9 @@ int main(int argc, char **argv) {
   if (argc > 7 && atoi(argv[7]) > 0) {
     const int T = atoi(argv[7]);
     in.copy_b_base = (T + 7) & ~7;
+    long long runs = 1;
+    for (size_t r = 1; r < idx.size(); ++r) runs += idx[r] != idx[r - 1];
+    in.match_every_candidate = (long long)idx.size() >= 3 * runs;  // as p3cs_mesh.cu does
   }
   auto t0 = std::chrono::steady_clock::now();
   p3cs::RunPlanHost p = p3cs::build_run_plan(in, atoi(argv[4]), atoi(argv[5]), argc > 6 ? atoi(argv[6]) : 0);
