@@ -75,6 +75,30 @@ struct RunPlanInput {
   bool match_every_candidate = true;
 };
 
+// Which instance and which tiles a CTA of a run-kernel launch takes (p3cs_run.cuh, RunGeom).  Two-dimensional grid
+// (whole_instances < 0): CTA (x, y) takes tiles [x * tiles_per_cta, ...) of instance y.  Tail split (one-dimensional
+// grid): CTA u < whole_instances takes all of instance u; the CTAs behind take the remaining instances in `tail_parts`
+// pieces of `tail_tiles_per_cta` tiles each, piece after piece, instance after instance.
+P3CS_PLAN_HD inline void run_unit_decode(int block_x, int block_y, int num_tiles, int tiles_per_cta, int whole_instances, int tail_parts,
+                                         int tail_tiles_per_cta, int *instance, int *tile_begin, int *tile_end) {
+  int part = block_x, inst = block_y, tiles = tiles_per_cta;
+  if (whole_instances >= 0) {
+    if (block_x < whole_instances) {
+      inst = block_x;
+      part = 0;
+      tiles = num_tiles;
+    } else {
+      const int v = block_x - whole_instances;
+      inst = whole_instances + v / tail_parts;
+      part = v % tail_parts;
+      tiles = tail_tiles_per_cta;
+    }
+  }
+  *instance = inst;
+  *tile_begin = part * tiles;
+  *tile_end = *tile_begin + tiles < num_tiles ? *tile_begin + tiles : num_tiles;
+}
+
 // Entry of joint j in palette copy B.
 P3CS_PLAN_HD inline int palette_copy_b_index(int j, int copy_b_base) { return copy_b_base + (j & ~7) + (((j >> 3) + 3 * (j & 7)) & 7); }
 // ... and back: the joint behind an index of the palette area (3 * 3 = 1 modulo 8).

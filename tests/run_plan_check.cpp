@@ -166,9 +166,37 @@ static void check_plan(std::mt19937 &rng, int N, int T, int B, int order, bool s
          p.gather_wavefronts, p.gather_ideal);
 }
 
+// every (instance, tile) of a launch belongs to exactly one CTA, with and without the tail split
+static void check_units(int count, int num_tiles, int tiles_per_cta, int whole, int parts, int tail_tpc) {
+  std::vector<int> covered((size_t)count * num_tiles, 0);
+  long long ctas = 0;
+  auto take = [&](int bx, int by) {
+    int inst, t0, t1;
+    p3cs::run_unit_decode(bx, by, num_tiles, tiles_per_cta, whole, parts, tail_tpc, &inst, &t0, &t1);
+    CHECK(inst >= 0 && inst < count, "unit (%d,%d): instance %d of %d", bx, by, inst, count);
+    for (int t = t0; t < t1; ++t) ++covered[(size_t)inst * num_tiles + t];
+    ++ctas;
+  };
+  if (whole >= 0) {
+    for (int u = 0; u < whole + (count - whole) * parts; ++u) take(u, 0);
+  } else {
+    const int cpi = (num_tiles + tiles_per_cta - 1) / tiles_per_cta;
+    for (int y = 0; y < count; ++y)
+      for (int x = 0; x < cpi; ++x) take(x, y);
+  }
+  for (size_t i = 0; i < covered.size(); ++i) CHECK(covered[i] == 1, "instance %zu tile %zu covered %d times", i / num_tiles, i % num_tiles, covered[i]);
+  printf("ok units: %d instances x %d tiles, whole %d, parts %d x %d tiles: %lld CTAs\n", count, num_tiles, whole, parts, tail_tpc, ctas);
+}
+
 int main() {
   std::mt19937 rng(20261020);
   check_matching(rng);
+  check_units(1250, 17, 17, 806, 2, 9);
+  check_units(10000, 17, 17, 9556, 2, 9);
+  check_units(900, 5, 5, 456, 3, 2);
+  check_units(444, 4, 4, 0, 4, 1);
+  check_units(37, 17, 6, -1, 0, 0);
+  check_units(3, 391, 1, -1, 0, 0);
   for (int two = 0; two < 2; ++two) {
     check_plan(rng, 20000, 128, 4096, 1, false, 1248, 12, two, 4);
     check_plan(rng, 20000, 128, 4096, 0, false, 1120, 12, two, 4);
